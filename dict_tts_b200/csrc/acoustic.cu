@@ -1,0 +1,525 @@
+// Acoustic model behind the C ABI: S2PA text encoder, duration predictor, length regulator, FVAE decoder with its
+// residual-coupling prior flow.  Mirrors PortaSpeech_dict.forward(infer=True) (modules/dict_tts/model.py:36-122).
+#include "engine.cuh"
+
+using namespace dtts;
+
+namespace {
+
+struct EncLayerW {
+  ConvW qkv, o, ffn1, ffn2;
+  const float *g1, *b1, *g2, *b2;
+};
+struct EncoderW {
+  std::vector<EncLayerW> layers;
+  const float *last_g, *last_b;
+};
+struct WNW {
+  ConvW cond;
+  std::vector<ConvW> in_layers, res_skip;
+};
+struct FlowW {
+  ConvW pre, post;
+  WNW wn;
+  int odd;     // 1: the latent is logically channel-flipped while this coupling layer runs
+};
+
+}  // namespace
+
+struct dtts_acoustic {
+  dtts_acoustic_desc d;
+  WeightTable tab;
+  Pool pool;
+  const float* word_emb;
+  const float* pinyin_emb;
+  EncoderW sem, lin;
+  ConvW s2pa_q, s2pa_kT, s2pa_v, s2pa_o;
+  std::vector<ConvW> dur_conv;
+  std::vector<const float*> dur_ln_g, dur_ln_b;
+  const float *dur_w, *dur_b;
+  ConvW g_pre, dec_pre, dec_out;
+  std::vector<FlowW> flows;   // in reference order (flows.0, .2, .4, .6)
+  WNW dec_wn;
+  uint64_t launches = 0;
+};
+
+namespace {
+
+// conv weight [C_out][C_in][K] (+ optional bias) -> packed
+int pack(dtts_acoustic* h, const std::string& name, int C_out, int C_in, int K, bool has_bias, ConvW* cw,
+         cudaStream_t s, int rci = 0, int rco = 0, const char* wsuffix = ".weight") {
+  const float* w = h->tab.get(name + wsuffix, (uint64_t)C_out * C_in * K);
+  if (!w) return DTTS_ERR_MISSING_WEIGHT;
+  const float* b = nullptr;
+  if (has_bias) {
+    b = h->tab.get(name + ".bias", C_out);
+    if (!b) return DTTS_ERR_MISSING_WEIGHT;
+    if (rco) {
+      float* rb = h->pool.take(C_out);
+      if (!rb) return fail(DTTS_ERR_CUDA, "weight pool exhausted");
+      DTTS_CUDA(reverse_vec(b, rb, C_out, s));
+      b = rb;
+    }
+  }
+  float* dst = h->pool.take((size_t)C_out * C_in * K);
+  if (!dst) return fail(DTTS_ERR_CUDA, "weight pool exhausted");
+  DTTS_CUDA(repack_conv(w, dst, C_out, C_in, K, rci, rco, s));
+  cw->w = dst; cw->bias = b; cw->C_out = C_out; cw->C_in = C_in; cw->ktaps = K; cw->phases = 1;
+  return DTTS_OK;
+}
+
+int pack_encoder(dtts_acoustic* h, const std::string& p, EncoderW* e, cudaStream_t s) {
+  const int H = h->d.hidden, F = h->d.ffn_filter, K = h->d.ffn_kernel;
+  for (int i = 0; i < h->d.enc_layers; ++i) {
+    EncLayerW L;
+    const std::string a = p + ".attn_layers." + std::to_string(i);
+    // q, k, v projections packed side by side: one [H][1][3H] weight, one launch
+    float* wqkv = h->pool.take((size_t)3 * H * H);
+    float* bqkv = h->pool.take((size_t)3 * H);
+    float* tmp = h->pool.take((size_t)H * H);
+    if (!wqkv || !bqkv || !tmp) return fail(DTTS_ERR_CUDA, "weight pool exhausted");
+    const char* names[3] = {".conv_q", ".conv_k", ".conv_v"};
+    for (int j = 0; j < 3; ++j) {
+      const float* w = h->tab.get(a + names[j] + ".weight", (uint64_t)H * H);
+      const float* b = h->tab.get(a + names[j] + ".bias", H);
+      if (!w || !b) return DTTS_ERR_MISSING_WEIGHT;
+      DTTS_CUDA(repack_conv(w, tmp, H, H, 1, 0, 0, s));                    // [ci][co]
+      DTTS_CUDA(cudaMemcpy2DAsync(wqkv + j * H, 3 * H * sizeof(float), tmp, H * sizeof(float), H * sizeof(float), H,
+                                  cudaMemcpyDeviceToDevice, s));
+      DTTS_CUDA(cudaMemcpyAsync(bqkv + j * H, b, H * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    L.qkv.w = wqkv; L.qkv.bias = bqkv; L.qkv.C_out = 3 * H; L.qkv.C_in = H; L.qkv.ktaps = 1; L.qkv.phases = 1;
+    DTTS_TRY(pack(h, a + ".conv_o", H, H, 1, true, &L.o, s));
+    const std::string f = p + ".ffn_layers." + std::to_string(i);
+    DTTS_TRY(pack(h, f + ".conv_1", F, H, K, true, &L.ffn1, s));
+    DTTS_TRY(pack(h, f + ".conv_2", H, F, 1, true, &L.ffn2, s));
+    L.g1 = h->tab.get(p + ".norm_layers_1." + std::to_string(i) + ".gamma", H);
+    L.b1 = h->tab.get(p + ".norm_layers_1." + std::to_string(i) + ".beta", H);
+    L.g2 = h->tab.get(p + ".norm_layers_2." + std::to_string(i) + ".gamma", H);
+    L.b2 = h->tab.get(p + ".norm_layers_2." + std::to_string(i) + ".beta", H);
+    if (!L.g1 || !L.b1 || !L.g2 || !L.b2) return DTTS_ERR_MISSING_WEIGHT;
+    e->layers.push_back(L);
+  }
+  e->last_g = h->tab.get(p + ".last_ln.gamma", H);
+  e->last_b = h->tab.get(p + ".last_ln.beta", H);
+  if (!e->last_g || !e->last_b) return DTTS_ERR_MISSING_WEIGHT;
+  return DTTS_OK;
+}
+
+int pack_wn(dtts_acoustic* h, const std::string& p, int hidden, int n_layers, int K, int gin, WNW* wn,
+            cudaStream_t s) {
+  DTTS_TRY(pack(h, p + ".cond_layer", 2 * hidden * n_layers, gin, 1, true, &wn->cond, s));
+  for (int i = 0; i < n_layers; ++i) {
+    ConvW a, r;
+    DTTS_TRY(pack(h, p + ".in_layers." + std::to_string(i), 2 * hidden, hidden, K, true, &a, s));
+    const int rs = (i < n_layers - 1) ? 2 * hidden : hidden;
+    DTTS_TRY(pack(h, p + ".res_skip_layers." + std::to_string(i), rs, hidden, 1, true, &r, s));
+    wn->in_layers.push_back(a);
+    wn->res_skip.push_back(r);
+  }
+  return DTTS_OK;
+}
+
+// Pre-LN transformer encoder (rel_transformer_encoder.py:55-79).  x is updated in place; the result is written to hbuf.
+void run_encoder(dtts_acoustic* h, const EncoderW& E, float* x, float* hbuf, float* qkv, float* att, float* ffn,
+                 const float* seq_mask, int B, int Tw, Launcher& L) {
+  const int H = h->d.hidden, F = h->d.ffn_filter, K = h->d.ffn_kernel;
+  cudaStream_t s = L.stream;
+  for (size_t i = 0; i < E.layers.size(); ++i) {
+    const EncLayerW& W = E.layers[i];
+    L(apply_mask(x, seq_mask, B, H, Tw, s));
+    L(channel_layernorm(x, hbuf, W.g1, W.b1, 1e-4f, nullptr, nullptr, B, H, Tw, s));
+    L(launch_conv1d_f32(conv_params(hbuf, Tw, W.qkv, 0, 3 * H, qkv, Tw, 1, 1, 0), B, s));
+    L(self_attention(qkv, qkv + (size_t)H * Tw, qkv + (size_t)2 * H * Tw, seq_mask, att, B, H, Tw, h->d.n_heads, s));
+    {
+      ConvParams p = conv_params(att, Tw, W.o, 0, H, x, Tw, 1, 1, 0);
+      p.res = x; p.r_bs = (long)H * Tw; p.r_cs = Tw; p.r_ts = 1;
+      L(launch_conv1d_f32(p, B, s));
+    }
+    L(channel_layernorm(x, hbuf, W.g2, W.b2, 1e-4f, nullptr, seq_mask, B, H, Tw, s));   // FFN input is x * x_mask
+    {
+      ConvParams p = conv_params(hbuf, Tw, W.ffn1, 0, F, ffn, Tw, 1, 1, K / 2);
+      p.act = ACT_RELU; p.mask = seq_mask; p.m_bs = Tw;
+      L(launch_conv1d_f32(p, B, s));
+    }
+    {
+      ConvParams p = conv_params(ffn, Tw, W.ffn2, 0, H, x, Tw, 1, 1, 0);
+      p.mask = seq_mask; p.m_bs = Tw;
+      p.res = x; p.r_bs = (long)H * Tw; p.r_cs = Tw; p.r_ts = 1;
+      L(launch_conv1d_f32(p, B, s));
+    }
+  }
+  L(channel_layernorm(x, hbuf, E.last_g, E.last_b, 1e-4f, nullptr, seq_mask, B, H, Tw, s));
+}
+
+// WN.forward with x_mask = 1 (modules/commons/wavenet.py:54-78).  hx [B,hidden,T] is updated in place,
+// skip [B,hidden,T] receives the output.
+void run_wn(const WNW& W, int hidden, int K, float* hx, const float* g, int gin, float* cond, float* a, float* acts,
+            float* skip, int B, int T, Launcher& L) {
+  cudaStream_t s = L.stream;
+  const int n = (int)W.in_layers.size();
+  (void)gin;
+  L(launch_conv1d_f32(conv_params(g, T, W.cond, 0, W.cond.C_out, cond, T, 1, 1, 0), B, s));
+  for (int i = 0; i < n; ++i) {
+    {
+      ConvParams p = conv_params(hx, T, W.in_layers[i], 0, 2 * hidden, a, T, 1, 1, K / 2);
+      p.res = cond + (size_t)2 * hidden * i * T; p.r_bs = (long)W.cond.C_out * T; p.r_cs = T; p.r_ts = 1;
+      L(launch_conv1d_f32(p, B, s));
+    }
+    L(wn_gate(a, acts, B, hidden, T, s));
+    if (i < n - 1) {
+      ConvParams p = conv_params(acts, T, W.res_skip[i], 0, hidden, hx, T, 1, 1, 0);          // x = x + rs[:hidden]
+      p.res = hx; p.r_bs = (long)hidden * T; p.r_cs = T; p.r_ts = 1;
+      L(launch_conv1d_f32(p, B, s));
+      ConvParams q = conv_params(acts, T, W.res_skip[i], hidden, hidden, skip, T, 1, 1, 0);    // out += rs[hidden:]
+      q.accumulate = (i > 0);
+      L(launch_conv1d_f32(q, B, s));
+    } else {
+      ConvParams q = conv_params(acts, T, W.res_skip[i], 0, hidden, skip, T, 1, 1, 0);
+      q.accumulate = (i > 0);
+      L(launch_conv1d_f32(q, B, s));
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int dtts_acoustic_create(const dtts_acoustic_desc* d, const float* arena_dev, uint64_t arena_floats,
+                                    const dtts_weight_entry* table, int32_t n_entries, void* stream,
+                                    dtts_acoustic** out) {
+  if (!d || !out) return fail(DTTS_ERR_BAD_ARG, "null descriptor/out");
+  *out = nullptr;
+  if (d->hidden <= 0 || d->hidden > 256 || d->hidden % d->n_heads || d->dict_dim % 4 || d->latent % 2 ||
+      d->frames_multiple != 4)
+    return fail(DTTS_ERR_BAD_SHAPE, "unsupported acoustic configuration");
+  DTTS_TRY(arch_check());
+  dtts_acoustic* h = new dtts_acoustic();
+  h->d = *d;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = h->tab.init(arena_dev, arena_floats, table, n_entries);
+  if (rc != DTTS_OK) { delete h; return rc; }
+  size_t total = 0;
+  for (auto& e : h->tab.entries) total += e.second.second + 64;
+  rc = h->pool.reserve(total + 2 * 1024 * 1024);
+  if (rc != DTTS_OK) { delete h; return rc; }
+  auto build = [&]() -> int {
+    const int H = d->hidden, D = d->dict_dim;
+    const std::string p = "dict_encoder.S2PA_module";
+    h->word_emb = h->tab.get(p + ".word_emb.weight", (uint64_t)d->word_size * H);
+    h->pinyin_emb = h->tab.get(p + ".s2pa_attention.pinyin_embedding.weight", (uint64_t)d->pinyin_size * H);
+    if (!h->word_emb || !h->pinyin_emb) return DTTS_ERR_MISSING_WEIGHT;
+    DTTS_TRY(pack_encoder(h, p + ".semantic_encoder", &h->sem, s));
+    DTTS_TRY(pack_encoder(h, p + ".linguistic_encoder", &h->lin, s));
+    const std::string a = p + ".s2pa_attention";
+    DTTS_TRY(pack(h, a + ".q_transform", H, H, 1, false, &h->s2pa_q, s));
+    DTTS_TRY(pack(h, a + ".v_transform", H, D, 1, false, &h->s2pa_v, s));
+    DTTS_TRY(pack(h, a + ".output_transform", H, H, 1, false, &h->s2pa_o, s));
+    {
+      // k_transform.weight is [H][D]; the folded form needs W_k^T as a 1x1 conv H -> D, packed [ci=H][D] = as stored.
+      const float* wk = h->tab.get(a + ".k_transform.weight", (uint64_t)H * D);
+      if (!wk) return DTTS_ERR_MISSING_WEIGHT;
+      h->s2pa_kT.w = wk; h->s2pa_kT.bias = nullptr; h->s2pa_kT.C_out = D; h->s2pa_kT.C_in = H; h->s2pa_kT.ktaps = 1;
+    }
+    for (int i = 0; i < d->dur_layers; ++i) {
+      ConvW c;
+      const std::string q = "dur_predictor.conv." + std::to_string(i);
+      DTTS_TRY(pack(h, q + ".1", d->dur_chans, i == 0 ? H : d->dur_chans, d->dur_kernel, true, &c, s));
+      h->dur_conv.push_back(c);
+      const float* g = h->tab.get(q + ".3.weight", d->dur_chans);
+      const float* b = h->tab.get(q + ".3.bias", d->dur_chans);
+      if (!g || !b) return DTTS_ERR_MISSING_WEIGHT;
+      h->dur_ln_g.push_back(g);
+      h->dur_ln_b.push_back(b);
+    }
+    h->dur_w = h->tab.get("dur_predictor.linear.0.weight", d->dur_chans);
+    h->dur_b = h->tab.get("dur_predictor.linear.0.bias", 1);
+    if (!h->dur_w || !h->dur_b) return DTTS_ERR_MISSING_WEIGHT;
+    DTTS_TRY(pack(h, "fvae.g_pre_net.0", H, H, 8, true, &h->g_pre, s));
+    const int half = d->latent / 2;
+    for (int f = 0; f < d->flow_blocks; ++f) {
+      FlowW F;
+      // reversed(flows) = Flip, RCL_{n-1}, Flip, RCL_{n-2}, ...: RCL_f runs after (n - f) flips.
+      F.odd = ((d->flow_blocks - f) & 1);
+      const std::string q = "fvae.prior_flow.flows." + std::to_string(2 * f);
+      DTTS_TRY(pack(h, q + ".pre", d->flow_hidden, half, 1, true, &F.pre, s, F.odd, 0));
+      DTTS_TRY(pack(h, q + ".post", half, d->flow_hidden, 1, true, &F.post, s, 0, F.odd));
+      DTTS_TRY(pack_wn(h, q + ".enc", d->flow_hidden, d->flow_layers, d->flow_kernel, H, &F.wn, s));
+      h->flows.push_back(F);
+    }
+    {
+      // ConvTranspose1d(latent -> H, k=4, s=4): weight [latent][H][4]
+      const float* w = h->tab.get("fvae.decoder.pre_net.0.weight", (uint64_t)d->latent * H * 4);
+      const float* b = h->tab.get("fvae.decoder.pre_net.0.bias", H);
+      if (!w || !b) return DTTS_ERR_MISSING_WEIGHT;
+      float* dst = h->pool.take((size_t)d->latent * H * 4);
+      if (!dst) return fail(DTTS_ERR_CUDA, "weight pool exhausted");
+      DTTS_CUDA(repack_convT(w, dst, d->latent, H, 4, 4, s));
+      h->dec_pre.w = dst; h->dec_pre.bias = b; h->dec_pre.C_out = H; h->dec_pre.C_in = d->latent;
+      h->dec_pre.ktaps = 1; h->dec_pre.phases = 4;
+    }
+    DTTS_TRY(pack_wn(h, "fvae.decoder.wn", H, d->dec_layers, d->dec_kernel, H, &h->dec_wn, s));
+    DTTS_TRY(pack(h, "fvae.decoder.out_proj", d->n_mel, H, 1, true, &h->dec_out, s));
+    return DTTS_OK;
+  };
+  rc = build();
+  if (rc == DTTS_OK) {
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) rc = fail(DTTS_ERR_CUDA, std::string("acoustic create: ") + cudaGetErrorString(e));
+  }
+  if (rc != DTTS_OK) {
+    h->pool.release();
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return DTTS_OK;
+}
+
+extern "C" int dtts_acoustic_destroy(dtts_acoustic* h) {
+  if (!h) return DTTS_OK;
+  h->pool.release();
+  delete h;
+  return DTTS_OK;
+}
+
+extern "C" uint64_t dtts_acoustic_launch_count(const dtts_acoustic* h) { return h ? h->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" uint64_t dtts_text_workspace_bytes(const dtts_acoustic* h, int32_t B, int32_t Tw, int32_t Lk, int32_t Lp) {
+  if (!h || B <= 0 || Tw <= 0 || Lk <= 0 || Lp <= 0) return 0;
+  const size_t H = h->d.hidden, F = h->d.ffn_filter, D = h->d.dict_dim, C = h->d.dur_chans;
+  const size_t bt = (size_t)B * Tw;
+  size_t n = 0;
+  auto add = [&](size_t floats) { n += ws_round(floats * sizeof(float)); };
+  add(bt * H); add(bt * H); add(bt * 3 * H); add(bt * H); add(bt * F);        // x, h, qkv, att, ffn
+  add(bt); add(bt); add(bt); add(B); add(64);                                  // masks, lens, maxes
+  add(bt * H); add(bt * D); add(bt * Lk); add(bt * D); add(bt * H); add(bt * H);  // q, qk, weights, ctx, ctxv, context
+  add(bt * H); add(bt * C); add(bt * C);                                        // dur_in, d1, d2
+  return n + 4096;
+}
+
+extern "C" int dtts_text_encode(dtts_acoustic* h, const dtts_text_in* in, const dtts_text_out* out, void* ws,
+                                uint64_t ws_bytes, void* stream) {
+  if (!h || !in || !out || !ws) return fail(DTTS_ERR_BAD_ARG, "dtts_text_encode: null argument");
+  const int B = in->B, Tw = in->Tw, Lk = in->Lk, Lp = in->Lp;
+  if (B <= 0 || Tw <= 0 || Lk <= 0 || Lp <= 0) return fail(DTTS_ERR_BAD_SHAPE, "dtts_text_encode: empty shape");
+  if (!in->word_tokens_dev || !in->keys_dev || !in->values_dev || !in->key_map_dev || !in->pinyin_dev ||
+      !in->pinyin_map_dev || !out->word_encoder_out_dev || !out->dict_attn_dev || !out->pron_attn_dev ||
+      !out->dur_dev || !out->dur_int_dev || !out->ilens_dev)
+    return fail(DTTS_ERR_BAD_ARG, "dtts_text_encode: null tensor");
+  if (((uintptr_t)in->keys_dev & 15) || ((uintptr_t)in->values_dev & 15))
+    return fail(DTTS_ERR_ALIGNMENT, "dtts_text_encode: keys/values must be 16-byte aligned");
+  if (ws_bytes < dtts_text_workspace_bytes(h, B, Tw, Lk, Lp))
+    return fail(DTTS_ERR_WORKSPACE_TOO_SMALL, "dtts_text_encode: workspace too small");
+  const dtts_acoustic_desc& d = h->d;
+  const int H = d.hidden, F = d.ffn_filter, D = d.dict_dim, C = d.dur_chans;
+  const size_t bt = (size_t)B * Tw;
+  Bump bump(ws, ws_bytes);
+  float* x = bump.take<float>(bt * H);
+  float* hb = bump.take<float>(bt * H);
+  float* qkv = bump.take<float>(bt * 3 * H);
+  float* att = bump.take<float>(bt * H);
+  float* ffn = bump.take<float>(bt * F);
+  float* seq_mask = bump.take<float>(bt);
+  float* tok_mask = bump.take<float>(bt);
+  float* keep = bump.take<float>(bt);
+  int* lens = bump.take<int>(B);
+  int* maxes = bump.take<int>(64);
+  float* q = bump.take<float>(bt * H);
+  float* qk = bump.take<float>(bt * D);
+  float* weights = bump.take<float>(bt * Lk);
+  float* ctx = bump.take<float>(bt * D);
+  float* ctxv = bump.take<float>(bt * H);
+  float* context = bump.take<float>(bt * H);
+  float* dur_in = bump.take<float>(bt * H);
+  float* d1 = bump.take<float>(bt * C);
+  float* d2 = bump.take<float>(bt * C);
+  if (!bump.ok) return fail(DTTS_ERR_WORKSPACE_TOO_SMALL, "dtts_text_encode: workspace too small");
+  Launcher L;
+  L.stream = (cudaStream_t)stream;
+  L.counter = &h->launches;
+  cudaStream_t s = L.stream;
+
+  // word embedding * sqrt(H), masks (dict_encoder.py:131-136)
+  L(embed_tokens(in->word_tokens_dev, h->word_emb, sqrtf((float)H), B, Tw, H, d.word_size, x, seq_mask, tok_mask, lens,
+                 s));
+  run_encoder(h, h->sem, x, hb, qkv, att, ffn, seq_mask, B, Tw, L);           // semantic encoder -> hb
+  // S2PA (dict_encoder.py:32-66), folded: logits = keys . (W_k^T (W_q x) * D^-1/2)
+  L(launch_conv1d_f32(conv_params(hb, Tw, h->s2pa_q, 0, H, q, Tw, 1, 1, 0), B, s));
+  {
+    ConvParams p = conv_params(q, Tw, h->s2pa_kT, 0, D, qk, Tw, 1, 1, 0);
+    p.alpha = 1.f / sqrtf((float)D);
+    L(launch_conv1d_f32(p, B, s));
+  }
+  L(s2pa_stream(in->keys_dev, in->values_dev, in->key_map_dev, qk, B, Tw, Lk, D, weights, out->dict_attn_dev, ctx, s));
+  L(launch_conv1d_f32(conv_params(ctx, Tw, h->s2pa_v, 0, H, ctxv, Tw, 1, 1, 0), B, s));
+  L(launch_conv1d_f32(conv_params(ctxv, Tw, h->s2pa_o, 0, H, context, Tw, 1, 1, 0), B, s));
+  L(dict_maxes(in->key_map_dev, bt * Lk, in->pinyin_map_dev, bt * Lp, maxes, s));
+  // x2 = context * x_mask + pron   (written into x, the input of the linguistic encoder)
+  L(s2pa_pron(weights, in->key_map_dev, in->pinyin_dev, in->pinyin_map_dev, in->pron_modified_dev, maxes,
+              h->pinyin_emb, d.pinyin_size, context, seq_mask, B, Tw, Lk, Lp, H, d.language_zh, out->pron_attn_dev, x,
+              s));
+  run_encoder(h, h->lin, x, hb, qkv, att, ffn, seq_mask, B, Tw, L);           // linguistic encoder -> hb
+  // word_encoder_out = x^T * (tokens > 0); dur_input; src_padding  (dict_encoder.py:168-170, model.py:94-96,73)
+  L(finish_text(hb, tok_mask, B, Tw, H, out->word_encoder_out_dev, dur_in, keep, s));
+  L(count_keep(keep, B, Tw, out->ilens_dev, s));
+  // duration predictor (portaspeech/model.py:58-66)
+  const float* cur = dur_in;
+  float* bufs[2] = {d1, d2};
+  for (int i = 0; i < d.dur_layers; ++i) {
+    float* c = bufs[0];
+    float* y = bufs[1];
+    ConvParams p = conv_params(cur, Tw, h->dur_conv[i], 0, C, c, Tw, 1, 1, (d.dur_kernel - 1) / 2);
+    p.act = ACT_RELU;
+    L(launch_conv1d_f32(p, B, s));
+    L(channel_layernorm(c, y, h->dur_ln_g[i], h->dur_ln_b[i], 1e-5f, nullptr, keep, B, C, Tw, s));
+    cur = y;
+    bufs[0] = c;      // conv output buffer can be reused: next conv reads y, writes c
+  }
+  L(dur_head(cur, h->dur_w, h->dur_b, keep, B, C, Tw, out->dur_dev, out->dur_int_dev, s));
+  if (L.err != cudaSuccess) return fail(DTTS_ERR_CUDA, std::string("dtts_text_encode: ") + cudaGetErrorString(L.err));
+  return DTTS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int dtts_length_regulate_scan(dtts_acoustic* h, const int64_t* dur_int, const int64_t* ilens, int32_t B,
+                                         int32_t Tw, int32_t* cum, int32_t* totals, int32_t* t_raw_host,
+                                         void* stream) {
+  if (!h || !dur_int || !ilens || !cum || !totals || !t_raw_host)
+    return fail(DTTS_ERR_BAD_ARG, "dtts_length_regulate_scan: null argument");
+  if (B <= 0 || Tw <= 0) return fail(DTTS_ERR_BAD_SHAPE, "dtts_length_regulate_scan: empty shape");
+  cudaStream_t s = (cudaStream_t)stream;
+  // totals has B+1 entries: the last one receives the batch maximum
+  DTTS_CUDA(cudaMemsetAsync(totals + B, 0, sizeof(int32_t), s));
+  DTTS_CUDA(lr_scan(dur_int, ilens, B, Tw, cum, totals, totals + B, s));
+  h->launches++;
+  DTTS_CUDA(cudaMemcpyAsync(t_raw_host, totals + B, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  DTTS_CUDA(cudaStreamSynchronize(s));
+  return DTTS_OK;
+}
+
+extern "C" int dtts_length_regulate_fill(dtts_acoustic* h, const int32_t* cum, const int64_t* ilens, int32_t B,
+                                         int32_t Tw, int32_t t_raw, int32_t T, int64_t* mel2word, void* stream) {
+  if (!h || !cum || !ilens || !mel2word) return fail(DTTS_ERR_BAD_ARG, "dtts_length_regulate_fill: null argument");
+  if (B <= 0 || Tw <= 0 || T <= 0 || t_raw <= 0 || t_raw > T)
+    return fail(DTTS_ERR_BAD_SHAPE, "dtts_length_regulate_fill: need 0 < t_raw <= T");
+  DTTS_CUDA(lr_fill(cum, ilens, B, Tw, t_raw, T, mel2word, (cudaStream_t)stream));
+  h->launches++;
+  return DTTS_OK;
+}
+
+extern "C" int dtts_expand(dtts_acoustic* h, const float* enc, const int64_t* mel2word, int32_t B, int32_t Tw,
+                           int32_t T, float* decoder_inp, float* g_bct, float* x_mask, void* stream) {
+  if (!h || !enc || !mel2word || !decoder_inp || !g_bct || !x_mask)
+    return fail(DTTS_ERR_BAD_ARG, "dtts_expand: null argument");
+  if (B <= 0 || Tw <= 0 || T <= 0) return fail(DTTS_ERR_BAD_SHAPE, "dtts_expand: empty shape");
+  DTTS_CUDA(lr_gather(enc, mel2word, B, Tw, T, h->d.hidden, decoder_inp, g_bct, x_mask, (cudaStream_t)stream));
+  h->launches++;
+  return DTTS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" uint64_t dtts_decode_workspace_bytes(const dtts_acoustic* h, int32_t B, int32_t T) {
+  if (!h || B <= 0 || T <= 0) return 0;
+  const size_t H = h->d.hidden, FH = h->d.flow_hidden, T4 = T / 4;
+  size_t n = 0;
+  auto add = [&](size_t floats) { n += ws_round(floats * sizeof(float)); };
+  add(B * H * T4);                                     // g_sqz
+  add(B * 2 * FH * h->d.flow_layers * T4);             // flow cond
+  add(B * FH * T4); add(B * 2 * FH * T4); add(B * FH * T4); add(B * FH * T4);   // h, a, acts, skip
+  add(B * H * T);                                      // x
+  add(B * 2 * H * h->d.dec_layers * T);                // cond
+  add(B * 2 * H * T); add(B * H * T); add(B * H * T);  // a, acts, skip
+  return n + 4096;
+}
+
+extern "C" int dtts_decode_mel(dtts_acoustic* h, const float* g, const float* z_in, int32_t B, int32_t T, float* mel,
+                               float* z_p, void* ws, uint64_t ws_bytes, void* stream) {
+  if (!h || !g || !z_in || !mel || !z_p || !ws) return fail(DTTS_ERR_BAD_ARG, "dtts_decode_mel: null argument");
+  if (B <= 0 || T <= 0 || T % h->d.frames_multiple)
+    return fail(DTTS_ERR_BAD_SHAPE, "dtts_decode_mel: T must be a positive multiple of frames_multiple");
+  if (ws_bytes < dtts_decode_workspace_bytes(h, B, T))
+    return fail(DTTS_ERR_WORKSPACE_TOO_SMALL, "dtts_decode_mel: workspace too small");
+  const dtts_acoustic_desc& d = h->d;
+  const int H = d.hidden, FH = d.flow_hidden, T4 = T / 4, half = d.latent / 2;
+  Bump bump(ws, ws_bytes);
+  float* g_sqz = bump.take<float>((size_t)B * H * T4);
+  float* fcond = bump.take<float>((size_t)B * 2 * FH * d.flow_layers * T4);
+  float* fh = bump.take<float>((size_t)B * FH * T4);
+  float* fa = bump.take<float>((size_t)B * 2 * FH * T4);
+  float* facts = bump.take<float>((size_t)B * FH * T4);
+  float* fskip = bump.take<float>((size_t)B * FH * T4);
+  float* x = bump.take<float>((size_t)B * H * T);
+  float* cond = bump.take<float>((size_t)B * 2 * H * d.dec_layers * T);
+  float* a = bump.take<float>((size_t)B * 2 * H * T);
+  float* acts = bump.take<float>((size_t)B * H * T);
+  float* skip = bump.take<float>((size_t)B * H * T);
+  if (!bump.ok) return fail(DTTS_ERR_WORKSPACE_TOO_SMALL, "dtts_decode_mel: workspace too small");
+  Launcher L;
+  L.stream = (cudaStream_t)stream;
+  L.counter = &h->launches;
+  cudaStream_t s = L.stream;
+
+  // g_sqz = Conv1d(H,H,k=8,s=4,p=2)(g)  (fvae_semantics.py:93-94; semantics == 0)
+  L(launch_conv1d_f32(conv_params(g, T, h->g_pre, 0, H, g_sqz, T4, 1, 4, 2), B, s));
+  // prior flow, reverse (glow_modules.py:108-128,157-163).  The channel Flip is folded into the pre/post weights:
+  // on "odd" layers the conditioning half is physical channels [half, 2*half) and the updated half is [0, half).
+  L(copy_f32(z_in, z_p, (size_t)B * d.latent * T4, s));
+  for (int f = d.flow_blocks - 1; f >= 0; --f) {
+    const FlowW& F = h->flows[f];
+    const int c_x0 = F.odd ? half : 0, c_x1 = F.odd ? 0 : half;
+    {
+      ConvParams p = conv_params(z_p + (size_t)c_x0 * T4, T4, F.pre, 0, FH, fh, T4, 1, 1, 0);
+      p.x_bs = (long)d.latent * T4;
+      L(launch_conv1d_f32(p, B, s));
+    }
+    run_wn(F.wn, FH, d.flow_kernel, fh, g_sqz, H, fcond, fa, facts, fskip, B, T4, L);
+    {
+      // x1 = x1 - m   (mean_only, logs = 0)
+      float* x1 = z_p + (size_t)c_x1 * T4;
+      ConvParams p = conv_params(fskip, T4, F.post, 0, half, x1, T4, 1, 1, 0);
+      p.o_bs = (long)d.latent * T4;
+      p.alpha = -1.f;
+      p.res = x1; p.r_bs = (long)d.latent * T4; p.r_cs = T4; p.r_ts = 1;
+      L(launch_conv1d_f32(p, B, s));
+    }
+  }
+  // decoder (fvae_semantics.py:53-58)
+  L(launch_conv1d_f32(convT_params(z_p, T4, h->dec_pre, x, T, 4, 0), B, s));
+  run_wn(h->dec_wn, H, d.dec_kernel, x, g, H, cond, a, acts, skip, B, T, L);
+  {
+    ConvParams p = conv_params(skip, T, h->dec_out, 0, d.n_mel, mel, T, 1, 1, 0);
+    p.o_bs = (long)T * d.n_mel; p.o_cs = 1; p.o_ts = d.n_mel;                 // mel_out is [B,T,80]
+    L(launch_conv1d_f32(p, B, s));
+  }
+  if (L.err != cudaSuccess) return fail(DTTS_ERR_CUDA, std::string("dtts_decode_mel: ") + cudaGetErrorString(L.err));
+  return DTTS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int dtts_debug_conv1d(const float* x, const float* w, const float* bias, float* out, int32_t B, int32_t C_in,
+                                 int32_t T_in, int32_t C_out, int32_t K, int32_t stride, int32_t padding,
+                                 int32_t dilation, int32_t transposed, float pre_slope, float* scratch_w,
+                                 void* stream) {
+  if (!x || !w || !out || !scratch_w) return fail(DTTS_ERR_BAD_ARG, "dtts_debug_conv1d: null argument");
+  DTTS_TRY(arch_check());
+  cudaStream_t s = (cudaStream_t)stream;
+  ConvW cw;
+  cw.bias = bias; cw.C_out = C_out; cw.C_in = C_in;
+  ConvParams p;
+  if (transposed) {
+    if (K % stride) return fail(DTTS_ERR_BAD_SHAPE, "transposed conv needs K % stride == 0");
+    DTTS_CUDA(repack_convT(w, scratch_w, C_in, C_out, K, stride, s));
+    cw.w = scratch_w; cw.ktaps = K / stride; cw.phases = stride;
+    const int T_out = (T_in - 1) * stride - 2 * padding + K;
+    p = convT_params(x, T_in, cw, out, T_out, stride, padding);
+  } else {
+    DTTS_CUDA(repack_conv(w, scratch_w, C_out, C_in, K, 0, 0, s));
+    cw.w = scratch_w; cw.ktaps = K; cw.phases = 1;
+    const int T_out = (T_in + 2 * padding - dilation * (K - 1) - 1) / stride + 1;
+    p = conv_params(x, T_in, cw, 0, C_out, out, T_out, dilation, stride, padding);
+  }
+  p.pre_slope = pre_slope;
+  DTTS_CUDA(launch_conv1d_f32(p, B, s));
+  return DTTS_OK;
+}

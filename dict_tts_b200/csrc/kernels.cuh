@@ -1,0 +1,69 @@
+// Launchers of the non-convolution kernels of the Dict-TTS path (definitions in text_kernels.cu, lr_kernels.cu,
+// repack.cu).  All activations inside the engine are fp32, channels-first [B, C, T] unless stated.
+#pragma once
+#include "common.cuh"
+
+namespace dtts {
+
+// ---- weight repack (create time) ----
+// Conv1d weight [C_out][C_in][K] -> [C_in][K][C_out]; reverse_ci / reverse_co implement the folded glow Flip.
+cudaError_t repack_conv(const float* w, float* out, int C_out, int C_in, int K, int reverse_ci, int reverse_co,
+                        cudaStream_t s);
+// ConvTranspose1d weight [C_in][C_out][K], stride S -> [S phases][C_in][K/S][C_out], Wp[ph][ci][m][co] = W[ci][co][m*S+ph]
+cudaError_t repack_convT(const float* w, float* out, int C_in, int C_out, int K, int S, cudaStream_t s);
+// Linear weight used transposed: in [R][C] -> out [C][R] (i.e. treat W^T as a 1x1 conv weight and pack it)
+cudaError_t transpose2d(const float* in, float* out, int R, int C, cudaStream_t s);
+cudaError_t reverse_vec(const float* in, float* out, int n, cudaStream_t s);
+cudaError_t fill_f32(float* p, float v, size_t n, cudaStream_t s);
+
+// ---- text encoder ----
+// x[b,c,t] = emb[tok[b,t]][c]*scale ; lens[b] = #(tok>0) ; seq_mask[b,t] = t < lens[b] ; tok_mask[b,t] = tok>0
+cudaError_t embed_tokens(const int64_t* tok, const float* emb, float scale, int B, int Tw, int H, int vocab,
+                         float* x, float* seq_mask, float* tok_mask, int* lens, cudaStream_t s);
+// y = LN_c(x * in_mask) * gamma + beta, then * out_mask   (masks may be null) ; layout [B,C,T]
+cudaError_t channel_layernorm(const float* x, float* y, const float* gamma, const float* beta, float eps,
+                              const float* in_mask, const float* out_mask, int B, int C, int T, cudaStream_t s);
+// x *= mask (in place), [B,C,T] with mask [B,T]
+cudaError_t apply_mask(float* x, const float* mask, int B, int C, int T, cudaStream_t s);
+// multi-head self attention on q,k,v [B,C,T] (C = heads*dk), mask [B,T]; out [B,C,T]
+cudaError_t self_attention(const float* q, const float* k, const float* v, const float* mask, float* out, int B,
+                           int C, int T, int heads, cudaStream_t s);
+// S2PA streaming pass. qk [B,D,Tw] (channels-first, already scaled). Writes weights [B,Tw,Lk], align [B,1,Lk,Tw],
+// ctx [B,D,Tw] = sum_l w*values.  key_map float [B,Tw,Lk].
+cudaError_t s2pa_stream(const float* keys, const float* values, const float* key_map, const float* qk, int B, int Tw,
+                        int Lk, int D, float* weights, float* align, float* ctx, cudaStream_t s);
+// global maxima of key_map (float, as int) and pinyin_map (int64) -> maxes[0], maxes[1]
+cudaError_t dict_maxes(const float* key_map, size_t n_key, const int64_t* pinyin_map, size_t n_pin, int* maxes,
+                       cudaStream_t s);
+// pronunciation mixing: pron_attn [B,Tw,Lp]; x2[b,h,t] = context[b,h,t]*seq_mask[b,t] + sum_p pron_w*pinyin_emb
+cudaError_t s2pa_pron(const float* weights, const float* key_map, const int64_t* pinyin, const int64_t* pinyin_map,
+                      const int64_t* pron_modified, const int* maxes, const float* pinyin_emb, int pinyin_vocab,
+                      const float* context, const float* seq_mask, int B, int Tw, int Lk, int Lp, int H,
+                      int apply_rule, float* pron_attn, float* x2, cudaStream_t s);
+// word_encoder_out[b,t,h] = x[b,h,t]*tok_mask ; dur_in[b,h,t] same (channels-first) ; keep[b,t] = (sum_h |.| != 0)
+cudaError_t finish_text(const float* x, const float* tok_mask, int B, int Tw, int H, float* enc_btc, float* dur_in,
+                        float* keep, cudaStream_t s);
+// ilens[b] = sum_t keep
+cudaError_t count_keep(const float* keep, int B, int Tw, int64_t* ilens, cudaStream_t s);
+// dur[b,t] = softplus(w . xs[b,:,t] + bias) * keep ; dur_int = clamp(rint(exp(dur)-1), 0)
+cudaError_t dur_head(const float* xs, const float* w, const float* bias, const float* keep, int B, int C, int Tw,
+                     float* dur, int64_t* dur_int, cudaStream_t s);
+
+// ---- length regulator ----
+// cum[b,w] inclusive prefix sum over the first ilens[b] durations (all-zero row -> durations 1); totals[b];
+// atomicMax into *t_max (must be zeroed by the caller)
+cudaError_t lr_scan(const int64_t* dur, const int64_t* ilens, int B, int Tw, int* cum, int* totals, int* t_max,
+                    cudaStream_t s);
+// mel2word[b,t] for t < T_raw from cum; columns [T_raw, T) repeat column T_raw-1
+cudaError_t lr_fill(const int* cum, const int64_t* ilens, int B, int Tw, int T_raw, int T, int64_t* mel2word,
+                    cudaStream_t s);
+// gather: out_btc[b,t,:] = enc[b, m-1, :] (0 if m==0) ; out_bct = transpose ; nonpad[b,t] = m>0
+cudaError_t lr_gather(const float* enc_btc, const int64_t* mel2word, int B, int Tw, int T, int H, float* out_btc,
+                      float* out_bct, float* nonpad, cudaStream_t s);
+
+// ---- WaveNet gate ----
+// acts[b,c,t] = tanh(a[b,c,t]) * sigmoid(a[b,c+H,t]),  a [B,2H,T]
+cudaError_t wn_gate(const float* a, float* acts, int B, int H, int T, cudaStream_t s);
+cudaError_t copy_f32(const float* in, float* out, size_t n, cudaStream_t s);
+
+}  // namespace dtts

@@ -1,0 +1,434 @@
+// Text-encoder side kernels: embedding, channel LayerNorm, tiny-sequence self attention, the S2PA dictionary
+// attention (streaming, folded form), pronunciation mixing, duration head.
+//
+// Reference semantics: modules/dict_tts/layers/dict_encoder.py:32-66,130-144, modules/dict_tts/layers/utils.py:40-58,
+// 109-115, modules/commons/rel_transformer_encoder.py:55-79,117-158,261-279, modules/portaspeech/model.py:58-66,
+// modules/dict_tts/model.py:64-82.
+#include "kernels.cuh"
+
+namespace dtts {
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void embed_kernel(const int64_t* __restrict__ tok, const float* __restrict__ emb, float scale, int Tw,
+                             int H, int vocab, float* __restrict__ x, float* __restrict__ seq_mask,
+                             float* __restrict__ tok_mask, int* __restrict__ lens) {
+  const int b = blockIdx.x;
+  __shared__ int s_len;
+  if (threadIdx.x == 0) s_len = 0;
+  __syncthreads();
+  int cnt = 0;
+  for (int t = threadIdx.x; t < Tw; t += blockDim.x) cnt += tok[(size_t)b * Tw + t] > 0;
+  cnt = (int)warp_sum((float)cnt);
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_len, cnt);
+  __syncthreads();
+  const int len = s_len;
+  if (threadIdx.x == 0) lens[b] = len;
+  for (int t = threadIdx.x; t < Tw; t += blockDim.x) {
+    seq_mask[(size_t)b * Tw + t] = t < len ? 1.f : 0.f;      // sequence_mask(x_lengths) -- prefix mask by COUNT
+    tok_mask[(size_t)b * Tw + t] = tok[(size_t)b * Tw + t] > 0 ? 1.f : 0.f;
+  }
+  for (int i = threadIdx.x; i < H * Tw; i += blockDim.x) {
+    const int c = i / Tw, t = i - c * Tw;
+    long id = tok[(size_t)b * Tw + t];
+    if (id < 0 || id >= vocab) id = 0;
+    x[(size_t)b * H * Tw + i] = emb[(size_t)id * H + c] * scale;
+  }
+}
+
+cudaError_t embed_tokens(const int64_t* tok, const float* emb, float scale, int B, int Tw, int H, int vocab, float* x,
+                         float* seq_mask, float* tok_mask, int* lens, cudaStream_t s) {
+  embed_kernel<<<B, 256, 0, s>>>(tok, emb, scale, Tw, H, vocab, x, seq_mask, tok_mask, lens);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// One thread per (b, t) column; lanes run along t so every pass over C is coalesced.
+__global__ void channel_ln_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, float eps, const float* __restrict__ in_mask,
+                                  const float* __restrict__ out_mask, int C, int T) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const float* xp = x + (size_t)b * C * T + t;
+  float* yp = y + (size_t)b * C * T + t;
+  const float im = in_mask ? in_mask[(size_t)b * T + t] : 1.f;
+  const float om = out_mask ? out_mask[(size_t)b * T + t] : 1.f;
+  float mean = 0.f;
+  for (int c = 0; c < C; ++c) mean += xp[(size_t)c * T] * im;
+  mean /= (float)C;
+  float var = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float d = xp[(size_t)c * T] * im - mean;
+    var = fmaf(d, d, var);
+  }
+  const float rstd = rsqrtf(var / (float)C + eps);
+  for (int c = 0; c < C; ++c) {
+    const float v = (xp[(size_t)c * T] * im - mean) * rstd * gamma[c] + beta[c];
+    yp[(size_t)c * T] = v * om;
+  }
+}
+
+cudaError_t channel_layernorm(const float* x, float* y, const float* gamma, const float* beta, float eps,
+                              const float* in_mask, const float* out_mask, int B, int C, int T, cudaStream_t s) {
+  dim3 grid(cdiv(T, 32), B);
+  channel_ln_kernel<<<grid, 32, 0, s>>>(x, y, gamma, beta, eps, in_mask, out_mask, C, T);
+  return cudaGetLastError();
+}
+
+__global__ void apply_mask_kernel(float* x, const float* __restrict__ mask, int C, int T, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t b = i / ((size_t)C * T);
+  const int t = (int)(i % T);
+  x[i] *= mask[b * T + t];
+}
+cudaError_t apply_mask(float* x, const float* mask, int B, int C, int T, cudaStream_t s) {
+  const size_t n = (size_t)B * C * T;
+  apply_mask_kernel<<<cdiv(n, 256), 256, 0, s>>>(x, mask, C, T, n);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Self attention for short sequences: one warp per query row, block = (b, head).  scores = q.k/sqrt(dk),
+// masked_fill(mask_t*mask_s == 0, -1e4), softmax over s, out = p.v  (rel_transformer_encoder.py:128-158, window None).
+__global__ void self_attn_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                                 const float* __restrict__ mask, float* __restrict__ out, int C, int T, int heads,
+                                 long bs) {
+  extern __shared__ float sm[];             // [warps][T] probabilities
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int dk = C / heads;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float* qb = q + (size_t)b * bs + (size_t)h * dk * T;
+  const float* kb = k + (size_t)b * bs + (size_t)h * dk * T;
+  const float* vb = v + (size_t)b * bs + (size_t)h * dk * T;
+  float* ob = out + (size_t)b * C * T + (size_t)h * dk * T;
+  const float* mb = mask + (size_t)b * T;
+  float* pr = sm + (size_t)warp * T;
+  const float inv = rsqrtf((float)dk);
+  for (int t = warp; t < T; t += nw) {
+    const float mt = mb[t];
+    float mx = -INFINITY;
+    for (int s = lane; s < T; s += 32) {
+      float acc = 0.f;
+      for (int d = 0; d < dk; ++d) acc = fmaf(qb[(size_t)d * T + t], kb[(size_t)d * T + s], acc);
+      acc *= inv;
+      if (mt * mb[s] == 0.f) acc = -1e4f;
+      pr[s] = acc;
+      mx = fmaxf(mx, acc);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int s = lane; s < T; s += 32) {
+      const float e = expf(pr[s] - mx);
+      pr[s] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float rs = 1.f / sum;
+    __syncwarp();
+    for (int d = lane; d < dk; d += 32) {
+      float acc = 0.f;
+      for (int s = 0; s < T; ++s) acc = fmaf(pr[s], vb[(size_t)d * T + s], acc);
+      ob[(size_t)d * T + t] = acc * rs;
+    }
+    __syncwarp();
+  }
+}
+
+cudaError_t self_attention(const float* q, const float* k, const float* v, const float* mask, float* out, int B, int C,
+                           int T, int heads, cudaStream_t s) {
+  const int threads = 256;
+  const size_t smem = (size_t)(threads / 32) * T * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  // q, k, v are slices of one [B, 3C, T] buffer: batch stride 3*C*T
+  self_attn_kernel<<<B * heads, threads, smem, s>>>(q, k, v, mask, out, C, T, heads, (long)3 * C * T);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// S2PA, folded form: logits[l] = keys[b,t,l,:] . qk[b,t,:]  (qk = W_k^T (W_q x) * D^-1/2), masked softmax over the
+// gloss tokens of this character, ctx = sum_l w[l] * values[b,t,l,:].  HBM-bound: every key/value row is read
+// exactly once with 128-bit streaming loads; rows with key_map == 0 (logit forced to -1e9 -> weight exactly 0
+// unless the whole row is masked) are not read at all.
+__global__ void __launch_bounds__(256) s2pa_stream_kernel(const float* __restrict__ keys,
+                                                           const float* __restrict__ values,
+                                                           const float* __restrict__ key_map,
+                                                           const float* __restrict__ qk, int Tw, int Lk, int D,
+                                                           float* __restrict__ weights, float* __restrict__ align,
+                                                           float* __restrict__ ctx) {
+  extern __shared__ float sm[];
+  float* s_q = sm;            // [D]
+  float* s_w = sm + D;        // [Lk]
+  __shared__ float s_red[8];
+  __shared__ int s_any;
+  const int bt = blockIdx.x;
+  const int b = bt / Tw, t = bt - b * Tw;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_any = 0;
+  for (int d = tid; d < D; d += 256) s_q[d] = qk[((size_t)b * D + d) * Tw + t];
+  __syncthreads();
+  const float* km = key_map + (size_t)bt * Lk;
+  const float4* kp = reinterpret_cast<const float4*>(keys + (size_t)bt * Lk * D);
+  const int D4 = D >> 2;
+  // pass 1: logits (one warp per gloss token)
+  for (int l = warp; l < Lk; l += 8) {
+    float logit = -1e9f;
+    if (km[l] != 0.f) {
+      float acc = 0.f;
+      for (int i = lane; i < D4; i += 32) {
+        const float4 kv = ld_stream_f4(kp + (size_t)l * D4 + i);
+        const float4 qv = *reinterpret_cast<const float4*>(s_q + 4 * i);
+        acc = fmaf(kv.x, qv.x, acc); acc = fmaf(kv.y, qv.y, acc);
+        acc = fmaf(kv.z, qv.z, acc); acc = fmaf(kv.w, qv.w, acc);
+      }
+      acc = warp_sum(acc);
+      logit = acc;
+      if (lane == 0) s_any = 1;
+    }
+    if (lane == 0) s_w[l] = logit;
+  }
+  __syncthreads();
+  // softmax over Lk
+  float mx = -INFINITY;
+  for (int l = tid; l < Lk; l += 256) mx = fmaxf(mx, s_w[l]);
+  mx = warp_max(mx);
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  mx = s_red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, s_red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int l = tid; l < Lk; l += 256) {
+    const float e = expf(s_w[l] - mx);
+    s_w[l] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) s_red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += s_red[i];
+  const float rs = 1.f / sum;
+  for (int l = tid; l < Lk; l += 256) {
+    const float w = s_w[l] * rs;
+    s_w[l] = w;
+    weights[(size_t)bt * Lk + l] = w;
+    align[((size_t)b * Lk + l) * Tw + t] = w;                 // [B,1,Lk,Tw]
+  }
+  __syncthreads();
+  // pass 2: ctx[d] = sum_l w[l] * values[l][d]; each thread owns float4 columns, rows with w == 0 are skipped.
+  // A fully masked row has uniform weights 1/Lk and all-zero-padded values: it still has to be read.
+  const float4* vp = reinterpret_cast<const float4*>(values + (size_t)bt * Lk * D);
+  const bool all_masked = (s_any == 0);
+  for (int i = tid; i < D4; i += 256) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int l = 0; l < Lk; ++l) {
+      const float w = s_w[l];
+      if (w == 0.f && !all_masked) continue;
+      const float4 vv = ld_stream_f4(vp + (size_t)l * D4 + i);
+      acc.x = fmaf(w, vv.x, acc.x); acc.y = fmaf(w, vv.y, acc.y);
+      acc.z = fmaf(w, vv.z, acc.z); acc.w = fmaf(w, vv.w, acc.w);
+    }
+    float* c = ctx + ((size_t)b * D + 4 * i) * Tw + t;
+    c[0] = acc.x; c[Tw] = acc.y; c[2 * (size_t)Tw] = acc.z; c[3 * (size_t)Tw] = acc.w;
+  }
+}
+
+cudaError_t s2pa_stream(const float* keys, const float* values, const float* key_map, const float* qk, int B, int Tw,
+                        int Lk, int D, float* weights, float* align, float* ctx, cudaStream_t s) {
+  if (D % 4) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)(D + Lk) * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(s2pa_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  s2pa_stream_kernel<<<B * Tw, 256, smem, s>>>(keys, values, key_map, qk, Tw, Lk, D, weights, align, ctx);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void dict_maxes_kernel(const float* __restrict__ key_map, size_t n_key, const int64_t* __restrict__ pm,
+                                  size_t n_pin, int* maxes) {
+  int m0 = 0, m1 = 0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_key; i += stride) m0 = max(m0, (int)key_map[i]);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pin; i += stride) m1 = max(m1, (int)pm[i]);
+  m0 = warp_max_i(m0);
+  m1 = warp_max_i(m1);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(maxes, m0);
+    atomicMax(maxes + 1, m1);
+  }
+}
+cudaError_t dict_maxes(const float* key_map, size_t n_key, const int64_t* pinyin_map, size_t n_pin, int* maxes,
+                       cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(maxes, 0, 2 * sizeof(int), s);
+  if (e != cudaSuccess) return e;
+  dict_maxes_kernel<<<148, 256, 0, s>>>(key_map, n_key, pinyin_map, n_pin, maxes);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// mask_weights_attn + add_pron_rule + pinyin mixing (layers/utils.py:49-58,109-115; dict_encoder.py:60-64).
+__global__ void s2pa_pron_kernel(const float* __restrict__ weights, const float* __restrict__ key_map,
+                                 const int64_t* __restrict__ pinyin, const int64_t* __restrict__ pinyin_map,
+                                 const int64_t* __restrict__ pron_modified, const int* __restrict__ maxes,
+                                 const float* __restrict__ pinyin_emb, int pinyin_vocab,
+                                 const float* __restrict__ context, const float* __restrict__ seq_mask, int Tw, int Lk,
+                                 int Lp, int H, int apply_rule, float* __restrict__ pron_attn, float* __restrict__ x2) {
+  extern __shared__ float s_pw[];            // [Lp]
+  const int bt = blockIdx.x;
+  const int b = bt / Tw, t = bt - b * Tw;
+  const int kmax = maxes[0], pmax = maxes[1];
+  const float* w = weights + (size_t)bt * Lk;
+  const float* km = key_map + (size_t)bt * Lk;
+  const int64_t* pm = pinyin_map + (size_t)bt * Lp;
+  const long forced = (apply_rule && pron_modified) ? (long)pron_modified[bt] : 0;
+  for (int p = threadIdx.x; p < Lp; p += blockDim.x) {
+    const long id = pm[p];
+    float acc = 0.f;
+    if (id >= 1 && id <= kmax) {
+      const float idf = (float)id;
+      for (int l = 0; l < Lk; ++l) acc += (km[l] == idf) ? w[l] : 0.f;
+    }
+    float r = acc;
+    if (forced >= 1 && forced <= pmax) {
+      const float oh = (id == forced) ? 1.f : 0.f;
+      r = (oh - acc) + acc;                                    // weights_ - weights.detach() + weights
+    } else if (apply_rule && pron_modified) {
+      r = (acc - acc) + acc;
+    }
+    s_pw[p] = r;
+    pron_attn[(size_t)bt * Lp + p] = r;
+  }
+  __syncthreads();
+  const float mk = seq_mask[bt];
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    float acc = 0.f;
+    for (int p = 0; p < Lp; ++p) {
+      long id = pinyin[(size_t)bt * Lp + p];
+      if (id < 0 || id >= pinyin_vocab) id = 0;
+      acc = fmaf(s_pw[p], pinyin_emb[(size_t)id * H + h], acc);
+    }
+    const size_t o = ((size_t)b * H + h) * Tw + t;
+    x2[o] = context[o] * mk + acc;
+  }
+}
+
+cudaError_t s2pa_pron(const float* weights, const float* key_map, const int64_t* pinyin, const int64_t* pinyin_map,
+                      const int64_t* pron_modified, const int* maxes, const float* pinyin_emb, int pinyin_vocab,
+                      const float* context, const float* seq_mask, int B, int Tw, int Lk, int Lp, int H, int apply_rule,
+                      float* pron_attn, float* x2, cudaStream_t s) {
+  s2pa_pron_kernel<<<B * Tw, 192, Lp * sizeof(float), s>>>(weights, key_map, pinyin, pinyin_map, pron_modified, maxes,
+                                                          pinyin_emb, pinyin_vocab, context, seq_mask, Tw, Lk, Lp, H,
+                                                          apply_rule, pron_attn, x2);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void finish_text_kernel(const float* __restrict__ x, const float* __restrict__ tok_mask, int Tw, int H,
+                                   float* __restrict__ enc_btc, float* __restrict__ dur_in, float* __restrict__ keep) {
+  const int bt = blockIdx.x;
+  const int b = bt / Tw, t = bt - b * Tw;
+  const float mk = tok_mask[bt];
+  __shared__ float s_red[8];
+  float a = 0.f;
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    const size_t i = ((size_t)b * H + h) * Tw + t;
+    const float v = x[i] * mk;
+    enc_btc[(size_t)bt * H + h] = v;
+    dur_in[i] = v;
+    a += fabsf(v);
+  }
+  a = warp_sum(a);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += s_red[i];
+    keep[bt] = tot == 0.f ? 0.f : 1.f;                         // src_padding = (abs().sum(-1) == 0)
+  }
+}
+cudaError_t finish_text(const float* x, const float* tok_mask, int B, int Tw, int H, float* enc_btc, float* dur_in,
+                        float* keep, cudaStream_t s) {
+  finish_text_kernel<<<B * Tw, 64, 0, s>>>(x, tok_mask, Tw, H, enc_btc, dur_in, keep);
+  return cudaGetLastError();
+}
+
+__global__ void count_keep_kernel(const float* __restrict__ keep, int Tw, int64_t* ilens) {
+  const int b = blockIdx.x;
+  float c = 0.f;
+  for (int t = threadIdx.x; t < Tw; t += 32) c += keep[(size_t)b * Tw + t];
+  c = warp_sum(c);
+  if (threadIdx.x == 0) ilens[b] = (int64_t)(c + 0.5f);
+}
+cudaError_t count_keep(const float* keep, int B, int Tw, int64_t* ilens, cudaStream_t s) {
+  count_keep_kernel<<<B, 32, 0, s>>>(keep, Tw, ilens);
+  return cudaGetLastError();
+}
+
+__global__ void dur_head_kernel(const float* __restrict__ xs, const float* __restrict__ w,
+                                const float* __restrict__ bias, const float* __restrict__ keep, int C, int Tw,
+                                float* __restrict__ dur, int64_t* __restrict__ dur_int, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int b = i / Tw, t = i - b * Tw;
+  float acc = 0.f;
+  for (int c = 0; c < C; ++c) acc = fmaf(w[c], xs[((size_t)b * C + c) * Tw + t], acc);
+  acc += bias[0];
+  const float sp = acc > 20.f ? acc : log1pf(expf(acc));        // nn.Softplus(beta=1, threshold=20)
+  const float d = sp * keep[i];
+  dur[i] = d;
+  float r = rintf(expf(d) - 1.f);                               // torch.round = half-to-even
+  r = fmaxf(r, 0.f);
+  dur_int[i] = (int64_t)r;
+}
+cudaError_t dur_head(const float* xs, const float* w, const float* bias, const float* keep, int B, int C, int Tw,
+                     float* dur, int64_t* dur_int, cudaStream_t s) {
+  const int n = B * Tw;
+  dur_head_kernel<<<cdiv(n, 128), 128, 0, s>>>(xs, w, bias, keep, C, Tw, dur, dur_int, n);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void wn_gate_kernel(const float* __restrict__ a, float* __restrict__ acts, int H, int T, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t per = (size_t)H * T;
+  const size_t b = i / per, r = i - b * per;
+  const float ta = a[b * 2 * per + r];
+  const float sa = a[b * 2 * per + per + r];
+  acts[i] = tanhf(ta) * (1.f / (1.f + expf(-sa)));
+}
+cudaError_t wn_gate(const float* a, float* acts, int B, int H, int T, cudaStream_t s) {
+  const size_t n = (size_t)B * H * T;
+  wn_gate_kernel<<<cdiv(n, 256), 256, 0, s>>>(a, acts, H, T, n);
+  return cudaGetLastError();
+}
+
+__global__ void copy_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+cudaError_t copy_f32(const float* in, float* out, size_t n, cudaStream_t s) {
+  if (!n) return cudaSuccess;
+  copy_kernel<<<cdiv(n, 256), 256, 0, s>>>(in, out, n);
+  return cudaGetLastError();
+}
+
+__global__ void fill_kernel(float* p, float v, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+cudaError_t fill_f32(float* p, float v, size_t n, cudaStream_t s) {
+  if (!n) return cudaSuccess;
+  fill_kernel<<<cdiv(n, 256), 256, 0, s>>>(p, v, n);
+  return cudaGetLastError();
+}
+
+}  // namespace dtts

@@ -1,0 +1,268 @@
+"""Host-side mirror of the reference's model interface on top of libdtts (tensor ownership + glue only).
+
+``DictTTSEngine.forward`` keeps the call signature and the returned dict of
+``PortaSpeech_dict.forward`` (modules/dict_tts/model.py:36-62) so ``DictTTSTask.test_step``
+(tasks/tts/dict_tts.py:179-196) can call it unchanged; ``HifiGanEngine`` is the generator behind
+``BaseVocoder.spec2wav`` (vocoders/hifigan.py:54-62).  All FLOPs run in the CUDA library; PyTorch only
+allocates buffers and hands out pointers.
+"""
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import binding
+from .config import AcousticConfig, VocoderConfig
+from .weights import drop_dead, fold_weight_norm, pack_arena
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev_f32(t, device):
+    return t.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+
+
+def _dev_i64(t, device):
+    return t.to(device=device, dtype=torch.int64, non_blocking=True).contiguous()
+
+
+class _Workspace:
+    """Grow-only device scratch buffer owned by PyTorch."""
+
+    def __init__(self, device):
+        self.device = device
+        self.buf = None
+
+    def get(self, nbytes: int) -> torch.Tensor:
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = None
+            self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self.buf
+
+
+class DictTTSEngine:
+    """Acoustic model (text -> mel).  ``state_dict`` uses the reference checkpoint keys (weight-norm pairs allowed)."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: Optional[AcousticConfig] = None, device="cuda:0",
+                 arena: Optional[torch.Tensor] = None, table=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("DictTTSEngine needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = binding.load()
+        self.cfg = cfg or AcousticConfig()
+        self.device = torch.device(device)
+        if arena is None:
+            host, table = pack_arena(drop_dead(fold_weight_norm(state_dict)))
+            arena = host.to(self.device)
+        self.arena, self.table = arena, table
+        c = self.cfg
+        desc = binding.AcousticDesc(c.hidden, c.n_heads, c.enc_layers, c.ffn_kernel, c.ffn_filter, c.dict_dim,
+                                    c.word_size, c.pinyin_size, c.dur_layers, c.dur_kernel, c.dur_chans,
+                                    c.frames_multiple, c.latent, c.dec_layers, c.dec_kernel, c.flow_hidden,
+                                    c.flow_kernel, c.flow_blocks, c.flow_layers, c.n_mel, int(c.language_zh))
+        tab, self._keep = binding.make_table(table)
+        self.handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            binding.check(self.lib.dtts_acoustic_create(C.byref(desc), _ptr(self.arena), self.arena.numel(), tab,
+                                                        len(table), _stream(), C.byref(self.handle)), "acoustic_create")
+        self.ws = _Workspace(self.device)
+        self._t_raw = C.c_int32(0)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.dtts_acoustic_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.dtts_acoustic_launch_count(self.handle))
+
+    # -- stages (each maps to one C-ABI call) --------------------------------------------------------------
+    def text_encode(self, word_tokens, pron_modified, keys, values, key_map, pinyin, pinyin_map):
+        dev = self.device
+        wt = _dev_i64(word_tokens, dev)
+        B, Tw = wt.shape
+        keys = _dev_f32(keys, dev)
+        values = keys if values is None else _dev_f32(values, dev)
+        key_map = _dev_f32(key_map, dev)
+        pinyin = _dev_i64(pinyin, dev)
+        pinyin_map = _dev_i64(pinyin_map, dev)
+        pm = None if pron_modified is None else _dev_i64(pron_modified, dev)
+        Lk, Lp = key_map.shape[2], pinyin.shape[2]
+        if tuple(keys.shape) != (B, Tw, Lk, self.cfg.dict_dim) or tuple(pinyin_map.shape) != (B, Tw, Lp):
+            raise ValueError("dict_msg tensors have inconsistent shapes")
+        H = self.cfg.hidden
+        out = dict(word_encoder_out=torch.empty(B, Tw, H, device=dev),
+                   dict_attn=torch.empty(B, 1, Lk, Tw, device=dev),
+                   pron_attn=torch.empty(B, Tw, Lp, device=dev),
+                   dur=torch.empty(B, Tw, device=dev),
+                   dur_int=torch.empty(B, Tw, dtype=torch.int64, device=dev),
+                   ilens=torch.empty(B, dtype=torch.int64, device=dev))
+        tin = binding.TextIn(_ptr(wt), _ptr(pm), _ptr(keys), _ptr(values), _ptr(key_map), _ptr(pinyin),
+                             _ptr(pinyin_map), B, Tw, Lk, Lp)
+        tout = binding.TextOut(*[_ptr(out[k]) for k in ("word_encoder_out", "dict_attn", "pron_attn", "dur",
+                                                          "dur_int", "ilens")])
+        nbytes = self.lib.dtts_text_workspace_bytes(self.handle, B, Tw, Lk, Lp)
+        ws = self.ws.get(nbytes)
+        binding.check(self.lib.dtts_text_encode(self.handle, C.byref(tin), C.byref(tout), _ptr(ws), ws.numel(),
+                                                _stream()), "text_encode")
+        return out
+
+    def length_regulate(self, dur_int, ilens):
+        """LengthRegulator + pad to frames_multiple.  Syncs once to learn T (data-dependent shape)."""
+        dev = self.device
+        B, Tw = dur_int.shape
+        cum = torch.empty(B, Tw, dtype=torch.int32, device=dev)
+        totals = torch.empty(B + 1, dtype=torch.int32, device=dev)
+        binding.check(self.lib.dtts_length_regulate_scan(self.handle, _ptr(dur_int), _ptr(ilens), B, Tw, _ptr(cum),
+                                                         _ptr(totals), C.byref(self._t_raw), _stream()), "lr_scan")
+        t_raw = int(self._t_raw.value)
+        if t_raw <= 0:
+            raise RuntimeError("length regulator produced an empty batch")
+        fm = self.cfg.frames_multiple
+        T = (t_raw + fm - 1) // fm * fm
+        mel2word = torch.empty(B, T, dtype=torch.int64, device=dev)
+        binding.check(self.lib.dtts_length_regulate_fill(self.handle, _ptr(cum), _ptr(ilens), B, Tw, t_raw, T,
+                                                         _ptr(mel2word), _stream()), "lr_fill")
+        return mel2word
+
+    def expand(self, word_encoder_out, mel2word):
+        dev = self.device
+        B, Tw, H = word_encoder_out.shape
+        T = mel2word.shape[1]
+        decoder_inp = torch.empty(B, T, H, device=dev)
+        g_bct = torch.empty(B, H, T, device=dev)
+        x_mask = torch.empty(B, T, device=dev)
+        binding.check(self.lib.dtts_expand(self.handle, _ptr(word_encoder_out), _ptr(mel2word), B, Tw, T,
+                                           _ptr(decoder_inp), _ptr(g_bct), _ptr(x_mask), _stream()), "expand")
+        return decoder_inp, g_bct, x_mask
+
+    def decode_mel(self, g_bct, z_in):
+        dev = self.device
+        B, H, T = g_bct.shape
+        z_in = _dev_f32(z_in, dev)
+        if tuple(z_in.shape) != (B, self.cfg.latent, T // self.cfg.frames_multiple):
+            raise ValueError(f"z_p must be [B,{self.cfg.latent},T/{self.cfg.frames_multiple}]")
+        mel = torch.empty(B, T, self.cfg.n_mel, device=dev)
+        z_p = torch.empty_like(z_in)
+        nbytes = self.lib.dtts_decode_workspace_bytes(self.handle, B, T)
+        ws = self.ws.get(nbytes)
+        binding.check(self.lib.dtts_decode_mel(self.handle, _ptr(g_bct), _ptr(z_in), B, T, _ptr(mel), _ptr(z_p),
+                                               _ptr(ws), ws.numel(), _stream()), "decode_mel")
+        return mel, z_p
+
+    # -- reference-shaped forward ---------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, txt_tokens, pron_modified, key_value_map=None, ph2word=None, word_len=None, dict_msg=None,
+                mel2word=None, mel2ph=None, spk_embed=None, infer=True, tgt_mels=None, forward_post_glow=True,
+                two_stage=True, z_p=None):
+        """Same arguments as PortaSpeech_dict.forward (model.py:36-37).  Inference only.  ``z_p`` (extension):
+        the N(0,1) prior sample; when None it is drawn exactly like the reference does -- on the host with the
+        global CPU generator (fvae_semantics.py:110-111)."""
+        if not infer:
+            raise NotImplementedError("the B200 engine implements the inference path only (infer=True)")
+        if spk_embed is not None:
+            raise NotImplementedError("multi-speaker conditioning is off in dict_tts.yaml (use_spk_embed: false)")
+        word_tokens = txt_tokens[0] if isinstance(txt_tokens, (tuple, list)) else txt_tokens
+        keys, values, key_map, pinyin, pinyin_map = dict_msg
+        with torch.cuda.device(self.device):
+            ret = {}
+            t = self.text_encode(word_tokens, pron_modified, keys, values, key_map, pinyin, pinyin_map)
+            ret["dict_attn"], ret["rel"], ret["dp_attn"] = t["dict_attn"], None, None
+            ret["pron_attn"], ret["dur"], ret["word_encoder_out"] = t["pron_attn"], t["dur"], t["word_encoder_out"]
+            fm = self.cfg.frames_multiple
+            if mel2word is None:
+                mel2word = self.length_regulate(t["dur_int"], t["ilens"])
+            else:
+                mel2word = _dev_i64(mel2word, self.device)
+                if mel2word.shape[1] % fm:                    # model.py:98-100
+                    pad = fm - mel2word.shape[1] % fm
+                    mel2word = torch.cat([mel2word] + [mel2word[:, -1:]] * pad, -1).contiguous()
+            ret["mel2word"] = mel2word
+            decoder_inp, g_bct, x_mask = self.expand(t["word_encoder_out"], mel2word)
+            ret["x_mask"], ret["decoder_inp"] = x_mask.unsqueeze(-1), decoder_inp
+            ret["synta"] = torch.zeros_like(g_bct)
+            B, _, T = g_bct.shape
+            if z_p is None:
+                z_p = torch.distributions.Normal(0, 1).sample([B, self.cfg.latent, T // fm])
+            mel, z_out = self.decode_mel(g_bct, z_p)
+            ret["mel_out_fvae"] = ret["mel_out"] = mel
+            ret["z_p"] = z_out
+        return ret
+
+    __call__ = forward
+
+
+class HifiGanEngine:
+    """HiFi-GAN V1 generator: mel [B,T,80] -> wav [B,T*hop] on the device."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: Optional[VocoderConfig] = None, device="cuda:0",
+                 arena: Optional[torch.Tensor] = None, table=None, precision: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("HifiGanEngine needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = binding.load()
+        self.cfg = cfg or VocoderConfig()
+        self.device = torch.device(device)
+        if arena is None:
+            host, table = pack_arena(fold_weight_norm(state_dict))
+            arena = host.to(self.device)
+        self.arena, self.table = arena, table
+        c = self.cfg
+        desc = binding.VocoderDesc()
+        desc.n_mel, desc.init_ch, desc.n_ups, desc.n_rb = c.n_mel, c.init_ch, len(c.up_rates), len(c.rb_kernels)
+        for i, (u, k) in enumerate(zip(c.up_rates, c.up_kernels)):
+            desc.up_rates[i], desc.up_kernels[i] = u, k
+        for j, (k, dl) in enumerate(zip(c.rb_kernels, c.rb_dilations)):
+            desc.rb_kernels[j] = k
+            if len(dl) != 3:
+                raise ValueError("ResBlock1 needs 3 dilations per block")
+            for m in range(3):
+                desc.rb_dilations[j][m] = dl[m]
+        desc.precision = precision
+        tab, self._keep = binding.make_table(table)
+        self.handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            binding.check(self.lib.dtts_vocoder_create(C.byref(desc), _ptr(self.arena), self.arena.numel(), tab,
+                                                       len(table), _stream(), C.byref(self.handle)), "vocoder_create")
+        self.ws = _Workspace(self.device)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.dtts_vocoder_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.dtts_vocoder_launch_count(self.handle))
+
+    @torch.no_grad()
+    def forward(self, mel: torch.Tensor) -> torch.Tensor:
+        mel = _dev_f32(mel, self.device)
+        if mel.dim() != 3 or mel.shape[2] != self.cfg.n_mel:
+            raise ValueError("mel must be [B,T,n_mel]")
+        B, T, _ = mel.shape
+        wav = torch.empty(B, T * self.cfg.hop, device=self.device)
+        with torch.cuda.device(self.device):
+            ws = self.ws.get(self.lib.dtts_vocode_workspace_bytes(self.handle, B, T))
+            binding.check(self.lib.dtts_vocode(self.handle, _ptr(mel), B, T, _ptr(wav), _ptr(ws), ws.numel(),
+                                               _stream()), "vocode")
+        return wav
+
+    __call__ = forward

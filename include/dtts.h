@@ -1,0 +1,161 @@
+/* libdtts -- C ABI of the B200-native Dict-TTS inference engine (text -> mel -> waveform forward pass).
+ *
+ * Drop-in boundary: everything the reference computes inside
+ *   PortaSpeech_dict.forward(infer=True)        /root/reference/modules/dict_tts/model.py:36-62
+ *   HifiGAN.spec2wav -> HifiGanGenerator.forward /root/reference/vocoders/hifigan.py:54-62,
+ *                                                /root/reference/modules/hifigan/hifigan.py:126-142
+ * is reached through the entry points below.  The reference is pure Python/PyTorch (no FFI of its own); the
+ * binding a maintainer adds is the ctypes stub in INTEGRATION.md (shipped as dict_tts_b200/binding.py).
+ *
+ * Conventions
+ *  - plain C types only; every pointer named *_dev is DEVICE memory owned by the caller (PyTorch allocates it);
+ *    the library allocates device memory only at *_create (its re-laid-out copy of the weights) and frees it
+ *    at *_destroy.  Workspaces are caller-provided, sized by the *_workspace_bytes queries.
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and no call synchronises, except
+ *    where stated.  Handles are not re-entrant; one handle per (process, device).
+ *  - every call returns 0 on success or a negative dtts_status; dtts_last_error() gives the message.
+ *  - float tensors are fp32, index tensors int64 (PyTorch's LongTensor), row-major, contiguous.
+ */
+#ifndef DTTS_H_
+#define DTTS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DTTS_ABI_VERSION 1
+
+typedef enum dtts_status {
+  DTTS_OK = 0,
+  DTTS_ERR_BAD_ARG = -1,
+  DTTS_ERR_BAD_SHAPE = -2,
+  DTTS_ERR_MISSING_WEIGHT = -3,
+  DTTS_ERR_WORKSPACE_TOO_SMALL = -4,
+  DTTS_ERR_UNSUPPORTED_ARCH = -5, /* device is not sm_100 */
+  DTTS_ERR_CUDA = -6,
+  DTTS_ERR_ALIGNMENT = -7
+} dtts_status;
+
+/* One entry of the weight table: `name` is the reference checkpoint key after weight-norm folding
+ * (e.g. "fvae.decoder.wn.in_layers.0.weight"), `offset` counts floats from the arena base. */
+typedef struct dtts_weight_entry {
+  const char* name;
+  uint64_t offset;
+  uint64_t numel;
+} dtts_weight_entry;
+
+/* Hyper-parameters of the acoustic model (egs/datasets/audio/biaobei/dict_tts.yaml, resolved). */
+typedef struct dtts_acoustic_desc {
+  int32_t hidden, n_heads, enc_layers, ffn_kernel, ffn_filter, dict_dim;
+  int32_t word_size, pinyin_size;
+  int32_t dur_layers, dur_kernel, dur_chans;
+  int32_t frames_multiple, latent;
+  int32_t dec_layers, dec_kernel;
+  int32_t flow_hidden, flow_kernel, flow_blocks, flow_layers;
+  int32_t n_mel;
+  int32_t language_zh; /* 1: apply add_pron_rule (layers/utils.py:109-115) */
+} dtts_acoustic_desc;
+
+/* HiFi-GAN V1 generator description (egs/egs_bases/tts/vocoder/hifigan.yaml:3-10). */
+#define DTTS_MAX_UPS 8
+#define DTTS_MAX_RB 4
+typedef struct dtts_vocoder_desc {
+  int32_t n_mel, init_ch, n_ups, n_rb;
+  int32_t up_rates[DTTS_MAX_UPS], up_kernels[DTTS_MAX_UPS];
+  int32_t rb_kernels[DTTS_MAX_RB];
+  int32_t rb_dilations[DTTS_MAX_RB][3];
+  int32_t precision; /* 0 = fp32 FMA pipe (exact path), 1 = tensor-core split-bf16 path */
+} dtts_vocoder_desc;
+
+typedef struct dtts_acoustic dtts_acoustic; /* opaque */
+typedef struct dtts_vocoder dtts_vocoder;   /* opaque */
+
+int dtts_abi_version(void);
+/* Message of the last failing call on this thread (never NULL). */
+const char* dtts_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Acoustic model: replaces PortaSpeech_dict (modules/dict_tts/model.py:14-122) after
+ * PortaSpeechFlowTask.test_start's weight-norm removal (tasks/tts/ps_flow.py:257-268).
+ * ---------------------------------------------------------------------------------------------------------- */
+int dtts_acoustic_create(const dtts_acoustic_desc* desc, const float* arena_dev, uint64_t arena_floats,
+                         const dtts_weight_entry* table, int32_t n_entries, void* stream, dtts_acoustic** out);
+int dtts_acoustic_destroy(dtts_acoustic* h);
+
+/* Text side: DictEncoder.forward + duration predictor (model.py:84-97 -> dict_encoder.py:130-172,
+ * portaspeech/model.py:58-66, model.py:64-82).  Shapes: B utterances, Tw word tokens, Lk gloss tokens per
+ * character, Lp pinyin slots per character. */
+typedef struct dtts_text_in {
+  const int64_t* word_tokens_dev;   /* [B,Tw]                                                       */
+  const int64_t* pron_modified_dev; /* [B,Tw] or NULL                                               */
+  const float* keys_dev;            /* [B,Tw,Lk,dict_dim]                                           */
+  const float* values_dev;          /* [B,Tw,Lk,dict_dim] (may alias keys_dev)                      */
+  const float* key_map_dev;         /* [B,Tw,Lk] float, 0 = masked (dataset_utils.py:287-288)       */
+  const int64_t* pinyin_dev;        /* [B,Tw,Lp]                                                    */
+  const int64_t* pinyin_map_dev;    /* [B,Tw,Lp]                                                    */
+  int32_t B, Tw, Lk, Lp;
+} dtts_text_in;
+
+typedef struct dtts_text_out {
+  float* word_encoder_out_dev; /* [B,Tw,hidden]   ret['word_encoder_out']                    */
+  float* dict_attn_dev;        /* [B,1,Lk,Tw]     ret['dict_attn']                           */
+  float* pron_attn_dev;        /* [B,Tw,Lp]       ret['pron_attn']                           */
+  float* dur_dev;              /* [B,Tw]          ret['dur'] (log-scale, softplus output)    */
+  int64_t* dur_int_dev;        /* [B,Tw]          clamp(round(exp(dur)-1),0)                 */
+  int64_t* ilens_dev;          /* [B]             (1-src_padding).sum(-1)                    */
+} dtts_text_out;
+
+uint64_t dtts_text_workspace_bytes(const dtts_acoustic* h, int32_t B, int32_t Tw, int32_t Lk, int32_t Lp);
+int dtts_text_encode(dtts_acoustic* h, const dtts_text_in* in, const dtts_text_out* out, void* ws_dev,
+                     uint64_t ws_bytes, void* stream);
+
+/* Length regulator (modules/fastspeech/tts_modules.py:215-251).  Step 1 scans durations on the device and
+ * returns the longest utterance in *t_raw_host -- this call SYNCHRONISES the stream (the one data-dependent shape
+ * on the path).  cum_dev is int32 [B,Tw] scratch kept for step 2; totals_dev is int32 [B+1]
+ * (per-utterance frame counts, then the batch maximum). */
+int dtts_length_regulate_scan(dtts_acoustic* h, const int64_t* dur_int_dev, const int64_t* ilens_dev, int32_t B,
+                              int32_t Tw, int32_t* cum_dev, int32_t* totals_dev, int32_t* t_raw_host, void* stream);
+/* Step 2: mel2word [B,T] with T = t_raw rounded up to frames_multiple; the padded columns repeat the last
+ * column (modules/dict_tts/model.py:98-100). */
+int dtts_length_regulate_fill(dtts_acoustic* h, const int32_t* cum_dev, const int64_t* ilens_dev, int32_t B,
+                              int32_t Tw, int32_t t_raw, int32_t T, int64_t* mel2word_dev, void* stream);
+/* Zero-row pad + gather + x*tgt_nonpadding (model.py:101-107,53): decoder_inp [B,T,hidden], x_mask [B,T]. */
+int dtts_expand(dtts_acoustic* h, const float* word_encoder_out_dev, const int64_t* mel2word_dev, int32_t B,
+                int32_t Tw, int32_t T, float* decoder_inp_dev, float* g_bct_dev, float* x_mask_dev, void* stream);
+
+/* FVAE_semantics.forward(infer=True) (modules/dict_tts/fvae_semantics.py:84-115): g_bct is decoder_inp in
+ * [B,hidden,T] layout (second output of dtts_expand), z_in the N(0,1) prior sample [B,latent,T/4] drawn by the
+ * host; writes mel [B,T,n_mel] and z_p [B,latent,T/4].  T must be a multiple of frames_multiple. */
+uint64_t dtts_decode_workspace_bytes(const dtts_acoustic* h, int32_t B, int32_t T);
+int dtts_decode_mel(dtts_acoustic* h, const float* g_bct_dev, const float* z_in_dev, int32_t B, int32_t T,
+                    float* mel_dev, float* z_p_dev, void* ws_dev, uint64_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Vocoder: replaces HifiGanGenerator.forward behind BaseVocoder.spec2wav (vocoders/hifigan.py:54-62).
+ * mel [B,T,n_mel] -> wav [B, T*hop].
+ * ---------------------------------------------------------------------------------------------------------- */
+int dtts_vocoder_create(const dtts_vocoder_desc* desc, const float* arena_dev, uint64_t arena_floats,
+                        const dtts_weight_entry* table, int32_t n_entries, void* stream, dtts_vocoder** out);
+int dtts_vocoder_destroy(dtts_vocoder* h);
+uint64_t dtts_vocode_workspace_bytes(const dtts_vocoder* h, int32_t B, int32_t T);
+int dtts_vocode(dtts_vocoder* h, const float* mel_dev, int32_t B, int32_t T, float* wav_dev, void* ws_dev,
+                uint64_t ws_bytes, void* stream);
+/* Kernels launched by this handle since creation (for bench.py's gpu_launches claim). */
+uint64_t dtts_vocoder_launch_count(const dtts_vocoder* h);
+uint64_t dtts_acoustic_launch_count(const dtts_acoustic* h);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Unit-test hook: the generic fp32 convolution kernel on raw tensors (torch.nn.functional.conv1d /
+ * conv_transpose1d semantics, weights in PyTorch layout).  x [B,C_in,T_in] -> out [B,C_out,T_out].
+ * ---------------------------------------------------------------------------------------------------------- */
+int dtts_debug_conv1d(const float* x_dev, const float* w_dev, const float* bias_dev, float* out_dev, int32_t B,
+                      int32_t C_in, int32_t T_in, int32_t C_out, int32_t K, int32_t stride, int32_t padding,
+                      int32_t dilation, int32_t transposed, float pre_slope, float* scratch_w_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DTTS_H_ */

@@ -1,0 +1,173 @@
+"""GPU parity suite (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle and the
+reference-generated golden fixtures.  Tolerances are the north star's (tests/cases.py)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from dict_tts_b200 import binding, synth
+from dict_tts_b200.config import AcousticConfig, VocoderConfig
+from dict_tts_b200.weights import fold_weight_norm
+from oracle import dtts_oracle as O
+from tests.cases import (ACOUSTIC_CASES, ACOUSTIC_SEED, TOL_MEL_MAXABS, TOL_WAV_RMS, VOCODER_CASES, VOCODER_SEED)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def acoustic():
+    from dict_tts_b200.engine import DictTTSEngine
+    sd = synth.make_acoustic_state_dict(ACOUSTIC_SEED)
+    eng = DictTTSEngine(sd)
+    yield eng, fold_weight_norm(sd)
+    eng.close()
+
+
+@pytest.fixture(scope="module")
+def vocoder():
+    from dict_tts_b200.engine import HifiGanEngine
+    sd = synth.make_vocoder_state_dict(VOCODER_SEED)
+    eng = HifiGanEngine(sd)
+    yield eng, fold_weight_norm(sd)
+    eng.close()
+
+
+def _run_acoustic(eng, batch, predicted, z):
+    return eng.forward((batch["word_tokens"], batch["word_tokens"]), batch["pron_modified"], (None, None, None),
+                       ph2word=None, word_len=batch["word_lengths"].max(),
+                       dict_msg=(batch["keys"], batch["values"], batch["key_map"], batch["pinyin"], batch["pinyin_map"]),
+                       infer=True, forward_post_glow=False, two_stage=True,
+                       mel2word=None if predicted else batch["mel2word"], z_p=z)
+
+
+# --------------------------------------------------------------------------------------------------
+# generic convolution kernel vs torch (CPU fp32) on the shapes the model uses
+# --------------------------------------------------------------------------------------------------
+CONV_SHAPES = [
+    # B, C_in, T_in, C_out, K, stride, pad, dil, transposed, pre_slope
+    (2, 80, 37, 512, 7, 1, 3, 1, 0, 1.0),       # conv_pre
+    (2, 512, 19, 256, 16, 8, 4, 1, 1, 0.1),     # ups.0
+    (1, 64, 300, 32, 4, 2, 1, 1, 1, 0.1),       # ups.3
+    (2, 128, 700, 128, 11, 1, 25, 5, 0, 0.1),   # resblock k11 d5
+    (1, 32, 3000, 32, 3, 1, 3, 3, 0, 0.1),      # last stage
+    (1, 32, 2500, 1, 7, 1, 3, 1, 0, 0.01),      # conv_post (no tanh here)
+    (3, 192, 22, 768, 5, 1, 2, 1, 0, 1.0),      # encoder FFN
+    (3, 192, 100, 192, 8, 4, 2, 1, 0, 1.0),     # g_pre_net
+    (2, 16, 25, 192, 4, 4, 0, 1, 1, 1.0),       # FVAE decoder pre_net
+    (2, 64, 25, 8, 1, 1, 0, 1, 0, 1.0),         # flow post
+    (1, 192, 1, 192, 1, 1, 0, 1, 0, 1.0),       # single position
+]
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv1d_kernel_matches_torch(shape):
+    B, Ci, Ti, Co, K, s, p, d, tr, slope = shape
+    lib = binding.load()
+    g = torch.Generator().manual_seed(sum(shape[:9]))
+    x = torch.randn(B, Ci, Ti, generator=g)
+    w = torch.randn((Ci, Co, K) if tr else (Co, Ci, K), generator=g) / (Ci * K) ** 0.5
+    b = torch.randn(Co, generator=g)
+    xin = F.leaky_relu(x, slope) if slope != 1.0 else x
+    ref = F.conv_transpose1d(xin, w, b, stride=s, padding=p) if tr else F.conv1d(xin, w, b, stride=s, padding=p,
+                                                                                  dilation=d)
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+    out = torch.full(ref.shape, float("nan"), device="cuda")
+    scratch = torch.empty(w.numel(), device="cuda")
+    rc = lib.dtts_debug_conv1d(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), out.data_ptr(), B, Ci, Ti, Co, K, s, p, d,
+                               tr, C.c_float(slope), scratch.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    binding.check(rc, "debug_conv1d")
+    torch.cuda.synchronize()
+    err = (out.cpu() - ref).abs().max().item()
+    assert err < 2e-5 * max(1.0, ref.abs().max().item()), err
+
+
+# --------------------------------------------------------------------------------------------------
+# acoustic model: stage by stage vs golden (reference outputs) and oracle
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(ACOUSTIC_CASES))
+def test_acoustic_matches_reference_golden(name, golden_dir, acoustic):
+    eng, _ = acoustic
+    kw, predicted = ACOUSTIC_CASES[name]
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    batch = synth.make_batch(**kw)
+    out = _run_acoustic(eng, batch, predicted, torch.from_numpy(gold["z_in"]))
+    torch.cuda.synchronize()
+    assert np.array_equal(out["mel2word"].cpu().numpy(), gold["mel2word"]), "mel2word must be bit-exact"
+    tol = dict(word_encoder_out=2e-4, dict_attn=1e-5, pron_attn=1e-5, dur=1e-4, z_p=1e-4, mel_out=TOL_MEL_MAXABS)
+    for k, t in tol.items():
+        err = np.abs(out[k].cpu().numpy() - gold[k]).max()
+        assert err < t, (k, err)
+    # the gather is an index copy: decoder_inp must equal word_encoder_out rows bit for bit
+    enc = out["word_encoder_out"].cpu()
+    x, nonpad = O.expand_by_mel2word(enc, out["mel2word"].cpu())
+    assert torch.equal(out["decoder_inp"].cpu(), x)
+    assert torch.equal(out["x_mask"].cpu(), nonpad)
+
+
+def test_length_regulator_bit_exact_edge_cases(acoustic):
+    eng, _ = acoustic
+    g = torch.Generator().manual_seed(3)
+    B, Tw = 7, 37
+    dur = torch.randint(0, 9, (B, Tw), generator=g)
+    ilens = torch.tensor([37, 1, 5, 36, 20, 3, 33])
+    dur[1] = 0            # all-zero row -> ones
+    dur[2, :5] = 0        # all zero inside ilen, garbage after
+    dur[5, 1] = 0
+    want = O.length_regulate(dur, ilens, 4)
+    got = eng.length_regulate(dur.cuda(), ilens.cuda())
+    assert torch.equal(got.cpu(), want)
+    # long sequence, single utterance
+    dur = torch.randint(0, 30, (1, 1500), generator=g)
+    want = O.length_regulate(dur, torch.tensor([1500]), 4)
+    got = eng.length_regulate(dur.cuda(), torch.tensor([1500]).cuda())
+    assert torch.equal(got.cpu(), want)
+
+
+def test_decoder_only_matches_oracle(acoustic):
+    eng, W = acoustic
+    cfg = AcousticConfig()
+    g = torch.Generator().manual_seed(9)
+    B, T = 2, 52
+    dec_in = torch.randn(B, T, cfg.hidden, generator=g) * 0.5
+    z = synth.draw_z(B, cfg.latent, T // 4, 77)
+    with torch.no_grad():
+        want, zp = O.decode_mel(W, cfg, dec_in, z)
+    mel, z_out = eng.decode_mel(dec_in.transpose(1, 2).contiguous().cuda(), z)
+    assert (z_out.cpu() - zp).abs().max() < 1e-4
+    assert (mel.cpu() - want).abs().max() < TOL_MEL_MAXABS
+
+
+# --------------------------------------------------------------------------------------------------
+# vocoder
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(VOCODER_CASES))
+def test_vocoder_matches_reference_golden(name, golden_dir, vocoder):
+    eng, _ = vocoder
+    kw = VOCODER_CASES[name]
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))["wav"]
+    wav = eng(synth.make_mel(kw["seed"], kw["B"], kw["T"])).cpu().numpy()
+    rms = float(np.sqrt(np.mean((wav - gold) ** 2)))
+    assert rms < TOL_WAV_RMS, rms
+    assert np.abs(wav - gold).max() < 1e-3
+
+
+def test_vocoder_batch_equals_single(vocoder):
+    """Utterances are independent: batching must not change any sample."""
+    eng, _ = vocoder
+    mel = synth.make_mel(5, 3, 40)
+    full = eng(mel)
+    for b in range(3):
+        one = eng(mel[b:b + 1])
+        assert torch.equal(one[0], full[b])
+
+
+def test_bad_arguments_raise(acoustic, vocoder):
+    eng, _ = acoustic
+    with pytest.raises(RuntimeError):
+        eng.decode_mel(torch.zeros(1, 192, 6, device="cuda"), torch.zeros(1, 16, 1))      # T % 4 != 0 -> BAD_SHAPE
+    v, _ = vocoder
+    with pytest.raises(ValueError):
+        v(torch.zeros(1, 10, 79))
