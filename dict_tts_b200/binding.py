@@ -62,6 +62,8 @@ SYMBOLS = {
     "dtts_vocoder_launch_count": (_U64, [_P]),
     "dtts_acoustic_launch_count": (_U64, [_P]),
     "dtts_debug_conv1d": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P]),
+    "dtts_debug_tc_conv1d": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _F, _I, _P,
+                                       _U64, _P]),
 }
 
 _lib = None

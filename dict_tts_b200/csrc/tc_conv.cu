@@ -1,0 +1,538 @@
+// tcgen05 implicit-GEMM convolution (see tc_conv.cuh for the layout and the math).
+//
+// CTA = 224 threads, warp-specialised:
+//   warp 0 (1 lane)  activation producer : cp.async.bulk of (tile + halo) rows, one per 8-channel slab and plane
+//   warp 1 (1 lane)  weight producer     : cp.async.bulk of one pre-packed blob per (K chunk, tap)
+//   warp 2           TMEM alloc/free; 1 lane issues tcgen05.mma (M=128, N=C_out, K=16) into NACC accumulators
+//   warps 3..6       epilogue: tcgen05.ld -> bias / residual / mean scaling -> fp32 stream + leaky-ReLU'd bf16 hi/lo planes
+// Pipelines: a_full/a_empty (activation stages), w_full/w_empty (weight stages), acc_full (MMA -> epilogue); the
+// shared-memory slots are released by tcgen05.commit.
+#include "tc_conv.cuh"
+
+#include <cstdlib>
+
+namespace dtts {
+
+namespace {
+
+constexpr int kThreads = 224;
+constexpr int kMaxAStages = 2, kMaxWStages = 4;
+constexpr int kSmemHeader = 1280;            // barriers + tmem ptr (128 B) then bias (<= 256 floats) then pad
+constexpr int kSmemLimit = 227 * 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch failure on the host) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, no swizzle, K-major: core matrix = 8 rows x 16 B stored contiguously (128 B);
+// LBO = byte distance between the two 16-byte K halves of one MMA, SBO = byte distance between 8-row groups.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;  // descriptor version 1 (sm_100)
+  return d;
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+__global__ void __launch_bounds__(kThreads) tc_conv_kernel(const TcConvParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * p.MT;
+  const int g = blockIdx.y;
+  const int b = blockIdx.z;
+  const int phase = g % p.phases, nb = g / p.phases;
+  const int N = p.N, KC = p.KC, PL = p.planes;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  // bars[0..1] a_full, [2..3] a_empty, [4..7] w_full, [8..11] w_empty, [12] acc_full
+  const uint32_t bar0 = smem_u32(bars);
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_empty = [&](int s) { return bar0 + 8u * (2 + s); };
+  auto w_full = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto w_empty = [&](int s) { return bar0 + 8u * (8 + s); };
+  const uint32_t acc_full = bar0 + 8u * 12;
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + 112);
+  float* bias_s = reinterpret_cast<float*>(smem + 128);
+
+  const uint32_t a_plane_bytes = (uint32_t)(KC / 8) * p.RA * 16u;
+  const uint32_t a_stage_bytes = a_plane_bytes * PL;
+  const uint32_t w_plane_bytes = (uint32_t)N * KC * 2u;
+  const uint32_t w_blob_bytes = w_plane_bytes * PL;
+  const uint32_t a_base = smem_u32(smem + kSmemHeader);
+  const uint32_t w_base = a_base + p.a_stages * a_stage_bytes;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kMaxAStages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < kMaxWStages; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem + 112)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    // ------------------------------------------------ activation producer
+    if (lane == 0) {
+      const int slabs = KC / 8;
+      const uint32_t row_bytes = (uint32_t)p.RA * 16u;
+      const size_t row0 = (size_t)(p.a_pad + q0 + p.min_off);
+      for (int c = 0; c < p.nchunks; ++c) {
+        const int s = c % p.a_stages, n = c / p.a_stages;
+        mbar_wait(a_empty(s), (n & 1) ^ 1);
+        mbar_arrive_expect_tx(a_full(s), a_stage_bytes);
+        for (int pl = 0; pl < PL; ++pl) {
+          const __nv_bfloat16* src = (pl ? p.a_lo : p.a_hi) + (size_t)b * p.a_bs;
+          for (int sl = 0; sl < slabs; ++sl) {
+            const __nv_bfloat16* gp = src + ((size_t)(c * slabs + sl) * p.a_rows + row0) * 8;
+            bulk_g2s(a_base + s * a_stage_bytes + pl * a_plane_bytes + sl * row_bytes, gp, row_bytes, a_full(s));
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ weight producer
+    if (lane == 0) {
+      const size_t blob_elems = (size_t)w_blob_bytes / 2;
+      const __nv_bfloat16* wg = p.w + (size_t)g * p.nchunks * p.ktaps * blob_elems;
+      const int total = p.nchunks * p.ktaps;
+      for (int it = 0; it < total; ++it) {
+        const int s = it % p.w_stages, n = it / p.w_stages;
+        mbar_wait(w_empty(s), (n & 1) ^ 1);
+        mbar_arrive_expect_tx(w_full(s), w_blob_bytes);
+        bulk_g2s(w_base + s * w_blob_bytes, wg + (size_t)it * blob_elems, w_blob_bytes, w_full(s));
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 @17, M>>4 @24
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+      uint32_t a_lbo = (uint32_t)p.RA * 16u, a_sbo = 128u, b_lbo = (uint32_t)N * 16u, b_sbo = 128u;
+      if (p.variant & 1u) {
+        uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t;
+        t = b_lbo; b_lbo = b_sbo; b_sbo = t;
+      }
+      const int ksteps = KC / 16;
+      int it = 0;
+      for (int c = 0; c < p.nchunks; ++c) {
+        const int sa = c % p.a_stages;
+        mbar_wait(a_full(sa), (c / p.a_stages) & 1);
+        tc_fence_after();
+        const uint32_t a_stage = a_base + sa * a_stage_bytes;
+        for (int j = 0; j < p.ktaps; ++j, ++it) {
+          const int sw = it % p.w_stages;
+          mbar_wait(w_full(sw), (it / p.w_stages) & 1);
+          tc_fence_after();
+          const uint32_t w_stage = w_base + sw * w_blob_bytes;
+          const uint32_t row_off = (uint32_t)(p.tap_off0 + j * p.tap_step - p.min_off);
+          for (int m = 0; m < p.NACC; ++m) {
+            const uint32_t d = tmem_base + (uint32_t)(m * N);
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint32_t a_addr = a_stage + (uint32_t)(2 * ks) * (uint32_t)p.RA * 16u + (m * 128u + row_off) * 16u;
+              const uint32_t b_addr = w_stage + (uint32_t)(2 * ks) * (uint32_t)N * 16u;
+              const uint64_t a_hi = make_desc(a_addr, a_lbo, a_sbo);
+              const uint64_t b_hi = make_desc(b_addr, b_lbo, b_sbo);
+              const uint32_t acc = (c | j | ks) != 0 ? 1u : 0u;
+              umma_bf16(d, a_hi, b_hi, idesc, acc);
+              if (PL == 2) {
+                const uint64_t a_lo = make_desc(a_addr + a_plane_bytes, a_lbo, a_sbo);
+                const uint64_t b_lo = make_desc(b_addr + w_plane_bytes, b_lbo, b_sbo);
+                umma_bf16(d, a_hi, b_lo, idesc, 1u);
+                umma_bf16(d, a_lo, b_hi, idesc, 1u);
+              }
+            }
+          }
+          umma_commit(w_empty(sw));     // weight slot free once these MMAs have read it
+        }
+        umma_commit(a_empty(sa));
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    // ------------------------------------------------ epilogue (warps 3..6)
+    const int et = threadIdx.x - 96;                 // 0..127
+    const int quad = warp & 3;                       // TMEM lanes [32*quad, 32*quad+32) are visible to this warp
+    const int co_off = nb * N;
+    for (int i = et; i < N; i += 128) bias_s[i] = p.bias ? __ldg(p.bias + co_off + i) : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const bool split = PL == 2;
+    for (int m = 0; m < p.NACC; ++m) {
+      const int q = q0 + m * 128 + quad * 32 + lane;
+      const int t = q * p.ot_mul + p.ot_add + phase;
+      const bool ok = q < p.nq && t >= 0 && t < p.T_out;
+      for (int cc = 0; cc < N / 32; ++cc) {
+        uint32_t r[32];
+        __syncwarp();                                  // tcgen05.ld is .sync.aligned: reconverge after the guarded stores
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(m * N + cc * 32), r);
+        if (!ok) continue;
+        const int n0 = co_off + cc * 32;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + bias_s[cc * 32 + i];
+        if (p.res) {
+          const float4* rp = reinterpret_cast<const float4*>(p.res + (size_t)b * p.o32_bs) +
+                             ((size_t)(n0 / 4) * p.T_out + t);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float4 x = rp[(size_t)k * p.T_out];   // may alias o32 (in-place y += conv)
+            v[4 * k] += x.x; v[4 * k + 1] += x.y; v[4 * k + 2] += x.z; v[4 * k + 3] += x.w;
+          }
+        }
+        if (p.post != 1.f) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= p.post;
+        }
+        if (p.o32) {
+          float4* op = reinterpret_cast<float4*>(p.o32 + (size_t)b * p.o32_bs) + ((size_t)(n0 / 4) * p.T_out + t);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float4 x;
+            if (p.accumulate) {
+              x = op[(size_t)k * p.T_out];
+              v[4 * k] += x.x; v[4 * k + 1] += x.y; v[4 * k + 2] += x.z; v[4 * k + 3] += x.w;
+            }
+            x.x = v[4 * k]; x.y = v[4 * k + 1]; x.z = v[4 * k + 2]; x.w = v[4 * k + 3];
+            op[(size_t)k * p.T_out] = x;
+          }
+        }
+        if (p.o_hi) {
+          const size_t prow = (size_t)b * p.op_bs + ((size_t)(n0 / 8) * p.op_rows + p.op_pad + t) * 8;
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a0 = leaky(v[8 * h + 2 * e], p.slope), a1 = leaky(v[8 * h + 2 * e + 1], p.slope);
+              const __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
+              hw[e] = pack_bf16(h0, h1);
+              lw[e] = pack_bf16(__float2bfloat16_rn(a0 - __bfloat162float(h0)),
+                                __float2bfloat16_rn(a1 - __bfloat162float(h1)));
+            }
+            const size_t off = prow + (size_t)h * p.op_rows * 8;
+            *reinterpret_cast<uint4*>(p.o_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            if (split) *reinterpret_cast<uint4*>(p.o_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// helper kernels
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void tc_pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int C_out,
+                                       int C_in, int K, int transposed, int stride, int N, int KC, int planes,
+                                       int ktaps, int phases) {
+  const size_t total = (size_t)C_out * C_in * ktaps * phases * planes;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  // destination index [g][chunk][tap][plane][slab][n][e]
+  size_t r = i;
+  const int e = r % 8; r /= 8;
+  const int n = r % N; r /= N;
+  const int sl = r % (KC / 8); r /= (KC / 8);
+  const int pl = r % planes; r /= planes;
+  const int j = r % ktaps; r /= ktaps;
+  const int nchunks = C_in / KC;
+  const int c = r % nchunks; r /= nchunks;
+  const int g = (int)r;
+  const int phase = g % phases, nb = g / phases;
+  const int co = nb * N + n, ci = c * KC + sl * 8 + e;
+  float v;
+  if (transposed) v = w[((size_t)ci * C_out + co) * K + phase + j * stride];
+  else v = w[((size_t)co * C_in + ci) * K + j];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  out[i] = pl ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
+}
+
+__global__ void tc_to_planes_kernel(const float* __restrict__ x, long bs, long cs, long ts, int C, int T, float slope,
+                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int rows, int pad) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int sl = blockIdx.y, b = blockIdx.z;
+  if (t >= T) return;
+  uint32_t hw[4], lw[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float a0 = leaky(x[(size_t)b * bs + (size_t)(sl * 8 + 2 * e) * cs + (size_t)t * ts], slope);
+    const float a1 = leaky(x[(size_t)b * bs + (size_t)(sl * 8 + 2 * e + 1) * cs + (size_t)t * ts], slope);
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
+    hw[e] = pack_bf16(h0, h1);
+    lw[e] = pack_bf16(__float2bfloat16_rn(a0 - __bfloat162float(h0)), __float2bfloat16_rn(a1 - __bfloat162float(h1)));
+  }
+  const size_t off = (((size_t)b * (C / 8) + sl) * rows + pad + t) * 8;
+  *reinterpret_cast<uint4*>(hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+  if (lo) *reinterpret_cast<uint4*>(lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+
+__global__ void tc_zero_halo_kernel(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int rows, int pad,
+                                    int T) {
+  const size_t slab = blockIdx.x;
+  const int nz = rows - T;                       // zero rows: [0,pad) then [pad+T, rows)
+  uint4* ph = reinterpret_cast<uint4*>(hi) + slab * rows;
+  uint4* pl = lo ? reinterpret_cast<uint4*>(lo) + slab * rows : nullptr;
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < nz; i += blockDim.x) {
+    const int row = i < pad ? i : T + i;
+    ph[row] = z;
+    if (pl) pl[row] = z;
+  }
+}
+
+__global__ void tc_stream_to_nct_kernel(const float* __restrict__ st, float* __restrict__ out, int C, int T) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s4 = blockIdx.y, b = blockIdx.z;
+  if (t >= T) return;
+  const float4 v = reinterpret_cast<const float4*>(st)[((size_t)b * (C / 4) + s4) * T + t];
+  float* o = out + ((size_t)b * C + s4 * 4) * T + t;
+  o[0] = v.x; o[(size_t)T] = v.y; o[(size_t)2 * T] = v.z; o[(size_t)3 * T] = v.w;
+}
+__global__ void tc_nct_to_stream_kernel(const float* __restrict__ in, float* __restrict__ st, int C, int T) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s4 = blockIdx.y, b = blockIdx.z;
+  if (t >= T) return;
+  const float* o = in + ((size_t)b * C + s4 * 4) * T + t;
+  reinterpret_cast<float4*>(st)[((size_t)b * (C / 4) + s4) * T + t] =
+      make_float4(o[0], o[(size_t)T], o[(size_t)2 * T], o[(size_t)3 * T]);
+}
+
+__global__ void tc_planes_to_nct_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                        float* __restrict__ out, int C, int T, int rows, int pad) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int sl = blockIdx.y, b = blockIdx.z;
+  if (t >= T) return;
+  const size_t off = (((size_t)b * (C / 8) + sl) * rows + pad + t) * 8;
+  for (int e = 0; e < 8; ++e) {
+    float v = __bfloat162float(hi[off + e]);
+    if (lo) v += __bfloat162float(lo[off + e]);
+    out[((size_t)b * C + sl * 8 + e) * T + t] = v;
+  }
+}
+
+// conv_post + tanh on the CUDA cores (C_out = 1: 2*C*K flop per sample against C*4 bytes read -> HBM bound).
+template <int KMAX>
+__global__ void __launch_bounds__(256) tc_conv_post_kernel(const float* __restrict__ st, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, float* __restrict__ wav,
+                                                           int C, int T, int K, float slope) {
+  __shared__ float ws[64 * KMAX];
+  for (int i = threadIdx.x; i < C * K; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (t >= T) return;
+  const int pad = (K - 1) / 2;
+  float acc = bias ? bias[0] : 0.f;
+  const float4* sp = reinterpret_cast<const float4*>(st) + (size_t)b * (C / 4) * T;
+  for (int s4 = 0; s4 < C / 4; ++s4) {
+    const float4* row = sp + (size_t)s4 * T;
+    const float* wc = ws + s4 * 4 * K;
+    for (int j = 0; j < K; ++j) {
+      const int tt = t + j - pad;
+      if (tt < 0 || tt >= T) continue;
+      const float4 x = __ldg(row + tt);
+      acc = fmaf(wc[j], leaky(x.x, slope), acc);
+      acc = fmaf(wc[K + j], leaky(x.y, slope), acc);
+      acc = fmaf(wc[2 * K + j], leaky(x.z, slope), acc);
+      acc = fmaf(wc[3 * K + j], leaky(x.w, slope), acc);
+    }
+  }
+  wav[(size_t)b * T + t] = tanhf(acc);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+cudaError_t tc_conv_init() {
+  return cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq) {
+  p->w = w.w; p->bias = w.bias;
+  p->C_in = w.C_in; p->N = w.N; p->KC = w.KC; p->nchunks = w.C_in / w.KC; p->ktaps = w.ktaps;
+  p->planes = w.planes; p->nblocks = w.C_out / w.N; p->phases = w.phases;
+  p->nq = nq;
+  int nacc = 512 / w.N;
+  if (nacc > 4) nacc = 4;
+  const int force = env_int("DTTS_TC_NACC", 0);
+  if (force > 0 && force <= nacc) nacc = force;
+  while (nacc > 1 && (nacc - 1) * 128 >= nq) --nacc;         // short sequences: do not compute empty sub-tiles
+  p->NACC = nacc;
+  p->MT = 128 * nacc;
+  const int o0 = p->tap_off0, o1 = p->tap_off0 + (p->ktaps - 1) * p->tap_step;
+  p->min_off = o0 < o1 ? o0 : o1;
+  const int max_off = o0 < o1 ? o1 : o0;
+  p->RA = p->MT + (max_off - p->min_off);
+  int cols = 32;
+  while (cols < nacc * w.N) cols <<= 1;
+  p->tmem_cols = cols;
+  p->a_stages = p->nchunks > 1 ? 2 : 1;
+  const size_t a_stage = (size_t)(p->KC / 8) * p->RA * 16 * p->planes;
+  const size_t w_blob = (size_t)p->N * p->KC * 2 * p->planes;
+  size_t budget = kSmemLimit - kSmemHeader - p->a_stages * a_stage;
+  int ws = (int)(budget / w_blob);
+  if (ws > kMaxWStages) ws = kMaxWStages;
+  const int total = p->nchunks * p->ktaps;
+  if (ws > total) ws = total;
+  p->w_stages = ws;
+  p->variant = (unsigned)env_int("DTTS_TC_VARIANT", 0);
+}
+
+static size_t tc_smem_bytes(const TcConvParams& p) {
+  const size_t a_stage = (size_t)(p.KC / 8) * p.RA * 16 * p.planes;
+  const size_t w_blob = (size_t)p.N * p.KC * 2 * p.planes;
+  size_t bytes = kSmemHeader + p.a_stages * a_stage + p.w_stages * w_blob;
+  // a CTA that owns all 512 TMEM columns must be alone on its SM, otherwise a co-resident CTA would block in alloc
+  if (p.tmem_cols > 256 && bytes < 116 * 1024) bytes = 116 * 1024;
+  return bytes;
+}
+
+cudaError_t launch_tc_conv(TcConvParams p, int B, cudaStream_t stream) {
+  if (B <= 0 || p.nq <= 0) return cudaSuccess;
+  if (p.w_stages < 1 || p.N % 32 != 0 || p.N > 256 || p.KC % 16 != 0 || p.C_in % p.KC != 0 || p.N > 256)
+    return cudaErrorInvalidConfiguration;
+  const int ntiles = cdiv(p.nq, p.MT);
+  const int max_off = p.min_off + (p.RA - p.MT);
+  if (p.a_pad + p.min_off < 0 || p.a_pad + ntiles * p.MT + max_off > p.a_rows) return cudaErrorInvalidValue;
+  const size_t smem = tc_smem_bytes(p);
+  if (smem > (size_t)kSmemLimit) return cudaErrorInvalidConfiguration;
+  dim3 grid(ntiles, p.nblocks * p.phases, B);
+  tc_conv_kernel<<<grid, kThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t tc_pack_weights(const float* w_ref, __nv_bfloat16* out, int C_out, int C_in, int K, int transposed,
+                            int stride, int N, int KC, int planes, cudaStream_t s) {
+  const int phases = transposed ? stride : 1;
+  const int ktaps = transposed ? K / stride : K;
+  if (C_out % N || C_in % KC || (transposed && K % stride)) return cudaErrorInvalidValue;
+  const size_t total = (size_t)C_out * C_in * ktaps * phases * planes;
+  tc_pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w_ref, out, C_out, C_in, K, transposed, stride,
+                                                                        N, KC, planes, ktaps, phases);
+  return cudaGetLastError();
+}
+
+cudaError_t tc_to_planes(const float* x, long bs, long cs, long ts, int B, int C, int T, float slope,
+                         __nv_bfloat16* hi, __nv_bfloat16* lo, int rows, int pad, cudaStream_t s) {
+  if (C % 8) return cudaErrorInvalidValue;
+  dim3 grid(cdiv(T, 128), C / 8, B);
+  tc_to_planes_kernel<<<grid, 128, 0, s>>>(x, bs, cs, ts, C, T, slope, hi, lo, rows, pad);
+  return cudaGetLastError();
+}
+
+cudaError_t tc_zero_halo(__nv_bfloat16* hi, __nv_bfloat16* lo, int n_slabs_total, int rows, int pad, int T,
+                         cudaStream_t s) {
+  tc_zero_halo_kernel<<<n_slabs_total, 128, 0, s>>>(hi, lo, rows, pad, T);
+  return cudaGetLastError();
+}
+
+cudaError_t tc_stream_to_nct(const float* st, float* out, int B, int C, int T, cudaStream_t s) {
+  dim3 grid(cdiv(T, 128), C / 4, B);
+  tc_stream_to_nct_kernel<<<grid, 128, 0, s>>>(st, out, C, T);
+  return cudaGetLastError();
+}
+cudaError_t tc_nct_to_stream(const float* in, float* st, int B, int C, int T, cudaStream_t s) {
+  dim3 grid(cdiv(T, 128), C / 4, B);
+  tc_nct_to_stream_kernel<<<grid, 128, 0, s>>>(in, st, C, T);
+  return cudaGetLastError();
+}
+
+cudaError_t tc_planes_to_nct(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* out, int B, int C, int T,
+                             int rows, int pad, cudaStream_t s) {
+  dim3 grid(cdiv(T, 128), C / 8, B);
+  tc_planes_to_nct_kernel<<<grid, 128, 0, s>>>(hi, lo, out, C, T, rows, pad);
+  return cudaGetLastError();
+}
+
+cudaError_t tc_conv_post(const float* st, const float* w, const float* bias, float* wav, int B, int C, int T, int K,
+                         float slope, cudaStream_t s) {
+  if (C % 4 || C > 64 || K > 16) return cudaErrorInvalidValue;
+  dim3 grid(cdiv(T, 256), B);
+  tc_conv_post_kernel<16><<<grid, 256, 0, s>>>(st, w, bias, wav, C, T, K, slope);
+  return cudaGetLastError();
+}
+
+}  // namespace dtts

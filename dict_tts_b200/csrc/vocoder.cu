@@ -3,6 +3,7 @@
 // residual add / 1/3 resblock mean / tanh fused into the epilogue (the reference launches 78 cuDNN convolutions
 // plus 127 element-wise kernels per call).
 #include "engine.cuh"
+#include "tc_conv.cuh"
 
 using namespace dtts;
 
@@ -16,6 +17,11 @@ struct dtts_vocoder {
   uint64_t launches = 0;
   int hop = 1;
   size_t unit = 0;               // max over stages of C*T_len per input frame
+  // tensor-core path (precision 1 = split bf16 hi/lo, 3 MMAs; 2 = single bf16)
+  __nv_bfloat16* tc_pool = nullptr;
+  TcConvW tc_pre;
+  std::vector<TcConvW> tc_ups, tc_rb1, tc_rb2;
+  const float *post_w = nullptr, *post_b = nullptr;
 };
 
 namespace {
@@ -45,6 +51,196 @@ int pack_convT(dtts_vocoder* h, const std::string& name, int C_in, int C_out, in
   return DTTS_OK;
 }
 
+int tc_pack(dtts_vocoder* h, __nv_bfloat16** cursor, const std::string& name, int C_out, int C_in, int K,
+            int transposed, int stride, int planes, TcConvW* cw, cudaStream_t s) {
+  const float* w = h->tab.get(name + ".weight", (uint64_t)C_out * C_in * K);
+  if (!w) return DTTS_ERR_MISSING_WEIGHT;
+  const float* b = h->tab.get(name + ".bias", C_out);
+  if (!b) return DTTS_ERR_MISSING_WEIGHT;
+  cw->C_in = C_in; cw->C_out = C_out;
+  cw->N = C_out > 256 ? 256 : C_out;
+  cw->KC = (C_in % 32 == 0) ? 32 : 16;
+  cw->ktaps = transposed ? K / stride : K;
+  cw->phases = transposed ? stride : 1;
+  cw->planes = planes;
+  cw->bias = b;
+  if (C_out % cw->N || cw->N % 32 || C_in % cw->KC)
+    return fail(DTTS_ERR_BAD_SHAPE, "tensor-core vocoder: unsupported channel count in " + name);
+  cw->w = *cursor;
+  DTTS_CUDA(tc_pack_weights(w, *cursor, C_out, C_in, K, transposed, stride, cw->N, cw->KC, planes, s));
+  *cursor += (cw->elems() + 63) / 64 * 64;
+  return DTTS_OK;
+}
+
+int tc_create(dtts_vocoder* h, cudaStream_t s) {
+  const dtts_vocoder_desc& d = h->desc;
+  const int planes = d.precision == 1 ? 2 : 1;
+  // bf16 elements needed: planes * (all conv weights) + alignment slack
+  size_t total = (size_t)d.init_ch * d.n_mel * 7 * planes + 64;
+  int ch = d.init_ch;
+  for (int i = 0; i < d.n_ups; ++i) {
+    total += (size_t)ch * (ch / 2) * d.up_kernels[i] * planes + 64;
+    ch /= 2;
+    for (int j = 0; j < d.n_rb; ++j) total += 6 * ((size_t)ch * ch * d.rb_kernels[j] * planes + 64);
+  }
+  cudaError_t e = cudaMalloc((void**)&h->tc_pool, total * sizeof(__nv_bfloat16));
+  if (e != cudaSuccess) return fail(DTTS_ERR_CUDA, std::string("cudaMalloc(tc weight pool): ") + cudaGetErrorString(e));
+  e = tc_conv_init();
+  if (e != cudaSuccess) return fail(DTTS_ERR_CUDA, std::string("tc_conv_init: ") + cudaGetErrorString(e));
+  __nv_bfloat16* cur = h->tc_pool;
+  DTTS_TRY(tc_pack(h, &cur, "conv_pre", d.init_ch, d.n_mel, 7, 0, 1, planes, &h->tc_pre, s));
+  ch = d.init_ch;
+  for (int i = 0; i < d.n_ups; ++i) {
+    TcConvW u;
+    DTTS_TRY(tc_pack(h, &cur, "ups." + std::to_string(i), ch / 2, ch, d.up_kernels[i], 1, d.up_rates[i], planes, &u, s));
+    h->tc_ups.push_back(u);
+    ch /= 2;
+    for (int j = 0; j < d.n_rb; ++j) {
+      const std::string r = "resblocks." + std::to_string(i * d.n_rb + j);
+      for (int m = 0; m < 3; ++m) {
+        TcConvW c1, c2;
+        DTTS_TRY(tc_pack(h, &cur, r + ".convs1." + std::to_string(m), ch, ch, d.rb_kernels[j], 0, 1, planes, &c1, s));
+        DTTS_TRY(tc_pack(h, &cur, r + ".convs2." + std::to_string(m), ch, ch, d.rb_kernels[j], 0, 1, planes, &c2, s));
+        h->tc_rb1.push_back(c1);
+        h->tc_rb2.push_back(c2);
+      }
+    }
+  }
+  if ((size_t)(cur - h->tc_pool) > total) return fail(DTTS_ERR_CUDA, "tc weight pool overrun");
+  if (ch % 4 || ch > 64) return fail(DTTS_ERR_BAD_SHAPE, "tensor-core vocoder: conv_post needs <= 64 input channels");
+  h->post_w = h->tab.get("conv_post.weight", (uint64_t)ch * 7);
+  h->post_b = h->tab.get("conv_post.bias", 1);
+  if (!h->post_w || !h->post_b) return DTTS_ERR_MISSING_WEIGHT;
+  return DTTS_OK;
+}
+
+// per-call buffer geometry of the tensor-core path
+struct TcGeom {
+  size_t plane_elems = 0;   // elements of ONE bf16 plane buffer (max over stages)
+  size_t stream_elems = 0;  // floats of one fp32 stream buffer (max over stages)
+  size_t mel_plane_elems = 0;
+};
+TcGeom tc_geom(const dtts_vocoder* h, int B, int T) {
+  const dtts_vocoder_desc& d = h->desc;
+  TcGeom g;
+  g.mel_plane_elems = (size_t)B * d.n_mel * tc_rows(T);
+  int ch = d.init_ch, len = T;
+  g.plane_elems = (size_t)B * ch * tc_rows(len);
+  for (int i = 0; i < d.n_ups; ++i) {
+    ch /= 2;
+    len *= d.up_rates[i];
+    const size_t pe = (size_t)B * ch * tc_rows(len), se = (size_t)B * ch * len;
+    if (pe > g.plane_elems) g.plane_elems = pe;
+    if (se > g.stream_elems) g.stream_elems = se;
+  }
+  return g;
+}
+
+struct PlaneBuf {
+  __nv_bfloat16 *hi = nullptr, *lo = nullptr;
+  int C = 0, T = 0, rows = 0;
+  long bs() const { return (long)C * rows; }
+};
+
+int tc_vocode(dtts_vocoder* h, const float* mel, int B, int T, float* wav, void* ws, uint64_t ws_bytes, cudaStream_t s) {
+  const dtts_vocoder_desc& d = h->desc;
+  const bool split = d.precision == 1;
+  const TcGeom g = tc_geom(h, B, T);
+  Bump bump(ws, ws_bytes);
+  PlaneBuf PM, PX, PXU, PT, PY;
+  PM.hi = bump.take<__nv_bfloat16>(g.mel_plane_elems);
+  PM.lo = split ? bump.take<__nv_bfloat16>(g.mel_plane_elems) : nullptr;
+  PlaneBuf* pbs[4] = {&PX, &PXU, &PT, &PY};
+  for (PlaneBuf* pb : pbs) {
+    pb->hi = bump.take<__nv_bfloat16>(g.plane_elems);
+    pb->lo = split ? bump.take<__nv_bfloat16>(g.plane_elems) : nullptr;
+  }
+  float* XU32 = bump.take<float>(g.stream_elems);
+  float* Y32 = bump.take<float>(g.stream_elems);
+  float* ACC32 = bump.take<float>(g.stream_elems);
+  if (!bump.ok) return fail(DTTS_ERR_WORKSPACE_TOO_SMALL, "dtts_vocode: workspace too small");
+  Launcher L;
+  L.stream = s;
+  L.counter = &h->launches;
+
+  auto shape = [&](PlaneBuf& pb, int C, int Tn) {      // re-purpose a plane buffer: new geometry + zero halos
+    pb.C = C; pb.T = Tn; pb.rows = tc_rows(Tn);
+    L(tc_zero_halo(pb.hi, pb.lo, B * (C / 8), pb.rows, TC_PADF, Tn, s));
+  };
+  auto base = [&](const TcConvW& w, const PlaneBuf& in, int nq, int off0, int step) {
+    TcConvParams p{};
+    p.a_hi = in.hi; p.a_lo = in.lo; p.a_bs = in.bs(); p.a_rows = in.rows; p.a_pad = TC_PADF;
+    p.tap_off0 = off0; p.tap_step = step;
+    tc_conv_plan(&p, w, nq);
+    p.ot_mul = 1; p.ot_add = 0;
+    p.post = 1.f; p.slope = 0.1f; p.accumulate = 0;
+    return p;
+  };
+  auto out_planes = [&](TcConvParams& p, const PlaneBuf& o) {
+    p.o_hi = o.hi; p.o_lo = o.lo; p.op_bs = o.bs(); p.op_rows = o.rows; p.op_pad = TC_PADF;
+  };
+
+  // mel [B,T,n_mel] -> operand planes (no activation in front of conv_pre)
+  shape(PM, d.n_mel, T);
+  L(tc_to_planes(mel, (long)T * d.n_mel, 1, d.n_mel, B, d.n_mel, T, 1.f, PM.hi, PM.lo, PM.rows, TC_PADF, s));
+  shape(PX, d.init_ch, T);
+  {
+    TcConvParams p = base(h->tc_pre, PM, T, -3, 1);
+    p.T_out = T;
+    out_planes(p, PX);                                  // leaky(., 0.1) of conv_pre feeds ups.0
+    L(launch_tc_conv(p, B, s));
+  }
+  int ch = d.init_ch, len = T;
+  for (int i = 0; i < d.n_ups; ++i) {
+    const int u = d.up_rates[i], k = d.up_kernels[i];
+    const int len_o = len * u, co = ch / 2;
+    const bool last_stage = i == d.n_ups - 1;
+    shape(PXU, co, len_o);
+    shape(PT, co, len_o);
+    shape(PY, co, len_o);
+    {
+      const TcConvW& w = h->tc_ups[i];
+      TcConvParams p = base(w, PX, len + w.ktaps - 1, 0, -1);
+      p.ot_mul = u; p.ot_add = -(k - u) / 2; p.T_out = len_o;
+      p.o32 = XU32; p.o32_bs = (long)co * len_o;
+      out_planes(p, PXU);
+      L(launch_tc_conv(p, B, s));
+    }
+    ch = co; len = len_o;
+    if (!last_stage) shape(PX, ch, len);                // PX is free again: it becomes the next stage's input
+    for (int j = 0; j < d.n_rb; ++j) {
+      const int kr = d.rb_kernels[j];
+      for (int m = 0; m < 3; ++m) {
+        const int dil = d.rb_dilations[j][m];
+        const TcConvW& c1 = h->tc_rb1[(i * d.n_rb + j) * 3 + m];
+        const TcConvW& c2 = h->tc_rb2[(i * d.n_rb + j) * 3 + m];
+        TcConvParams p1 = base(c1, m == 0 ? PXU : PY, len, -(kr * dil - dil) / 2, dil);
+        p1.T_out = len;
+        out_planes(p1, PT);
+        L(launch_tc_conv(p1, B, s));
+        TcConvParams p2 = base(c2, PT, len, -(kr - 1) / 2, 1);
+        p2.T_out = len;
+        p2.res = m == 0 ? XU32 : Y32;
+        p2.o32_bs = (long)ch * len;
+        if (m < 2) {
+          p2.o32 = Y32;
+          out_planes(p2, PY);
+        } else {                                         // xs (+)= resblock_j(x); x = xs / num_kernels
+          p2.o32 = ACC32;
+          p2.post = 1.f / (float)d.n_rb;
+          p2.accumulate = j > 0;
+          if (j == d.n_rb - 1 && !last_stage) out_planes(p2, PX);
+        }
+        L(launch_tc_conv(p2, B, s));
+      }
+    }
+  }
+  // F.leaky_relu default slope 0.01 (hifigan.py:138), conv_post, tanh
+  L(tc_conv_post(ACC32, h->post_w, h->post_b, wav, B, ch, len, 7, 0.01f, s));
+  if (L.err != cudaSuccess) return fail(DTTS_ERR_CUDA, std::string("dtts_vocode(tc): ") + cudaGetErrorString(L.err));
+  return DTTS_OK;
+}
+
 }  // namespace
 
 extern "C" int dtts_vocoder_create(const dtts_vocoder_desc* d, const float* arena_dev, uint64_t arena_floats,
@@ -59,7 +255,7 @@ extern "C" int dtts_vocoder_create(const dtts_vocoder_desc* d, const float* aren
     if (u < 1 || k % u != 0 || (k - u) % 2 != 0)
       return fail(DTTS_ERR_BAD_SHAPE, "upsample kernel must be a multiple of its rate with even (k-u)");
   }
-  if (d->precision != 0) return fail(DTTS_ERR_BAD_ARG, "vocoder precision mode not available in this build");
+  if (d->precision < 0 || d->precision > 2) return fail(DTTS_ERR_BAD_ARG, "vocoder precision must be 0, 1 or 2");
   DTTS_TRY(arch_check());
   dtts_vocoder* h = new dtts_vocoder();
   h->desc = *d;
@@ -100,6 +296,13 @@ extern "C" int dtts_vocoder_create(const dtts_vocoder_desc* d, const float* aren
   h->hop = (int)len;
   rc = pack_conv(h, "conv_post", 1, ch, 7, &h->conv_post, s);
   if (rc != DTTS_OK) return bail(rc);
+  if (d->precision != 0) {
+    rc = tc_create(h, s);
+    if (rc != DTTS_OK) {
+      if (h->tc_pool) cudaFree(h->tc_pool);
+      return bail(rc);
+    }
+  }
   cudaError_t e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) return bail(fail(DTTS_ERR_CUDA, std::string("vocoder create: ") + cudaGetErrorString(e)));
   *out = h;
@@ -109,6 +312,7 @@ extern "C" int dtts_vocoder_create(const dtts_vocoder_desc* d, const float* aren
 extern "C" int dtts_vocoder_destroy(dtts_vocoder* h) {
   if (!h) return DTTS_OK;
   h->pool.release();
+  if (h->tc_pool) cudaFree(h->tc_pool);
   delete h;
   return DTTS_OK;
 }
@@ -117,6 +321,12 @@ extern "C" uint64_t dtts_vocoder_launch_count(const dtts_vocoder* h) { return h 
 
 extern "C" uint64_t dtts_vocode_workspace_bytes(const dtts_vocoder* h, int32_t B, int32_t T) {
   if (!h || B <= 0 || T <= 0) return 0;
+  if (h->desc.precision != 0) {
+    const TcGeom g = tc_geom(h, B, T);
+    const int planes = h->desc.precision == 1 ? 2 : 1;
+    return planes * (ws_round(g.mel_plane_elems * 2) + 4 * ws_round(g.plane_elems * 2)) +
+           3 * ws_round(g.stream_elems * 4) + 4096;
+  }
   return 5 * ws_round((size_t)B * T * h->unit * sizeof(float)) + 1024;
 }
 
@@ -127,6 +337,7 @@ extern "C" int dtts_vocode(dtts_vocoder* h, const float* mel, int32_t B, int32_t
   if (ws_bytes < dtts_vocode_workspace_bytes(h, B, T))
     return fail(DTTS_ERR_WORKSPACE_TOO_SMALL, "dtts_vocode: workspace too small");
   const dtts_vocoder_desc& d = h->desc;
+  if (d.precision != 0) return tc_vocode(h, mel, B, T, wav, ws, ws_bytes, (cudaStream_t)stream);
   Bump bump(ws, ws_bytes);
   float* buf[5];
   for (int i = 0; i < 5; ++i) buf[i] = bump.take<float>((size_t)B * T * h->unit);
@@ -189,5 +400,58 @@ extern "C" int dtts_vocode(dtts_vocoder* h, const float* mel, int32_t B, int32_t
     L(launch_conv1d_f32(p, B, s));
   }
   if (L.err != cudaSuccess) return fail(DTTS_ERR_CUDA, std::string("dtts_vocode: ") + cudaGetErrorString(L.err));
+  return DTTS_OK;
+}
+
+// Unit-test hook for the tensor-core convolution: fp32 [B,C_in,T_in] in, fp32 [B,C_out,T_out] out (and optionally the
+// leaky-ReLU'd operand planes it would hand to the next layer, reconstructed as hi+lo).
+extern "C" int dtts_debug_tc_conv1d(const float* x, const float* w, const float* bias, const float* res, float* out,
+                                    float* out_act, int32_t B, int32_t C_in, int32_t T_in, int32_t C_out, int32_t K,
+                                    int32_t stride, int32_t padding, int32_t dilation, int32_t transposed,
+                                    float pre_slope, float post, float act_slope, int32_t split, void* scratch,
+                                    uint64_t scratch_bytes, void* stream) {
+  if (!x || !w || !out || !scratch) return fail(DTTS_ERR_BAD_ARG, "dtts_debug_tc_conv1d: null argument");
+  if (!transposed && stride != 1) return fail(DTTS_ERR_BAD_SHAPE, "tensor-core conv: stride must be 1");
+  if (transposed && (K % stride || (K - stride) % 2 || padding != (K - stride) / 2))
+    return fail(DTTS_ERR_BAD_SHAPE, "tensor-core transposed conv: K % stride == 0 and padding == (K-stride)/2");
+  DTTS_TRY(arch_check());
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = tc_conv_init();
+  if (e != cudaSuccess) return fail(DTTS_ERR_CUDA, std::string("tc_conv_init: ") + cudaGetErrorString(e));
+  const int planes = split ? 2 : 1;
+  TcConvW cw;
+  cw.C_in = C_in; cw.C_out = C_out; cw.N = C_out > 256 ? 256 : C_out; cw.KC = (C_in % 32 == 0) ? 32 : 16;
+  cw.ktaps = transposed ? K / stride : K; cw.phases = transposed ? stride : 1; cw.planes = planes; cw.bias = bias;
+  if (C_out % cw.N || cw.N % 32 || C_in % cw.KC) return fail(DTTS_ERR_BAD_SHAPE, "tensor-core conv: unsupported channels");
+  const int T_out = transposed ? (T_in - 1) * stride - 2 * padding + K : T_in + 2 * padding - dilation * (K - 1);
+  if (T_out <= 0) return fail(DTTS_ERR_BAD_SHAPE, "tensor-core conv: empty output");
+  Bump bump(scratch, scratch_bytes);
+  const int rows_in = tc_rows(T_in), rows_out = tc_rows(T_out);
+  __nv_bfloat16* wp = bump.take<__nv_bfloat16>(cw.elems());
+  __nv_bfloat16* a_hi = bump.take<__nv_bfloat16>((size_t)B * C_in * rows_in);
+  __nv_bfloat16* a_lo = split ? bump.take<__nv_bfloat16>((size_t)B * C_in * rows_in) : nullptr;
+  __nv_bfloat16* o_hi = bump.take<__nv_bfloat16>((size_t)B * C_out * rows_out);
+  __nv_bfloat16* o_lo = split ? bump.take<__nv_bfloat16>((size_t)B * C_out * rows_out) : nullptr;
+  float* o32 = bump.take<float>((size_t)B * C_out * T_out);
+  float* r32 = res ? bump.take<float>((size_t)B * C_out * T_out) : nullptr;
+  if (!bump.ok) return fail(DTTS_ERR_WORKSPACE_TOO_SMALL, "dtts_debug_tc_conv1d: scratch too small");
+  cw.w = wp;
+  DTTS_CUDA(tc_pack_weights(w, wp, C_out, C_in, K, transposed, stride, cw.N, cw.KC, planes, s));
+  DTTS_CUDA(tc_zero_halo(a_hi, a_lo, B * (C_in / 8), rows_in, TC_PADF, T_in, s));
+  DTTS_CUDA(tc_to_planes(x, (long)C_in * T_in, T_in, 1, B, C_in, T_in, pre_slope, a_hi, a_lo, rows_in, TC_PADF, s));
+  if (res) DTTS_CUDA(tc_nct_to_stream(res, r32, B, C_out, T_out, s));
+  TcConvParams p{};
+  p.a_hi = a_hi; p.a_lo = a_lo; p.a_bs = (long)C_in * rows_in; p.a_rows = rows_in; p.a_pad = TC_PADF;
+  int nq;
+  if (transposed) { p.tap_off0 = 0; p.tap_step = -1; nq = T_in + cw.ktaps - 1; }
+  else { p.tap_off0 = -padding; p.tap_step = dilation; nq = T_out; }
+  tc_conv_plan(&p, cw, nq);
+  p.ot_mul = transposed ? stride : 1; p.ot_add = transposed ? -padding : 0; p.T_out = T_out;
+  p.o32 = o32; p.res = r32; p.o32_bs = (long)C_out * T_out;
+  p.o_hi = o_hi; p.o_lo = o_lo; p.op_bs = (long)C_out * rows_out; p.op_rows = rows_out; p.op_pad = TC_PADF;
+  p.post = post; p.slope = act_slope; p.accumulate = 0;
+  DTTS_CUDA(launch_tc_conv(p, B, s));
+  DTTS_CUDA(tc_stream_to_nct(o32, out, B, C_out, T_out, s));
+  if (out_act) DTTS_CUDA(tc_planes_to_nct(o_hi, o_lo, out_act, B, C_out, T_out, rows_out, TC_PADF, s));
   return DTTS_OK;
 }

@@ -1,0 +1,143 @@
+"""GPU parity suite for the tcgen05 tensor-core vocoder path (-m gpu).
+
+The convolution kernel is checked against torch.nn.functional (fp32, CPU) on the shapes HiFi-GAN V1 uses, the
+whole generator against the reference-generated golden waveforms with the north-star tolerance (1e-4 RMS) in
+split-bf16 mode (precision 1).  Single-pass bf16 (precision 2, BASELINE.json cfg 3) is a throughput mode: its error
+is measured and bounded loosely here, and reported by bench.py.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from dict_tts_b200 import binding, synth
+from dict_tts_b200.weights import fold_weight_norm
+from oracle import dtts_oracle as O
+from tests.cases import TOL_WAV_RMS, VOCODER_CASES, VOCODER_SEED
+
+pytestmark = pytest.mark.gpu
+
+TC_CONV_SHAPES = [
+    # B, C_in, T_in, C_out, K, stride, pad, dil, transposed, pre_slope
+    (2, 32, 300, 32, 3, 1, 1, 1, 0, 0.1),        # last stage, single K chunk
+    (1, 32, 1500, 32, 11, 1, 25, 5, 0, 0.1),     # widest halo, several tiles
+    (2, 64, 700, 64, 7, 1, 9, 3, 0, 0.1),        # two K chunks
+    (2, 128, 1100, 128, 11, 1, 5, 1, 0, 0.1),    # stage 2
+    (2, 256, 519, 256, 3, 1, 3, 3, 0, 0.1),      # stage 1, N = 256
+    (1, 256, 64, 256, 7, 1, 3, 1, 0, 0.1),       # short sequence (one sub-tile)
+    (2, 80, 37, 512, 7, 1, 3, 1, 0, 1.0),        # conv_pre: KC = 16, two N blocks
+    (2, 512, 19, 256, 16, 8, 4, 1, 1, 0.1),      # ups.0
+    (1, 256, 150, 128, 16, 8, 4, 1, 1, 0.1),     # ups.1
+    (1, 128, 600, 64, 4, 2, 1, 1, 1, 0.1),       # ups.2
+    (2, 64, 513, 32, 4, 2, 1, 1, 1, 0.1),        # ups.3, T_in just over one tile
+]
+
+
+def _run_tc_conv(shape, split, with_res):
+    B, Ci, Ti, Co, K, s, p, d, tr, slope = shape
+    lib = binding.load()
+    g = torch.Generator().manual_seed(sum(shape[:9]) + 7)
+    x = torch.randn(B, Ci, Ti, generator=g)
+    w = torch.randn((Ci, Co, K) if tr else (Co, Ci, K), generator=g) / (Ci * K) ** 0.5
+    b = torch.randn(Co, generator=g)
+    xin = F.leaky_relu(x, slope) if slope != 1.0 else x
+    ref = F.conv_transpose1d(xin, w, b, stride=s, padding=p) if tr else F.conv1d(xin, w, b, padding=p, dilation=d)
+    res = torch.randn(ref.shape, generator=g) if with_res else None
+    post = 1.0 / 3.0 if with_res else 1.0
+    if res is not None:
+        ref = (ref + res) * post
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+    rd = res.cuda() if res is not None else None
+    out = torch.full(ref.shape, float("nan"), device="cuda")
+    act = torch.full(ref.shape, float("nan"), device="cuda")
+    scratch = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    rc = lib.dtts_debug_tc_conv1d(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), rd.data_ptr() if rd is not None else None,
+                                  out.data_ptr(), act.data_ptr(), B, Ci, Ti, Co, K, s, p, d, tr, C.c_float(slope),
+                                  C.c_float(post), C.c_float(0.1), split, scratch.data_ptr(), scratch.numel(),
+                                  torch.cuda.current_stream().cuda_stream)
+    binding.check(rc, "debug_tc_conv1d")
+    torch.cuda.synchronize()
+    return out.cpu(), act.cpu(), ref
+
+
+@pytest.mark.parametrize("shape", TC_CONV_SHAPES)
+def test_tc_conv_split_matches_torch(shape):
+    out, act, ref = _run_tc_conv(shape, split=1, with_res=False)
+    scale = max(1.0, ref.abs().max().item())
+    err = (out - ref).abs().max().item()
+    assert err < 1e-4 * scale, err           # hi/lo split: ~2^-16 relative per product
+    want_act = F.leaky_relu(out, 0.1)
+    assert (act - want_act).abs().max().item() < 2e-5 * scale      # hi + lo planes carry 16 mantissa bits
+
+
+@pytest.mark.parametrize("shape", TC_CONV_SHAPES[2:5])
+def test_tc_conv_residual_and_scale(shape):
+    out, _, ref = _run_tc_conv(shape, split=1, with_res=True)
+    assert (out - ref).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("shape", [TC_CONV_SHAPES[0], TC_CONV_SHAPES[3], TC_CONV_SHAPES[7]])
+def test_tc_conv_bf16_single_pass(shape):
+    out, _, ref = _run_tc_conv(shape, split=0, with_res=False)
+    # one bf16 rounding per operand: relative error ~2^-8 per product, averaged over the reduction
+    assert (out - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item())
+
+
+@pytest.fixture(scope="module")
+def vocoder_tc():
+    from dict_tts_b200.engine import HifiGanEngine
+    sd = synth.make_vocoder_state_dict(VOCODER_SEED)
+    eng = HifiGanEngine(sd, precision=1)
+    yield eng, fold_weight_norm(sd)
+    eng.close()
+
+
+@pytest.mark.parametrize("name", sorted(VOCODER_CASES))
+def test_tc_vocoder_matches_reference_golden(name, golden_dir, vocoder_tc):
+    eng, _ = vocoder_tc
+    kw = VOCODER_CASES[name]
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))["wav"]
+    wav = eng(synth.make_mel(kw["seed"], kw["B"], kw["T"])).cpu().numpy()
+    rms = float(np.sqrt(np.mean((wav - gold) ** 2)))
+    assert rms < TOL_WAV_RMS, rms
+    assert np.abs(wav - gold).max() < 1e-3
+
+
+def test_tc_vocoder_long_batch_vs_fp32_path(vocoder_tc):
+    """Multi-tile sequences (T = 150 frames -> 38 400 samples) against the exact-fp32 CUDA path and the CPU oracle."""
+    from dict_tts_b200.engine import HifiGanEngine
+    eng, W = vocoder_tc
+    mel = synth.make_mel(31, 3, 150)
+    wav = eng(mel)
+    ref_eng = HifiGanEngine(synth.make_vocoder_state_dict(VOCODER_SEED), precision=0)
+    ref = ref_eng(mel)
+    rms = (wav - ref).pow(2).mean().sqrt().item()
+    assert rms < TOL_WAV_RMS, rms
+    with torch.no_grad():
+        cpu = O.hifigan_forward(W, eng.cfg, mel[:1])
+    assert (wav[:1].cpu() - cpu).pow(2).mean().sqrt().item() < TOL_WAV_RMS
+    ref_eng.close()
+
+
+def test_tc_vocoder_batch_equals_single(vocoder_tc):
+    eng, _ = vocoder_tc
+    mel = synth.make_mel(5, 3, 40)
+    full = eng(mel)
+    for b in range(3):
+        one = eng(mel[b:b + 1])
+        assert torch.equal(one[0], full[b])
+
+
+def test_bf16_vocoder_error_is_bounded():
+    from dict_tts_b200.engine import HifiGanEngine
+    sd = synth.make_vocoder_state_dict(VOCODER_SEED)
+    eng = HifiGanEngine(sd, precision=2)
+    kw = VOCODER_CASES["voc_small"]
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "voc_small.npz"))["wav"]
+    wav = eng(synth.make_mel(kw["seed"], kw["B"], kw["T"])).cpu().numpy()
+    rms = float(np.sqrt(np.mean((wav - gold) ** 2)))
+    assert rms < 5e-3, rms          # measured ~7e-4 on the CPU emulation; NOT within the fp32 tolerance
+    eng.close()
