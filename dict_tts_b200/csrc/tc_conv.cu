@@ -15,9 +15,10 @@ namespace dtts {
 
 namespace {
 
-constexpr int kThreads = 224;
-constexpr int kMaxAStages = 2, kMaxWStages = 4;
-constexpr int kSmemHeader = 1280;            // barriers + tmem ptr (128 B) then bias (<= 256 floats) then pad
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 96 + kEpiWarps * 32;
+constexpr int kMaxAStages = 2, kMaxWStages = 6;
+constexpr int kSmemHeader = 2304;            // barriers + tmem ptr (256 B) then bias (<= 512 floats)
 constexpr int kSmemLimit = 227 * 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -77,7 +78,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
   return d;
 }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -87,32 +88,55 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// One lane of a converged warp (the compiler keeps warp-uniform operands in uniform registers inside the branch).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
-__global__ void __launch_bounds__(kThreads) tc_conv_kernel(const TcConvParams p) {
+// Tile decode: tile -> (time tile, group = nblock*phases + phase, batch)
+struct TileCoord { int q0, g, b; };
+__device__ __forceinline__ TileCoord decode_tile(const TcConvParams& p, int tile) {
+  TileCoord c;
+  const int groups = p.nblocks * p.phases;
+  c.q0 = (tile % p.ntiles) * p.MT;
+  const int r = tile / p.ntiles;
+  c.g = r % groups;
+  c.b = r / groups;
+  return c;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * p.MT;
-  const int g = blockIdx.y;
-  const int b = blockIdx.z;
-  const int phase = g % p.phases, nb = g / p.phases;
   const int N = p.N, KC = p.KC, PL = p.planes;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  // bars[0..1] a_full, [2..3] a_empty, [4..7] w_full, [8..11] w_empty, [12] acc_full
+  // bars: [0..1] a_full, [2..3] a_empty, [4..9] w_full, [10..15] w_empty, [16..17] acc_full, [18..19] acc_empty
   const uint32_t bar0 = smem_u32(bars);
   auto a_full = [&](int s) { return bar0 + 8u * s; };
   auto a_empty = [&](int s) { return bar0 + 8u * (2 + s); };
   auto w_full = [&](int s) { return bar0 + 8u * (4 + s); };
-  auto w_empty = [&](int s) { return bar0 + 8u * (8 + s); };
-  const uint32_t acc_full = bar0 + 8u * 12;
-  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + 112);
-  float* bias_s = reinterpret_cast<float*>(smem + 128);
+  auto w_empty = [&](int s) { return bar0 + 8u * (10 + s); };
+  auto acc_full = [&](int s) { return bar0 + 8u * (16 + s); };
+  auto acc_empty = [&](int s) { return bar0 + 8u * (18 + s); };
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + 192);
+  float* bias_s = reinterpret_cast<float*>(smem + 256);          // [nblocks * N] <= 512 floats
 
   const uint32_t a_plane_bytes = (uint32_t)(KC / 8) * p.RA * 16u;
   const uint32_t a_stage_bytes = a_plane_bytes * PL;
@@ -120,16 +144,17 @@ __global__ void __launch_bounds__(kThreads) tc_conv_kernel(const TcConvParams p)
   const uint32_t w_blob_bytes = w_plane_bytes * PL;
   const uint32_t a_base = smem_u32(smem + kSmemHeader);
   const uint32_t w_base = a_base + p.a_stages * a_stage_bytes;
+  const int total_tiles = p.ntiles * p.nblocks * p.phases * p.B;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxAStages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < kMaxWStages; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
-    mbar_init(acc_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem + 112)),
-                 "r"((uint32_t)p.tmem_cols)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem + 192)),
+                 "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -140,158 +165,207 @@ __global__ void __launch_bounds__(kThreads) tc_conv_kernel(const TcConvParams p)
 
   if (warp == 0) {
     // ------------------------------------------------ activation producer
-    if (lane == 0) {
-      const int slabs = KC / 8;
-      const uint32_t row_bytes = (uint32_t)p.RA * 16u;
-      const size_t row0 = (size_t)(p.a_pad + q0 + p.min_off);
-      for (int c = 0; c < p.nchunks; ++c) {
-        const int s = c % p.a_stages, n = c / p.a_stages;
+    const int slabs = KC / 8;
+    const uint32_t row_bytes = (uint32_t)p.RA * 16u;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      const size_t row0 = (size_t)(p.a_pad + tc.q0 + p.min_off);
+      for (int c = 0; c < p.nchunks; ++c, ++it) {
+        const int s = it % p.a_stages, n = it / p.a_stages;
         mbar_wait(a_empty(s), (n & 1) ^ 1);
-        mbar_arrive_expect_tx(a_full(s), a_stage_bytes);
-        for (int pl = 0; pl < PL; ++pl) {
-          const __nv_bfloat16* src = (pl ? p.a_lo : p.a_hi) + (size_t)b * p.a_bs;
-          for (int sl = 0; sl < slabs; ++sl) {
-            const __nv_bfloat16* gp = src + ((size_t)(c * slabs + sl) * p.a_rows + row0) * 8;
-            bulk_g2s(a_base + s * a_stage_bytes + pl * a_plane_bytes + sl * row_bytes, gp, row_bytes, a_full(s));
+        if (elect_one()) {
+          mbar_arrive_expect_tx(a_full(s), a_stage_bytes);
+          for (int pl = 0; pl < PL; ++pl) {
+            const __nv_bfloat16* src = (pl ? p.a_lo : p.a_hi) + (size_t)tc.b * p.a_bs;
+            for (int sl = 0; sl < slabs; ++sl) {
+              const __nv_bfloat16* gp = src + ((size_t)(c * slabs + sl) * p.a_rows + row0) * 8;
+              bulk_g2s(a_base + s * a_stage_bytes + pl * a_plane_bytes + sl * row_bytes, gp, row_bytes, a_full(s));
+            }
           }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------ weight producer
-    if (lane == 0) {
-      const size_t blob_elems = (size_t)w_blob_bytes / 2;
-      const __nv_bfloat16* wg = p.w + (size_t)g * p.nchunks * p.ktaps * blob_elems;
-      const int total = p.nchunks * p.ktaps;
-      for (int it = 0; it < total; ++it) {
+    const size_t blob_elems = (size_t)w_blob_bytes / 2;
+    const int per_tile = p.nchunks * p.ktaps;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      const __nv_bfloat16* wg = p.w + (size_t)tc.g * per_tile * blob_elems;
+      for (int i = 0; i < per_tile; ++i, ++it) {
         const int s = it % p.w_stages, n = it / p.w_stages;
         mbar_wait(w_empty(s), (n & 1) ^ 1);
-        mbar_arrive_expect_tx(w_full(s), w_blob_bytes);
-        bulk_g2s(w_base + s * w_blob_bytes, wg + (size_t)it * blob_elems, w_blob_bytes, w_full(s));
+        if (elect_one()) {
+          mbar_arrive_expect_tx(w_full(s), w_blob_bytes);
+          bulk_g2s(w_base + s * w_blob_bytes, wg + (size_t)i * blob_elems, w_blob_bytes, w_full(s));
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 2) {
-    // ------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 @17, M>>4 @24
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
-      uint32_t a_lbo = (uint32_t)p.RA * 16u, a_sbo = 128u, b_lbo = (uint32_t)N * 16u, b_sbo = 128u;
-      if (p.variant & 1u) {
-        uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t;
-        t = b_lbo; b_lbo = b_sbo; b_sbo = t;
-      }
-      const int ksteps = KC / 16;
-      int it = 0;
-      for (int c = 0; c < p.nchunks; ++c) {
-        const int sa = c % p.a_stages;
-        mbar_wait(a_full(sa), (c / p.a_stages) & 1);
+    // ------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
+    // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 @17, M>>4 @24
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t a_lbo = (uint32_t)p.RA * 16u, a_sbo = 128u, b_lbo = (uint32_t)N * 16u, b_sbo = 128u;
+    const int ksteps = KC / 16;
+    // descriptors advance by (bytes >> 4) in their low word: +2*RA per K step (two slabs), +128 per accumulator
+    const uint32_t a_kstep = 2u * (uint32_t)p.RA, b_kstep = 2u * (uint32_t)N;
+    const uint32_t a_lo_off = a_plane_bytes >> 4, b_lo_off = w_plane_bytes >> 4;
+    int a_it = 0, w_it = 0, t_it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t_it) {
+      const int as = t_it & 1;
+      mbar_wait(acc_empty(as), ((t_it >> 1) & 1) ^ 1);       // epilogue has drained this accumulator set
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + (uint32_t)(as * 256);
+      for (int c = 0; c < p.nchunks; ++c, ++a_it) {
+        const int sa = a_it % p.a_stages;
+        mbar_wait(a_full(sa), (a_it / p.a_stages) & 1);
         tc_fence_after();
-        const uint32_t a_stage = a_base + sa * a_stage_bytes;
-        for (int j = 0; j < p.ktaps; ++j, ++it) {
-          const int sw = it % p.w_stages;
-          mbar_wait(w_full(sw), (it / p.w_stages) & 1);
+        const uint64_t a_stage_desc = make_desc(a_base + sa * a_stage_bytes, a_lbo, a_sbo);
+        for (int j = 0; j < p.ktaps; ++j, ++w_it) {
+          const int sw = w_it % p.w_stages;
+          mbar_wait(w_full(sw), (w_it / p.w_stages) & 1);
           tc_fence_after();
-          const uint32_t w_stage = w_base + sw * w_blob_bytes;
-          const uint32_t row_off = (uint32_t)(p.tap_off0 + j * p.tap_step - p.min_off);
-          for (int m = 0; m < p.NACC; ++m) {
-            const uint32_t d = tmem_base + (uint32_t)(m * N);
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint32_t a_addr = a_stage + (uint32_t)(2 * ks) * (uint32_t)p.RA * 16u + (m * 128u + row_off) * 16u;
-              const uint32_t b_addr = w_stage + (uint32_t)(2 * ks) * (uint32_t)N * 16u;
-              const uint64_t a_hi = make_desc(a_addr, a_lbo, a_sbo);
-              const uint64_t b_hi = make_desc(b_addr, b_lbo, b_sbo);
-              const uint32_t acc = (c | j | ks) != 0 ? 1u : 0u;
-              umma_bf16(d, a_hi, b_hi, idesc, acc);
-              if (PL == 2) {
-                const uint64_t a_lo = make_desc(a_addr + a_plane_bytes, a_lbo, a_sbo);
-                const uint64_t b_lo = make_desc(b_addr + w_plane_bytes, b_lbo, b_sbo);
-                umma_bf16(d, a_hi, b_lo, idesc, 1u);
-                umma_bf16(d, a_lo, b_hi, idesc, 1u);
+          if (elect_one()) {
+            const uint64_t b_desc0 = make_desc(w_base + sw * w_blob_bytes, b_lbo, b_sbo);
+            const uint64_t a_desc0 = a_stage_desc + (uint32_t)(p.tap_off0 + j * p.tap_step - p.min_off);
+            for (int m = 0; m < p.NACC; ++m) {
+              const uint32_t d = d_base + (uint32_t)(m * N);
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint64_t a_hi = a_desc0 + (uint32_t)(m * 128) + ks * a_kstep;
+                const uint64_t b_hi = b_desc0 + ks * b_kstep;
+                umma_bf16(d, a_hi, b_hi, idesc, (c | j | ks) != 0 ? 1u : 0u);
+                if (PL == 2) {
+                  umma_bf16(d, a_hi, b_hi + b_lo_off, idesc, 1u);
+                  umma_bf16(d, a_hi + a_lo_off, b_hi, idesc, 1u);
+                }
               }
             }
+            umma_commit(w_empty(sw));     // weight slot free once these MMAs have read it
+            if (j == p.ktaps - 1) {
+              umma_commit(a_empty(sa));
+              if (c == p.nchunks - 1) umma_commit(acc_full(as));
+            }
           }
-          umma_commit(w_empty(sw));     // weight slot free once these MMAs have read it
+          __syncwarp();
         }
-        umma_commit(a_empty(sa));
       }
-      umma_commit(acc_full);
     }
   } else {
-    // ------------------------------------------------ epilogue (warps 3..6)
-    const int et = threadIdx.x - 96;                 // 0..127
+    // ------------------------------------------------ epilogue (warps 3..10; two warps per TMEM lane quadrant)
+    const int et = threadIdx.x - 96;                 // 0..255
     const int quad = warp & 3;                       // TMEM lanes [32*quad, 32*quad+32) are visible to this warp
-    const int co_off = nb * N;
-    for (int i = et; i < N; i += 128) bias_s[i] = p.bias ? __ldg(p.bias + co_off + i) : 0.f;
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
+    const int half = (warp - 3) >> 2;
+    const int nbias = N * p.nblocks;
+    for (int i = et; i < nbias; i += kEpiWarps * 32) bias_s[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     const bool split = PL == 2;
-    for (int m = 0; m < p.NACC; ++m) {
-      const int q = q0 + m * 128 + quad * 32 + lane;
-      const int t = q * p.ot_mul + p.ot_add + phase;
-      const bool ok = q < p.nq && t >= 0 && t < p.T_out;
-      for (int cc = 0; cc < N / 32; ++cc) {
+    const int ncc = N / 32;
+    const int nitems = p.NACC * ncc;
+    int t_it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t_it) {
+      const TileCoord tc = decode_tile(p, tile);
+      const int phase = tc.g % p.phases, co_off = (tc.g / p.phases) * N;
+      const int as = t_it & 1;
+      const float* resb = p.res ? p.res + (size_t)tc.b * p.o32_bs : nullptr;
+      float* o32b = p.o32 ? p.o32 + (size_t)tc.b * p.o32_bs : nullptr;
+
+      // residual prefetch of the first item (overlaps the tail of this tile's MMAs)
+      float4 rc[8];
+      auto item_row = [&](int idx, int& t, bool& ok) {
+        const int m = idx / ncc;
+        const int q = tc.q0 + m * 128 + quad * 32 + lane;
+        t = q * p.ot_mul + p.ot_add + phase;
+        ok = q < p.nq && t >= 0 && t < p.T_out;
+      };
+      auto load_res = [&](int idx, float4 (&dst)[8]) {
+        int t; bool ok;
+        item_row(idx, t, ok);
+        if (resb && ok) {
+          const int n0 = co_off + (idx % ncc) * 32;
+          const float4* rp = reinterpret_cast<const float4*>(resb) + ((size_t)(n0 / 4) * p.T_out + t);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) dst[k] = rp[(size_t)k * p.T_out];   // may alias o32 (in-place y += conv)
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      if (half < nitems) load_res(half, rc);
+
+      mbar_wait(acc_full(as), (t_it >> 1) & 1);
+      tc_fence_after();
+      for (int idx = half; idx < nitems; idx += 2) {
+        const int m = idx / ncc, cc = idx % ncc;
+        int t; bool ok;
+        item_row(idx, t, ok);
         uint32_t r[32];
-        __syncwarp();                                  // tcgen05.ld is .sync.aligned: reconverge after the guarded stores
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(m * N + cc * 32), r);
-        if (!ok) continue;
-        const int n0 = co_off + cc * 32;
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + bias_s[cc * 32 + i];
-        if (p.res) {
-          const float4* rp = reinterpret_cast<const float4*>(p.res + (size_t)b * p.o32_bs) +
-                             ((size_t)(n0 / 4) * p.T_out + t);
+        __syncwarp();                                  // tcgen05.ld is .sync.aligned
+        tmem_ld32_nowait(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256 + m * N + cc * 32), r);
+        float4 rn[8];
+        if (idx + 2 < nitems) load_res(idx + 2, rn);   // next item's residual is in flight while this one is processed
+        tmem_ld_wait();
+        if (ok) {
+          const int n0 = co_off + cc * 32;
+          float v[32];
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            const float4 x = rp[(size_t)k * p.T_out];   // may alias o32 (in-place y += conv)
-            v[4 * k] += x.x; v[4 * k + 1] += x.y; v[4 * k + 2] += x.z; v[4 * k + 3] += x.w;
+            v[4 * k] = (__uint_as_float(r[4 * k]) + bias_s[n0 + 4 * k] + rc[k].x) * p.post;
+            v[4 * k + 1] = (__uint_as_float(r[4 * k + 1]) + bias_s[n0 + 4 * k + 1] + rc[k].y) * p.post;
+            v[4 * k + 2] = (__uint_as_float(r[4 * k + 2]) + bias_s[n0 + 4 * k + 2] + rc[k].z) * p.post;
+            v[4 * k + 3] = (__uint_as_float(r[4 * k + 3]) + bias_s[n0 + 4 * k + 3] + rc[k].w) * p.post;
           }
-        }
-        if (p.post != 1.f) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] *= p.post;
-        }
-        if (p.o32) {
-          float4* op = reinterpret_cast<float4*>(p.o32 + (size_t)b * p.o32_bs) + ((size_t)(n0 / 4) * p.T_out + t);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            float4 x;
+          if (o32b) {
+            float4* op = reinterpret_cast<float4*>(o32b) + ((size_t)(n0 / 4) * p.T_out + t);
             if (p.accumulate) {
-              x = op[(size_t)k * p.T_out];
-              v[4 * k] += x.x; v[4 * k + 1] += x.y; v[4 * k + 2] += x.z; v[4 * k + 3] += x.w;
+              float4 old[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) old[k] = op[(size_t)k * p.T_out];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                v[4 * k] += old[k].x; v[4 * k + 1] += old[k].y; v[4 * k + 2] += old[k].z; v[4 * k + 3] += old[k].w;
+              }
             }
-            x.x = v[4 * k]; x.y = v[4 * k + 1]; x.z = v[4 * k + 2]; x.w = v[4 * k + 3];
-            op[(size_t)k * p.T_out] = x;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              op[(size_t)k * p.T_out] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          }
+          if (p.o_hi) {
+            const size_t prow = (size_t)tc.b * p.op_bs + ((size_t)(n0 / 8) * p.op_rows + p.op_pad + t) * 8;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float a0 = leaky(v[8 * h + 2 * e], p.slope), a1 = leaky(v[8 * h + 2 * e + 1], p.slope);
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
+                hw[e] = pack_bf16(h0, h1);
+                lw[e] = pack_bf16(__float2bfloat16_rn(a0 - __bfloat162float(h0)),
+                                  __float2bfloat16_rn(a1 - __bfloat162float(h1)));
+              }
+              const size_t off = prow + (size_t)h * p.op_rows * 8;
+              *reinterpret_cast<uint4*>(p.o_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              if (split) *reinterpret_cast<uint4*>(p.o_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
           }
         }
-        if (p.o_hi) {
-          const size_t prow = (size_t)b * p.op_bs + ((size_t)(n0 / 8) * p.op_rows + p.op_pad + t) * 8;
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            uint32_t hw[4], lw[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float a0 = leaky(v[8 * h + 2 * e], p.slope), a1 = leaky(v[8 * h + 2 * e + 1], p.slope);
-              const __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
-              hw[e] = pack_bf16(h0, h1);
-              lw[e] = pack_bf16(__float2bfloat16_rn(a0 - __bfloat162float(h0)),
-                                __float2bfloat16_rn(a1 - __bfloat162float(h1)));
-            }
-            const size_t off = prow + (size_t)h * p.op_rows * 8;
-            *reinterpret_cast<uint4*>(p.o_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            if (split) *reinterpret_cast<uint4*>(p.o_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-          }
-        }
+        for (int k = 0; k < 8; ++k) rc[k] = rn[k];
       }
+      // this warp no longer reads accumulator set `as`
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(as));
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
-                 : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -435,51 +509,58 @@ void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq) {
   p->C_in = w.C_in; p->N = w.N; p->KC = w.KC; p->nchunks = w.C_in / w.KC; p->ktaps = w.ktaps;
   p->planes = w.planes; p->nblocks = w.C_out / w.N; p->phases = w.phases;
   p->nq = nq;
-  int nacc = 512 / w.N;
+  int nacc = 256 / w.N;                                      // one accumulator set = 256 TMEM columns (two sets)
   if (nacc > 4) nacc = 4;
   const int force = env_int("DTTS_TC_NACC", 0);
   if (force > 0 && force <= nacc) nacc = force;
   while (nacc > 1 && (nacc - 1) * 128 >= nq) --nacc;         // short sequences: do not compute empty sub-tiles
   p->NACC = nacc;
   p->MT = 128 * nacc;
+  p->ntiles = cdiv(nq, p->MT);
   const int o0 = p->tap_off0, o1 = p->tap_off0 + (p->ktaps - 1) * p->tap_step;
   p->min_off = o0 < o1 ? o0 : o1;
   const int max_off = o0 < o1 ? o1 : o0;
   p->RA = p->MT + (max_off - p->min_off);
-  int cols = 32;
-  while (cols < nacc * w.N) cols <<= 1;
-  p->tmem_cols = cols;
-  p->a_stages = p->nchunks > 1 ? 2 : 1;
+  p->a_stages = kMaxAStages;
   const size_t a_stage = (size_t)(p->KC / 8) * p->RA * 16 * p->planes;
   const size_t w_blob = (size_t)p->N * p->KC * 2 * p->planes;
-  size_t budget = kSmemLimit - kSmemHeader - p->a_stages * a_stage;
+  const size_t budget = kSmemLimit - kSmemHeader - p->a_stages * a_stage;
   int ws = (int)(budget / w_blob);
   if (ws > kMaxWStages) ws = kMaxWStages;
-  const int total = p->nchunks * p->ktaps;
-  if (ws > total) ws = total;
+  const int force_ws = env_int("DTTS_TC_WSTAGES", 0);
+  if (force_ws > 0 && force_ws < ws) ws = force_ws;
   p->w_stages = ws;
-  p->variant = (unsigned)env_int("DTTS_TC_VARIANT", 0);
 }
 
 static size_t tc_smem_bytes(const TcConvParams& p) {
   const size_t a_stage = (size_t)(p.KC / 8) * p.RA * 16 * p.planes;
   const size_t w_blob = (size_t)p.N * p.KC * 2 * p.planes;
   size_t bytes = kSmemHeader + p.a_stages * a_stage + p.w_stages * w_blob;
-  // a CTA that owns all 512 TMEM columns must be alone on its SM, otherwise a co-resident CTA would block in alloc
-  if (p.tmem_cols > 256 && bytes < 116 * 1024) bytes = 116 * 1024;
+  // the CTA owns all 512 TMEM columns: it must be alone on its SM, or a co-resident CTA would block in tcgen05.alloc
+  if (bytes < 116 * 1024) bytes = 116 * 1024;
   return bytes;
 }
 
+static int g_num_sms = 0;
+
 cudaError_t launch_tc_conv(TcConvParams p, int B, cudaStream_t stream) {
   if (B <= 0 || p.nq <= 0) return cudaSuccess;
-  if (p.w_stages < 1 || p.N % 32 != 0 || p.N > 256 || p.KC % 16 != 0 || p.C_in % p.KC != 0 || p.N > 256)
+  if (p.w_stages < 1 || p.N % 32 != 0 || p.N > 256 || p.KC % 16 != 0 || p.C_in % p.KC != 0 ||
+      p.N * p.nblocks > 512 || p.NACC * p.N > 256)
     return cudaErrorInvalidConfiguration;
-  const int ntiles = cdiv(p.nq, p.MT);
   const int max_off = p.min_off + (p.RA - p.MT);
-  if (p.a_pad + p.min_off < 0 || p.a_pad + ntiles * p.MT + max_off > p.a_rows) return cudaErrorInvalidValue;
+  if (p.a_pad + p.min_off < 0 || p.a_pad + p.ntiles * p.MT + max_off > p.a_rows) return cudaErrorInvalidValue;
   const size_t smem = tc_smem_bytes(p);
   if (smem > (size_t)kSmemLimit) return cudaErrorInvalidConfiguration;
-  dim3 grid(ntiles, p.nblocks * p.phases, B);
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+  }
+  p.B = B;
+  const long total = (long)p.ntiles * p.nblocks * p.phases * B;
+  const int grid = (int)(total < g_num_sms ? total : g_num_sms);       // persistent: one CTA per SM
   tc_conv_kernel<<<grid, kThreads, smem, stream>>>(p);
   return cudaGetLastError();
 }

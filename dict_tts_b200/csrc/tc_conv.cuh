@@ -62,8 +62,8 @@ struct TcConvParams {
   int op_rows, op_pad;
   float post, slope;
   int accumulate;
-  int a_stages, w_stages, tmem_cols;
-  unsigned variant;              // debug knob: bit0 swaps LBO/SBO in the descriptors
+  int a_stages, w_stages;
+  int ntiles, B;                 // time tiles per (group, batch item); batch size (set by the launcher)
 };
 
 // Launch plan / launcher.  `split` = 1: hi/lo planes (3 MMAs), 0: single bf16 plane.
