@@ -1,0 +1,191 @@
+"""Standalone inference task: what ``tasks/run.py --infer`` does for ``DictTTSTask`` in the reference, without the
+training stack (Trainer / DDP / TensorBoard / matplotlib).
+
+Flow mirrored:
+  start()       Trainer.test -> fit -> build_model -> restore newest checkpoint     utils/trainer.py:90-120
+  test_start()  gen dir, vocoder = get_vocoder_cls(hparams)(), fold weight-norm     tts_base.py:247-254, ps_flow.py:257
+  test_step()   model(...) with the reference's argument tuple                      dict_tts.py:179-196
+  after_infer() spec2wav, int16 wav, argmax(pron_attn) -> pinyin tokens             dict_tts.py:227-311
+  test_end()    meta.csv                                                            tts_base.py:371-376
+Differences, all on purpose: utterances are batched (``max_sentences``), the mel stays on the device between the
+acoustic model and the vocoder, and with several GPUs every rank owns ``batches[rank::world]`` and receives the
+weights through one NCCL broadcast.
+"""
+import csv
+import importlib
+import os
+import pickle
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import hparams as hp_mod
+from .config import AcousticConfig, VocoderConfig
+from .data import DictTTSTestSet
+from .engine import DictTTSEngine, HifiGanEngine
+from .weights import load_acoustic_checkpoint, load_vocoder_checkpoint, pack_arena
+
+
+def get_vocoder_cls(hp):
+    """Name registry + dotted-path import, as vocoders/base_vocoder.py:15-23."""
+    name = hp.get("vocoder", "HifiGAN")
+    if name in ("HifiGAN", "hifigan", "vocoders.hifigan.HifiGAN", "B200HifiGAN"):
+        from .plugin import B200HifiGAN
+        return B200HifiGAN
+    pkg, cls = name.rsplit(".", 1)
+    return getattr(importlib.import_module(pkg), cls)
+
+
+def save_wav(wav: np.ndarray, path: str, sr: int, norm: bool = False) -> None:
+    """utils/audio.py:11-16: optional peak normalisation, x32767, int16 PCM."""
+    from scipy.io import wavfile
+    wav = np.asarray(wav, dtype=np.float32)
+    if norm:
+        wav = wav / np.abs(wav).max()
+    wavfile.write(path, sr, (wav * 32767).astype(np.int16))
+
+
+def broadcast_arena(host_arena: Optional[torch.Tensor], numel: int, device, rank: int, world: int) -> torch.Tensor:
+    """Rank 0 holds the packed weights; everyone leaves with a device copy (one collective)."""
+    import torch.distributed as dist
+    if world == 1:
+        return host_arena.to(device)
+    buf = host_arena.to(device) if rank == 0 else torch.empty(numel, dtype=torch.float32, device=device)
+    dist.broadcast(buf, 0)
+    return buf
+
+
+class B200DictTTSTask:
+    def __init__(self, hp: Optional[Dict] = None, device: str = "cuda:0", rank: int = 0, world: int = 1):
+        self.hp = hp if hp is not None else hp_mod.hparams
+        self.device, self.rank, self.world = device, rank, world
+        self.model: Optional[DictTTSEngine] = None
+        self.vocoder = None
+        self.global_step = 0
+        self.results: List[Dict] = []
+
+    # ---- reference entry point: task_cls.start() (tasks/base_task.py:318-352, --infer branch) -------------------
+    @classmethod
+    def start(cls):
+        hp = hp_mod.hparams
+        if not hp.get("infer", True):
+            raise SystemExit("dict_tts_b200 implements the --infer path only")
+        if not torch.cuda.is_available():
+            raise RuntimeError("B200DictTTSTask needs a CUDA device (sm_100a); there is no CPU fallback")
+        rank = int(os.environ.get("RANK", "0"))
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        if world > 1:
+            import torch.distributed as dist
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        task = cls(hp, f"cuda:{local}", rank, world)
+        task.build_model()
+        task.test_start()
+        outputs = []
+        ds = DictTTSTestSet(hp, hp.get("test_set_name", "test"))
+        bs = int(hp.get("b200_max_sentences", hp.get("max_valid_sentences", 1)) or 1)
+        for i, batch in enumerate(ds.batches(bs, rank, world)):
+            outputs.extend(task.test_step(batch, i))
+        task.test_end(outputs)
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
+        return outputs
+
+    # ---- build_model + restore_weights ---------------------------------------------------------------------------
+    def build_model(self):
+        import torch.distributed as dist
+        hp, rank, world = self.hp, self.rank, self.world
+        acfg = AcousticConfig.from_hparams(hp)
+        meta = [None]
+        arena = None
+        if rank == 0:
+            sd, self.global_step = load_acoustic_checkpoint(hp["work_dir"], with_step=True)
+            arena, table = pack_arena(sd)
+            meta = [(table, arena.numel(), self.global_step)]
+        if world > 1:
+            dist.broadcast_object_list(meta, 0)
+        table, numel, self.global_step = meta[0]
+        dev_arena = broadcast_arena(arena, numel, self.device, rank, world)
+        self.model = DictTTSEngine(None, acfg, self.device, arena=dev_arena, table=table)
+        return self.model
+
+    def test_start(self):
+        hp = self.hp
+        self.gen_dir = os.path.join(hp["work_dir"], f'generated_{self.global_step}_{hp.get("gen_dir_name", "")}')
+        os.makedirs(os.path.join(self.gen_dir, "wavs"), exist_ok=True)
+        cls = get_vocoder_cls(hp)
+        self.vocoder = cls(device=self.device) if cls.__name__ == "B200HifiGAN" else cls()
+        path = os.path.join(hp["binary_data_dir"], "pinyin_encoder.pkl")
+        self.pinyin_encoder = None
+        if os.path.exists(path):
+            with open(path, "rb") as f:
+                self.pinyin_encoder = pickle.load(f)
+        self.results_id = 0
+
+    def run_model(self, sample: Dict) -> Dict:
+        """The exact call of DictTTSTask.test_step (dict_tts.py:183-196)."""
+        hp = self.hp
+        return self.model(
+            (sample["word_tokens"], sample["txt_tokens"]), sample.get("pron_modified"), (None, None, None),
+            ph2word=sample.get("ph2word"), word_len=sample["word_lengths"].max(),
+            dict_msg=(sample["keys"], sample["values"], sample["key_map"], sample["pinyin"], sample["pinyin_map"]),
+            infer=True, forward_post_glow=False, spk_embed=None, two_stage=hp.get("two_stage", True),
+            mel2word=sample["mel2word"] if hp.get("profile_infer", False) else None)
+
+    @torch.no_grad()
+    def test_step(self, sample: Dict, batch_idx: int) -> List[Dict]:
+        out = self.run_model(sample)
+        sample["outputs"] = out["mel_out"]
+        sample["pron_attn"] = out["pron_attn"]
+        sample["mel2word_pred"] = out["mel2word"]
+        return self.after_infer(sample)
+
+    def after_infer(self, sample: Dict) -> List[Dict]:
+        hp = self.hp
+        mel = sample["outputs"]                                   # [B,T,80] on the device
+        B = mel.shape[0]
+        hop = hp.get("hop_size", 256)
+        if hasattr(self.vocoder, "spec2wav_batch"):
+            wav = self.vocoder.spec2wav_batch(mel)                # [B, T*hop], mel never leaves HBM
+            wav = wav.cpu().numpy()
+        else:
+            wav = np.stack([self.vocoder.spec2wav(mel[b].cpu().numpy()) for b in range(B)])
+        frames = (sample["mel2word_pred"] > 0).sum(-1).cpu().numpy()      # valid frames per utterance
+        pron_attn = sample["pron_attn"].cpu()
+        results = []
+        for b in range(B):
+            name, text = sample["item_name"][b], sample["text"][b]
+            base_fn = f'[{self.rank}_{self.results_id:06d}][{str(name).replace("%", "_")}][%s]'
+            if text is not None:
+                base_fn += str(text).replace(":", "$3A")[:80]
+            base_fn = base_fn.replace(" ", "_")
+            n = int(frames[b]) * hop if B > 1 else wav.shape[1]   # B=1: keep the padded tail like the reference
+            if not hp.get("profile_infer", False):
+                save_wav(wav[b, :n], os.path.join(self.gen_dir, "wavs", (base_fn % "P") + ".wav"),
+                         hp.get("audio_sample_rate", 22050), norm=hp.get("out_wav_norm", False))
+            # dict_tts.py:295-304: two pinyin tokens per character from argmax(pron_attn)
+            tokens = []
+            if self.pinyin_encoder is not None:
+                n_words = int(sample["word_lengths"][b])
+                idx = pron_attn[b].max(-1)[1]
+                pin = sample["pinyin"][b]
+                for i in range(1, n_words - 1):
+                    for t in pin[i][idx[i]:idx[i] + 2]:
+                        tokens.append(self.pinyin_encoder[int(t)])
+            results.append(dict(item_name=name, text=None if text is None else str(text).replace(",", "，").replace(".", "。"),
+                                pinyin_tokens=" ".join(tokens), wav_fn_pred=base_fn % "P", wav_fn_gt=base_fn % "G"))
+            self.results_id += 1
+        return results
+
+    def test_end(self, outputs: List[Dict]):
+        path = os.path.join(self.gen_dir, "meta.csv" if self.world == 1 else f"meta.rank{self.rank}.csv")
+        with open(path, "w", newline="") as f:
+            w = csv.DictWriter(f, fieldnames=["item_name", "text", "pinyin_tokens", "wav_fn_pred", "wav_fn_gt"])
+            w.writeheader()
+            for r in outputs:
+                w.writerow(r)
+        return {}

@@ -64,11 +64,14 @@ def get_last_checkpoint(work_dir: str):
     return ckpt, paths[0]
 
 
-def load_acoustic_checkpoint(work_dir: str) -> Dict[str, torch.Tensor]:
+def load_acoustic_checkpoint(work_dir: str, with_step: bool = False):
+    """Newest checkpoint of an experiment -> live, weight-norm-folded ``model`` tensors (the ``mel_disc`` child and the
+    train-only parameters are dropped).  ``with_step``: also return ``global_step`` (names the output directory)."""
     ckpt, path = get_last_checkpoint(work_dir)
     if ckpt is None:
         raise FileNotFoundError(f"no model_ckpt_steps_*.ckpt under {work_dir}")
-    return drop_dead(fold_weight_norm(ckpt["state_dict"]["model"]))
+    sd = drop_dead(fold_weight_norm(ckpt["state_dict"]["model"]))
+    return (sd, int(ckpt.get("global_step", 0))) if with_step else sd
 
 
 def load_vocoder_checkpoint(base_dir: str):

@@ -1,0 +1,102 @@
+"""GPU suite (-m gpu) for the drop-in seams: the ``--infer`` entry point on a fabricated experiment tree in the
+reference's on-disk formats, and the ``BaseVocoder.spec2wav`` plugin class."""
+import csv
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from dict_tts_b200 import fake_exp, hparams as hp_mod, synth
+from dict_tts_b200.config import AcousticConfig, VocoderConfig
+from dict_tts_b200.data import DictTTSTestSet
+from dict_tts_b200.weights import fold_weight_norm
+from oracle import dtts_oracle as O
+from tests.cases import TOL_MEL_MAXABS, TOL_WAV_RMS, VOCODER_CASES
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def exp(tmp_path_factory):
+    return fake_exp.write(str(tmp_path_factory.mktemp("exp")), n_items=5)
+
+
+def _read_wav(path):
+    from scipy.io import wavfile
+    sr, pcm = wavfile.read(path)
+    return sr, pcm
+
+
+@pytest.mark.parametrize("max_sentences", [1, 3])
+def test_infer_entry_point_writes_reference_outputs(exp, max_sentences):
+    from dict_tts_b200 import run
+    cwd = os.getcwd()
+    os.chdir(exp["root"])
+    try:
+        torch.manual_seed(1234)
+        results = run.main(["--exp_name", exp["exp"], "--infer", "--hparams",
+                            f"b200_max_sentences={max_sentences},gen_dir_name=bs{max_sentences}"])
+    finally:
+        os.chdir(cwd)
+    gen = os.path.join(exp["work_dir"], f"generated_3000_bs{max_sentences}")
+    with open(os.path.join(gen, "meta.csv")) as f:
+        rows = list(csv.DictReader(f))
+    assert len(rows) == len(results) == exp["n_items"]
+    assert sorted(r["item_name"] for r in rows) == sorted(f"fake_{i:03d}" for i in range(exp["n_items"]))
+    for r in rows:
+        sr, pcm = _read_wav(os.path.join(gen, "wavs", r["wav_fn_pred"] + ".wav"))
+        assert sr == 22050 and pcm.dtype == np.int16 and len(pcm) > 0 and len(pcm) % 256 == 0
+        n_chars = len(r["text"])
+        assert len(r["pinyin_tokens"].split()) == 2 * n_chars          # two pinyin tokens per character
+
+
+def test_task_step_matches_oracle(exp):
+    """One batched test_step of the standalone task == oracle forward on the same collated batch (predicted durations)."""
+    from dict_tts_b200.task import B200DictTTSTask
+    hp = hp_mod.set_hparams("", exp["exp"], "", root=exp["root"], global_hparams=False)
+    hp["work_dir"] = exp["work_dir"]
+    task = B200DictTTSTask(hp)
+    task.build_model()
+    batch = next(DictTTSTestSet(hp).batches(3))
+    B, Tw = batch["word_tokens"].shape
+    W = fold_weight_norm(synth.make_acoustic_state_dict(1234))
+    torch.manual_seed(7)
+    out = task.run_model(batch)
+    T = out["mel_out"].shape[1]
+    torch.manual_seed(7)
+    z = torch.distributions.Normal(0, 1).sample([B, 16, T // 4])
+    with torch.no_grad():
+        ref = O.acoustic_forward(W, AcousticConfig(), batch, None, z)
+    assert torch.equal(out["mel2word"].cpu(), ref["mel2word"])
+    assert (out["mel_out"].cpu() - ref["mel_out"]).abs().max() < TOL_MEL_MAXABS
+    assert (out["pron_attn"].cpu() - ref["pron_attn"]).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("name", sorted(VOCODER_CASES))
+def test_vocoder_plugin_spec2wav(name, golden_dir):
+    from dict_tts_b200.plugin import B200HifiGAN
+    voc = B200HifiGAN(state_dict=synth.make_vocoder_state_dict(4321), config=None)
+    kw = VOCODER_CASES[name]
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))["wav"]
+    mel = synth.make_mel(kw["seed"], kw["B"], kw["T"])
+    wav = voc.spec2wav(mel[0].numpy())                    # ndarray [T,80] in, ndarray [T*256] out (hifigan.py:54-62)
+    assert isinstance(wav, np.ndarray) and wav.dtype == np.float32 and wav.shape == (kw["T"] * 256,)
+    assert float(np.sqrt(np.mean((wav - gold[0]) ** 2))) < TOL_WAV_RMS
+    batch = voc.spec2wav_batch(mel.cuda())
+    assert batch.is_cuda and batch.shape == (kw["B"], kw["T"] * 256)
+    assert float(np.sqrt(np.mean((batch.cpu().numpy() - gold) ** 2))) < TOL_WAV_RMS
+    with pytest.raises(ValueError):
+        voc.spec2wav(mel.numpy())                         # a batch is not one utterance
+
+
+def test_vocoder_plugin_from_checkpoint_dir(exp):
+    from dict_tts_b200.plugin import B200HifiGAN
+    hp_mod.hparams.clear()
+    hp_mod.hparams.update(exp["hparams"])
+    voc = B200HifiGAN()
+    mel = synth.make_mel(3, 1, 20)
+    wav = voc.spec2wav(mel[0])
+    with torch.no_grad():
+        ref = O.hifigan_forward(fold_weight_norm(synth.make_vocoder_state_dict(4321)), VocoderConfig(), mel)
+    assert float((torch.from_numpy(wav) - ref[0]).pow(2).mean().sqrt()) < TOL_WAV_RMS
