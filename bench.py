@@ -254,14 +254,17 @@ def main():
 
     peaks = load_peaks()
     dtype = {0: "f32", 1: "f32 (vocoder convs: bf16x3 split on tcgen05, fp32 accumulate)",
-             2: "bf16 vocoder convs (tcgen05), f32 elsewhere"}[args.vocoder_precision]
+             2: "bf16 vocoder convs (tcgen05), f32 elsewhere",
+             3: "f32 (vocoder convs: fp16 activations x fp16 hi/lo weights on tcgen05, fp32 accumulate)",
+             4: "fp16 vocoder convs (tcgen05), f32 elsewhere"}[args.vocoder_precision]
     config["vocoder_precision"] = args.vocoder_precision
     voc_s = stage_ms["vocode"] / 1e3
     padded_frames = WORKLOAD["B"] * WORKLOAD["max_frames"]           # the vocoder computes padded frames too
     achieved = padded_frames * VOCODER_FLOP_PER_FRAME / voc_s / 1e12
     n_voc_launch = 1 + 4 + 72 + (1 if args.vocoder_precision == 0 else 0)   # conv_post is a separate CUDA-core kernel on the TC path
-    kname = {0: "conv1d_f32_kernel (fp32 FMA pipe)", 1: "tc_conv_kernel (tcgen05, split bf16 hi/lo: 3 MMAs per product)",
-             2: "tc_conv_kernel (tcgen05, single bf16)"}[args.vocoder_precision]
+    kname = {0: "conv1d_f32_kernel (fp32 FMA pipe)", 1: "tc_conv_kernel (tcgen05, bf16 hi/lo x hi/lo: 3 MMAs per product)",
+             2: "tc_conv_kernel (tcgen05, bf16: 1 MMA)", 3: "tc_conv_kernel (tcgen05, fp16 x fp16 hi/lo weights: 2 MMAs)",
+             4: "tc_conv_kernel (tcgen05, fp16: 1 MMA)"}[args.vocoder_precision]
     roofline = dict(bound="tensor", kernel="%s, HiFi-GAN stack, %d launches/step" % (kname, n_voc_launch),
                     achieved=achieved, peak=peaks["tflops"], unit="TFLOP/s", frac=achieved / peaks["tflops"],
                     traffic=None, peak_source=peaks["source"] + " bf16 dense (sustained)",

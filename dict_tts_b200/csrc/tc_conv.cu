@@ -7,6 +7,12 @@
 //   warps 3..6       epilogue: tcgen05.ld -> bias / residual / mean scaling -> fp32 stream + leaky-ReLU'd bf16 hi/lo planes
 // Pipelines: a_full/a_empty (activation stages), w_full/w_empty (weight stages), acc_full (MMA -> epilogue); the
 // shared-memory slots are released by tcgen05.commit.
+//
+// Thread-block clusters: the CTAs of a cluster work on consecutive time tiles of the SAME weight group in lockstep,
+// so every weight blob is fetched from L2 once per cluster: CTA r loads slice r of the blob and multicasts it into the
+// shared memory of all its peers (cp.async.bulk ... .multicast::cluster); a weight slot is re-filled only after the
+// MMA warps of ALL peers have released it (tcgen05.commit ... .multicast::cluster onto every peer's w_empty barrier).
+// Without this the weight stream (C_out*C_in*K*2 B per 128-row tile) makes the big layers L2-bandwidth bound.
 #include "tc_conv.cuh"
 
 #include <cstdlib>
@@ -64,19 +70,33 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// arrives on the barrier at the same shared-memory offset in every CTA of the cluster named by mask
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// Shared-memory matrix descriptor, no swizzle, K-major: core matrix = 8 rows x 16 B stored contiguously (128 B);
-// LBO = byte distance between the two 16-byte K halves of one MMA, SBO = byte distance between 8-row groups.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
-  d |= 1ull << 46;  // descriptor version 1 (sm_100)
-  return d;
-}
+// Shared-memory matrix descriptors are no-swizzle, K-major: core matrix = 8 rows x 16 B stored contiguously (128 B);
+// LBO = byte distance between the two 16-byte K halves of one MMA, SBO = byte distance between 8-row groups
+// (bits 0-13 start >> 4, 16-29 LBO >> 4, 32-45 SBO >> 4, bit 46 = descriptor version 1 on sm_100).
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -105,26 +125,64 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
-  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+// fp32 -> 16-bit operand (fmt 0: fp16, saturated to the finite range; 1: bf16), round to nearest even, and back.
+__device__ __forceinline__ uint32_t cvt16(float v, int fmt) {
+  if (fmt) return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  return __half_as_ushort(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)));
+}
+__device__ __forceinline__ float back16(uint32_t h, int fmt) {
+  if (fmt) return __bfloat162float(__ushort_as_bfloat16((unsigned short)h));
+  return __half2float(__ushort_as_half((unsigned short)h));
+}
+// two consecutive channels -> packed hi word and (residual) lo word
+__device__ __forceinline__ void split2(float a0, float a1, int fmt, uint32_t& hw, uint32_t& lw) {
+  const uint32_t h0 = cvt16(a0, fmt), h1 = cvt16(a1, fmt);
+  hw = h0 | (h1 << 16);
+  lw = cvt16(a0 - back16(h0, fmt), fmt) | (cvt16(a1 - back16(h1, fmt), fmt) << 16);
 }
 
-// Tile decode: tile -> (time tile, group = nblock*phases + phase, batch)
-struct TileCoord { int q0, g, b; };
-__device__ __forceinline__ TileCoord decode_tile(const TcConvParams& p, int tile) {
+// Work decode.  A unit = csize consecutive row tiles (row tile rt = b * ntiles + time tile) of one weight group
+// g = nblock*phases + phase; the CTA of cluster rank r takes row tile (unit % nu) * csize + r.  Row tiles past the end
+// are dummies: they follow the weight pipeline (the peers depend on it) but issue no MMAs and store nothing.
+struct TileCoord { int q0, g, b; bool dummy; };
+__device__ __forceinline__ TileCoord decode_unit(const TcConvParams& p, int unit, int rank) {
   TileCoord c;
-  const int groups = p.nblocks * p.phases;
-  c.q0 = (tile % p.ntiles) * p.MT;
-  const int r = tile / p.ntiles;
-  c.g = r % groups;
-  c.b = r / groups;
+  c.g = unit / p.nu;
+  int rt = (unit % p.nu) * p.csize + rank;
+  const int nrt = p.ntiles * p.B;
+  c.dummy = rt >= nrt;
+  if (c.dummy) rt = nrt - 1;
+  c.b = rt / p.ntiles;
+  c.q0 = (rt % p.ntiles) * p.MT;
   return c;
+}
+
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+
+// All MMAs of one (K chunk, tap) weight blob into one 128-row accumulator.  Descriptors differ only in their low
+// word (start address >> 4), so a time shift / K step / lo plane is one 32-bit add; fully unrolled per operand mode so
+// that the single issuing thread spends a couple of instructions per tcgen05.mma (it is the serial resource of the CTA).
+template <int KSTEPS, int APL, int WPL>
+__device__ __forceinline__ void issue_mmas(uint32_t d, uint32_t a_lo, uint32_t a_hiw, uint32_t b_lo, uint32_t b_hiw,
+                                           uint32_t a_kstep, uint32_t b_kstep, uint32_t a_plane, uint32_t b_plane,
+                                           uint32_t idesc, uint32_t first) {
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks) {
+    const uint64_t a = desc64(a_lo + ks * a_kstep, a_hiw), b = desc64(b_lo + ks * b_kstep, b_hiw);
+    umma_bf16(d, a, b, idesc, ks == 0 ? first : 1u);
+    if (WPL == 2) umma_bf16(d, a, desc64(b_lo + ks * b_kstep + b_plane, b_hiw), idesc, 1u);
+    if (APL == 2) umma_bf16(d, desc64(a_lo + ks * a_kstep + a_plane, a_hiw), b, idesc, 1u);
+  }
 }
 
 __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int N = p.N, KC = p.KC, PL = p.planes;
+  const int N = p.N, KC = p.KC, APL = p.a_planes, WPL = p.w_planes;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   // bars: [0..1] a_full, [2..3] a_empty, [4..9] w_full, [10..15] w_empty, [16..17] acc_full, [18..19] acc_empty
@@ -139,16 +197,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
   float* bias_s = reinterpret_cast<float*>(smem + 256);          // [nblocks * N] <= 512 floats
 
   const uint32_t a_plane_bytes = (uint32_t)(KC / 8) * p.RA * 16u;
-  const uint32_t a_stage_bytes = a_plane_bytes * PL;
+  const uint32_t a_stage_bytes = a_plane_bytes * APL;
   const uint32_t w_plane_bytes = (uint32_t)N * KC * 2u;
-  const uint32_t w_blob_bytes = w_plane_bytes * PL;
+  const uint32_t w_blob_bytes = w_plane_bytes * WPL;
   const uint32_t a_base = smem_u32(smem + kSmemHeader);
   const uint32_t w_base = a_base + p.a_stages * a_stage_bytes;
-  const int total_tiles = p.ntiles * p.nblocks * p.phases * p.B;
+  const int total_units = p.nu * p.nblocks * p.phases;
+  const int csize = p.csize;
+  const int rank = csize > 1 ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / csize, nclusters = gridDim.x / csize;
+  const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxAStages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < kMaxWStages; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+    for (int s = 0; s < kMaxWStages; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), csize); }
     for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -160,6 +222,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
   }
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();           // every peer's barriers are initialised before any remote arrive / copy
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
@@ -167,91 +230,108 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
     // ------------------------------------------------ activation producer
     const int slabs = KC / 8;
     const uint32_t row_bytes = (uint32_t)p.RA * 16u;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(p, tile);
+    int s = 0;
+    uint32_t ph = 1;                                             // producers start on the "previous phase done" parity
+    for (int unit = cluster_id; unit < total_units; unit += nclusters) {
+      const TileCoord tc = decode_unit(p, unit, rank);
       const size_t row0 = (size_t)(p.a_pad + tc.q0 + p.min_off);
-      for (int c = 0; c < p.nchunks; ++c, ++it) {
-        const int s = it % p.a_stages, n = it / p.a_stages;
-        mbar_wait(a_empty(s), (n & 1) ^ 1);
+      for (int c = 0; c < p.nchunks; ++c) {
+        mbar_wait(a_empty(s), ph);
         if (elect_one()) {
           mbar_arrive_expect_tx(a_full(s), a_stage_bytes);
-          for (int pl = 0; pl < PL; ++pl) {
-            const __nv_bfloat16* src = (pl ? p.a_lo : p.a_hi) + (size_t)tc.b * p.a_bs;
+          for (int pl = 0; pl < APL; ++pl) {
+            const tc16* src = (pl ? p.a_lo : p.a_hi) + (size_t)tc.b * p.a_bs;
             for (int sl = 0; sl < slabs; ++sl) {
-              const __nv_bfloat16* gp = src + ((size_t)(c * slabs + sl) * p.a_rows + row0) * 8;
+              const tc16* gp = src + ((size_t)(c * slabs + sl) * p.a_rows + row0) * 8;
               bulk_g2s(a_base + s * a_stage_bytes + pl * a_plane_bytes + sl * row_bytes, gp, row_bytes, a_full(s));
             }
           }
         }
         __syncwarp();
+        if (++s == p.a_stages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------ weight producer
     const size_t blob_elems = (size_t)w_blob_bytes / 2;
     const int per_tile = p.nchunks * p.ktaps;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(p, tile);
-      const __nv_bfloat16* wg = p.w + (size_t)tc.g * per_tile * blob_elems;
-      for (int i = 0; i < per_tile; ++i, ++it) {
-        const int s = it % p.w_stages, n = it / p.w_stages;
-        mbar_wait(w_empty(s), (n & 1) ^ 1);
+    const uint32_t slice_bytes = w_blob_bytes / (uint32_t)csize;      // this CTA's share of every blob
+    int s = 0;
+    uint32_t ph = 1;
+    for (int unit = cluster_id; unit < total_units; unit += nclusters) {
+      const TileCoord tc = decode_unit(p, unit, rank);
+      const tc16* wg = p.w + (size_t)tc.g * per_tile * blob_elems;
+      for (int i = 0; i < per_tile; ++i) {
+        mbar_wait(w_empty(s), ph);                                    // released by the MMA warps of ALL peers
         if (elect_one()) {
-          mbar_arrive_expect_tx(w_full(s), w_blob_bytes);
-          bulk_g2s(w_base + s * w_blob_bytes, wg + (size_t)i * blob_elems, w_blob_bytes, w_full(s));
+          mbar_arrive_expect_tx(w_full(s), w_blob_bytes);             // the whole blob lands here, one slice per peer
+          const uint32_t dst = w_base + s * w_blob_bytes + rank * slice_bytes;
+          const tc16* src = wg + (size_t)i * blob_elems + (size_t)rank * (slice_bytes / 2);
+          if (csize > 1) bulk_g2s_mc(dst, src, slice_bytes, w_full(s), cmask);
+          else bulk_g2s(dst, src, slice_bytes, w_full(s));
         }
         __syncwarp();
+        if (++s == p.w_stages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 2) {
     // ------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
-    // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 @17, M>>4 @24
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t a_lbo = (uint32_t)p.RA * 16u, a_sbo = 128u, b_lbo = (uint32_t)N * 16u, b_sbo = 128u;
-    const int ksteps = KC / 16;
-    // descriptors advance by (bytes >> 4) in their low word: +2*RA per K step (two slabs), +128 per accumulator
+    // instruction descriptor: D=f32 @4, A/B format @7/@10 (0 = f16, 1 = bf16), both K-major, N>>3 @17, M>>4 @24
+    const uint32_t f16b = p.fmt ? 1u : 0u;
+    const uint32_t idesc = (1u << 4) | (f16b << 7) | (f16b << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+    // shared-memory descriptors: high word = SBO (128 B) | version 1 << 14; low word = start >> 4 | LBO >> 4 << 16
+    const uint32_t hiw = (128u >> 4) | (1u << 14);
+    const uint32_t a_low0 = ((a_base >> 4) & 0x3FFFu) | ((uint32_t)p.RA << 16);      // LBO = RA * 16 B
+    const uint32_t b_low0 = ((w_base >> 4) & 0x3FFFu) | ((uint32_t)N << 16);         // LBO = N * 16 B
+    const uint32_t a_stage16 = a_stage_bytes >> 4, w_blob16 = w_blob_bytes >> 4;
+    // low-word steps (units of 16 B): +2*RA per K step (two slabs), +128 per accumulator, + plane size for the lo plane
     const uint32_t a_kstep = 2u * (uint32_t)p.RA, b_kstep = 2u * (uint32_t)N;
-    const uint32_t a_lo_off = a_plane_bytes >> 4, b_lo_off = w_plane_bytes >> 4;
-    int a_it = 0, w_it = 0, t_it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t_it) {
+    const uint32_t a_plane = a_plane_bytes >> 4, b_plane = w_plane_bytes >> 4;
+    const int variant = (KC == 32 ? 3 : 0) + (APL == 2 ? 2 : (WPL == 2 ? 1 : 0));
+    const int tap0 = p.tap_off0 - p.min_off;
+    int sa = 0, sw = 0;
+    uint32_t pa = 0, pw = 0;                                      // stage cursors + phase parities (no div/mod here)
+    int t_it = 0;
+    for (int unit = cluster_id; unit < total_units; unit += nclusters, ++t_it) {
+      const bool dummy = decode_unit(p, unit, rank).dummy;
+      const int nacc = dummy ? 0 : p.NACC;
       const int as = t_it & 1;
-      mbar_wait(acc_empty(as), ((t_it >> 1) & 1) ^ 1);       // epilogue has drained this accumulator set
+      mbar_wait(acc_empty(as), ((t_it >> 1) & 1) ^ 1);            // epilogue has drained this accumulator set
       tc_fence_after();
       const uint32_t d_base = tmem_base + (uint32_t)(as * 256);
-      for (int c = 0; c < p.nchunks; ++c, ++a_it) {
-        const int sa = a_it % p.a_stages;
-        mbar_wait(a_full(sa), (a_it / p.a_stages) & 1);
+      for (int c = 0; c < p.nchunks; ++c) {
+        mbar_wait(a_full(sa), pa);
         tc_fence_after();
-        const uint64_t a_stage_desc = make_desc(a_base + sa * a_stage_bytes, a_lbo, a_sbo);
-        for (int j = 0; j < p.ktaps; ++j, ++w_it) {
-          const int sw = w_it % p.w_stages;
-          mbar_wait(w_full(sw), (w_it / p.w_stages) & 1);
+        const uint32_t a_lo_stage = a_low0 + (uint32_t)sa * a_stage16;
+        for (int j = 0; j < p.ktaps; ++j) {
+          mbar_wait(w_full(sw), pw);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t b_desc0 = make_desc(w_base + sw * w_blob_bytes, b_lbo, b_sbo);
-            const uint64_t a_desc0 = a_stage_desc + (uint32_t)(p.tap_off0 + j * p.tap_step - p.min_off);
-            for (int m = 0; m < p.NACC; ++m) {
-              const uint32_t d = d_base + (uint32_t)(m * N);
-              for (int ks = 0; ks < ksteps; ++ks) {
-                const uint64_t a_hi = a_desc0 + (uint32_t)(m * 128) + ks * a_kstep;
-                const uint64_t b_hi = b_desc0 + ks * b_kstep;
-                umma_bf16(d, a_hi, b_hi, idesc, (c | j | ks) != 0 ? 1u : 0u);
-                if (PL == 2) {
-                  umma_bf16(d, a_hi, b_hi + b_lo_off, idesc, 1u);
-                  umma_bf16(d, a_hi + a_lo_off, b_hi, idesc, 1u);
-                }
+            const uint32_t b_lo = b_low0 + (uint32_t)sw * w_blob16;
+            const uint32_t a_lo = a_lo_stage + (uint32_t)(tap0 + j * p.tap_step);
+            const uint32_t first = (c | j) != 0 ? 1u : 0u;
+            for (int m = 0; m < nacc; ++m) {
+              const uint32_t d = d_base + (uint32_t)(m * N), am = a_lo + (uint32_t)(m * 128);
+              switch (variant) {
+                case 0: issue_mmas<1, 1, 1>(d, am, hiw, b_lo, hiw, a_kstep, b_kstep, a_plane, b_plane, idesc, first); break;
+                case 1: issue_mmas<1, 1, 2>(d, am, hiw, b_lo, hiw, a_kstep, b_kstep, a_plane, b_plane, idesc, first); break;
+                case 2: issue_mmas<1, 2, 2>(d, am, hiw, b_lo, hiw, a_kstep, b_kstep, a_plane, b_plane, idesc, first); break;
+                case 3: issue_mmas<2, 1, 1>(d, am, hiw, b_lo, hiw, a_kstep, b_kstep, a_plane, b_plane, idesc, first); break;
+                case 4: issue_mmas<2, 1, 2>(d, am, hiw, b_lo, hiw, a_kstep, b_kstep, a_plane, b_plane, idesc, first); break;
+                default: issue_mmas<2, 2, 2>(d, am, hiw, b_lo, hiw, a_kstep, b_kstep, a_plane, b_plane, idesc, first); break;
               }
             }
-            umma_commit(w_empty(sw));     // weight slot free once these MMAs have read it
+            if (csize > 1) umma_commit_mc(w_empty(sw), cmask);   // weight slot free (here and at every peer's producer)
+            else umma_commit(w_empty(sw));                       // once these MMAs have read it
             if (j == p.ktaps - 1) {
               umma_commit(a_empty(sa));
               if (c == p.nchunks - 1) umma_commit(acc_full(as));
             }
           }
           __syncwarp();
+          if (++sw == p.w_stages) { sw = 0; pw ^= 1u; }
         }
+        if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
       }
     }
   } else {
@@ -262,12 +342,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
     const int nbias = N * p.nblocks;
     for (int i = et; i < nbias; i += kEpiWarps * 32) bias_s[i] = p.bias ? __ldg(p.bias + i) : 0.f;
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    const bool split = PL == 2;
+    const bool split = p.o_lo != nullptr;
+    const int fmt = p.fmt;
     const int ncc = N / 32;
     const int nitems = p.NACC * ncc;
     int t_it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t_it) {
-      const TileCoord tc = decode_tile(p, tile);
+    for (int unit = cluster_id; unit < total_units; unit += nclusters, ++t_it) {
+      const TileCoord tc = decode_unit(p, unit, rank);
       const int phase = tc.g % p.phases, co_off = (tc.g / p.phases) * N;
       const int as = t_it & 1;
       const float* resb = p.res ? p.res + (size_t)tc.b * p.o32_bs : nullptr;
@@ -279,7 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
         const int m = idx / ncc;
         const int q = tc.q0 + m * 128 + quad * 32 + lane;
         t = q * p.ot_mul + p.ot_add + phase;
-        ok = q < p.nq && t >= 0 && t < p.T_out;
+        ok = !tc.dummy && q < p.nq && t >= 0 && t < p.T_out;
       };
       auto load_res = [&](int idx, float4 (&dst)[8]) {
         int t; bool ok;
@@ -339,13 +420,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
             for (int h = 0; h < 4; ++h) {
               uint32_t hw[4], lw[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float a0 = leaky(v[8 * h + 2 * e], p.slope), a1 = leaky(v[8 * h + 2 * e + 1], p.slope);
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
-                hw[e] = pack_bf16(h0, h1);
-                lw[e] = pack_bf16(__float2bfloat16_rn(a0 - __bfloat162float(h0)),
-                                  __float2bfloat16_rn(a1 - __bfloat162float(h1)));
-              }
+              for (int e = 0; e < 4; ++e)
+                split2(leaky(v[8 * h + 2 * e], p.slope), leaky(v[8 * h + 2 * e + 1], p.slope), fmt, hw[e], lw[e]);
               const size_t off = prow + (size_t)h * p.op_rows * 8;
               *reinterpret_cast<uint4*>(p.o_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
               if (split) *reinterpret_cast<uint4*>(p.o_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
@@ -363,6 +439,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
   }
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();           // no peer may still multicast into / arrive on this CTA's shared memory
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -372,9 +449,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
 // ---------------------------------------------------------------------------------------------------------------
 // helper kernels
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void tc_pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int C_out,
+__global__ void tc_pack_weights_kernel(const float* __restrict__ w, tc16* __restrict__ out, int C_out,
                                        int C_in, int K, int transposed, int stride, int N, int KC, int planes,
-                                       int ktaps, int phases) {
+                                       int ktaps, int phases, int fmt) {
   const size_t total = (size_t)C_out * C_in * ktaps * phases * planes;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -393,12 +470,12 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ w, __nv_bfloat1
   float v;
   if (transposed) v = w[((size_t)ci * C_out + co) * K + phase + j * stride];
   else v = w[((size_t)co * C_in + ci) * K + j];
-  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-  out[i] = pl ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
+  const uint32_t hi = cvt16(v, fmt);
+  out[i] = (tc16)(pl ? cvt16(v - back16(hi, fmt), fmt) : hi);
 }
 
 __global__ void tc_to_planes_kernel(const float* __restrict__ x, long bs, long cs, long ts, int C, int T, float slope,
-                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int rows, int pad) {
+                                    tc16* __restrict__ hi, tc16* __restrict__ lo, int rows, int pad, int fmt) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int sl = blockIdx.y, b = blockIdx.z;
   if (t >= T) return;
@@ -407,16 +484,14 @@ __global__ void tc_to_planes_kernel(const float* __restrict__ x, long bs, long c
   for (int e = 0; e < 4; ++e) {
     const float a0 = leaky(x[(size_t)b * bs + (size_t)(sl * 8 + 2 * e) * cs + (size_t)t * ts], slope);
     const float a1 = leaky(x[(size_t)b * bs + (size_t)(sl * 8 + 2 * e + 1) * cs + (size_t)t * ts], slope);
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
-    hw[e] = pack_bf16(h0, h1);
-    lw[e] = pack_bf16(__float2bfloat16_rn(a0 - __bfloat162float(h0)), __float2bfloat16_rn(a1 - __bfloat162float(h1)));
+    split2(a0, a1, fmt, hw[e], lw[e]);
   }
   const size_t off = (((size_t)b * (C / 8) + sl) * rows + pad + t) * 8;
   *reinterpret_cast<uint4*>(hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
   if (lo) *reinterpret_cast<uint4*>(lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
 }
 
-__global__ void tc_zero_halo_kernel(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int rows, int pad,
+__global__ void tc_zero_halo_kernel(tc16* __restrict__ hi, tc16* __restrict__ lo, int rows, int pad,
                                     int T) {
   const size_t slab = blockIdx.x;
   const int nz = rows - T;                       // zero rows: [0,pad) then [pad+T, rows)
@@ -447,15 +522,15 @@ __global__ void tc_nct_to_stream_kernel(const float* __restrict__ in, float* __r
       make_float4(o[0], o[(size_t)T], o[(size_t)2 * T], o[(size_t)3 * T]);
 }
 
-__global__ void tc_planes_to_nct_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
-                                        float* __restrict__ out, int C, int T, int rows, int pad) {
+__global__ void tc_planes_to_nct_kernel(const tc16* __restrict__ hi, const tc16* __restrict__ lo,
+                                        float* __restrict__ out, int C, int T, int rows, int pad, int fmt) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int sl = blockIdx.y, b = blockIdx.z;
   if (t >= T) return;
   const size_t off = (((size_t)b * (C / 8) + sl) * rows + pad + t) * 8;
   for (int e = 0; e < 8; ++e) {
-    float v = __bfloat162float(hi[off + e]);
-    if (lo) v += __bfloat162float(lo[off + e]);
+    float v = back16(hi[off + e], fmt);
+    if (lo) v += back16(lo[off + e], fmt);
     out[((size_t)b * C + sl * 8 + e) * T + t] = v;
   }
 }
@@ -504,10 +579,10 @@ static int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq) {
+void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq, int a_planes) {
   p->w = w.w; p->bias = w.bias;
   p->C_in = w.C_in; p->N = w.N; p->KC = w.KC; p->nchunks = w.C_in / w.KC; p->ktaps = w.ktaps;
-  p->planes = w.planes; p->nblocks = w.C_out / w.N; p->phases = w.phases;
+  p->a_planes = a_planes; p->w_planes = w.planes; p->fmt = w.fmt; p->nblocks = w.C_out / w.N; p->phases = w.phases;
   p->nq = nq;
   int nacc = 256 / w.N;                                      // one accumulator set = 256 TMEM columns (two sets)
   if (nacc > 4) nacc = 4;
@@ -522,19 +597,21 @@ void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq) {
   const int max_off = o0 < o1 ? o1 : o0;
   p->RA = p->MT + (max_off - p->min_off);
   p->a_stages = kMaxAStages;
-  const size_t a_stage = (size_t)(p->KC / 8) * p->RA * 16 * p->planes;
-  const size_t w_blob = (size_t)p->N * p->KC * 2 * p->planes;
+  const size_t a_stage = (size_t)(p->KC / 8) * p->RA * 16 * p->a_planes;
+  const size_t w_blob = (size_t)p->N * p->KC * 2 * p->w_planes;
   const size_t budget = kSmemLimit - kSmemHeader - p->a_stages * a_stage;
   int ws = (int)(budget / w_blob);
   if (ws > kMaxWStages) ws = kMaxWStages;
   const int force_ws = env_int("DTTS_TC_WSTAGES", 0);
   if (force_ws > 0 && force_ws < ws) ws = force_ws;
   p->w_stages = ws;
+  p->csize = 1;
+  p->nu = 0;
 }
 
 static size_t tc_smem_bytes(const TcConvParams& p) {
-  const size_t a_stage = (size_t)(p.KC / 8) * p.RA * 16 * p.planes;
-  const size_t w_blob = (size_t)p.N * p.KC * 2 * p.planes;
+  const size_t a_stage = (size_t)(p.KC / 8) * p.RA * 16 * p.a_planes;
+  const size_t w_blob = (size_t)p.N * p.KC * 2 * p.w_planes;
   size_t bytes = kSmemHeader + p.a_stages * a_stage + p.w_stages * w_blob;
   // the CTA owns all 512 TMEM columns: it must be alone on its SM, or a co-resident CTA would block in tcgen05.alloc
   if (bytes < 116 * 1024) bytes = 116 * 1024;
@@ -542,9 +619,21 @@ static size_t tc_smem_bytes(const TcConvParams& p) {
 }
 
 static int g_num_sms = 0;
+static int g_max_clusters[9] = {0};     // [csize] -> co-resident clusters of tc_conv_kernel (0 = not queried yet)
+
+// Cluster size per layer: weights are re-streamed once per row tile, so the layers whose blob traffic per MMA cycle is
+// highest (N = 256 / 128) share them 4 ways; the small layers pair up (a 2-cluster wastes no SM on this part).
+static int pick_cluster(const TcConvParams& p, long row_tiles) {
+  int c = env_int("DTTS_TC_CLUSTER", 0);
+  if (c <= 0) c = p.N >= 128 ? 4 : 2;
+  while (c > 1 && (row_tiles < c || (p.N * p.KC * 2 * p.w_planes) % (16 * c))) c >>= 1;
+  return c;
+}
 
 cudaError_t launch_tc_conv(TcConvParams p, int B, cudaStream_t stream) {
   if (B <= 0 || p.nq <= 0) return cudaSuccess;
+  if (p.a_planes < 1 || p.a_planes > 2 || p.w_planes < 1 || p.w_planes > 2 || (p.a_planes == 2 && !p.a_lo))
+    return cudaErrorInvalidValue;
   if (p.w_stages < 1 || p.N % 32 != 0 || p.N > 256 || p.KC % 16 != 0 || p.C_in % p.KC != 0 ||
       p.N * p.nblocks > 512 || p.NACC * p.N > 256)
     return cudaErrorInvalidConfiguration;
@@ -559,32 +648,60 @@ cudaError_t launch_tc_conv(TcConvParams p, int B, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
   }
   p.B = B;
-  const long total = (long)p.ntiles * p.nblocks * p.phases * B;
-  const int grid = (int)(total < g_num_sms ? total : g_num_sms);       // persistent: one CTA per SM
-  tc_conv_kernel<<<grid, kThreads, smem, stream>>>(p);
-  return cudaGetLastError();
+  const long row_tiles = (long)p.ntiles * B;
+  int csize = pick_cluster(p, row_tiles);
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int max_clusters = 0;
+  for (; csize >= 1; csize >>= 1) {
+    if (csize == 1) { max_clusters = g_num_sms; break; }
+    if (g_max_clusters[csize] == 0) {
+      attr[0].val.clusterDim = {(unsigned)csize, 1, 1};
+      cfg.gridDim = dim3((unsigned)(g_num_sms / csize * csize));
+      int n = 0;
+      cfg.dynamicSmemBytes = kSmemLimit;
+      cudaError_t e = cudaOccupancyMaxActiveClusters(&n, tc_conv_kernel, &cfg);
+      cfg.dynamicSmemBytes = smem;
+      g_max_clusters[csize] = (e == cudaSuccess && n > 0) ? n : -1;
+      if (e != cudaSuccess) (void)cudaGetLastError();
+    }
+    if (g_max_clusters[csize] > 0) { max_clusters = g_max_clusters[csize]; break; }
+  }
+  p.csize = csize;
+  p.nu = (int)((row_tiles + csize - 1) / csize);
+  const long total_units = (long)p.nu * p.nblocks * p.phases;
+  const int nclusters = (int)(total_units < max_clusters ? total_units : max_clusters);   // persistent
+  attr[0].val.clusterDim = {(unsigned)csize, 1, 1};
+  cfg.gridDim = dim3((unsigned)(nclusters * csize));
+  return cudaLaunchKernelEx(&cfg, tc_conv_kernel, p);
 }
 
-cudaError_t tc_pack_weights(const float* w_ref, __nv_bfloat16* out, int C_out, int C_in, int K, int transposed,
-                            int stride, int N, int KC, int planes, cudaStream_t s) {
+cudaError_t tc_pack_weights(const float* w_ref, tc16* out, int C_out, int C_in, int K, int transposed,
+                            int stride, int N, int KC, int planes, int fmt, cudaStream_t s) {
   const int phases = transposed ? stride : 1;
   const int ktaps = transposed ? K / stride : K;
   if (C_out % N || C_in % KC || (transposed && K % stride)) return cudaErrorInvalidValue;
   const size_t total = (size_t)C_out * C_in * ktaps * phases * planes;
   tc_pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w_ref, out, C_out, C_in, K, transposed, stride,
-                                                                        N, KC, planes, ktaps, phases);
+                                                                        N, KC, planes, ktaps, phases, fmt);
   return cudaGetLastError();
 }
 
 cudaError_t tc_to_planes(const float* x, long bs, long cs, long ts, int B, int C, int T, float slope,
-                         __nv_bfloat16* hi, __nv_bfloat16* lo, int rows, int pad, cudaStream_t s) {
+                         tc16* hi, tc16* lo, int rows, int pad, int fmt, cudaStream_t s) {
   if (C % 8) return cudaErrorInvalidValue;
   dim3 grid(cdiv(T, 128), C / 8, B);
-  tc_to_planes_kernel<<<grid, 128, 0, s>>>(x, bs, cs, ts, C, T, slope, hi, lo, rows, pad);
+  tc_to_planes_kernel<<<grid, 128, 0, s>>>(x, bs, cs, ts, C, T, slope, hi, lo, rows, pad, fmt);
   return cudaGetLastError();
 }
 
-cudaError_t tc_zero_halo(__nv_bfloat16* hi, __nv_bfloat16* lo, int n_slabs_total, int rows, int pad, int T,
+cudaError_t tc_zero_halo(tc16* hi, tc16* lo, int n_slabs_total, int rows, int pad, int T,
                          cudaStream_t s) {
   tc_zero_halo_kernel<<<n_slabs_total, 128, 0, s>>>(hi, lo, rows, pad, T);
   return cudaGetLastError();
@@ -601,10 +718,10 @@ cudaError_t tc_nct_to_stream(const float* in, float* st, int B, int C, int T, cu
   return cudaGetLastError();
 }
 
-cudaError_t tc_planes_to_nct(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* out, int B, int C, int T,
-                             int rows, int pad, cudaStream_t s) {
+cudaError_t tc_planes_to_nct(const tc16* hi, const tc16* lo, float* out, int B, int C, int T,
+                             int rows, int pad, int fmt, cudaStream_t s) {
   dim3 grid(cdiv(T, 128), C / 8, B);
-  tc_planes_to_nct_kernel<<<grid, 128, 0, s>>>(hi, lo, out, C, T, rows, pad);
+  tc_planes_to_nct_kernel<<<grid, 128, 0, s>>>(hi, lo, out, C, T, rows, pad, fmt);
   return cudaGetLastError();
 }
 

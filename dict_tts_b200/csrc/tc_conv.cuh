@@ -2,9 +2,11 @@
 //
 //   D[q, co] = sum_{tap j} sum_{ci} A[q + off_j, ci] * W_j[co, ci]        M = time (128 rows / MMA), N = C_out, K = C_in
 //
-// Operands are bf16; "split" mode feeds every fp32 value as hi + lo bf16 and issues hi*hi + hi*lo + lo*hi
-// (3 MMAs, fp32 accumulate in TMEM) -- ~2^-16 relative error per product, which keeps the waveform within the
-// north-star tolerance (1e-4 RMS) where single-pass bf16 / tf32 do not ("vocoder precision").
+// Operands are 16-bit (bf16 or fp16, TcMode::fmt) and either operand may be fed as hi + lo planes: the kernel issues
+// a_hi*w_hi (+ a_hi*w_lo when the weights are split) (+ a_lo*w_hi when the activations are split), fp32 accumulate
+// in TMEM.  bf16 hi/lo on both sides (3 MMAs) is fp32-class (~2^-16 per product); fp16 activations against hi/lo fp16
+// weights (2 MMAs) leaves only the 2^-12 activation rounding; see DESIGN.md "vocoder precision" for the measured
+// waveform error of every mode against the 1e-4 RMS tolerance.
 //
 // Memory layout ("slab planes", chosen so that a time shift is a pure address offset for the UMMA descriptor):
 //   operand plane   bf16  [B][C/8][rows][8]   row = pad + t ; rows outside [pad, pad+T) are zero (conv zero padding)
@@ -18,10 +20,32 @@
 // modules/hifigan/hifigan.py:27-58 (ResBlock1), :101-142 (HifiGanGenerator.forward).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
 namespace dtts {
+
+typedef uint16_t tc16;   // storage of one operand element (bf16 or fp16 bit pattern)
+
+// Operand format of a tensor-core convolution.
+struct TcMode {
+  int fmt = 1;        // 0: fp16, 1: bf16
+  int a_planes = 2;   // activations: 1 = single rounding, 2 = hi + lo
+  int w_planes = 2;   // weights:     1 = single rounding, 2 = hi + lo
+  int mmas() const { return a_planes + w_planes - 1; }
+};
+// dtts_vocoder_desc.precision -> mode (1: bf16 3-MMA split, 2: bf16, 3: fp16 x fp16 hi/lo weights, 4: fp16)
+static inline TcMode tc_mode(int precision) {
+  TcMode m;
+  switch (precision) {
+    case 2: m.fmt = 1; m.a_planes = 1; m.w_planes = 1; break;
+    case 3: m.fmt = 0; m.a_planes = 1; m.w_planes = 2; break;
+    case 4: m.fmt = 0; m.a_planes = 1; m.w_planes = 1; break;
+    default: m.fmt = 1; m.a_planes = 2; m.w_planes = 2; break;
+  }
+  return m;
+}
 
 constexpr int TC_PADF = 32;        // zero rows in front of t = 0 (>= largest left halo: k=11, d=5 -> 25)
 constexpr int TC_PADB = 32;        // zero rows kept after the last tile
@@ -32,23 +56,26 @@ static inline int tc_rows(int T) { return TC_PADF + (T + 8 + TC_ROW_ALIGN - 1) /
 // Packed weights of one convolution: blobs [group][chunk][tap] of {hi plane, lo plane}, each plane [KC/8][N][8] bf16
 // (the shared-memory image of the B operand).  group = nblock * phases + phase.
 struct TcConvW {
-  const __nv_bfloat16* w = nullptr;
+  const tc16* w = nullptr;
   const float* bias = nullptr;   // [C_out] fp32
   int C_in = 0, C_out = 0;       // full channel counts
   int N = 0;                     // output channels per MMA (<= 256); C_out = N * nblocks
   int KC = 0;                    // channels per K chunk (16 or 32)
-  int ktaps = 0, phases = 1, planes = 2;
+  int ktaps = 0, phases = 1;
+  int planes = 2;                // weight planes (TcMode::w_planes)
+  int fmt = 1;                   // TcMode::fmt
   size_t elems() const { return (size_t)C_out * C_in * ktaps * phases * planes; }
 };
 
 struct TcConvParams {
-  const __nv_bfloat16* a_hi;     // input operand planes
-  const __nv_bfloat16* a_lo;
+  const tc16* a_hi;     // input operand planes
+  const tc16* a_lo;
   long a_bs;                     // batch stride in elements
   int a_rows, a_pad;
-  const __nv_bfloat16* w;
+  const tc16* w;
   const float* bias;
-  int C_in, N, KC, nchunks, ktaps, planes, nblocks, phases;
+  int C_in, N, KC, nchunks, ktaps, nblocks, phases;
+  int a_planes, w_planes, fmt;   // operand planes of A (activations) and B (weights); 16-bit format
   int tap_off0, tap_step;        // tap j reads input row q + tap_off0 + j*tap_step
   int min_off, RA;               // staged rows per slab: [q0 + min_off, q0 + min_off + RA)
   int nq, MT, NACC;
@@ -56,37 +83,39 @@ struct TcConvParams {
   float* o32;                    // fp32 stream out (may be null)
   const float* res;              // fp32 stream residual (may be null), same geometry as o32
   long o32_bs;                   // = C_out * T_out
-  __nv_bfloat16* o_hi;           // operand planes out (may be null): leaky(v, slope) split in hi / lo
-  __nv_bfloat16* o_lo;
+  tc16* o_hi;           // operand planes out (may be null): leaky(v, slope) split in hi / lo
+  tc16* o_lo;
   long op_bs;
   int op_rows, op_pad;
   float post, slope;
   int accumulate;
   int a_stages, w_stages;
   int ntiles, B;                 // time tiles per (group, batch item); batch size (set by the launcher)
+  int csize, nu;                 // cluster size; units (= csize consecutive row tiles) per weight group (launcher)
 };
 
-// Launch plan / launcher.  `split` = 1: hi/lo planes (3 MMAs), 0: single bf16 plane.
+// Launch plan / launcher.
 cudaError_t tc_conv_init();
 cudaError_t launch_tc_conv(TcConvParams p, int B, cudaStream_t stream);
-// Fills the derived fields (KC-dependent tiling, shared-memory stages, TMEM columns) of p from the weights + geometry.
-void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq);
+// Fills the derived fields (KC-dependent tiling, shared-memory stages, TMEM columns) of p from the weights + geometry;
+// a_planes = planes of the INPUT activation buffers.
+void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq, int a_planes);
 
 // Weight packing: reference layout ([C_out][C_in][K], or [C_in][C_out][K] for ConvTranspose1d) -> blobs.
-cudaError_t tc_pack_weights(const float* w_ref, __nv_bfloat16* out, int C_out, int C_in, int K, int transposed,
-                            int stride, int N, int KC, int planes, cudaStream_t s);
+cudaError_t tc_pack_weights(const float* w_ref, tc16* out, int C_out, int C_in, int K, int transposed,
+                            int stride, int N, int KC, int planes, int fmt, cudaStream_t s);
 // fp32 strided tensor x[b*bs + c*cs + t*ts] -> operand planes of leaky(x, slope) (valid rows only)
 cudaError_t tc_to_planes(const float* x, long bs, long cs, long ts, int B, int C, int T, float slope,
-                         __nv_bfloat16* hi, __nv_bfloat16* lo, int rows, int pad, cudaStream_t s);
+                         tc16* hi, tc16* lo, int rows, int pad, int fmt, cudaStream_t s);
 // zero the halo rows [0,pad) and [pad+T, rows) of every slab of a plane pair
-cudaError_t tc_zero_halo(__nv_bfloat16* hi, __nv_bfloat16* lo, int n_slabs_total, int rows, int pad, int T,
+cudaError_t tc_zero_halo(tc16* hi, tc16* lo, int n_slabs_total, int rows, int pad, int T,
                          cudaStream_t s);
 // fp32 stream <-> [B][C][T]
 cudaError_t tc_stream_to_nct(const float* st, float* out, int B, int C, int T, cudaStream_t s);
 cudaError_t tc_nct_to_stream(const float* in, float* st, int B, int C, int T, cudaStream_t s);
 // operand planes (hi + lo) -> fp32 [B][C][T]  (tests)
-cudaError_t tc_planes_to_nct(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* out, int B, int C, int T,
-                             int rows, int pad, cudaStream_t s);
+cudaError_t tc_planes_to_nct(const tc16* hi, const tc16* lo, float* out, int B, int C, int T,
+                             int rows, int pad, int fmt, cudaStream_t s);
 // conv_post: y[b,t] = tanh(bias + sum_{c,j} w[c][j] * leaky(x[b,c,t+j-pad], slope)) from an fp32 stream
 cudaError_t tc_conv_post(const float* st, const float* w, const float* bias, float* wav, int B, int C, int T, int K,
                          float slope, cudaStream_t s);

@@ -17,8 +17,9 @@ struct dtts_vocoder {
   uint64_t launches = 0;
   int hop = 1;
   size_t unit = 0;               // max over stages of C*T_len per input frame
-  // tensor-core path (precision 1 = split bf16 hi/lo, 3 MMAs; 2 = single bf16)
-  __nv_bfloat16* tc_pool = nullptr;
+  // tensor-core path (precision >= 1, see tc_mode() in tc_conv.cuh)
+  TcMode mode;
+  tc16* tc_pool = nullptr;
   TcConvW tc_pre;
   std::vector<TcConvW> tc_ups, tc_rb1, tc_rb2;
   const float *post_w = nullptr, *post_b = nullptr;
@@ -51,8 +52,9 @@ int pack_convT(dtts_vocoder* h, const std::string& name, int C_in, int C_out, in
   return DTTS_OK;
 }
 
-int tc_pack(dtts_vocoder* h, __nv_bfloat16** cursor, const std::string& name, int C_out, int C_in, int K,
-            int transposed, int stride, int planes, TcConvW* cw, cudaStream_t s) {
+int tc_pack(dtts_vocoder* h, tc16** cursor, const std::string& name, int C_out, int C_in, int K,
+            int transposed, int stride, TcMode mode, TcConvW* cw, cudaStream_t s) {
+  const int planes = mode.w_planes;
   const float* w = h->tab.get(name + ".weight", (uint64_t)C_out * C_in * K);
   if (!w) return DTTS_ERR_MISSING_WEIGHT;
   const float* b = h->tab.get(name + ".bias", C_out);
@@ -63,44 +65,47 @@ int tc_pack(dtts_vocoder* h, __nv_bfloat16** cursor, const std::string& name, in
   cw->ktaps = transposed ? K / stride : K;
   cw->phases = transposed ? stride : 1;
   cw->planes = planes;
+  cw->fmt = mode.fmt;
   cw->bias = b;
   if (C_out % cw->N || cw->N % 32 || C_in % cw->KC)
     return fail(DTTS_ERR_BAD_SHAPE, "tensor-core vocoder: unsupported channel count in " + name);
   cw->w = *cursor;
-  DTTS_CUDA(tc_pack_weights(w, *cursor, C_out, C_in, K, transposed, stride, cw->N, cw->KC, planes, s));
+  DTTS_CUDA(tc_pack_weights(w, *cursor, C_out, C_in, K, transposed, stride, cw->N, cw->KC, planes, mode.fmt, s));
   *cursor += (cw->elems() + 63) / 64 * 64;
   return DTTS_OK;
 }
 
 int tc_create(dtts_vocoder* h, cudaStream_t s) {
   const dtts_vocoder_desc& d = h->desc;
-  const int planes = d.precision == 1 ? 2 : 1;
-  // bf16 elements needed: planes * (all conv weights) + alignment slack
-  size_t total = (size_t)d.init_ch * d.n_mel * 7 * planes + 64;
+  h->mode = tc_mode(d.precision);
+  const TcMode mode = h->mode;
+  const int wp = mode.w_planes;
+  // 16-bit elements needed: weight planes * (all conv weights) + alignment slack
+  size_t total = (size_t)d.init_ch * d.n_mel * 7 * wp + 64;
   int ch = d.init_ch;
   for (int i = 0; i < d.n_ups; ++i) {
-    total += (size_t)ch * (ch / 2) * d.up_kernels[i] * planes + 64;
+    total += (size_t)ch * (ch / 2) * d.up_kernels[i] * wp + 64;
     ch /= 2;
-    for (int j = 0; j < d.n_rb; ++j) total += 6 * ((size_t)ch * ch * d.rb_kernels[j] * planes + 64);
+    for (int j = 0; j < d.n_rb; ++j) total += 6 * ((size_t)ch * ch * d.rb_kernels[j] * wp + 64);
   }
-  cudaError_t e = cudaMalloc((void**)&h->tc_pool, total * sizeof(__nv_bfloat16));
+  cudaError_t e = cudaMalloc((void**)&h->tc_pool, total * sizeof(tc16));
   if (e != cudaSuccess) return fail(DTTS_ERR_CUDA, std::string("cudaMalloc(tc weight pool): ") + cudaGetErrorString(e));
   e = tc_conv_init();
   if (e != cudaSuccess) return fail(DTTS_ERR_CUDA, std::string("tc_conv_init: ") + cudaGetErrorString(e));
-  __nv_bfloat16* cur = h->tc_pool;
-  DTTS_TRY(tc_pack(h, &cur, "conv_pre", d.init_ch, d.n_mel, 7, 0, 1, planes, &h->tc_pre, s));
+  tc16* cur = h->tc_pool;
+  DTTS_TRY(tc_pack(h, &cur, "conv_pre", d.init_ch, d.n_mel, 7, 0, 1, mode, &h->tc_pre, s));
   ch = d.init_ch;
   for (int i = 0; i < d.n_ups; ++i) {
     TcConvW u;
-    DTTS_TRY(tc_pack(h, &cur, "ups." + std::to_string(i), ch / 2, ch, d.up_kernels[i], 1, d.up_rates[i], planes, &u, s));
+    DTTS_TRY(tc_pack(h, &cur, "ups." + std::to_string(i), ch / 2, ch, d.up_kernels[i], 1, d.up_rates[i], mode, &u, s));
     h->tc_ups.push_back(u);
     ch /= 2;
     for (int j = 0; j < d.n_rb; ++j) {
       const std::string r = "resblocks." + std::to_string(i * d.n_rb + j);
       for (int m = 0; m < 3; ++m) {
         TcConvW c1, c2;
-        DTTS_TRY(tc_pack(h, &cur, r + ".convs1." + std::to_string(m), ch, ch, d.rb_kernels[j], 0, 1, planes, &c1, s));
-        DTTS_TRY(tc_pack(h, &cur, r + ".convs2." + std::to_string(m), ch, ch, d.rb_kernels[j], 0, 1, planes, &c2, s));
+        DTTS_TRY(tc_pack(h, &cur, r + ".convs1." + std::to_string(m), ch, ch, d.rb_kernels[j], 0, 1, mode, &c1, s));
+        DTTS_TRY(tc_pack(h, &cur, r + ".convs2." + std::to_string(m), ch, ch, d.rb_kernels[j], 0, 1, mode, &c2, s));
         h->tc_rb1.push_back(c1);
         h->tc_rb2.push_back(c2);
       }
@@ -137,23 +142,24 @@ TcGeom tc_geom(const dtts_vocoder* h, int B, int T) {
 }
 
 struct PlaneBuf {
-  __nv_bfloat16 *hi = nullptr, *lo = nullptr;
+  tc16 *hi = nullptr, *lo = nullptr;
   int C = 0, T = 0, rows = 0;
   long bs() const { return (long)C * rows; }
 };
 
 int tc_vocode(dtts_vocoder* h, const float* mel, int B, int T, float* wav, void* ws, uint64_t ws_bytes, cudaStream_t s) {
   const dtts_vocoder_desc& d = h->desc;
-  const bool split = d.precision == 1;
+  const bool split = h->mode.a_planes == 2;
+  const int fmt = h->mode.fmt;
   const TcGeom g = tc_geom(h, B, T);
   Bump bump(ws, ws_bytes);
   PlaneBuf PM, PX, PXU, PT, PY;
-  PM.hi = bump.take<__nv_bfloat16>(g.mel_plane_elems);
-  PM.lo = split ? bump.take<__nv_bfloat16>(g.mel_plane_elems) : nullptr;
+  PM.hi = bump.take<tc16>(g.mel_plane_elems);
+  PM.lo = split ? bump.take<tc16>(g.mel_plane_elems) : nullptr;
   PlaneBuf* pbs[4] = {&PX, &PXU, &PT, &PY};
   for (PlaneBuf* pb : pbs) {
-    pb->hi = bump.take<__nv_bfloat16>(g.plane_elems);
-    pb->lo = split ? bump.take<__nv_bfloat16>(g.plane_elems) : nullptr;
+    pb->hi = bump.take<tc16>(g.plane_elems);
+    pb->lo = split ? bump.take<tc16>(g.plane_elems) : nullptr;
   }
   float* XU32 = bump.take<float>(g.stream_elems);
   float* Y32 = bump.take<float>(g.stream_elems);
@@ -171,7 +177,7 @@ int tc_vocode(dtts_vocoder* h, const float* mel, int B, int T, float* wav, void*
     TcConvParams p{};
     p.a_hi = in.hi; p.a_lo = in.lo; p.a_bs = in.bs(); p.a_rows = in.rows; p.a_pad = TC_PADF;
     p.tap_off0 = off0; p.tap_step = step;
-    tc_conv_plan(&p, w, nq);
+    tc_conv_plan(&p, w, nq, h->mode.a_planes);
     p.ot_mul = 1; p.ot_add = 0;
     p.post = 1.f; p.slope = 0.1f; p.accumulate = 0;
     return p;
@@ -182,7 +188,7 @@ int tc_vocode(dtts_vocoder* h, const float* mel, int B, int T, float* wav, void*
 
   // mel [B,T,n_mel] -> operand planes (no activation in front of conv_pre)
   shape(PM, d.n_mel, T);
-  L(tc_to_planes(mel, (long)T * d.n_mel, 1, d.n_mel, B, d.n_mel, T, 1.f, PM.hi, PM.lo, PM.rows, TC_PADF, s));
+  L(tc_to_planes(mel, (long)T * d.n_mel, 1, d.n_mel, B, d.n_mel, T, 1.f, PM.hi, PM.lo, PM.rows, TC_PADF, fmt, s));
   shape(PX, d.init_ch, T);
   {
     TcConvParams p = base(h->tc_pre, PM, T, -3, 1);
@@ -255,7 +261,7 @@ extern "C" int dtts_vocoder_create(const dtts_vocoder_desc* d, const float* aren
     if (u < 1 || k % u != 0 || (k - u) % 2 != 0)
       return fail(DTTS_ERR_BAD_SHAPE, "upsample kernel must be a multiple of its rate with even (k-u)");
   }
-  if (d->precision < 0 || d->precision > 2) return fail(DTTS_ERR_BAD_ARG, "vocoder precision must be 0, 1 or 2");
+  if (d->precision < 0 || d->precision > 4) return fail(DTTS_ERR_BAD_ARG, "vocoder precision must be 0..4");
   DTTS_TRY(arch_check());
   dtts_vocoder* h = new dtts_vocoder();
   h->desc = *d;
@@ -323,7 +329,7 @@ extern "C" uint64_t dtts_vocode_workspace_bytes(const dtts_vocoder* h, int32_t B
   if (!h || B <= 0 || T <= 0) return 0;
   if (h->desc.precision != 0) {
     const TcGeom g = tc_geom(h, B, T);
-    const int planes = h->desc.precision == 1 ? 2 : 1;
+    const int planes = h->mode.a_planes;
     return planes * (ws_round(g.mel_plane_elems * 2) + 4 * ws_round(g.plane_elems * 2)) +
            3 * ws_round(g.stream_elems * 4) + 4096;
   }
@@ -408,8 +414,11 @@ extern "C" int dtts_vocode(dtts_vocoder* h, const float* mel, int32_t B, int32_t
 extern "C" int dtts_debug_tc_conv1d(const float* x, const float* w, const float* bias, const float* res, float* out,
                                     float* out_act, int32_t B, int32_t C_in, int32_t T_in, int32_t C_out, int32_t K,
                                     int32_t stride, int32_t padding, int32_t dilation, int32_t transposed,
-                                    float pre_slope, float post, float act_slope, int32_t split, void* scratch,
+                                    float pre_slope, float post, float act_slope, int32_t precision, void* scratch,
                                     uint64_t scratch_bytes, void* stream) {
+  if (precision < 1 || precision > 4) return fail(DTTS_ERR_BAD_ARG, "dtts_debug_tc_conv1d: precision must be 1..4");
+  const TcMode mode = tc_mode(precision);
+  const bool split = mode.a_planes == 2;
   if (!x || !w || !out || !scratch) return fail(DTTS_ERR_BAD_ARG, "dtts_debug_tc_conv1d: null argument");
   if (!transposed && stride != 1) return fail(DTTS_ERR_BAD_SHAPE, "tensor-core conv: stride must be 1");
   if (transposed && (K % stride || (K - stride) % 2 || padding != (K - stride) / 2))
@@ -418,40 +427,40 @@ extern "C" int dtts_debug_tc_conv1d(const float* x, const float* w, const float*
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e = tc_conv_init();
   if (e != cudaSuccess) return fail(DTTS_ERR_CUDA, std::string("tc_conv_init: ") + cudaGetErrorString(e));
-  const int planes = split ? 2 : 1;
+  const int planes = mode.w_planes;
   TcConvW cw;
   cw.C_in = C_in; cw.C_out = C_out; cw.N = C_out > 256 ? 256 : C_out; cw.KC = (C_in % 32 == 0) ? 32 : 16;
-  cw.ktaps = transposed ? K / stride : K; cw.phases = transposed ? stride : 1; cw.planes = planes; cw.bias = bias;
+  cw.ktaps = transposed ? K / stride : K; cw.phases = transposed ? stride : 1; cw.planes = planes; cw.fmt = mode.fmt; cw.bias = bias;
   if (C_out % cw.N || cw.N % 32 || C_in % cw.KC) return fail(DTTS_ERR_BAD_SHAPE, "tensor-core conv: unsupported channels");
   const int T_out = transposed ? (T_in - 1) * stride - 2 * padding + K : T_in + 2 * padding - dilation * (K - 1);
   if (T_out <= 0) return fail(DTTS_ERR_BAD_SHAPE, "tensor-core conv: empty output");
   Bump bump(scratch, scratch_bytes);
   const int rows_in = tc_rows(T_in), rows_out = tc_rows(T_out);
-  __nv_bfloat16* wp = bump.take<__nv_bfloat16>(cw.elems());
-  __nv_bfloat16* a_hi = bump.take<__nv_bfloat16>((size_t)B * C_in * rows_in);
-  __nv_bfloat16* a_lo = split ? bump.take<__nv_bfloat16>((size_t)B * C_in * rows_in) : nullptr;
-  __nv_bfloat16* o_hi = bump.take<__nv_bfloat16>((size_t)B * C_out * rows_out);
-  __nv_bfloat16* o_lo = split ? bump.take<__nv_bfloat16>((size_t)B * C_out * rows_out) : nullptr;
+  tc16* wp = bump.take<tc16>(cw.elems());
+  tc16* a_hi = bump.take<tc16>((size_t)B * C_in * rows_in);
+  tc16* a_lo = split ? bump.take<tc16>((size_t)B * C_in * rows_in) : nullptr;
+  tc16* o_hi = bump.take<tc16>((size_t)B * C_out * rows_out);
+  tc16* o_lo = split ? bump.take<tc16>((size_t)B * C_out * rows_out) : nullptr;
   float* o32 = bump.take<float>((size_t)B * C_out * T_out);
   float* r32 = res ? bump.take<float>((size_t)B * C_out * T_out) : nullptr;
   if (!bump.ok) return fail(DTTS_ERR_WORKSPACE_TOO_SMALL, "dtts_debug_tc_conv1d: scratch too small");
   cw.w = wp;
-  DTTS_CUDA(tc_pack_weights(w, wp, C_out, C_in, K, transposed, stride, cw.N, cw.KC, planes, s));
+  DTTS_CUDA(tc_pack_weights(w, wp, C_out, C_in, K, transposed, stride, cw.N, cw.KC, planes, mode.fmt, s));
   DTTS_CUDA(tc_zero_halo(a_hi, a_lo, B * (C_in / 8), rows_in, TC_PADF, T_in, s));
-  DTTS_CUDA(tc_to_planes(x, (long)C_in * T_in, T_in, 1, B, C_in, T_in, pre_slope, a_hi, a_lo, rows_in, TC_PADF, s));
+  DTTS_CUDA(tc_to_planes(x, (long)C_in * T_in, T_in, 1, B, C_in, T_in, pre_slope, a_hi, a_lo, rows_in, TC_PADF, mode.fmt, s));
   if (res) DTTS_CUDA(tc_nct_to_stream(res, r32, B, C_out, T_out, s));
   TcConvParams p{};
   p.a_hi = a_hi; p.a_lo = a_lo; p.a_bs = (long)C_in * rows_in; p.a_rows = rows_in; p.a_pad = TC_PADF;
   int nq;
   if (transposed) { p.tap_off0 = 0; p.tap_step = -1; nq = T_in + cw.ktaps - 1; }
   else { p.tap_off0 = -padding; p.tap_step = dilation; nq = T_out; }
-  tc_conv_plan(&p, cw, nq);
+  tc_conv_plan(&p, cw, nq, mode.a_planes);
   p.ot_mul = transposed ? stride : 1; p.ot_add = transposed ? -padding : 0; p.T_out = T_out;
   p.o32 = o32; p.res = r32; p.o32_bs = (long)C_out * T_out;
   p.o_hi = o_hi; p.o_lo = o_lo; p.op_bs = (long)C_out * rows_out; p.op_rows = rows_out; p.op_pad = TC_PADF;
   p.post = post; p.slope = act_slope; p.accumulate = 0;
   DTTS_CUDA(launch_tc_conv(p, B, s));
   DTTS_CUDA(tc_stream_to_nct(o32, out, B, C_out, T_out, s));
-  if (out_act) DTTS_CUDA(tc_planes_to_nct(o_hi, o_lo, out_act, B, C_out, T_out, rows_out, TC_PADF, s));
+  if (out_act) DTTS_CUDA(tc_planes_to_nct(o_hi, o_lo, out_act, B, C_out, T_out, rows_out, TC_PADF, mode.fmt, s));
   return DTTS_OK;
 }

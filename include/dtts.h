@@ -67,7 +67,8 @@ typedef struct dtts_vocoder_desc {
   int32_t up_rates[DTTS_MAX_UPS], up_kernels[DTTS_MAX_UPS];
   int32_t rb_kernels[DTTS_MAX_RB];
   int32_t rb_dilations[DTTS_MAX_RB][3];
-  int32_t precision; /* 0 = fp32 FMA pipe; 1 = tcgen05, bf16 hi/lo split (3 MMAs, fp32-class accuracy); 2 = tcgen05, single bf16 */
+  int32_t precision; /* 0 = fp32 FMA pipe; tcgen05 modes: 1 = bf16 hi/lo x hi/lo (3 MMAs, fp32-class accuracy),
+                        2 = bf16 (1 MMA), 3 = fp16 activations x fp16 hi/lo weights (2 MMAs), 4 = fp16 (1 MMA) */
 } dtts_vocoder_desc;
 
 typedef struct dtts_acoustic dtts_acoustic; /* opaque */
@@ -158,11 +159,12 @@ int dtts_debug_conv1d(const float* x_dev, const float* w_dev, const float* bias_
 /* Unit-test hook for the tcgen05 tensor-core convolution of the HiFi-GAN stack (stride-1 Conv1d, or
  * ConvTranspose1d with K % stride == 0 and padding == (K-stride)/2).  x [B,C_in,T_in] -> out [B,C_out,T_out] =
  * post * (conv(leaky(x, pre_slope)) + bias + res); out_act (optional) = leaky(out, act_slope) as it is handed to the next
- * layer (bf16 hi+lo planes when split != 0, one bf16 plane otherwise).  scratch_dev: caller-provided device scratch. */
+ * layer (hi [+ lo] 16-bit planes, reconstructed to fp32).  precision: 1..4 as dtts_vocoder_desc.precision.
+ * scratch_dev: caller-provided device scratch. */
 int dtts_debug_tc_conv1d(const float* x_dev, const float* w_dev, const float* bias_dev, const float* res_dev,
                          float* out_dev, float* out_act_dev, int32_t B, int32_t C_in, int32_t T_in, int32_t C_out,
                          int32_t K, int32_t stride, int32_t padding, int32_t dilation, int32_t transposed,
-                         float pre_slope, float post, float act_slope, int32_t split, void* scratch_dev,
+                         float pre_slope, float post, float act_slope, int32_t precision, void* scratch_dev,
                          uint64_t scratch_bytes, void* stream);
 
 #ifdef __cplusplus

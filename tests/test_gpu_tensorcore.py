@@ -36,7 +36,7 @@ TC_CONV_SHAPES = [
 ]
 
 
-def _run_tc_conv(shape, split, with_res):
+def _run_tc_conv(shape, precision, with_res):
     B, Ci, Ti, Co, K, s, p, d, tr, slope = shape
     lib = binding.load()
     g = torch.Generator().manual_seed(sum(shape[:9]) + 7)
@@ -56,7 +56,7 @@ def _run_tc_conv(shape, split, with_res):
     scratch = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     rc = lib.dtts_debug_tc_conv1d(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), rd.data_ptr() if rd is not None else None,
                                   out.data_ptr(), act.data_ptr(), B, Ci, Ti, Co, K, s, p, d, tr, C.c_float(slope),
-                                  C.c_float(post), C.c_float(0.1), split, scratch.data_ptr(), scratch.numel(),
+                                  C.c_float(post), C.c_float(0.1), precision, scratch.data_ptr(), scratch.numel(),
                                   torch.cuda.current_stream().cuda_stream)
     binding.check(rc, "debug_tc_conv1d")
     torch.cuda.synchronize()
@@ -65,7 +65,7 @@ def _run_tc_conv(shape, split, with_res):
 
 @pytest.mark.parametrize("shape", TC_CONV_SHAPES)
 def test_tc_conv_split_matches_torch(shape):
-    out, act, ref = _run_tc_conv(shape, split=1, with_res=False)
+    out, act, ref = _run_tc_conv(shape, precision=1, with_res=False)
     scale = max(1.0, ref.abs().max().item())
     err = (out - ref).abs().max().item()
     assert err < 1e-4 * scale, err           # hi/lo split: ~2^-16 relative per product
@@ -75,15 +75,37 @@ def test_tc_conv_split_matches_torch(shape):
 
 @pytest.mark.parametrize("shape", TC_CONV_SHAPES[2:5])
 def test_tc_conv_residual_and_scale(shape):
-    out, _, ref = _run_tc_conv(shape, split=1, with_res=True)
+    out, _, ref = _run_tc_conv(shape, precision=1, with_res=True)
     assert (out - ref).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())
 
 
 @pytest.mark.parametrize("shape", [TC_CONV_SHAPES[0], TC_CONV_SHAPES[3], TC_CONV_SHAPES[7]])
 def test_tc_conv_bf16_single_pass(shape):
-    out, _, ref = _run_tc_conv(shape, split=0, with_res=False)
+    out, _, ref = _run_tc_conv(shape, precision=2, with_res=False)
     # one bf16 rounding per operand: relative error ~2^-8 per product, averaged over the reduction
     assert (out - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("precision,tol", [(3, 1.5e-3), (4, 3e-3)])
+@pytest.mark.parametrize("shape", [TC_CONV_SHAPES[0], TC_CONV_SHAPES[1], TC_CONV_SHAPES[3], TC_CONV_SHAPES[6],
+                                   TC_CONV_SHAPES[8], TC_CONV_SHAPES[10]])
+def test_tc_conv_fp16_modes(shape, precision, tol):
+    """precision 3: fp16 activations x (hi + lo) fp16 weights -- only the 2^-12 activation rounding is left;
+    precision 4: one fp16 rounding per operand."""
+    out, act, ref = _run_tc_conv(shape, precision=precision, with_res=False)
+    scale = max(1.0, ref.abs().max().item())
+    assert (out - ref).abs().max().item() < tol * scale
+    # the activation plane handed to the next layer is leaky(out) rounded once to fp16
+    want_act = F.leaky_relu(out, 0.1)
+    assert (act - want_act).abs().max().item() < 6e-4 * scale
+
+
+def test_tc_conv_weight_split_is_tighter_than_single_fp16():
+    shape = TC_CONV_SHAPES[3]
+    o3, _, ref = _run_tc_conv(shape, precision=3, with_res=False)
+    o4, _, _ = _run_tc_conv(shape, precision=4, with_res=False)
+    e3, e4 = (o3 - ref).pow(2).mean().sqrt().item(), (o4 - ref).pow(2).mean().sqrt().item()
+    assert e3 < e4
 
 
 @pytest.fixture(scope="module")
@@ -129,6 +151,38 @@ def test_tc_vocoder_batch_equals_single(vocoder_tc):
     for b in range(3):
         one = eng(mel[b:b + 1])
         assert torch.equal(one[0], full[b])
+
+
+@pytest.mark.parametrize("precision", [3, 4])
+def test_fp16_vocoder_modes_within_tolerance(precision, golden_dir):
+    """fp16 operand modes: measured against the reference-generated golden waveforms with the north-star tolerance.
+    Mode 3 (2 MMAs) is the default of bench.py; mode 4 (1 MMA) holds the tolerance with less margin."""
+    from dict_tts_b200.engine import HifiGanEngine
+    eng = HifiGanEngine(synth.make_vocoder_state_dict(VOCODER_SEED), precision=precision)
+    for name, kw in sorted(VOCODER_CASES.items()):
+        gold = np.load(os.path.join(golden_dir, name + ".npz"))["wav"]
+        wav = eng(synth.make_mel(kw["seed"], kw["B"], kw["T"])).cpu().numpy()
+        rms = float(np.sqrt(np.mean((wav - gold) ** 2)))
+        print(f"precision {precision} {name}: wav rms err {rms:.3e}")
+        assert rms < TOL_WAV_RMS, (name, rms)
+    eng.close()
+
+
+def test_fp16_vocoder_long_batch_vs_fp32_path():
+    from dict_tts_b200.engine import HifiGanEngine
+    mel = synth.make_mel(31, 3, 150)
+    ref_eng = HifiGanEngine(synth.make_vocoder_state_dict(VOCODER_SEED), precision=0)
+    ref = ref_eng(mel)
+    for precision in (3, 4):
+        eng = HifiGanEngine(synth.make_vocoder_state_dict(VOCODER_SEED), precision=precision)
+        wav = eng(mel)
+        rms = (wav - ref).pow(2).mean().sqrt().item()
+        print(f"precision {precision} T=150: wav rms err {rms:.3e}")
+        assert rms < TOL_WAV_RMS, (precision, rms)
+        for b in range(3):                                   # batching never changes a sample
+            assert torch.equal(eng(mel[b:b + 1])[0], wav[b])
+        eng.close()
+    ref_eng.close()
 
 
 def test_bf16_vocoder_error_is_bounded():

@@ -14,7 +14,7 @@ if __name__ == "__main__":
     for i in which:
         shape = TC_CONV_SHAPES[i]
         try:
-            out, act, ref = _run_tc_conv(shape, 1, False)
+            out, act, ref = _run_tc_conv(shape, int(os.environ.get("DTTS_TC_PRECISION", "1")), False)
             err = (out - ref).abs()
             print(i, shape, "max err %.3e  mean err %.3e  ref max %.2f  nan %d" %
                   (err.max().item(), err.mean().item(), ref.abs().max().item(), int(torch.isnan(out).sum())), flush=True)
