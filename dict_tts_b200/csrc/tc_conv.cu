@@ -134,20 +134,41 @@ __device__ __forceinline__ float back16(uint32_t h, int fmt) {
   if (fmt) return __bfloat162float(__ushort_as_bfloat16((unsigned short)h));
   return __half2float(__ushort_as_half((unsigned short)h));
 }
+// two consecutive channels -> one packed 32-bit word with a single F2FP instruction (fp16 saturates to the finite range)
+__device__ __forceinline__ uint32_t pack2(float a0, float a1, int fmt) {
+  if (fmt) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+  const __half2 lim = __floats2half2_rn(65504.f, 65504.f);
+  const __half2 h = __hmin2(__hmax2(__floats2half2_rn(a0, a1), __hneg2(lim)), lim);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
 // two consecutive channels -> packed hi word and (residual) lo word
 __device__ __forceinline__ void split2(float a0, float a1, int fmt, uint32_t& hw, uint32_t& lw) {
-  const uint32_t h0 = cvt16(a0, fmt), h1 = cvt16(a1, fmt);
-  hw = h0 | (h1 << 16);
-  lw = cvt16(a0 - back16(h0, fmt), fmt) | (cvt16(a1 - back16(h1, fmt), fmt) << 16);
+  hw = pack2(a0, a1, fmt);
+  lw = pack2(a0 - back16(hw & 0xFFFFu, fmt), a1 - back16(hw >> 16, fmt), fmt);
 }
 
-// Work decode.  A unit = csize consecutive row tiles (row tile rt = b * ntiles + time tile) of one weight group
-// g = nblock*phases + phase; the CTA of cluster rank r takes row tile (unit % nu) * csize + r.  Row tiles past the end
-// are dummies: they follow the weight pipeline (the peers depend on it) but issue no MMAs and store nothing.
+
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+
+// Work decode.  A unit = csize consecutive row tiles (row tile rt = b * ntiles + time tile) of one output-channel
+// block; the CTA of cluster rank r takes row tile (unit % nu) * csize + r.  A cluster walks its units
+// (cluster_id, cluster_id + nclusters, ...) and, inside each unit, ALL polyphase components of a transposed convolution
+// back to back (weight group g = nblock*phases + phase): the interleaved output samples t = q*stride + phase of one row
+// tile are then written by the same SM within a few microseconds and merge into full sectors in L2 instead of
+// reaching HBM as partial-sector read-modify-writes.  Row tiles past the end are dummies: they follow the weight
+// pipeline (the peers depend on it) but issue no MMAs and store nothing.
 struct TileCoord { int q0, g, b; bool dummy; };
-__device__ __forceinline__ TileCoord decode_unit(const TcConvParams& p, int unit, int rank) {
+__device__ __forceinline__ TileCoord decode_unit(const TcConvParams& p, int it, int cluster_id, int nclusters, int rank) {
   TileCoord c;
-  c.g = unit / p.nu;
+  const int unit = cluster_id + (it / p.phases) * nclusters;
+  c.g = (unit / p.nu) * p.phases + it % p.phases;
   int rt = (unit % p.nu) * p.csize + rank;
   const int nrt = p.ntiles * p.B;
   c.dummy = rt >= nrt;
@@ -157,32 +178,81 @@ __device__ __forceinline__ TileCoord decode_unit(const TcConvParams& p, int unit
   return c;
 }
 
-__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
-  uint64_t d;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
-  return d;
-}
+// Everything the MMA-issuing warp needs, precomputed once (descriptor low words are in units of 16 B).
+struct MmaCtx {
+  uint32_t bar0, tmem_base;
+  uint32_t a_low0, b_low0;          // start >> 4 | LBO >> 4 << 16 of stage 0
+  uint32_t a_stage16, w_blob16;     // stage strides
+  uint32_t w_tap16;                 // one tap inside a weight stage
+  uint32_t a_kstep, b_kstep;        // +K step (two 8-channel slabs)
+  uint32_t a_plane, b_plane;        // + lo plane
+  uint32_t idesc, idesc_n;          // instruction descriptors with N = NM (main) and N = p.N (a_lo x w_hi when stacked)
+  int cluster_id, nclusters, n_it, rank, csize;
+  uint16_t cmask;
+};
 
-// All MMAs of one (K chunk, tap) weight blob into one 128-row accumulator.  Descriptors differ only in their low
-// word (start address >> 4), so a time shift / K step / lo plane is one 32-bit add; fully unrolled per operand mode so
-// that the single issuing thread spends a couple of instructions per tcgen05.mma (it is the serial resource of the CTA).
-template <int KSTEPS, int APL, int WPL>
-__device__ __forceinline__ void issue_mmas(uint32_t d, uint32_t a_lo, uint32_t a_hiw, uint32_t b_lo, uint32_t b_hiw,
-                                           uint32_t a_kstep, uint32_t b_kstep, uint32_t a_plane, uint32_t b_plane,
-                                           uint32_t idesc, uint32_t first) {
+// The MMA-issuing warp.  One elected lane issues; the loop is instantiated per operand mode so that the single issuing
+// thread -- the serial resource of the CTA -- spends a handful of uniform-datapath instructions per tcgen05.mma.
+//   WMODE 0: one weight plane; 1: hi and lo planes, one MMA each; 2: hi | lo stacked along N (one MMA, the epilogue adds
+//   the two column halves) -- an M=128,K=16 MMA costs max(64, N/2) cycles (A is read from shared memory at 64 B/clk), so
+//   for C_out <= 64 the second weight plane is free this way.
+template <int KSTEPS, int APL, int WMODE>
+__device__ __forceinline__ void mma_warp_loop(const TcConvParams& p, const MmaCtx& x) {
+  if (elect_one()) {                                 // ONE thread runs the whole loop: waits, MMAs and commits
+    const uint32_t hiw = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
+    const int ktaps = p.ktaps, nchunks = p.nchunks, tap_step = p.tap_step, w_stages = p.w_stages, a_stages = p.a_stages;
+    const int NM = p.NM, TG = p.TG;
+    const uint32_t tap0 = (uint32_t)(p.tap_off0 - p.min_off);
+    auto bar = [&](int i) { return x.bar0 + 8u * (uint32_t)i; };  // [0..1] a_full [2..3] a_empty [4..9] w_full [10..15] w_empty
+    int sa = 0, sw = 0;
+    uint32_t pa = 0, pw = 0;                         // stage cursors + phase parities (no div/mod in this loop)
+    int t_it = 0;
+    for (int it = 0; it < x.n_it; ++it, ++t_it) {
+      const int nacc = decode_unit(p, it, x.cluster_id, x.nclusters, x.rank).dummy ? 0 : p.NACC;
+      const int as = t_it & 1;
+      mbar_wait(bar(18 + as), ((t_it >> 1) & 1) ^ 1);  // acc_empty: the epilogue has drained this accumulator set
+      tc_fence_after();
+      const uint32_t d_base = x.tmem_base + (uint32_t)(as * 256);
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(bar(sa), pa);                      // a_full
+        tc_fence_after();
+        uint32_t a_tap = x.a_low0 + (uint32_t)sa * x.a_stage16 + tap0;
+        for (int j0 = 0; j0 < ktaps; j0 += TG) {     // one weight stage = TG consecutive taps of this K chunk
+          mbar_wait(bar(4 + sw), pw);                // w_full
+          tc_fence_after();
+          uint32_t b_lo = x.b_low0 + (uint32_t)sw * x.w_blob16;
+          const int j1 = min(j0 + TG, ktaps);
+          for (int j = j0; j < j1; ++j, a_tap += (uint32_t)tap_step, b_lo += x.w_tap16) {
+            const uint32_t first = (c | j) != 0 ? 1u : 0u;
+            uint32_t d = d_base, am = a_tap;
+            for (int m = 0; m < nacc; ++m, d += (uint32_t)NM, am += 128u) {
 #pragma unroll
-  for (int ks = 0; ks < KSTEPS; ++ks) {
-    const uint64_t a = desc64(a_lo + ks * a_kstep, a_hiw), b = desc64(b_lo + ks * b_kstep, b_hiw);
-    umma_bf16(d, a, b, idesc, ks == 0 ? first : 1u);
-    if (WPL == 2) umma_bf16(d, a, desc64(b_lo + ks * b_kstep + b_plane, b_hiw), idesc, 1u);
-    if (APL == 2) umma_bf16(d, desc64(a_lo + ks * a_kstep + a_plane, a_hiw), b, idesc, 1u);
+              for (int ks = 0; ks < KSTEPS; ++ks) {
+                const uint64_t a = desc64(am + ks * x.a_kstep, hiw), b = desc64(b_lo + ks * x.b_kstep, hiw);
+                umma_bf16(d, a, b, x.idesc, ks == 0 ? first : 1u);
+                if (WMODE == 1) umma_bf16(d, a, desc64(b_lo + ks * x.b_kstep + x.b_plane, hiw), x.idesc, 1u);
+                if (APL == 2)
+                  umma_bf16(d, desc64(am + ks * x.a_kstep + x.a_plane, hiw), b, WMODE == 2 ? x.idesc_n : x.idesc, 1u);
+              }
+            }
+          }
+          if (x.csize > 1) umma_commit_mc(bar(10 + sw), x.cmask);   // w_empty here and at every peer's producer
+          else umma_commit(bar(10 + sw));
+          if (++sw == w_stages) { sw = 0; pw ^= 1u; }
+        }
+        umma_commit(bar(2 + sa));                                     // a_empty
+        if (c == nchunks - 1) umma_commit(bar(16 + as));              // acc_full
+        if (++sa == a_stages) { sa = 0; pa ^= 1u; }
+      }
+    }
   }
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int N = p.N, KC = p.KC, APL = p.a_planes, WPL = p.w_planes;
+  const int N = p.N, NM = p.NM, KC = p.KC, APL = p.a_planes, WPL = p.w_planes;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   // bars: [0..1] a_full, [2..3] a_empty, [4..9] w_full, [10..15] w_empty, [16..17] acc_full, [18..19] acc_empty
@@ -198,14 +268,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
 
   const uint32_t a_plane_bytes = (uint32_t)(KC / 8) * p.RA * 16u;
   const uint32_t a_stage_bytes = a_plane_bytes * APL;
-  const uint32_t w_plane_bytes = (uint32_t)N * KC * 2u;
-  const uint32_t w_blob_bytes = w_plane_bytes * WPL;
+  const uint32_t w_plane_bytes = (uint32_t)NM * KC * 2u;      // NM = 2N when hi | lo are stacked along N (then WPL = 1)
+  const uint32_t w_tap_bytes = w_plane_bytes * WPL;             // one (K chunk, tap) blob
+  const uint32_t w_blob_bytes = w_tap_bytes * (uint32_t)p.TG;   // one weight stage = TG consecutive taps
   const uint32_t a_base = smem_u32(smem + kSmemHeader);
   const uint32_t w_base = a_base + p.a_stages * a_stage_bytes;
-  const int total_units = p.nu * p.nblocks * p.phases;
+  const int total_units = p.nu * p.nblocks;                      // x phases each
   const int csize = p.csize;
   const int rank = csize > 1 ? (int)cluster_ctarank() : 0;
   const int cluster_id = blockIdx.x / csize, nclusters = gridDim.x / csize;
+  const int n_it = (total_units - cluster_id + nclusters - 1) / nclusters * p.phases;   // (unit, phase) steps of this cluster
   const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
 
   if (threadIdx.x == 0) {
@@ -232,8 +304,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
     const uint32_t row_bytes = (uint32_t)p.RA * 16u;
     int s = 0;
     uint32_t ph = 1;                                             // producers start on the "previous phase done" parity
-    for (int unit = cluster_id; unit < total_units; unit += nclusters) {
-      const TileCoord tc = decode_unit(p, unit, rank);
+    for (int it = 0; it < n_it; ++it) {
+      const TileCoord tc = decode_unit(p, it, cluster_id, nclusters, rank);
       const size_t row0 = (size_t)(p.a_pad + tc.q0 + p.min_off);
       for (int c = 0; c < p.nchunks; ++c) {
         mbar_wait(a_empty(s), ph);
@@ -253,86 +325,62 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
     }
   } else if (warp == 1) {
     // ------------------------------------------------ weight producer
-    const size_t blob_elems = (size_t)w_blob_bytes / 2;
+    const size_t tap_elems = (size_t)w_tap_bytes / 2;
     const int per_tile = p.nchunks * p.ktaps;
-    const uint32_t slice_bytes = w_blob_bytes / (uint32_t)csize;      // this CTA's share of every blob
+    const uint32_t tap_slice = w_tap_bytes / (uint32_t)csize;         // this CTA's share of every stage, per tap in it
     int s = 0;
     uint32_t ph = 1;
-    for (int unit = cluster_id; unit < total_units; unit += nclusters) {
-      const TileCoord tc = decode_unit(p, unit, rank);
-      const tc16* wg = p.w + (size_t)tc.g * per_tile * blob_elems;
-      for (int i = 0; i < per_tile; ++i) {
-        mbar_wait(w_empty(s), ph);                                    // released by the MMA warps of ALL peers
-        if (elect_one()) {
-          mbar_arrive_expect_tx(w_full(s), w_blob_bytes);             // the whole blob lands here, one slice per peer
-          const uint32_t dst = w_base + s * w_blob_bytes + rank * slice_bytes;
-          const tc16* src = wg + (size_t)i * blob_elems + (size_t)rank * (slice_bytes / 2);
-          if (csize > 1) bulk_g2s_mc(dst, src, slice_bytes, w_full(s), cmask);
-          else bulk_g2s(dst, src, slice_bytes, w_full(s));
+    for (int it = 0; it < n_it; ++it) {
+      const TileCoord tc = decode_unit(p, it, cluster_id, nclusters, rank);
+      const tc16* wg = p.w + (size_t)tc.g * per_tile * tap_elems;
+      for (int c = 0; c < p.nchunks; ++c) {
+        for (int j0 = 0; j0 < p.ktaps; j0 += p.TG) {
+          const uint32_t ntap = (uint32_t)min(p.TG, p.ktaps - j0);
+          mbar_wait(w_empty(s), ph);                                  // released by the MMA warps of ALL peers
+          if (elect_one()) {
+            mbar_arrive_expect_tx(w_full(s), ntap * w_tap_bytes);     // the whole stage lands here, one slice per peer
+            // the ntap tap blobs are contiguous in global and in shared memory: peer r copies bytes [r, r+1) * slice
+            const uint32_t slice = ntap * tap_slice;
+            const uint32_t dst = w_base + s * w_blob_bytes + rank * slice;
+            const tc16* src = wg + (size_t)(c * p.ktaps + j0) * tap_elems + (size_t)rank * (slice / 2);
+            if (csize > 1) bulk_g2s_mc(dst, src, slice, w_full(s), cmask);
+            else bulk_g2s(dst, src, slice, w_full(s));
+          }
+          __syncwarp();
+          if (++s == p.w_stages) { s = 0; ph ^= 1u; }
         }
-        __syncwarp();
-        if (++s == p.w_stages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 2) {
     // ------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
+    MmaCtx x;
     // instruction descriptor: D=f32 @4, A/B format @7/@10 (0 = f16, 1 = bf16), both K-major, N>>3 @17, M>>4 @24
     const uint32_t f16b = p.fmt ? 1u : 0u;
-    const uint32_t idesc = (1u << 4) | (f16b << 7) | (f16b << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
-    // shared-memory descriptors: high word = SBO (128 B) | version 1 << 14; low word = start >> 4 | LBO >> 4 << 16
-    const uint32_t hiw = (128u >> 4) | (1u << 14);
-    const uint32_t a_low0 = ((a_base >> 4) & 0x3FFFu) | ((uint32_t)p.RA << 16);      // LBO = RA * 16 B
-    const uint32_t b_low0 = ((w_base >> 4) & 0x3FFFu) | ((uint32_t)N << 16);         // LBO = N * 16 B
-    const uint32_t a_stage16 = a_stage_bytes >> 4, w_blob16 = w_blob_bytes >> 4;
-    // low-word steps (units of 16 B): +2*RA per K step (two slabs), +128 per accumulator, + plane size for the lo plane
-    const uint32_t a_kstep = 2u * (uint32_t)p.RA, b_kstep = 2u * (uint32_t)N;
-    const uint32_t a_plane = a_plane_bytes >> 4, b_plane = w_plane_bytes >> 4;
-    const int variant = (KC == 32 ? 3 : 0) + (APL == 2 ? 2 : (WPL == 2 ? 1 : 0));
-    const int tap0 = p.tap_off0 - p.min_off;
-    int sa = 0, sw = 0;
-    uint32_t pa = 0, pw = 0;                                      // stage cursors + phase parities (no div/mod here)
-    int t_it = 0;
-    for (int unit = cluster_id; unit < total_units; unit += nclusters, ++t_it) {
-      const bool dummy = decode_unit(p, unit, rank).dummy;
-      const int nacc = dummy ? 0 : p.NACC;
-      const int as = t_it & 1;
-      mbar_wait(acc_empty(as), ((t_it >> 1) & 1) ^ 1);            // epilogue has drained this accumulator set
-      tc_fence_after();
-      const uint32_t d_base = tmem_base + (uint32_t)(as * 256);
-      for (int c = 0; c < p.nchunks; ++c) {
-        mbar_wait(a_full(sa), pa);
-        tc_fence_after();
-        const uint32_t a_lo_stage = a_low0 + (uint32_t)sa * a_stage16;
-        for (int j = 0; j < p.ktaps; ++j) {
-          mbar_wait(w_full(sw), pw);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t b_lo = b_low0 + (uint32_t)sw * w_blob16;
-            const uint32_t a_lo = a_lo_stage + (uint32_t)(tap0 + j * p.tap_step);
-            const uint32_t first = (c | j) != 0 ? 1u : 0u;
-            for (int m = 0; m < nacc; ++m) {
-              const uint32_t d = d_base + (uint32_t)(m * N), am = a_lo + (uint32_t)(m * 128);
-              switch (variant) {
-                case 0: issue_mmas<1, 1, 1>(d, am, hiw, b_lo, hiw, a_kstep, b_kstep, a_plane, b_plane, idesc, first); break;
-                case 1: issue_mmas<1, 1, 2>(d, am, hiw, b_lo, hiw, a_kstep, b_kstep, a_plane, b_plane, idesc, first); break;
-                case 2: issue_mmas<1, 2, 2>(d, am, hiw, b_lo, hiw, a_kstep, b_kstep, a_plane, b_plane, idesc, first); break;
-                case 3: issue_mmas<2, 1, 1>(d, am, hiw, b_lo, hiw, a_kstep, b_kstep, a_plane, b_plane, idesc, first); break;
-                case 4: issue_mmas<2, 1, 2>(d, am, hiw, b_lo, hiw, a_kstep, b_kstep, a_plane, b_plane, idesc, first); break;
-                default: issue_mmas<2, 2, 2>(d, am, hiw, b_lo, hiw, a_kstep, b_kstep, a_plane, b_plane, idesc, first); break;
-              }
-            }
-            if (csize > 1) umma_commit_mc(w_empty(sw), cmask);   // weight slot free (here and at every peer's producer)
-            else umma_commit(w_empty(sw));                       // once these MMAs have read it
-            if (j == p.ktaps - 1) {
-              umma_commit(a_empty(sa));
-              if (c == p.nchunks - 1) umma_commit(acc_full(as));
-            }
-          }
-          __syncwarp();
-          if (++sw == p.w_stages) { sw = 0; pw ^= 1u; }
-        }
-        if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
-      }
+    const uint32_t ibase = (1u << 4) | (f16b << 7) | (f16b << 10) | ((128u >> 4) << 24);
+    x.idesc = ibase | ((uint32_t)(NM >> 3) << 17);
+    x.idesc_n = ibase | ((uint32_t)(N >> 3) << 17);
+    x.bar0 = bar0; x.tmem_base = tmem_base;
+    x.a_low0 = ((a_base >> 4) & 0x3FFFu) | ((uint32_t)p.RA << 16);      // LBO = RA * 16 B
+    x.b_low0 = ((w_base >> 4) & 0x3FFFu) | ((uint32_t)NM << 16);        // LBO = NM * 16 B
+    x.a_stage16 = a_stage_bytes >> 4; x.w_blob16 = w_blob_bytes >> 4; x.w_tap16 = w_tap_bytes >> 4;
+    x.a_kstep = 2u * (uint32_t)p.RA; x.b_kstep = 2u * (uint32_t)NM;
+    x.a_plane = a_plane_bytes >> 4; x.b_plane = w_plane_bytes >> 4;
+    x.cluster_id = cluster_id; x.nclusters = nclusters; x.n_it = n_it; x.rank = rank; x.csize = csize;
+    x.cmask = cmask;
+    const int wmode = p.stack ? 2 : (WPL == 2 ? 1 : 0);
+    switch ((KC == 32 ? 6 : 0) + (APL == 2 ? 3 : 0) + wmode) {
+      case 0: mma_warp_loop<1, 1, 0>(p, x); break;
+      case 1: mma_warp_loop<1, 1, 1>(p, x); break;
+      case 2: mma_warp_loop<1, 1, 2>(p, x); break;
+      case 3: mma_warp_loop<1, 2, 0>(p, x); break;
+      case 4: mma_warp_loop<1, 2, 1>(p, x); break;
+      case 5: mma_warp_loop<1, 2, 2>(p, x); break;
+      case 6: mma_warp_loop<2, 1, 0>(p, x); break;
+      case 7: mma_warp_loop<2, 1, 1>(p, x); break;
+      case 8: mma_warp_loop<2, 1, 2>(p, x); break;
+      case 9: mma_warp_loop<2, 2, 0>(p, x); break;
+      case 10: mma_warp_loop<2, 2, 1>(p, x); break;
+      default: mma_warp_loop<2, 2, 2>(p, x); break;
     }
   } else {
     // ------------------------------------------------ epilogue (warps 3..10; two warps per TMEM lane quadrant)
@@ -347,8 +395,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
     const int ncc = N / 32;
     const int nitems = p.NACC * ncc;
     int t_it = 0;
-    for (int unit = cluster_id; unit < total_units; unit += nclusters, ++t_it) {
-      const TileCoord tc = decode_unit(p, unit, rank);
+    for (int it = 0; it < n_it; ++it, ++t_it) {
+      const TileCoord tc = decode_unit(p, it, cluster_id, nclusters, rank);
       const int phase = tc.g % p.phases, co_off = (tc.g / p.phases) * N;
       const int as = t_it & 1;
       const float* resb = p.res ? p.res + (size_t)tc.b * p.o32_bs : nullptr;
@@ -385,19 +433,39 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
         item_row(idx, t, ok);
         uint32_t r[32];
         __syncwarp();                                  // tcgen05.ld is .sync.aligned
-        tmem_ld32_nowait(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256 + m * N + cc * 32), r);
+        const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256 + m * NM + cc * 32);
+        tmem_ld32_nowait(tcol, r);
         float4 rn[8];
         if (idx + 2 < nitems) load_res(idx + 2, rn);   // next item's residual is in flight while this one is processed
+        if (p.stack) {                                 // a*w_lo landed N columns further: fold it in
+          uint32_t r2[32];
+          tmem_ld32_nowait(tcol + (uint32_t)N, r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) + __uint_as_float(r2[k]));
+        }
         tmem_ld_wait();
         if (ok) {
           const int n0 = co_off + cc * 32;
           float v[32];
+          const float4* bs4 = reinterpret_cast<const float4*>(bias_s + n0);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            v[4 * k] = (__uint_as_float(r[4 * k]) + bias_s[n0 + 4 * k] + rc[k].x) * p.post;
-            v[4 * k + 1] = (__uint_as_float(r[4 * k + 1]) + bias_s[n0 + 4 * k + 1] + rc[k].y) * p.post;
-            v[4 * k + 2] = (__uint_as_float(r[4 * k + 2]) + bias_s[n0 + 4 * k + 2] + rc[k].z) * p.post;
-            v[4 * k + 3] = (__uint_as_float(r[4 * k + 3]) + bias_s[n0 + 4 * k + 3] + rc[k].w) * p.post;
+            const float4 bq = bs4[k];
+            v[4 * k] = __uint_as_float(r[4 * k]) + bq.x;
+            v[4 * k + 1] = __uint_as_float(r[4 * k + 1]) + bq.y;
+            v[4 * k + 2] = __uint_as_float(r[4 * k + 2]) + bq.z;
+            v[4 * k + 3] = __uint_as_float(r[4 * k + 3]) + bq.w;
+          }
+          if (resb) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              v[4 * k] += rc[k].x; v[4 * k + 1] += rc[k].y; v[4 * k + 2] += rc[k].z; v[4 * k + 3] += rc[k].w;
+            }
+          }
+          if (p.post != 1.f) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] *= p.post;
           }
           if (o32b) {
             float4* op = reinterpret_cast<float4*>(o32b) + ((size_t)(n0 / 4) * p.T_out + t);
@@ -416,15 +484,31 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
           }
           if (p.o_hi) {
             const size_t prow = (size_t)tc.b * p.op_bs + ((size_t)(n0 / 8) * p.op_rows + p.op_pad + t) * 8;
+            // leaky(v) = max(v, slope * v) for 0 <= slope <= 1 (all HiFi-GAN slopes)
+            if (split) {
 #pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              uint32_t hw[4], lw[4];
+              for (int h = 0; h < 4; ++h) {
+                uint32_t hw[4], lw[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e)
-                split2(leaky(v[8 * h + 2 * e], p.slope), leaky(v[8 * h + 2 * e + 1], p.slope), fmt, hw[e], lw[e]);
-              const size_t off = prow + (size_t)h * p.op_rows * 8;
-              *reinterpret_cast<uint4*>(p.o_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-              if (split) *reinterpret_cast<uint4*>(p.o_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                for (int e = 0; e < 4; ++e) {
+                  const float a0 = v[8 * h + 2 * e], a1 = v[8 * h + 2 * e + 1];
+                  split2(fmaxf(a0, a0 * p.slope), fmaxf(a1, a1 * p.slope), fmt, hw[e], lw[e]);
+                }
+                const size_t off = prow + (size_t)h * p.op_rows * 8;
+                *reinterpret_cast<uint4*>(p.o_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                *reinterpret_cast<uint4*>(p.o_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+              }
+            } else {
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                uint32_t hw[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float a0 = v[8 * h + 2 * e], a1 = v[8 * h + 2 * e + 1];
+                  hw[e] = pack2(fmaxf(a0, a0 * p.slope), fmaxf(a1, a1 * p.slope), fmt);
+                }
+                *reinterpret_cast<uint4*>(p.o_hi + prow + (size_t)h * p.op_rows * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              }
             }
           }
         }
@@ -451,16 +535,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void tc_pack_weights_kernel(const float* __restrict__ w, tc16* __restrict__ out, int C_out,
                                        int C_in, int K, int transposed, int stride, int N, int KC, int planes,
-                                       int ktaps, int phases, int fmt) {
-  const size_t total = (size_t)C_out * C_in * ktaps * phases * planes;
+                                       int ktaps, int phases, int fmt, int stack) {
+  const size_t total = (size_t)C_out * C_in * ktaps * phases * planes * (stack ? 2 : 1);
+  const int NMs = stack ? 2 * N : N;                 // rows per K slab of one blob plane
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   // destination index [g][chunk][tap][plane][slab][n][e]
   size_t r = i;
   const int e = r % 8; r /= 8;
-  const int n = r % N; r /= N;
+  int n = r % NMs; r /= NMs;
   const int sl = r % (KC / 8); r /= (KC / 8);
-  const int pl = r % planes; r /= planes;
+  int pl = r % planes; r /= planes;
+  if (stack) { pl = n >= N; n -= pl * N; }           // stacked: rows [0,N) = hi, [N,2N) = lo of the same channel
   const int j = r % ktaps; r /= ktaps;
   const int nchunks = C_in / KC;
   const int c = r % nchunks; r /= nchunks;
@@ -582,9 +668,10 @@ static int env_int(const char* name, int dflt) {
 void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq, int a_planes) {
   p->w = w.w; p->bias = w.bias;
   p->C_in = w.C_in; p->N = w.N; p->KC = w.KC; p->nchunks = w.C_in / w.KC; p->ktaps = w.ktaps;
-  p->a_planes = a_planes; p->w_planes = w.planes; p->fmt = w.fmt; p->nblocks = w.C_out / w.N; p->phases = w.phases;
+  p->a_planes = a_planes; p->w_planes = w.planes; p->fmt = w.fmt; p->stack = w.stack; p->NM = w.stack ? 2 * w.N : w.N;
+  p->nblocks = w.C_out / w.N; p->phases = w.phases;
   p->nq = nq;
-  int nacc = 256 / w.N;                                      // one accumulator set = 256 TMEM columns (two sets)
+  int nacc = 256 / p->NM;                                    // one accumulator set = 256 TMEM columns (two sets)
   if (nacc > 4) nacc = 4;
   const int force = env_int("DTTS_TC_NACC", 0);
   if (force > 0 && force <= nacc) nacc = force;
@@ -598,7 +685,15 @@ void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq, int a_planes) {
   p->RA = p->MT + (max_off - p->min_off);
   p->a_stages = kMaxAStages;
   const size_t a_stage = (size_t)(p->KC / 8) * p->RA * 16 * p->a_planes;
-  const size_t w_blob = (size_t)p->N * p->KC * 2 * p->w_planes;
+  const size_t w_tap = (size_t)p->NM * p->KC * 2 * p->w_planes;
+  // taps per weight stage: ~32 KB stages, so that the per-stage barrier round trip is amortised over >= 8 MMAs
+  int tg = env_int("DTTS_TC_TG", 0);
+  if (tg <= 0) tg = (int)((32 * 1024) / w_tap);
+  if (tg < 1) tg = 1;
+  if (tg > p->ktaps) tg = p->ktaps;
+  tg = cdiv(p->ktaps, cdiv(p->ktaps, tg));                   // balance the groups (11 taps, 4 per stage -> 4 + 4 + 3)
+  p->TG = tg;
+  const size_t w_blob = w_tap * tg;
   const size_t budget = kSmemLimit - kSmemHeader - p->a_stages * a_stage;
   int ws = (int)(budget / w_blob);
   if (ws > kMaxWStages) ws = kMaxWStages;
@@ -611,7 +706,7 @@ void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq, int a_planes) {
 
 static size_t tc_smem_bytes(const TcConvParams& p) {
   const size_t a_stage = (size_t)(p.KC / 8) * p.RA * 16 * p.a_planes;
-  const size_t w_blob = (size_t)p.N * p.KC * 2 * p.w_planes;
+  const size_t w_blob = (size_t)p.NM * p.KC * 2 * p.w_planes * p.TG;
   size_t bytes = kSmemHeader + p.a_stages * a_stage + p.w_stages * w_blob;
   // the CTA owns all 512 TMEM columns: it must be alone on its SM, or a co-resident CTA would block in tcgen05.alloc
   if (bytes < 116 * 1024) bytes = 116 * 1024;
@@ -626,7 +721,7 @@ static int g_max_clusters[9] = {0};     // [csize] -> co-resident clusters of tc
 static int pick_cluster(const TcConvParams& p, long row_tiles) {
   int c = env_int("DTTS_TC_CLUSTER", 0);
   if (c <= 0) c = p.N >= 128 ? 4 : 2;
-  while (c > 1 && (row_tiles < c || (p.N * p.KC * 2 * p.w_planes) % (16 * c))) c >>= 1;
+  while (c > 1 && (row_tiles < c || (p.NM * p.KC * 2 * p.w_planes) % (16 * c))) c >>= 1;
   return c;
 }
 
@@ -634,8 +729,9 @@ cudaError_t launch_tc_conv(TcConvParams p, int B, cudaStream_t stream) {
   if (B <= 0 || p.nq <= 0) return cudaSuccess;
   if (p.a_planes < 1 || p.a_planes > 2 || p.w_planes < 1 || p.w_planes > 2 || (p.a_planes == 2 && !p.a_lo))
     return cudaErrorInvalidValue;
-  if (p.w_stages < 1 || p.N % 32 != 0 || p.N > 256 || p.KC % 16 != 0 || p.C_in % p.KC != 0 ||
-      p.N * p.nblocks > 512 || p.NACC * p.N > 256)
+  if (p.TG < 1 || p.w_stages < 1 || p.N % 32 != 0 || p.N > 256 || p.KC % 16 != 0 || p.C_in % p.KC != 0 ||
+      p.N * p.nblocks > 512 || p.NACC * p.NM > 256 || (p.stack && (p.w_planes != 1 || p.NM != 2 * p.N)) ||
+      (!p.stack && p.NM != p.N))
     return cudaErrorInvalidConfiguration;
   const int max_off = p.min_off + (p.RA - p.MT);
   if (p.a_pad + p.min_off < 0 || p.a_pad + p.ntiles * p.MT + max_off > p.a_rows) return cudaErrorInvalidValue;
@@ -675,7 +771,7 @@ cudaError_t launch_tc_conv(TcConvParams p, int B, cudaStream_t stream) {
   }
   p.csize = csize;
   p.nu = (int)((row_tiles + csize - 1) / csize);
-  const long total_units = (long)p.nu * p.nblocks * p.phases;
+  const long total_units = (long)p.nu * p.nblocks;             // each walks its `phases` polyphase components
   const int nclusters = (int)(total_units < max_clusters ? total_units : max_clusters);   // persistent
   attr[0].val.clusterDim = {(unsigned)csize, 1, 1};
   cfg.gridDim = dim3((unsigned)(nclusters * csize));
@@ -683,13 +779,14 @@ cudaError_t launch_tc_conv(TcConvParams p, int B, cudaStream_t stream) {
 }
 
 cudaError_t tc_pack_weights(const float* w_ref, tc16* out, int C_out, int C_in, int K, int transposed,
-                            int stride, int N, int KC, int planes, int fmt, cudaStream_t s) {
+                            int stride, int N, int KC, int planes, int fmt, int stack, cudaStream_t s) {
   const int phases = transposed ? stride : 1;
   const int ktaps = transposed ? K / stride : K;
   if (C_out % N || C_in % KC || (transposed && K % stride)) return cudaErrorInvalidValue;
-  const size_t total = (size_t)C_out * C_in * ktaps * phases * planes;
+  if (stack && (planes != 1 || 2 * N > 256)) return cudaErrorInvalidValue;
+  const size_t total = (size_t)C_out * C_in * ktaps * phases * planes * (stack ? 2 : 1);
   tc_pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w_ref, out, C_out, C_in, K, transposed, stride,
-                                                                        N, KC, planes, ktaps, phases, fmt);
+                                                                        N, KC, planes, ktaps, phases, fmt, stack);
   return cudaGetLastError();
 }
 

@@ -62,9 +62,16 @@ struct TcConvW {
   int N = 0;                     // output channels per MMA (<= 256); C_out = N * nblocks
   int KC = 0;                    // channels per K chunk (16 or 32)
   int ktaps = 0, phases = 1;
-  int planes = 2;                // weight planes (TcMode::w_planes)
+  int planes = 2;                // separately addressed weight planes (hi, lo): one MMA each
+  int stack = 0;                 // 1: hi | lo stacked along N inside ONE plane (N <= 64): one MMA of N' = 2N, planes = 1
   int fmt = 1;                   // TcMode::fmt
-  size_t elems() const { return (size_t)C_out * C_in * ktaps * phases * planes; }
+  size_t elems() const { return (size_t)C_out * C_in * ktaps * phases * planes * (stack ? 2 : 1); }
+  // operand mode -> plane arrangement of this layer
+  void set_mode(const TcMode& m) {
+    fmt = m.fmt;
+    stack = (m.w_planes == 2 && N <= 64) ? 1 : 0;
+    planes = stack ? 1 : m.w_planes;
+  }
 };
 
 struct TcConvParams {
@@ -76,6 +83,7 @@ struct TcConvParams {
   const float* bias;
   int C_in, N, KC, nchunks, ktaps, nblocks, phases;
   int a_planes, w_planes, fmt;   // operand planes of A (activations) and B (weights); 16-bit format
+  int stack, NM;                 // weights hi | lo stacked along N; N of the main MMAs (2N when stacked, else N)
   int tap_off0, tap_step;        // tap j reads input row q + tap_off0 + j*tap_step
   int min_off, RA;               // staged rows per slab: [q0 + min_off, q0 + min_off + RA)
   int nq, MT, NACC;
@@ -90,6 +98,7 @@ struct TcConvParams {
   float post, slope;
   int accumulate;
   int a_stages, w_stages;
+  int TG;                        // taps per weight stage
   int ntiles, B;                 // time tiles per (group, batch item); batch size (set by the launcher)
   int csize, nu;                 // cluster size; units (= csize consecutive row tiles) per weight group (launcher)
 };
@@ -103,7 +112,7 @@ void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq, int a_planes);
 
 // Weight packing: reference layout ([C_out][C_in][K], or [C_in][C_out][K] for ConvTranspose1d) -> blobs.
 cudaError_t tc_pack_weights(const float* w_ref, tc16* out, int C_out, int C_in, int K, int transposed,
-                            int stride, int N, int KC, int planes, int fmt, cudaStream_t s);
+                            int stride, int N, int KC, int planes, int fmt, int stack, cudaStream_t s);
 // fp32 strided tensor x[b*bs + c*cs + t*ts] -> operand planes of leaky(x, slope) (valid rows only)
 cudaError_t tc_to_planes(const float* x, long bs, long cs, long ts, int B, int C, int T, float slope,
                          tc16* hi, tc16* lo, int rows, int pad, int fmt, cudaStream_t s);

@@ -54,7 +54,6 @@ int pack_convT(dtts_vocoder* h, const std::string& name, int C_in, int C_out, in
 
 int tc_pack(dtts_vocoder* h, tc16** cursor, const std::string& name, int C_out, int C_in, int K,
             int transposed, int stride, TcMode mode, TcConvW* cw, cudaStream_t s) {
-  const int planes = mode.w_planes;
   const float* w = h->tab.get(name + ".weight", (uint64_t)C_out * C_in * K);
   if (!w) return DTTS_ERR_MISSING_WEIGHT;
   const float* b = h->tab.get(name + ".bias", C_out);
@@ -64,13 +63,13 @@ int tc_pack(dtts_vocoder* h, tc16** cursor, const std::string& name, int C_out, 
   cw->KC = (C_in % 32 == 0) ? 32 : 16;
   cw->ktaps = transposed ? K / stride : K;
   cw->phases = transposed ? stride : 1;
-  cw->planes = planes;
-  cw->fmt = mode.fmt;
+  cw->set_mode(mode);
   cw->bias = b;
   if (C_out % cw->N || cw->N % 32 || C_in % cw->KC)
     return fail(DTTS_ERR_BAD_SHAPE, "tensor-core vocoder: unsupported channel count in " + name);
   cw->w = *cursor;
-  DTTS_CUDA(tc_pack_weights(w, *cursor, C_out, C_in, K, transposed, stride, cw->N, cw->KC, planes, mode.fmt, s));
+  DTTS_CUDA(tc_pack_weights(w, *cursor, C_out, C_in, K, transposed, stride, cw->N, cw->KC, cw->planes, cw->fmt, cw->stack,
+                            s));
   *cursor += (cw->elems() + 63) / 64 * 64;
   return DTTS_OK;
 }
@@ -427,10 +426,9 @@ extern "C" int dtts_debug_tc_conv1d(const float* x, const float* w, const float*
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e = tc_conv_init();
   if (e != cudaSuccess) return fail(DTTS_ERR_CUDA, std::string("tc_conv_init: ") + cudaGetErrorString(e));
-  const int planes = mode.w_planes;
   TcConvW cw;
   cw.C_in = C_in; cw.C_out = C_out; cw.N = C_out > 256 ? 256 : C_out; cw.KC = (C_in % 32 == 0) ? 32 : 16;
-  cw.ktaps = transposed ? K / stride : K; cw.phases = transposed ? stride : 1; cw.planes = planes; cw.fmt = mode.fmt; cw.bias = bias;
+  cw.ktaps = transposed ? K / stride : K; cw.phases = transposed ? stride : 1; cw.set_mode(mode); cw.bias = bias;
   if (C_out % cw.N || cw.N % 32 || C_in % cw.KC) return fail(DTTS_ERR_BAD_SHAPE, "tensor-core conv: unsupported channels");
   const int T_out = transposed ? (T_in - 1) * stride - 2 * padding + K : T_in + 2 * padding - dilation * (K - 1);
   if (T_out <= 0) return fail(DTTS_ERR_BAD_SHAPE, "tensor-core conv: empty output");
@@ -445,7 +443,7 @@ extern "C" int dtts_debug_tc_conv1d(const float* x, const float* w, const float*
   float* r32 = res ? bump.take<float>((size_t)B * C_out * T_out) : nullptr;
   if (!bump.ok) return fail(DTTS_ERR_WORKSPACE_TOO_SMALL, "dtts_debug_tc_conv1d: scratch too small");
   cw.w = wp;
-  DTTS_CUDA(tc_pack_weights(w, wp, C_out, C_in, K, transposed, stride, cw.N, cw.KC, planes, mode.fmt, s));
+  DTTS_CUDA(tc_pack_weights(w, wp, C_out, C_in, K, transposed, stride, cw.N, cw.KC, cw.planes, cw.fmt, cw.stack, s));
   DTTS_CUDA(tc_zero_halo(a_hi, a_lo, B * (C_in / 8), rows_in, TC_PADF, T_in, s));
   DTTS_CUDA(tc_to_planes(x, (long)C_in * T_in, T_in, 1, B, C_in, T_in, pre_slope, a_hi, a_lo, rows_in, TC_PADF, mode.fmt, s));
   if (res) DTTS_CUDA(tc_nct_to_stream(res, r32, B, C_out, T_out, s));

@@ -34,15 +34,18 @@ def split(x, dt, planes):
     return hi + rnd(x - hi, dt)
 
 
-def emulate(W, vcfg, mel, a_dt, a_planes, w_dt, w_planes, cross=True):
-    """hifigan_forward with quantised conv operands.  cross=False drops nothing (kept for clarity): with split
-    operands the CUDA kernel issues hi*hi + hi*lo + lo*hi, i.e. everything but lo*lo (~2^-2p relative)."""
+def emulate(W, vcfg, mel, a_dt, a_planes, w_dt, w_planes):
+    """hifigan_forward with quantised conv operands (with split operands the CUDA kernel issues hi*hi + hi*lo + lo*hi,
+    i.e. everything but lo*lo, ~2^-2p relative).  w_planes may be a function of the layer's C_out."""
     qa = lambda t: split(t, a_dt, a_planes)      # noqa: E731
-    qw = lambda t: split(t, w_dt, w_planes)      # noqa: E731
+
+    def qw(t, c_out=None):
+        planes = w_planes(c_out if c_out is not None else t.shape[0]) if callable(w_planes) else w_planes
+        return split(t, w_dt, planes)
     x = F.conv1d(qa(mel.transpose(1, 2)), qw(W["conv_pre.weight"]), W["conv_pre.bias"], padding=3)
     nk = len(vcfg.rb_kernels)
     for i, (u, k) in enumerate(zip(vcfg.up_rates, vcfg.up_kernels)):
-        x = F.conv_transpose1d(qa(F.leaky_relu(x, 0.1)), qw(W[f"ups.{i}.weight"]), W[f"ups.{i}.bias"], stride=u,
+        x = F.conv_transpose1d(qa(F.leaky_relu(x, 0.1)), qw(W[f"ups.{i}.weight"], W[f"ups.{i}.weight"].shape[1]), W[f"ups.{i}.bias"], stride=u,
                                padding=(k - u) // 2)
         xs = None
         for j, (kr, dils) in enumerate(zip(vcfg.rb_kernels, vcfg.rb_dilations)):
@@ -66,6 +69,9 @@ MODES = [
     ("fp16 x fp16            (1 MMA)", torch.float16, 1, torch.float16, 1),
     ("fp16 x fp16 hi+lo      (2 MMA)", torch.float16, 1, torch.float16, 2),
     ("fp16 hi+lo x fp16      (2 MMA)", torch.float16, 2, torch.float16, 1),
+    ("fp16 x fp16 hi+lo only C_out<=64", torch.float16, 1, torch.float16, lambda c: 2 if c <= 64 else 1),
+    ("fp16 x fp16 hi+lo only C_out<=128", torch.float16, 1, torch.float16, lambda c: 2 if c <= 128 else 1),
+    ("fp16 x fp16 hi+lo only C_out>=128", torch.float16, 1, torch.float16, lambda c: 2 if c >= 128 else 1),
     ("bf16 hi+lo x bf16 hi+lo (3 MMA)", torch.bfloat16, 2, torch.bfloat16, 2),
     ("fp16 hi+lo x fp16 hi+lo (3 MMA)", torch.float16, 2, torch.float16, 2),
 ]
