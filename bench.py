@@ -118,9 +118,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--vocoder-precision", type=int, default=int(os.environ.get("DTTS_VOCODER_PRECISION", "1")),
-                    help="0: fp32 FMA pipe; 1 (default): tcgen05 split-bf16 hi/lo, 3 MMAs, inside the fp32 parity "
-                         "tolerance; 2: tcgen05 single bf16 (BASELINE.json cfg 3; outside the tolerance)")
+    ap.add_argument("--vocoder-precision", type=int, default=int(os.environ.get("DTTS_VOCODER_PRECISION", "3")),
+                    help="0: fp32 FMA pipe; 1: tcgen05 bf16 hi/lo x hi/lo (3 MMAs, ~1e-6 wav RMS); 2: tcgen05 bf16 (cfg 3, "
+                         "outside the tolerance); 3 (default): tcgen05 fp16 x fp16 hi/lo weights (2 MMAs, ~6e-5 wav RMS, "
+                         "inside the 1e-4 tolerance); 4: tcgen05 fp16 (1 MMA, ~8.5e-5)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -716,11 +716,12 @@ static size_t tc_smem_bytes(const TcConvParams& p) {
 static int g_num_sms = 0;
 static int g_max_clusters[9] = {0};     // [csize] -> co-resident clusters of tc_conv_kernel (0 = not queried yet)
 
-// Cluster size per layer: weights are re-streamed once per row tile, so the layers whose blob traffic per MMA cycle is
-// highest (N = 256 / 128) share them 4 ways; the small layers pair up (a 2-cluster wastes no SM on this part).
+// Cluster size (CTAs sharing every weight stage through multicast).  Measured on B200 at the cfg-2 vocoder shapes
+// (profiles/r01_summary.md): 1 -> 35.2 ms, 2 -> 36.0 ms, 4 -> 36.0 ms per pass; the weight stream (<= 3.8 TB/s out of
+// L2) is not what bounds these layers, so the default is 1 and DTTS_TC_CLUSTER=2|4 turns the multicast path on.
 static int pick_cluster(const TcConvParams& p, long row_tiles) {
   int c = env_int("DTTS_TC_CLUSTER", 0);
-  if (c <= 0) c = p.N >= 128 ? 4 : 2;
+  if (c <= 0) c = 1;
   while (c > 1 && (row_tiles < c || (p.NM * p.KC * 2 * p.w_planes) % (16 * c))) c >>= 1;
   return c;
 }

@@ -100,6 +100,19 @@ def test_tc_conv_fp16_modes(shape, precision, tol):
     assert (act - want_act).abs().max().item() < 6e-4 * scale
 
 
+@pytest.mark.parametrize("cluster", [2, 4])
+@pytest.mark.parametrize("shape", [TC_CONV_SHAPES[1], TC_CONV_SHAPES[3], TC_CONV_SHAPES[4], TC_CONV_SHAPES[8]])
+def test_tc_conv_cluster_multicast_is_bit_identical(shape, cluster, monkeypatch):
+    """Thread-block clusters that share every weight stage through cp.async.bulk multicast (DTTS_TC_CLUSTER) must not
+    change a single bit: same MMAs, same order, only the weight delivery differs.  Covers row-tile counts that are not
+    a multiple of the cluster size (dummy tiles)."""
+    monkeypatch.setenv("DTTS_TC_CLUSTER", "1")
+    base, base_act, _ = _run_tc_conv(shape, precision=3, with_res=False)
+    monkeypatch.setenv("DTTS_TC_CLUSTER", str(cluster))
+    out, act, _ = _run_tc_conv(shape, precision=3, with_res=False)
+    assert torch.equal(out, base) and torch.equal(act, base_act)
+
+
 def test_tc_conv_weight_split_is_tighter_than_single_fp16():
     shape = TC_CONV_SHAPES[3]
     o3, _, ref = _run_tc_conv(shape, precision=3, with_res=False)
