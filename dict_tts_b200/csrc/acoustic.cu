@@ -1,13 +1,18 @@
 // Acoustic model behind the C ABI: S2PA text encoder, duration predictor, length regulator, FVAE decoder with its
 // residual-coupling prior flow.  Mirrors PortaSpeech_dict.forward(infer=True) (modules/dict_tts/model.py:36-122).
 #include "engine.cuh"
+#include "tc_conv.cuh"
 
 using namespace dtts;
 
 namespace {
 
+// Every dense convolution exists twice: packed for the fp32 FMA kernel (precision 0, the exact path) and as tcgen05
+// blobs (precision 1: bf16 hi/lo on both operands, 3 MMAs per product, fp32-class accuracy -- durations must round the
+// same way as the reference's fp32 forward).
 struct EncLayerW {
   ConvW qkv, o, ffn1, ffn2;
+  TcConvW t_qkv, t_o, t_ffn1, t_ffn2;
   const float *g1, *b1, *g2, *b2;
 };
 struct EncoderW {
@@ -17,6 +22,8 @@ struct EncoderW {
 struct WNW {
   ConvW cond;
   std::vector<ConvW> in_layers, res_skip;
+  TcConvW t_cond;
+  std::vector<TcConvW> t_in, t_rs;      // t_rs blocks of `hidden` channels: [0] -> x update, [1] -> skip
 };
 struct FlowW {
   ConvW pre, post;
@@ -34,7 +41,13 @@ struct dtts_acoustic {
   const float* pinyin_emb;
   EncoderW sem, lin;
   ConvW s2pa_q, s2pa_kT, s2pa_v, s2pa_o;
+  TcConvW t_s2pa_q, t_s2pa_kT, t_s2pa_v, t_s2pa_o;
   std::vector<ConvW> dur_conv;
+  std::vector<TcConvW> t_dur;
+  int precision = 0;              // 0: fp32 FMA pipe; 1: tcgen05 (bf16 hi/lo x hi/lo)
+  TcMode mode;
+  tc16* tc_pool = nullptr;
+  size_t tc_cap = 0, tc_used = 0;
   std::vector<const float*> dur_ln_g, dur_ln_b;
   const float *dur_w, *dur_b;
   ConvW g_pre, dec_pre, dec_out;
@@ -68,6 +81,97 @@ int pack(dtts_acoustic* h, const std::string& name, int C_out, int C_in, int K, 
   return DTTS_OK;
 }
 
+int pick_n(int C_out) {
+  for (int n = 256; n >= 32; n -= 32)
+    if (C_out % n == 0) return n;
+  return 0;
+}
+
+// Packs `parts` convolutions that share (C_in, K) side by side along C_out into one tensor-core weight set (each part
+// becomes whole N-blocks).  w[i] in reference layout [C_out_i][C_in][K] ([C_in][C_out_i][K] when transposed).
+int tc_pack(dtts_acoustic* h, const float* const* w, int parts, const float* bias, int C_out_part, int C_in, int K,
+            int transposed, int N, TcConvW* cw, cudaStream_t s) {
+  if (!h->precision) return DTTS_OK;
+  cw->C_in = C_in; cw->C_out = C_out_part * parts;
+  cw->N = N ? N : pick_n(C_out_part);
+  cw->KC = (C_in % 32 == 0) ? 32 : 16;
+  cw->ktaps = K; cw->phases = 1;
+  cw->set_mode(h->mode);
+  cw->bias = bias;
+  if (!cw->N || C_out_part % cw->N || C_in % cw->KC)
+    return fail(DTTS_ERR_BAD_SHAPE, "tensor-core acoustic path: unsupported channel count");
+  const size_t part_elems = cw->elems() / parts;
+  h->tc_used = (h->tc_used + 63) & ~(size_t)63;
+  if (h->tc_used + cw->elems() > h->tc_cap) return fail(DTTS_ERR_CUDA, "tensor-core weight pool exhausted");
+  tc16* dst = h->tc_pool + h->tc_used;
+  cw->w = dst;
+  for (int i = 0; i < parts; ++i)
+    DTTS_CUDA(tc_pack_weights(w[i], dst + (size_t)i * part_elems, C_out_part, C_in, K, transposed, 1, cw->N, cw->KC,
+                              cw->planes, cw->fmt, cw->stack, s));
+  h->tc_used += cw->elems();
+  return DTTS_OK;
+}
+int tc_pack1(dtts_acoustic* h, const std::string& name, bool has_bias, int C_out, int C_in, int K, int N, TcConvW* cw,
+             cudaStream_t s, int transposed = 0) {
+  if (!h->precision) return DTTS_OK;
+  const float* w = h->tab.get(name + ".weight", (uint64_t)C_out * C_in * K);
+  if (!w) return DTTS_ERR_MISSING_WEIGHT;
+  const float* b = nullptr;
+  if (has_bias && !(b = h->tab.get(name + ".bias", C_out))) return DTTS_ERR_MISSING_WEIGHT;
+  return tc_pack(h, &w, 1, b, C_out, C_in, K, transposed, N, cw, s);
+}
+
+// Per-call context of the tensor-core convolutions: one scratch pair of operand planes (the input of the next
+// convolution is converted into it, halo rows zeroed in the same launch) and the launch glue.
+struct TcRun {
+  dtts_acoustic* h;
+  Launcher* L;
+  int B;
+  tc16 *hi, *lo;
+  size_t cap;                     // elements per plane
+  int C = 0, T = 0, rows = 0;     // what is staged
+  struct Epi {
+    const float* res = nullptr; long r_bs = 0, r_cs = 0, r_ts = 1;
+    const float* mask = nullptr; int m_bs = 0;
+    int act = 0; float alpha = 1.f, post = 1.f; int accumulate = 0;
+  };
+  // x element (c,t) of batch b at x[b*bs + c*cs + t*ts]
+  void stage(const float* x, long bs, long cs, long ts, int C_, int T_) {
+    C = C_; T = T_; rows = tc_rows(T_);
+    if ((size_t)B * C * rows > cap) { (*L)(cudaErrorInvalidValue); return; }
+    (*L)(tc_to_planes_full(x, bs, cs, ts, B, C, T, 1.f, hi, h->mode.a_planes == 2 ? lo : nullptr, rows, TC_PADF,
+                           h->mode.fmt, L->stream));
+  }
+  void stage_nct(const float* x, int C_, int T_) { stage(x, (long)C_ * T_, T_, 1, C_, T_); }
+  // blocks [blk0, blk0+nblk) of w -> out element (c,t) at out[b*o_bs + c*o_cs + t*o_ts], c counted from the first block
+  void conv(const TcConvW& w, int blk0, int nblk, float* out, long o_bs, long o_cs, long o_ts, int T_out, int dil,
+            int pad, const Epi& e) {
+    if (w.C_in != C) { (*L)(cudaErrorInvalidValue); return; }
+    TcConvW sub = w;
+    const int nblocks = w.C_out / w.N;
+    if (nblk <= 0) nblk = nblocks - blk0;
+    sub.C_out = nblk * w.N;
+    sub.w = w.w + (size_t)blk0 * (w.elems() / nblocks);
+    sub.bias = w.bias ? w.bias + (size_t)blk0 * w.N : nullptr;
+    TcConvParams p{};
+    p.a_hi = hi; p.a_lo = h->mode.a_planes == 2 ? lo : nullptr;
+    p.a_bs = (long)C * rows; p.a_rows = rows; p.a_pad = TC_PADF;
+    p.tap_off0 = -pad; p.tap_step = dil;
+    tc_conv_plan(&p, sub, T_out, h->mode.a_planes);
+    p.ot_mul = 1; p.ot_add = 0; p.T_out = T_out;
+    p.o32 = out; p.o32_bs = o_bs; p.o_nct = 1; p.o_cs = o_cs; p.o_ts = o_ts;
+    p.res = e.res; p.r_bs = e.r_bs; p.r_cs = e.r_cs; p.r_ts = e.r_ts;
+    p.mask = e.mask; p.m_bs = e.m_bs; p.act = e.act; p.alpha = e.alpha; p.post = e.post; p.accumulate = e.accumulate;
+    p.slope = 1.f;
+    (*L)(launch_tc_conv(p, B, L->stream));
+  }
+  void conv_nct(const TcConvW& w, float* out, int T_out, int dil, int pad, const Epi& e, int blk0 = 0, int nblk = 0) {
+    const int nblocks = w.C_out / w.N;
+    const int co = (nblk > 0 ? nblk : nblocks - blk0) * w.N;
+    conv(w, blk0, nblk, out, (long)co * T_out, T_out, 1, T_out, dil, pad, e);
+  }
+};
+
 int pack_encoder(dtts_acoustic* h, const std::string& p, EncoderW* e, cudaStream_t s) {
   const int H = h->d.hidden, F = h->d.ffn_filter, K = h->d.ffn_kernel;
   for (int i = 0; i < h->d.enc_layers; ++i) {
@@ -93,6 +197,14 @@ int pack_encoder(dtts_acoustic* h, const std::string& p, EncoderW* e, cudaStream
     const std::string f = p + ".ffn_layers." + std::to_string(i);
     DTTS_TRY(pack(h, f + ".conv_1", F, H, K, true, &L.ffn1, s));
     DTTS_TRY(pack(h, f + ".conv_2", H, F, 1, true, &L.ffn2, s));
+    if (h->precision) {
+      const float* ws[3];
+      for (int j = 0; j < 3; ++j) ws[j] = h->tab.get(a + names[j] + ".weight", (uint64_t)H * H);
+      DTTS_TRY(tc_pack(h, ws, 3, bqkv, H, H, 1, 0, 0, &L.t_qkv, s));
+      DTTS_TRY(tc_pack1(h, a + ".conv_o", true, H, H, 1, 0, &L.t_o, s));
+      DTTS_TRY(tc_pack1(h, f + ".conv_1", true, F, H, K, 0, &L.t_ffn1, s));
+      DTTS_TRY(tc_pack1(h, f + ".conv_2", true, H, F, 1, 0, &L.t_ffn2, s));
+    }
     L.g1 = h->tab.get(p + ".norm_layers_1." + std::to_string(i) + ".gamma", H);
     L.b1 = h->tab.get(p + ".norm_layers_1." + std::to_string(i) + ".beta", H);
     L.g2 = h->tab.get(p + ".norm_layers_2." + std::to_string(i) + ".gamma", H);
@@ -116,15 +228,48 @@ int pack_wn(dtts_acoustic* h, const std::string& p, int hidden, int n_layers, in
     DTTS_TRY(pack(h, p + ".res_skip_layers." + std::to_string(i), rs, hidden, 1, true, &r, s));
     wn->in_layers.push_back(a);
     wn->res_skip.push_back(r);
+    if (h->precision) {
+      TcConvW ta, tr;
+      DTTS_TRY(tc_pack1(h, p + ".in_layers." + std::to_string(i), true, 2 * hidden, hidden, K, 0, &ta, s));
+      DTTS_TRY(tc_pack1(h, p + ".res_skip_layers." + std::to_string(i), true, rs, hidden, 1, hidden, &tr, s));
+      wn->t_in.push_back(ta);
+      wn->t_rs.push_back(tr);
+    }
   }
+  DTTS_TRY(tc_pack1(h, p + ".cond_layer", true, 2 * hidden * n_layers, gin, 1, 0, &wn->t_cond, s));
   return DTTS_OK;
 }
 
 // Pre-LN transformer encoder (rel_transformer_encoder.py:55-79).  x is updated in place; the result is written to hbuf.
 void run_encoder(dtts_acoustic* h, const EncoderW& E, float* x, float* hbuf, float* qkv, float* att, float* ffn,
-                 const float* seq_mask, int B, int Tw, Launcher& L) {
+                 const float* seq_mask, int B, int Tw, Launcher& L, TcRun* tc) {
   const int H = h->d.hidden, F = h->d.ffn_filter, K = h->d.ffn_kernel;
   cudaStream_t s = L.stream;
+  if (tc) {
+    for (size_t i = 0; i < E.layers.size(); ++i) {
+      const EncLayerW& W = E.layers[i];
+      L(apply_mask(x, seq_mask, B, H, Tw, s));
+      L(channel_layernorm(x, hbuf, W.g1, W.b1, 1e-4f, nullptr, nullptr, B, H, Tw, s));
+      tc->stage_nct(hbuf, H, Tw);
+      tc->conv_nct(W.t_qkv, qkv, Tw, 1, 0, TcRun::Epi());
+      L(self_attention(qkv, qkv + (size_t)H * Tw, qkv + (size_t)2 * H * Tw, seq_mask, att, B, H, Tw, h->d.n_heads, s));
+      TcRun::Epi res_x;
+      res_x.res = x; res_x.r_bs = (long)H * Tw; res_x.r_cs = Tw; res_x.r_ts = 1;
+      tc->stage_nct(att, H, Tw);
+      tc->conv_nct(W.t_o, x, Tw, 1, 0, res_x);
+      L(channel_layernorm(x, hbuf, W.g2, W.b2, 1e-4f, nullptr, seq_mask, B, H, Tw, s));   // FFN input is x * x_mask
+      TcRun::Epi e1;
+      e1.act = 1; e1.mask = seq_mask; e1.m_bs = Tw;
+      tc->stage_nct(hbuf, H, Tw);
+      tc->conv_nct(W.t_ffn1, ffn, Tw, 1, K / 2, e1);
+      TcRun::Epi e2 = res_x;
+      e2.mask = seq_mask; e2.m_bs = Tw;
+      tc->stage_nct(ffn, F, Tw);
+      tc->conv_nct(W.t_ffn2, x, Tw, 1, 0, e2);
+    }
+    L(channel_layernorm(x, hbuf, E.last_g, E.last_b, 1e-4f, nullptr, seq_mask, B, H, Tw, s));
+    return;
+  }
   for (size_t i = 0; i < E.layers.size(); ++i) {
     const EncLayerW& W = E.layers[i];
     L(apply_mask(x, seq_mask, B, H, Tw, s));
@@ -155,9 +300,31 @@ void run_encoder(dtts_acoustic* h, const EncoderW& E, float* x, float* hbuf, flo
 // WN.forward with x_mask = 1 (modules/commons/wavenet.py:54-78).  hx [B,hidden,T] is updated in place,
 // skip [B,hidden,T] receives the output.
 void run_wn(const WNW& W, int hidden, int K, float* hx, const float* g, int gin, float* cond, float* a, float* acts,
-            float* skip, int B, int T, Launcher& L) {
+            float* skip, int B, int T, Launcher& L, TcRun* tc) {
   cudaStream_t s = L.stream;
   const int n = (int)W.in_layers.size();
+  if (tc) {
+    tc->stage_nct(g, gin, T);
+    tc->conv_nct(W.t_cond, cond, T, 1, 0, TcRun::Epi());
+    for (int i = 0; i < n; ++i) {
+      TcRun::Epi ea;
+      ea.res = cond + (size_t)2 * hidden * i * T; ea.r_bs = (long)W.cond.C_out * T; ea.r_cs = T; ea.r_ts = 1;
+      tc->stage_nct(hx, hidden, T);
+      tc->conv_nct(W.t_in[i], a, T, 1, K / 2, ea);
+      L(wn_gate(a, acts, B, hidden, T, s));
+      tc->stage_nct(acts, hidden, T);
+      TcRun::Epi ex, es;
+      ex.res = hx; ex.r_bs = (long)hidden * T; ex.r_cs = T; ex.r_ts = 1;
+      es.accumulate = (i > 0);
+      if (i < n - 1) {
+        tc->conv_nct(W.t_rs[i], hx, T, 1, 0, ex, 0, 1);                 // x = x + rs[:hidden]
+        tc->conv_nct(W.t_rs[i], skip, T, 1, 0, es, 1, 1);               // out += rs[hidden:]
+      } else {
+        tc->conv_nct(W.t_rs[i], skip, T, 1, 0, es, 0, 1);
+      }
+    }
+    return;
+  }
   (void)gin;
   L(launch_conv1d_f32(conv_params(g, T, W.cond, 0, W.cond.C_out, cond, T, 1, 1, 0), B, s));
   for (int i = 0; i < n; ++i) {
@@ -192,9 +359,13 @@ extern "C" int dtts_acoustic_create(const dtts_acoustic_desc* d, const float* ar
   if (d->hidden <= 0 || d->hidden > 256 || d->hidden % d->n_heads || d->dict_dim % 4 || d->latent % 2 ||
       d->frames_multiple != 4)
     return fail(DTTS_ERR_BAD_SHAPE, "unsupported acoustic configuration");
+  if (d->precision != 0 && d->precision != 1)
+    return fail(DTTS_ERR_BAD_ARG, "acoustic precision must be 0 (fp32 FMA) or 1 (tcgen05, bf16 hi/lo split)");
   DTTS_TRY(arch_check());
   dtts_acoustic* h = new dtts_acoustic();
   h->d = *d;
+  h->precision = d->precision;
+  h->mode = tc_mode(1);
   cudaStream_t s = (cudaStream_t)stream;
   int rc = h->tab.init(arena_dev, arena_floats, table, n_entries);
   if (rc != DTTS_OK) { delete h; return rc; }
@@ -202,6 +373,16 @@ extern "C" int dtts_acoustic_create(const dtts_acoustic_desc* d, const float* ar
   for (auto& e : h->tab.entries) total += e.second.second + 64;
   rc = h->pool.reserve(total + 2 * 1024 * 1024);
   if (rc != DTTS_OK) { delete h; return rc; }
+  if (h->precision) {
+    h->tc_cap = 2 * total + (1 << 20);               // two 16-bit planes per weight
+    cudaError_t e = cudaMalloc((void**)&h->tc_pool, h->tc_cap * sizeof(tc16));
+    if (e == cudaSuccess) e = tc_conv_init();
+    if (e != cudaSuccess) {
+      h->pool.release();
+      delete h;
+      return fail(DTTS_ERR_CUDA, std::string("acoustic tensor-core pool: ") + cudaGetErrorString(e));
+    }
+  }
   auto build = [&]() -> int {
     const int H = d->hidden, D = d->dict_dim;
     const std::string p = "dict_encoder.S2PA_module";
@@ -219,12 +400,22 @@ extern "C" int dtts_acoustic_create(const dtts_acoustic_desc* d, const float* ar
       const float* wk = h->tab.get(a + ".k_transform.weight", (uint64_t)H * D);
       if (!wk) return DTTS_ERR_MISSING_WEIGHT;
       h->s2pa_kT.w = wk; h->s2pa_kT.bias = nullptr; h->s2pa_kT.C_out = D; h->s2pa_kT.C_in = H; h->s2pa_kT.ktaps = 1;
+      // tensor-core copy: [H][D] is the ConvTranspose layout [C_in][C_out][1]
+      DTTS_TRY(tc_pack(h, &wk, 1, nullptr, D, H, 1, 1, 0, &h->t_s2pa_kT, s));
     }
+    DTTS_TRY(tc_pack1(h, a + ".q_transform", false, H, H, 1, 0, &h->t_s2pa_q, s));
+    DTTS_TRY(tc_pack1(h, a + ".v_transform", false, H, D, 1, 0, &h->t_s2pa_v, s));
+    DTTS_TRY(tc_pack1(h, a + ".output_transform", false, H, H, 1, 0, &h->t_s2pa_o, s));
     for (int i = 0; i < d->dur_layers; ++i) {
       ConvW c;
       const std::string q = "dur_predictor.conv." + std::to_string(i);
       DTTS_TRY(pack(h, q + ".1", d->dur_chans, i == 0 ? H : d->dur_chans, d->dur_kernel, true, &c, s));
       h->dur_conv.push_back(c);
+      if (h->precision) {
+        TcConvW tcw;
+        DTTS_TRY(tc_pack1(h, q + ".1", true, d->dur_chans, i == 0 ? H : d->dur_chans, d->dur_kernel, 0, &tcw, s));
+        h->t_dur.push_back(tcw);
+      }
       const float* g = h->tab.get(q + ".3.weight", d->dur_chans);
       const float* b = h->tab.get(q + ".3.bias", d->dur_chans);
       if (!g || !b) return DTTS_ERR_MISSING_WEIGHT;
@@ -268,6 +459,7 @@ extern "C" int dtts_acoustic_create(const dtts_acoustic_desc* d, const float* ar
   }
   if (rc != DTTS_OK) {
     h->pool.release();
+    if (h->tc_pool) cudaFree(h->tc_pool);
     delete h;
     return rc;
   }
@@ -278,6 +470,7 @@ extern "C" int dtts_acoustic_create(const dtts_acoustic_desc* d, const float* ar
 extern "C" int dtts_acoustic_destroy(dtts_acoustic* h) {
   if (!h) return DTTS_OK;
   h->pool.release();
+  if (h->tc_pool) cudaFree(h->tc_pool);
   delete h;
   return DTTS_OK;
 }
@@ -295,6 +488,7 @@ extern "C" uint64_t dtts_text_workspace_bytes(const dtts_acoustic* h, int32_t B,
   add(bt); add(bt); add(bt); add(B); add(64);                                  // masks, lens, maxes
   add(bt * H); add(bt * D); add(bt * Lk); add(bt * D); add(bt * H); add(bt * H);  // q, qk, weights, ctx, ctxv, context
   add(bt * H); add(bt * C); add(bt * C);                                        // dur_in, d1, d2
+  if (h->precision) n += 2 * ws_round((size_t)B * (F > D ? F : D) * tc_rows(Tw) * sizeof(tc16));   // operand planes
   return n + 4096;
 }
 
@@ -334,32 +528,55 @@ extern "C" int dtts_text_encode(dtts_acoustic* h, const dtts_text_in* in, const 
   float* dur_in = bump.take<float>(bt * H);
   float* d1 = bump.take<float>(bt * C);
   float* d2 = bump.take<float>(bt * C);
+  TcRun tcr{};
+  TcRun* tc = nullptr;
+  if (h->precision) {
+    tcr.cap = (size_t)B * (F > D ? F : D) * tc_rows(Tw);
+    tcr.hi = bump.take<tc16>(tcr.cap);
+    tcr.lo = bump.take<tc16>(tcr.cap);
+    tc = &tcr;
+  }
   if (!bump.ok) return fail(DTTS_ERR_WORKSPACE_TOO_SMALL, "dtts_text_encode: workspace too small");
   Launcher L;
   L.stream = (cudaStream_t)stream;
   L.counter = &h->launches;
   cudaStream_t s = L.stream;
+  tcr.h = h; tcr.L = &L; tcr.B = B;
 
   // word embedding * sqrt(H), masks (dict_encoder.py:131-136)
   L(embed_tokens(in->word_tokens_dev, h->word_emb, sqrtf((float)H), B, Tw, H, d.word_size, x, seq_mask, tok_mask, lens,
                  s));
-  run_encoder(h, h->sem, x, hb, qkv, att, ffn, seq_mask, B, Tw, L);           // semantic encoder -> hb
+  run_encoder(h, h->sem, x, hb, qkv, att, ffn, seq_mask, B, Tw, L, tc);       // semantic encoder -> hb
   // S2PA (dict_encoder.py:32-66), folded: logits = keys . (W_k^T (W_q x) * D^-1/2)
-  L(launch_conv1d_f32(conv_params(hb, Tw, h->s2pa_q, 0, H, q, Tw, 1, 1, 0), B, s));
-  {
+  if (tc) {
+    tc->stage_nct(hb, H, Tw);
+    tc->conv_nct(h->t_s2pa_q, q, Tw, 1, 0, TcRun::Epi());
+    TcRun::Epi ek;
+    ek.alpha = 1.f / sqrtf((float)D);
+    tc->stage_nct(q, H, Tw);
+    tc->conv_nct(h->t_s2pa_kT, qk, Tw, 1, 0, ek);
+  } else {
+    L(launch_conv1d_f32(conv_params(hb, Tw, h->s2pa_q, 0, H, q, Tw, 1, 1, 0), B, s));
     ConvParams p = conv_params(q, Tw, h->s2pa_kT, 0, D, qk, Tw, 1, 1, 0);
     p.alpha = 1.f / sqrtf((float)D);
     L(launch_conv1d_f32(p, B, s));
   }
   L(s2pa_stream(in->keys_dev, in->values_dev, in->key_map_dev, qk, B, Tw, Lk, D, weights, out->dict_attn_dev, ctx, s));
-  L(launch_conv1d_f32(conv_params(ctx, Tw, h->s2pa_v, 0, H, ctxv, Tw, 1, 1, 0), B, s));
-  L(launch_conv1d_f32(conv_params(ctxv, Tw, h->s2pa_o, 0, H, context, Tw, 1, 1, 0), B, s));
+  if (tc) {
+    tc->stage_nct(ctx, D, Tw);
+    tc->conv_nct(h->t_s2pa_v, ctxv, Tw, 1, 0, TcRun::Epi());
+    tc->stage_nct(ctxv, H, Tw);
+    tc->conv_nct(h->t_s2pa_o, context, Tw, 1, 0, TcRun::Epi());
+  } else {
+    L(launch_conv1d_f32(conv_params(ctx, Tw, h->s2pa_v, 0, H, ctxv, Tw, 1, 1, 0), B, s));
+    L(launch_conv1d_f32(conv_params(ctxv, Tw, h->s2pa_o, 0, H, context, Tw, 1, 1, 0), B, s));
+  }
   L(dict_maxes(in->key_map_dev, bt * Lk, in->pinyin_map_dev, bt * Lp, maxes, s));
   // x2 = context * x_mask + pron   (written into x, the input of the linguistic encoder)
   L(s2pa_pron(weights, in->key_map_dev, in->pinyin_dev, in->pinyin_map_dev, in->pron_modified_dev, maxes,
               h->pinyin_emb, d.pinyin_size, context, seq_mask, B, Tw, Lk, Lp, H, d.language_zh, out->pron_attn_dev, x,
               s));
-  run_encoder(h, h->lin, x, hb, qkv, att, ffn, seq_mask, B, Tw, L);           // linguistic encoder -> hb
+  run_encoder(h, h->lin, x, hb, qkv, att, ffn, seq_mask, B, Tw, L, tc);       // linguistic encoder -> hb
   // word_encoder_out = x^T * (tokens > 0); dur_input; src_padding  (dict_encoder.py:168-170, model.py:94-96,73)
   L(finish_text(hb, tok_mask, B, Tw, H, out->word_encoder_out_dev, dur_in, keep, s));
   L(count_keep(keep, B, Tw, out->ilens_dev, s));
@@ -369,9 +586,16 @@ extern "C" int dtts_text_encode(dtts_acoustic* h, const dtts_text_in* in, const 
   for (int i = 0; i < d.dur_layers; ++i) {
     float* c = bufs[0];
     float* y = bufs[1];
-    ConvParams p = conv_params(cur, Tw, h->dur_conv[i], 0, C, c, Tw, 1, 1, (d.dur_kernel - 1) / 2);
-    p.act = ACT_RELU;
-    L(launch_conv1d_f32(p, B, s));
+    if (tc) {
+      TcRun::Epi er;
+      er.act = 1;
+      tc->stage_nct(cur, i == 0 ? H : C, Tw);
+      tc->conv_nct(h->t_dur[i], c, Tw, 1, (d.dur_kernel - 1) / 2, er);
+    } else {
+      ConvParams p = conv_params(cur, Tw, h->dur_conv[i], 0, C, c, Tw, 1, 1, (d.dur_kernel - 1) / 2);
+      p.act = ACT_RELU;
+      L(launch_conv1d_f32(p, B, s));
+    }
     L(channel_layernorm(c, y, h->dur_ln_g[i], h->dur_ln_b[i], 1e-5f, nullptr, keep, B, C, Tw, s));
     cur = y;
     bufs[0] = c;      // conv output buffer can be reused: next conv reads y, writes c
@@ -430,6 +654,7 @@ extern "C" uint64_t dtts_decode_workspace_bytes(const dtts_acoustic* h, int32_t 
   add(B * H * T);                                      // x
   add(B * 2 * H * h->d.dec_layers * T);                // cond
   add(B * 2 * H * T); add(B * H * T); add(B * H * T);  // a, acts, skip
+  if (h->precision) n += 2 * ws_round((size_t)B * H * tc_rows(T) * sizeof(tc16));   // operand planes
   return n + 4096;
 }
 
@@ -454,11 +679,20 @@ extern "C" int dtts_decode_mel(dtts_acoustic* h, const float* g, const float* z_
   float* a = bump.take<float>((size_t)B * 2 * H * T);
   float* acts = bump.take<float>((size_t)B * H * T);
   float* skip = bump.take<float>((size_t)B * H * T);
+  TcRun tcr{};
+  TcRun* tc = nullptr;
+  if (h->precision) {
+    tcr.cap = (size_t)B * H * tc_rows(T);
+    tcr.hi = bump.take<tc16>(tcr.cap);
+    tcr.lo = bump.take<tc16>(tcr.cap);
+    tc = &tcr;
+  }
   if (!bump.ok) return fail(DTTS_ERR_WORKSPACE_TOO_SMALL, "dtts_decode_mel: workspace too small");
   Launcher L;
   L.stream = (cudaStream_t)stream;
   L.counter = &h->launches;
   cudaStream_t s = L.stream;
+  tcr.h = h; tcr.L = &L; tcr.B = B;
 
   // g_sqz = Conv1d(H,H,k=8,s=4,p=2)(g)  (fvae_semantics.py:93-94; semantics == 0)
   L(launch_conv1d_f32(conv_params(g, T, h->g_pre, 0, H, g_sqz, T4, 1, 4, 2), B, s));
@@ -473,7 +707,7 @@ extern "C" int dtts_decode_mel(dtts_acoustic* h, const float* g, const float* z_
       p.x_bs = (long)d.latent * T4;
       L(launch_conv1d_f32(p, B, s));
     }
-    run_wn(F.wn, FH, d.flow_kernel, fh, g_sqz, H, fcond, fa, facts, fskip, B, T4, L);
+    run_wn(F.wn, FH, d.flow_kernel, fh, g_sqz, H, fcond, fa, facts, fskip, B, T4, L, tc);
     {
       // x1 = x1 - m   (mean_only, logs = 0)
       float* x1 = z_p + (size_t)c_x1 * T4;
@@ -486,7 +720,7 @@ extern "C" int dtts_decode_mel(dtts_acoustic* h, const float* g, const float* z_
   }
   // decoder (fvae_semantics.py:53-58)
   L(launch_conv1d_f32(convT_params(z_p, T4, h->dec_pre, x, T, 4, 0), B, s));
-  run_wn(h->dec_wn, H, d.dec_kernel, x, g, H, cond, a, acts, skip, B, T, L);
+  run_wn(h->dec_wn, H, d.dec_kernel, x, g, H, cond, a, acts, skip, B, T, L, tc);
   {
     ConvParams p = conv_params(skip, T, h->dec_out, 0, d.n_mel, mel, T, 1, 1, 0);
     p.o_bs = (long)T * d.n_mel; p.o_cs = 1; p.o_ts = d.n_mel;                 // mel_out is [B,T,80]

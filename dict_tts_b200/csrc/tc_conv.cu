@@ -24,7 +24,8 @@ namespace {
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 96 + kEpiWarps * 32;
 constexpr int kMaxAStages = 2, kMaxWStages = 6;
-constexpr int kSmemHeader = 2304;            // barriers + tmem ptr (256 B) then bias (<= 512 floats)
+constexpr int kMaxBias = 2048;               // output channels of one launch (bias staged in shared memory)
+constexpr int kSmemHeader = 256 + kMaxBias * 4;   // barriers + tmem ptr (256 B) then bias
 constexpr int kSmemLimit = 227 * 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
   auto acc_full = [&](int s) { return bar0 + 8u * (16 + s); };
   auto acc_empty = [&](int s) { return bar0 + 8u * (18 + s); };
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + 192);
-  float* bias_s = reinterpret_cast<float*>(smem + 256);          // [nblocks * N] <= 512 floats
+  float* bias_s = reinterpret_cast<float*>(smem + 256);          // [nblocks * N] <= kMaxBias floats
 
   const uint32_t a_plane_bytes = (uint32_t)(KC / 8) * p.RA * 16u;
   const uint32_t a_stage_bytes = a_plane_bytes * APL;
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
       const TileCoord tc = decode_unit(p, it, cluster_id, nclusters, rank);
       const int phase = tc.g % p.phases, co_off = (tc.g / p.phases) * N;
       const int as = t_it & 1;
-      const float* resb = p.res ? p.res + (size_t)tc.b * p.o32_bs : nullptr;
+      const float* resb = p.res ? p.res + (size_t)tc.b * (p.o_nct ? p.r_bs : p.o32_bs) : nullptr;
       float* o32b = p.o32 ? p.o32 + (size_t)tc.b * p.o32_bs : nullptr;
 
       // residual prefetch of the first item (overlaps the tail of this tile's MMAs)
@@ -415,9 +416,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
         item_row(idx, t, ok);
         if (resb && ok) {
           const int n0 = co_off + (idx % ncc) * 32;
-          const float4* rp = reinterpret_cast<const float4*>(resb) + ((size_t)(n0 / 4) * p.T_out + t);
+          if (p.o_nct) {                                 // generic strides: element (c, t) at res[b*r_bs + c*r_cs + t*r_ts]
+            const float* rp = resb + (size_t)n0 * p.r_cs + (size_t)t * p.r_ts;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) dst[k] = rp[(size_t)k * p.T_out];   // may alias o32 (in-place y += conv)
+            for (int k = 0; k < 8; ++k)
+              dst[k] = make_float4(rp[(size_t)(4 * k) * p.r_cs], rp[(size_t)(4 * k + 1) * p.r_cs],
+                                   rp[(size_t)(4 * k + 2) * p.r_cs], rp[(size_t)(4 * k + 3) * p.r_cs]);
+          } else {
+            const float4* rp = reinterpret_cast<const float4*>(resb) + ((size_t)(n0 / 4) * p.T_out + t);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) dst[k] = rp[(size_t)k * p.T_out];   // may alias o32 (in-place y += conv)
+          }
         } else {
 #pragma unroll
           for (int k = 0; k < 8; ++k) dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -457,6 +466,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
             v[4 * k + 2] = __uint_as_float(r[4 * k + 2]) + bq.z;
             v[4 * k + 3] = __uint_as_float(r[4 * k + 3]) + bq.w;
           }
+          if (p.act == 1) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = fmaxf(v[k], 0.f);
+          }
+          if (p.alpha != 1.f || p.mask) {               // out = post * (act(conv + bias) * alpha * mask + res)
+            const float am = p.alpha * (p.mask ? __ldg(p.mask + (size_t)tc.b * p.m_bs + t) : 1.f);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] *= am;
+          }
           if (resb) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -467,7 +485,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
 #pragma unroll
             for (int k = 0; k < 32; ++k) v[k] *= p.post;
           }
-          if (o32b) {
+          if (o32b && p.o_nct) {                        // element (c, t) at out[b*o32_bs + c*o_cs + t*o_ts]
+            float* op = o32b + (size_t)n0 * p.o_cs + (size_t)t * p.o_ts;
+            if (p.accumulate) {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) v[k] += op[(size_t)k * p.o_cs];
+            }
+#pragma unroll
+            for (int k = 0; k < 32; ++k) op[(size_t)k * p.o_cs] = v[k];
+          } else if (o32b) {
             float4* op = reinterpret_cast<float4*>(o32b) + ((size_t)(n0 / 4) * p.T_out + t);
             if (p.accumulate) {
               float4 old[8];
@@ -561,10 +587,22 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ w, tc16* __rest
 }
 
 __global__ void tc_to_planes_kernel(const float* __restrict__ x, long bs, long cs, long ts, int C, int T, float slope,
-                                    tc16* __restrict__ hi, tc16* __restrict__ lo, int rows, int pad, int fmt) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+                                    tc16* __restrict__ hi, tc16* __restrict__ lo, int rows, int pad, int fmt, int full) {
+  // full: the grid walks ALL rows of the slab and zero-fills the halo rows (one launch instead of convert + zero_halo)
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = full ? r - pad : r;
   const int sl = blockIdx.y, b = blockIdx.z;
-  if (t >= T) return;
+  if (full) {
+    if (r >= rows) return;
+    if (t < 0 || t >= T) {
+      const size_t zoff = (((size_t)b * (C / 8) + sl) * rows + r) * 8;
+      *reinterpret_cast<uint4*>(hi + zoff) = make_uint4(0, 0, 0, 0);
+      if (lo) *reinterpret_cast<uint4*>(lo + zoff) = make_uint4(0, 0, 0, 0);
+      return;
+    }
+  } else if (t >= T) {
+    return;
+  }
   uint32_t hw[4], lw[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
@@ -702,6 +740,8 @@ void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq, int a_planes) {
   p->w_stages = ws;
   p->csize = 1;
   p->nu = 0;
+  p->o_nct = 0; p->o_cs = p->o_ts = 0; p->r_bs = p->r_cs = p->r_ts = 0;
+  p->mask = nullptr; p->m_bs = 0; p->act = 0; p->alpha = 1.f;
 }
 
 static size_t tc_smem_bytes(const TcConvParams& p) {
@@ -731,7 +771,7 @@ cudaError_t launch_tc_conv(TcConvParams p, int B, cudaStream_t stream) {
   if (p.a_planes < 1 || p.a_planes > 2 || p.w_planes < 1 || p.w_planes > 2 || (p.a_planes == 2 && !p.a_lo))
     return cudaErrorInvalidValue;
   if (p.TG < 1 || p.w_stages < 1 || p.N % 32 != 0 || p.N > 256 || p.KC % 16 != 0 || p.C_in % p.KC != 0 ||
-      p.N * p.nblocks > 512 || p.NACC * p.NM > 256 || (p.stack && (p.w_planes != 1 || p.NM != 2 * p.N)) ||
+      p.N * p.nblocks > kMaxBias || p.NACC * p.NM > 256 || (p.stack && (p.w_planes != 1 || p.NM != 2 * p.N)) ||
       (!p.stack && p.NM != p.N))
     return cudaErrorInvalidConfiguration;
   const int max_off = p.min_off + (p.RA - p.MT);
@@ -795,7 +835,15 @@ cudaError_t tc_to_planes(const float* x, long bs, long cs, long ts, int B, int C
                          tc16* hi, tc16* lo, int rows, int pad, int fmt, cudaStream_t s) {
   if (C % 8) return cudaErrorInvalidValue;
   dim3 grid(cdiv(T, 128), C / 8, B);
-  tc_to_planes_kernel<<<grid, 128, 0, s>>>(x, bs, cs, ts, C, T, slope, hi, lo, rows, pad, fmt);
+  tc_to_planes_kernel<<<grid, 128, 0, s>>>(x, bs, cs, ts, C, T, slope, hi, lo, rows, pad, fmt, 0);
+  return cudaGetLastError();
+}
+
+cudaError_t tc_to_planes_full(const float* x, long bs, long cs, long ts, int B, int C, int T, float slope, tc16* hi,
+                              tc16* lo, int rows, int pad, int fmt, cudaStream_t s) {
+  if (C % 8) return cudaErrorInvalidValue;
+  dim3 grid(cdiv(rows, 128), C / 8, B);
+  tc_to_planes_kernel<<<grid, 128, 0, s>>>(x, bs, cs, ts, C, T, slope, hi, lo, rows, pad, fmt, 1);
   return cudaGetLastError();
 }
 

@@ -51,7 +51,10 @@ constexpr int TC_PADF = 32;        // zero rows in front of t = 0 (>= largest le
 constexpr int TC_PADB = 32;        // zero rows kept after the last tile
 constexpr int TC_ROW_ALIGN = 512;  // tiles are at most 512 rows
 // rows allocated per slab for a tensor of T time steps
-static inline int tc_rows(int T) { return TC_PADF + (T + 8 + TC_ROW_ALIGN - 1) / TC_ROW_ALIGN * TC_ROW_ALIGN + TC_PADB; }
+static inline int tc_rows(int T) {
+  const int align = T + 8 <= 128 ? 128 : (T + 8 <= 256 ? 256 : TC_ROW_ALIGN);   // short sequences use 128/256-row tiles
+  return TC_PADF + (T + 8 + align - 1) / align * align + TC_PADB;
+}
 
 // Packed weights of one convolution: blobs [group][chunk][tap] of {hi plane, lo plane}, each plane [KC/8][N][8] bf16
 // (the shared-memory image of the B operand).  group = nblock * phases + phase.
@@ -97,6 +100,13 @@ struct TcConvParams {
   int op_rows, op_pad;
   float post, slope;
   int accumulate;
+  // generic-stride fp32 output / residual (acoustic model, [B,C,T] or [B,T,C] tensors) instead of the fp32 stream:
+  int o_nct;                     // 1: out element (c,t) at o32[b*o32_bs + c*o_cs + t*o_ts], res at res[b*r_bs + c*r_cs + t*r_ts]
+  long o_cs, o_ts, r_bs, r_cs, r_ts;
+  const float* mask;             // optional [B][m_bs] multiplier per (b, t)
+  int m_bs;
+  int act;                       // 0: none, 1: ReLU (applied to conv + bias)
+  float alpha;                   // out = post * (act(conv + bias) * alpha * mask + res)  (+ out if accumulate)
   int a_stages, w_stages;
   int TG;                        // taps per weight stage
   int ntiles, B;                 // time tiles per (group, batch item); batch size (set by the launcher)
@@ -116,6 +126,9 @@ cudaError_t tc_pack_weights(const float* w_ref, tc16* out, int C_out, int C_in, 
 // fp32 strided tensor x[b*bs + c*cs + t*ts] -> operand planes of leaky(x, slope) (valid rows only)
 cudaError_t tc_to_planes(const float* x, long bs, long cs, long ts, int B, int C, int T, float slope,
                          tc16* hi, tc16* lo, int rows, int pad, int fmt, cudaStream_t s);
+// same, and zero-fills every row outside [pad, pad+T) (one launch for a freshly re-shaped scratch buffer)
+cudaError_t tc_to_planes_full(const float* x, long bs, long cs, long ts, int B, int C, int T, float slope, tc16* hi,
+                              tc16* lo, int rows, int pad, int fmt, cudaStream_t s);
 // zero the halo rows [0,pad) and [pad+T, rows) of every slab of a plane pair
 cudaError_t tc_zero_halo(tc16* hi, tc16* lo, int n_slabs_total, int rows, int pad, int T,
                          cudaStream_t s);

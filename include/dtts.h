@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DTTS_ABI_VERSION 1
+#define DTTS_ABI_VERSION 2
 
 typedef enum dtts_status {
   DTTS_OK = 0,
@@ -57,6 +57,8 @@ typedef struct dtts_acoustic_desc {
   int32_t flow_hidden, flow_kernel, flow_blocks, flow_layers;
   int32_t n_mel;
   int32_t language_zh; /* 1: apply add_pron_rule (layers/utils.py:109-115) */
+  int32_t precision;   /* dense convolutions (encoder QKV/O/FFN, S2PA projections, duration predictor, WaveNet stacks):
+                          0 = fp32 FMA pipe (exact), 1 = tcgen05 with bf16 hi/lo split operands (3 MMAs, fp32-class) */
 } dtts_acoustic_desc;
 
 /* HiFi-GAN V1 generator description (egs/egs_bases/tts/vocoder/hifigan.yaml:3-10). */

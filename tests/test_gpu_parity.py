@@ -17,11 +17,13 @@ from tests.cases import (ACOUSTIC_CASES, ACOUSTIC_SEED, TOL_MEL_MAXABS, TOL_WAV_
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def acoustic():
+@pytest.fixture(scope="module", params=[0, 1], ids=["fp32", "tcgen05"])
+def acoustic(request):
+    """Both acoustic precisions: 0 = every convolution on the fp32 FMA pipe, 1 = dense convolutions on tcgen05 with
+    bf16 hi/lo split operands (the default of the engine)."""
     from dict_tts_b200.engine import DictTTSEngine
     sd = synth.make_acoustic_state_dict(ACOUSTIC_SEED)
-    eng = DictTTSEngine(sd)
+    eng = DictTTSEngine(sd, precision=request.param)
     yield eng, fold_weight_norm(sd)
     eng.close()
 
@@ -30,7 +32,7 @@ def acoustic():
 def vocoder():
     from dict_tts_b200.engine import HifiGanEngine
     sd = synth.make_vocoder_state_dict(VOCODER_SEED)
-    eng = HifiGanEngine(sd)
+    eng = HifiGanEngine(sd, precision=0)            # exact fp32 path; the tcgen05 modes are in test_gpu_tensorcore.py
     yield eng, fold_weight_norm(sd)
     eng.close()
 

@@ -107,7 +107,7 @@ def test_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/dtts.h but not exported"
     assert declared == set(binding.SYMBOLS), declared ^ set(binding.SYMBOLS)
-    assert binding.load().dtts_abi_version() == 1
+    assert binding.load().dtts_abi_version() == binding.ABI_VERSION
 
 
 def test_engine_refuses_to_run_without_cuda():
