@@ -2,6 +2,7 @@
 // residual-coupling prior flow.  Mirrors PortaSpeech_dict.forward(infer=True) (modules/dict_tts/model.py:36-122).
 #include "engine.cuh"
 #include "tc_conv.cuh"
+#include "tc16.cuh"
 
 using namespace dtts;
 
@@ -121,32 +122,50 @@ int tc_pack1(dtts_acoustic* h, const std::string& name, bool has_bias, int C_out
   return tc_pack(h, &w, 1, b, C_out, C_in, K, transposed, N, cw, s);
 }
 
-// Per-call context of the tensor-core convolutions: one scratch pair of operand planes (the input of the next
-// convolution is converted into it, halo rows zeroed in the same launch) and the launch glue.
+// One set of operand planes in the caller's workspace; (C, T, rows) describe what it currently holds.
+struct Planes {
+  tc16 *hi = nullptr, *lo = nullptr;
+  size_t cap = 0;                 // elements per plane
+  int C = 0, T = 0, rows = 0;
+};
+
+// Per-call context of the tensor-core convolutions: operand-plane sets (inputs are written there by the producing
+// kernel -- LayerNorm, attention, gate, a convolution epilogue -- or converted from fp32 by stage()) and launch glue.
 struct TcRun {
   dtts_acoustic* h;
   Launcher* L;
   int B;
-  tc16 *hi, *lo;
-  size_t cap;                     // elements per plane
-  int C = 0, T = 0, rows = 0;     // what is staged
+  Planes P[3];
   struct Epi {
     const float* res = nullptr; long r_bs = 0, r_cs = 0, r_ts = 1;
     const float* mask = nullptr; int m_bs = 0;
     int act = 0; float alpha = 1.f, post = 1.f; int accumulate = 0;
   };
-  // x element (c,t) of batch b at x[b*bs + c*cs + t*ts]
-  void stage(const float* x, long bs, long cs, long ts, int C_, int T_) {
-    C = C_; T = T_; rows = tc_rows(T_);
-    if ((size_t)B * C * rows > cap) { (*L)(cudaErrorInvalidValue); return; }
-    (*L)(tc_to_planes_full(x, bs, cs, ts, B, C, T, 1.f, hi, h->mode.a_planes == 2 ? lo : nullptr, rows, TC_PADF,
+  bool shape(Planes& p, int C, int T) {
+    p.C = C; p.T = T; p.rows = tc_rows(T);
+    if ((size_t)B * C * p.rows > p.cap) { (*L)(cudaErrorInvalidValue); return false; }
+    return true;
+  }
+  // destination descriptor for a producer kernel
+  PlaneOut out_of(Planes& p, int C, int T, bool zero_halo) {
+    PlaneOut o;
+    if (!shape(p, C, T)) return o;
+    o.hi = p.hi; o.lo = h->mode.a_planes == 2 ? p.lo : nullptr;
+    o.rows = p.rows; o.pad = TC_PADF; o.fmt = h->mode.fmt; o.zero_halo = zero_halo ? 1 : 0;
+    return o;
+  }
+  // fp32 x (element (c,t) of batch b at x[b*bs + c*cs + t*ts]) -> planes, halo rows zeroed
+  void stage(Planes& p, const float* x, long bs, long cs, long ts, int C, int T) {
+    if (!shape(p, C, T)) return;
+    (*L)(tc_to_planes_full(x, bs, cs, ts, B, C, T, 1.f, p.hi, h->mode.a_planes == 2 ? p.lo : nullptr, p.rows, TC_PADF,
                            h->mode.fmt, L->stream));
   }
-  void stage_nct(const float* x, int C_, int T_) { stage(x, (long)C_ * T_, T_, 1, C_, T_); }
-  // blocks [blk0, blk0+nblk) of w -> out element (c,t) at out[b*o_bs + c*o_cs + t*o_ts], c counted from the first block
-  void conv(const TcConvW& w, int blk0, int nblk, float* out, long o_bs, long o_cs, long o_ts, int T_out, int dil,
-            int pad, const Epi& e) {
-    if (w.C_in != C) { (*L)(cudaErrorInvalidValue); return; }
+  void stage_nct(Planes& p, const float* x, int C, int T) { stage(p, x, (long)C * T, T, 1, C, T); }
+  // blocks [blk0, blk0+nblk) of w applied to `in`; fp32 result (optional) element (c,t) at out[b*o_bs + c*o_cs + t*o_ts]
+  // with c counted from the first block; `po` (optional) receives the result as operand planes of the next convolution.
+  void conv(const Planes& in, const TcConvW& w, int blk0, int nblk, float* out, long o_bs, long o_cs, long o_ts,
+            int T_out, int dil, int pad, const Epi& e, Planes* po = nullptr) {
+    if (w.C_in != in.C) { (*L)(cudaErrorInvalidValue); return; }
     TcConvW sub = w;
     const int nblocks = w.C_out / w.N;
     if (nblk <= 0) nblk = nblocks - blk0;
@@ -154,8 +173,8 @@ struct TcRun {
     sub.w = w.w + (size_t)blk0 * (w.elems() / nblocks);
     sub.bias = w.bias ? w.bias + (size_t)blk0 * w.N : nullptr;
     TcConvParams p{};
-    p.a_hi = hi; p.a_lo = h->mode.a_planes == 2 ? lo : nullptr;
-    p.a_bs = (long)C * rows; p.a_rows = rows; p.a_pad = TC_PADF;
+    p.a_hi = in.hi; p.a_lo = h->mode.a_planes == 2 ? in.lo : nullptr;
+    p.a_bs = (long)in.C * in.rows; p.a_rows = in.rows; p.a_pad = TC_PADF;
     p.tap_off0 = -pad; p.tap_step = dil;
     tc_conv_plan(&p, sub, T_out, h->mode.a_planes);
     p.ot_mul = 1; p.ot_add = 0; p.T_out = T_out;
@@ -163,12 +182,26 @@ struct TcRun {
     p.res = e.res; p.r_bs = e.r_bs; p.r_cs = e.r_cs; p.r_ts = e.r_ts;
     p.mask = e.mask; p.m_bs = e.m_bs; p.act = e.act; p.alpha = e.alpha; p.post = e.post; p.accumulate = e.accumulate;
     p.slope = 1.f;
+    if (po) {
+      if (!shape(*po, sub.C_out, T_out)) return;
+      p.o_hi = po->hi; p.o_lo = h->mode.a_planes == 2 ? po->lo : nullptr;
+      p.op_bs = (long)po->C * po->rows; p.op_rows = po->rows; p.op_pad = TC_PADF;
+    }
     (*L)(launch_tc_conv(p, B, L->stream));
   }
-  void conv_nct(const TcConvW& w, float* out, int T_out, int dil, int pad, const Epi& e, int blk0 = 0, int nblk = 0) {
+  void conv_nct(const Planes& in, const TcConvW& w, float* out, int T_out, int dil, int pad, const Epi& e, int blk0 = 0,
+                int nblk = 0, Planes* po = nullptr) {
     const int nblocks = w.C_out / w.N;
     const int co = (nblk > 0 ? nblk : nblocks - blk0) * w.N;
-    conv(w, blk0, nblk, out, (long)co * T_out, T_out, 1, T_out, dil, pad, e);
+    conv(in, w, blk0, nblk, out, (long)co * T_out, T_out, 1, T_out, dil, pad, e, po);
+  }
+  // carve `n` plane sets of `cap` elements per plane out of the workspace
+  void take(Bump& bump, int n, size_t cap) {
+    for (int i = 0; i < n; ++i) {
+      P[i].cap = cap;
+      P[i].hi = bump.take<tc16>(cap);
+      P[i].lo = bump.take<tc16>(cap);
+    }
   }
 };
 
@@ -246,28 +279,36 @@ void run_encoder(dtts_acoustic* h, const EncoderW& E, float* x, float* hbuf, flo
   const int H = h->d.hidden, F = h->d.ffn_filter, K = h->d.ffn_kernel;
   cudaStream_t s = L.stream;
   if (tc) {
+    Planes &P0 = tc->P[0], &P1 = tc->P[1];
+    TcRun::Epi res_x;
+    res_x.res = x; res_x.r_bs = (long)H * Tw; res_x.r_cs = Tw; res_x.r_ts = 1;
     for (size_t i = 0; i < E.layers.size(); ++i) {
       const EncLayerW& W = E.layers[i];
-      L(apply_mask(x, seq_mask, B, H, Tw, s));
-      L(channel_layernorm(x, hbuf, W.g1, W.b1, 1e-4f, nullptr, nullptr, B, H, Tw, s));
-      tc->stage_nct(hbuf, H, Tw);
-      tc->conv_nct(W.t_qkv, qkv, Tw, 1, 0, TcRun::Epi());
-      L(self_attention(qkv, qkv + (size_t)H * Tw, qkv + (size_t)2 * H * Tw, seq_mask, att, B, H, Tw, h->d.n_heads, s));
-      TcRun::Epi res_x;
-      res_x.res = x; res_x.r_bs = (long)H * Tw; res_x.r_cs = Tw; res_x.r_ts = 1;
-      tc->stage_nct(att, H, Tw);
-      tc->conv_nct(W.t_o, x, Tw, 1, 0, res_x);
-      L(channel_layernorm(x, hbuf, W.g2, W.b2, 1e-4f, nullptr, seq_mask, B, H, Tw, s));   // FFN input is x * x_mask
+      // x = x * x_mask ; LN1 -> operand planes of the fused q|k|v projection
+      L(channel_layernorm_planes(x, x, nullptr, W.g1, W.b1, 1e-4f, seq_mask, nullptr, B, H, Tw,
+                                 tc->out_of(P0, H, Tw, false), s));
+      tc->conv_nct(P0, W.t_qkv, qkv, Tw, 1, 0, TcRun::Epi());
+      if (Tw <= 64) {
+        L(self_attention_planes(qkv, qkv + (size_t)H * Tw, qkv + (size_t)2 * H * Tw, seq_mask, nullptr, B, H, Tw,
+                                h->d.n_heads, tc->out_of(P0, H, Tw, false), s));
+      } else {
+        L(self_attention(qkv, qkv + (size_t)H * Tw, qkv + (size_t)2 * H * Tw, seq_mask, att, B, H, Tw, h->d.n_heads, s));
+        tc->stage_nct(P0, att, H, Tw);
+      }
+      tc->conv_nct(P0, W.t_o, x, Tw, 1, 0, res_x);
+      // LN2 (* x_mask) -> planes with zeroed halo (the FFN's first convolution has k = 5)
+      L(channel_layernorm_planes(x, nullptr, nullptr, W.g2, W.b2, 1e-4f, nullptr, seq_mask, B, H, Tw,
+                                 tc->out_of(P0, H, Tw, true), s));
       TcRun::Epi e1;
       e1.act = 1; e1.mask = seq_mask; e1.m_bs = Tw;
-      tc->stage_nct(hbuf, H, Tw);
-      tc->conv_nct(W.t_ffn1, ffn, Tw, 1, K / 2, e1);
+      tc->conv_nct(P0, W.t_ffn1, nullptr, Tw, 1, K / 2, e1, 0, 0, &P1);      // relu(.) * mask straight into planes
       TcRun::Epi e2 = res_x;
       e2.mask = seq_mask; e2.m_bs = Tw;
-      tc->stage_nct(ffn, F, Tw);
-      tc->conv_nct(W.t_ffn2, x, Tw, 1, 0, e2);
+      tc->conv_nct(P1, W.t_ffn2, x, Tw, 1, 0, e2);
     }
-    L(channel_layernorm(x, hbuf, E.last_g, E.last_b, 1e-4f, nullptr, seq_mask, B, H, Tw, s));
+    // last LN: fp32 [B,H,T] for the consumers and planes (P0) for the S2PA query projection
+    L(channel_layernorm_planes(x, nullptr, hbuf, E.last_g, E.last_b, 1e-4f, nullptr, seq_mask, B, H, Tw,
+                               tc->out_of(P0, H, Tw, false), s));
     return;
   }
   for (size_t i = 0; i < E.layers.size(); ++i) {
@@ -304,23 +345,23 @@ void run_wn(const WNW& W, int hidden, int K, float* hx, const float* g, int gin,
   cudaStream_t s = L.stream;
   const int n = (int)W.in_layers.size();
   if (tc) {
-    tc->stage_nct(g, gin, T);
-    tc->conv_nct(W.t_cond, cond, T, 1, 0, TcRun::Epi());
+    Planes &Pg = tc->P[0], &Px = tc->P[1], &Pa = tc->P[2];
+    tc->stage_nct(Pg, g, gin, T);
+    tc->conv_nct(Pg, W.t_cond, cond, T, 1, 0, TcRun::Epi());
+    tc->stage_nct(Px, hx, hidden, T);                                   // halo zeroed once; epilogues refresh rows [0,T)
     for (int i = 0; i < n; ++i) {
       TcRun::Epi ea;
       ea.res = cond + (size_t)2 * hidden * i * T; ea.r_bs = (long)W.cond.C_out * T; ea.r_cs = T; ea.r_ts = 1;
-      tc->stage_nct(hx, hidden, T);
-      tc->conv_nct(W.t_in[i], a, T, 1, K / 2, ea);
-      L(wn_gate(a, acts, B, hidden, T, s));
-      tc->stage_nct(acts, hidden, T);
+      tc->conv_nct(Px, W.t_in[i], a, T, 1, K / 2, ea);
+      L(wn_gate_planes(a, B, hidden, T, tc->out_of(Pa, hidden, T, false), s));
       TcRun::Epi ex, es;
       ex.res = hx; ex.r_bs = (long)hidden * T; ex.r_cs = T; ex.r_ts = 1;
       es.accumulate = (i > 0);
       if (i < n - 1) {
-        tc->conv_nct(W.t_rs[i], hx, T, 1, 0, ex, 0, 1);                 // x = x + rs[:hidden]
-        tc->conv_nct(W.t_rs[i], skip, T, 1, 0, es, 1, 1);               // out += rs[hidden:]
+        tc->conv_nct(Pa, W.t_rs[i], hx, T, 1, 0, ex, 0, 1, &Px);        // x = x + rs[:hidden]  (fp32 + planes)
+        tc->conv_nct(Pa, W.t_rs[i], skip, T, 1, 0, es, 1, 1);           // out += rs[hidden:]
       } else {
-        tc->conv_nct(W.t_rs[i], skip, T, 1, 0, es, 0, 1);
+        tc->conv_nct(Pa, W.t_rs[i], skip, T, 1, 0, es, 0, 1);
       }
     }
     return;
@@ -488,7 +529,7 @@ extern "C" uint64_t dtts_text_workspace_bytes(const dtts_acoustic* h, int32_t B,
   add(bt); add(bt); add(bt); add(B); add(64);                                  // masks, lens, maxes
   add(bt * H); add(bt * D); add(bt * Lk); add(bt * D); add(bt * H); add(bt * H);  // q, qk, weights, ctx, ctxv, context
   add(bt * H); add(bt * C); add(bt * C);                                        // dur_in, d1, d2
-  if (h->precision) n += 2 * ws_round((size_t)B * (F > D ? F : D) * tc_rows(Tw) * sizeof(tc16));   // operand planes
+  if (h->precision) n += 4 * ws_round((size_t)B * (F > D ? F : D) * tc_rows(Tw) * sizeof(tc16));   // 2 operand-plane sets
   return n + 4096;
 }
 
@@ -531,9 +572,8 @@ extern "C" int dtts_text_encode(dtts_acoustic* h, const dtts_text_in* in, const 
   TcRun tcr{};
   TcRun* tc = nullptr;
   if (h->precision) {
-    tcr.cap = (size_t)B * (F > D ? F : D) * tc_rows(Tw);
-    tcr.hi = bump.take<tc16>(tcr.cap);
-    tcr.lo = bump.take<tc16>(tcr.cap);
+    tcr.B = B;
+    tcr.take(bump, 2, (size_t)B * (F > D ? F : D) * tc_rows(Tw));
     tc = &tcr;
   }
   if (!bump.ok) return fail(DTTS_ERR_WORKSPACE_TOO_SMALL, "dtts_text_encode: workspace too small");
@@ -549,12 +589,10 @@ extern "C" int dtts_text_encode(dtts_acoustic* h, const dtts_text_in* in, const 
   run_encoder(h, h->sem, x, hb, qkv, att, ffn, seq_mask, B, Tw, L, tc);       // semantic encoder -> hb
   // S2PA (dict_encoder.py:32-66), folded: logits = keys . (W_k^T (W_q x) * D^-1/2)
   if (tc) {
-    tc->stage_nct(hb, H, Tw);
-    tc->conv_nct(h->t_s2pa_q, q, Tw, 1, 0, TcRun::Epi());
     TcRun::Epi ek;
     ek.alpha = 1.f / sqrtf((float)D);
-    tc->stage_nct(q, H, Tw);
-    tc->conv_nct(h->t_s2pa_kT, qk, Tw, 1, 0, ek);
+    tc->conv_nct(tc->P[0], h->t_s2pa_q, nullptr, Tw, 1, 0, TcRun::Epi(), 0, 0, &tc->P[1]);   // P[0] = last LN of the encoder
+    tc->conv_nct(tc->P[1], h->t_s2pa_kT, qk, Tw, 1, 0, ek);
   } else {
     L(launch_conv1d_f32(conv_params(hb, Tw, h->s2pa_q, 0, H, q, Tw, 1, 1, 0), B, s));
     ConvParams p = conv_params(q, Tw, h->s2pa_kT, 0, D, qk, Tw, 1, 1, 0);
@@ -563,10 +601,9 @@ extern "C" int dtts_text_encode(dtts_acoustic* h, const dtts_text_in* in, const 
   }
   L(s2pa_stream(in->keys_dev, in->values_dev, in->key_map_dev, qk, B, Tw, Lk, D, weights, out->dict_attn_dev, ctx, s));
   if (tc) {
-    tc->stage_nct(ctx, D, Tw);
-    tc->conv_nct(h->t_s2pa_v, ctxv, Tw, 1, 0, TcRun::Epi());
-    tc->stage_nct(ctxv, H, Tw);
-    tc->conv_nct(h->t_s2pa_o, context, Tw, 1, 0, TcRun::Epi());
+    tc->stage_nct(tc->P[0], ctx, D, Tw);
+    tc->conv_nct(tc->P[0], h->t_s2pa_v, nullptr, Tw, 1, 0, TcRun::Epi(), 0, 0, &tc->P[1]);
+    tc->conv_nct(tc->P[1], h->t_s2pa_o, context, Tw, 1, 0, TcRun::Epi());
   } else {
     L(launch_conv1d_f32(conv_params(ctx, Tw, h->s2pa_v, 0, H, ctxv, Tw, 1, 1, 0), B, s));
     L(launch_conv1d_f32(conv_params(ctxv, Tw, h->s2pa_o, 0, H, context, Tw, 1, 1, 0), B, s));
@@ -583,20 +620,23 @@ extern "C" int dtts_text_encode(dtts_acoustic* h, const dtts_text_in* in, const 
   // duration predictor (portaspeech/model.py:58-66)
   const float* cur = dur_in;
   float* bufs[2] = {d1, d2};
+  if (tc) tc->stage_nct(tc->P[0], dur_in, H, Tw);
   for (int i = 0; i < d.dur_layers; ++i) {
     float* c = bufs[0];
     float* y = bufs[1];
     if (tc) {
       TcRun::Epi er;
       er.act = 1;
-      tc->stage_nct(cur, i == 0 ? H : C, Tw);
-      tc->conv_nct(h->t_dur[i], c, Tw, 1, (d.dur_kernel - 1) / 2, er);
+      tc->conv_nct(tc->P[0], h->t_dur[i], c, Tw, 1, (d.dur_kernel - 1) / 2, er);
+      const bool last = i == d.dur_layers - 1;              // LayerNorm -> next convolution's planes (k = 5: zero halo)
+      L(channel_layernorm_planes(c, nullptr, y, h->dur_ln_g[i], h->dur_ln_b[i], 1e-5f, nullptr, keep, B, C, Tw,
+                                 last ? PlaneOut() : tc->out_of(tc->P[0], C, Tw, true), s));
     } else {
       ConvParams p = conv_params(cur, Tw, h->dur_conv[i], 0, C, c, Tw, 1, 1, (d.dur_kernel - 1) / 2);
       p.act = ACT_RELU;
       L(launch_conv1d_f32(p, B, s));
+      L(channel_layernorm(c, y, h->dur_ln_g[i], h->dur_ln_b[i], 1e-5f, nullptr, keep, B, C, Tw, s));
     }
-    L(channel_layernorm(c, y, h->dur_ln_g[i], h->dur_ln_b[i], 1e-5f, nullptr, keep, B, C, Tw, s));
     cur = y;
     bufs[0] = c;      // conv output buffer can be reused: next conv reads y, writes c
   }
@@ -654,7 +694,7 @@ extern "C" uint64_t dtts_decode_workspace_bytes(const dtts_acoustic* h, int32_t 
   add(B * H * T);                                      // x
   add(B * 2 * H * h->d.dec_layers * T);                // cond
   add(B * 2 * H * T); add(B * H * T); add(B * H * T);  // a, acts, skip
-  if (h->precision) n += 2 * ws_round((size_t)B * H * tc_rows(T) * sizeof(tc16));   // operand planes
+  if (h->precision) n += 6 * ws_round((size_t)B * H * tc_rows(T) * sizeof(tc16));   // 3 operand-plane sets
   return n + 4096;
 }
 
@@ -682,9 +722,8 @@ extern "C" int dtts_decode_mel(dtts_acoustic* h, const float* g, const float* z_
   TcRun tcr{};
   TcRun* tc = nullptr;
   if (h->precision) {
-    tcr.cap = (size_t)B * H * tc_rows(T);
-    tcr.hi = bump.take<tc16>(tcr.cap);
-    tcr.lo = bump.take<tc16>(tcr.cap);
+    tcr.B = B;
+    tcr.take(bump, 3, (size_t)B * H * tc_rows(T));
     tc = &tcr;
   }
   if (!bump.ok) return fail(DTTS_ERR_WORKSPACE_TOO_SMALL, "dtts_decode_mel: workspace too small");

@@ -2,6 +2,7 @@
 // repack.cu).  All activations inside the engine are fp32, channels-first [B, C, T] unless stated.
 #pragma once
 #include "common.cuh"
+#include "tc_conv.cuh"
 
 namespace dtts {
 
@@ -23,6 +24,15 @@ cudaError_t embed_tokens(const int64_t* tok, const float* emb, float scale, int 
 // y = LN_c(x * in_mask) * gamma + beta, then * out_mask   (masks may be null) ; layout [B,C,T]
 cudaError_t channel_layernorm(const float* x, float* y, const float* gamma, const float* beta, float eps,
                               const float* in_mask, const float* out_mask, int B, int C, int T, cudaStream_t s);
+// Tiled LayerNorm with optional extra outputs: xw = x * in_mask (may alias x), y [B,C,T] (may be null) and operand planes.
+struct PlaneOut;
+cudaError_t channel_layernorm_planes(const float* x, float* xw, float* y, const float* gamma, const float* beta, float eps,
+                                     const float* in_mask, const float* out_mask, int B, int C, int T, const PlaneOut& po,
+                                     cudaStream_t s);
+// Shared-memory self attention for T <= 64; q,k,v are the three C-channel thirds of one [B,3C,T] tensor.
+cudaError_t self_attention_planes(const float* q, const float* k, const float* v, const float* mask, float* out, int B,
+                                  int C, int T, int heads, const PlaneOut& po, cudaStream_t s);
+cudaError_t wn_gate_planes(const float* a, int B, int H, int T, const PlaneOut& po, cudaStream_t s);
 // x *= mask (in place), [B,C,T] with mask [B,T]
 cudaError_t apply_mask(float* x, const float* mask, int B, int C, int T, cudaStream_t s);
 // multi-head self attention on q,k,v [B,C,T] (C = heads*dk), mask [B,T]; out [B,C,T]

@@ -14,6 +14,7 @@
 // MMA warps of ALL peers have released it (tcgen05.commit ... .multicast::cluster onto every peer's w_empty barrier).
 // Without this the weight stream (C_out*C_in*K*2 B per 128-row tile) makes the big layers L2-bandwidth bound.
 #include "tc_conv.cuh"
+#include "tc16.cuh"
 
 #include <cstdlib>
 
@@ -125,32 +126,6 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
-
-// fp32 -> 16-bit operand (fmt 0: fp16, saturated to the finite range; 1: bf16), round to nearest even, and back.
-__device__ __forceinline__ uint32_t cvt16(float v, int fmt) {
-  if (fmt) return __bfloat16_as_ushort(__float2bfloat16_rn(v));
-  return __half_as_ushort(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)));
-}
-__device__ __forceinline__ float back16(uint32_t h, int fmt) {
-  if (fmt) return __bfloat162float(__ushort_as_bfloat16((unsigned short)h));
-  return __half2float(__ushort_as_half((unsigned short)h));
-}
-// two consecutive channels -> one packed 32-bit word with a single F2FP instruction (fp16 saturates to the finite range)
-__device__ __forceinline__ uint32_t pack2(float a0, float a1, int fmt) {
-  if (fmt) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
-    return *reinterpret_cast<const uint32_t*>(&h);
-  }
-  const __half2 lim = __floats2half2_rn(65504.f, 65504.f);
-  const __half2 h = __hmin2(__hmax2(__floats2half2_rn(a0, a1), __hneg2(lim)), lim);
-  return *reinterpret_cast<const uint32_t*>(&h);
-}
-// two consecutive channels -> packed hi word and (residual) lo word
-__device__ __forceinline__ void split2(float a0, float a1, int fmt, uint32_t& hw, uint32_t& lw) {
-  hw = pack2(a0, a1, fmt);
-  lw = pack2(a0 - back16(hw & 0xFFFFu, fmt), a1 - back16(hw >> 16, fmt), fmt);
-}
-
 
 __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
   uint64_t d;

@@ -5,6 +5,7 @@
 // 109-115, modules/commons/rel_transformer_encoder.py:55-79,117-158,261-279, modules/portaspeech/model.py:58-66,
 // modules/dict_tts/model.py:64-82.
 #include "kernels.cuh"
+#include "tc16.cuh"
 
 namespace dtts {
 
@@ -72,6 +73,178 @@ cudaError_t channel_layernorm(const float* x, float* y, const float* gamma, cons
                               const float* in_mask, const float* out_mask, int B, int C, int T, cudaStream_t s) {
   dim3 grid(cdiv(T, 32), B);
   channel_ln_kernel<<<grid, 32, 0, s>>>(x, y, gamma, beta, eps, in_mask, out_mask, C, T);
+  return cudaGetLastError();
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// Tiled channel LayerNorm: block = (32 time steps, batch item), 256 threads = 8 channel groups x 32 lanes along t.
+// The tile is staged in shared memory (coalesced along t), statistics are two-pass like the reference, and the result
+// goes to y [B,C,T] and/or straight into tensor-core operand planes (saves a conversion launch per convolution).
+// xw (optional): x * in_mask is written back (Encoder.forward's `x = x * x_mask`, rel_transformer_encoder.py:58).
+__global__ void __launch_bounds__(256) channel_ln_tiled_kernel(const float* __restrict__ x, float* __restrict__ xw,
+                                                               float* __restrict__ y, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, float eps,
+                                                               const float* __restrict__ in_mask,
+                                                               const float* __restrict__ out_mask, int C, int T,
+                                                               PlaneOut po) {
+  extern __shared__ float sm[];                      // xs[C][33], red[8][32], mean[32], rstd[32]
+  float* xs = sm;
+  float* red = sm + (size_t)C * 33;
+  float* mean_s = red + 256;
+  float* rstd_s = mean_s + 32;
+  const int b = blockIdx.y, t0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int t = t0 + lane;
+  const bool tv = t < T;
+  const float im = (in_mask && tv) ? in_mask[(size_t)b * T + t] : 1.f;
+  const float om = (out_mask && tv) ? out_mask[(size_t)b * T + t] : 1.f;
+  const float* xb = x + (size_t)b * C * T;
+  float part = 0.f;
+  for (int c = grp; c < C; c += 8) {
+    const float v = tv ? xb[(size_t)c * T + t] * im : 0.f;
+    xs[c * 33 + lane] = v;
+    if (xw && tv) xw[(size_t)b * C * T + (size_t)c * T + t] = v;
+    part += v;
+  }
+  red[grp * 32 + lane] = part;
+  __syncthreads();
+  if (grp == 0) {
+    float m = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) m += red[g * 32 + lane];
+    mean_s[lane] = m / (float)C;
+  }
+  __syncthreads();
+  const float mean = mean_s[lane];
+  part = 0.f;
+  for (int c = grp; c < C; c += 8) {
+    const float d = xs[c * 33 + lane] - mean;
+    part = fmaf(d, d, part);
+  }
+  red[grp * 32 + lane] = part;
+  __syncthreads();
+  if (grp == 0) {
+    float v = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) v += red[g * 32 + lane];
+    rstd_s[lane] = rsqrtf(v / (float)C + eps);
+  }
+  __syncthreads();
+  const float rstd = rstd_s[lane];
+  for (int c = grp; c < C; c += 8) {
+    const float v = ((xs[c * 33 + lane] - mean) * rstd * gamma[c] + beta[c]) * om;
+    xs[c * 33 + lane] = v;
+    if (y && tv) y[(size_t)b * C * T + (size_t)c * T + t] = v;
+  }
+  if (po.hi) {
+    __syncthreads();
+    for (int sl = grp; sl < C / 8; sl += 8) {
+      if (!tv) continue;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = xs[(sl * 8 + e) * 33 + lane];
+      store_slab(po, b, C, sl, t, v);
+    }
+    if (po.zero_halo && blockIdx.x == 0) zero_halo_rows(po, b, C, T);
+  }
+}
+
+cudaError_t channel_layernorm_planes(const float* x, float* xw, float* y, const float* gamma, const float* beta, float eps,
+                                     const float* in_mask, const float* out_mask, int B, int C, int T, const PlaneOut& po,
+                                     cudaStream_t s) {
+  if (po.hi && C % 8) return cudaErrorInvalidValue;
+  const size_t smem = ((size_t)C * 33 + 256 + 64) * sizeof(float);
+  if (smem > 48 * 1024) return cudaErrorInvalidConfiguration;
+  dim3 grid(cdiv(T, 32), B);
+  channel_ln_tiled_kernel<<<grid, 256, smem, s>>>(x, xw, y, gamma, beta, eps, in_mask, out_mask, C, T, po);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Self attention for short sequences (T <= 64) with q, k, v of one (batch item, head) resident in shared memory:
+// scores = q.k/sqrt(dk), masked_fill(mask_t*mask_s == 0, -1e4), softmax over s, out = p.v
+// (rel_transformer_encoder.py:128-158, window_size None).  Output to [B,C,T] and/or operand planes.
+__global__ void __launch_bounds__(256) self_attn_small_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                              const float* __restrict__ v,
+                                                              const float* __restrict__ mask, float* __restrict__ out,
+                                                              int C, int T, int heads, long bs, PlaneOut po) {
+  extern __shared__ float sm[];                      // qs[dk][T], ks[dk][T], vs[dk][T], p[T][T+1]
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int dk = C / heads;
+  float* qs = sm;
+  float* ks = qs + (size_t)dk * T;
+  float* vs = ks + (size_t)dk * T;
+  float* ps = vs + (size_t)dk * T;
+  const size_t base = (size_t)b * bs + (size_t)h * dk * T;
+  for (int i = threadIdx.x; i < dk * T; i += blockDim.x) {
+    qs[i] = q[base + i];
+    ks[i] = k[base + i];
+    vs[i] = v[base + i];
+  }
+  __syncthreads();
+  const float* mb = mask + (size_t)b * T;
+  const float inv = rsqrtf((float)dk);
+  for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
+    const int t = i / T, s2 = i - t * T;
+    float acc = 0.f;
+    for (int d = 0; d < dk; ++d) acc = fmaf(qs[d * T + t], ks[d * T + s2], acc);
+    acc *= inv;
+    if (mb[t] * mb[s2] == 0.f) acc = -1e4f;
+    ps[t * (T + 1) + s2] = acc;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int t = warp; t < T; t += nw) {               // softmax of row t by one warp
+    float* pr = ps + t * (T + 1);
+    float mx = -INFINITY;
+    for (int s2 = lane; s2 < T; s2 += 32) mx = fmaxf(mx, pr[s2]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int s2 = lane; s2 < T; s2 += 32) {
+      const float e = expf(pr[s2] - mx);
+      pr[s2] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float rs = 1.f / sum;
+    for (int s2 = lane; s2 < T; s2 += 32) pr[s2] *= rs;
+  }
+  __syncthreads();
+  // out[d, t] = sum_s p[t, s] v[d, s]; results overwrite qs (q is dead) so the plane store can read 8 channels per thread
+  for (int i = threadIdx.x; i < dk * T; i += blockDim.x) {
+    const int d = i / T, t = i - d * T;
+    float acc = 0.f;
+    const float* pr = ps + t * (T + 1);
+    for (int s2 = 0; s2 < T; ++s2) acc = fmaf(pr[s2], vs[d * T + s2], acc);
+    qs[i] = acc;
+    if (out) out[(size_t)b * C * T + (size_t)h * dk * T + i] = acc;
+  }
+  if (po.hi) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < (dk / 8) * T; i += blockDim.x) {
+      const int sl = i / T, t = i - sl * T;
+      float v8[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v8[e] = qs[(sl * 8 + e) * T + t];
+      store_slab(po, b, C, h * (dk / 8) + sl, t, v8);
+    }
+  }
+}
+
+cudaError_t self_attention_planes(const float* q, const float* k, const float* v, const float* mask, float* out, int B,
+                                  int C, int T, int heads, const PlaneOut& po, cudaStream_t s) {
+  const int dk = C / heads;
+  if (T > 64 || (po.hi && dk % 8)) return cudaErrorInvalidValue;
+  const size_t smem = ((size_t)3 * dk * T + (size_t)T * (T + 1)) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(self_attn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (smem > 160 * 1024) return cudaErrorInvalidConfiguration;
+  self_attn_small_kernel<<<B * heads, 256, smem, s>>>(q, k, v, mask, out, C, T, heads, (long)3 * C * T, po);
   return cudaGetLastError();
 }
 
@@ -408,6 +581,28 @@ __global__ void wn_gate_kernel(const float* __restrict__ a, float* __restrict__ 
 cudaError_t wn_gate(const float* a, float* acts, int B, int H, int T, cudaStream_t s) {
   const size_t n = (size_t)B * H * T;
   wn_gate_kernel<<<cdiv(n, 256), 256, 0, s>>>(a, acts, H, T, n);
+  return cudaGetLastError();
+}
+
+// Same gate, written straight into tensor-core operand planes: thread = (8-channel slab, t).
+__global__ void wn_gate_planes_kernel(const float* __restrict__ a, int H, int T, PlaneOut po) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int sl = blockIdx.y, b = blockIdx.z;
+  if (t >= T) return;
+  const float* ab = a + (size_t)b * 2 * H * T;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float ta = ab[(size_t)(sl * 8 + e) * T + t];
+    const float sa = ab[(size_t)(H + sl * 8 + e) * T + t];
+    v[e] = tanhf(ta) * (1.f / (1.f + expf(-sa)));
+  }
+  store_slab(po, b, H, sl, t, v);
+}
+cudaError_t wn_gate_planes(const float* a, int B, int H, int T, const PlaneOut& po, cudaStream_t s) {
+  if (H % 8 || !po.hi) return cudaErrorInvalidValue;
+  dim3 grid(cdiv(T, 128), H / 8, B);
+  wn_gate_planes_kernel<<<grid, 128, 0, s>>>(a, H, T, po);
   return cudaGetLastError();
 }
 
