@@ -81,6 +81,68 @@ class TextToWav:
         torch.cuda.current_stream(self.device).synchronize()
         return wav_out
 
+    def synthesize_stream(self, batches, wav_bufs=None):
+        """Throughput API: iterate over collated HOST batches, yield host waveforms [B, T*hop] in order.
+
+        The host->device copy of batch i+1 runs on a second CUDA stream while batch i is computed, and the waveform of
+        batch i is read back while batch i+1 starts (double-buffered device inputs and pinned output buffers), so a
+        step costs max(copy, compute) instead of their sum.  ``wav_bufs``: optional list of two pinned tensors to
+        write into (they are reused alternately; consume a result before requesting the one after next)."""
+        dev = self.device
+        compute = torch.cuda.current_stream(dev)
+        copy = getattr(self, "_copy_stream", None)
+        if copy is None:
+            copy = self._copy_stream = torch.cuda.Stream(dev)
+        it = iter(batches)
+        slots = [None, None]                 # (device batch, copied event)
+        free = [None, None]                  # event: compute has finished reading slot i
+
+        def upload(i, batch):
+            with torch.cuda.stream(copy):
+                if free[i] is not None:
+                    copy.wait_event(free[i])
+                d = self.to_device(batch)
+                for t in d.values():
+                    t.record_stream(compute)          # allocated on the copy stream, consumed on the compute stream
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            slots[i] = (d, ev)
+
+        try:
+            first = next(it)
+        except StopIteration:
+            return
+        upload(0, first)
+        pending = None                       # (wav_host, done event) of the previous batch
+        k = 0
+        while slots[k % 2] is not None:
+            cur = k % 2
+            d, ev = slots[cur]
+            slots[cur] = None
+            nxt = next(it, None)
+            if nxt is not None:
+                upload(1 - cur, nxt)         # overlaps with the compute below
+            compute.wait_event(ev)
+            _, wav = self.run_device(d)
+            done_reading = torch.cuda.Event()
+            done_reading.record(compute)
+            free[cur] = done_reading
+            if wav_bufs is not None:
+                out = wav_bufs[cur][:wav.shape[0], :wav.shape[1]]
+            else:
+                out = torch.empty(wav.shape, dtype=wav.dtype, pin_memory=True)
+            out.copy_(wav, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(compute)
+            if pending is not None:
+                pending[1].synchronize()
+                yield pending[0]
+            pending = (out, done)
+            k += 1
+        if pending is not None:
+            pending[1].synchronize()
+            yield pending[0]
+
     def close(self):
         self.acoustic.close()
         self.vocoder.close()

@@ -100,3 +100,23 @@ def test_vocoder_plugin_from_checkpoint_dir(exp):
     with torch.no_grad():
         ref = O.hifigan_forward(fold_weight_norm(synth.make_vocoder_state_dict(4321)), VocoderConfig(), mel)
     assert float((torch.from_numpy(wav) - ref[0]).pow(2).mean().sqrt()) < TOL_WAV_RMS
+
+
+def test_pipeline_stream_equals_serial_calls():
+    """TextToWav.synthesize_stream (upload of batch i+1 overlapped with the compute of batch i) returns, batch by batch,
+    exactly what the one-shot synthesize() returns, and both agree with the oracle."""
+    from dict_tts_b200.pipeline import TextToWav
+    pipe = TextToWav(synth.make_acoustic_state_dict(1234), synth.make_vocoder_state_dict(4321))
+    batches = [synth.make_batch(seed=40 + i, B=3, min_chars=3, max_chars=6, max_frames=40, Lk_cap=32) for i in range(4)]
+    serial = [pipe.synthesize(b).clone() for b in batches]
+    streamed = [w.clone() for w in pipe.synthesize_stream(iter(batches))]
+    assert len(streamed) == len(serial)
+    for a, b in zip(serial, streamed):
+        assert torch.equal(a, b)
+    W = fold_weight_norm(synth.make_acoustic_state_dict(1234))
+    Wv = fold_weight_norm(synth.make_vocoder_state_dict(4321))
+    with torch.no_grad():
+        ref = O.acoustic_forward(W, AcousticConfig(), batches[2], batches[2]["mel2word"], batches[2]["z_p"])
+        ref_wav = O.hifigan_forward(Wv, VocoderConfig(), ref["mel_out"])
+    assert float((streamed[2] - ref_wav).pow(2).mean().sqrt()) < TOL_WAV_RMS
+    pipe.close()
