@@ -112,6 +112,26 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+// 32 contiguous bytes (one full L2 sector) from one thread; the address must be 32-byte aligned
+__device__ __forceinline__ void st_global_256(void* p, uint4 a, uint4 b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z),
+               "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+// two 16-byte pieces that are adjacent in memory (lo at p, hi at p + 16 B); either may be disabled
+__device__ __forceinline__ void st_pair(void* p, uint4 a, uint4 b, bool oka, bool okb) {
+  if (oka && okb && (((uintptr_t)p) & 31) == 0) {
+    st_global_256(p, a, b);
+  } else {
+    if (oka) *reinterpret_cast<uint4*>(p) = a;
+    if (okb) *(reinterpret_cast<uint4*>(p) + 1) = b;
+  }
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -363,7 +383,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
     const int et = threadIdx.x - 96;                 // 0..255
     const int quad = warp & 3;                       // TMEM lanes [32*quad, 32*quad+32) are visible to this warp
     const int half = (warp - 3) >> 2;
-    const int nbias = N * p.nblocks;
+    const int nbias = p.il_u ? p.il_cb * p.nblocks : N * p.nblocks;
     for (int i = et; i < nbias; i += kEpiWarps * 32) bias_s[i] = p.bias ? __ldg(p.bias + i) : 0.f;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const bool split = p.o_lo != nullptr;
@@ -411,6 +431,89 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
 
       mbar_wait(acc_full(as), (t_it >> 1) & 1);
       tc_fence_after();
+      if (p.il_u) {
+        // ---- transposed convolution with all `u` polyphase components stacked along N (column = phase * cb + c):
+        // the thread of row q holds out[t = q*u - pad + phase] for every phase, so two adjacent output samples of
+        // one channel group leave as ONE 32-byte store = a whole L2 sector (16-byte strided pieces made the L2 fetch
+        // every sector from HBM before merging: 2x the DRAM traffic and 5x the time of these layers).
+        const int u = p.il_u, cb = p.il_cb, nc8 = cb / 8;
+        const int blk = tc.g;                          // output-channel block (phases == 1 in this mode)
+        for (int idx = half; idx < p.NACC * nc8; idx += 2) {
+          const int m = idx / nc8, c8 = idx - m * nc8;
+          const int q = tc.q0 + m * 128 + quad * 32 + lane;
+          const bool okq = !tc.dummy && q < p.nq;
+          const int co = blk * cb + c8 * 8;            // first of the 8 output channels of this sub-item
+          const float4 b0 = *reinterpret_cast<const float4*>(bias_s + co);
+          const float4 b1 = *reinterpret_cast<const float4*>(bias_s + co + 4);
+          const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256 + m * NM + c8 * 8);
+          for (int ph = 0; ph < u; ph += 2) {
+            uint32_t ra[8], rb[8];
+            __syncwarp();
+            tmem_ld8_nowait(tbase + (uint32_t)(ph * cb), ra);
+            tmem_ld8_nowait(tbase + (uint32_t)((ph + 1) * cb), rb);
+            if (p.stack) {
+              uint32_t la[8], lb[8];
+              tmem_ld8_nowait(tbase + (uint32_t)(N + ph * cb), la);
+              tmem_ld8_nowait(tbase + (uint32_t)(N + (ph + 1) * cb), lb);
+              tmem_ld_wait();
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                ra[k] = __float_as_uint(__uint_as_float(ra[k]) + __uint_as_float(la[k]));
+                rb[k] = __float_as_uint(__uint_as_float(rb[k]) + __uint_as_float(lb[k]));
+              }
+            }
+            tmem_ld_wait();
+            const int t0 = q * u + p.ot_add + ph, t1 = t0 + 1;
+            const bool ok0 = okq && t0 >= 0 && t0 < p.T_out, ok1 = okq && t1 >= 0 && t1 < p.T_out;
+            if (!ok0 && !ok1) continue;
+            float va[8], vb[8];
+            va[0] = __uint_as_float(ra[0]) + b0.x; va[1] = __uint_as_float(ra[1]) + b0.y;
+            va[2] = __uint_as_float(ra[2]) + b0.z; va[3] = __uint_as_float(ra[3]) + b0.w;
+            va[4] = __uint_as_float(ra[4]) + b1.x; va[5] = __uint_as_float(ra[5]) + b1.y;
+            va[6] = __uint_as_float(ra[6]) + b1.z; va[7] = __uint_as_float(ra[7]) + b1.w;
+            vb[0] = __uint_as_float(rb[0]) + b0.x; vb[1] = __uint_as_float(rb[1]) + b0.y;
+            vb[2] = __uint_as_float(rb[2]) + b0.z; vb[3] = __uint_as_float(rb[3]) + b0.w;
+            vb[4] = __uint_as_float(rb[4]) + b1.x; vb[5] = __uint_as_float(rb[5]) + b1.y;
+            vb[6] = __uint_as_float(rb[6]) + b1.z; vb[7] = __uint_as_float(rb[7]) + b1.w;
+            if (o32b) {                                // fp32 stream [C/4][T][4]: samples t0, t1 of a quad are adjacent
+#pragma unroll
+              for (int hq = 0; hq < 2; ++hq) {
+                float4* op = reinterpret_cast<float4*>(o32b) + ((size_t)(co / 4 + hq) * p.T_out + t0);
+                st_pair(op,
+                        make_uint4(__float_as_uint(va[4 * hq]), __float_as_uint(va[4 * hq + 1]),
+                                   __float_as_uint(va[4 * hq + 2]), __float_as_uint(va[4 * hq + 3])),
+                        make_uint4(__float_as_uint(vb[4 * hq]), __float_as_uint(vb[4 * hq + 1]),
+                                   __float_as_uint(vb[4 * hq + 2]), __float_as_uint(vb[4 * hq + 3])),
+                        ok0, ok1);
+              }
+            }
+            if (p.o_hi) {                              // operand planes [C/8][rows][8]: rows t0, t1 of a slab are adjacent
+              const size_t prow = (size_t)tc.b * p.op_bs + ((size_t)(co / 8) * p.op_rows + p.op_pad + t0) * 8;
+              uint32_t ha[4], hb[4], la[4], lb[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float a0 = fmaxf(va[2 * e], va[2 * e] * p.slope), a1 = fmaxf(va[2 * e + 1], va[2 * e + 1] * p.slope);
+                const float c0 = fmaxf(vb[2 * e], vb[2 * e] * p.slope), c1 = fmaxf(vb[2 * e + 1], vb[2 * e + 1] * p.slope);
+                if (split) {
+                  split2(a0, a1, fmt, ha[e], la[e]);
+                  split2(c0, c1, fmt, hb[e], lb[e]);
+                } else {
+                  ha[e] = pack2(a0, a1, fmt);
+                  hb[e] = pack2(c0, c1, fmt);
+                }
+              }
+              st_pair(p.o_hi + prow, make_uint4(ha[0], ha[1], ha[2], ha[3]), make_uint4(hb[0], hb[1], hb[2], hb[3]), ok0, ok1);
+              if (split)
+                st_pair(p.o_lo + prow, make_uint4(la[0], la[1], la[2], la[3]), make_uint4(lb[0], lb[1], lb[2], lb[3]), ok0,
+                        ok1);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty(as));
+        continue;
+      }
       for (int idx = half; idx < nitems; idx += 2) {
         const int m = idx / ncc, cc = idx % ncc;
         int t; bool ok;
@@ -536,8 +639,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void tc_pack_weights_kernel(const float* __restrict__ w, tc16* __restrict__ out, int C_out,
                                        int C_in, int K, int transposed, int stride, int N, int KC, int planes,
-                                       int ktaps, int phases, int fmt, int stack) {
-  const size_t total = (size_t)C_out * C_in * ktaps * phases * planes * (stack ? 2 : 1);
+                                       int ktaps, int phases, int fmt, int stack, int il_cb) {
+  // il_cb > 0 (transposed only): all `stride` polyphase components of a block of il_cb output channels are stacked along
+  // N (row n = phase * il_cb + c); the caller passes phases = 1 and N = stride * il_cb.
+  const size_t total = (size_t)C_out * C_in * ktaps * (il_cb ? stride : phases) * planes * (stack ? 2 : 1);
   const int NMs = stack ? 2 * N : N;                 // rows per K slab of one blob plane
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -552,8 +657,10 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ w, tc16* __rest
   const int nchunks = C_in / KC;
   const int c = r % nchunks; r /= nchunks;
   const int g = (int)r;
-  const int phase = g % phases, nb = g / phases;
-  const int co = nb * N + n, ci = c * KC + sl * 8 + e;
+  int phase = g % phases, nb = g / phases;
+  int co = nb * N + n;
+  const int ci = c * KC + sl * 8 + e;
+  if (il_cb) { phase = n / il_cb; co = nb * il_cb + n % il_cb; }
   float v;
   if (transposed) v = w[((size_t)ci * C_out + co) * K + phase + j * stride];
   else v = w[((size_t)co * C_in + ci) * K + j];
@@ -682,7 +789,8 @@ void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq, int a_planes) {
   p->w = w.w; p->bias = w.bias;
   p->C_in = w.C_in; p->N = w.N; p->KC = w.KC; p->nchunks = w.C_in / w.KC; p->ktaps = w.ktaps;
   p->a_planes = a_planes; p->w_planes = w.planes; p->fmt = w.fmt; p->stack = w.stack; p->NM = w.stack ? 2 * w.N : w.N;
-  p->nblocks = w.C_out / w.N; p->phases = w.phases;
+  p->nblocks = (w.il_u ? w.C_out * w.il_u : w.C_out) / w.N; p->phases = w.phases;
+  p->il_u = w.il_u; p->il_cb = w.il_cb;
   p->nq = nq;
   int nacc = 256 / p->NM;                                    // one accumulator set = 256 TMEM columns (two sets)
   if (nacc > 4) nacc = 4;
@@ -795,14 +903,19 @@ cudaError_t launch_tc_conv(TcConvParams p, int B, cudaStream_t stream) {
 }
 
 cudaError_t tc_pack_weights(const float* w_ref, tc16* out, int C_out, int C_in, int K, int transposed,
-                            int stride, int N, int KC, int planes, int fmt, int stack, cudaStream_t s) {
-  const int phases = transposed ? stride : 1;
+                            int stride, int N, int KC, int planes, int fmt, int stack, cudaStream_t s, int il_cb) {
+  const int phases = (transposed && !il_cb) ? stride : 1;
   const int ktaps = transposed ? K / stride : K;
-  if (C_out % N || C_in % KC || (transposed && K % stride)) return cudaErrorInvalidValue;
+  if (il_cb) {
+    if (!transposed || N != stride * il_cb || C_out % il_cb || (stride & 1) || il_cb % 8) return cudaErrorInvalidValue;
+  } else if (C_out % N) {
+    return cudaErrorInvalidValue;
+  }
+  if (C_in % KC || (transposed && K % stride)) return cudaErrorInvalidValue;
   if (stack && (planes != 1 || 2 * N > 256)) return cudaErrorInvalidValue;
-  const size_t total = (size_t)C_out * C_in * ktaps * phases * planes * (stack ? 2 : 1);
+  const size_t total = (size_t)C_out * C_in * ktaps * (il_cb ? stride : phases) * planes * (stack ? 2 : 1);
   tc_pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w_ref, out, C_out, C_in, K, transposed, stride,
-                                                                        N, KC, planes, ktaps, phases, fmt, stack);
+                                                                        N, KC, planes, ktaps, phases, fmt, stack, il_cb);
   return cudaGetLastError();
 }
 

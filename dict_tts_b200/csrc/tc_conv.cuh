@@ -68,7 +68,12 @@ struct TcConvW {
   int planes = 2;                // separately addressed weight planes (hi, lo): one MMA each
   int stack = 0;                 // 1: hi | lo stacked along N inside ONE plane (N <= 64): one MMA of N' = 2N, planes = 1
   int fmt = 1;                   // TcMode::fmt
-  size_t elems() const { return (size_t)C_out * C_in * ktaps * phases * planes * (stack ? 2 : 1); }
+  // transposed convolution in "interleaved" form: all il_u (= stride) polyphase components of a block of il_cb output
+  // channels stacked along N (N = il_u * il_cb, phases = 1); the epilogue de-interleaves (t = q*stride - pad + phase)
+  int il_u = 0, il_cb = 0;
+  size_t elems() const {
+    return (size_t)(il_u ? il_u : 1) * C_out * C_in * ktaps * phases * planes * (stack ? 2 : 1);
+  }
   // operand mode -> plane arrangement of this layer
   void set_mode(const TcMode& m) {
     fmt = m.fmt;
@@ -87,6 +92,7 @@ struct TcConvParams {
   int C_in, N, KC, nchunks, ktaps, nblocks, phases;
   int a_planes, w_planes, fmt;   // operand planes of A (activations) and B (weights); 16-bit format
   int stack, NM;                 // weights hi | lo stacked along N; N of the main MMAs (2N when stacked, else N)
+  int il_u, il_cb;               // interleaved transposed convolution (see TcConvW); 0 = off
   int tap_off0, tap_step;        // tap j reads input row q + tap_off0 + j*tap_step
   int min_off, RA;               // staged rows per slab: [q0 + min_off, q0 + min_off + RA)
   int nq, MT, NACC;
@@ -113,6 +119,15 @@ struct TcConvParams {
   int csize, nu;                 // cluster size; units (= csize consecutive row tiles) per weight group (launcher)
 };
 
+// output channels per N block of an interleaved transposed convolution: the largest multiple of 8 dividing C_out with
+// stride * cb <= 256 and stride * cb a multiple of 32 (0: unsupported)
+static inline int tc_il_block(int C_out, int stride) {
+  if (stride < 2 || (stride & 1)) return 0;
+  for (int cb = 256 / stride / 8 * 8; cb >= 8; cb -= 8)
+    if (C_out % cb == 0 && (stride * cb) % 32 == 0) return cb;
+  return 0;
+}
+
 // Launch plan / launcher.
 cudaError_t tc_conv_init();
 cudaError_t launch_tc_conv(TcConvParams p, int B, cudaStream_t stream);
@@ -122,7 +137,7 @@ void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq, int a_planes);
 
 // Weight packing: reference layout ([C_out][C_in][K], or [C_in][C_out][K] for ConvTranspose1d) -> blobs.
 cudaError_t tc_pack_weights(const float* w_ref, tc16* out, int C_out, int C_in, int K, int transposed,
-                            int stride, int N, int KC, int planes, int fmt, int stack, cudaStream_t s);
+                            int stride, int N, int KC, int planes, int fmt, int stack, cudaStream_t s, int il_cb = 0);
 // fp32 strided tensor x[b*bs + c*cs + t*ts] -> operand planes of leaky(x, slope) (valid rows only)
 cudaError_t tc_to_planes(const float* x, long bs, long cs, long ts, int B, int C, int T, float slope,
                          tc16* hi, tc16* lo, int rows, int pad, int fmt, cudaStream_t s);

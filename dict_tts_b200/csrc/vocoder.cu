@@ -59,17 +59,25 @@ int tc_pack(dtts_vocoder* h, tc16** cursor, const std::string& name, int C_out, 
   const float* b = h->tab.get(name + ".bias", C_out);
   if (!b) return DTTS_ERR_MISSING_WEIGHT;
   cw->C_in = C_in; cw->C_out = C_out;
-  cw->N = C_out > 256 ? 256 : C_out;
   cw->KC = (C_in % 32 == 0) ? 32 : 16;
   cw->ktaps = transposed ? K / stride : K;
-  cw->phases = transposed ? stride : 1;
+  cw->phases = 1;
+  if (transposed) {                                   // all polyphase components stacked along N (tc_conv.cuh)
+    cw->il_u = stride;
+    cw->il_cb = tc_il_block(C_out, stride);
+    cw->N = cw->il_cb * stride;
+    if (!cw->il_cb) return fail(DTTS_ERR_BAD_SHAPE, "tensor-core vocoder: unsupported transposed convolution " + name);
+  } else {
+    cw->N = C_out > 256 ? 256 : C_out;
+    if (C_out % cw->N) return fail(DTTS_ERR_BAD_SHAPE, "tensor-core vocoder: unsupported channel count in " + name);
+  }
   cw->set_mode(mode);
   cw->bias = b;
-  if (C_out % cw->N || cw->N % 32 || C_in % cw->KC)
+  if (cw->N % 32 || cw->N > 256 || C_in % cw->KC)
     return fail(DTTS_ERR_BAD_SHAPE, "tensor-core vocoder: unsupported channel count in " + name);
   cw->w = *cursor;
   DTTS_CUDA(tc_pack_weights(w, *cursor, C_out, C_in, K, transposed, stride, cw->N, cw->KC, cw->planes, cw->fmt, cw->stack,
-                            s));
+                            s, cw->il_cb));
   *cursor += (cw->elems() + 63) / 64 * 64;
   return DTTS_OK;
 }
@@ -133,7 +141,7 @@ TcGeom tc_geom(const dtts_vocoder* h, int B, int T) {
   for (int i = 0; i < d.n_ups; ++i) {
     ch /= 2;
     len *= d.up_rates[i];
-    const size_t pe = (size_t)B * ch * tc_rows(len), se = (size_t)B * ch * len;
+    const size_t pe = (size_t)B * ch * tc_rows(len) + 64, se = (size_t)B * ch * len + 64;   // + slack for the odd-pad offset
     if (pe > g.plane_elems) g.plane_elems = pe;
     if (se > g.stream_elems) g.stream_elems = se;
   }
@@ -200,15 +208,22 @@ int tc_vocode(dtts_vocoder* h, const float* mel, int B, int T, float* wav, void*
     const int u = d.up_rates[i], k = d.up_kernels[i];
     const int len_o = len * u, co = ch / 2;
     const bool last_stage = i == d.n_ups - 1;
-    shape(PXU, co, len_o);
+    // A transposed convolution writes the samples (t, t+1) of one row with a single 32-byte store; with an odd padding
+    // t is odd, so its outputs start 16 bytes into a sector to keep those stores sector-aligned.
+    const int odd = ((k - u) / 2) & 1;
+    PlaneBuf PXUo = PXU;
+    PXUo.hi = PXU.hi + 8 * odd;
+    PXUo.lo = PXU.lo ? PXU.lo + 8 * odd : nullptr;
+    float* XU = XU32 + 4 * odd;
+    shape(PXUo, co, len_o);
     shape(PT, co, len_o);
     shape(PY, co, len_o);
     {
       const TcConvW& w = h->tc_ups[i];
       TcConvParams p = base(w, PX, len + w.ktaps - 1, 0, -1);
       p.ot_mul = u; p.ot_add = -(k - u) / 2; p.T_out = len_o;
-      p.o32 = XU32; p.o32_bs = (long)co * len_o;
-      out_planes(p, PXU);
+      p.o32 = XU; p.o32_bs = (long)co * len_o;
+      out_planes(p, PXUo);
       L(launch_tc_conv(p, B, s));
     }
     ch = co; len = len_o;
@@ -219,13 +234,13 @@ int tc_vocode(dtts_vocoder* h, const float* mel, int B, int T, float* wav, void*
         const int dil = d.rb_dilations[j][m];
         const TcConvW& c1 = h->tc_rb1[(i * d.n_rb + j) * 3 + m];
         const TcConvW& c2 = h->tc_rb2[(i * d.n_rb + j) * 3 + m];
-        TcConvParams p1 = base(c1, m == 0 ? PXU : PY, len, -(kr * dil - dil) / 2, dil);
+        TcConvParams p1 = base(c1, m == 0 ? PXUo : PY, len, -(kr * dil - dil) / 2, dil);
         p1.T_out = len;
         out_planes(p1, PT);
         L(launch_tc_conv(p1, B, s));
         TcConvParams p2 = base(c2, PT, len, -(kr - 1) / 2, 1);
         p2.T_out = len;
-        p2.res = m == 0 ? XU32 : Y32;
+        p2.res = m == 0 ? XU : Y32;
         p2.o32_bs = (long)ch * len;
         if (m < 2) {
           p2.o32 = Y32;
@@ -427,9 +442,17 @@ extern "C" int dtts_debug_tc_conv1d(const float* x, const float* w, const float*
   cudaError_t e = tc_conv_init();
   if (e != cudaSuccess) return fail(DTTS_ERR_CUDA, std::string("tc_conv_init: ") + cudaGetErrorString(e));
   TcConvW cw;
-  cw.C_in = C_in; cw.C_out = C_out; cw.N = C_out > 256 ? 256 : C_out; cw.KC = (C_in % 32 == 0) ? 32 : 16;
-  cw.ktaps = transposed ? K / stride : K; cw.phases = transposed ? stride : 1; cw.set_mode(mode); cw.bias = bias;
-  if (C_out % cw.N || cw.N % 32 || C_in % cw.KC) return fail(DTTS_ERR_BAD_SHAPE, "tensor-core conv: unsupported channels");
+  cw.C_in = C_in; cw.C_out = C_out; cw.KC = (C_in % 32 == 0) ? 32 : 16;
+  cw.ktaps = transposed ? K / stride : K; cw.phases = 1;
+  if (transposed) {
+    cw.il_u = stride; cw.il_cb = tc_il_block(C_out, stride); cw.N = cw.il_cb * stride;
+    if (!cw.il_cb) return fail(DTTS_ERR_BAD_SHAPE, "tensor-core transposed conv: unsupported stride / channels");
+  } else {
+    cw.N = C_out > 256 ? 256 : C_out;
+    if (C_out % cw.N) return fail(DTTS_ERR_BAD_SHAPE, "tensor-core conv: unsupported channels");
+  }
+  cw.set_mode(mode); cw.bias = bias;
+  if (cw.N % 32 || cw.N > 256 || C_in % cw.KC) return fail(DTTS_ERR_BAD_SHAPE, "tensor-core conv: unsupported channels");
   const int T_out = transposed ? (T_in - 1) * stride - 2 * padding + K : T_in + 2 * padding - dilation * (K - 1);
   if (T_out <= 0) return fail(DTTS_ERR_BAD_SHAPE, "tensor-core conv: empty output");
   Bump bump(scratch, scratch_bytes);
@@ -443,7 +466,8 @@ extern "C" int dtts_debug_tc_conv1d(const float* x, const float* w, const float*
   float* r32 = res ? bump.take<float>((size_t)B * C_out * T_out) : nullptr;
   if (!bump.ok) return fail(DTTS_ERR_WORKSPACE_TOO_SMALL, "dtts_debug_tc_conv1d: scratch too small");
   cw.w = wp;
-  DTTS_CUDA(tc_pack_weights(w, wp, C_out, C_in, K, transposed, stride, cw.N, cw.KC, cw.planes, cw.fmt, cw.stack, s));
+  DTTS_CUDA(tc_pack_weights(w, wp, C_out, C_in, K, transposed, stride, cw.N, cw.KC, cw.planes, cw.fmt, cw.stack, s,
+                            cw.il_cb));
   DTTS_CUDA(tc_zero_halo(a_hi, a_lo, B * (C_in / 8), rows_in, TC_PADF, T_in, s));
   DTTS_CUDA(tc_to_planes(x, (long)C_in * T_in, T_in, 1, B, C_in, T_in, pre_slope, a_hi, a_lo, rows_in, TC_PADF, mode.fmt, s));
   if (res) DTTS_CUDA(tc_nct_to_stream(res, r32, B, C_out, T_out, s));
