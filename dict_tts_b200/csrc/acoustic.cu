@@ -108,7 +108,7 @@ int tc_pack(dtts_acoustic* h, const float* const* w, int parts, const float* bia
   cw->w = dst;
   for (int i = 0; i < parts; ++i)
     DTTS_CUDA(tc_pack_weights(w[i], dst + (size_t)i * part_elems, C_out_part, C_in, K, transposed, 1, cw->N, cw->KC,
-                              cw->planes, cw->fmt, cw->stack, s));
+                              cw->planes, cw->fmt, cw->stack, s, 0, cw->pair));
   h->tc_used += cw->elems();
   return DTTS_OK;
 }

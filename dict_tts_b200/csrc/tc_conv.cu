@@ -84,6 +84,31 @@ __device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint3
       "l"(src), "r"(bytes), "r"(bar), "h"(mask)
       : "memory");
 }
+// cta_group::2 forms: the MMA spans the CTA pair (M = 256: 128 rows from each CTA's A tile, each CTA holds half of B),
+// the commit multicasts to the barriers of both CTAs.
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(bar), "r"(rank));
+  // relaxed: what the arrive publishes was produced by the async proxy (bulk copy completed on the local barrier) or is
+  // a completed tcgen05.ld (wait::ld) -- there is no generic-proxy write to release, and a release at cluster scope costs
+  // a full memory barrier per stage on the relay thread (measured: the pair was slower than two single CTAs with it).
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -185,6 +210,7 @@ struct MmaCtx {
   uint32_t idesc, idesc_n;          // instruction descriptors with N = NM (main) and N = p.N (a_lo x w_hi when stacked)
   int cluster_id, nclusters, n_it, rank, csize;
   uint16_t cmask;
+  int pair;                         // 1: cta_group::2 -- this thread is the leader of a CTA pair
 };
 
 // The MMA-issuing warp.  One elected lane issues; the loop is instantiated per operand mode so that the single issuing
@@ -192,8 +218,14 @@ struct MmaCtx {
 //   WMODE 0: one weight plane; 1: hi and lo planes, one MMA each; 2: hi | lo stacked along N (one MMA, the epilogue adds
 //   the two column halves) -- an M=128,K=16 MMA costs max(64, N/2) cycles (A is read from shared memory at 64 B/clk), so
 //   for C_out <= 64 the second weight plane is free this way.
-template <int KSTEPS, int APL, int WMODE>
+template <int KSTEPS, int APL, int WMODE, bool PAIR>
 __device__ __forceinline__ void mma_warp_loop(const TcConvParams& p, const MmaCtx& x) {
+  // PAIR: tcgen05.mma.cta_group::2 issued by the leader CTA only; the peer's warp 2 relays its "stage full" events to the
+  // leader's pa_full / pw_full barriers ([20..21], [22..27]) and every commit is multicast to both CTAs.
+  auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    if (PAIR) umma_bf16_2cta(d, a, b, idesc, acc);
+    else umma_bf16(d, a, b, idesc, acc);
+  };
   if (elect_one()) {                                 // ONE thread runs the whole loop: waits, MMAs and commits
     const uint32_t hiw = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
     const int ktaps = p.ktaps, nchunks = p.nchunks, tap_step = p.tap_step, w_stages = p.w_stages, a_stages = p.a_stages;
@@ -206,15 +238,17 @@ __device__ __forceinline__ void mma_warp_loop(const TcConvParams& p, const MmaCt
     for (int it = 0; it < x.n_it; ++it, ++t_it) {
       const int nacc = decode_unit(p, it, x.cluster_id, x.nclusters, x.rank).dummy ? 0 : p.NACC;
       const int as = t_it & 1;
-      mbar_wait(bar(18 + as), ((t_it >> 1) & 1) ^ 1);  // acc_empty: the epilogue has drained this accumulator set
+      mbar_wait(bar(18 + as), ((t_it >> 1) & 1) ^ 1);  // acc_empty: the epilogue(s) drained this accumulator set
       tc_fence_after();
       const uint32_t d_base = x.tmem_base + (uint32_t)(as * 256);
       for (int c = 0; c < nchunks; ++c) {
         mbar_wait(bar(sa), pa);                      // a_full
+        if (PAIR) mbar_wait(bar(20 + sa), pa);       // ... and the peer's A tile
         tc_fence_after();
         uint32_t a_tap = x.a_low0 + (uint32_t)sa * x.a_stage16 + tap0;
         for (int j0 = 0; j0 < ktaps; j0 += TG) {     // one weight stage = TG consecutive taps of this K chunk
           mbar_wait(bar(4 + sw), pw);                // w_full
+          if (PAIR) mbar_wait(bar(22 + sw), pw);     // ... and the peer's half of the weights
           tc_fence_after();
           uint32_t b_lo = x.b_low0 + (uint32_t)sw * x.w_blob16;
           const int j1 = min(j0 + TG, ktaps);
@@ -225,19 +259,25 @@ __device__ __forceinline__ void mma_warp_loop(const TcConvParams& p, const MmaCt
 #pragma unroll
               for (int ks = 0; ks < KSTEPS; ++ks) {
                 const uint64_t a = desc64(am + ks * x.a_kstep, hiw), b = desc64(b_lo + ks * x.b_kstep, hiw);
-                umma_bf16(d, a, b, x.idesc, ks == 0 ? first : 1u);
-                if (WMODE == 1) umma_bf16(d, a, desc64(b_lo + ks * x.b_kstep + x.b_plane, hiw), x.idesc, 1u);
+                mma(d, a, b, x.idesc, ks == 0 ? first : 1u);
+                if (WMODE == 1) mma(d, a, desc64(b_lo + ks * x.b_kstep + x.b_plane, hiw), x.idesc, 1u);
                 if (APL == 2)
-                  umma_bf16(d, desc64(am + ks * x.a_kstep + x.a_plane, hiw), b, WMODE == 2 ? x.idesc_n : x.idesc, 1u);
+                  mma(d, desc64(am + ks * x.a_kstep + x.a_plane, hiw), b, WMODE == 2 ? x.idesc_n : x.idesc, 1u);
               }
             }
           }
-          if (x.csize > 1) umma_commit_mc(bar(10 + sw), x.cmask);   // w_empty here and at every peer's producer
+          if (PAIR) umma_commit_2cta(bar(10 + sw));                   // w_empty of both CTAs
+          else if (x.csize > 1) umma_commit_mc(bar(10 + sw), x.cmask);   // w_empty here and at every peer's producer
           else umma_commit(bar(10 + sw));
           if (++sw == w_stages) { sw = 0; pw ^= 1u; }
         }
-        umma_commit(bar(2 + sa));                                     // a_empty
-        if (c == nchunks - 1) umma_commit(bar(16 + as));              // acc_full
+        if (PAIR) {
+          umma_commit_2cta(bar(2 + sa));                              // a_empty of both CTAs
+          if (c == nchunks - 1) umma_commit_2cta(bar(16 + as));       // acc_full of both CTAs
+        } else {
+          umma_commit(bar(2 + sa));                                   // a_empty
+          if (c == nchunks - 1) umma_commit(bar(16 + as));            // acc_full
+        }
         if (++sa == a_stages) { sa = 0; pa ^= 1u; }
       }
     }
@@ -245,13 +285,17 @@ __device__ __forceinline__ void mma_warp_loop(const TcConvParams& p, const MmaCt
   __syncwarp();
 }
 
+// PAIR = true is the cta_group::2 build of the same kernel (launched as clusters of 2 only: a cubin that contains
+// cta_group::2 instructions cannot be launched without a cluster).
+template <bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = p.N, NM = p.NM, KC = p.KC, APL = p.a_planes, WPL = p.w_planes;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  // bars: [0..1] a_full, [2..3] a_empty, [4..9] w_full, [10..15] w_empty, [16..17] acc_full, [18..19] acc_empty
+  // bars: [0..1] a_full, [2..3] a_empty, [4..9] w_full, [10..15] w_empty, [16..17] acc_full, [18..19] acc_empty,
+  //       pair mode, leader only: [20..21] pa_full, [22..27] pw_full (the peer's stages are full)
   const uint32_t bar0 = smem_u32(bars);
   auto a_full = [&](int s) { return bar0 + 8u * s; };
   auto a_empty = [&](int s) { return bar0 + 8u * (2 + s); };
@@ -259,12 +303,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
   auto w_empty = [&](int s) { return bar0 + 8u * (10 + s); };
   auto acc_full = [&](int s) { return bar0 + 8u * (16 + s); };
   auto acc_empty = [&](int s) { return bar0 + 8u * (18 + s); };
-  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + 192);
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + 240);
   float* bias_s = reinterpret_cast<float*>(smem + 256);          // [nblocks * N] <= kMaxBias floats
 
   const uint32_t a_plane_bytes = (uint32_t)(KC / 8) * p.RA * 16u;
   const uint32_t a_stage_bytes = a_plane_bytes * APL;
-  const uint32_t w_plane_bytes = (uint32_t)NM * KC * 2u;      // NM = 2N when hi | lo are stacked along N (then WPL = 1)
+  constexpr int pair = PAIR ? 1 : 0;                            // CTA pair: each CTA stages half of every weight blob
+  const uint32_t w_plane_bytes = (uint32_t)(pair ? NM / 2 : NM) * KC * 2u;   // NM = 2N when hi | lo are stacked (WPL = 1)
   const uint32_t w_tap_bytes = w_plane_bytes * WPL;             // one (K chunk, tap) blob
   const uint32_t w_blob_bytes = w_tap_bytes * (uint32_t)p.TG;   // one weight stage = TG consecutive taps
   const uint32_t a_base = smem_u32(smem + kSmemHeader);
@@ -278,15 +323,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxAStages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < kMaxWStages; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), csize); }
-    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), kEpiWarps); }
+    for (int s = 0; s < kMaxWStages; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), pair ? 1 : csize); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), pair ? 2 * kEpiWarps : kEpiWarps); }
+    for (int s = 0; s < kMaxAStages + kMaxWStages; ++s) mbar_init(bar0 + 8u * (20 + s), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem + 192)),
-                 "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem + 240)),
+                   "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem + 240)),
+                   "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -328,12 +381,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
     uint32_t ph = 1;
     for (int it = 0; it < n_it; ++it) {
       const TileCoord tc = decode_unit(p, it, cluster_id, nclusters, rank);
-      const tc16* wg = p.w + (size_t)tc.g * per_tile * tap_elems;
+      const tc16* wg = p.w + (size_t)tc.g * per_tile * tap_elems * (pair ? 2 : 1);
       for (int c = 0; c < p.nchunks; ++c) {
         for (int j0 = 0; j0 < p.ktaps; j0 += p.TG) {
           const uint32_t ntap = (uint32_t)min(p.TG, p.ktaps - j0);
           mbar_wait(w_empty(s), ph);                                  // released by the MMA warps of ALL peers
-          if (elect_one()) {
+          if (pair) {
+            // CTA pair: the packed weights hold [tap][half][...]; this CTA stages half `rank` of every tap of the group
+            if (elect_one()) {
+              mbar_arrive_expect_tx(w_full(s), ntap * w_tap_bytes);
+              for (uint32_t jj = 0; jj < ntap; ++jj)
+                bulk_g2s(w_base + s * w_blob_bytes + jj * w_tap_bytes,
+                         wg + ((size_t)(c * p.ktaps + j0 + (int)jj) * 2 + rank) * tap_elems, w_tap_bytes, w_full(s));
+            }
+          } else if (elect_one()) {
             mbar_arrive_expect_tx(w_full(s), ntap * w_tap_bytes);     // the whole stage lands here, one slice per peer
             // the ntap tap blobs are contiguous in global and in shared memory: peer r copies bytes [r, r+1) * slice
             const uint32_t slice = ntap * tap_slice;
@@ -355,28 +416,61 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
     const uint32_t ibase = (1u << 4) | (f16b << 7) | (f16b << 10) | ((128u >> 4) << 24);
     x.idesc = ibase | ((uint32_t)(NM >> 3) << 17);
     x.idesc_n = ibase | ((uint32_t)(N >> 3) << 17);
+    if (pair) {                                                         // M = 256 across the CTA pair
+      x.idesc = (x.idesc & ~(0x1Fu << 24)) | ((256u >> 4) << 24);
+      x.idesc_n = (x.idesc_n & ~(0x1Fu << 24)) | ((256u >> 4) << 24);
+    }
     x.bar0 = bar0; x.tmem_base = tmem_base;
     x.a_low0 = ((a_base >> 4) & 0x3FFFu) | ((uint32_t)p.RA << 16);      // LBO = RA * 16 B
-    x.b_low0 = ((w_base >> 4) & 0x3FFFu) | ((uint32_t)NM << 16);        // LBO = NM * 16 B
+    x.b_low0 = ((w_base >> 4) & 0x3FFFu) | ((uint32_t)(pair ? NM / 2 : NM) << 16);   // LBO = rows of B in this CTA * 16 B
     x.a_stage16 = a_stage_bytes >> 4; x.w_blob16 = w_blob_bytes >> 4; x.w_tap16 = w_tap_bytes >> 4;
-    x.a_kstep = 2u * (uint32_t)p.RA; x.b_kstep = 2u * (uint32_t)NM;
+    x.a_kstep = 2u * (uint32_t)p.RA; x.b_kstep = 2u * (uint32_t)(pair ? NM / 2 : NM);
     x.a_plane = a_plane_bytes >> 4; x.b_plane = w_plane_bytes >> 4;
     x.cluster_id = cluster_id; x.nclusters = nclusters; x.n_it = n_it; x.rank = rank; x.csize = csize;
     x.cmask = cmask;
+    x.pair = pair;
     const int wmode = p.stack ? 2 : (WPL == 2 ? 1 : 0);
-    switch ((KC == 32 ? 6 : 0) + (APL == 2 ? 3 : 0) + wmode) {
-      case 0: mma_warp_loop<1, 1, 0>(p, x); break;
-      case 1: mma_warp_loop<1, 1, 1>(p, x); break;
-      case 2: mma_warp_loop<1, 1, 2>(p, x); break;
-      case 3: mma_warp_loop<1, 2, 0>(p, x); break;
-      case 4: mma_warp_loop<1, 2, 1>(p, x); break;
-      case 5: mma_warp_loop<1, 2, 2>(p, x); break;
-      case 6: mma_warp_loop<2, 1, 0>(p, x); break;
-      case 7: mma_warp_loop<2, 1, 1>(p, x); break;
-      case 8: mma_warp_loop<2, 1, 2>(p, x); break;
-      case 9: mma_warp_loop<2, 2, 0>(p, x); break;
-      case 10: mma_warp_loop<2, 2, 1>(p, x); break;
-      default: mma_warp_loop<2, 2, 2>(p, x); break;
+    if (PAIR && rank != 0) {
+      // ---- peer of a CTA pair: no MMAs are issued here; forward "my stage is full" to the leader, in pipeline order
+      if (elect_one()) {
+        int sa = 0, sw = 0;
+        uint32_t pa = 0, pw = 0;
+        for (int it = 0; it < n_it; ++it) {
+          for (int c = 0; c < p.nchunks; ++c) {
+            mbar_wait(a_full(sa), pa);
+            mbar_arrive_remote(bar0 + 8u * (20 + sa), 0);
+            for (int j0 = 0; j0 < p.ktaps; j0 += p.TG) {
+              mbar_wait(w_full(sw), pw);
+              mbar_arrive_remote(bar0 + 8u * (22 + sw), 0);
+              if (++sw == p.w_stages) { sw = 0; pw ^= 1u; }
+            }
+            if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
+          }
+        }
+      }
+      __syncwarp();
+    } else if constexpr (PAIR) {
+      switch ((KC == 32 ? 2 : 0) + (WPL == 2 ? 1 : 0)) {      // pair mode: single-plane activations, unstacked weights
+        case 0: mma_warp_loop<1, 1, 0, true>(p, x); break;
+        case 1: mma_warp_loop<1, 1, 1, true>(p, x); break;
+        case 2: mma_warp_loop<2, 1, 0, true>(p, x); break;
+        default: mma_warp_loop<2, 1, 1, true>(p, x); break;
+      }
+    } else {
+      switch ((KC == 32 ? 6 : 0) + (APL == 2 ? 3 : 0) + wmode) {
+        case 0: mma_warp_loop<1, 1, 0, false>(p, x); break;
+        case 1: mma_warp_loop<1, 1, 1, false>(p, x); break;
+        case 2: mma_warp_loop<1, 1, 2, false>(p, x); break;
+        case 3: mma_warp_loop<1, 2, 0, false>(p, x); break;
+        case 4: mma_warp_loop<1, 2, 1, false>(p, x); break;
+        case 5: mma_warp_loop<1, 2, 2, false>(p, x); break;
+        case 6: mma_warp_loop<2, 1, 0, false>(p, x); break;
+        case 7: mma_warp_loop<2, 1, 1, false>(p, x); break;
+        case 8: mma_warp_loop<2, 1, 2, false>(p, x); break;
+        case 9: mma_warp_loop<2, 2, 0, false>(p, x); break;
+        case 10: mma_warp_loop<2, 2, 1, false>(p, x); break;
+        default: mma_warp_loop<2, 2, 2, false>(p, x); break;
+      }
     }
   } else {
     // ------------------------------------------------ epilogue (warps 3..10; two warps per TMEM lane quadrant)
@@ -511,7 +605,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty(as));
+        if (lane == 0) {
+          if (pair && rank != 0) mbar_arrive_remote(acc_empty(as), 0);
+          else mbar_arrive(acc_empty(as));
+        }
         continue;
       }
       for (int idx = half; idx < nitems; idx += 2) {
@@ -622,7 +719,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
       // this warp no longer reads accumulator set `as`
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty(as));
+      if (lane == 0) {
+        if (pair && rank != 0) mbar_arrive_remote(acc_empty(as), 0);   // the leader issues the MMAs of both CTAs
+        else mbar_arrive(acc_empty(as));
+      }
     }
   }
   tc_fence_before();
@@ -630,7 +730,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
   if (csize > 1) cluster_sync_all();           // no peer may still multicast into / arrive on this CTA's shared memory
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -639,7 +742,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void tc_pack_weights_kernel(const float* __restrict__ w, tc16* __restrict__ out, int C_out,
                                        int C_in, int K, int transposed, int stride, int N, int KC, int planes,
-                                       int ktaps, int phases, int fmt, int stack, int il_cb) {
+                                       int ktaps, int phases, int fmt, int stack, int il_cb, int pair) {
   // il_cb > 0 (transposed only): all `stride` polyphase components of a block of il_cb output channels are stacked along
   // N (row n = phase * il_cb + c); the caller passes phases = 1 and N = stride * il_cb.
   const size_t total = (size_t)C_out * C_in * ktaps * (il_cb ? stride : phases) * planes * (stack ? 2 : 1);
@@ -649,9 +752,17 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ w, tc16* __rest
   // destination index [g][chunk][tap][plane][slab][n][e]
   size_t r = i;
   const int e = r % 8; r /= 8;
-  int n = r % NMs; r /= NMs;
-  const int sl = r % (KC / 8); r /= (KC / 8);
-  int pl = r % planes; r /= planes;
+  int n, sl, pl;
+  if (pair) {                                        // [..][tap][half][plane][slab][N/2][8]: each CTA of a pair copies its half
+    n = r % (NMs / 2); r /= (NMs / 2);
+    sl = r % (KC / 8); r /= (KC / 8);
+    pl = r % planes; r /= planes;
+    n += (int)(r % 2) * (NMs / 2); r /= 2;
+  } else {
+    n = r % NMs; r /= NMs;
+    sl = r % (KC / 8); r /= (KC / 8);
+    pl = r % planes; r /= planes;
+  }
   if (stack) { pl = n >= N; n -= pl * N; }           // stacked: rows [0,N) = hi, [N,2N) = lo of the same channel
   const int j = r % ktaps; r /= ktaps;
   const int nchunks = C_in / KC;
@@ -777,7 +888,9 @@ __global__ void __launch_bounds__(256) tc_conv_post_kernel(const float* __restri
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 cudaError_t tc_conv_init() {
-  return cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+  cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(tc_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
 }
 
 static int env_int(const char* name, int dflt) {
@@ -791,6 +904,7 @@ void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq, int a_planes) {
   p->a_planes = a_planes; p->w_planes = w.planes; p->fmt = w.fmt; p->stack = w.stack; p->NM = w.stack ? 2 * w.N : w.N;
   p->nblocks = (w.il_u ? w.C_out * w.il_u : w.C_out) / w.N; p->phases = w.phases;
   p->il_u = w.il_u; p->il_cb = w.il_cb;
+  p->pair = w.pair;
   p->nq = nq;
   int nacc = 256 / p->NM;                                    // one accumulator set = 256 TMEM columns (two sets)
   if (nacc > 4) nacc = 4;
@@ -806,7 +920,7 @@ void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq, int a_planes) {
   p->RA = p->MT + (max_off - p->min_off);
   p->a_stages = kMaxAStages;
   const size_t a_stage = (size_t)(p->KC / 8) * p->RA * 16 * p->a_planes;
-  const size_t w_tap = (size_t)p->NM * p->KC * 2 * p->w_planes;
+  const size_t w_tap = (size_t)(p->pair ? p->NM / 2 : p->NM) * p->KC * 2 * p->w_planes;   // per CTA
   // taps per weight stage: ~32 KB stages, so that the per-stage barrier round trip is amortised over >= 8 MMAs
   int tg = env_int("DTTS_TC_TG", 0);
   if (tg <= 0) tg = (int)((32 * 1024) / w_tap);
@@ -829,20 +943,28 @@ void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq, int a_planes) {
 
 static size_t tc_smem_bytes(const TcConvParams& p) {
   const size_t a_stage = (size_t)(p.KC / 8) * p.RA * 16 * p.a_planes;
-  const size_t w_blob = (size_t)p.NM * p.KC * 2 * p.w_planes * p.TG;
+  const size_t w_blob = (size_t)(p.pair ? p.NM / 2 : p.NM) * p.KC * 2 * p.w_planes * p.TG;
   size_t bytes = kSmemHeader + p.a_stages * a_stage + p.w_stages * w_blob;
   // the CTA owns all 512 TMEM columns: it must be alone on its SM, or a co-resident CTA would block in tcgen05.alloc
   if (bytes < 116 * 1024) bytes = 116 * 1024;
   return bytes;
 }
 
+int tc_pair_enabled() {
+  static int v = -1;
+  if (v < 0) v = env_int("DTTS_TC_PAIR", 1) != 0;
+  return v;
+}
+
 static int g_num_sms = 0;
-static int g_max_clusters[9] = {0};     // [csize] -> co-resident clusters of tc_conv_kernel (0 = not queried yet)
+static int g_max_clusters[9] = {0};     // [csize] -> co-resident clusters of tc_conv_kernel<false> (0 = not queried yet)
+static int g_max_pairs = 0;             // co-resident CTA pairs of tc_conv_kernel<true>
 
 // Cluster size (CTAs sharing every weight stage through multicast).  Measured on B200 at the cfg-2 vocoder shapes
 // (profiles/r01_summary.md): 1 -> 35.2 ms, 2 -> 36.0 ms, 4 -> 36.0 ms per pass; the weight stream (<= 3.8 TB/s out of
 // L2) is not what bounds these layers, so the default is 1 and DTTS_TC_CLUSTER=2|4 turns the multicast path on.
 static int pick_cluster(const TcConvParams& p, long row_tiles) {
+  if (p.pair) return 2;
   int c = env_int("DTTS_TC_CLUSTER", 0);
   if (c <= 0) c = 1;
   while (c > 1 && (row_tiles < c || (p.NM * p.KC * 2 * p.w_planes) % (16 * c))) c >>= 1;
@@ -853,6 +975,7 @@ cudaError_t launch_tc_conv(TcConvParams p, int B, cudaStream_t stream) {
   if (B <= 0 || p.nq <= 0) return cudaSuccess;
   if (p.a_planes < 1 || p.a_planes > 2 || p.w_planes < 1 || p.w_planes > 2 || (p.a_planes == 2 && !p.a_lo))
     return cudaErrorInvalidValue;
+  if (p.pair && (p.stack || p.a_planes != 1 || p.NM % 32 || p.NM < 64)) return cudaErrorInvalidConfiguration;
   if (p.TG < 1 || p.w_stages < 1 || p.N % 32 != 0 || p.N > 256 || p.KC % 16 != 0 || p.C_in % p.KC != 0 ||
       p.N * p.nblocks > kMaxBias || p.NACC * p.NM > 256 || (p.stack && (p.w_planes != 1 || p.NM != 2 * p.N)) ||
       (!p.stack && p.NM != p.N))
@@ -879,6 +1002,26 @@ cudaError_t launch_tc_conv(TcConvParams p, int B, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int max_clusters = 0;
+  if (p.pair) {
+    if (g_max_pairs == 0) {
+      attr[0].val.clusterDim = {2, 1, 1};
+      cfg.gridDim = dim3((unsigned)(g_num_sms / 2 * 2));
+      int n = 0;
+      cfg.dynamicSmemBytes = kSmemLimit;
+      cudaError_t e = cudaOccupancyMaxActiveClusters(&n, tc_conv_kernel<true>, &cfg);
+      cfg.dynamicSmemBytes = smem;
+      if (e != cudaSuccess) return e;
+      g_max_pairs = n > 0 ? n : -1;
+    }
+    if (g_max_pairs <= 0) return cudaErrorInvalidConfiguration;
+    p.csize = 2;
+    p.nu = (int)((row_tiles + 1) / 2);
+    const long units = (long)p.nu * p.nblocks;
+    const int npairs = (int)(units < g_max_pairs ? units : g_max_pairs);
+    attr[0].val.clusterDim = {2, 1, 1};
+    cfg.gridDim = dim3((unsigned)(npairs * 2));
+    return cudaLaunchKernelEx(&cfg, tc_conv_kernel<true>, p);
+  }
   for (; csize >= 1; csize >>= 1) {
     if (csize == 1) { max_clusters = g_num_sms; break; }
     if (g_max_clusters[csize] == 0) {
@@ -886,7 +1029,7 @@ cudaError_t launch_tc_conv(TcConvParams p, int B, cudaStream_t stream) {
       cfg.gridDim = dim3((unsigned)(g_num_sms / csize * csize));
       int n = 0;
       cfg.dynamicSmemBytes = kSmemLimit;
-      cudaError_t e = cudaOccupancyMaxActiveClusters(&n, tc_conv_kernel, &cfg);
+      cudaError_t e = cudaOccupancyMaxActiveClusters(&n, tc_conv_kernel<false>, &cfg);
       cfg.dynamicSmemBytes = smem;
       g_max_clusters[csize] = (e == cudaSuccess && n > 0) ? n : -1;
       if (e != cudaSuccess) (void)cudaGetLastError();
@@ -899,11 +1042,12 @@ cudaError_t launch_tc_conv(TcConvParams p, int B, cudaStream_t stream) {
   const int nclusters = (int)(total_units < max_clusters ? total_units : max_clusters);   // persistent
   attr[0].val.clusterDim = {(unsigned)csize, 1, 1};
   cfg.gridDim = dim3((unsigned)(nclusters * csize));
-  return cudaLaunchKernelEx(&cfg, tc_conv_kernel, p);
+  return cudaLaunchKernelEx(&cfg, tc_conv_kernel<false>, p);
 }
 
 cudaError_t tc_pack_weights(const float* w_ref, tc16* out, int C_out, int C_in, int K, int transposed,
-                            int stride, int N, int KC, int planes, int fmt, int stack, cudaStream_t s, int il_cb) {
+                            int stride, int N, int KC, int planes, int fmt, int stack, cudaStream_t s, int il_cb,
+                            int pair) {
   const int phases = (transposed && !il_cb) ? stride : 1;
   const int ktaps = transposed ? K / stride : K;
   if (il_cb) {
@@ -915,7 +1059,7 @@ cudaError_t tc_pack_weights(const float* w_ref, tc16* out, int C_out, int C_in, 
   if (stack && (planes != 1 || 2 * N > 256)) return cudaErrorInvalidValue;
   const size_t total = (size_t)C_out * C_in * ktaps * (il_cb ? stride : phases) * planes * (stack ? 2 : 1);
   tc_pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w_ref, out, C_out, C_in, K, transposed, stride,
-                                                                        N, KC, planes, ktaps, phases, fmt, stack, il_cb);
+                                                                        N, KC, planes, ktaps, phases, fmt, stack, il_cb, pair);
   return cudaGetLastError();
 }
 

@@ -56,6 +56,9 @@ static inline int tc_rows(int T) {
   return TC_PADF + (T + 8 + align - 1) / align * align + TC_PADB;
 }
 
+// DTTS_TC_PAIR=0 turns the CTA-pair path off (default on)
+int tc_pair_enabled();
+
 // Packed weights of one convolution: blobs [group][chunk][tap] of {hi plane, lo plane}, each plane [KC/8][N][8] bf16
 // (the shared-memory image of the B operand).  group = nblock * phases + phase.
 struct TcConvW {
@@ -71,6 +74,10 @@ struct TcConvW {
   // transposed convolution in "interleaved" form: all il_u (= stride) polyphase components of a block of il_cb output
   // channels stacked along N (N = il_u * il_cb, phases = 1); the epilogue de-interleaves (t = q*stride - pad + phase)
   int il_u = 0, il_cb = 0;
+  // CTA-pair execution (tcgen05 cta_group::2): the two CTAs of a cluster compute adjacent 128-row tiles with ONE M = 256
+  // MMA; each stages its own A tile and only half of every weight blob, which halves the shared-memory traffic of the
+  // B operand and of the weight stream per SM (the limiter of the C >= 128 layers).  Weights are packed [tap][half].
+  int pair = 0;
   size_t elems() const {
     return (size_t)(il_u ? il_u : 1) * C_out * C_in * ktaps * phases * planes * (stack ? 2 : 1);
   }
@@ -79,6 +86,7 @@ struct TcConvW {
     fmt = m.fmt;
     stack = (m.w_planes == 2 && N <= 64) ? 1 : 0;
     planes = stack ? 1 : m.w_planes;
+    pair = (!stack && m.a_planes == 1 && N >= 128 && tc_pair_enabled()) ? 1 : 0;
   }
 };
 
@@ -93,6 +101,7 @@ struct TcConvParams {
   int a_planes, w_planes, fmt;   // operand planes of A (activations) and B (weights); 16-bit format
   int stack, NM;                 // weights hi | lo stacked along N; N of the main MMAs (2N when stacked, else N)
   int il_u, il_cb;               // interleaved transposed convolution (see TcConvW); 0 = off
+  int pair;                      // CTA-pair (cta_group::2) execution
   int tap_off0, tap_step;        // tap j reads input row q + tap_off0 + j*tap_step
   int min_off, RA;               // staged rows per slab: [q0 + min_off, q0 + min_off + RA)
   int nq, MT, NACC;
@@ -137,7 +146,8 @@ void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq, int a_planes);
 
 // Weight packing: reference layout ([C_out][C_in][K], or [C_in][C_out][K] for ConvTranspose1d) -> blobs.
 cudaError_t tc_pack_weights(const float* w_ref, tc16* out, int C_out, int C_in, int K, int transposed,
-                            int stride, int N, int KC, int planes, int fmt, int stack, cudaStream_t s, int il_cb = 0);
+                            int stride, int N, int KC, int planes, int fmt, int stack, cudaStream_t s, int il_cb = 0,
+                            int pair = 0);
 // fp32 strided tensor x[b*bs + c*cs + t*ts] -> operand planes of leaky(x, slope) (valid rows only)
 cudaError_t tc_to_planes(const float* x, long bs, long cs, long ts, int B, int C, int T, float slope,
                          tc16* hi, tc16* lo, int rows, int pad, int fmt, cudaStream_t s);

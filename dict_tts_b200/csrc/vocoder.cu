@@ -77,7 +77,7 @@ int tc_pack(dtts_vocoder* h, tc16** cursor, const std::string& name, int C_out, 
     return fail(DTTS_ERR_BAD_SHAPE, "tensor-core vocoder: unsupported channel count in " + name);
   cw->w = *cursor;
   DTTS_CUDA(tc_pack_weights(w, *cursor, C_out, C_in, K, transposed, stride, cw->N, cw->KC, cw->planes, cw->fmt, cw->stack,
-                            s, cw->il_cb));
+                            s, cw->il_cb, cw->pair));
   *cursor += (cw->elems() + 63) / 64 * 64;
   return DTTS_OK;
 }
@@ -467,7 +467,7 @@ extern "C" int dtts_debug_tc_conv1d(const float* x, const float* w, const float*
   if (!bump.ok) return fail(DTTS_ERR_WORKSPACE_TOO_SMALL, "dtts_debug_tc_conv1d: scratch too small");
   cw.w = wp;
   DTTS_CUDA(tc_pack_weights(w, wp, C_out, C_in, K, transposed, stride, cw.N, cw.KC, cw.planes, cw.fmt, cw.stack, s,
-                            cw.il_cb));
+                            cw.il_cb, cw.pair));
   DTTS_CUDA(tc_zero_halo(a_hi, a_lo, B * (C_in / 8), rows_in, TC_PADF, T_in, s));
   DTTS_CUDA(tc_to_planes(x, (long)C_in * T_in, T_in, 1, B, C_in, T_in, pre_slope, a_hi, a_lo, rows_in, TC_PADF, mode.fmt, s));
   if (res) DTTS_CUDA(tc_nct_to_stream(res, r32, B, C_out, T_out, s));
