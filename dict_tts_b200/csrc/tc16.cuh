@@ -23,9 +23,9 @@ __device__ __forceinline__ uint32_t pack2(float a0, float a1, int fmt) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
     return *reinterpret_cast<const uint32_t*>(&h);
   }
-  const __half2 lim = __floats2half2_rn(65504.f, 65504.f);
-  const __half2 h = __hmin2(__hmax2(__floats2half2_rn(a0, a1), __hneg2(lim)), lim);
-  return *reinterpret_cast<const uint32_t*>(&h);
+  uint32_t r;                                       // one F2FP.SATFINITE.F16.F32.PACK_AB: a0 -> low half, a1 -> high half
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(a1), "f"(a0));
+  return r;
 }
 // two consecutive channels -> packed hi word and (residual) lo word
 __device__ __forceinline__ void split2(float a0, float a1, int fmt, uint32_t& hw, uint32_t& lw) {

@@ -24,9 +24,15 @@ namespace {
 
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 96 + kEpiWarps * 32;
-constexpr int kMaxAStages = 2, kMaxWStages = 6;
+constexpr int kMaxAStages = 4, kMaxWStages = 6;
+// mbarrier slots (8 B each) at the start of shared memory
+constexpr int kBarAFull = 0, kBarAEmpty = kBarAFull + kMaxAStages, kBarWFull = kBarAEmpty + kMaxAStages,
+              kBarWEmpty = kBarWFull + kMaxWStages, kBarAccFull = kBarWEmpty + kMaxWStages, kBarAccEmpty = kBarAccFull + 2,
+              kBarPAFull = kBarAccEmpty + 2, kBarPWFull = kBarPAFull + kMaxAStages, kNumBars = kBarPWFull + kMaxWStages;
+constexpr int kTmemPtrOff = kNumBars * 8;                 // uint32: TMEM base address
+constexpr int kBiasOff = (kTmemPtrOff + 4 + 63) / 64 * 64;
 constexpr int kMaxBias = 2048;               // output channels of one launch (bias staged in shared memory)
-constexpr int kSmemHeader = 256 + kMaxBias * 4;   // barriers + tmem ptr (256 B) then bias
+constexpr int kSmemHeader = kBiasOff + kMaxBias * 4;   // barriers + tmem ptr, then bias
 constexpr int kSmemLimit = 227 * 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -188,14 +194,18 @@ __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
 struct TileCoord { int q0, g, b; bool dummy; };
 __device__ __forceinline__ TileCoord decode_unit(const TcConvParams& p, int it, int cluster_id, int nclusters, int rank) {
   TileCoord c;
-  const int unit = cluster_id + (it / p.phases) * nclusters;
-  c.g = (unit / p.nu) * p.phases + it % p.phases;
-  int rt = (unit % p.nu) * p.csize + rank;
-  const int nrt = p.ntiles * p.B;
+  uint32_t step = (uint32_t)it, ph = 0;
+  if (p.phases != 1) { step = (uint32_t)it / (uint32_t)p.phases; ph = (uint32_t)it - step * (uint32_t)p.phases; }
+  const uint32_t unit = (uint32_t)cluster_id + step * (uint32_t)nclusters;
+  const uint32_t blk = unit / (uint32_t)p.nu, j = unit - blk * (uint32_t)p.nu;
+  c.g = (int)(blk * (uint32_t)p.phases + ph);
+  uint32_t rt = j * (uint32_t)p.csize + (uint32_t)rank;
+  const uint32_t nrt = (uint32_t)(p.ntiles * p.B);
   c.dummy = rt >= nrt;
   if (c.dummy) rt = nrt - 1;
-  c.b = rt / p.ntiles;
-  c.q0 = (rt % p.ntiles) * p.MT;
+  const uint32_t b = rt / (uint32_t)p.ntiles;
+  c.b = (int)b;
+  c.q0 = (int)(rt - b * (uint32_t)p.ntiles) * p.MT;
   return c;
 }
 
@@ -231,24 +241,24 @@ __device__ __forceinline__ void mma_warp_loop(const TcConvParams& p, const MmaCt
     const int ktaps = p.ktaps, nchunks = p.nchunks, tap_step = p.tap_step, w_stages = p.w_stages, a_stages = p.a_stages;
     const int NM = p.NM, TG = p.TG;
     const uint32_t tap0 = (uint32_t)(p.tap_off0 - p.min_off);
-    auto bar = [&](int i) { return x.bar0 + 8u * (uint32_t)i; };  // [0..1] a_full [2..3] a_empty [4..9] w_full [10..15] w_empty
+    auto bar = [&](int i) { return x.bar0 + 8u * (uint32_t)i; };  // index = kBar* + stage
     int sa = 0, sw = 0;
     uint32_t pa = 0, pw = 0;                         // stage cursors + phase parities (no div/mod in this loop)
     int t_it = 0;
     for (int it = 0; it < x.n_it; ++it, ++t_it) {
       const int nacc = decode_unit(p, it, x.cluster_id, x.nclusters, x.rank).dummy ? 0 : p.NACC;
       const int as = t_it & 1;
-      mbar_wait(bar(18 + as), ((t_it >> 1) & 1) ^ 1);  // acc_empty: the epilogue(s) drained this accumulator set
+      mbar_wait(bar(kBarAccEmpty + as), ((t_it >> 1) & 1) ^ 1);  // acc_empty: the epilogue(s) drained this accumulator set
       tc_fence_after();
       const uint32_t d_base = x.tmem_base + (uint32_t)(as * 256);
       for (int c = 0; c < nchunks; ++c) {
-        mbar_wait(bar(sa), pa);                      // a_full
-        if (PAIR) mbar_wait(bar(20 + sa), pa);       // ... and the peer's A tile
+        mbar_wait(bar(kBarAFull + sa), pa);          // a_full
+        if (PAIR) mbar_wait(bar(kBarPAFull + sa), pa);       // ... and the peer's A tile
         tc_fence_after();
         uint32_t a_tap = x.a_low0 + (uint32_t)sa * x.a_stage16 + tap0;
         for (int j0 = 0; j0 < ktaps; j0 += TG) {     // one weight stage = TG consecutive taps of this K chunk
-          mbar_wait(bar(4 + sw), pw);                // w_full
-          if (PAIR) mbar_wait(bar(22 + sw), pw);     // ... and the peer's half of the weights
+          mbar_wait(bar(kBarWFull + sw), pw);                // w_full
+          if (PAIR) mbar_wait(bar(kBarPWFull + sw), pw);     // ... and the peer's half of the weights
           tc_fence_after();
           uint32_t b_lo = x.b_low0 + (uint32_t)sw * x.w_blob16;
           const int j1 = min(j0 + TG, ktaps);
@@ -266,17 +276,17 @@ __device__ __forceinline__ void mma_warp_loop(const TcConvParams& p, const MmaCt
               }
             }
           }
-          if (PAIR) umma_commit_2cta(bar(10 + sw));                   // w_empty of both CTAs
-          else if (x.csize > 1) umma_commit_mc(bar(10 + sw), x.cmask);   // w_empty here and at every peer's producer
-          else umma_commit(bar(10 + sw));
+          if (PAIR) umma_commit_2cta(bar(kBarWEmpty + sw));                   // w_empty of both CTAs
+          else if (x.csize > 1) umma_commit_mc(bar(kBarWEmpty + sw), x.cmask);   // w_empty here and at every peer's producer
+          else umma_commit(bar(kBarWEmpty + sw));
           if (++sw == w_stages) { sw = 0; pw ^= 1u; }
         }
         if (PAIR) {
-          umma_commit_2cta(bar(2 + sa));                              // a_empty of both CTAs
-          if (c == nchunks - 1) umma_commit_2cta(bar(16 + as));       // acc_full of both CTAs
+          umma_commit_2cta(bar(kBarAEmpty + sa));                              // a_empty of both CTAs
+          if (c == nchunks - 1) umma_commit_2cta(bar(kBarAccFull + as));       // acc_full of both CTAs
         } else {
-          umma_commit(bar(2 + sa));                                   // a_empty
-          if (c == nchunks - 1) umma_commit(bar(16 + as));            // acc_full
+          umma_commit(bar(kBarAEmpty + sa));                                   // a_empty
+          if (c == nchunks - 1) umma_commit(bar(kBarAccFull + as));            // acc_full
         }
         if (++sa == a_stages) { sa = 0; pa ^= 1u; }
       }
@@ -294,17 +304,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
   const int N = p.N, NM = p.NM, KC = p.KC, APL = p.a_planes, WPL = p.w_planes;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  // bars: [0..1] a_full, [2..3] a_empty, [4..9] w_full, [10..15] w_empty, [16..17] acc_full, [18..19] acc_empty,
-  //       pair mode, leader only: [20..21] pa_full, [22..27] pw_full (the peer's stages are full)
+  // mbarriers: see kBar* (a_full/a_empty per activation stage, w_full/w_empty per weight stage, acc_full/acc_empty per
+  // accumulator set; pair mode, leader only: pa_full / pw_full = "the peer's stage is full")
   const uint32_t bar0 = smem_u32(bars);
-  auto a_full = [&](int s) { return bar0 + 8u * s; };
-  auto a_empty = [&](int s) { return bar0 + 8u * (2 + s); };
-  auto w_full = [&](int s) { return bar0 + 8u * (4 + s); };
-  auto w_empty = [&](int s) { return bar0 + 8u * (10 + s); };
-  auto acc_full = [&](int s) { return bar0 + 8u * (16 + s); };
-  auto acc_empty = [&](int s) { return bar0 + 8u * (18 + s); };
-  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + 240);
-  float* bias_s = reinterpret_cast<float*>(smem + 256);          // [nblocks * N] <= kMaxBias floats
+  auto a_full = [&](int s) { return bar0 + 8u * (kBarAFull + s); };
+  auto a_empty = [&](int s) { return bar0 + 8u * (kBarAEmpty + s); };
+  auto w_full = [&](int s) { return bar0 + 8u * (kBarWFull + s); };
+  auto w_empty = [&](int s) { return bar0 + 8u * (kBarWEmpty + s); };
+  auto acc_full = [&](int s) { return bar0 + 8u * (kBarAccFull + s); };
+  auto acc_empty = [&](int s) { return bar0 + 8u * (kBarAccEmpty + s); };
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + kTmemPtrOff);
+  float* bias_s = reinterpret_cast<float*>(smem + kBiasOff);          // [nblocks * N] <= kMaxBias floats
 
   const uint32_t a_plane_bytes = (uint32_t)(KC / 8) * p.RA * 16u;
   const uint32_t a_stage_bytes = a_plane_bytes * APL;
@@ -325,17 +335,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
     for (int s = 0; s < kMaxAStages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < kMaxWStages; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), pair ? 1 : csize); }
     for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), pair ? 2 * kEpiWarps : kEpiWarps); }
-    for (int s = 0; s < kMaxAStages + kMaxWStages; ++s) mbar_init(bar0 + 8u * (20 + s), 1);
+    for (int s = 0; s < kMaxAStages + kMaxWStages; ++s) mbar_init(bar0 + 8u * (kBarPAFull + s), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
     if constexpr (PAIR) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem + 240)),
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem + kTmemPtrOff)),
                    "r"(512u)
                    : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem + 240)),
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem + kTmemPtrOff)),
                    "r"(512u)
                    : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -438,10 +448,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
         for (int it = 0; it < n_it; ++it) {
           for (int c = 0; c < p.nchunks; ++c) {
             mbar_wait(a_full(sa), pa);
-            mbar_arrive_remote(bar0 + 8u * (20 + sa), 0);
+            mbar_arrive_remote(bar0 + 8u * (kBarPAFull + sa), 0);
             for (int j0 = 0; j0 < p.ktaps; j0 += p.TG) {
               mbar_wait(w_full(sw), pw);
-              mbar_arrive_remote(bar0 + 8u * (22 + sw), 0);
+              mbar_arrive_remote(bar0 + 8u * (kBarPWFull + sw), 0);
               if (++sw == p.w_stages) { sw = 0; pw ^= 1u; }
             }
             if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
@@ -494,17 +504,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
 
       // residual prefetch of the first item (overlaps the tail of this tile's MMAs)
       float4 rc[8];
-      auto item_row = [&](int idx, int& t, bool& ok) {
-        const int m = idx / ncc;
+      // item = (accumulator m, 32-column chunk cc); this warp takes every second item of its TMEM lane quadrant, walked
+      // with (m, cc) counters (no divisions on this path: the epilogue is instruction-issue bound on the C <= 64 layers)
+      auto item_row = [&](int m, int& t, bool& ok) {
         const int q = tc.q0 + m * 128 + quad * 32 + lane;
         t = q * p.ot_mul + p.ot_add + phase;
         ok = !tc.dummy && q < p.nq && t >= 0 && t < p.T_out;
       };
-      auto load_res = [&](int idx, float4 (&dst)[8]) {
+      auto advance = [&](int& m, int& cc) {
+        cc += 2;
+        while (cc >= ncc) { cc -= ncc; ++m; }
+      };
+      auto load_res = [&](int m, int cc, float4 (&dst)[8]) {
         int t; bool ok;
-        item_row(idx, t, ok);
+        item_row(m, t, ok);
         if (resb && ok) {
-          const int n0 = co_off + (idx % ncc) * 32;
+          const int n0 = co_off + cc * 32;
           if (p.o_nct) {                                 // generic strides: element (c, t) at res[b*r_bs + c*r_cs + t*r_ts]
             const float* rp = resb + (size_t)n0 * p.r_cs + (size_t)t * p.r_ts;
 #pragma unroll
@@ -521,7 +536,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
           for (int k = 0; k < 8; ++k) dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       };
-      if (half < nitems) load_res(half, rc);
+      int m = 0, cc = half;
+      while (cc >= ncc) { cc -= ncc; ++m; }
+      if (half < nitems) load_res(m, cc, rc);
 
       mbar_wait(acc_full(as), (t_it >> 1) & 1);
       tc_fence_after();
@@ -612,15 +629,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
         continue;
       }
       for (int idx = half; idx < nitems; idx += 2) {
-        const int m = idx / ncc, cc = idx % ncc;
         int t; bool ok;
-        item_row(idx, t, ok);
+        item_row(m, t, ok);
         uint32_t r[32];
         __syncwarp();                                  // tcgen05.ld is .sync.aligned
         const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256 + m * NM + cc * 32);
         tmem_ld32_nowait(tcol, r);
         float4 rn[8];
-        if (idx + 2 < nitems) load_res(idx + 2, rn);   // next item's residual is in flight while this one is processed
+        int mn = m, ccn = cc;
+        advance(mn, ccn);
+        if (idx + 2 < nitems) load_res(mn, ccn, rn);   // next item's residual is in flight while this one is processed
         if (p.stack) {                                 // a*w_lo landed N columns further: fold it in
           uint32_t r2[32];
           tmem_ld32_nowait(tcol + (uint32_t)N, r2);
@@ -715,6 +733,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) rc[k] = rn[k];
+        m = mn; cc = ccn;
       }
       // this warp no longer reads accumulator set `as`
       tc_fence_before();
@@ -918,8 +937,14 @@ void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq, int a_planes) {
   p->min_off = o0 < o1 ? o0 : o1;
   const int max_off = o0 < o1 ? o1 : o0;
   p->RA = p->MT + (max_off - p->min_off);
-  p->a_stages = kMaxAStages;
   const size_t a_stage = (size_t)(p->KC / 8) * p->RA * 16 * p->a_planes;
+  // activation stages: the (tile + halo) loads come from HBM with ~1.5 us latency; short tiles (few taps, small C) need
+  // more of them in flight than the 2 a long K loop gets away with.  Keep at least ~64 KB for the weight stages.
+  int as = env_int("DTTS_TC_ASTAGES", 0);
+  if (as <= 0) as = 2;                                   // measured: 3 or 4 stages do not help (profiles/r01_summary.md)
+  if (as > kMaxAStages) as = kMaxAStages;
+  while (as > 2 && (size_t)as * a_stage > (size_t)kSmemLimit - kSmemHeader - 64 * 1024) --as;
+  p->a_stages = as;
   const size_t w_tap = (size_t)(p->pair ? p->NM / 2 : p->NM) * p->KC * 2 * p->w_planes;   // per CTA
   // taps per weight stage: ~32 KB stages, so that the per-stage barrier round trip is amortised over >= 8 MMAs
   int tg = env_int("DTTS_TC_TG", 0);
