@@ -28,6 +28,7 @@ from dict_tts_b200.weights import drop_dead, fold_weight_norm, pack_arena  # noq
 
 # algorithmic work model (checked against torch FlopCounterMode on the reference)
 VOCODER_FLOP_PER_FRAME = 614.1e6
+TC_CONV_DRAM_BYTES_PER_LAUNCH = 1.253e9   # measured (ncu), see profiles/r01_launches_bench_aggregate.txt
 WORKLOAD = dict(B=60, min_chars=12, max_chars=20, max_frames=400, Lk_cap=96)
 CPU_SAMPLE_UTTS = 2
 
@@ -148,7 +149,7 @@ def main():
             warmup=min(args.warmup, 1), ms_per_step=secs * 1e3, higher_is_better=True, scaling="weak",
             vs_baseline=None, dtype="f32", data="synthetic", config=config, rtf=secs / audio,
             cpu_baseline=dict(value=fps, unit="frames/s", cores=cores, kind="port", sample=sample),
-            e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+            e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))), flush=True)
         return
 
     if not torch.cuda.is_available():
@@ -293,7 +294,10 @@ def main():
              4: "tc_conv_kernel (tcgen05, fp16: 1 MMA)"}[args.vocoder_precision]
     roofline = dict(bound="tensor", kernel="%s, HiFi-GAN stack, %d launches/step" % (kname, n_voc_launch),
                     achieved=achieved, peak=peaks["tflops"], unit="TFLOP/s", frac=achieved / peaks["tflops"],
-                    traffic=None, peak_source=peaks["source"] + " bf16 dense (sustained)",
+                    traffic=(TC_CONV_DRAM_BYTES_PER_LAUNCH if args.vocoder_precision == 3 else None),
+                    traffic_source="profiles/r01_launches_bench_aggregate.txt (ncu dram__bytes_read+write, average over "
+                                   "the 77 vocoder launches of one step)",
+                    peak_source=peaks["source"] + " bf16 dense (sustained)",
                     avg_launch_ms=stage_ms["vocode"] / n_voc_launch,
                     flop_per_launch=padded_frames * VOCODER_FLOP_PER_FRAME / n_voc_launch)
     line = dict(metric="mel_frames_per_s", value=total_frames / (dev_ms / 1e3), unit="frames/s", n_gpus=world,
@@ -314,7 +318,7 @@ def main():
                                            f"oracle port on {cores} host threads, best of 2", seconds=secs)
     else:
         line["cpu_baseline"] = None
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)      # flush before NCCL teardown: a buffered line can be lost at process exit
     if world > 1:
         dist.destroy_process_group()
 

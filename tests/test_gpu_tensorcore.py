@@ -198,6 +198,23 @@ def test_fp16_vocoder_long_batch_vs_fp32_path():
     ref_eng.close()
 
 
+@pytest.mark.parametrize("B,T", [(1, 300), (16, 32), (5, 77), (2, 1)])
+def test_default_vocoder_mode_on_baseline_shapes(B, T):
+    """BASELINE.json shapes in miniature: cfg 1 (one long utterance), cfg 4 (many 32-frame segments), odd sizes and a
+    single frame -- the default tensor-core mode (CTA pairs on the wide layers, stacked planes on the narrow ones,
+    interleaved transposed convolutions) against the exact fp32 CUDA path."""
+    from dict_tts_b200.engine import HifiGanEngine
+    sd = synth.make_vocoder_state_dict(VOCODER_SEED)
+    ref_eng, eng = HifiGanEngine(sd, precision=0), HifiGanEngine(sd)
+    mel = synth.make_mel(50 + B, B, T)
+    ref, wav = ref_eng(mel), eng(mel)
+    assert wav.shape == (B, T * 256)
+    rms = (wav - ref).pow(2).mean().sqrt().item()
+    assert rms < TOL_WAV_RMS, rms
+    ref_eng.close()
+    eng.close()
+
+
 def test_bf16_vocoder_error_is_bounded():
     from dict_tts_b200.engine import HifiGanEngine
     sd = synth.make_vocoder_state_dict(VOCODER_SEED)
