@@ -263,6 +263,31 @@ def main():
     l1.record(stream)
     barrier()
     e2e_serial_ms = max_over_ranks(l0.elapsed_time(l1)) / min(args.steps, 5)
+    # ---- same end-to-end call with the GPU-resident dictionary bank: the characters are named by
+    # id, keys/values never cross the bus again (the bank -- here one entry per character position of this batch -- is
+    # uploaded once, outside the timed region, like the weights)
+    from dict_tts_b200.bank import DictBank
+    bank, dict_ids = DictBank.from_batch(batch)
+    pipe.acoustic.set_dict_bank(bank)
+    slim = {k: v for k, v in host.items() if k not in ("keys", "values", "key_map", "pinyin", "pinyin_map")}
+    slim["dict_ids"] = dict_ids.pin_memory()
+
+    def slim_batches(n):
+        for _ in range(n):
+            yield slim
+    for _ in pipe.synthesize_stream(slim_batches(2), wav_bufs):
+        pass
+    barrier()
+    b0 = torch.cuda.Event(enable_timing=True)
+    b1 = torch.cuda.Event(enable_timing=True)
+    b0.record(stream)
+    for w in pipe.synthesize_stream(slim_batches(args.steps), wav_bufs):
+        pass
+    b1.record(stream)
+    barrier()
+    bank_ms = max_over_ranks(b0.elapsed_time(b1)) / args.steps
+    bank_h2d = sum(slim[k].numel() * slim[k].element_size() for k in
+                   ("word_tokens", "pron_modified", "dict_ids", "mel2word", "z_p"))
     clocks = sampler.stop() if rank == 0 else None
     h2d = sum(host[k].numel() * host[k].element_size() for k in
               ("word_tokens", "pron_modified", "keys", "values", "key_map", "pinyin", "pinyin_map", "mel2word", "z_p"))
@@ -310,7 +335,11 @@ def main():
                          d2h_bytes_per_step=int(d2h), ms_per_step=e2e_ms,
                          x_realtime=(total_frames * HOP_SIZE / SAMPLE_RATE) / (e2e_ms / 1e3),
                          api="TextToWav.synthesize_stream (copy of step i+1 overlaps compute of step i)",
-                         serial_ms_per_step=e2e_serial_ms))
+                         serial_ms_per_step=e2e_serial_ms),
+                e2e_dict_bank=dict(value=total_frames / (bank_ms / 1e3), unit="frames/s", ms_per_step=bank_ms,
+                                   h2d_bytes_per_step=int(bank_h2d), d2h_bytes_per_step=int(d2h),
+                                   bank_bytes_resident=int(bank.nbytes),
+                                   note="same call with characters named by dictionary-bank id (SURVEY.md 8f-1)"))
     if not args.no_cpu_baseline and world == 1:
         fps, secs, fr = cpu_port_run(batch, CPU_SAMPLE_UTTS, cores, 2)
         line["cpu_baseline"] = dict(value=fps, unit="frames/s", cores=cores, kind="port",

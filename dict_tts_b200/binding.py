@@ -40,6 +40,17 @@ class TextOut(C.Structure):
                 ("dur", C.c_void_p), ("dur_int", C.c_void_p), ("ilens", C.c_void_p)]
 
 
+class DictBankStruct(C.Structure):
+    _fields_ = [("keys", C.c_void_p), ("values", C.c_void_p), ("key_map", C.c_void_p), ("tok_offsets", C.c_void_p),
+                ("pinyin", C.c_void_p), ("pinyin_map", C.c_void_p), ("pin_offsets", C.c_void_p),
+                ("n_entries", C.c_int32)]
+
+
+class TextInBank(C.Structure):
+    _fields_ = [("word_tokens", C.c_void_p), ("pron_modified", C.c_void_p), ("dict_ids", C.c_void_p),
+                ("B", C.c_int32), ("Tw", C.c_int32), ("Lk", C.c_int32), ("Lp", C.c_int32)]
+
+
 # every symbol include/dtts.h declares: name -> (restype, argtypes)
 _P, _I, _U64, _F = C.c_void_p, C.c_int32, C.c_uint64, C.c_float
 SYMBOLS = {
@@ -50,6 +61,9 @@ SYMBOLS = {
     "dtts_acoustic_destroy": (C.c_int, [_P]),
     "dtts_text_workspace_bytes": (_U64, [_P, _I, _I, _I, _I]),
     "dtts_text_encode": (C.c_int, [_P, C.POINTER(TextIn), C.POINTER(TextOut), _P, _U64, _P]),
+    "dtts_text_bank_workspace_bytes": (_U64, [_P, _I, _I, _I, _I]),
+    "dtts_text_encode_bank": (C.c_int, [_P, C.POINTER(DictBankStruct), C.POINTER(TextInBank), C.POINTER(TextOut), _P,
+                                        _U64, _P]),
     "dtts_length_regulate_scan": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, C.POINTER(C.c_int32), _P]),
     "dtts_length_regulate_fill": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "dtts_expand": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),

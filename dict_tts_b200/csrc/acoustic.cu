@@ -533,8 +533,10 @@ extern "C" uint64_t dtts_text_workspace_bytes(const dtts_acoustic* h, int32_t B,
   return n + 4096;
 }
 
-extern "C" int dtts_text_encode(dtts_acoustic* h, const dtts_text_in* in, const dtts_text_out* out, void* ws,
-                                uint64_t ws_bytes, void* stream) {
+// Shared body of dtts_text_encode / dtts_text_encode_bank.  row_off / row_len != null: in->keys_dev / values_dev are the
+// dictionary bank [rows][dict_dim] and character (b,t) owns rows [row_off, row_off + row_len) of it.
+static int text_encode_impl(dtts_acoustic* h, const dtts_text_in* in, const dtts_text_out* out, void* ws,
+                            uint64_t ws_bytes, void* stream, const int64_t* row_off, const int32_t* row_len) {
   if (!h || !in || !out || !ws) return fail(DTTS_ERR_BAD_ARG, "dtts_text_encode: null argument");
   const int B = in->B, Tw = in->Tw, Lk = in->Lk, Lp = in->Lp;
   if (B <= 0 || Tw <= 0 || Lk <= 0 || Lp <= 0) return fail(DTTS_ERR_BAD_SHAPE, "dtts_text_encode: empty shape");
@@ -599,7 +601,8 @@ extern "C" int dtts_text_encode(dtts_acoustic* h, const dtts_text_in* in, const 
     p.alpha = 1.f / sqrtf((float)D);
     L(launch_conv1d_f32(p, B, s));
   }
-  L(s2pa_stream(in->keys_dev, in->values_dev, in->key_map_dev, qk, B, Tw, Lk, D, weights, out->dict_attn_dev, ctx, s));
+  L(s2pa_stream(in->keys_dev, in->values_dev, in->key_map_dev, qk, B, Tw, Lk, D, weights, out->dict_attn_dev, ctx, s,
+                row_off, row_len));
   if (tc) {
     tc->stage_nct(tc->P[0], ctx, D, Tw);
     tc->conv_nct(tc->P[0], h->t_s2pa_v, nullptr, Tw, 1, 0, TcRun::Epi(), 0, 0, &tc->P[1]);
@@ -643,6 +646,61 @@ extern "C" int dtts_text_encode(dtts_acoustic* h, const dtts_text_in* in, const 
   L(dur_head(cur, h->dur_w, h->dur_b, keep, B, C, Tw, out->dur_dev, out->dur_int_dev, s));
   if (L.err != cudaSuccess) return fail(DTTS_ERR_CUDA, std::string("dtts_text_encode: ") + cudaGetErrorString(L.err));
   return DTTS_OK;
+}
+
+extern "C" int dtts_text_encode(dtts_acoustic* h, const dtts_text_in* in, const dtts_text_out* out, void* ws,
+                                uint64_t ws_bytes, void* stream) {
+  return text_encode_impl(h, in, out, ws, ws_bytes, stream, nullptr, nullptr);
+}
+
+// ---- GPU-resident dictionary bank: the per-batch dict_msg is a function of the character ids ----
+static size_t bank_gather_bytes(int B, int Tw, int Lk, int Lp) {
+  const size_t bt = (size_t)B * Tw;
+  return ws_round(bt * Lk * sizeof(float)) + 2 * ws_round(bt * Lp * sizeof(int64_t)) + ws_round(bt * sizeof(int64_t)) +
+         ws_round(bt * sizeof(int32_t)) + ws_round(sizeof(int)) + 2048;
+}
+
+extern "C" uint64_t dtts_text_bank_workspace_bytes(const dtts_acoustic* h, int32_t B, int32_t Tw, int32_t Lk,
+                                                   int32_t Lp) {
+  const uint64_t base = dtts_text_workspace_bytes(h, B, Tw, Lk, Lp);
+  return base ? base + bank_gather_bytes(B, Tw, Lk, Lp) : 0;
+}
+
+extern "C" int dtts_text_encode_bank(dtts_acoustic* h, const dtts_dict_bank* bank, const dtts_text_in_bank* in,
+                                     const dtts_text_out* out, void* ws, uint64_t ws_bytes, void* stream) {
+  if (!h || !bank || !in || !out || !ws) return fail(DTTS_ERR_BAD_ARG, "dtts_text_encode_bank: null argument");
+  if (!bank->keys_dev || !bank->values_dev || !bank->key_map_dev || !bank->tok_offsets_dev || !bank->pinyin_dev ||
+      !bank->pinyin_map_dev || !bank->pin_offsets_dev || bank->n_entries <= 0 || !in->dict_ids_dev ||
+      !in->word_tokens_dev)
+    return fail(DTTS_ERR_BAD_ARG, "dtts_text_encode_bank: null bank / id tensor");
+  const int B = in->B, Tw = in->Tw, Lk = in->Lk, Lp = in->Lp;
+  if (B <= 0 || Tw <= 0 || Lk <= 0 || Lp <= 0) return fail(DTTS_ERR_BAD_SHAPE, "dtts_text_encode_bank: empty shape");
+  if (ws_bytes < dtts_text_bank_workspace_bytes(h, B, Tw, Lk, Lp))
+    return fail(DTTS_ERR_WORKSPACE_TOO_SMALL, "dtts_text_encode_bank: workspace too small");
+  const size_t gbytes = bank_gather_bytes(B, Tw, Lk, Lp);
+  const size_t bt = (size_t)B * Tw;
+  Bump bump(ws, gbytes);
+  float* key_map = bump.take<float>(bt * Lk);
+  int64_t* pinyin = bump.take<int64_t>(bt * Lp);
+  int64_t* pinyin_map = bump.take<int64_t>(bt * Lp);
+  int64_t* row_off = bump.take<int64_t>(bt);
+  int32_t* row_len = bump.take<int32_t>(bt);
+  int* err = bump.take<int>(1);
+  if (!bump.ok) return fail(DTTS_ERR_WORKSPACE_TOO_SMALL, "dtts_text_encode_bank: workspace too small");
+  DTTS_CUDA(dict_bank_gather(in->dict_ids_dev, bank->tok_offsets_dev, bank->pin_offsets_dev, bank->key_map_dev,
+                             bank->pinyin_dev, bank->pinyin_map_dev, bank->n_entries, B, Tw, Lk, Lp, key_map, pinyin,
+                             pinyin_map, row_off, row_len, err, (cudaStream_t)stream));
+  h->launches++;
+  dtts_text_in tin{};
+  tin.word_tokens_dev = in->word_tokens_dev;
+  tin.pron_modified_dev = in->pron_modified_dev;
+  tin.keys_dev = bank->keys_dev;
+  tin.values_dev = bank->values_dev;
+  tin.key_map_dev = key_map;
+  tin.pinyin_dev = pinyin;
+  tin.pinyin_map_dev = pinyin_map;
+  tin.B = B; tin.Tw = Tw; tin.Lk = Lk; tin.Lp = Lp;
+  return text_encode_impl(h, &tin, out, (char*)ws + gbytes, ws_bytes - gbytes, stream, row_off, row_len);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

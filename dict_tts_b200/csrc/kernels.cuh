@@ -41,7 +41,14 @@ cudaError_t self_attention(const float* q, const float* k, const float* v, const
 // S2PA streaming pass. qk [B,D,Tw] (channels-first, already scaled). Writes weights [B,Tw,Lk], align [B,1,Lk,Tw],
 // ctx [B,D,Tw] = sum_l w*values.  key_map float [B,Tw,Lk].
 cudaError_t s2pa_stream(const float* keys, const float* values, const float* key_map, const float* qk, int B, int Tw,
-                        int Lk, int D, float* weights, float* align, float* ctx, cudaStream_t s);
+                        int Lk, int D, float* weights, float* align, float* ctx, cudaStream_t s,
+                        const int64_t* row_off = nullptr, const int32_t* row_len = nullptr);
+// GPU-resident dictionary bank: per-batch key_map / pinyin / pinyin_map in the collater's padded
+// layout plus the row window of each character in the keys / values bank.  *err != 0: an id or a length was out of range.
+cudaError_t dict_bank_gather(const int64_t* ids, const int64_t* tok_off, const int64_t* pin_off,
+                             const float* bank_key_map, const int64_t* bank_pinyin, const int64_t* bank_pinyin_map,
+                             int n_entries, int B, int Tw, int Lk, int Lp, float* key_map, int64_t* pinyin,
+                             int64_t* pinyin_map, int64_t* row_off, int32_t* row_len, int* err, cudaStream_t s);
 // global maxima of key_map (float, as int) and pinyin_map (int64) -> maxes[0], maxes[1]
 cudaError_t dict_maxes(const float* key_map, size_t n_key, const int64_t* pinyin_map, size_t n_pin, int* maxes,
                        cudaStream_t s);

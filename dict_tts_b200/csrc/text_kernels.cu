@@ -331,7 +331,11 @@ __global__ void __launch_bounds__(256) s2pa_stream_kernel(const float* __restric
                                                            const float* __restrict__ key_map,
                                                            const float* __restrict__ qk, int Tw, int Lk, int D,
                                                            float* __restrict__ weights, float* __restrict__ align,
-                                                           float* __restrict__ ctx) {
+                                                           float* __restrict__ ctx,
+                                                           const int64_t* __restrict__ row_off,
+                                                           const int32_t* __restrict__ row_len) {
+  // row_off != null: keys / values are a dictionary BANK [rows][D]; character (b,t) owns rows
+  // [row_off[bt], row_off[bt] + row_len[bt]) of it and every further gloss position is an all-zero row (never read).
   extern __shared__ float sm[];
   float* s_q = sm;            // [D]
   float* s_w = sm + D;        // [Lk]
@@ -344,14 +348,16 @@ __global__ void __launch_bounds__(256) s2pa_stream_kernel(const float* __restric
   for (int d = tid; d < D; d += 256) s_q[d] = qk[((size_t)b * D + d) * Tw + t];
   __syncthreads();
   const float* km = key_map + (size_t)bt * Lk;
-  const float4* kp = reinterpret_cast<const float4*>(keys + (size_t)bt * Lk * D);
+  const int nrow = row_off ? row_len[bt] : Lk;                 // rows that exist in memory
+  const size_t row0 = row_off ? (size_t)(nrow > 0 ? row_off[bt] : 0) : (size_t)bt * Lk;
+  const float4* kp = reinterpret_cast<const float4*>(keys + row0 * D);
   const int D4 = D >> 2;
   // pass 1: logits (one warp per gloss token)
   for (int l = warp; l < Lk; l += 8) {
     float logit = -1e9f;
     if (km[l] != 0.f) {
       float acc = 0.f;
-      for (int i = lane; i < D4; i += 32) {
+      for (int i = lane; l < nrow && i < D4; i += 32) {
         const float4 kv = ld_stream_f4(kp + (size_t)l * D4 + i);
         const float4 qv = *reinterpret_cast<const float4*>(s_q + 4 * i);
         acc = fmaf(kv.x, qv.x, acc); acc = fmaf(kv.y, qv.y, acc);
@@ -396,11 +402,11 @@ __global__ void __launch_bounds__(256) s2pa_stream_kernel(const float* __restric
   __syncthreads();
   // pass 2: ctx[d] = sum_l w[l] * values[l][d]; each thread owns float4 columns, rows with w == 0 are skipped.
   // A fully masked row has uniform weights 1/Lk and all-zero-padded values: it still has to be read.
-  const float4* vp = reinterpret_cast<const float4*>(values + (size_t)bt * Lk * D);
+  const float4* vp = reinterpret_cast<const float4*>(values + row0 * D);
   const bool all_masked = (s_any == 0);
   for (int i = tid; i < D4; i += 256) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int l = 0; l < Lk; ++l) {
+    for (int l = 0; l < nrow; ++l) {
       const float w = s_w[l];
       if (w == 0.f && !all_masked) continue;
       const float4 vv = ld_stream_f4(vp + (size_t)l * D4 + i);
@@ -413,14 +419,62 @@ __global__ void __launch_bounds__(256) s2pa_stream_kernel(const float* __restric
 }
 
 cudaError_t s2pa_stream(const float* keys, const float* values, const float* key_map, const float* qk, int B, int Tw,
-                        int Lk, int D, float* weights, float* align, float* ctx, cudaStream_t s) {
+                        int Lk, int D, float* weights, float* align, float* ctx, cudaStream_t s,
+                        const int64_t* row_off, const int32_t* row_len) {
   if (D % 4) return cudaErrorInvalidValue;
   const size_t smem = (size_t)(D + Lk) * sizeof(float);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(s2pa_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  s2pa_stream_kernel<<<B * Tw, 256, smem, s>>>(keys, values, key_map, qk, Tw, Lk, D, weights, align, ctx);
+  s2pa_stream_kernel<<<B * Tw, 256, smem, s>>>(keys, values, key_map, qk, Tw, Lk, D, weights, align, ctx, row_off,
+                                               row_len);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Dictionary bank -> the small per-batch tensors of dict_msg, exactly as DictTTSDataset.collater pads them
+// (tasks/tts/dataset_utils.py:264-302): id >= 0: the entry's key_map / pinyin / pinyin_map, zero padded; id == -1
+// (BOS / EOS row): key_map 1, pinyin 0, pinyin_map 1 over the whole row; id == -2 (padding): zeros.  Also the row
+// window of the big keys / values bank for s2pa_stream.  One block per (b, t).
+__global__ void dict_bank_gather_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ tok_off,
+                                        const int64_t* __restrict__ pin_off, const float* __restrict__ bank_key_map,
+                                        const int64_t* __restrict__ bank_pinyin,
+                                        const int64_t* __restrict__ bank_pinyin_map, int n_entries, int Lk, int Lp,
+                                        float* __restrict__ key_map, int64_t* __restrict__ pinyin,
+                                        int64_t* __restrict__ pinyin_map, int64_t* __restrict__ row_off,
+                                        int32_t* __restrict__ row_len, int* __restrict__ err) {
+  const int bt = blockIdx.x;
+  const int64_t id = ids[bt];
+  int64_t t0 = 0, p0 = 0;
+  int nl = 0, np = 0;
+  if (id >= 0) {
+    if (id >= n_entries) {
+      if (threadIdx.x == 0) atomicExch(err, 1);
+    } else {
+      t0 = tok_off[id]; nl = (int)(tok_off[id + 1] - t0);
+      p0 = pin_off[id]; np = (int)(pin_off[id + 1] - p0);
+      if (nl > Lk || np > Lp) {
+        if (threadIdx.x == 0) atomicExch(err, 2);
+        nl = min(nl, Lk); np = min(np, Lp);
+      }
+    }
+  }
+  const float edge = id == -1 ? 1.f : 0.f;
+  for (int l = threadIdx.x; l < Lk; l += blockDim.x) key_map[(size_t)bt * Lk + l] = l < nl ? bank_key_map[t0 + l] : edge;
+  for (int p = threadIdx.x; p < Lp; p += blockDim.x) {
+    pinyin[(size_t)bt * Lp + p] = p < np ? bank_pinyin[p0 + p] : 0;
+    pinyin_map[(size_t)bt * Lp + p] = p < np ? bank_pinyin_map[p0 + p] : (int64_t)edge;
+  }
+  if (threadIdx.x == 0) { row_off[bt] = t0; row_len[bt] = nl; }
+}
+
+cudaError_t dict_bank_gather(const int64_t* ids, const int64_t* tok_off, const int64_t* pin_off,
+                             const float* bank_key_map, const int64_t* bank_pinyin, const int64_t* bank_pinyin_map,
+                             int n_entries, int B, int Tw, int Lk, int Lp, float* key_map, int64_t* pinyin,
+                             int64_t* pinyin_map, int64_t* row_off, int32_t* row_len, int* err, cudaStream_t s) {
+  dict_bank_gather_kernel<<<B * Tw, 128, 0, s>>>(ids, tok_off, pin_off, bank_key_map, bank_pinyin, bank_pinyin_map,
+                                                 n_entries, Lk, Lp, key_map, pinyin, pinyin_map, row_off, row_len, err);
   return cudaGetLastError();
 }
 

@@ -121,6 +121,43 @@ class DictTTSEngine:
                                                 _stream()), "text_encode")
         return out
 
+    # -- GPU-resident dictionary bank ------------------------------------------------------
+    def set_dict_bank(self, bank):
+        """Uploads (if needed) and registers a dict_tts_b200.bank.DictBank; afterwards forward(dict_ids=...) and
+        text_encode_bank() name characters by id instead of shipping keys/values for every batch."""
+        self.bank = bank if bank.keys.is_cuda else bank.to(self.device)
+        return self.bank
+
+    def text_encode_bank(self, word_tokens, pron_modified, dict_ids, Lk: int = 0, Lp: int = 0):
+        bank = getattr(self, "bank", None)
+        if bank is None:
+            raise RuntimeError("no dictionary bank registered: call set_dict_bank() first")
+        dev = self.device
+        if Lk <= 0 or Lp <= 0:                                # host-side validation of the ids + the collater's widths
+            lk, lp = bank.batch_dims(dict_ids)                #   (pass Lk, Lp to skip the device->host read of the ids)
+            Lk, Lp = max(int(Lk), lk), max(int(Lp), lp)
+        wt = _dev_i64(word_tokens, dev)
+        ids = _dev_i64(dict_ids, dev)
+        B, Tw = wt.shape
+        if tuple(ids.shape) != (B, Tw):
+            raise ValueError("dict_ids must be [B,Tw] like word_tokens")
+        pm = None if pron_modified is None else _dev_i64(pron_modified, dev)
+        H = self.cfg.hidden
+        out = dict(word_encoder_out=torch.empty(B, Tw, H, device=dev),
+                   dict_attn=torch.empty(B, 1, Lk, Tw, device=dev),
+                   pron_attn=torch.empty(B, Tw, Lp, device=dev),
+                   dur=torch.empty(B, Tw, device=dev),
+                   dur_int=torch.empty(B, Tw, dtype=torch.int64, device=dev),
+                   ilens=torch.empty(B, dtype=torch.int64, device=dev))
+        tin = binding.TextInBank(_ptr(wt), _ptr(pm), _ptr(ids), B, Tw, Lk, Lp)
+        tout = binding.TextOut(*[_ptr(out[k]) for k in ("word_encoder_out", "dict_attn", "pron_attn", "dur",
+                                                          "dur_int", "ilens")])
+        ws = self.ws.get(self.lib.dtts_text_bank_workspace_bytes(self.handle, B, Tw, Lk, Lp))
+        st = bank.c_struct()
+        binding.check(self.lib.dtts_text_encode_bank(self.handle, C.byref(st), C.byref(tin), C.byref(tout), _ptr(ws),
+                                                     ws.numel(), _stream()), "text_encode_bank")
+        return out
+
     def length_regulate(self, dur_int, ilens):
         """LengthRegulator + pad to frames_multiple.  Syncs once to learn T (data-dependent shape)."""
         dev = self.device
@@ -168,7 +205,7 @@ class DictTTSEngine:
     @torch.no_grad()
     def forward(self, txt_tokens, pron_modified, key_value_map=None, ph2word=None, word_len=None, dict_msg=None,
                 mel2word=None, mel2ph=None, spk_embed=None, infer=True, tgt_mels=None, forward_post_glow=True,
-                two_stage=True, z_p=None):
+                two_stage=True, z_p=None, dict_ids=None):
         """Same arguments as PortaSpeech_dict.forward (model.py:36-37).  Inference only.  ``z_p`` (extension):
         the N(0,1) prior sample; when None it is drawn exactly like the reference does -- on the host with the
         global CPU generator (fvae_semantics.py:110-111)."""
@@ -177,10 +214,13 @@ class DictTTSEngine:
         if spk_embed is not None:
             raise NotImplementedError("multi-speaker conditioning is off in dict_tts.yaml (use_spk_embed: false)")
         word_tokens = txt_tokens[0] if isinstance(txt_tokens, (tuple, list)) else txt_tokens
-        keys, values, key_map, pinyin, pinyin_map = dict_msg
         with torch.cuda.device(self.device):
             ret = {}
-            t = self.text_encode(word_tokens, pron_modified, keys, values, key_map, pinyin, pinyin_map)
+            if dict_ids is not None and dict_msg is None:     # extension: characters named by dictionary-bank id
+                t = self.text_encode_bank(word_tokens, pron_modified, dict_ids)
+            else:
+                keys, values, key_map, pinyin, pinyin_map = dict_msg
+                t = self.text_encode(word_tokens, pron_modified, keys, values, key_map, pinyin, pinyin_map)
             ret["dict_attn"], ret["rel"], ret["dp_attn"] = t["dict_attn"], None, None
             ret["pron_attn"], ret["dur"], ret["word_encoder_out"] = t["pron_attn"], t["dur"], t["word_encoder_out"]
             fm = self.cfg.frames_multiple

@@ -12,7 +12,8 @@ import torch
 from .config import AcousticConfig, VocoderConfig
 from .engine import DictTTSEngine, HifiGanEngine
 
-_INPUT_KEYS = ("word_tokens", "pron_modified", "keys", "values", "key_map", "pinyin", "pinyin_map", "mel2word", "z_p")
+_INPUT_KEYS = ("word_tokens", "pron_modified", "keys", "values", "key_map", "pinyin", "pinyin_map", "mel2word", "z_p",
+               "dict_ids")
 
 
 class TextToWav:
@@ -37,16 +38,21 @@ class TextToWav:
             v = batch.get(k)
             if v is not None:
                 out[k] = v.to(self.device, non_blocking=True)
-        if out.get("values") is None:
+        if out.get("values") is None and "keys" in out:
             out["values"] = out["keys"]
+        if "keys" not in out:                     # bank batch: the (Lk, Lp) the collater would pad to, from host offsets
+            out["_dims"] = self.acoustic.bank.batch_dims(batch["dict_ids"])
         return out
 
     def run_device(self, dev: Dict[str, torch.Tensor], record=None):
         """Device-resident inputs -> (ret dict, wav [B, T*hop]) on the device.  ``record(name)`` marks stage ends."""
         eng = self.acoustic
         with torch.cuda.device(self.device):
-            t = eng.text_encode(dev["word_tokens"], dev.get("pron_modified"), dev["keys"], dev["values"],
-                                dev["key_map"], dev["pinyin"], dev["pinyin_map"])
+            if "keys" in dev:
+                t = eng.text_encode(dev["word_tokens"], dev.get("pron_modified"), dev["keys"], dev["values"],
+                                    dev["key_map"], dev["pinyin"], dev["pinyin_map"])
+            else:                                 # GPU-resident dictionary bank: only ids cross the bus
+                t = eng.text_encode_bank(dev["word_tokens"], dev.get("pron_modified"), dev["dict_ids"], *dev["_dims"])
             if record:
                 record("text_encode")
             m2w = dev.get("mel2word")
@@ -103,7 +109,8 @@ class TextToWav:
                     copy.wait_event(free[i])
                 d = self.to_device(batch)
                 for t in d.values():
-                    t.record_stream(compute)          # allocated on the copy stream, consumed on the compute stream
+                    if torch.is_tensor(t):
+                        t.record_stream(compute)      # allocated on the copy stream, consumed on the compute stream
                 ev = torch.cuda.Event()
                 ev.record(copy)
             slots[i] = (d, ev)

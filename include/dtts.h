@@ -115,6 +115,36 @@ uint64_t dtts_text_workspace_bytes(const dtts_acoustic* h, int32_t B, int32_t Tw
 int dtts_text_encode(dtts_acoustic* h, const dtts_text_in* in, const dtts_text_out* out, void* ws_dev,
                      uint64_t ws_bytes, void* stream);
 
+/* GPU-resident dictionary bank.  keys / values / key_map / pinyin / pinyin_map of a character are a
+ * pure function of its dictionary id (tasks/tts/dataset_utils.py:305-330 reads them from dict_embed.{data,idx} for
+ * every batch), so the bank is uploaded once and a batch names its characters by id: entry i owns gloss rows
+ * [tok_offsets[i], tok_offsets[i+1]) of keys/values/key_map and pronunciation slots [pin_offsets[i], pin_offsets[i+1])
+ * of pinyin/pinyin_map.  dict_ids: >= 0 bank entry, -1 the BOS/EOS row the collater builds (keys 0, key_map 1,
+ * pinyin 0, pinyin_map 1; dataset_utils.py:286-296), -2 padding.  Lk / Lp: padded widths of this batch (>= the longest
+ * entry used; they are the Lk / Lp of the outputs dict_attn / pron_attn).  Results are identical to dtts_text_encode on
+ * the tensors the collater would have built. */
+typedef struct dtts_dict_bank {
+  const float* keys_dev;          /* [rows, dict_dim]                       */
+  const float* values_dev;        /* [rows, dict_dim] (may alias keys_dev)  */
+  const float* key_map_dev;       /* [rows]                                 */
+  const int64_t* tok_offsets_dev; /* [n_entries + 1]                        */
+  const int64_t* pinyin_dev;      /* [slots]                                */
+  const int64_t* pinyin_map_dev;  /* [slots]                                */
+  const int64_t* pin_offsets_dev; /* [n_entries + 1]                        */
+  int32_t n_entries;
+} dtts_dict_bank;
+
+typedef struct dtts_text_in_bank {
+  const int64_t* word_tokens_dev;   /* [B,Tw]         */
+  const int64_t* pron_modified_dev; /* [B,Tw] or NULL */
+  const int64_t* dict_ids_dev;      /* [B,Tw]         */
+  int32_t B, Tw, Lk, Lp;
+} dtts_text_in_bank;
+
+uint64_t dtts_text_bank_workspace_bytes(const dtts_acoustic* h, int32_t B, int32_t Tw, int32_t Lk, int32_t Lp);
+int dtts_text_encode_bank(dtts_acoustic* h, const dtts_dict_bank* bank, const dtts_text_in_bank* in,
+                          const dtts_text_out* out, void* ws_dev, uint64_t ws_bytes, void* stream);
+
 /* Length regulator (modules/fastspeech/tts_modules.py:215-251).  Step 1 scans durations on the device and
  * returns the longest utterance in *t_raw_host -- this call SYNCHRONISES the stream (the one data-dependent shape
  * on the path).  cum_dev is int32 [B,Tw] scratch kept for step 2; totals_dev is int32 [B+1]

@@ -120,3 +120,50 @@ def test_pipeline_stream_equals_serial_calls():
         ref_wav = O.hifigan_forward(Wv, VocoderConfig(), ref["mel_out"])
     assert float((streamed[2] - ref_wav).pow(2).mean().sqrt()) < TOL_WAV_RMS
     pipe.close()
+
+
+def test_dictionary_bank_path_equals_explicit_dict_msg():
+    """naming characters by bank id must give exactly what shipping keys/values gives."""
+    from dict_tts_b200.bank import DictBank
+    from dict_tts_b200.engine import DictTTSEngine
+    eng = DictTTSEngine(synth.make_acoustic_state_dict(1234))
+    for seed, kw in ((61, dict(B=4, min_chars=1, max_chars=9, max_frames=64, Lk_cap=64, pron_modified_p=0.1)),
+                     (62, dict(B=2, min_chars=6, max_chars=6, max_frames=40, Lk_cap=96))):
+        batch = synth.make_batch(seed=seed, **kw)
+        bank, ids = DictBank.from_batch(batch)
+        eng.set_dict_bank(bank)
+        Lk, Lp = batch["key_map"].shape[2], batch["pinyin"].shape[2]
+        ref = eng.text_encode(batch["word_tokens"], batch["pron_modified"], batch["keys"], batch["values"],
+                              batch["key_map"], batch["pinyin"], batch["pinyin_map"])
+        got = eng.text_encode_bank(batch["word_tokens"], batch["pron_modified"], ids, Lk, Lp)
+        for k in ("word_encoder_out", "dict_attn", "pron_attn", "dur", "dur_int", "ilens"):
+            assert torch.equal(ref[k], got[k]), k
+        # forward() with dict_ids only (widths derived from the bank) agrees with the oracle on the collated tensors
+        out = eng.forward((batch["word_tokens"],), batch["pron_modified"], dict_ids=ids, mel2word=batch["mel2word"],
+                          z_p=batch["z_p"])
+        lk, lp = bank.batch_dims(ids)
+        exp = dict(batch, **bank.collate(ids, lk, lp))
+        W = fold_weight_norm(synth.make_acoustic_state_dict(1234))
+        with torch.no_grad():
+            want = O.acoustic_forward(W, AcousticConfig(), exp, batch["mel2word"], batch["z_p"])
+        assert (out["mel_out"].cpu() - want["mel_out"]).abs().max() < TOL_MEL_MAXABS
+        assert (out["dict_attn"].cpu() - want["dict_attn"]).abs().max() < 1e-5
+    eng.close()
+
+
+def test_pipeline_with_bank_equals_explicit():
+    from dict_tts_b200.bank import DictBank
+    from dict_tts_b200.pipeline import TextToWav
+    pipe = TextToWav(synth.make_acoustic_state_dict(1234), synth.make_vocoder_state_dict(4321))
+    batch = synth.make_batch(seed=70, B=3, min_chars=3, max_chars=6, max_frames=40, Lk_cap=32)
+    explicit = pipe.synthesize(batch).clone()
+    bank, ids = DictBank.from_batch(batch)
+    pipe.acoustic.set_dict_bank(bank)
+    slim = {k: v for k, v in batch.items() if k not in ("keys", "values", "key_map", "pinyin", "pinyin_map")}
+    slim["dict_ids"] = ids
+    # same widths as the explicit batch so that the outputs are comparable bit for bit
+    via_bank = pipe.synthesize(slim).clone()
+    assert torch.allclose(explicit, via_bank, atol=2e-6)
+    streamed = [w.clone() for w in pipe.synthesize_stream(iter([slim, slim]))]
+    assert torch.equal(streamed[0], via_bank) and torch.equal(streamed[1], via_bank)
+    pipe.close()

@@ -212,3 +212,31 @@ def test_world_size_2_gloo_broadcast_and_sharding(exp, tmp_path):
     assert res["equal"] and res["n"] > 100
     r0, r1 = res["names"]
     assert not set(r0) & set(r1) and len(r0) + len(r1) == exp["n_items"]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# dictionary bank: host side
+# ---------------------------------------------------------------------------------------------------------------
+def test_dict_bank_round_trip_reproduces_the_collated_batch():
+    from dict_tts_b200.bank import BOS_EOS, PAD, DictBank
+    batch = synth.make_batch(seed=9, B=3, min_chars=2, max_chars=5, max_frames=32, Lk_cap=40)
+    bank, ids = DictBank.from_batch(batch)
+    n_chars = int((batch["word_tokens"] >= 3).sum())
+    assert bank.n_entries == n_chars and int((ids >= 0).sum()) == n_chars
+    assert int((ids == BOS_EOS).sum()) == 2 * 3 and int((ids == PAD).sum()) == int((batch["word_tokens"] == 0).sum())
+    Lk, Lp = batch["key_map"].shape[2], batch["pinyin"].shape[2]
+    assert bank.batch_dims(ids) <= (Lk, Lp) or bank.batch_dims(ids)[0] <= Lk
+    again = bank.collate(ids, Lk, Lp)
+    for k in ("keys", "values", "key_map", "pinyin", "pinyin_map"):
+        assert torch.equal(again[k], batch[k]), k
+    with pytest.raises(ValueError):
+        bank.batch_dims(torch.tensor([[bank.n_entries]]))
+    with pytest.raises(RuntimeError):
+        bank.c_struct()                       # host bank: must be moved to the device first
+
+
+def test_dict_ids_from_words():
+    from dict_tts_b200.bank import ids_from_words
+    w2i = {"<pad>": 0, "<EOS>": 1, "<UNK>": 2, "<BOS>": 3, "a": 4, "b": 5}
+    ids = ids_from_words([["<BOS>", "a", "b", "<EOS>"], ["<BOS>", "zz", "<EOS>"]], w2i, 5)
+    assert ids.tolist() == [[-1, 4, 5, -1, -2], [-1, 2, -1, -2, -2]]
