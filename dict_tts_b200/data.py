@@ -120,6 +120,20 @@ class DictTTSTestSet:
             self.dict_ds = IndexedDataset(os.path.join(self.dir, "dict_embed"))
         return self.dict_ds[self.word_to_id.get(word, 2)]            # 2 = <UNK> (dataset_utils.py:312-315)
 
+    def build_bank(self):
+        """The whole ``dict_embed`` table as one DictBank (entry index = word id, as get_dict_embeddings looks it up,
+        dataset_utils.py:305-330).  After this call the items carry ``dict_ids`` instead of keys/values tensors."""
+        from .bank import DictBank
+        if self.dict_ds is None:
+            self.dict_ds = IndexedDataset(os.path.join(self.dir, "dict_embed"))
+        entries = []
+        for wid in range(len(self.dict_ds)):
+            e = self.dict_ds[wid]
+            entries.append(dict(key=e["key"], value=e["value"], key_map=e["key_map"],
+                                pinyin=[self._pinyin_index[p] for p in e["pinyin"]], pinyin_map=e["pinyin_map"]))
+        self.bank = DictBank.from_entries(entries)
+        return self.bank
+
     def __getitem__(self, i: int) -> Dict:
         if self.items is None:
             self.items = IndexedDataset(os.path.join(self.dir, self.prefix))
@@ -133,6 +147,9 @@ class DictTTSTestSet:
             s["mel2word"] = torch.LongTensor(item["mel2word"])[:T]
         if "pron_modified" in item:
             s["pron_modified"] = torch.LongTensor(item["pron_modified"])
+        if getattr(self, "bank", None) is not None:                  # characters named by bank id
+            s["dict_ids"] = torch.LongTensor([-1] + [self.word_to_id.get(w, 2) for w in item["words"][1:-1]] + [-1])
+            return s
         keys, values, key_map, pinyin, pinyin_map = [], [], [], [], []
         for word in item["words"][1:-1]:                             # BOS / EOS carry no dictionary entry
             e = self._dict_entry(word)
@@ -157,6 +174,9 @@ class DictTTSTestSet:
         b["mel2word"] = pad_1d([s["mel2word"] for s in samples]) if "mel2word" in samples[0] else None
         b["pron_modified"] = (pad_1d([s["pron_modified"] for s in samples]) if "pron_modified" in samples[0]
                               else None)
+        if "dict_ids" in samples[0]:
+            b["dict_ids"] = pad_1d([s["dict_ids"] for s in samples], pad=-2)
+            return b
         b["keys"] = F.pad(pad_3d([s["keys"] for s in samples]), (0, 0, 0, 0, 1, 1))
         b["values"] = F.pad(pad_3d([s["values"] for s in samples]), (0, 0, 0, 0, 1, 1))
         b["key_map"] = F.pad(pad_3d([s["key_map"].unsqueeze(-1) for s in samples]).squeeze(-1), (0, 0, 1, 1), value=1)

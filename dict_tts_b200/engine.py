@@ -158,6 +158,39 @@ class DictTTSEngine:
                                                      ws.numel(), _stream()), "text_encode_bank")
         return out
 
+    # -- after_infer on the device ----------------------------------------------------------
+    def pcm16(self, wav: torch.Tensor) -> torch.Tensor:
+        """float waveform [.., n] on the device -> int16 PCM, (wav * 32767).astype(int16) of utils/audio.py:15-16."""
+        wav = _dev_f32(wav, self.device)
+        n = wav.numel()
+        if n % 4:
+            raise ValueError("sample count must be a multiple of 4 (it is a multiple of hop_size)")
+        pcm = torch.empty(wav.shape, dtype=torch.int16, device=self.device)
+        with torch.cuda.device(self.device):
+            binding.check(self.lib.dtts_wav_to_pcm16(_ptr(wav), n, _ptr(pcm), _stream()), "wav_to_pcm16")
+        return pcm
+
+    def pron_tokens(self, pron_attn: torch.Tensor, pinyin=None, dict_ids=None) -> torch.Tensor:
+        """[B,Tw,2] pinyin ids picked by argmax(pron_attn) (tasks/tts/dict_tts.py:295-304); -1 past the row end."""
+        pa = _dev_f32(pron_attn, self.device)
+        B, Tw, Lp = pa.shape
+        pairs = torch.empty(B, Tw, 2, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            if pinyin is not None:
+                py = _dev_i64(pinyin, self.device)
+                if tuple(py.shape) != (B, Tw, Lp):
+                    raise ValueError("pinyin must be [B,Tw,Lp] like pron_attn")
+                rc = self.lib.dtts_pron_tokens(_ptr(pa), _ptr(py), None, None, B, Tw, Lp, _ptr(pairs), _stream())
+            else:
+                bank = getattr(self, "bank", None)
+                if bank is None or dict_ids is None:
+                    raise ValueError("pron_tokens needs the pinyin tensor, or dict_ids with a registered bank")
+                ids = _dev_i64(dict_ids, self.device)
+                st = bank.c_struct()
+                rc = self.lib.dtts_pron_tokens(_ptr(pa), None, C.byref(st), _ptr(ids), B, Tw, Lp, _ptr(pairs), _stream())
+            binding.check(rc, "pron_tokens")
+        return pairs
+
     def length_regulate(self, dur_int, ilens):
         """LengthRegulator + pad to frames_multiple.  Syncs once to learn T (data-dependent shape)."""
         dev = self.device

@@ -85,6 +85,8 @@ class B200DictTTSTask:
         task.test_start()
         outputs = []
         ds = DictTTSTestSet(hp, hp.get("test_set_name", "test"))
+        if hp.get("b200_dict_bank", True):                 # upload the dictionary once; batches then carry ids only
+            task.model.set_dict_bank(ds.build_bank())
         bs = int(hp.get("b200_max_sentences", hp.get("max_valid_sentences", 1)) or 1)
         for i, batch in enumerate(ds.batches(bs, rank, world)):
             outputs.extend(task.test_step(batch, i))
@@ -129,10 +131,13 @@ class B200DictTTSTask:
     def run_model(self, sample: Dict) -> Dict:
         """The exact call of DictTTSTask.test_step (dict_tts.py:183-196)."""
         hp = self.hp
+        bank = "dict_ids" in sample
         return self.model(
             (sample["word_tokens"], sample["txt_tokens"]), sample.get("pron_modified"), (None, None, None),
             ph2word=sample.get("ph2word"), word_len=sample["word_lengths"].max(),
-            dict_msg=(sample["keys"], sample["values"], sample["key_map"], sample["pinyin"], sample["pinyin_map"]),
+            dict_msg=None if bank else (sample["keys"], sample["values"], sample["key_map"], sample["pinyin"],
+                                        sample["pinyin_map"]),
+            dict_ids=sample["dict_ids"] if bank else None,
             infer=True, forward_post_glow=False, spk_embed=None, two_stage=hp.get("two_stage", True),
             mel2word=sample["mel2word"] if hp.get("profile_infer", False) else None)
 
@@ -149,13 +154,19 @@ class B200DictTTSTask:
         mel = sample["outputs"]                                   # [B,T,80] on the device
         B = mel.shape[0]
         hop = hp.get("hop_size", 256)
+        pcm = None
         if hasattr(self.vocoder, "spec2wav_batch"):
             wav = self.vocoder.spec2wav_batch(mel)                # [B, T*hop], mel never leaves HBM
-            wav = wav.cpu().numpy()
+            if not hp.get("out_wav_norm", False):
+                pcm = self.model.pcm16(wav).cpu().numpy()         # int16 on the device: half the D2H bytes
+            else:
+                wav = wav.cpu().numpy()
         else:
             wav = np.stack([self.vocoder.spec2wav(mel[b].cpu().numpy()) for b in range(B)])
         frames = (sample["mel2word_pred"] > 0).sum(-1).cpu().numpy()      # valid frames per utterance
-        pron_attn = sample["pron_attn"].cpu()
+        # dict_tts.py:295-304 on the device: argmax(pron_attn) -> the two pinyin ids of every character
+        pairs = self.model.pron_tokens(sample["pron_attn"], pinyin=sample.get("pinyin"),
+                                       dict_ids=sample.get("dict_ids")).cpu()
         results = []
         for b in range(B):
             name, text = sample["item_name"][b], sample["text"][b]
@@ -163,19 +174,23 @@ class B200DictTTSTask:
             if text is not None:
                 base_fn += str(text).replace(":", "$3A")[:80]
             base_fn = base_fn.replace(" ", "_")
-            n = int(frames[b]) * hop if B > 1 else wav.shape[1]   # B=1: keep the padded tail like the reference
+            total = pcm.shape[1] if pcm is not None else wav.shape[1]
+            n = int(frames[b]) * hop if B > 1 else total          # B=1: keep the padded tail like the reference
             if not hp.get("profile_infer", False):
-                save_wav(wav[b, :n], os.path.join(self.gen_dir, "wavs", (base_fn % "P") + ".wav"),
-                         hp.get("audio_sample_rate", 22050), norm=hp.get("out_wav_norm", False))
+                path = os.path.join(self.gen_dir, "wavs", (base_fn % "P") + ".wav")
+                if pcm is not None:
+                    from scipy.io import wavfile
+                    wavfile.write(path, hp.get("audio_sample_rate", 22050), pcm[b, :n])
+                else:
+                    save_wav(wav[b, :n], path, hp.get("audio_sample_rate", 22050), norm=True)
             # dict_tts.py:295-304: two pinyin tokens per character from argmax(pron_attn)
             tokens = []
             if self.pinyin_encoder is not None:
                 n_words = int(sample["word_lengths"][b])
-                idx = pron_attn[b].max(-1)[1]
-                pin = sample["pinyin"][b]
                 for i in range(1, n_words - 1):
-                    for t in pin[i][idx[i]:idx[i] + 2]:
-                        tokens.append(self.pinyin_encoder[int(t)])
+                    for t in pairs[b, i].tolist():
+                        if t >= 0:
+                            tokens.append(self.pinyin_encoder[int(t)])
             results.append(dict(item_name=name, text=None if text is None else str(text).replace(",", "，").replace(".", "。"),
                                 pinyin_tokens=" ".join(tokens), wav_fn_pred=base_fn % "P", wav_fn_gt=base_fn % "G"))
             self.results_id += 1

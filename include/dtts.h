@@ -181,6 +181,17 @@ uint64_t dtts_vocoder_launch_count(const dtts_vocoder* h);
 uint64_t dtts_acoustic_launch_count(const dtts_acoustic* h);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * after_infer on the device (replaces the host work of DictTTSTask.after_infer,
+ * tasks/tts/dict_tts.py:227-311 and utils/audio.py:11-16).
+ * dtts_wav_to_pcm16: pcm = (int16)(wav * 32767) truncated toward zero (numpy astype semantics); n_samples % 4 == 0.
+ * dtts_pron_tokens:  pairs[b,t,:] = pinyin[b,t, i : i+2] with i = first argmax of pron_attn[b,t,:] (-1 past the end);
+ *                    pinyin is the explicit [B,Tw,Lp] tensor, or NULL with (bank, dict_ids) naming the characters.
+ * ---------------------------------------------------------------------------------------------------------- */
+int dtts_wav_to_pcm16(const float* wav_dev, uint64_t n_samples, int16_t* pcm_dev, void* stream);
+int dtts_pron_tokens(const float* pron_attn_dev, const int64_t* pinyin_dev, const dtts_dict_bank* bank,
+                     const int64_t* dict_ids_dev, int32_t B, int32_t Tw, int32_t Lp, int64_t* pairs_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Unit-test hook: the generic fp32 convolution kernel on raw tensors (torch.nn.functional.conv1d /
  * conv_transpose1d semantics, weights in PyTorch layout).  x [B,C_in,T_in] -> out [B,C_out,T_out].
  * ---------------------------------------------------------------------------------------------------------- */

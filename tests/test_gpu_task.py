@@ -167,3 +167,34 @@ def test_pipeline_with_bank_equals_explicit():
     streamed = [w.clone() for w in pipe.synthesize_stream(iter([slim, slim]))]
     assert torch.equal(streamed[0], via_bank) and torch.equal(streamed[1], via_bank)
     pipe.close()
+
+
+def test_device_after_infer_matches_host_semantics():
+    """int16 conversion and pinyin-token selection on the device == the host code of the reference
+    (utils/audio.py:15-16, tasks/tts/dict_tts.py:295-304), with the explicit pinyin tensor and with the bank."""
+    from dict_tts_b200.bank import DictBank
+    from dict_tts_b200.engine import DictTTSEngine
+    eng = DictTTSEngine(synth.make_acoustic_state_dict(1234))
+    g = torch.Generator().manual_seed(5)
+    wav = (torch.rand(3, 1024, generator=g) * 2 - 1) * 0.999
+    wav[0, :4] = torch.tensor([0.99999, -0.99999, 0.0, 3.05e-5])
+    pcm = eng.pcm16(wav.cuda()).cpu().numpy()
+    assert pcm.dtype == np.int16 and np.array_equal(pcm, (wav.numpy() * 32767).astype(np.int16))
+    batch = synth.make_batch(seed=81, B=3, min_chars=2, max_chars=7, max_frames=32, Lk_cap=48)
+    B, Tw, Lp = batch["pinyin"].shape
+    pron_attn = torch.rand(B, Tw, Lp, generator=g)
+    pron_attn[0, 1, :] = 0.25                                    # ties -> first maximum
+    pron_attn[1, 2, Lp - 1] = 2.0                                # maximum in the last slot -> one token only
+    want = torch.full((B, Tw, 2), -1, dtype=torch.long)
+    idx = pron_attn.max(-1)[1]
+    for b in range(B):
+        for t in range(Tw):
+            sl = batch["pinyin"][b, t][idx[b, t]:idx[b, t] + 2]
+            want[b, t, :len(sl)] = sl
+    got = eng.pron_tokens(pron_attn, pinyin=batch["pinyin"]).cpu()
+    assert torch.equal(got, want)
+    bank, ids = DictBank.from_batch(batch)
+    eng.set_dict_bank(bank)
+    got_bank = eng.pron_tokens(pron_attn, dict_ids=ids).cpu()
+    assert torch.equal(got_bank, want)
+    eng.close()
