@@ -1,5 +1,7 @@
 // Acoustic model behind the C ABI: S2PA text encoder, duration predictor, length regulator, FVAE decoder with its
 // residual-coupling prior flow.  Mirrors PortaSpeech_dict.forward(infer=True) (modules/dict_tts/model.py:36-122).
+#include <algorithm>
+
 #include "engine.cuh"
 #include "tc_conv.cuh"
 #include "tc16.cuh"
@@ -43,6 +45,9 @@ struct dtts_acoustic {
   EncoderW sem, lin;
   ConvW s2pa_q, s2pa_kT, s2pa_v, s2pa_o;
   TcConvW t_s2pa_q, t_s2pa_kT, t_s2pa_v, t_s2pa_o;
+  TcConvW t_gpre;                 // g_pre_net as a stride-1 k=3 convolution over the 4x space-to-depth input (C' = 4H)
+  TcConvW t_out;                  // out_proj with C_out zero-padded to a multiple of 32
+  int out_pad = 0;
   std::vector<ConvW> dur_conv;
   std::vector<TcConvW> t_dur;
   int precision = 0;              // 0: fp32 FMA pipe; 1: tcgen05 (bf16 hi/lo x hi/lo)
@@ -140,6 +145,7 @@ struct TcRun {
     const float* res = nullptr; long r_bs = 0, r_cs = 0, r_ts = 1;
     const float* mask = nullptr; int m_bs = 0;
     int act = 0; float alpha = 1.f, post = 1.f; int accumulate = 0;
+    int c_valid = 0;              // > 0: number of real output channels (the rest is zero padding)
   };
   bool shape(Planes& p, int C, int T) {
     p.C = C; p.T = T; p.rows = tc_rows(T);
@@ -161,6 +167,11 @@ struct TcRun {
                            h->mode.fmt, L->stream));
   }
   void stage_nct(Planes& p, const float* x, int C, int T) { stage(p, x, (long)C * T, T, 1, C, T); }
+  // channels [c_off, c_off + C) of planes already shaped to (C_total, T)
+  void stage_sub(Planes& p, const float* x, long bs, long cs, long ts, int C, int c_off) {
+    (*L)(tc_to_planes_full(x, bs, cs, ts, B, C, p.T, 1.f, p.hi, h->mode.a_planes == 2 ? p.lo : nullptr, p.rows, TC_PADF,
+                           h->mode.fmt, L->stream, p.C, c_off));
+  }
   // blocks [blk0, blk0+nblk) of w applied to `in`; fp32 result (optional) element (c,t) at out[b*o_bs + c*o_cs + t*o_ts]
   // with c counted from the first block; `po` (optional) receives the result as operand planes of the next convolution.
   void conv(const Planes& in, const TcConvW& w, int blk0, int nblk, float* out, long o_bs, long o_cs, long o_ts,
@@ -182,6 +193,7 @@ struct TcRun {
     p.res = e.res; p.r_bs = e.r_bs; p.r_cs = e.r_cs; p.r_ts = e.r_ts;
     p.mask = e.mask; p.m_bs = e.m_bs; p.act = e.act; p.alpha = e.alpha; p.post = e.post; p.accumulate = e.accumulate;
     p.slope = 1.f;
+    if (e.c_valid > 0) p.c_valid = e.c_valid;
     if (po) {
       if (!shape(*po, sub.C_out, T_out)) return;
       p.o_hi = po->hi; p.o_lo = h->mode.a_planes == 2 ? po->lo : nullptr;
@@ -467,6 +479,18 @@ extern "C" int dtts_acoustic_create(const dtts_acoustic_desc* d, const float* ar
     h->dur_b = h->tab.get("dur_predictor.linear.0.bias", 1);
     if (!h->dur_w || !h->dur_b) return DTTS_ERR_MISSING_WEIGHT;
     DTTS_TRY(pack(h, "fvae.g_pre_net.0", H, H, 8, true, &h->g_pre, s));
+    if (h->precision) {
+      // Conv1d(H,H,k=8,s=4,p=2) == Conv1d(4H,H,k=3,p=1) over x'[(s,ci), q] = g[ci, 4q+s] with
+      // w'[co,(s,ci),a] = w[co,ci,4(a-1)+s+2] (zero where that tap does not exist)
+      const float* w8 = h->tab.get("fvae.g_pre_net.0.weight", (uint64_t)H * H * 8);
+      const float* b8 = h->tab.get("fvae.g_pre_net.0.bias", H);
+      if (!w8 || !b8) return DTTS_ERR_MISSING_WEIGHT;
+      float* w3 = h->pool.take((size_t)H * 4 * H * 3);
+      if (!w3) return fail(DTTS_ERR_CUDA, "weight pool exhausted");
+      DTTS_CUDA(repack_s2d4(w8, w3, H, H, s));
+      const float* w3c = w3;
+      DTTS_TRY(tc_pack(h, &w3c, 1, b8, H, 4 * H, 3, 0, 0, &h->t_gpre, s));
+    }
     const int half = d->latent / 2;
     for (int f = 0; f < d->flow_blocks; ++f) {
       FlowW F;
@@ -491,6 +515,23 @@ extern "C" int dtts_acoustic_create(const dtts_acoustic_desc* d, const float* ar
     }
     DTTS_TRY(pack_wn(h, "fvae.decoder.wn", H, d->dec_layers, d->dec_kernel, H, &h->dec_wn, s));
     DTTS_TRY(pack(h, "fvae.decoder.out_proj", d->n_mel, H, 1, true, &h->dec_out, s));
+    if (h->precision) {
+      // out_proj: C_out = n_mel (80) padded with zero rows to a multiple of 32 for the MMA's N
+      const int np = (d->n_mel + 31) / 32 * 32;
+      const float* wo = h->tab.get("fvae.decoder.out_proj.weight", (uint64_t)d->n_mel * H);
+      const float* bo = h->tab.get("fvae.decoder.out_proj.bias", d->n_mel);
+      if (!wo || !bo) return DTTS_ERR_MISSING_WEIGHT;
+      float* wp = h->pool.take((size_t)np * H);
+      float* bp = h->pool.take(np);
+      if (!wp || !bp) return fail(DTTS_ERR_CUDA, "weight pool exhausted");
+      DTTS_CUDA(cudaMemsetAsync(wp, 0, (size_t)np * H * sizeof(float), s));
+      DTTS_CUDA(cudaMemsetAsync(bp, 0, np * sizeof(float), s));
+      DTTS_CUDA(cudaMemcpyAsync(wp, wo, (size_t)d->n_mel * H * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      DTTS_CUDA(cudaMemcpyAsync(bp, bo, d->n_mel * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      const float* wpc = wp;
+      DTTS_TRY(tc_pack(h, &wpc, 1, bp, np, H, 1, 0, 0, &h->t_out, s));
+      h->out_pad = np;
+    }
     return DTTS_OK;
   };
   rc = build();
@@ -752,7 +793,8 @@ extern "C" uint64_t dtts_decode_workspace_bytes(const dtts_acoustic* h, int32_t 
   add(B * H * T);                                      // x
   add(B * 2 * H * h->d.dec_layers * T);                // cond
   add(B * 2 * H * T); add(B * H * T); add(B * H * T);  // a, acts, skip
-  if (h->precision) n += 6 * ws_round((size_t)B * H * tc_rows(T) * sizeof(tc16));   // 3 operand-plane sets
+  if (h->precision)                                                                    // 3 operand-plane sets
+    n += 6 * ws_round((size_t)B * H * (size_t)std::max(tc_rows(T), 4 * tc_rows(T / 4)) * sizeof(tc16));
   return n + 4096;
 }
 
@@ -781,7 +823,7 @@ extern "C" int dtts_decode_mel(dtts_acoustic* h, const float* g, const float* z_
   TcRun* tc = nullptr;
   if (h->precision) {
     tcr.B = B;
-    tcr.take(bump, 3, (size_t)B * H * tc_rows(T));
+    tcr.take(bump, 3, (size_t)B * H * (size_t)std::max(tc_rows(T), 4 * tc_rows(T4)));
     tc = &tcr;
   }
   if (!bump.ok) return fail(DTTS_ERR_WORKSPACE_TOO_SMALL, "dtts_decode_mel: workspace too small");
@@ -792,7 +834,15 @@ extern "C" int dtts_decode_mel(dtts_acoustic* h, const float* g, const float* z_
   tcr.h = h; tcr.L = &L; tcr.B = B;
 
   // g_sqz = Conv1d(H,H,k=8,s=4,p=2)(g)  (fvae_semantics.py:93-94; semantics == 0)
-  L(launch_conv1d_f32(conv_params(g, T, h->g_pre, 0, H, g_sqz, T4, 1, 4, 2), B, s));
+  if (tc) {
+    Planes& P0 = tc->P[0];
+    if (tc->shape(P0, 4 * H, T4)) {
+      for (int sp = 0; sp < 4; ++sp) tc->stage_sub(P0, g + sp, (long)H * T, T, 4, H, sp * H);
+      tc->conv_nct(P0, h->t_gpre, g_sqz, T4, 1, 1, TcRun::Epi());
+    }
+  } else {
+    L(launch_conv1d_f32(conv_params(g, T, h->g_pre, 0, H, g_sqz, T4, 1, 4, 2), B, s));
+  }
   // prior flow, reverse (glow_modules.py:108-128,157-163).  The channel Flip is folded into the pre/post weights:
   // on "odd" layers the conditioning half is physical channels [half, 2*half) and the updated half is [0, half).
   L(copy_f32(z_in, z_p, (size_t)B * d.latent * T4, s));
@@ -818,7 +868,12 @@ extern "C" int dtts_decode_mel(dtts_acoustic* h, const float* g, const float* z_
   // decoder (fvae_semantics.py:53-58)
   L(launch_conv1d_f32(convT_params(z_p, T4, h->dec_pre, x, T, 4, 0), B, s));
   run_wn(h->dec_wn, H, d.dec_kernel, x, g, H, cond, a, acts, skip, B, T, L, tc);
-  {
+  if (tc) {
+    TcRun::Epi eo;
+    eo.c_valid = d.n_mel;
+    tc->stage_nct(tc->P[0], skip, H, T);
+    tc->conv(tc->P[0], h->t_out, 0, 0, mel, (long)T * d.n_mel, 1, d.n_mel, T, 1, 0, eo);    // mel_out is [B,T,80]
+  } else {
     ConvParams p = conv_params(skip, T, h->dec_out, 0, d.n_mel, mel, T, 1, 1, 0);
     p.o_bs = (long)T * d.n_mel; p.o_cs = 1; p.o_ts = d.n_mel;                 // mel_out is [B,T,80]
     L(launch_conv1d_f32(p, B, s));

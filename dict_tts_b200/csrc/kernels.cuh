@@ -15,6 +15,8 @@ cudaError_t repack_convT(const float* w, float* out, int C_in, int C_out, int K,
 // Linear weight used transposed: in [R][C] -> out [C][R] (i.e. treat W^T as a 1x1 conv weight and pack it)
 cudaError_t transpose2d(const float* in, float* out, int R, int C, cudaStream_t s);
 cudaError_t reverse_vec(const float* in, float* out, int n, cudaStream_t s);
+// stride-4 / pad-2 / k=8 Conv1d weight -> the stride-1 / pad-1 / k=3 weight over the 4x space-to-depth input
+cudaError_t repack_s2d4(const float* w, float* out, int C_out, int C_in, cudaStream_t s);
 cudaError_t fill_f32(float* p, float v, size_t n, cudaStream_t s);
 
 // ---- text encoder ----

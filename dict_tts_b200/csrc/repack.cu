@@ -59,4 +59,24 @@ cudaError_t reverse_vec(const float* in, float* out, int n, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+// Conv1d weight [C_out][C_in][8] of a stride-4, pad-2 convolution -> [C_out][4*C_in][3] of the equivalent stride-1, pad-1
+// convolution over the 4x space-to-depth input x'[(s,ci), q] = x[ci, 4q+s]:  w'[co][s*C_in+ci][a] = w[co][ci][4(a-1)+s+2]
+__global__ void repack_s2d4_kernel(const float* __restrict__ w, float* __restrict__ out, int C_out, int C_in) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)C_out * 4 * C_in * 3;
+  if (i >= total) return;
+  const int a = (int)(i % 3);
+  size_t r = i / 3;
+  const int cc = (int)(r % (4 * C_in));
+  const int co = (int)(r / (4 * C_in));
+  const int sp = cc / C_in, ci = cc % C_in;
+  const int j = 4 * (a - 1) + sp + 2;
+  out[i] = (j >= 0 && j < 8) ? w[((size_t)co * C_in + ci) * 8 + j] : 0.f;
+}
+cudaError_t repack_s2d4(const float* w, float* out, int C_out, int C_in, cudaStream_t s) {
+  const size_t total = (size_t)C_out * 4 * C_in * 3;
+  repack_s2d4_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w, out, C_out, C_in);
+  return cudaGetLastError();
+}
+
 }  // namespace dtts

@@ -680,12 +680,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
           }
           if (o32b && p.o_nct) {                        // element (c, t) at out[b*o32_bs + c*o_cs + t*o_ts]
             float* op = o32b + (size_t)n0 * p.o_cs + (size_t)t * p.o_ts;
+            const int kmax = p.c_valid - n0;            // channels >= c_valid are zero padding of the weights (C_out % 32)
             if (p.accumulate) {
 #pragma unroll
-              for (int k = 0; k < 32; ++k) v[k] += op[(size_t)k * p.o_cs];
+              for (int k = 0; k < 32; ++k)
+                if (k < kmax) v[k] += op[(size_t)k * p.o_cs];
             }
 #pragma unroll
-            for (int k = 0; k < 32; ++k) op[(size_t)k * p.o_cs] = v[k];
+            for (int k = 0; k < 32; ++k)
+              if (k < kmax) op[(size_t)k * p.o_cs] = v[k];
           } else if (o32b) {
             float4* op = reinterpret_cast<float4*>(o32b) + ((size_t)(n0 / 4) * p.T_out + t);
             if (p.accumulate) {
@@ -799,15 +802,18 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ w, tc16* __rest
 }
 
 __global__ void tc_to_planes_kernel(const float* __restrict__ x, long bs, long cs, long ts, int C, int T, float slope,
-                                    tc16* __restrict__ hi, tc16* __restrict__ lo, int rows, int pad, int fmt, int full) {
+                                    tc16* __restrict__ hi, tc16* __restrict__ lo, int rows, int pad, int fmt, int full,
+                                    int slabs_total, int slab0) {
   // full: the grid walks ALL rows of the slab and zero-fills the halo rows (one launch instead of convert + zero_halo)
+  // slabs_total / slab0: the C source channels fill slabs [slab0, slab0 + C/8) of planes holding slabs_total slabs
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const int t = full ? r - pad : r;
   const int sl = blockIdx.y, b = blockIdx.z;
+  const size_t dslab = (size_t)b * slabs_total + slab0 + sl;
   if (full) {
     if (r >= rows) return;
     if (t < 0 || t >= T) {
-      const size_t zoff = (((size_t)b * (C / 8) + sl) * rows + r) * 8;
+      const size_t zoff = (dslab * rows + r) * 8;
       *reinterpret_cast<uint4*>(hi + zoff) = make_uint4(0, 0, 0, 0);
       if (lo) *reinterpret_cast<uint4*>(lo + zoff) = make_uint4(0, 0, 0, 0);
       return;
@@ -822,7 +828,7 @@ __global__ void tc_to_planes_kernel(const float* __restrict__ x, long bs, long c
     const float a1 = leaky(x[(size_t)b * bs + (size_t)(sl * 8 + 2 * e + 1) * cs + (size_t)t * ts], slope);
     split2(a0, a1, fmt, hw[e], lw[e]);
   }
-  const size_t off = (((size_t)b * (C / 8) + sl) * rows + pad + t) * 8;
+  const size_t off = (dslab * rows + pad + t) * 8;
   *reinterpret_cast<uint4*>(hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
   if (lo) *reinterpret_cast<uint4*>(lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
 }
@@ -964,6 +970,7 @@ void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq, int a_planes) {
   p->nu = 0;
   p->o_nct = 0; p->o_cs = p->o_ts = 0; p->r_bs = p->r_cs = p->r_ts = 0;
   p->mask = nullptr; p->m_bs = 0; p->act = 0; p->alpha = 1.f;
+  p->c_valid = w.C_out;
 }
 
 static size_t tc_smem_bytes(const TcConvParams& p) {
@@ -1092,15 +1099,16 @@ cudaError_t tc_to_planes(const float* x, long bs, long cs, long ts, int B, int C
                          tc16* hi, tc16* lo, int rows, int pad, int fmt, cudaStream_t s) {
   if (C % 8) return cudaErrorInvalidValue;
   dim3 grid(cdiv(T, 128), C / 8, B);
-  tc_to_planes_kernel<<<grid, 128, 0, s>>>(x, bs, cs, ts, C, T, slope, hi, lo, rows, pad, fmt, 0);
+  tc_to_planes_kernel<<<grid, 128, 0, s>>>(x, bs, cs, ts, C, T, slope, hi, lo, rows, pad, fmt, 0, C / 8, 0);
   return cudaGetLastError();
 }
 
 cudaError_t tc_to_planes_full(const float* x, long bs, long cs, long ts, int B, int C, int T, float slope, tc16* hi,
-                              tc16* lo, int rows, int pad, int fmt, cudaStream_t s) {
-  if (C % 8) return cudaErrorInvalidValue;
+                              tc16* lo, int rows, int pad, int fmt, cudaStream_t s, int C_total, int c_off) {
+  if (C_total <= 0) C_total = C;
+  if (C % 8 || C_total % 8 || c_off % 8 || c_off + C > C_total) return cudaErrorInvalidValue;
   dim3 grid(cdiv(rows, 128), C / 8, B);
-  tc_to_planes_kernel<<<grid, 128, 0, s>>>(x, bs, cs, ts, C, T, slope, hi, lo, rows, pad, fmt, 1);
+  tc_to_planes_kernel<<<grid, 128, 0, s>>>(x, bs, cs, ts, C, T, slope, hi, lo, rows, pad, fmt, 1, C_total / 8, c_off / 8);
   return cudaGetLastError();
 }
 

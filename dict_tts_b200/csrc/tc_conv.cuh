@@ -122,6 +122,7 @@ struct TcConvParams {
   int m_bs;
   int act;                       // 0: none, 1: ReLU (applied to conv + bias)
   float alpha;                   // out = post * (act(conv + bias) * alpha * mask + res)  (+ out if accumulate)
+  int c_valid;                   // o_nct: only output channels < c_valid are stored (weights zero-padded to N % 32 == 0)
   int a_stages, w_stages;
   int TG;                        // taps per weight stage
   int ntiles, B;                 // time tiles per (group, batch item); batch size (set by the launcher)
@@ -152,8 +153,9 @@ cudaError_t tc_pack_weights(const float* w_ref, tc16* out, int C_out, int C_in, 
 cudaError_t tc_to_planes(const float* x, long bs, long cs, long ts, int B, int C, int T, float slope,
                          tc16* hi, tc16* lo, int rows, int pad, int fmt, cudaStream_t s);
 // same, and zero-fills every row outside [pad, pad+T) (one launch for a freshly re-shaped scratch buffer)
+// C_total / c_off: the C source channels become channels [c_off, c_off + C) of planes that hold C_total channels
 cudaError_t tc_to_planes_full(const float* x, long bs, long cs, long ts, int B, int C, int T, float slope, tc16* hi,
-                              tc16* lo, int rows, int pad, int fmt, cudaStream_t s);
+                              tc16* lo, int rows, int pad, int fmt, cudaStream_t s, int C_total = 0, int c_off = 0);
 // zero the halo rows [0,pad) and [pad+T, rows) of every slab of a plane pair
 cudaError_t tc_zero_halo(tc16* hi, tc16* lo, int n_slabs_total, int rows, int pad, int T,
                          cudaStream_t s);
