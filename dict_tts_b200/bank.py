@@ -115,12 +115,27 @@ class DictBank:
         return dict(keys=keys, values=values, key_map=key_map, pinyin=pinyin, pinyin_map=pinyin_map)
 
     # ---- device side ------------------------------------------------------------------------------------------------
-    def to(self, device) -> "DictBank":
+    def to(self, device, non_blocking: bool = False) -> "DictBank":
         alias = self.values.data_ptr() == self.keys.data_ptr()
-        keys = self.keys.to(device)
-        values = keys if alias or torch.equal(self.keys, self.values) else self.values.to(device)
-        return DictBank(keys, values, self.key_map.to(device), self.tok_offsets.to(device), self.pinyin.to(device),
-                        self.pinyin_map.to(device), self.pin_offsets.to(device))
+        mv = lambda t: t.to(device, non_blocking=non_blocking)      # noqa: E731
+        keys = mv(self.keys)
+        values = keys if alias or torch.equal(self.keys, self.values) else mv(self.values)
+        out = DictBank.__new__(DictBank)                            # offsets were validated when self was built
+        out.keys, out.values, out.key_map, out.tok_offsets = keys, values, mv(self.key_map), mv(self.tok_offsets)
+        out.pinyin, out.pinyin_map, out.pin_offsets = mv(self.pinyin), mv(self.pinyin_map), mv(self.pin_offsets)
+        out.n_entries, out._host_tok, out._host_pin, out._struct = self.n_entries, self._host_tok, self._host_pin, None
+        return out
+
+    def pin_memory(self) -> "DictBank":
+        """Host bank in pinned memory, so that to(device, non_blocking=True) overlaps with compute."""
+        alias = self.values.data_ptr() == self.keys.data_ptr() or torch.equal(self.keys, self.values)
+        keys = self.keys.pin_memory()
+        return DictBank(keys, keys if alias else self.values.pin_memory(), self.key_map.pin_memory(),
+                        self.tok_offsets.pin_memory(), self.pinyin.pin_memory(), self.pinyin_map.pin_memory(),
+                        self.pin_offsets.pin_memory())
+
+    def tensors(self) -> List[torch.Tensor]:
+        return [self.keys, self.values, self.key_map, self.tok_offsets, self.pinyin, self.pinyin_map, self.pin_offsets]
 
     @property
     def nbytes(self) -> int:

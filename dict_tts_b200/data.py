@@ -111,6 +111,7 @@ class DictTTSTestSet:
         self._pinyin_index = {p: i for i, p in enumerate(self.pinyin_encoder)}
         self.items = None
         self.dict_ds = None
+        self.ragged = False          # True: items carry word ids and collate_ragged() builds a batch-local DictBank
 
     def __len__(self):
         return len(self.idxs)
@@ -150,6 +151,9 @@ class DictTTSTestSet:
         if getattr(self, "bank", None) is not None:                  # characters named by bank id
             s["dict_ids"] = torch.LongTensor([-1] + [self.word_to_id.get(w, 2) for w in item["words"][1:-1]] + [-1])
             return s
+        if self.ragged:                                              # word ids only; collate_ragged reads the entries
+            s["word_ids"] = [self.word_to_id.get(w, 2) for w in item["words"][1:-1]]
+            return s
         keys, values, key_map, pinyin, pinyin_map = [], [], [], [], []
         for word in item["words"][1:-1]:                             # BOS / EOS carry no dictionary entry
             e = self._dict_entry(word)
@@ -185,13 +189,55 @@ class DictTTSTestSet:
                                 value=1)
         return b
 
-    def batches(self, max_sentences: int = 1, rank: int = 0, world: int = 1, sort_by_len: bool = True
-                ) -> Iterator[Dict]:
-        """Length-sorted batches of at most ``max_sentences``; batches are dealt round-robin to the ranks exactly
-        like the reference deals them (``x[rank::num_replicas]``, tasks/tts/tts_base.py:148-151)."""
-        order = list(range(len(self)))
-        if sort_by_len:
-            order.sort(key=lambda i: -self.sizes[i])
-        groups = [order[i:i + max_sentences] for i in range(0, len(order), max_sentences)]
-        for g in groups[rank::world]:
-            yield self.collate([self[i] for i in g])
+    def collate_ragged(self, samples: List[Dict]) -> Dict:
+        """Ragged (CSR) ``dict_msg``: instead of ``collate_3d``'s ``[B,Tw,Lk,768]`` padding
+        (utils/__init__.py:153-167) the batch carries a batch-local DictBank holding each DISTINCT character of the
+        batch once, un-padded, plus ``dict_ids [B,Tw]`` into it (-1 BOS/EOS row, -2 padding).  The engine reads the
+        gloss tokens through the offsets (``dtts_text_encode_bank``), with results bit-identical to the padded batch."""
+        from .bank import DictBank
+        if self.dict_ds is None:
+            self.dict_ds = IndexedDataset(os.path.join(self.dir, "dict_embed"))
+        local, entries, rows = {}, [], []
+        for s in samples:
+            row = [-1]
+            for wid in s["word_ids"]:
+                if wid not in local:
+                    e = self.dict_ds[wid]
+                    local[wid] = len(entries)
+                    entries.append(dict(key=e["key"], value=e["value"], key_map=e["key_map"],
+                                        pinyin=[self._pinyin_index[p] for p in e["pinyin"]],
+                                        pinyin_map=e["pinyin_map"]))
+                row.append(local[wid])
+            rows.append(torch.LongTensor(row + [-1]))
+        stripped = [{k: v for k, v in s.items() if k != "word_ids"} for s in samples]
+        for s, r in zip(stripped, rows):
+            s["dict_ids"] = r
+        b = self.collate(stripped)
+        b["dict_bank"] = DictBank.from_entries(entries) if entries else None
+        return b
+
+    def batches(self, max_sentences: int = 1, rank: int = 0, world: int = 1, sort_by_len: bool = True,
+                max_tokens: Optional[int] = None, deal: str = "batches") -> Iterator[Dict]:
+        """Collated batches for one rank.
+
+        ``deal="batches"`` (default): longest-first groups of at most ``max_sentences`` utterances, whole groups dealt
+        round-robin to the ranks -- every rank gets full-size batches of similar lengths (least padding).
+        ``deal="reference"``: the reference's sampler (tasks/tts/tts_base.py:113-155 through
+        ``batching.build_batch_sampler``): natural order, global groups of ``max_sentences * world`` (and at most
+        ``max_tokens * world`` padded frames when given), every group dealt ``x[rank::world]``; groups that do not
+        divide by ``world`` are kept here (the reference drops them -- it would lose utterances at inference)."""
+        collate = self.collate_ragged if self.ragged else self.collate
+        if deal == "reference":
+            from .batching import build_batch_sampler
+            groups = build_batch_sampler(self.sizes, max_tokens=max_tokens, max_sentences=max_sentences,
+                                         by_size=max_tokens is not None, world=world, rank=rank,
+                                         max_frames=self.hp.get("max_frames"), drop_ragged=False)
+        elif deal == "batches":
+            order = list(range(len(self)))
+            if sort_by_len:
+                order.sort(key=lambda i: -self.sizes[i])
+            groups = [order[i:i + max_sentences] for i in range(0, len(order), max_sentences)][rank::world]
+        else:
+            raise ValueError("deal must be 'batches' or 'reference'")
+        for g in groups:
+            yield collate([self[i] for i in g])

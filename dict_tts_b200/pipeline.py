@@ -41,7 +41,12 @@ class TextToWav:
         if out.get("values") is None and "keys" in out:
             out["values"] = out["keys"]
         if "keys" not in out:                     # bank batch: the (Lk, Lp) the collater would pad to, from host offsets
-            out["_dims"] = self.acoustic.bank.batch_dims(batch["dict_ids"])
+            local = batch.get("dict_bank")        # ragged batch: its own un-padded bank travels with it
+            if local is not None:
+                out["_dims"] = local.batch_dims(batch["dict_ids"])
+                out["_bank"] = local.to(self.device, non_blocking=True)
+            else:
+                out["_dims"] = self.acoustic.bank.batch_dims(batch["dict_ids"])
         return out
 
     def run_device(self, dev: Dict[str, torch.Tensor], record=None):
@@ -52,6 +57,8 @@ class TextToWav:
                 t = eng.text_encode(dev["word_tokens"], dev.get("pron_modified"), dev["keys"], dev["values"],
                                     dev["key_map"], dev["pinyin"], dev["pinyin_map"])
             else:                                 # GPU-resident dictionary bank: only ids cross the bus
+                if "_bank" in dev:
+                    eng.set_dict_bank(dev["_bank"])
                 t = eng.text_encode_bank(dev["word_tokens"], dev.get("pron_modified"), dev["dict_ids"], *dev["_dims"])
             if record:
                 record("text_encode")
@@ -108,7 +115,7 @@ class TextToWav:
                 if free[i] is not None:
                     copy.wait_event(free[i])
                 d = self.to_device(batch)
-                for t in d.values():
+                for t in list(d.values()) + (d["_bank"].tensors() if "_bank" in d else []):
                     if torch.is_tensor(t):
                         t.record_stream(compute)      # allocated on the copy stream, consumed on the compute stream
                 ev = torch.cuda.Event()
