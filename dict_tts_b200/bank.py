@@ -63,10 +63,9 @@ class DictBank:
         for b in range(B):
             for t in range(Tw):
                 tok = int(wt[b, t])
-                if tok == 0:
-                    continue
-                if tok == 1:                                   # BOS / EOS (utils/text_encoder.py: EOS = 1)
-                    ids[b, t] = BOS_EOS
+                if tok <= 1:                                   # padding or BOS / EOS (utils/text_encoder.py: EOS = 1):
+                    if bool((key_map[b, t] == 1).all()):       # the row the collater adds (keys 0, key_map 1, pinyin_map 1)
+                        ids[b, t] = BOS_EOS                    # ... wherever THIS batch has it (dataset_utils.py:286-296)
                     continue
                 nz = (keys[b, t].abs().sum(-1) != 0).nonzero()
                 L = int(nz.max()) + 1 if nz.numel() else 1
@@ -155,10 +154,12 @@ class DictBank:
 
 def ids_from_words(words: List[List[str]], word_to_id: Dict[str, int], Tw: int) -> torch.Tensor:
     """dict_ids for a batch of word lists as the test-set reader holds them (['<BOS>', c1, ..., '<EOS>']): entry
-    index = word id in word_set.json order, unknown characters map to <UNK> = 2 (dataset_utils.py:312-315)."""
+    index = word id in word_set.json order, unknown characters map to <UNK> = 2 (dataset_utils.py:312-315).  Rows are
+    the ones the reference collater builds: BOS_EOS in column 0 and column Tw-1 of every utterance, PAD (all-zero row)
+    everywhere else outside the characters -- see data.collate_dict_ids."""
     ids = torch.full((len(words), Tw), PAD, dtype=torch.long)
+    ids[:, 0] = ids[:, Tw - 1] = BOS_EOS
     for b, ws in enumerate(words):
-        ids[b, 0] = ids[b, len(ws) - 1] = BOS_EOS
         for t, w in enumerate(ws[1:-1], start=1):
             ids[b, t] = word_to_id.get(w, 2)
     return ids

@@ -87,6 +87,20 @@ def pad_3d(seqs: List[torch.Tensor], pad=0) -> torch.Tensor:
     return out
 
 
+def collate_dict_ids(char_ids: List[torch.Tensor]) -> torch.Tensor:
+    """Per-utterance bank ids of the characters (no BOS/EOS) -> ``dict_ids [B, Tw]`` naming exactly the rows the
+    reference collater builds (dataset_utils.py:286-296): it pads the per-character tensors with zeros to the longest
+    utterance and only THEN adds one row in front and one behind, so column 0 and column Tw-1 of EVERY utterance are
+    the (keys 0, key_map 1, pinyin 0, pinyin_map 1) row (-1) and the EOS position of a shorter utterance is an
+    all-zero row (-2) like the rest of its padding."""
+    n = max(int(c.numel()) for c in char_ids)
+    ids = torch.full((len(char_ids), n + 2), -2, dtype=torch.long)
+    ids[:, 0] = ids[:, n + 1] = -1
+    for b, c in enumerate(char_ids):
+        ids[b, 1:1 + c.numel()] = c
+    return ids
+
+
 class DictTTSTestSet:
     def __init__(self, hp: Dict, prefix: str = "test", data_dir: Optional[str] = None):
         self.hp = hp
@@ -149,7 +163,7 @@ class DictTTSTestSet:
         if "pron_modified" in item:
             s["pron_modified"] = torch.LongTensor(item["pron_modified"])
         if getattr(self, "bank", None) is not None:                  # characters named by bank id
-            s["dict_ids"] = torch.LongTensor([-1] + [self.word_to_id.get(w, 2) for w in item["words"][1:-1]] + [-1])
+            s["dict_ids"] = torch.LongTensor([self.word_to_id.get(w, 2) for w in item["words"][1:-1]])
             return s
         if self.ragged:                                              # word ids only; collate_ragged reads the entries
             s["word_ids"] = [self.word_to_id.get(w, 2) for w in item["words"][1:-1]]
@@ -179,7 +193,7 @@ class DictTTSTestSet:
         b["pron_modified"] = (pad_1d([s["pron_modified"] for s in samples]) if "pron_modified" in samples[0]
                               else None)
         if "dict_ids" in samples[0]:
-            b["dict_ids"] = pad_1d([s["dict_ids"] for s in samples], pad=-2)
+            b["dict_ids"] = collate_dict_ids([s["dict_ids"] for s in samples])
             return b
         b["keys"] = F.pad(pad_3d([s["keys"] for s in samples]), (0, 0, 0, 0, 1, 1))
         b["values"] = F.pad(pad_3d([s["values"] for s in samples]), (0, 0, 0, 0, 1, 1))
@@ -208,7 +222,7 @@ class DictTTSTestSet:
                                         pinyin=[self._pinyin_index[p] for p in e["pinyin"]],
                                         pinyin_map=e["pinyin_map"]))
                 row.append(local[wid])
-            rows.append(torch.LongTensor(row + [-1]))
+            rows.append(torch.LongTensor(row[1:]))
         stripped = [{k: v for k, v in s.items() if k != "word_ids"} for s in samples]
         for s, r in zip(stripped, rows):
             s["dict_ids"] = r

@@ -198,3 +198,38 @@ def test_device_after_infer_matches_host_semantics():
     got_bank = eng.pron_tokens(pron_attn, dict_ids=ids).cpu()
     assert torch.equal(got_bank, want)
     eng.close()
+
+
+def test_ragged_batch_equals_padded_batch(exp):
+    """a batch collated ragged (batch-local bank of its distinct characters + dict_ids naming the rows
+    the reference collater builds) gives bit for bit what the reference-shaped padded batch gives -- including the
+    collater's quirk that the appended (key_map 1) row sits in column Tw-1 of every utterance."""
+    from dict_tts_b200.engine import DictTTSEngine
+    from dict_tts_b200.pipeline import TextToWav
+    padded = next(DictTTSTestSet(exp["hparams"]).batches(max_sentences=4))
+    ds = DictTTSTestSet(exp["hparams"])
+    ds.ragged = True
+    ragged = next(ds.batches(max_sentences=4))
+    assert len(set(padded["word_lengths"].tolist())) > 1            # unequal lengths: the quirk is exercised
+    eng = DictTTSEngine(synth.make_acoustic_state_dict(1234))
+    ref = eng.text_encode(padded["word_tokens"], padded["pron_modified"], padded["keys"], padded["values"],
+                          padded["key_map"], padded["pinyin"], padded["pinyin_map"])
+    eng.set_dict_bank(ragged["dict_bank"])
+    got = eng.text_encode_bank(ragged["word_tokens"], ragged["pron_modified"], ragged["dict_ids"])
+    for k in ("word_encoder_out", "dict_attn", "pron_attn", "dur", "dur_int", "ilens"):
+        assert torch.equal(ref[k], got[k]), k
+    eng.close()
+    # through the public pipeline: the ragged batch carries its own bank (pinned), serial and streamed calls agree
+    pipe = TextToWav(synth.make_acoustic_state_dict(1234), synth.make_vocoder_state_dict(4321))
+    torch.manual_seed(7)
+    T4 = (padded["mel2word"].shape[1] + 3) // 4 * 4
+    z = torch.randn(padded["word_tokens"].shape[0], 16, T4 // 4)
+    want = pipe.synthesize(dict(padded, z_p=z)).clone()
+    rb = dict(ragged, z_p=z, dict_bank=ragged["dict_bank"].pin_memory())
+    got_wav = pipe.synthesize(rb).clone()
+    assert torch.equal(want, got_wav)
+    streamed = [w.clone() for w in pipe.synthesize_stream(iter([rb, rb]))]
+    assert torch.equal(streamed[0], want) and torch.equal(streamed[1], want)
+    h2d_ragged = sum(t.numel() * t.element_size() for t in rb["dict_bank"].tensors()[:1]) + rb["dict_ids"].numel() * 8
+    assert h2d_ragged < padded["keys"].numel() * 4
+    pipe.close()

@@ -239,4 +239,4 @@ def test_dict_ids_from_words():
     from dict_tts_b200.bank import ids_from_words
     w2i = {"<pad>": 0, "<EOS>": 1, "<UNK>": 2, "<BOS>": 3, "a": 4, "b": 5}
     ids = ids_from_words([["<BOS>", "a", "b", "<EOS>"], ["<BOS>", "zz", "<EOS>"]], w2i, 5)
-    assert ids.tolist() == [[-1, 4, 5, -1, -2], [-1, 2, -1, -2, -2]]
+    assert ids.tolist() == [[-1, 4, 5, -2, -1], [-1, 2, -2, -2, -1]]     # column 0 and Tw-1: the collater's added rows
