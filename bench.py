@@ -28,9 +28,9 @@ from dict_tts_b200.weights import drop_dead, fold_weight_norm, pack_arena  # noq
 
 # algorithmic work model (checked against torch FlopCounterMode on the reference)
 VOCODER_FLOP_PER_FRAME = 614.1e6
-TC_CONV_DRAM_BYTES_PER_LAUNCH = 1.253e9   # measured (ncu), see profiles/r01_launches_bench_aggregate.txt
+TC_CONV_DRAM_BYTES_PER_LAUNCH = 1.240e9   # measured (ncu): 95.5 GB over the 77 launches, profiles/r01_vocoder_dram_agg.txt
 WORKLOAD = dict(B=60, min_chars=12, max_chars=20, max_frames=400, Lk_cap=96)
-CPU_SAMPLE_UTTS = 2
+CPU_SAMPLE_UTTS = 30      # ~10 k of the batch's 20.7 k frames: 10-20 s of host work for the two timed passes
 
 
 def load_peaks():
@@ -320,8 +320,8 @@ def main():
     roofline = dict(bound="tensor", kernel="%s, HiFi-GAN stack, %d launches/step" % (kname, n_voc_launch),
                     achieved=achieved, peak=peaks["tflops"], unit="TFLOP/s", frac=achieved / peaks["tflops"],
                     traffic=(TC_CONV_DRAM_BYTES_PER_LAUNCH if args.vocoder_precision == 3 else None),
-                    traffic_source="profiles/r01_launches_bench_aggregate.txt (ncu dram__bytes_read+write, average over "
-                                   "the 77 vocoder launches of one step)",
+                    traffic_source="profiles/r01_vocoder_dram_agg.txt (ncu dram__bytes_read+write, average over the 77 "
+                                   "tc_conv_kernel launches of one vocode pass; algorithmic: 1.245 GB)",
                     peak_source=peaks["source"] + " bf16 dense (sustained)",
                     avg_launch_ms=stage_ms["vocode"] / n_voc_launch,
                     flop_per_launch=padded_frames * VOCODER_FLOP_PER_FRAME / n_voc_launch)

@@ -6,7 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdtts.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 DTTS_MAX_UPS = 8
 DTTS_MAX_RB = 4
 
@@ -19,7 +19,7 @@ class AcousticDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "hidden", "n_heads", "enc_layers", "ffn_kernel", "ffn_filter", "dict_dim", "word_size", "pinyin_size",
         "dur_layers", "dur_kernel", "dur_chans", "frames_multiple", "latent", "dec_layers", "dec_kernel",
-        "flow_hidden", "flow_kernel", "flow_blocks", "flow_layers", "n_mel", "language_zh", "precision")]
+        "flow_hidden", "flow_kernel", "flow_blocks", "flow_layers", "n_mel", "language_zh", "precision", "s2pa_route")]
 
 
 class VocoderDesc(C.Structure):

@@ -45,6 +45,7 @@ struct dtts_acoustic {
   EncoderW sem, lin;
   ConvW s2pa_q, s2pa_kT, s2pa_v, s2pa_o;
   TcConvW t_s2pa_q, t_s2pa_kT, t_s2pa_v, t_s2pa_o;
+  TcConvW t_s2pa_kv;              // s2pa_route = 1: [W_k ; W_v] side by side, dict_dim -> 2 * hidden (block 0 = k, block 1 = v)
   TcConvW t_gpre;                 // g_pre_net as a stride-1 k=3 convolution over the 4x space-to-depth input (C' = 4H)
   TcConvW t_out;                  // out_proj with C_out zero-padded to a multiple of 32
   int out_pad = 0;
@@ -414,6 +415,10 @@ extern "C" int dtts_acoustic_create(const dtts_acoustic_desc* d, const float* ar
     return fail(DTTS_ERR_BAD_SHAPE, "unsupported acoustic configuration");
   if (d->precision != 0 && d->precision != 1)
     return fail(DTTS_ERR_BAD_ARG, "acoustic precision must be 0 (fp32 FMA) or 1 (tcgen05, bf16 hi/lo split)");
+  if (d->s2pa_route != 0 && d->s2pa_route != 1)
+    return fail(DTTS_ERR_BAD_ARG, "s2pa_route must be 0 (folded streaming pass) or 1 (K/V projection GEMM)");
+  if (d->s2pa_route == 1 && (d->precision != 1 || d->hidden % 32 || d->dict_dim % 32))
+    return fail(DTTS_ERR_BAD_ARG, "s2pa_route = 1 runs on tcgen05: it needs precision = 1, hidden and dict_dim % 32 == 0");
   DTTS_TRY(arch_check());
   dtts_acoustic* h = new dtts_acoustic();
   h->d = *d;
@@ -428,6 +433,7 @@ extern "C" int dtts_acoustic_create(const dtts_acoustic_desc* d, const float* ar
   if (rc != DTTS_OK) { delete h; return rc; }
   if (h->precision) {
     h->tc_cap = 2 * total + (1 << 20);               // two 16-bit planes per weight
+    if (d->s2pa_route == 1) h->tc_cap += (size_t)4 * d->hidden * d->dict_dim + 256;   // second copy of W_k, W_v
     cudaError_t e = cudaMalloc((void**)&h->tc_pool, h->tc_cap * sizeof(tc16));
     if (e == cudaSuccess) e = tc_conv_init();
     if (e != cudaSuccess) {
@@ -459,6 +465,12 @@ extern "C" int dtts_acoustic_create(const dtts_acoustic_desc* d, const float* ar
     DTTS_TRY(tc_pack1(h, a + ".q_transform", false, H, H, 1, 0, &h->t_s2pa_q, s));
     DTTS_TRY(tc_pack1(h, a + ".v_transform", false, H, D, 1, 0, &h->t_s2pa_v, s));
     DTTS_TRY(tc_pack1(h, a + ".output_transform", false, H, H, 1, 0, &h->t_s2pa_o, s));
+    if (d->s2pa_route == 1) {
+      const float* wkv[2] = {h->tab.get(a + ".k_transform.weight", (uint64_t)H * D),
+                             h->tab.get(a + ".v_transform.weight", (uint64_t)H * D)};
+      if (!wkv[0] || !wkv[1]) return DTTS_ERR_MISSING_WEIGHT;
+      DTTS_TRY(tc_pack(h, wkv, 2, nullptr, H, D, 1, 0, H, &h->t_s2pa_kv, s));      // N = H: one block per projection
+    }
     for (int i = 0; i < d->dur_layers; ++i) {
       ConvW c;
       const std::string q = "dur_predictor.conv." + std::to_string(i);
@@ -571,6 +583,10 @@ extern "C" uint64_t dtts_text_workspace_bytes(const dtts_acoustic* h, int32_t B,
   add(bt * H); add(bt * D); add(bt * Lk); add(bt * D); add(bt * H); add(bt * H);  // q, qk, weights, ctx, ctxv, context
   add(bt * H); add(bt * C); add(bt * C);                                        // dur_in, d1, d2
   if (h->precision) n += 4 * ws_round((size_t)B * (F > D ? F : D) * tc_rows(Tw) * sizeof(tc16));   // 2 operand-plane sets
+  if (h->d.s2pa_route == 1) {                                                  // gloss-token planes (hi, lo) + k|v
+    n += 2 * ws_round((size_t)B * D * tc_rows(Tw * Lk) * sizeof(tc16));
+    add(bt * Lk * 2 * H);
+  }
   return n + 4096;
 }
 
@@ -619,6 +635,17 @@ static int text_encode_impl(dtts_acoustic* h, const dtts_text_in* in, const dtts
     tcr.take(bump, 2, (size_t)B * (F > D ? F : D) * tc_rows(Tw));
     tc = &tcr;
   }
+  const bool gemm_route = d.s2pa_route == 1;
+  if (gemm_route && row_off)
+    return fail(DTTS_ERR_BAD_ARG, "s2pa_route = 1 (K/V projection GEMM) is not available with the dictionary bank");
+  Planes KP;                                                   // gloss tokens as operand planes: C = D, T = Tw * Lk
+  float* kv = nullptr;
+  if (gemm_route) {
+    KP.cap = (size_t)B * D * tc_rows(Tw * Lk);
+    KP.hi = bump.take<tc16>(KP.cap);
+    KP.lo = bump.take<tc16>(KP.cap);
+    kv = bump.take<float>(bt * Lk * 2 * H);
+  }
   if (!bump.ok) return fail(DTTS_ERR_WORKSPACE_TOO_SMALL, "dtts_text_encode: workspace too small");
   Launcher L;
   L.stream = (cudaStream_t)stream;
@@ -630,6 +657,26 @@ static int text_encode_impl(dtts_acoustic* h, const dtts_text_in* in, const dtts
   L(embed_tokens(in->word_tokens_dev, h->word_emb, sqrtf((float)H), B, Tw, H, d.word_size, x, seq_mask, tok_mask, lens,
                  s));
   run_encoder(h, h->sem, x, hb, qkv, att, ffn, seq_mask, B, Tw, L, tc);       // semantic encoder -> hb
+  if (gemm_route) {
+    // S2PA as written (dict_encoder.py:40-58): q = W_q x * D^-1/2; k = W_k keys and v = W_v values for every gloss
+    // token -- the [B*Tw*Lk, D] x [D, 2H] "dict-attention GEMM" on tcgen05 -- then scores / softmax / weighted sum.
+    const int TL = Tw * Lk;
+    TcRun::Epi eq;
+    eq.alpha = 1.f / sqrtf((float)D);
+    tc->conv_nct(tc->P[0], h->t_s2pa_q, q, Tw, 1, 0, eq);                         // P[0] = last LN of the encoder
+    const long gbs = (long)TL * D;                                                // gloss row (b, t*Lk + l) = D floats
+    tc->stage(KP, in->keys_dev, gbs, 1, D, D, TL);
+    if (in->values_dev == in->keys_dev) {
+      tc->conv(KP, h->t_s2pa_kv, 0, 2, kv, (long)2 * H * TL, TL, 1, TL, 1, 0, TcRun::Epi());
+    } else {
+      tc->conv(KP, h->t_s2pa_kv, 0, 1, kv, (long)2 * H * TL, TL, 1, TL, 1, 0, TcRun::Epi());
+      tc->stage(KP, in->values_dev, gbs, 1, D, D, TL);
+      tc->conv(KP, h->t_s2pa_kv, 1, 1, kv + (size_t)H * TL, (long)2 * H * TL, TL, 1, TL, 1, 0, TcRun::Epi());
+    }
+    L(s2pa_attend(kv, q, in->key_map_dev, B, Tw, Lk, H, weights, out->dict_attn_dev, ctxv, s));
+    tc->stage_nct(tc->P[0], ctxv, H, Tw);
+    tc->conv_nct(tc->P[0], h->t_s2pa_o, context, Tw, 1, 0, TcRun::Epi());
+  } else {
   // S2PA (dict_encoder.py:32-66), folded: logits = keys . (W_k^T (W_q x) * D^-1/2)
   if (tc) {
     TcRun::Epi ek;
@@ -652,6 +699,7 @@ static int text_encode_impl(dtts_acoustic* h, const dtts_text_in* in, const dtts
     L(launch_conv1d_f32(conv_params(ctx, Tw, h->s2pa_v, 0, H, ctxv, Tw, 1, 1, 0), B, s));
     L(launch_conv1d_f32(conv_params(ctxv, Tw, h->s2pa_o, 0, H, context, Tw, 1, 1, 0), B, s));
   }
+  }   // folded route
   L(dict_maxes(in->key_map_dev, bt * Lk, in->pinyin_map_dev, bt * Lp, maxes, s));
   // x2 = context * x_mask + pron   (written into x, the input of the linguistic encoder)
   L(s2pa_pron(weights, in->key_map_dev, in->pinyin_dev, in->pinyin_map_dev, in->pron_modified_dev, maxes,

@@ -45,6 +45,10 @@ cudaError_t self_attention(const float* q, const float* k, const float* v, const
 cudaError_t s2pa_stream(const float* keys, const float* values, const float* key_map, const float* qk, int B, int Tw,
                         int Lk, int D, float* weights, float* align, float* ctx, cudaStream_t s,
                         const int64_t* row_off = nullptr, const int32_t* row_len = nullptr);
+// S2PA over projected rows (s2pa_route = 1): kv [B][2H][Tw*Lk] (k | v), q [B][H][Tw] scaled; same outputs as
+// s2pa_stream with ctx [B,H,Tw] already in the projected space (only W_o remains).
+cudaError_t s2pa_attend(const float* kv, const float* q, const float* key_map, int B, int Tw, int Lk, int H,
+                        float* weights, float* align, float* ctx, cudaStream_t s);
 // GPU-resident dictionary bank: per-batch key_map / pinyin / pinyin_map in the collater's padded
 // layout plus the row window of each character in the keys / values bank.  *err != 0: an id or a length was out of range.
 cudaError_t dict_bank_gather(const int64_t* ids, const int64_t* tok_off, const int64_t* pin_off,

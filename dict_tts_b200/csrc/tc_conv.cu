@@ -822,11 +822,21 @@ __global__ void tc_to_planes_kernel(const float* __restrict__ x, long bs, long c
     return;
   }
   uint32_t hw[4], lw[4];
+  if (cs == 1 && ((bs | ts) & 3) == 0 && (((uintptr_t)x) & 15) == 0) {
+    // channels-last source (e.g. the [.., dict_dim] gloss rows of S2PA): the 8 channels of a slab are 32 contiguous bytes
+    const float4* src = reinterpret_cast<const float4*>(x + (size_t)b * bs + (size_t)t * ts + (size_t)sl * 8);
+    const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
+    split2(leaky(v0.x, slope), leaky(v0.y, slope), fmt, hw[0], lw[0]);
+    split2(leaky(v0.z, slope), leaky(v0.w, slope), fmt, hw[1], lw[1]);
+    split2(leaky(v1.x, slope), leaky(v1.y, slope), fmt, hw[2], lw[2]);
+    split2(leaky(v1.z, slope), leaky(v1.w, slope), fmt, hw[3], lw[3]);
+  } else {
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const float a0 = leaky(x[(size_t)b * bs + (size_t)(sl * 8 + 2 * e) * cs + (size_t)t * ts], slope);
-    const float a1 = leaky(x[(size_t)b * bs + (size_t)(sl * 8 + 2 * e + 1) * cs + (size_t)t * ts], slope);
-    split2(a0, a1, fmt, hw[e], lw[e]);
+    for (int e = 0; e < 4; ++e) {
+      const float a0 = leaky(x[(size_t)b * bs + (size_t)(sl * 8 + 2 * e) * cs + (size_t)t * ts], slope);
+      const float a1 = leaky(x[(size_t)b * bs + (size_t)(sl * 8 + 2 * e + 1) * cs + (size_t)t * ts], slope);
+      split2(a0, a1, fmt, hw[e], lw[e]);
+    }
   }
   const size_t off = (dslab * rows + pad + t) * 8;
   *reinterpret_cast<uint4*>(hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);

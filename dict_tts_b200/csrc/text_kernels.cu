@@ -433,6 +433,80 @@ cudaError_t s2pa_stream(const float* keys, const float* values, const float* key
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// S2PA as the reference computes it (s2pa_route = 1, dict_encoder.py:40-58): kv [B][2H][Tw*Lk] holds k = W_k keys
+// (channels [0,H)) and v = W_v values (channels [H,2H)) of EVERY gloss token, written by the tcgen05 projection GEMM;
+// q [B][H][Tw] is W_q x * dict_dim^-1/2.  One block per character: logits[l] = k[:, l] . q, masked_fill(key_map == 0,
+// -1e9), softmax over l, ctx[c] = sum_l w[l] * v[c, l].  Reads are coalesced along l (the fastest axis of kv).
+__global__ void __launch_bounds__(256) s2pa_attend_kernel(const float* __restrict__ kv, const float* __restrict__ q,
+                                                           const float* __restrict__ key_map, int Tw, int Lk, int H,
+                                                           float* __restrict__ weights, float* __restrict__ align,
+                                                           float* __restrict__ ctx) {
+  extern __shared__ float sm[];
+  float* s_q = sm;            // [H]
+  float* s_w = sm + H;        // [Lk]
+  __shared__ float s_red[8];
+  const int bt = blockIdx.x;
+  const int b = bt / Tw, t = bt - b * Tw;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t TL = (size_t)Tw * Lk;
+  const float* kb = kv + (size_t)b * 2 * H * TL + (size_t)t * Lk;      // k[c][l] = kb[c*TL + l]
+  const float* vb = kb + (size_t)H * TL;
+  for (int c = tid; c < H; c += 256) s_q[c] = q[((size_t)b * H + c) * Tw + t];
+  __syncthreads();
+  const float* km = key_map + (size_t)bt * Lk;
+  for (int l = tid; l < Lk; l += 256) {
+    float acc = 0.f;
+    for (int c = 0; c < H; ++c) acc = fmaf(__ldg(kb + (size_t)c * TL + l), s_q[c], acc);
+    s_w[l] = km[l] != 0.f ? acc : -1e9f;
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int l = tid; l < Lk; l += 256) mx = fmaxf(mx, s_w[l]);
+  mx = warp_max(mx);
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  mx = s_red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, s_red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int l = tid; l < Lk; l += 256) {
+    const float e = expf(s_w[l] - mx);
+    s_w[l] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) s_red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += s_red[i];
+  const float rs = 1.f / sum;
+  for (int l = tid; l < Lk; l += 256) {
+    const float w = s_w[l] * rs;
+    s_w[l] = w;
+    weights[(size_t)bt * Lk + l] = w;
+    align[((size_t)b * Lk + l) * Tw + t] = w;                 // [B,1,Lk,Tw]
+  }
+  __syncthreads();
+  // ctx[c] = sum_l w[l] * v[c][l]: one warp per channel, lanes along l
+  for (int c = warp; c < H; c += 8) {
+    float acc = 0.f;
+    for (int l = lane; l < Lk; l += 32) acc = fmaf(s_w[l], __ldg(vb + (size_t)c * TL + l), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) ctx[((size_t)b * H + c) * Tw + t] = acc;
+  }
+}
+
+cudaError_t s2pa_attend(const float* kv, const float* q, const float* key_map, int B, int Tw, int Lk, int H,
+                        float* weights, float* align, float* ctx, cudaStream_t s) {
+  const size_t smem = (size_t)(H + Lk) * sizeof(float);
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  s2pa_attend_kernel<<<B * Tw, 256, smem, s>>>(kv, q, key_map, Tw, Lk, H, weights, align, ctx);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Dictionary bank -> the small per-batch tensors of dict_msg, exactly as DictTTSDataset.collater pads them
 // (tasks/tts/dataset_utils.py:264-302): id >= 0: the entry's key_map / pinyin / pinyin_map, zero padded; id == -1
 // (BOS / EOS row): key_map 1, pinyin 0, pinyin_map 1 over the whole row; id == -2 (padding): zeros.  Also the row

@@ -50,9 +50,11 @@ class DictTTSEngine:
     """Acoustic model (text -> mel).  ``state_dict`` uses the reference checkpoint keys (weight-norm pairs allowed)."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: Optional[AcousticConfig] = None, device="cuda:0",
-                 arena: Optional[torch.Tensor] = None, table=None, precision: int = 1):
+                 arena: Optional[torch.Tensor] = None, table=None, precision: int = 1, s2pa_route: int = 0):
         """precision 0: every convolution on the fp32 FMA pipe (exact); 1 (default): dense convolutions on tcgen05 with
-        bf16 hi/lo split operands (3 MMAs per product, fp32-class accuracy)."""
+        bf16 hi/lo split operands (3 MMAs per product, fp32-class accuracy).
+        s2pa_route 0 (default): folded streaming S2PA; 1: K/V projection of every gloss token as one tcgen05 GEMM, as
+        the reference computes it (layers/dict_encoder.py:40-58) -- see dtts_acoustic_desc.s2pa_route."""
         if not torch.cuda.is_available():
             raise RuntimeError("DictTTSEngine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = binding.load()
@@ -66,7 +68,8 @@ class DictTTSEngine:
         desc = binding.AcousticDesc(c.hidden, c.n_heads, c.enc_layers, c.ffn_kernel, c.ffn_filter, c.dict_dim,
                                     c.word_size, c.pinyin_size, c.dur_layers, c.dur_kernel, c.dur_chans,
                                     c.frames_multiple, c.latent, c.dec_layers, c.dec_kernel, c.flow_hidden,
-                                    c.flow_kernel, c.flow_blocks, c.flow_layers, c.n_mel, int(c.language_zh), int(precision))
+                                    c.flow_kernel, c.flow_blocks, c.flow_layers, c.n_mel, int(c.language_zh), int(precision),
+                                    int(s2pa_route))
         tab, self._keep = binding.make_table(table)
         self.handle = C.c_void_p()
         with torch.cuda.device(self.device):

@@ -19,12 +19,13 @@ _INPUT_KEYS = ("word_tokens", "pron_modified", "keys", "values", "key_map", "pin
 class TextToWav:
     def __init__(self, acoustic_sd, vocoder_sd, acfg: Optional[AcousticConfig] = None,
                  vcfg: Optional[VocoderConfig] = None, device="cuda:0", arenas=None, vocoder_precision: int = 3,
-                 acoustic_precision: int = 1):
+                 acoustic_precision: int = 1, s2pa_route: int = 0):
         a_arena = a_table = v_arena = v_table = None
         if arenas is not None:
             (a_arena, a_table), (v_arena, v_table) = arenas
         self.device = torch.device(device)
-        self.acoustic = DictTTSEngine(acoustic_sd, acfg, device, a_arena, a_table, precision=acoustic_precision)
+        self.acoustic = DictTTSEngine(acoustic_sd, acfg, device, a_arena, a_table, precision=acoustic_precision,
+                                      s2pa_route=s2pa_route)
         self.vocoder = HifiGanEngine(vocoder_sd, vcfg, device, v_arena, v_table, precision=vocoder_precision)
         self.events = None
 

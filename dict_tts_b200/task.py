@@ -85,10 +85,23 @@ class B200DictTTSTask:
         task.test_start()
         outputs = []
         ds = DictTTSTestSet(hp, hp.get("test_set_name", "test"))
-        if hp.get("b200_dict_bank", True):                 # upload the dictionary once; batches then carry ids only
+        # dictionary features: "bank" (default) uploads dict_embed once, batches then carry ids only;
+        # "ragged": every batch carries an un-padded bank of its own distinct characters (§8f-4, for dictionaries that
+        # do not fit in HBM); "padded": the reference collater's [B,Tw,Lk,768] tensors.  b200_dict_bank=False = "padded".
+        mode = str(hp.get("b200_dict_mode", "bank" if hp.get("b200_dict_bank", True) else "padded"))
+        if mode not in ("bank", "ragged", "padded"):
+            raise ValueError("b200_dict_mode must be bank, ragged or padded")
+        if int(hp.get("b200_s2pa_route", 0)) == 1:
+            mode = "padded"                                # the projection-GEMM route reads the collated tensors
+        if mode == "bank":
             task.model.set_dict_bank(ds.build_bank())
+        ds.ragged = mode == "ragged"
         bs = int(hp.get("b200_max_sentences", hp.get("max_valid_sentences", 1)) or 1)
-        for i, batch in enumerate(ds.batches(bs, rank, world)):
+        max_tokens = hp.get("b200_max_tokens")             # padded frames per batch and device, as max_tokens is upstream
+        for i, batch in enumerate(ds.batches(bs, rank, world, max_tokens=max_tokens,
+                                             deal=str(hp.get("b200_deal", "batches")))):
+            if batch.get("dict_bank") is not None:
+                task.model.set_dict_bank(batch["dict_bank"])
             outputs.extend(task.test_step(batch, i))
         task.test_end(outputs)
         if world > 1:
@@ -112,7 +125,9 @@ class B200DictTTSTask:
             dist.broadcast_object_list(meta, 0)
         table, numel, self.global_step = meta[0]
         dev_arena = broadcast_arena(arena, numel, self.device, rank, world)
-        self.model = DictTTSEngine(None, acfg, self.device, arena=dev_arena, table=table)
+        self.model = DictTTSEngine(None, acfg, self.device, arena=dev_arena, table=table,
+                                   precision=int(hp.get("b200_acoustic_precision", 1)),
+                                   s2pa_route=int(hp.get("b200_s2pa_route", 0)))
         return self.model
 
     def test_start(self):

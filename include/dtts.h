@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DTTS_ABI_VERSION 2
+#define DTTS_ABI_VERSION 3
 
 typedef enum dtts_status {
   DTTS_OK = 0,
@@ -59,6 +59,13 @@ typedef struct dtts_acoustic_desc {
   int32_t language_zh; /* 1: apply add_pron_rule (layers/utils.py:109-115) */
   int32_t precision;   /* dense convolutions (encoder QKV/O/FFN, S2PA projections, duration predictor, WaveNet stacks):
                           0 = fp32 FMA pipe (exact), 1 = tcgen05 with bf16 hi/lo split operands (3 MMAs, fp32-class) */
+  int32_t s2pa_route;  /* S2PAAttention (layers/dict_encoder.py:32-66) over the gloss tokens:
+                          0 = folded streaming pass: logits = keys.(W_k^T q), context = W_o W_v (sum_l w_l values_l) --
+                              algebraically identical, 0.3 % of the FLOPs, one HBM pass over keys/values (default);
+                          1 = as the reference computes it: k = W_k keys, v = W_v values for EVERY gloss token as one
+                              [B*Tw*Lk, dict_dim] x [dict_dim, 2*hidden] GEMM on tcgen05 (needs precision = 1), then
+                              per-character scores / softmax / weighted sum over the projected rows.  Not available
+                              with the dictionary bank (dtts_text_encode_bank). */
 } dtts_acoustic_desc;
 
 /* HiFi-GAN V1 generator description (egs/egs_bases/tts/vocoder/hifigan.yaml:3-10). */

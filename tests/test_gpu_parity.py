@@ -17,13 +17,14 @@ from tests.cases import (ACOUSTIC_CASES, ACOUSTIC_SEED, TOL_MEL_MAXABS, TOL_WAV_
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=[0, 1], ids=["fp32", "tcgen05"])
+@pytest.fixture(scope="module", params=[(0, 0), (1, 0), (1, 1)], ids=["fp32", "tcgen05", "tcgen05-s2pa_gemm"])
 def acoustic(request):
     """Both acoustic precisions: 0 = every convolution on the fp32 FMA pipe, 1 = dense convolutions on tcgen05 with
-    bf16 hi/lo split operands (the default of the engine)."""
+    bf16 hi/lo split operands (the default of the engine); and, on tcgen05, both S2PA routes: 0 = folded streaming pass,
+    1 = K/V projection of every gloss token as one GEMM (dtts_acoustic_desc.s2pa_route)."""
     from dict_tts_b200.engine import DictTTSEngine
     sd = synth.make_acoustic_state_dict(ACOUSTIC_SEED)
-    eng = DictTTSEngine(sd, precision=request.param)
+    eng = DictTTSEngine(sd, precision=request.param[0], s2pa_route=request.param[1])
     yield eng, fold_weight_norm(sd)
     eng.close()
 
@@ -173,3 +174,42 @@ def test_bad_arguments_raise(acoustic, vocoder):
     v, _ = vocoder
     with pytest.raises(ValueError):
         v(torch.zeros(1, 10, 79))
+
+
+def test_s2pa_gemm_route_agrees_with_folded_route_and_oracle():
+    """dtts_acoustic_desc.s2pa_route = 1 (k = W_k keys, v = W_v values for every gloss token on tcgen05, then scores /
+    softmax / weighted sum -- dict_encoder.py:40-58 as written) against route 0 and the oracle, with values != keys
+    (two staging passes + two projection launches) and with values aliasing keys (one GEMM for k | v)."""
+    from dict_tts_b200.bank import DictBank
+    from dict_tts_b200.engine import DictTTSEngine
+    sd = synth.make_acoustic_state_dict(ACOUSTIC_SEED)
+    W = fold_weight_norm(sd)
+    folded = DictTTSEngine(sd, precision=1, s2pa_route=0)
+    gemm = DictTTSEngine(sd, precision=1, s2pa_route=1)
+    batch = synth.make_batch(seed=91, B=3, min_chars=2, max_chars=8, max_frames=48, Lk_cap=72, pron_modified_p=0.1)
+    g = torch.Generator().manual_seed(5)
+    other = batch["values"] + 0.1 * torch.randn(batch["values"].shape, generator=g) * (batch["values"] != 0)
+    for values in (other, None):
+        vals = batch["keys"] if values is None else values
+        a = folded.text_encode(batch["word_tokens"], batch["pron_modified"], batch["keys"], values, batch["key_map"],
+                               batch["pinyin"], batch["pinyin_map"])
+        b = gemm.text_encode(batch["word_tokens"], batch["pron_modified"], batch["keys"], values, batch["key_map"],
+                             batch["pinyin"], batch["pinyin_map"])
+        with torch.no_grad():
+            enc, dict_attn, pron_attn, _ = O.text_encode(W, AcousticConfig(), batch["word_tokens"], batch["pron_modified"],
+                                                         batch["keys"], vals, batch["key_map"], batch["pinyin"],
+                                                         batch["pinyin_map"])
+        ref = dict(word_encoder_out=enc, dict_attn=dict_attn, pron_attn=pron_attn)
+        for k, tol in (("word_encoder_out", 2e-4), ("dict_attn", 1e-5), ("pron_attn", 1e-5), ("dur", 1e-4)):
+            assert (a[k] - b[k]).abs().max().item() < tol, (k, "route 0 vs 1")
+            if k in ref:
+                assert (b[k].cpu() - ref[k]).abs().max().item() < tol, (k, "route 1 vs oracle")
+        assert torch.equal(a["ilens"], b["ilens"])
+    bank, ids = DictBank.from_batch(batch)
+    gemm.set_dict_bank(bank)
+    with pytest.raises(RuntimeError, match="dictionary bank"):
+        gemm.text_encode_bank(batch["word_tokens"], batch["pron_modified"], ids)
+    folded.close()
+    gemm.close()
+    with pytest.raises(RuntimeError, match="s2pa_route"):
+        DictTTSEngine(sd, precision=0, s2pa_route=1)

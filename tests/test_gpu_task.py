@@ -233,3 +233,37 @@ def test_ragged_batch_equals_padded_batch(exp):
     h2d_ragged = sum(t.numel() * t.element_size() for t in rb["dict_bank"].tensors()[:1]) + rb["dict_ids"].numel() * 8
     assert h2d_ragged < padded["keys"].numel() * 4
     pipe.close()
+
+
+def test_infer_entry_point_dict_modes_agree(exp):
+    """The three ways the dictionary features reach the engine -- GPU-resident bank (default), ragged per-batch bank,
+    the reference collater's padded tensors -- write identical waveforms and pinyin tokens; so does the reference's
+    own rank dealing (deal=reference) up to the order of the rows."""
+    from dict_tts_b200 import run
+    outs = {}
+    cwd = os.getcwd()
+    os.chdir(exp["root"])
+    try:
+        for mode, extra in (("bank", ""), ("ragged", ""), ("padded", ""), ("bank", ",b200_deal=reference")):
+            tag = mode + ("_ref" if extra else "")
+            torch.manual_seed(1234)
+            run.main(["--exp_name", exp["exp"], "--infer", "--hparams",
+                      f"b200_max_sentences=3,gen_dir_name=m_{tag},b200_dict_mode={mode}{extra}"])
+            gen = os.path.join(exp["work_dir"], f"generated_3000_m_{tag}")
+            with open(os.path.join(gen, "meta.csv")) as f:
+                rows = {r["item_name"]: r for r in csv.DictReader(f)}
+            outs[tag] = {n: (r["pinyin_tokens"], _read_wav(os.path.join(gen, "wavs", r["wav_fn_pred"] + ".wav"))[1])
+                         for n, r in rows.items()}
+    finally:
+        os.chdir(cwd)
+    assert len(outs["bank"]) == exp["n_items"]
+    for tag in ("ragged", "padded"):
+        assert outs[tag].keys() == outs["bank"].keys()
+        for n, (tok, pcm) in outs["bank"].items():
+            assert outs[tag][n][0] == tok, (tag, n)
+            assert np.array_equal(outs[tag][n][1], pcm), (tag, n)
+    # reference dealing groups the utterances differently (natural order, not longest-first): the noise z and the
+    # padding differ, so only the discrete outputs are comparable
+    assert outs["bank_ref"].keys() == outs["bank"].keys()
+    for n, (tok, _) in outs["bank"].items():
+        assert outs["bank_ref"][n][0] == tok

@@ -23,7 +23,7 @@ def main(path, first_kernel="embed"):
             scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
             per_id[i]["rd" if "read" in m else "wr"] = v * scale
     rows = [per_id[i] for i in order]
-    idx = [i for i, x in enumerate(rows) if first_kernel in x["name"]]
+    idx = [] if first_kernel == "ALL" else [i for i, x in enumerate(rows) if first_kernel in x["name"]]
     start = idx[-1] if idx else 0
     agg, tot = {}, 0.0
     for r in rows[start:]:

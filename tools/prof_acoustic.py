@@ -13,8 +13,9 @@ from dict_tts_b200.engine import DictTTSEngine  # noqa: E402
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=2)
+    ap.add_argument("--s2pa-route", type=int, default=0, help="1: K/V projection GEMM on tcgen05 (dtts.h s2pa_route)")
     a = ap.parse_args()
-    eng = DictTTSEngine(synth.make_acoustic_state_dict(1234))
+    eng = DictTTSEngine(synth.make_acoustic_state_dict(1234), s2pa_route=a.s2pa_route)
     b = synth.make_batch(seed=1234, B=60, min_chars=12, max_chars=20, max_frames=400, Lk_cap=96)
     dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in b.items()}
 
@@ -30,4 +31,11 @@ if __name__ == "__main__":
     once()
     e1.record()
     torch.cuda.synchronize()
-    print("acoustic cfg2: %.3f ms" % e0.elapsed_time(e1))
+    print("acoustic cfg2 (s2pa_route %d): %.3f ms" % (a.s2pa_route, e0.elapsed_time(e1)))
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    eng.text_encode(dev["word_tokens"], dev["pron_modified"], dev["keys"], dev["values"], dev["key_map"], dev["pinyin"],
+                    dev["pinyin_map"])
+    t1.record()
+    torch.cuda.synchronize()
+    print("text_encode cfg2 (s2pa_route %d): %.3f ms" % (a.s2pa_route, t0.elapsed_time(t1)))
