@@ -33,15 +33,19 @@ struct TcMode {
   int fmt = 1;        // 0: fp16, 1: bf16
   int a_planes = 2;   // activations: 1 = single rounding, 2 = hi + lo
   int w_planes = 2;   // weights:     1 = single rounding, 2 = hi + lo
+  int hybrid = 0;     // 1: layers with C_out >= 128 use ONE weight plane (there the second MMA costs time); narrower layers
+                      //    keep hi | lo stacked along N, where the second plane is free
   int mmas() const { return a_planes + w_planes - 1; }
 };
-// dtts_vocoder_desc.precision -> mode (1: bf16 3-MMA split, 2: bf16, 3: fp16 x fp16 hi/lo weights, 4: fp16)
+// dtts_vocoder_desc.precision -> mode (1: bf16 3-MMA split, 2: bf16, 3: fp16 x fp16 hi/lo weights, 4: fp16,
+// 5: fp16 x fp16, hi/lo weights only where C_out < 128)
 static inline TcMode tc_mode(int precision) {
   TcMode m;
   switch (precision) {
     case 2: m.fmt = 1; m.a_planes = 1; m.w_planes = 1; break;
     case 3: m.fmt = 0; m.a_planes = 1; m.w_planes = 2; break;
     case 4: m.fmt = 0; m.a_planes = 1; m.w_planes = 1; break;
+    case 5: m.fmt = 0; m.a_planes = 1; m.w_planes = 2; m.hybrid = 1; break;
     default: m.fmt = 1; m.a_planes = 2; m.w_planes = 2; break;
   }
   return m;
@@ -84,8 +88,9 @@ struct TcConvW {
   // operand mode -> plane arrangement of this layer
   void set_mode(const TcMode& m) {
     fmt = m.fmt;
-    stack = (m.w_planes == 2 && N <= 64) ? 1 : 0;
-    planes = stack ? 1 : m.w_planes;
+    const int wp = (m.hybrid && C_out >= 128) ? 1 : m.w_planes;
+    stack = (wp == 2 && N <= 64) ? 1 : 0;
+    planes = stack ? 1 : wp;
     pair = (!stack && m.a_planes == 1 && N >= 128 && tc_pair_enabled()) ? 1 : 0;
   }
 };

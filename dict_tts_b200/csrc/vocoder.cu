@@ -275,7 +275,7 @@ extern "C" int dtts_vocoder_create(const dtts_vocoder_desc* d, const float* aren
     if (u < 1 || k % u != 0 || (k - u) % 2 != 0)
       return fail(DTTS_ERR_BAD_SHAPE, "upsample kernel must be a multiple of its rate with even (k-u)");
   }
-  if (d->precision < 0 || d->precision > 4) return fail(DTTS_ERR_BAD_ARG, "vocoder precision must be 0..4");
+  if (d->precision < 0 || d->precision > 5) return fail(DTTS_ERR_BAD_ARG, "vocoder precision must be 0..5");
   DTTS_TRY(arch_check());
   dtts_vocoder* h = new dtts_vocoder();
   h->desc = *d;

@@ -77,7 +77,8 @@ typedef struct dtts_vocoder_desc {
   int32_t rb_kernels[DTTS_MAX_RB];
   int32_t rb_dilations[DTTS_MAX_RB][3];
   int32_t precision; /* 0 = fp32 FMA pipe; tcgen05 modes: 1 = bf16 hi/lo x hi/lo (3 MMAs, fp32-class accuracy),
-                        2 = bf16 (1 MMA), 3 = fp16 activations x fp16 hi/lo weights (2 MMAs), 4 = fp16 (1 MMA) */
+                        2 = bf16 (1 MMA), 3 = fp16 activations x fp16 hi/lo weights (2 MMAs), 4 = fp16 (1 MMA),
+                        5 = as 3, but layers with C_out >= 128 use one weight plane (1 MMA there; hi|lo stacked elsewhere) */
 } dtts_vocoder_desc;
 
 typedef struct dtts_acoustic dtts_acoustic; /* opaque */
