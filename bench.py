@@ -28,7 +28,7 @@ from dict_tts_b200.weights import drop_dead, fold_weight_norm, pack_arena  # noq
 
 # algorithmic work model (checked against torch FlopCounterMode on the reference)
 VOCODER_FLOP_PER_FRAME = 614.1e6
-TC_CONV_DRAM_BYTES_PER_LAUNCH = 1.240e9   # measured (ncu): 95.5 GB over the 77 launches, profiles/r01_vocoder_dram_agg.txt
+TC_CONV_DRAM_BYTES_PER_LAUNCH = 1.076e9   # measured (ncu): 82.9 GB over the 77 launches of a valid-length pass (95.5 GB full length)
 WORKLOAD = dict(B=60, min_chars=12, max_chars=20, max_frames=400, Lk_cap=96)
 CPU_SAMPLE_UTTS = 30      # ~10 k of the batch's 20.7 k frames: 10-20 s of host work for the two timed passes
 
@@ -328,7 +328,10 @@ def main():
     config["vocoder_precision"] = args.vocoder_precision
     config["acoustic_precision"] = args.acoustic_precision
     voc_s = stage_ms["vocode"] / 1e3
-    padded_frames = WORKLOAD["B"] * WORKLOAD["max_frames"]           # the vocoder computes padded frames too
+    # the vocoder is run up to each utterance's valid length (dtts_vocode_lens): algorithmic work = valid frames only
+    # (the ~1 frame of receptive-field margin it also computes per utterance is not counted)
+    padded_frames = frames
+    config["vocoder_frames"] = "valid frames + receptive-field margin (padded tail of the batch skipped)"
     achieved = padded_frames * VOCODER_FLOP_PER_FRAME / voc_s / 1e12
     n_voc_launch = 1 + 4 + 72 + (1 if args.vocoder_precision == 0 else 0)   # conv_post is a separate CUDA-core kernel on the TC path
     kname = {0: "conv1d_f32_kernel (fp32 FMA pipe)", 1: "tc_conv_kernel (tcgen05, bf16 hi/lo x hi/lo: 3 MMAs per product)",
@@ -338,8 +341,8 @@ def main():
     roofline = dict(bound="tensor", kernel="%s, HiFi-GAN stack, %d launches/step" % (kname, n_voc_launch),
                     achieved=achieved, peak=peaks["tflops"], unit="TFLOP/s", frac=achieved / peaks["tflops"],
                     traffic=(TC_CONV_DRAM_BYTES_PER_LAUNCH if args.vocoder_precision == 3 else None),
-                    traffic_source="profiles/r01_vocoder_dram_agg.txt (ncu dram__bytes_read+write, average over the 77 "
-                                   "tc_conv_kernel launches of one vocode pass; algorithmic: 1.245 GB)",
+                    traffic_source="profiles/r01_vocoder_lens_dram_agg.txt (ncu dram__bytes_read+write, average over the "
+                                   "77 tc_conv_kernel launches of one valid-length vocode pass; algorithmic: 1.08 GB)",
                     peak_source=peaks["source"] + " bf16 dense (sustained)",
                     avg_launch_ms=stage_ms["vocode"] / n_voc_launch,
                     flop_per_launch=padded_frames * VOCODER_FLOP_PER_FRAME / n_voc_launch)

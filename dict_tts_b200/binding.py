@@ -74,6 +74,7 @@ SYMBOLS = {
     "dtts_vocoder_destroy": (C.c_int, [_P]),
     "dtts_vocode_workspace_bytes": (_U64, [_P, _I, _I]),
     "dtts_vocode": (C.c_int, [_P, _P, _I, _I, _P, _P, _U64, _P]),
+    "dtts_vocode_lens": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _U64, _P]),
     "dtts_wav_to_pcm16": (C.c_int, [_P, _U64, _P, _P]),
     "dtts_pron_tokens": (C.c_int, [_P, _P, C.POINTER(DictBankStruct), _P, _I, _I, _I, _P, _P]),
     "dtts_vocoder_launch_count": (_U64, [_P]),

@@ -32,7 +32,9 @@ constexpr int kBarAFull = 0, kBarAEmpty = kBarAFull + kMaxAStages, kBarWFull = k
 constexpr int kTmemPtrOff = kNumBars * 8;                 // uint32: TMEM base address
 constexpr int kBiasOff = (kTmemPtrOff + 4 + 63) / 64 * 64;
 constexpr int kMaxBias = 2048;               // output channels of one launch (bias staged in shared memory)
-constexpr int kSmemHeader = kBiasOff + kMaxBias * 4;   // barriers + tmem ptr, then bias
+constexpr int kPrefOff = kBiasOff + kMaxBias * 4;      // ragged launches: int32 tile prefix [kMaxItems + 1], then limits [kMaxItems]
+constexpr int kMaxItems = TC_MAX_RAGGED_ITEMS;
+constexpr int kSmemHeader = kPrefOff + (2 * kMaxItems + 8) * 4;   // barriers + tmem ptr, bias, ragged tables
 constexpr int kSmemLimit = 227 * 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -191,22 +193,55 @@ __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
 // tile are then written by the same SM within a few microseconds and merge into full sectors in L2 instead of
 // reaching HBM as partial-sector read-modify-writes.  Row tiles past the end are dummies: they follow the weight
 // pipeline (the peers depend on it) but issue no MMAs and store nothing.
-struct TileCoord { int q0, g, b; bool dummy; };
-__device__ __forceinline__ TileCoord decode_unit(const TcConvParams& p, int it, int cluster_id, int nclusters, int rank) {
+struct TileCoord { int q0, g, b, lim; bool dummy; };   // lim: rows [0, lim) of item b are computed / stored by this launch
+// Row-tile schedule of a launch.  Uniform: every batch item has p.ntiles tiles.  Ragged (p.lens != null): item b has
+// ceil(lim_b / MT) tiles with lim_b = min(nq, lens[b] * len_mul + len_add); pref[] (shared memory) is the exclusive
+// prefix of the tile counts, so the persistent CTAs walk ONLY tiles that hold rows somebody needs.
+struct Sched {
+  const int* pref;     // [B + 1] in shared memory, null when uniform
+  const int* limv;     // [B] in shared memory
+  int nu, nrt;         // units per weight group, row tiles in total
+};
+// Each role walks its tiles in increasing order, so the batch item of a row tile is found by advancing a cursor
+// (no division / search on the per-tile path: for the short k = 3 tiles the tile decode of the MMA-issuing thread is on the
+// critical path).
+struct Cursor { int b = 0; uint32_t base = 0; };
+__device__ __forceinline__ TileCoord decode_unit(const TcConvParams& p, const Sched& sc, int it, int cluster_id,
+                                                 int nclusters, int rank, Cursor& cur) {
   TileCoord c;
   uint32_t step = (uint32_t)it, ph = 0;
   if (p.phases != 1) { step = (uint32_t)it / (uint32_t)p.phases; ph = (uint32_t)it - step * (uint32_t)p.phases; }
   const uint32_t unit = (uint32_t)cluster_id + step * (uint32_t)nclusters;
-  const uint32_t blk = unit / (uint32_t)p.nu, j = unit - blk * (uint32_t)p.nu;
+  uint32_t blk = 0, j = unit;
+  if (p.nblocks != 1) { blk = unit / (uint32_t)sc.nu; j = unit - blk * (uint32_t)sc.nu; }
   c.g = (int)(blk * (uint32_t)p.phases + ph);
   uint32_t rt = j * (uint32_t)p.csize + (uint32_t)rank;
-  const uint32_t nrt = (uint32_t)(p.ntiles * p.B);
+  const uint32_t nrt = (uint32_t)sc.nrt;
   c.dummy = rt >= nrt;
   if (c.dummy) rt = nrt - 1;
-  const uint32_t b = rt / (uint32_t)p.ntiles;
-  c.b = (int)b;
-  c.q0 = (int)(rt - b * (uint32_t)p.ntiles) * p.MT;
+  if (sc.pref) {
+    int b = cur.b;
+    if (rt < (uint32_t)sc.pref[b]) b = 0;                      // next weight group: the walk starts over
+    while (b + 1 < p.B && (uint32_t)sc.pref[b + 1] <= rt) ++b;   // largest b with pref[b] <= rt (empty items are skipped)
+    cur.b = b;
+    c.b = b;
+    c.q0 = (int)(rt - (uint32_t)sc.pref[b]) * p.MT;
+    c.lim = sc.limv[b];
+  } else {
+    const uint32_t nt = (uint32_t)p.ntiles;
+    if (rt < cur.base) { cur.b = 0; cur.base = 0; }
+    while (rt >= cur.base + nt) { cur.base += nt; ++cur.b; }
+    c.b = cur.b;
+    c.q0 = (int)(rt - cur.base) * p.MT;
+    c.lim = p.nq;
+  }
   return c;
+}
+// 128-row sub-tiles of a tile that hold rows below the item's limit (the MMAs of the others are not issued)
+__device__ __forceinline__ int tile_nacc(const TcConvParams& p, const TileCoord& c) {
+  if (c.dummy) return 0;
+  const int n = (c.lim - c.q0 + 127) >> 7;
+  return n < p.NACC ? n : p.NACC;
 }
 
 // Everything the MMA-issuing warp needs, precomputed once (descriptor low words are in units of 16 B).
@@ -219,6 +254,7 @@ struct MmaCtx {
   uint32_t a_plane, b_plane;        // + lo plane
   uint32_t idesc, idesc_n;          // instruction descriptors with N = NM (main) and N = p.N (a_lo x w_hi when stacked)
   int cluster_id, nclusters, n_it, rank, csize;
+  Sched sc;
   uint16_t cmask;
   int pair;                         // 1: cta_group::2 -- this thread is the leader of a CTA pair
 };
@@ -245,8 +281,10 @@ __device__ __forceinline__ void mma_warp_loop(const TcConvParams& p, const MmaCt
     int sa = 0, sw = 0;
     uint32_t pa = 0, pw = 0;                         // stage cursors + phase parities (no div/mod in this loop)
     int t_it = 0;
+    Cursor cur;
     for (int it = 0; it < x.n_it; ++it, ++t_it) {
-      const int nacc = decode_unit(p, it, x.cluster_id, x.nclusters, x.rank).dummy ? 0 : p.NACC;
+      int nacc = tile_nacc(p, decode_unit(p, x.sc, it, x.cluster_id, x.nclusters, x.rank, cur));
+      if (PAIR) nacc = max(nacc, tile_nacc(p, decode_unit(p, x.sc, it, x.cluster_id, x.nclusters, 1, cur)));   // M = 256 spans both tiles
       const int as = t_it & 1;
       mbar_wait(bar(kBarAccEmpty + as), ((t_it >> 1) & 1) ^ 1);  // acc_empty: the epilogue(s) drained this accumulator set
       tc_fence_after();
@@ -324,12 +362,34 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
   const uint32_t w_blob_bytes = w_tap_bytes * (uint32_t)p.TG;   // one weight stage = TG consecutive taps
   const uint32_t a_base = smem_u32(smem + kSmemHeader);
   const uint32_t w_base = a_base + p.a_stages * a_stage_bytes;
-  const int total_units = p.nu * p.nblocks;                      // x phases each
   const int csize = p.csize;
   const int rank = csize > 1 ? (int)cluster_ctarank() : 0;
   const int cluster_id = blockIdx.x / csize, nclusters = gridDim.x / csize;
-  const int n_it = (total_units - cluster_id + nclusters - 1) / nclusters * p.phases;   // (unit, phase) steps of this cluster
   const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
+  int* pref_s = reinterpret_cast<int*>(smem + kPrefOff);              // ragged launches only
+  int* lim_s = pref_s + kMaxItems + 1;
+  if (p.lens && warp == 3) {
+    // per-item row limits and the exclusive prefix of their tile counts (B <= kMaxItems, checked by the launcher)
+    int carry = 0;
+    for (int b0 = 0; b0 < p.B; b0 += 32) {
+      const int b = b0 + lane;
+      int lim = 0;
+      if (b < p.B) {
+        const long v = (long)__ldg(p.lens + b) * p.len_mul + p.len_add;
+        lim = v < 0 ? 0 : (v > p.nq ? p.nq : (int)v);
+        lim_s[b] = lim;
+      }
+      int nt = (lim + p.MT - 1) / p.MT, inc = nt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+      }
+      if (b < p.B) pref_s[b] = carry + inc - nt;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) pref_s[p.B] = carry;
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxAStages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
@@ -356,6 +416,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
   if (csize > 1) cluster_sync_all();           // every peer's barriers are initialised before any remote arrive / copy
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  Sched sc;
+  sc.pref = p.lens ? pref_s : nullptr;
+  sc.limv = lim_s;
+  sc.nrt = p.lens ? pref_s[p.B] : p.ntiles * p.B;
+  sc.nu = p.lens ? (sc.nrt + csize - 1) / csize : p.nu;
+  const int total_units = sc.nu * p.nblocks;                     // x phases each
+  // (unit, phase) steps of this cluster; a ragged launch may leave a cluster without work
+  const int n_it = total_units > cluster_id ? (total_units - cluster_id + nclusters - 1) / nclusters * p.phases : 0;
 
   if (warp == 0) {
     // ------------------------------------------------ activation producer
@@ -363,8 +431,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
     const uint32_t row_bytes = (uint32_t)p.RA * 16u;
     int s = 0;
     uint32_t ph = 1;                                             // producers start on the "previous phase done" parity
+    Cursor cur;
     for (int it = 0; it < n_it; ++it) {
-      const TileCoord tc = decode_unit(p, it, cluster_id, nclusters, rank);
+      const TileCoord tc = decode_unit(p, sc, it, cluster_id, nclusters, rank, cur);
       const size_t row0 = (size_t)(p.a_pad + tc.q0 + p.min_off);
       for (int c = 0; c < p.nchunks; ++c) {
         mbar_wait(a_empty(s), ph);
@@ -389,8 +458,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
     const uint32_t tap_slice = w_tap_bytes / (uint32_t)csize;         // this CTA's share of every stage, per tap in it
     int s = 0;
     uint32_t ph = 1;
+    Cursor cur;
     for (int it = 0; it < n_it; ++it) {
-      const TileCoord tc = decode_unit(p, it, cluster_id, nclusters, rank);
+      const TileCoord tc = decode_unit(p, sc, it, cluster_id, nclusters, rank, cur);
       const tc16* wg = p.w + (size_t)tc.g * per_tile * tap_elems * (pair ? 2 : 1);
       for (int c = 0; c < p.nchunks; ++c) {
         for (int j0 = 0; j0 < p.ktaps; j0 += p.TG) {
@@ -437,6 +507,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
     x.a_kstep = 2u * (uint32_t)p.RA; x.b_kstep = 2u * (uint32_t)(pair ? NM / 2 : NM);
     x.a_plane = a_plane_bytes >> 4; x.b_plane = w_plane_bytes >> 4;
     x.cluster_id = cluster_id; x.nclusters = nclusters; x.n_it = n_it; x.rank = rank; x.csize = csize;
+    x.sc = sc;
     x.cmask = cmask;
     x.pair = pair;
     const int wmode = p.stack ? 2 : (WPL == 2 ? 1 : 0);
@@ -495,8 +566,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
     const int ncc = N / 32;
     const int nitems = p.NACC * ncc;
     int t_it = 0;
+    Cursor cur;
     for (int it = 0; it < n_it; ++it, ++t_it) {
-      const TileCoord tc = decode_unit(p, it, cluster_id, nclusters, rank);
+      const TileCoord tc = decode_unit(p, sc, it, cluster_id, nclusters, rank, cur);
       const int phase = tc.g % p.phases, co_off = (tc.g / p.phases) * N;
       const int as = t_it & 1;
       const float* resb = p.res ? p.res + (size_t)tc.b * (p.o_nct ? p.r_bs : p.o32_bs) : nullptr;
@@ -509,7 +581,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
       auto item_row = [&](int m, int& t, bool& ok) {
         const int q = tc.q0 + m * 128 + quad * 32 + lane;
         t = q * p.ot_mul + p.ot_add + phase;
-        ok = !tc.dummy && q < p.nq && t >= 0 && t < p.T_out;
+        ok = !tc.dummy && q < tc.lim && t >= 0 && t < p.T_out;
       };
       auto advance = [&](int& m, int& cc) {
         cc += 2;
@@ -552,7 +624,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
         for (int idx = half; idx < p.NACC * nc8; idx += 2) {
           const int m = idx / nc8, c8 = idx - m * nc8;
           const int q = tc.q0 + m * 128 + quad * 32 + lane;
-          const bool okq = !tc.dummy && q < p.nq;
+          const bool okq = !tc.dummy && q < tc.lim;
           const int co = blk * cb + c8 * 8;            // first of the 8 output channels of this sub-item
           const float4 b0 = *reinterpret_cast<const float4*>(bias_s + co);
           const float4 b1 = *reinterpret_cast<const float4*>(bias_s + co + 4);
@@ -891,13 +963,22 @@ __global__ void tc_planes_to_nct_kernel(const tc16* __restrict__ hi, const tc16*
 template <int KMAX>
 __global__ void __launch_bounds__(256) tc_conv_post_kernel(const float* __restrict__ st, const float* __restrict__ w,
                                                            const float* __restrict__ bias, float* __restrict__ wav,
-                                                           int C, int T, int K, float slope) {
+                                                           int C, int T, int K, float slope,
+                                                           const int* __restrict__ lens, int len_mul) {
   __shared__ float ws[64 * KMAX];
+  const int b = blockIdx.y;
+  // ragged: samples past the item's valid length are zero (their inputs were never computed)
+  const long valid = lens ? (long)__ldg(lens + b) * len_mul : (long)T;
+  if (lens && (long)blockIdx.x * blockDim.x >= valid) {          // whole block past the end
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t0 < T) wav[(size_t)b * T + t0] = 0.f;
+    return;
+  }
   for (int i = threadIdx.x; i < C * K; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = blockIdx.y;
   if (t >= T) return;
+  if ((long)t >= valid) { wav[(size_t)b * T + t] = 0.f; return; }
   const int pad = (K - 1) / 2;
   float acc = bias ? bias[0] : 0.f;
   const float4* sp = reinterpret_cast<const float4*>(st) + (size_t)b * (C / 4) * T;
@@ -981,6 +1062,7 @@ void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq, int a_planes) {
   p->o_nct = 0; p->o_cs = p->o_ts = 0; p->r_bs = p->r_cs = p->r_ts = 0;
   p->mask = nullptr; p->m_bs = 0; p->act = 0; p->alpha = 1.f;
   p->c_valid = w.C_out;
+  p->lens = nullptr; p->len_mul = 0; p->len_add = 0;
 }
 
 static size_t tc_smem_bytes(const TcConvParams& p) {
@@ -1033,6 +1115,9 @@ cudaError_t launch_tc_conv(TcConvParams p, int B, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
   }
   p.B = B;
+  if (p.lens && B > TC_MAX_RAGGED_ITEMS) return cudaErrorInvalidValue;
+  // (a ragged launch has at most as many row tiles as the uniform one: the grid below is an upper bound, CTAs that
+  // find no unit in the device-side schedule leave after the prologue)
   const long row_tiles = (long)p.ntiles * B;
   int csize = pick_cluster(p, row_tiles);
   cudaLaunchConfig_t cfg{};
@@ -1147,10 +1232,10 @@ cudaError_t tc_planes_to_nct(const tc16* hi, const tc16* lo, float* out, int B, 
 }
 
 cudaError_t tc_conv_post(const float* st, const float* w, const float* bias, float* wav, int B, int C, int T, int K,
-                         float slope, cudaStream_t s) {
+                         float slope, cudaStream_t s, const int* lens, int len_mul) {
   if (C % 4 || C > 64 || K > 16) return cudaErrorInvalidValue;
   dim3 grid(cdiv(T, 256), B);
-  tc_conv_post_kernel<16><<<grid, 256, 0, s>>>(st, w, bias, wav, C, T, K, slope);
+  tc_conv_post_kernel<16><<<grid, 256, 0, s>>>(st, w, bias, wav, C, T, K, slope, lens, len_mul);
   return cudaGetLastError();
 }
 

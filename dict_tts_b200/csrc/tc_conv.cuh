@@ -54,6 +54,7 @@ static inline TcMode tc_mode(int precision) {
 constexpr int TC_PADF = 32;        // zero rows in front of t = 0 (>= largest left halo: k=11, d=5 -> 25)
 constexpr int TC_PADB = 32;        // zero rows kept after the last tile
 constexpr int TC_ROW_ALIGN = 512;  // tiles are at most 512 rows
+constexpr int TC_MAX_RAGGED_ITEMS = 512;   // batch items of a launch with per-item row limits (TcConvParams::lens)
 // rows allocated per slab for a tensor of T time steps
 static inline int tc_rows(int T) {
   const int align = T + 8 <= 128 ? 128 : (T + 8 <= 256 ? 256 : TC_ROW_ALIGN);   // short sequences use 128/256-row tiles
@@ -132,6 +133,11 @@ struct TcConvParams {
   int TG;                        // taps per weight stage
   int ntiles, B;                 // time tiles per (group, batch item); batch size (set by the launcher)
   int csize, nu;                 // cluster size; units (= csize consecutive row tiles) per weight group (launcher)
+  // Ragged launch (optional): item b only needs rows [0, lim_b), lim_b = clamp(lens[b] * len_mul + len_add, 0, nq).
+  // Tiles beyond lim_b are neither computed nor stored (what is there is stale); the caller owns the argument why nobody
+  // needs them (receptive field of the layers that follow, see tc_vocode).  lens: device int32 [B], B <= 512.
+  const int* lens;
+  int len_mul, len_add;
 };
 
 // output channels per N block of an interleaved transposed convolution: the largest multiple of 8 dividing C_out with
@@ -171,7 +177,8 @@ cudaError_t tc_nct_to_stream(const float* in, float* st, int B, int C, int T, cu
 cudaError_t tc_planes_to_nct(const tc16* hi, const tc16* lo, float* out, int B, int C, int T,
                              int rows, int pad, int fmt, cudaStream_t s);
 // conv_post: y[b,t] = tanh(bias + sum_{c,j} w[c][j] * leaky(x[b,c,t+j-pad], slope)) from an fp32 stream
+// lens (optional, device int32 [B]): samples t >= lens[b] * len_mul of item b are written as 0 without being computed
 cudaError_t tc_conv_post(const float* st, const float* w, const float* bias, float* wav, int B, int C, int T, int K,
-                         float slope, cudaStream_t s);
+                         float slope, cudaStream_t s, const int* lens = nullptr, int len_mul = 0);
 
 }  // namespace dtts

@@ -154,8 +154,46 @@ struct PlaneBuf {
   long bs() const { return (long)C * rows; }
 };
 
-int tc_vocode(dtts_vocoder* h, const float* mel, int B, int T, float* wav, void* ws, uint64_t ws_bytes, cudaStream_t s) {
+// Valid-length schedule of a vocode call (lens = valid mel frames per item, optional).  An item's wav is only wanted up
+// to lens[b] * hop samples; working backwards through the generator, every layer only has to be right on the rows those
+// samples can see.  Each launch computes rows [0, lens[b] * mul + add) of item b (clamped to the full length):
+//   conv_post (k7)      needs the last stage up to  len * hop + 3
+//   stage i convs       compute up to  need_i + rb_halo, rb_halo = max over ResBlocks of sum_m (k-1)/2 * (d_m + 1) (+4):
+//                       all six convolutions of a ResBlock use the same limit; what they compute from rows the previous
+//                       layer did not produce is garbage that stays within rb_halo rows of the limit
+//   ups[i] (stride u)   output rows < lim need q < (lim + pad + u - 1) / u + 1 of its input, which is need_{i-1}
+// Valid samples are bit-identical to the full-length call (tests/test_gpu_tensorcore.py); at cfg 2 (300-400 of 400 frames
+// valid) this skips ~13 % of stages 2-4.
+struct LenSched {
+  int stage_add[DTTS_MAX_UPS], ups_add[DTTS_MAX_UPS], rpf[DTTS_MAX_UPS + 1];   // rpf[i]: rows per mel frame before ups[i]
+  int pre_add;
+};
+LenSched len_sched(const dtts_vocoder_desc& d) {
+  LenSched ls{};
+  ls.rpf[0] = 1;
+  for (int i = 0; i < d.n_ups; ++i) ls.rpf[i + 1] = ls.rpf[i] * d.up_rates[i];
+  int rb_halo = 0;
+  for (int j = 0; j < d.n_rb; ++j) {
+    int hsum = 0;
+    for (int m = 0; m < 3; ++m) hsum += (d.rb_kernels[j] - 1) / 2 * (d.rb_dilations[j][m] + 1);
+    rb_halo = hsum > rb_halo ? hsum : rb_halo;
+  }
+  rb_halo += 4;
+  int need = 3 + 1;                                     // conv_post half width (+1 slack)
+  for (int i = d.n_ups - 1; i >= 0; --i) {
+    ls.stage_add[i] = need + rb_halo;
+    const int u = d.up_rates[i], pad = (d.up_kernels[i] - u) / 2;
+    ls.ups_add[i] = (ls.stage_add[i] + pad + u - 1) / u + 1;
+    need = ls.ups_add[i];
+  }
+  ls.pre_add = need;
+  return ls;
+}
+
+int tc_vocode(dtts_vocoder* h, const float* mel, int B, int T, float* wav, void* ws, uint64_t ws_bytes, cudaStream_t s,
+              const int* lens = nullptr) {
   const dtts_vocoder_desc& d = h->desc;
+  const LenSched ls = len_sched(d);
   const bool split = h->mode.a_planes == 2;
   const int fmt = h->mode.fmt;
   const TcGeom g = tc_geom(h, B, T);
@@ -200,6 +238,7 @@ int tc_vocode(dtts_vocoder* h, const float* mel, int B, int T, float* wav, void*
   {
     TcConvParams p = base(h->tc_pre, PM, T, -3, 1);
     p.T_out = T;
+    p.lens = lens; p.len_mul = 1; p.len_add = ls.pre_add;
     out_planes(p, PX);                                  // leaky(., 0.1) of conv_pre feeds ups.0
     L(launch_tc_conv(p, B, s));
   }
@@ -223,6 +262,7 @@ int tc_vocode(dtts_vocoder* h, const float* mel, int B, int T, float* wav, void*
       TcConvParams p = base(w, PX, len + w.ktaps - 1, 0, -1);
       p.ot_mul = u; p.ot_add = -(k - u) / 2; p.T_out = len_o;
       p.o32 = XU; p.o32_bs = (long)co * len_o;
+      p.lens = lens; p.len_mul = ls.rpf[i]; p.len_add = ls.ups_add[i];
       out_planes(p, PXUo);
       L(launch_tc_conv(p, B, s));
     }
@@ -236,10 +276,12 @@ int tc_vocode(dtts_vocoder* h, const float* mel, int B, int T, float* wav, void*
         const TcConvW& c2 = h->tc_rb2[(i * d.n_rb + j) * 3 + m];
         TcConvParams p1 = base(c1, m == 0 ? PXUo : PY, len, -(kr * dil - dil) / 2, dil);
         p1.T_out = len;
+        p1.lens = lens; p1.len_mul = ls.rpf[i + 1]; p1.len_add = ls.stage_add[i];
         out_planes(p1, PT);
         L(launch_tc_conv(p1, B, s));
         TcConvParams p2 = base(c2, PT, len, -(kr - 1) / 2, 1);
         p2.T_out = len;
+        p2.lens = lens; p2.len_mul = ls.rpf[i + 1]; p2.len_add = ls.stage_add[i];
         p2.res = m == 0 ? XU : Y32;
         p2.o32_bs = (long)ch * len;
         if (m < 2) {
@@ -256,7 +298,7 @@ int tc_vocode(dtts_vocoder* h, const float* mel, int B, int T, float* wav, void*
     }
   }
   // F.leaky_relu default slope 0.01 (hifigan.py:138), conv_post, tanh
-  L(tc_conv_post(ACC32, h->post_w, h->post_b, wav, B, ch, len, 7, 0.01f, s));
+  L(tc_conv_post(ACC32, h->post_w, h->post_b, wav, B, ch, len, 7, 0.01f, s, lens, ls.rpf[d.n_ups]));
   if (L.err != cudaSuccess) return fail(DTTS_ERR_CUDA, std::string("dtts_vocode(tc): ") + cudaGetErrorString(L.err));
   return DTTS_OK;
 }
@@ -350,14 +392,35 @@ extern "C" uint64_t dtts_vocode_workspace_bytes(const dtts_vocoder* h, int32_t B
   return 5 * ws_round((size_t)B * T * h->unit * sizeof(float)) + 1024;
 }
 
+__global__ void zero_tail_kernel(float* __restrict__ wav, const int* __restrict__ lens, int hop, long n) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (t < n && t >= (long)lens[b] * hop) wav[(size_t)b * n + t] = 0.f;
+}
+
+static int vocode_impl(dtts_vocoder* h, const float* mel, const int32_t* lens, int32_t B, int32_t T, float* wav,
+                       void* ws, uint64_t ws_bytes, void* stream);
+
 extern "C" int dtts_vocode(dtts_vocoder* h, const float* mel, int32_t B, int32_t T, float* wav, void* ws,
                            uint64_t ws_bytes, void* stream) {
+  return vocode_impl(h, mel, nullptr, B, T, wav, ws, ws_bytes, stream);
+}
+
+extern "C" int dtts_vocode_lens(dtts_vocoder* h, const float* mel, const int32_t* lens_dev, int32_t B, int32_t T,
+                                float* wav, void* ws, uint64_t ws_bytes, void* stream) {
+  if (!lens_dev) return fail(DTTS_ERR_BAD_ARG, "dtts_vocode_lens: null lengths");
+  if (B > TC_MAX_RAGGED_ITEMS) return fail(DTTS_ERR_BAD_SHAPE, "dtts_vocode_lens: at most 512 items per call");
+  return vocode_impl(h, mel, lens_dev, B, T, wav, ws, ws_bytes, stream);
+}
+
+static int vocode_impl(dtts_vocoder* h, const float* mel, const int32_t* lens, int32_t B, int32_t T, float* wav,
+                       void* ws, uint64_t ws_bytes, void* stream) {
   if (!h || !mel || !wav || !ws) return fail(DTTS_ERR_BAD_ARG, "dtts_vocode: null argument");
   if (B <= 0 || T <= 0) return fail(DTTS_ERR_BAD_SHAPE, "dtts_vocode: B and T must be positive");
   if (ws_bytes < dtts_vocode_workspace_bytes(h, B, T))
     return fail(DTTS_ERR_WORKSPACE_TOO_SMALL, "dtts_vocode: workspace too small");
   const dtts_vocoder_desc& d = h->desc;
-  if (d.precision != 0) return tc_vocode(h, mel, B, T, wav, ws, ws_bytes, (cudaStream_t)stream);
+  if (d.precision != 0) return tc_vocode(h, mel, B, T, wav, ws, ws_bytes, (cudaStream_t)stream, lens);
   Bump bump(ws, ws_bytes);
   float* buf[5];
   for (int i = 0; i < 5; ++i) buf[i] = bump.take<float>((size_t)B * T * h->unit);
@@ -418,6 +481,11 @@ extern "C" int dtts_vocode(dtts_vocoder* h, const float* mel, int32_t B, int32_t
     p.pre_slope = 0.01f;                    // F.leaky_relu default slope (hifigan.py:138)
     p.act = ACT_TANH;
     L(launch_conv1d_f32(p, B, s));
+  }
+  if (lens) {                                // the exact fp32 path computes every frame; same contract: zero past the end
+    const long n = (long)len;
+    zero_tail_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)B), 256, 0, s>>>(wav, lens, h->hop, n);
+    L(cudaGetLastError());
   }
   if (L.err != cudaSuccess) return fail(DTTS_ERR_CUDA, std::string("dtts_vocode: ") + cudaGetErrorString(L.err));
   return DTTS_OK;

@@ -331,7 +331,10 @@ class HifiGanEngine:
         return int(self.lib.dtts_vocoder_launch_count(self.handle))
 
     @torch.no_grad()
-    def forward(self, mel: torch.Tensor) -> torch.Tensor:
+    def forward(self, mel: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """mel [B,T,n_mel] -> wav [B,T*hop].  ``lengths`` (optional, [B] valid mel frames per item): samples before
+        lengths[b]*hop are bit for bit those of the full-length call, samples after it are 0 and the work only they
+        depend on is skipped (dtts_vocode_lens)."""
         mel = _dev_f32(mel, self.device)
         if mel.dim() != 3 or mel.shape[2] != self.cfg.n_mel:
             raise ValueError("mel must be [B,T,n_mel]")
@@ -339,8 +342,16 @@ class HifiGanEngine:
         wav = torch.empty(B, T * self.cfg.hop, device=self.device)
         with torch.cuda.device(self.device):
             ws = self.ws.get(self.lib.dtts_vocode_workspace_bytes(self.handle, B, T))
-            binding.check(self.lib.dtts_vocode(self.handle, _ptr(mel), B, T, _ptr(wav), _ptr(ws), ws.numel(),
-                                               _stream()), "vocode")
+            if lengths is None:
+                binding.check(self.lib.dtts_vocode(self.handle, _ptr(mel), B, T, _ptr(wav), _ptr(ws), ws.numel(),
+                                                   _stream()), "vocode")
+            else:
+                lens = torch.as_tensor(lengths).to(self.device, torch.int32).contiguous()
+                if tuple(lens.shape) != (B,):
+                    raise ValueError("lengths must be [B]")
+                lens = lens.clamp(0, T)
+                binding.check(self.lib.dtts_vocode_lens(self.handle, _ptr(mel), _ptr(lens), B, T, _ptr(wav), _ptr(ws),
+                                                        ws.numel(), _stream()), "vocode_lens")
         return wav
 
     __call__ = forward

@@ -19,7 +19,9 @@ _INPUT_KEYS = ("word_tokens", "pron_modified", "keys", "values", "key_map", "pin
 class TextToWav:
     def __init__(self, acoustic_sd, vocoder_sd, acfg: Optional[AcousticConfig] = None,
                  vcfg: Optional[VocoderConfig] = None, device="cuda:0", arenas=None, vocoder_precision: int = 3,
-                 acoustic_precision: int = 1, s2pa_route: int = 0):
+                 acoustic_precision: int = 1, s2pa_route: int = 0, trim_padding: bool = True):
+        """trim_padding: vocode only up to each utterance's valid length (the waveform past it is 0 instead of the
+        vocoded padding frames; valid samples are bit-identical either way)."""
         a_arena = a_table = v_arena = v_table = None
         if arenas is not None:
             (a_arena, a_table), (v_arena, v_table) = arenas
@@ -28,6 +30,7 @@ class TextToWav:
                                       s2pa_route=s2pa_route)
         self.vocoder = HifiGanEngine(vocoder_sd, vcfg, device, v_arena, v_table, precision=vocoder_precision)
         self.events = None
+        self.trim_padding = trim_padding
 
     @property
     def launches(self) -> int:
@@ -79,7 +82,8 @@ class TextToWav:
             mel, z_p = eng.decode_mel(g_bct, z)
             if record:
                 record("decode_mel")
-            wav = self.vocoder(mel)
+            # valid frames per utterance: the vocoder skips what only the padded tail depends on (dtts_vocode_lens)
+            wav = self.vocoder(mel, (m2w > 0).sum(-1) if self.trim_padding else None)
             if record:
                 record("vocode")
         t.update(mel2word=m2w, decoder_inp=dec_in, x_mask=x_mask, mel_out=mel, z_p=z_p)

@@ -56,9 +56,10 @@ class B200HifiGAN:
             raise ValueError("spec2wav expects one utterance [T, n_mel]")
         return self.engine(m.unsqueeze(0)).view(-1).cpu().numpy()
 
-    def spec2wav_batch(self, mel: torch.Tensor) -> torch.Tensor:
-        """mel [B,T,n_mel] (host or device) -> device tensor [B, T*hop]; the mel never leaves HBM."""
-        return self.engine(mel)
+    def spec2wav_batch(self, mel: torch.Tensor, lengths=None) -> torch.Tensor:
+        """mel [B,T,n_mel] (host or device) -> device tensor [B, T*hop]; the mel never leaves HBM.  ``lengths`` [B]
+        (valid frames per utterance): the waveform is computed up to lengths[b]*hop and zero after it."""
+        return self.engine(mel, lengths)
 
     @staticmethod
     def wav2spec(wav_fn, return_linear=False):

@@ -171,7 +171,9 @@ class B200DictTTSTask:
         hop = hp.get("hop_size", 256)
         pcm = None
         if hasattr(self.vocoder, "spec2wav_batch"):
-            wav = self.vocoder.spec2wav_batch(mel)                # [B, T*hop], mel never leaves HBM
+            frames_dev = (sample["mel2word_pred"] > 0).sum(-1)
+            # B = 1 keeps the padded tail like the reference; a batch is vocoded up to each utterance's valid length
+            wav = self.vocoder.spec2wav_batch(mel, frames_dev if B > 1 else None)   # [B, T*hop], mel never leaves HBM
             if not hp.get("out_wav_norm", False):
                 pcm = self.model.pcm16(wav).cpu().numpy()         # int16 on the device: half the D2H bytes
             else:

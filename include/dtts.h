@@ -184,6 +184,13 @@ int dtts_vocoder_destroy(dtts_vocoder* h);
 uint64_t dtts_vocode_workspace_bytes(const dtts_vocoder* h, int32_t B, int32_t T);
 int dtts_vocode(dtts_vocoder* h, const float* mel_dev, int32_t B, int32_t T, float* wav_dev, void* ws_dev,
                 uint64_t ws_bytes, void* stream);
+/* The same with the valid length of every item (extension; SURVEY.md §8b: spec2wav_batch(mel, lengths)).
+ * lens_dev: int32 [B], valid mel frames per item (0 <= lens[b] <= T), B <= 512.  wav[b, t] for t < lens[b]*hop is bit
+ * for bit what dtts_vocode writes (the frames after lens[b] still feed the receptive field of the last valid samples,
+ * exactly as in the full-length call); samples past lens[b]*hop are written as 0 and the rows only they depend on are
+ * not computed -- DictTTSTask.after_infer never looks at them (B = 1 upstream; here the task trims to the valid length). */
+int dtts_vocode_lens(dtts_vocoder* h, const float* mel_dev, const int32_t* lens_dev, int32_t B, int32_t T,
+                     float* wav_dev, void* ws_dev, uint64_t ws_bytes, void* stream);
 /* Kernels launched by this handle since creation (for bench.py's gpu_launches claim). */
 uint64_t dtts_vocoder_launch_count(const dtts_vocoder* h);
 uint64_t dtts_acoustic_launch_count(const dtts_acoustic* h);

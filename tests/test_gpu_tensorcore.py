@@ -225,3 +225,48 @@ def test_bf16_vocoder_error_is_bounded():
     rms = float(np.sqrt(np.mean((wav - gold) ** 2)))
     assert rms < 5e-3, rms          # measured ~7e-4 on the CPU emulation; NOT within the fp32 tolerance
     eng.close()
+
+
+@pytest.mark.parametrize("precision", [0, 1, 3, 5])
+def test_vocode_with_lengths_is_bit_identical_on_valid_samples(precision):
+    """dtts_vocode_lens: samples before lengths[b]*hop are bit for bit those of the full-length call (the padded frames
+    still feed the receptive field of the last valid samples), samples after it are 0.  Edge lengths: 0, 1, T, and
+    lengths that end exactly on / just after a row-tile boundary of every stage."""
+    from dict_tts_b200.engine import HifiGanEngine
+    eng = HifiGanEngine(synth.make_vocoder_state_dict(VOCODER_SEED), precision=precision)
+    T = 72
+    lens = torch.tensor([72, 0, 1, 16, 17, 33, 64, 71, 40, 2])
+    mel = synth.make_mel(77, len(lens), T)
+    full = eng(mel)
+    part = eng(mel, lens)
+    for b, n in enumerate(lens.tolist()):
+        assert torch.equal(part[b, :n * 256], full[b, :n * 256]), (precision, b, n)
+        assert (part[b, n * 256:] == 0).all(), (precision, b, n)
+    # stale rows of a previous, longer call must not leak into a shorter one: same call again after a full-length one,
+    # and lengths in a different order
+    perm = torch.tensor([3, 9, 0, 5, 1, 7, 2, 8, 6, 4])
+    again = eng(mel[perm], lens[perm])
+    for i, b in enumerate(perm.tolist()):
+        n = int(lens[b])
+        assert torch.equal(again[i, :n * 256], full[b, :n * 256]), (precision, b, n)
+    with pytest.raises(ValueError):
+        eng(mel, lens[:3])
+    eng.close()
+
+
+def test_vocode_with_lengths_cfg2_shape():
+    """The bench workload: 60 utterances of 300-400 valid frames in a 400-frame batch (CTA pairs in stages 1-2, ragged
+    tile schedule in every launch)."""
+    from dict_tts_b200.engine import HifiGanEngine
+    eng = HifiGanEngine(synth.make_vocoder_state_dict(VOCODER_SEED))
+    g = torch.Generator().manual_seed(3)
+    lens = torch.randint(300, 401, (60,), generator=g)
+    lens[0], lens[7] = 400, 300
+    mel = synth.make_mel(78, 60, 400)
+    full = eng(mel)
+    part = eng(mel, lens)
+    for b in range(60):
+        n = int(lens[b]) * 256
+        assert torch.equal(part[b, :n], full[b, :n]), b
+        assert (part[b, n:] == 0).all(), b
+    eng.close()
