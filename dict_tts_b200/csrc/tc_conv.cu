@@ -17,6 +17,7 @@
 #include "tc16.cuh"
 
 #include <cstdlib>
+#include <type_traits>
 
 namespace dtts {
 
@@ -164,6 +165,30 @@ __device__ __forceinline__ void st_pair(void* p, uint4 a, uint4 b, bool oka, boo
     if (oka) *reinterpret_cast<uint4*>(p) = a;
     if (okb) *(reinterpret_cast<uint4*>(p) + 1) = b;
   }
+}
+// Packed fp32 pairs (FADD2 / FMUL2 on sm_100): the epilogue is latency bound on the narrow layers (two warps per
+// scheduler), every instruction it does not issue counts.  Per lane these are the IEEE operations of the scalar forms.
+#ifdef DTTS_NO_PACKED_F32      // A/B switch for measurements: the scalar forms
+__device__ __forceinline__ void add2(float& x0, float& x1, float y0, float y1) { x0 += y0; x1 += y1; }
+__device__ __forceinline__ void mul2(float& x0, float& x1, float y0, float y1) { x0 *= y0; x1 *= y1; }
+#else
+__device__ __forceinline__ void add2(float& x0, float& x1, float y0, float y1) {
+  asm("{\n\t.reg .b64 a, b;\n\tmov.b64 a, {%0, %1};\n\tmov.b64 b, {%2, %3};\n\tadd.rn.f32x2 a, a, b;\n\tmov.b64 {%0, %1}, a;\n\t}"
+      : "+f"(x0), "+f"(x1)
+      : "f"(y0), "f"(y1));
+}
+__device__ __forceinline__ void mul2(float& x0, float& x1, float y0, float y1) {
+  asm("{\n\t.reg .b64 a, b;\n\tmov.b64 a, {%0, %1};\n\tmov.b64 b, {%2, %3};\n\tmul.rn.f32x2 a, a, b;\n\tmov.b64 {%0, %1}, a;\n\t}"
+      : "+f"(x0), "+f"(x1)
+      : "f"(y0), "f"(y1));
+}
+#endif
+// leaky(v) = max(v, slope * v) for 0 <= slope <= 1, two channels at a time
+__device__ __forceinline__ void leaky2(float a0, float a1, float slope, float& o0, float& o1) {
+  float m0 = a0, m1 = a1;
+  mul2(m0, m1, slope, slope);
+  o0 = fmaxf(a0, m0);
+  o1 = fmaxf(a1, m1);
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -700,6 +725,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
         }
         continue;
       }
+      // The item loop exists twice: with a residual (conv2 of a ResBlock: the next item's residual is prefetched while
+      // this one is processed -- that ordering is what keeps those HBM-bound layers at 6 TB/s) and without one (conv1:
+      // no residual registers at all; its epilogue is latency bound, 64 fewer moves per item).
+      auto items = [&](auto has_res_tag) {
+      constexpr bool HAS_RES = decltype(has_res_tag)::value;
       for (int idx = half; idx < nitems; idx += 2) {
         int t; bool ok;
         item_row(m, t, ok);
@@ -710,13 +740,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
         float4 rn[8];
         int mn = m, ccn = cc;
         advance(mn, ccn);
-        if (idx + 2 < nitems) load_res(mn, ccn, rn);   // next item's residual is in flight while this one is processed
+        if constexpr (HAS_RES) {
+          if (idx + 2 < nitems) load_res(mn, ccn, rn);   // next item's residual is in flight while this one is processed
+        }
         if (p.stack) {                                 // a*w_lo landed N columns further: fold it in
           uint32_t r2[32];
           tmem_ld32_nowait(tcol + (uint32_t)N, r2);
           tmem_ld_wait();
+          float* rf = reinterpret_cast<float*>(r);
+          const float* r2f = reinterpret_cast<const float*>(r2);
 #pragma unroll
-          for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) + __uint_as_float(r2[k]));
+          for (int k = 0; k < 32; k += 2) add2(rf[k], rf[k + 1], r2f[k], r2f[k + 1]);
         }
         tmem_ld_wait();
         if (ok) {
@@ -726,10 +760,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const float4 bq = bs4[k];
-            v[4 * k] = __uint_as_float(r[4 * k]) + bq.x;
-            v[4 * k + 1] = __uint_as_float(r[4 * k + 1]) + bq.y;
-            v[4 * k + 2] = __uint_as_float(r[4 * k + 2]) + bq.z;
-            v[4 * k + 3] = __uint_as_float(r[4 * k + 3]) + bq.w;
+            v[4 * k] = __uint_as_float(r[4 * k]); v[4 * k + 1] = __uint_as_float(r[4 * k + 1]);
+            v[4 * k + 2] = __uint_as_float(r[4 * k + 2]); v[4 * k + 3] = __uint_as_float(r[4 * k + 3]);
+            add2(v[4 * k], v[4 * k + 1], bq.x, bq.y);
+            add2(v[4 * k + 2], v[4 * k + 3], bq.z, bq.w);
           }
           if (p.act == 1) {
 #pragma unroll
@@ -738,17 +772,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
           if (p.alpha != 1.f || p.mask) {               // out = post * (act(conv + bias) * alpha * mask + res)
             const float am = p.alpha * (p.mask ? __ldg(p.mask + (size_t)tc.b * p.m_bs + t) : 1.f);
 #pragma unroll
-            for (int k = 0; k < 32; ++k) v[k] *= am;
+            for (int k = 0; k < 32; k += 2) mul2(v[k], v[k + 1], am, am);
           }
-          if (resb) {
+          if constexpr (HAS_RES) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              v[4 * k] += rc[k].x; v[4 * k + 1] += rc[k].y; v[4 * k + 2] += rc[k].z; v[4 * k + 3] += rc[k].w;
+              add2(v[4 * k], v[4 * k + 1], rc[k].x, rc[k].y);
+              add2(v[4 * k + 2], v[4 * k + 3], rc[k].z, rc[k].w);
             }
           }
           if (p.post != 1.f) {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) v[k] *= p.post;
+            for (int k = 0; k < 32; k += 2) mul2(v[k], v[k + 1], p.post, p.post);
           }
           if (o32b && p.o_nct) {                        // element (c, t) at out[b*o32_bs + c*o_cs + t*o_ts]
             float* op = o32b + (size_t)n0 * p.o_cs + (size_t)t * p.o_ts;
@@ -785,8 +820,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
                 uint32_t hw[4], lw[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const float a0 = v[8 * h + 2 * e], a1 = v[8 * h + 2 * e + 1];
-                  split2(fmaxf(a0, a0 * p.slope), fmaxf(a1, a1 * p.slope), fmt, hw[e], lw[e]);
+                  float l0, l1;
+                  leaky2(v[8 * h + 2 * e], v[8 * h + 2 * e + 1], p.slope, l0, l1);
+                  split2(l0, l1, fmt, hw[e], lw[e]);
                 }
                 const size_t off = prow + (size_t)h * p.op_rows * 8;
                 *reinterpret_cast<uint4*>(p.o_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
@@ -798,18 +834,24 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
                 uint32_t hw[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const float a0 = v[8 * h + 2 * e], a1 = v[8 * h + 2 * e + 1];
-                  hw[e] = pack2(fmaxf(a0, a0 * p.slope), fmaxf(a1, a1 * p.slope), fmt);
+                  float l0, l1;
+                  leaky2(v[8 * h + 2 * e], v[8 * h + 2 * e + 1], p.slope, l0, l1);
+                  hw[e] = pack2(l0, l1, fmt);
                 }
                 *reinterpret_cast<uint4*>(p.o_hi + prow + (size_t)h * p.op_rows * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
               }
             }
           }
         }
+        if constexpr (HAS_RES) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) rc[k] = rn[k];
+          for (int k = 0; k < 8; ++k) rc[k] = rn[k];
+        }
         m = mn; cc = ccn;
       }
+      };
+      if (resb) items(std::true_type{});
+      else items(std::false_type{});
       // this warp no longer reads accumulator set `as`
       tc_fence_before();
       __syncwarp();

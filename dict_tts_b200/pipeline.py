@@ -111,6 +111,9 @@ class TextToWav:
         copy = getattr(self, "_copy_stream", None)
         if copy is None:
             copy = self._copy_stream = torch.cuda.Stream(dev)
+        readback = getattr(self, "_readback_stream", None)
+        if readback is None:
+            readback = self._readback_stream = torch.cuda.Stream(dev)
         it = iter(batches)
         slots = [None, None]                 # (device batch, copied event)
         free = [None, None]                  # event: compute has finished reading slot i
@@ -150,9 +153,13 @@ class TextToWav:
                 out = wav_bufs[cur][:wav.shape[0], :wav.shape[1]]
             else:
                 out = torch.empty(wav.shape, dtype=wav.dtype, pin_memory=True)
-            out.copy_(wav, non_blocking=True)
-            done = torch.cuda.Event()
-            done.record(compute)
+            # the read-back runs on its own stream, so the next batch's kernels do not queue behind it
+            readback.wait_event(done_reading)
+            with torch.cuda.stream(readback):
+                out.copy_(wav, non_blocking=True)
+                wav.record_stream(readback)
+                done = torch.cuda.Event()
+                done.record(readback)
             if pending is not None:
                 pending[1].synchronize()
                 yield pending[0]
