@@ -213,3 +213,56 @@ def test_s2pa_gemm_route_agrees_with_folded_route_and_oracle():
     gemm.close()
     with pytest.raises(RuntimeError, match="s2pa_route"):
         DictTTSEngine(sd, precision=0, s2pa_route=1)
+
+
+SWEEP = [
+    # seed, B, min_chars, max_chars, max_frames, Lk_cap, note
+    (301, 1, 1, 1, 9, 8, "one character, T = 9 (padded to 12 by repeating the last column)"),
+    (302, 2, 1, 3, 18, 12, "tiny gloss lists, T % 4 == 2"),
+    (303, 5, 2, 11, 61, 33, "odd everything"),
+    (304, 3, 20, 40, 200, 48, "Tw = 42: still the shared-memory attention"),
+    (305, 2, 70, 90, 400, 24, "Tw = 92 > 64: the general attention kernel"),
+    (306, 7, 1, 6, 28, 96, "many short utterances, long gloss lists"),
+]
+
+
+@pytest.mark.parametrize("case", SWEEP, ids=lambda c: "seed%d" % c[0])
+def test_acoustic_random_shapes_against_oracle(case, acoustic):
+    """Shapes the fixtures do not hold, every stage against the oracle run on the same batch (supplied alignment), and the
+    predicted-duration path bit-exactly.  pron_modified = None must equal an all-zero pron_modified."""
+    eng, W = acoustic
+    seed, B, cmin, cmax, frames, lk, _ = case
+    T4 = (frames + 3) // 4 * 4
+    batch = synth.make_batch(seed=seed, B=B, min_chars=cmin, max_chars=cmax, max_frames=T4, Lk_cap=lk,
+                             pron_modified_p=0.05)
+    batch["mel2word"] = batch["mel2word"][:, :frames].contiguous()      # T % 4 != 0: both sides repeat the last column
+    z = synth.draw_z(B, AcousticConfig().latent, T4 // 4, seed)
+    out = _run_acoustic(eng, batch, False, z)
+    with torch.no_grad():
+        ref = O.acoustic_forward(W, AcousticConfig(), batch, batch["mel2word"], z)
+    assert out["mel_out"].shape == (B, T4, 80)
+    assert torch.equal(out["mel2word"].cpu(), ref["mel2word"])
+    for k, tol in (("word_encoder_out", 2e-4), ("dict_attn", 1e-5), ("pron_attn", 1e-5), ("dur", 1e-4),
+                   ("mel_out", TOL_MEL_MAXABS)):
+        err = (out[k].cpu() - ref[k]).abs().max().item()
+        assert err < tol, (k, err)
+    x, nonpad = O.expand_by_mel2word(out["word_encoder_out"].cpu(), out["mel2word"].cpu())
+    assert torch.equal(out["decoder_inp"].cpu(), x) and torch.equal(out["x_mask"].cpu(), nonpad)
+    # predicted durations: integer path, bit-exact against the oracle's own prediction from ITS encoder output
+    t = eng.text_encode(batch["word_tokens"], batch["pron_modified"], batch["keys"], batch["values"], batch["key_map"],
+                        batch["pinyin"], batch["pinyin_map"])
+    m2w = eng.length_regulate(t["dur_int"], t["ilens"]).cpu()
+    assert torch.equal(m2w, O.length_regulate(t["dur_int"].cpu(), t["ilens"].cpu()))
+    with torch.no_grad():
+        dur_ref, pad_ref = O.duration_predictor(W, AcousticConfig(), ref["word_encoder_out"] *
+                                                (batch["word_tokens"] != 0).float().unsqueeze(-1))
+    assert torch.equal(t["dur_int"].cpu(), O.durations_to_int(dur_ref))
+    assert torch.equal(t["ilens"].cpu(), (1 - pad_ref.long()).sum(-1))
+    # no tone-sandhi overrides: None == zeros
+    zero = torch.zeros_like(batch["pron_modified"])
+    a = eng.text_encode(batch["word_tokens"], None, batch["keys"], batch["values"], batch["key_map"],
+                        batch["pinyin"], batch["pinyin_map"])
+    b = eng.text_encode(batch["word_tokens"], zero, batch["keys"], batch["values"], batch["key_map"],
+                        batch["pinyin"], batch["pinyin_map"])
+    for k in ("word_encoder_out", "pron_attn", "dur_int"):
+        assert torch.equal(a[k], b[k]), k

@@ -12,7 +12,9 @@ KEYS = [
     ("dram__bytes_read.sum", "dram read"),
     ("dram__bytes_write.sum", "dram write"),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram % of peak"),
-    ("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe active %"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor pipe active % of elapsed cycles"),
+    ("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+     "tensor pipe active %, _realtime flavour (varies between captures of the same launch: do not quote)"),
     ("l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem->tensor-core wavefronts % of peak"),
     ("l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum", "bulk-copy (TMA) bytes L2->smem"),
     ("lts__t_bytes.sum", "L2 bytes"),
