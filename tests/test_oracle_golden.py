@@ -118,3 +118,41 @@ def test_engine_refuses_to_run_without_cuda():
         DictTTSEngine({})
     with pytest.raises(RuntimeError):
         HifiGanEngine({})
+
+
+def test_abi_error_convention_without_a_gpu():
+    """Every entry point returns a negative dtts_status and leaves a message for dtts_last_error() instead of touching
+    the device when its arguments are unusable (include/dtts.h: status codes; SURVEY.md §8b error convention).  None of
+    these calls reaches a kernel launch, so they run on the CPU box too."""
+    lib = binding.load()
+    BAD_ARG, BAD_SHAPE = -1, -2
+
+    def last():
+        return lib.dtts_last_error().decode()
+
+    null = ctypes.c_void_p()
+    out = ctypes.c_void_p()
+    assert lib.dtts_acoustic_create(None, None, 0, None, 0, None, ctypes.byref(out)) == BAD_ARG and "null" in last()
+    assert lib.dtts_vocoder_create(None, None, 0, None, 0, None, ctypes.byref(out)) == BAD_ARG
+    d = binding.AcousticDesc(192, 2, 4, 5, 768, 768, 8000, 185, 3, 5, 128, 4, 16, 4, 5, 64, 3, 4, 4, 80, 1, 7, 0)
+    assert lib.dtts_acoustic_create(ctypes.byref(d), None, 0, None, 0, None, ctypes.byref(out)) == BAD_ARG
+    assert "precision" in last()
+    d.precision, d.s2pa_route = 0, 1
+    assert lib.dtts_acoustic_create(ctypes.byref(d), None, 0, None, 0, None, ctypes.byref(out)) == BAD_ARG
+    assert "s2pa_route" in last()
+    d.s2pa_route, d.frames_multiple = 0, 3
+    assert lib.dtts_acoustic_create(ctypes.byref(d), None, 0, None, 0, None, ctypes.byref(out)) == BAD_SHAPE
+    v = binding.VocoderDesc()
+    v.n_mel, v.init_ch, v.n_ups, v.n_rb, v.precision = 80, 512, 1, 1, 9
+    v.up_rates[0], v.up_kernels[0] = 8, 16
+    assert lib.dtts_vocoder_create(ctypes.byref(v), None, 0, None, 0, None, ctypes.byref(out)) == BAD_ARG
+    assert "precision" in last()
+    v.precision, v.up_kernels[0] = 3, 15                      # kernel not a multiple of the rate
+    assert lib.dtts_vocoder_create(ctypes.byref(v), None, 0, None, 0, None, ctypes.byref(out)) == BAD_SHAPE
+    assert lib.dtts_vocode(None, None, 1, 1, None, None, 0, None) == BAD_ARG
+    assert lib.dtts_vocode_lens(None, None, None, 1, 1, None, None, 0, None) == BAD_ARG and "lengths" in last()
+    assert lib.dtts_text_encode(None, None, None, None, 0, None) == BAD_ARG
+    assert lib.dtts_vocode_workspace_bytes(None, 1, 1) == 0 and lib.dtts_text_workspace_bytes(None, 1, 1, 1, 1) == 0
+    assert lib.dtts_acoustic_destroy(None) == 0 and lib.dtts_vocoder_destroy(None) == 0
+    with pytest.raises(RuntimeError, match="status -1"):
+        binding.check(BAD_ARG, "probe")
