@@ -33,6 +33,11 @@ __device__ __forceinline__ void split2(float a0, float a1, int fmt, uint32_t& hw
   lw = pack2(a0 - back16(hw & 0xFFFFu, fmt), a1 - back16(hw >> 16, fmt), fmt);
 }
 
+// FP8 lo-plane correction (tc_conv.cuh, TcMode::lo8): the weights of such a layer are packed x 2^10 -- fp16(w * 2^10) for the
+// hi plane, e5m2((w - fp16(w)) * 2^10) for the lo plane, which puts w_lo (2^-12 of w) into the e5m2 range -- and the epilogue
+// multiplies the accumulator by 2^-10.  The activations need no scale: their e5m2 copy is the high byte of the fp16 value.
+constexpr float kLo8WScale = 1024.f;
+
 // Destination operand planes of an element-wise producer: [B][C/8][rows][8], row = pad + t (tc_conv.cuh).
 struct PlaneOut {
   tc16* hi = nullptr;

@@ -29,7 +29,8 @@ constexpr int kMaxAStages = 4, kMaxWStages = 6;
 // mbarrier slots (8 B each) at the start of shared memory
 constexpr int kBarAFull = 0, kBarAEmpty = kBarAFull + kMaxAStages, kBarWFull = kBarAEmpty + kMaxAStages,
               kBarWEmpty = kBarWFull + kMaxWStages, kBarAccFull = kBarWEmpty + kMaxWStages, kBarAccEmpty = kBarAccFull + 2,
-              kBarPAFull = kBarAccEmpty + 2, kBarPWFull = kBarPAFull + kMaxAStages, kNumBars = kBarPWFull + kMaxWStages;
+              kBarPAFull = kBarAccEmpty + 2, kBarPWFull = kBarPAFull + kMaxAStages, kBarA8Ready = kBarPWFull + kMaxWStages,
+              kNumBars = kBarA8Ready + kMaxAStages;
 constexpr int kTmemPtrOff = kNumBars * 8;                 // uint32: TMEM base address
 constexpr int kBiasOff = (kTmemPtrOff + 4 + 63) / 64 * 64;
 constexpr int kMaxBias = 2048;               // output channels of one launch (bias staged in shared memory)
@@ -104,6 +105,25 @@ __device__ __forceinline__ void umma_bf16_2cta(uint32_t d_tmem, uint64_t adesc, 
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// FP8 forms (kind::f8f6f4, K = 32 per instruction): the lo-plane correction of TcMode::lo8
+__device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f8_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
                "h"((uint16_t)3)
@@ -117,6 +137,11 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) 
   // a completed tcgen05.ld (wait::ld) -- there is no generic-proxy write to release, and a release at cluster scope costs
   // a full memory barrier per stage on the relay thread (measured: the pair was slower than two single CTAs with it).
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t bar, uint32_t rank) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(bar), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -183,6 +208,17 @@ __device__ __forceinline__ void mul2(float& x0, float& x1, float y0, float y1) {
       : "f"(y0), "f"(y1));
 }
 #endif
+// x = x * s + y on a pair (FFMA2); s = 1 gives exactly x + y
+__device__ __forceinline__ void fma2(float& x0, float& x1, float s, float y0, float y1) {
+#ifdef DTTS_NO_PACKED_F32
+  x0 = fmaf(x0, s, y0); x1 = fmaf(x1, s, y1);
+#else
+  asm("{\n\t.reg .b64 a, b, c;\n\tmov.b64 a, {%0, %1};\n\tmov.b64 b, {%2, %2};\n\tmov.b64 c, {%3, %4};\n\t"
+      "fma.rn.f32x2 a, a, b, c;\n\tmov.b64 {%0, %1}, a;\n\t}"
+      : "+f"(x0), "+f"(x1)
+      : "f"(s), "f"(y0), "f"(y1));
+#endif
+}
 // leaky(v) = max(v, slope * v) for 0 <= slope <= 1, two channels at a time
 __device__ __forceinline__ void leaky2(float a0, float a1, float slope, float& o0, float& o1) {
   float m0 = a0, m1 = a1;
@@ -278,6 +314,7 @@ struct MmaCtx {
   uint32_t a_kstep, b_kstep;        // +K step (two 8-channel slabs)
   uint32_t a_plane, b_plane;        // + lo plane
   uint32_t idesc, idesc_n;          // instruction descriptors with N = NM (main) and N = p.N (a_lo x w_hi when stacked)
+  uint32_t a8_delta, b8_low0, w8_tap16, idesc8;   // lo8: e5m2 copy of the A tile (offset inside a stage), lo weights
   int cluster_id, nclusters, n_it, rank, csize;
   Sched sc;
   uint16_t cmask;
@@ -288,7 +325,8 @@ struct MmaCtx {
 // thread -- the serial resource of the CTA -- spends a handful of uniform-datapath instructions per tcgen05.mma.
 //   WMODE 0: one weight plane; 1: hi and lo planes, one MMA each; 2: hi | lo stacked along N (one MMA, the epilogue adds
 //   the two column halves) -- an M=128,K=16 MMA costs max(64, N/2) cycles (A is read from shared memory at 64 B/clk), so
-//   for C_out <= 64 the second weight plane is free this way.
+//   for C_out <= 64 the second weight plane is free this way; 3: fp16 hi plane + ONE FP8 MMA (K = 32) per tap for the lo
+//   plane (TcMode::lo8, KC = 32).
 template <int KSTEPS, int APL, int WMODE, bool PAIR>
 __device__ __forceinline__ void mma_warp_loop(const TcConvParams& p, const MmaCtx& x) {
   // PAIR: tcgen05.mma.cta_group::2 issued by the leader CTA only; the peer's warp 2 relays its "stage full" events to the
@@ -296,6 +334,10 @@ __device__ __forceinline__ void mma_warp_loop(const TcConvParams& p, const MmaCt
   auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
     if (PAIR) umma_bf16_2cta(d, a, b, idesc, acc);
     else umma_bf16(d, a, b, idesc, acc);
+  };
+  auto mma8 = [](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    if (PAIR) umma_f8_2cta(d, a, b, idesc, acc);
+    else umma_f8(d, a, b, idesc, acc);
   };
   if (elect_one()) {                                 // ONE thread runs the whole loop: waits, MMAs and commits
     const uint32_t hiw = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
@@ -315,7 +357,8 @@ __device__ __forceinline__ void mma_warp_loop(const TcConvParams& p, const MmaCt
       tc_fence_after();
       const uint32_t d_base = x.tmem_base + (uint32_t)(as * 256);
       for (int c = 0; c < nchunks; ++c) {
-        mbar_wait(bar(kBarAFull + sa), pa);          // a_full
+        // a_full -- with lo8 "the e5m2 copy of the tile is in place", which the producer warp signals after a_full
+        mbar_wait(bar((WMODE == 3 ? kBarA8Ready : kBarAFull) + sa), pa);
         if (PAIR) mbar_wait(bar(kBarPAFull + sa), pa);       // ... and the peer's A tile
         tc_fence_after();
         uint32_t a_tap = x.a_low0 + (uint32_t)sa * x.a_stage16 + tap0;
@@ -324,8 +367,9 @@ __device__ __forceinline__ void mma_warp_loop(const TcConvParams& p, const MmaCt
           if (PAIR) mbar_wait(bar(kBarPWFull + sw), pw);     // ... and the peer's half of the weights
           tc_fence_after();
           uint32_t b_lo = x.b_low0 + (uint32_t)sw * x.w_blob16;
+          uint32_t b8 = x.b8_low0 + (uint32_t)sw * x.w_blob16;
           const int j1 = min(j0 + TG, ktaps);
-          for (int j = j0; j < j1; ++j, a_tap += (uint32_t)tap_step, b_lo += x.w_tap16) {
+          for (int j = j0; j < j1; ++j, a_tap += (uint32_t)tap_step, b_lo += x.w_tap16, b8 += x.w8_tap16) {
             const uint32_t first = (c | j) != 0 ? 1u : 0u;
             uint32_t d = d_base, am = a_tap;
             for (int m = 0; m < nacc; ++m, d += (uint32_t)NM, am += 128u) {
@@ -337,6 +381,8 @@ __device__ __forceinline__ void mma_warp_loop(const TcConvParams& p, const MmaCt
                 if (APL == 2)
                   mma(d, desc64(am + ks * x.a_kstep + x.a_plane, hiw), b, WMODE == 2 ? x.idesc_n : x.idesc, 1u);
               }
+              // lo plane at the FP8 rate: the chunk's 32 channels in one K = 32 instruction
+              if (WMODE == 3) mma8(d, desc64(am + x.a8_delta, hiw), desc64(b8, hiw), x.idesc8, 1u);
             }
           }
           if (PAIR) umma_commit_2cta(bar(kBarWEmpty + sw));                   // w_empty of both CTAs
@@ -380,11 +426,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
   float* bias_s = reinterpret_cast<float*>(smem + kBiasOff);          // [nblocks * N] <= kMaxBias floats
 
   const uint32_t a_plane_bytes = (uint32_t)(KC / 8) * p.RA * 16u;
-  const uint32_t a_stage_bytes = a_plane_bytes * APL;
+  const uint32_t a8_bytes = p.lo8 ? (uint32_t)(KC / 16) * p.RA * 16u : 0u;      // e5m2 copy of the tile (lo8)
+  const uint32_t a_stage_bytes = a_plane_bytes * APL + a8_bytes;
   constexpr int pair = PAIR ? 1 : 0;                            // CTA pair: each CTA stages half of every weight blob
   const uint32_t w_plane_bytes = (uint32_t)(pair ? NM / 2 : NM) * KC * 2u;   // NM = 2N when hi | lo are stacked (WPL = 1)
   const uint32_t w_tap_bytes = w_plane_bytes * WPL;             // one (K chunk, tap) blob
-  const uint32_t w_blob_bytes = w_tap_bytes * (uint32_t)p.TG;   // one weight stage = TG consecutive taps
+  const uint32_t w8_tap_bytes = p.lo8 ? w_plane_bytes / 2u : 0u;               // its e5m2 lo plane (lo8)
+  // one weight stage = TG consecutive taps: [TG fp16 blobs][TG e5m2 blobs]
+  const uint32_t w_blob_bytes = (w_tap_bytes + w8_tap_bytes) * (uint32_t)p.TG;
   const uint32_t a_base = smem_u32(smem + kSmemHeader);
   const uint32_t w_base = a_base + p.a_stages * a_stage_bytes;
   const int csize = p.csize;
@@ -421,6 +470,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
     for (int s = 0; s < kMaxWStages; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), pair ? 1 : csize); }
     for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), pair ? 2 * kEpiWarps : kEpiWarps); }
     for (int s = 0; s < kMaxAStages + kMaxWStages; ++s) mbar_init(bar0 + 8u * (kBarPAFull + s), 1);
+    for (int s = 0; s < kMaxAStages; ++s) mbar_init(bar0 + 8u * (kBarA8Ready + s), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -457,13 +507,45 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
     int s = 0;
     uint32_t ph = 1;                                             // producers start on the "previous phase done" parity
     Cursor cur;
+    // lo8: the e5m2 copy of a staged tile is made HERE, in shared memory: e5m2 is fp16 with the mantissa cut to 2 bits, i.e.
+    // the high byte of every element, so no second plane ever crosses HBM.  The whole warp converts stage (cs, cpar) once
+    // its bulk copies have landed -- before it blocks on the next free slot, i.e. while the previous chunk's MMAs run.
+    int cs = 0, pend = 0;
+    uint32_t cpar = 0;
+    auto convert_stage = [&]() {
+      mbar_wait(a_full(cs), cpar);
+      const uint32_t src = a_base + cs * a_stage_bytes, dst = src + APL * a_plane_bytes;
+      const uint32_t slab = (uint32_t)p.RA * 16u;                // bytes of one 8-channel fp16 slab = one e5m2 slab
+      for (int s8 = 0; s8 < KC / 16; ++s8) {                     // e5m2 slab s8 = high bytes of fp16 slabs 2*s8, 2*s8 + 1
+        const uint32_t s0 = src + (uint32_t)(2 * s8) * slab, d0 = dst + (uint32_t)s8 * slab;
+#pragma unroll 4
+        for (int r = lane; r < p.RA; r += 32) {
+          uint4 lo, hi;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(s0 + (uint32_t)r * 16u));
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "r"(s0 + slab + (uint32_t)r * 16u));
+          const uint32_t o0 = __byte_perm(lo.x, lo.y, 0x7531), o1 = __byte_perm(lo.z, lo.w, 0x7531);
+          const uint32_t o2 = __byte_perm(hi.x, hi.y, 0x7531), o3 = __byte_perm(hi.z, hi.w, 0x7531);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d0 + (uint32_t)r * 16u), "r"(o0), "r"(o1),
+                       "r"(o2), "r"(o3)
+                       : "memory");
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar0 + 8u * (kBarA8Ready + cs));
+      if (++cs == p.a_stages) { cs = 0; cpar ^= 1u; }
+      --pend;
+    };
     for (int it = 0; it < n_it; ++it) {
       const TileCoord tc = decode_unit(p, sc, it, cluster_id, nclusters, rank, cur);
       const size_t row0 = (size_t)(p.a_pad + tc.q0 + p.min_off);
       for (int c = 0; c < p.nchunks; ++c) {
+        if (p.lo8 && pend > 0) convert_stage();
         mbar_wait(a_empty(s), ph);
         if (elect_one()) {
-          mbar_arrive_expect_tx(a_full(s), a_stage_bytes);
+          mbar_arrive_expect_tx(a_full(s), a_plane_bytes * APL);
           for (int pl = 0; pl < APL; ++pl) {
             const tc16* src = (pl ? p.a_lo : p.a_hi) + (size_t)tc.b * p.a_bs;
             for (int sl = 0; sl < slabs; ++sl) {
@@ -473,9 +555,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
           }
         }
         __syncwarp();
+        ++pend;
         if (++s == p.a_stages) { s = 0; ph ^= 1u; }
       }
     }
+    while (p.lo8 && pend > 0) convert_stage();
   } else if (warp == 1) {
     // ------------------------------------------------ weight producer
     const size_t tap_elems = (size_t)w_tap_bytes / 2;
@@ -494,13 +578,25 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
           if (pair) {
             // CTA pair: the packed weights hold [tap][half][...]; this CTA stages half `rank` of every tap of the group
             if (elect_one()) {
-              mbar_arrive_expect_tx(w_full(s), ntap * w_tap_bytes);
+              mbar_arrive_expect_tx(w_full(s), ntap * (w_tap_bytes + w8_tap_bytes));
               for (uint32_t jj = 0; jj < ntap; ++jj)
                 bulk_g2s(w_base + s * w_blob_bytes + jj * w_tap_bytes,
                          wg + ((size_t)(c * p.ktaps + j0 + (int)jj) * 2 + rank) * tap_elems, w_tap_bytes, w_full(s));
+              if (p.lo8) {
+                const uint8_t* wg8 = p.w8 + (size_t)tc.g * per_tile * w8_tap_bytes * 2;
+                for (uint32_t jj = 0; jj < ntap; ++jj)
+                  bulk_g2s(w_base + s * w_blob_bytes + (uint32_t)p.TG * w_tap_bytes + jj * w8_tap_bytes,
+                           wg8 + ((size_t)(c * p.ktaps + j0 + (int)jj) * 2 + rank) * w8_tap_bytes, w8_tap_bytes,
+                           w_full(s));
+              }
             }
           } else if (elect_one()) {
-            mbar_arrive_expect_tx(w_full(s), ntap * w_tap_bytes);     // the whole stage lands here, one slice per peer
+            mbar_arrive_expect_tx(w_full(s), ntap * (w_tap_bytes + w8_tap_bytes));   // the whole stage lands here, one slice per peer
+            if (p.lo8) {                                                // (lo8 launches are never multicast: csize == 1)
+              const uint8_t* wg8 = p.w8 + (size_t)tc.g * per_tile * w8_tap_bytes;
+              bulk_g2s(w_base + s * w_blob_bytes + (uint32_t)p.TG * w_tap_bytes,
+                       wg8 + (size_t)(c * p.ktaps + j0) * w8_tap_bytes, ntap * w8_tap_bytes, w_full(s));
+            }
             // the ntap tap blobs are contiguous in global and in shared memory: peer r copies bytes [r, r+1) * slice
             const uint32_t slice = ntap * tap_slice;
             const uint32_t dst = w_base + s * w_blob_bytes + rank * slice;
@@ -531,6 +627,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
     x.a_stage16 = a_stage_bytes >> 4; x.w_blob16 = w_blob_bytes >> 4; x.w_tap16 = w_tap_bytes >> 4;
     x.a_kstep = 2u * (uint32_t)p.RA; x.b_kstep = 2u * (uint32_t)(pair ? NM / 2 : NM);
     x.a_plane = a_plane_bytes >> 4; x.b_plane = w_plane_bytes >> 4;
+    // lo8: e5m2 operands, D = f32 @4, A/B format E5M2 = 1 @7/@10, same M / N fields
+    x.a8_delta = (a_plane_bytes * (uint32_t)APL) >> 4;
+    x.b8_low0 = (((w_base + (uint32_t)p.TG * w_tap_bytes) >> 4) & 0x3FFFu) | ((uint32_t)(pair ? NM / 2 : NM) << 16);
+    x.w8_tap16 = w8_tap_bytes >> 4;
+    x.idesc8 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NM >> 3) << 17) | ((pair ? 256u >> 4 : 128u >> 4) << 24);
     x.cluster_id = cluster_id; x.nclusters = nclusters; x.n_it = n_it; x.rank = rank; x.csize = csize;
     x.sc = sc;
     x.cmask = cmask;
@@ -543,8 +644,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
         uint32_t pa = 0, pw = 0;
         for (int it = 0; it < n_it; ++it) {
           for (int c = 0; c < p.nchunks; ++c) {
-            mbar_wait(a_full(sa), pa);
-            mbar_arrive_remote(bar0 + 8u * (kBarPAFull + sa), 0);
+            if (p.lo8) {                            // the peer's tile counts once ITS e5m2 copy is written (generic proxy:
+              mbar_wait(bar0 + 8u * (kBarA8Ready + sa), pa);      // release it at cluster scope)
+              mbar_arrive_remote_release(bar0 + 8u * (kBarPAFull + sa), 0);
+            } else {
+              mbar_wait(a_full(sa), pa);
+              mbar_arrive_remote(bar0 + 8u * (kBarPAFull + sa), 0);
+            }
             for (int j0 = 0; j0 < p.ktaps; j0 += p.TG) {
               mbar_wait(w_full(sw), pw);
               mbar_arrive_remote(bar0 + 8u * (kBarPWFull + sw), 0);
@@ -555,6 +661,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
         }
       }
       __syncwarp();
+    } else if (p.lo8) {                              // fp16 hi plane + FP8 lo plane (KC = 32, single-plane activations)
+      mma_warp_loop<2, 1, 3, PAIR>(p, x);
     } else if constexpr (PAIR) {
       switch ((KC == 32 ? 2 : 0) + (WPL == 2 ? 1 : 0)) {      // pair mode: single-plane activations, unstacked weights
         case 0: mma_warp_loop<1, 1, 0, true>(p, x); break;
@@ -588,6 +696,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const bool split = p.o_lo != nullptr;
     const int fmt = p.fmt;
+    const float acc_scale = p.acc_scale;
     const int ncc = N / 32;
     const int nitems = p.NACC * ncc;
     int t_it = 0;
@@ -762,8 +871,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
             const float4 bq = bs4[k];
             v[4 * k] = __uint_as_float(r[4 * k]); v[4 * k + 1] = __uint_as_float(r[4 * k + 1]);
             v[4 * k + 2] = __uint_as_float(r[4 * k + 2]); v[4 * k + 3] = __uint_as_float(r[4 * k + 3]);
-            add2(v[4 * k], v[4 * k + 1], bq.x, bq.y);
-            add2(v[4 * k + 2], v[4 * k + 3], bq.z, bq.w);
+            fma2(v[4 * k], v[4 * k + 1], acc_scale, bq.x, bq.y);      // lo8 layers accumulate 2^10 * conv (weights pre-scaled)
+            fma2(v[4 * k + 2], v[4 * k + 3], acc_scale, bq.z, bq.w);
           }
           if (p.act == 1) {
 #pragma unroll
@@ -878,7 +987,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void tc_pack_weights_kernel(const float* __restrict__ w, tc16* __restrict__ out, int C_out,
                                        int C_in, int K, int transposed, int stride, int N, int KC, int planes,
-                                       int ktaps, int phases, int fmt, int stack, int il_cb, int pair) {
+                                       int ktaps, int phases, int fmt, int stack, int il_cb, int pair, float wscale) {
   // il_cb > 0 (transposed only): all `stride` polyphase components of a block of il_cb output channels are stacked along
   // N (row n = phase * il_cb + c); the caller passes phases = 1 and N = stride * il_cb.
   const size_t total = (size_t)C_out * C_in * ktaps * (il_cb ? stride : phases) * planes * (stack ? 2 : 1);
@@ -911,8 +1020,33 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ w, tc16* __rest
   float v;
   if (transposed) v = w[((size_t)ci * C_out + co) * K + phase + j * stride];
   else v = w[((size_t)co * C_in + ci) * K + j];
+  v *= wscale;                                       // lo8 layers: 2^10 (exact), undone by the epilogue's acc_scale
   const uint32_t hi = cvt16(v, fmt);
   out[i] = (tc16)(pl ? cvt16(v - back16(hi, fmt), fmt) : hi);
+}
+
+// e5m2 lo plane of the weights (TcConvW::lo8): out[g][chunk][tap]([half])[KC/16][Nh][16] = e5m2((w - fp16(w)) * 2^10)
+__global__ void tc_pack_weights_lo8_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, int C_out, int C_in,
+                                           int K, int N, int KC, int fmt, int pair) {
+  const size_t total = (size_t)C_out * C_in * K;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  size_t r = i;
+  const int e = r % 16; r /= 16;
+  const int Nh = pair ? N / 2 : N;
+  int n = r % Nh; r /= Nh;
+  const int sl = r % (KC / 16); r /= (KC / 16);
+  if (pair) { n += (int)(r % 2) * Nh; r /= 2; }
+  const int j = r % K; r /= K;
+  const int nchunks = C_in / KC;
+  const int c = r % nchunks; r /= nchunks;
+  const int nb = (int)r;
+  const int co = nb * N + n, ci = c * KC + sl * 16 + e;
+  const float v = w[((size_t)co * C_in + ci) * K + j];
+  const float lo = (v - back16(cvt16(v, fmt), fmt)) * kLo8WScale;
+  uint16_t q;
+  asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(q) : "f"(0.f), "f"(lo));
+  out[i] = (uint8_t)(q & 0xFF);
 }
 
 __global__ void tc_to_planes_kernel(const float* __restrict__ x, long bs, long cs, long ts, int C, int T, float slope,
@@ -1063,6 +1197,8 @@ void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq, int a_planes) {
   p->nblocks = (w.il_u ? w.C_out * w.il_u : w.C_out) / w.N; p->phases = w.phases;
   p->il_u = w.il_u; p->il_cb = w.il_cb;
   p->pair = w.pair;
+  p->lo8 = w.lo8; p->w8 = w.w8;
+  p->acc_scale = w.lo8 ? 1.f / kLo8WScale : 1.f;
   p->nq = nq;
   int nacc = 256 / p->NM;                                    // one accumulator set = 256 TMEM columns (two sets)
   if (nacc > 4) nacc = 4;
@@ -1076,15 +1212,16 @@ void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq, int a_planes) {
   p->min_off = o0 < o1 ? o0 : o1;
   const int max_off = o0 < o1 ? o1 : o0;
   p->RA = p->MT + (max_off - p->min_off);
-  const size_t a_stage = (size_t)(p->KC / 8) * p->RA * 16 * p->a_planes;
+  const size_t a_stage = (size_t)(p->KC / 8) * p->RA * 16 * p->a_planes + (p->lo8 ? (size_t)(p->KC / 16) * p->RA * 16 : 0);
   // activation stages: the (tile + halo) loads come from HBM with ~1.5 us latency; short tiles (few taps, small C) need
   // more of them in flight than the 2 a long K loop gets away with.  Keep at least ~64 KB for the weight stages.
   int as = env_int("DTTS_TC_ASTAGES", 0);
-  if (as <= 0) as = 2;                                   // measured: 3 or 4 stages do not help (profiles/r01_summary.md)
+  if (as <= 0) as = p->lo8 ? 3 : 2;                      // measured: 3 or 4 stages do not help (profiles/r01_summary.md);
+                                                         // lo8 tiles are converted in shared memory after they land: one more
   if (as > kMaxAStages) as = kMaxAStages;
   while (as > 2 && (size_t)as * a_stage > (size_t)kSmemLimit - kSmemHeader - 64 * 1024) --as;
   p->a_stages = as;
-  const size_t w_tap = (size_t)(p->pair ? p->NM / 2 : p->NM) * p->KC * 2 * p->w_planes;   // per CTA
+  const size_t w_tap = (size_t)(p->pair ? p->NM / 2 : p->NM) * p->KC * (2 * p->w_planes + (p->lo8 ? 1 : 0));   // per CTA
   // taps per weight stage: ~32 KB stages, so that the per-stage barrier round trip is amortised over >= 8 MMAs
   int tg = env_int("DTTS_TC_TG", 0);
   if (tg <= 0) tg = (int)((32 * 1024) / w_tap);
@@ -1108,8 +1245,8 @@ void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq, int a_planes) {
 }
 
 static size_t tc_smem_bytes(const TcConvParams& p) {
-  const size_t a_stage = (size_t)(p.KC / 8) * p.RA * 16 * p.a_planes;
-  const size_t w_blob = (size_t)(p.pair ? p.NM / 2 : p.NM) * p.KC * 2 * p.w_planes * p.TG;
+  const size_t a_stage = (size_t)(p.KC / 8) * p.RA * 16 * p.a_planes + (p.lo8 ? (size_t)(p.KC / 16) * p.RA * 16 : 0);
+  const size_t w_blob = (size_t)(p.pair ? p.NM / 2 : p.NM) * p.KC * (2 * p.w_planes + (p.lo8 ? 1 : 0)) * p.TG;
   size_t bytes = kSmemHeader + p.a_stages * a_stage + p.w_stages * w_blob;
   // the CTA owns all 512 TMEM columns: it must be alone on its SM, or a co-resident CTA would block in tcgen05.alloc
   if (bytes < 116 * 1024) bytes = 116 * 1024;
@@ -1122,6 +1259,12 @@ int tc_pair_enabled() {
   return v;
 }
 
+int tc_lo8_min_taps() {
+  static int v = -1;
+  if (v < 0) v = env_int("DTTS_TC_LO8_MINTAPS", 7);
+  return v;
+}
+
 static int g_num_sms = 0;
 static int g_max_clusters[9] = {0};     // [csize] -> co-resident clusters of tc_conv_kernel<false> (0 = not queried yet)
 static int g_max_pairs = 0;             // co-resident CTA pairs of tc_conv_kernel<true>
@@ -1131,6 +1274,7 @@ static int g_max_pairs = 0;             // co-resident CTA pairs of tc_conv_kern
 // L2) is not what bounds these layers, so the default is 1 and DTTS_TC_CLUSTER=2|4 turns the multicast path on.
 static int pick_cluster(const TcConvParams& p, long row_tiles) {
   if (p.pair) return 2;
+  if (p.lo8) return 1;
   int c = env_int("DTTS_TC_CLUSTER", 0);
   if (c <= 0) c = 1;
   while (c > 1 && (row_tiles < c || (p.NM * p.KC * 2 * p.w_planes) % (16 * c))) c >>= 1;
@@ -1142,6 +1286,8 @@ cudaError_t launch_tc_conv(TcConvParams p, int B, cudaStream_t stream) {
   if (p.a_planes < 1 || p.a_planes > 2 || p.w_planes < 1 || p.w_planes > 2 || (p.a_planes == 2 && !p.a_lo))
     return cudaErrorInvalidValue;
   if (p.pair && (p.stack || p.a_planes != 1 || p.NM % 32 || p.NM < 64)) return cudaErrorInvalidConfiguration;
+  if (p.lo8 && (!p.w8 || p.KC != 32 || p.a_planes != 1 || p.w_planes != 1 || p.stack || p.il_u || p.fmt != 0))
+    return cudaErrorInvalidConfiguration;
   if (p.TG < 1 || p.w_stages < 1 || p.N % 32 != 0 || p.N > 256 || p.KC % 16 != 0 || p.C_in % p.KC != 0 ||
       p.N * p.nblocks > kMaxBias || p.NACC * p.NM > 256 || (p.stack && (p.w_planes != 1 || p.NM != 2 * p.N)) ||
       (!p.stack && p.NM != p.N))
@@ -1216,7 +1362,7 @@ cudaError_t launch_tc_conv(TcConvParams p, int B, cudaStream_t stream) {
 
 cudaError_t tc_pack_weights(const float* w_ref, tc16* out, int C_out, int C_in, int K, int transposed,
                             int stride, int N, int KC, int planes, int fmt, int stack, cudaStream_t s, int il_cb,
-                            int pair) {
+                            int pair, float wscale) {
   const int phases = (transposed && !il_cb) ? stride : 1;
   const int ktaps = transposed ? K / stride : K;
   if (il_cb) {
@@ -1228,7 +1374,7 @@ cudaError_t tc_pack_weights(const float* w_ref, tc16* out, int C_out, int C_in, 
   if (stack && (planes != 1 || 2 * N > 256)) return cudaErrorInvalidValue;
   const size_t total = (size_t)C_out * C_in * ktaps * (il_cb ? stride : phases) * planes * (stack ? 2 : 1);
   tc_pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w_ref, out, C_out, C_in, K, transposed, stride,
-                                                                        N, KC, planes, ktaps, phases, fmt, stack, il_cb, pair);
+                                                                        N, KC, planes, ktaps, phases, fmt, stack, il_cb, pair, wscale);
   return cudaGetLastError();
 }
 
@@ -1237,6 +1383,14 @@ cudaError_t tc_to_planes(const float* x, long bs, long cs, long ts, int B, int C
   if (C % 8) return cudaErrorInvalidValue;
   dim3 grid(cdiv(T, 128), C / 8, B);
   tc_to_planes_kernel<<<grid, 128, 0, s>>>(x, bs, cs, ts, C, T, slope, hi, lo, rows, pad, fmt, 0, C / 8, 0);
+  return cudaGetLastError();
+}
+
+cudaError_t tc_pack_weights_lo8(const float* w_ref, uint8_t* out, int C_out, int C_in, int K, int N, int KC, int fmt,
+                                int pair, cudaStream_t s) {
+  if (C_out % N || C_in % KC || KC % 16 || (pair && N % 2)) return cudaErrorInvalidValue;
+  const size_t total = (size_t)C_out * C_in * K;
+  tc_pack_weights_lo8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w_ref, out, C_out, C_in, K, N, KC, fmt, pair);
   return cudaGetLastError();
 }
 

@@ -35,10 +35,14 @@ struct TcMode {
   int w_planes = 2;   // weights:     1 = single rounding, 2 = hi + lo
   int hybrid = 0;     // 1: layers with C_out >= 128 use ONE weight plane (there the second MMA costs time); narrower layers
                       //    keep hi | lo stacked along N, where the second plane is free
+  int lo8 = 0;        // 1: in layers with C_out >= 128 the lo-plane correction a * w_lo runs as an FP8 MMA
+                      //    (kind::f8f6f4, e5m2(a) x e5m2(w_lo * 2^10), K = 32 per instruction = twice the fp16 rate):
+                      //    it corrects a 2^-11 term, so 2 mantissa bits are plenty (measured: same waveform error as two
+                      //    fp16 planes) and the layer issues 1.5 instead of 2 units of tensor work
   int mmas() const { return a_planes + w_planes - 1; }
 };
 // dtts_vocoder_desc.precision -> mode (1: bf16 3-MMA split, 2: bf16, 3: fp16 x fp16 hi/lo weights, 4: fp16,
-// 5: fp16 x fp16, hi/lo weights only where C_out < 128)
+// 5: fp16 x fp16, hi/lo weights only where C_out < 128, 6: as 3 with the lo plane of the C_out >= 128 convolutions in FP8)
 static inline TcMode tc_mode(int precision) {
   TcMode m;
   switch (precision) {
@@ -46,6 +50,7 @@ static inline TcMode tc_mode(int precision) {
     case 3: m.fmt = 0; m.a_planes = 1; m.w_planes = 2; break;
     case 4: m.fmt = 0; m.a_planes = 1; m.w_planes = 1; break;
     case 5: m.fmt = 0; m.a_planes = 1; m.w_planes = 2; m.hybrid = 1; break;
+    case 6: m.fmt = 0; m.a_planes = 1; m.w_planes = 2; m.lo8 = 1; break;
     default: m.fmt = 1; m.a_planes = 2; m.w_planes = 2; break;
   }
   return m;
@@ -63,6 +68,9 @@ static inline int tc_rows(int T) {
 
 // DTTS_TC_PAIR=0 turns the CTA-pair path off (default on)
 int tc_pair_enabled();
+// fewest taps of a convolution that uses the FP8 lo plane under TcMode::lo8 (DTTS_TC_LO8_MINTAPS, default 7: the k = 3
+// layers are latency / HBM bound, the extra conversion step in front of their MMAs costs more than the MMAs it saves)
+int tc_lo8_min_taps();
 
 // Packed weights of one convolution: blobs [group][chunk][tap] of {hi plane, lo plane}, each plane [KC/8][N][8] bf16
 // (the shared-memory image of the B operand).  group = nblock * phases + phase.
@@ -83,13 +91,20 @@ struct TcConvW {
   // MMA; each stages its own A tile and only half of every weight blob, which halves the shared-memory traffic of the
   // B operand and of the weight stream per SM (the limiter of the C >= 128 layers).  Weights are packed [tap][half].
   int pair = 0;
+  // lo plane as FP8 (TcMode::lo8): `w` then holds the hi plane only (planes = 1), packed x 2^10, and w8 the e5m2 lo
+  // plane e5m2((w - fp16(w)) * 2^10), [group][K-chunk][tap]([half])[KC/16][N][16] bytes
+  const uint8_t* w8 = nullptr;
+  int lo8 = 0;
+  size_t elems8() const { return (size_t)C_out * C_in * ktaps; }      // bytes of w8
   size_t elems() const {
     return (size_t)(il_u ? il_u : 1) * C_out * C_in * ktaps * phases * planes * (stack ? 2 : 1);
   }
   // operand mode -> plane arrangement of this layer
   void set_mode(const TcMode& m) {
     fmt = m.fmt;
-    const int wp = (m.hybrid && C_out >= 128) ? 1 : m.w_planes;
+    lo8 = (m.lo8 && !il_u && C_out >= 128 && N >= 128 && KC == 32 && m.a_planes == 1 && m.w_planes == 2 &&
+           ktaps >= tc_lo8_min_taps()) ? 1 : 0;
+    const int wp = ((m.hybrid && C_out >= 128) || lo8) ? 1 : m.w_planes;
     stack = (wp == 2 && N <= 64) ? 1 : 0;
     planes = stack ? 1 : wp;
     pair = (!stack && m.a_planes == 1 && N >= 128 && tc_pair_enabled()) ? 1 : 0;
@@ -138,6 +153,12 @@ struct TcConvParams {
   // needs them (receptive field of the layers that follow, see tc_vocode).  lens: device int32 [B], B <= 512.
   const int* lens;
   int len_mul, len_add;
+  // FP8 lo-plane correction (TcConvW::lo8): e5m2 lo weights; the e5m2 copy of the activations is cut out of the staged
+  // fp16 tile in shared memory (high byte of every element).  acc_scale: the accumulator holds conv / acc_scale
+  // (lo8 weights are packed x 2^10 so that w_lo lands in the e5m2 range); the epilogue applies it before the bias.
+  const uint8_t* w8;
+  int lo8;
+  float acc_scale;
 };
 
 // output channels per N block of an interleaved transposed convolution: the largest multiple of 8 dividing C_out with
@@ -159,10 +180,13 @@ void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq, int a_planes);
 // Weight packing: reference layout ([C_out][C_in][K], or [C_in][C_out][K] for ConvTranspose1d) -> blobs.
 cudaError_t tc_pack_weights(const float* w_ref, tc16* out, int C_out, int C_in, int K, int transposed,
                             int stride, int N, int KC, int planes, int fmt, int stack, cudaStream_t s, int il_cb = 0,
-                            int pair = 0);
+                            int pair = 0, float wscale = 1.f);
 // fp32 strided tensor x[b*bs + c*cs + t*ts] -> operand planes of leaky(x, slope) (valid rows only)
 cudaError_t tc_to_planes(const float* x, long bs, long cs, long ts, int B, int C, int T, float slope,
                          tc16* hi, tc16* lo, int rows, int pad, int fmt, cudaStream_t s);
+// e5m2 lo plane of the weights for TcConvW::lo8 (layout in TcConvW)
+cudaError_t tc_pack_weights_lo8(const float* w_ref, uint8_t* out, int C_out, int C_in, int K, int N, int KC, int fmt,
+                                int pair, cudaStream_t s);
 // same, and zero-fills every row outside [pad, pad+T) (one launch for a freshly re-shaped scratch buffer)
 // C_total / c_off: the C source channels become channels [c_off, c_off + C) of planes that hold C_total channels
 cudaError_t tc_to_planes_full(const float* x, long bs, long cs, long ts, int B, int C, int T, float slope, tc16* hi,

@@ -4,6 +4,7 @@
 // plus 127 element-wise kernels per call).
 #include "engine.cuh"
 #include "tc_conv.cuh"
+#include "tc16.cuh"
 
 using namespace dtts;
 
@@ -20,6 +21,7 @@ struct dtts_vocoder {
   // tensor-core path (precision >= 1, see tc_mode() in tc_conv.cuh)
   TcMode mode;
   tc16* tc_pool = nullptr;
+  uint8_t* tc_pool8 = nullptr;   // e5m2 lo planes (precision 6)
   TcConvW tc_pre;
   std::vector<TcConvW> tc_ups, tc_rb1, tc_rb2;
   const float *post_w = nullptr, *post_b = nullptr;
@@ -53,7 +55,7 @@ int pack_convT(dtts_vocoder* h, const std::string& name, int C_in, int C_out, in
 }
 
 int tc_pack(dtts_vocoder* h, tc16** cursor, const std::string& name, int C_out, int C_in, int K,
-            int transposed, int stride, TcMode mode, TcConvW* cw, cudaStream_t s) {
+            int transposed, int stride, TcMode mode, TcConvW* cw, cudaStream_t s, uint8_t** cursor8 = nullptr) {
   const float* w = h->tab.get(name + ".weight", (uint64_t)C_out * C_in * K);
   if (!w) return DTTS_ERR_MISSING_WEIGHT;
   const float* b = h->tab.get(name + ".bias", C_out);
@@ -76,8 +78,14 @@ int tc_pack(dtts_vocoder* h, tc16** cursor, const std::string& name, int C_out, 
   if (cw->N % 32 || cw->N > 256 || C_in % cw->KC)
     return fail(DTTS_ERR_BAD_SHAPE, "tensor-core vocoder: unsupported channel count in " + name);
   cw->w = *cursor;
+  if (cw->lo8) {
+    if (!cursor8 || !*cursor8) return fail(DTTS_ERR_CUDA, "tensor-core vocoder: no pool for the e5m2 weight planes");
+    cw->w8 = *cursor8;
+    DTTS_CUDA(tc_pack_weights_lo8(w, *cursor8, C_out, C_in, K, cw->N, cw->KC, cw->fmt, cw->pair, s));
+    *cursor8 += (cw->elems8() + 63) / 64 * 64;
+  }
   DTTS_CUDA(tc_pack_weights(w, *cursor, C_out, C_in, K, transposed, stride, cw->N, cw->KC, cw->planes, cw->fmt, cw->stack,
-                            s, cw->il_cb, cw->pair));
+                            s, cw->il_cb, cw->pair, cw->lo8 ? kLo8WScale : 1.f));
   *cursor += (cw->elems() + 63) / 64 * 64;
   return DTTS_OK;
 }
@@ -100,6 +108,18 @@ int tc_create(dtts_vocoder* h, cudaStream_t s) {
   e = tc_conv_init();
   if (e != cudaSuccess) return fail(DTTS_ERR_CUDA, std::string("tc_conv_init: ") + cudaGetErrorString(e));
   tc16* cur = h->tc_pool;
+  uint8_t* cur8 = nullptr;
+  if (mode.lo8) {                                    // one byte per ResBlock weight, 64-byte aligned entries
+    size_t total8 = 0;
+    int c8 = d.init_ch;
+    for (int i = 0; i < d.n_ups; ++i) {
+      c8 /= 2;
+      for (int j = 0; j < d.n_rb; ++j) total8 += 6 * ((size_t)c8 * c8 * d.rb_kernels[j] + 64);
+    }
+    e = cudaMalloc((void**)&h->tc_pool8, total8);
+    if (e != cudaSuccess) return fail(DTTS_ERR_CUDA, std::string("cudaMalloc(e5m2 weight pool): ") + cudaGetErrorString(e));
+    cur8 = h->tc_pool8;
+  }
   DTTS_TRY(tc_pack(h, &cur, "conv_pre", d.init_ch, d.n_mel, 7, 0, 1, mode, &h->tc_pre, s));
   ch = d.init_ch;
   for (int i = 0; i < d.n_ups; ++i) {
@@ -111,8 +131,8 @@ int tc_create(dtts_vocoder* h, cudaStream_t s) {
       const std::string r = "resblocks." + std::to_string(i * d.n_rb + j);
       for (int m = 0; m < 3; ++m) {
         TcConvW c1, c2;
-        DTTS_TRY(tc_pack(h, &cur, r + ".convs1." + std::to_string(m), ch, ch, d.rb_kernels[j], 0, 1, mode, &c1, s));
-        DTTS_TRY(tc_pack(h, &cur, r + ".convs2." + std::to_string(m), ch, ch, d.rb_kernels[j], 0, 1, mode, &c2, s));
+        DTTS_TRY(tc_pack(h, &cur, r + ".convs1." + std::to_string(m), ch, ch, d.rb_kernels[j], 0, 1, mode, &c1, s, &cur8));
+        DTTS_TRY(tc_pack(h, &cur, r + ".convs2." + std::to_string(m), ch, ch, d.rb_kernels[j], 0, 1, mode, &c2, s, &cur8));
         h->tc_rb1.push_back(c1);
         h->tc_rb2.push_back(c2);
       }
@@ -317,7 +337,7 @@ extern "C" int dtts_vocoder_create(const dtts_vocoder_desc* d, const float* aren
     if (u < 1 || k % u != 0 || (k - u) % 2 != 0)
       return fail(DTTS_ERR_BAD_SHAPE, "upsample kernel must be a multiple of its rate with even (k-u)");
   }
-  if (d->precision < 0 || d->precision > 5) return fail(DTTS_ERR_BAD_ARG, "vocoder precision must be 0..5");
+  if (d->precision < 0 || d->precision > 6) return fail(DTTS_ERR_BAD_ARG, "vocoder precision must be 0..6");
   DTTS_TRY(arch_check());
   dtts_vocoder* h = new dtts_vocoder();
   h->desc = *d;
@@ -362,6 +382,8 @@ extern "C" int dtts_vocoder_create(const dtts_vocoder_desc* d, const float* aren
     rc = tc_create(h, s);
     if (rc != DTTS_OK) {
       if (h->tc_pool) cudaFree(h->tc_pool);
+  if (h->tc_pool8) cudaFree(h->tc_pool8);
+      if (h->tc_pool8) cudaFree(h->tc_pool8);
       return bail(rc);
     }
   }
@@ -498,7 +520,7 @@ extern "C" int dtts_debug_tc_conv1d(const float* x, const float* w, const float*
                                     int32_t stride, int32_t padding, int32_t dilation, int32_t transposed,
                                     float pre_slope, float post, float act_slope, int32_t precision, void* scratch,
                                     uint64_t scratch_bytes, void* stream) {
-  if (precision < 1 || precision > 4) return fail(DTTS_ERR_BAD_ARG, "dtts_debug_tc_conv1d: precision must be 1..4");
+  if (precision < 1 || precision > 6) return fail(DTTS_ERR_BAD_ARG, "dtts_debug_tc_conv1d: precision must be 1..6");
   const TcMode mode = tc_mode(precision);
   const bool split = mode.a_planes == 2;
   if (!x || !w || !out || !scratch) return fail(DTTS_ERR_BAD_ARG, "dtts_debug_tc_conv1d: null argument");
@@ -532,10 +554,15 @@ extern "C" int dtts_debug_tc_conv1d(const float* x, const float* w, const float*
   tc16* o_lo = split ? bump.take<tc16>((size_t)B * C_out * rows_out) : nullptr;
   float* o32 = bump.take<float>((size_t)B * C_out * T_out);
   float* r32 = res ? bump.take<float>((size_t)B * C_out * T_out) : nullptr;
+  uint8_t* w8 = cw.lo8 ? bump.take<uint8_t>(cw.elems8() + 64) : nullptr;     // precision 6: e5m2 lo plane
   if (!bump.ok) return fail(DTTS_ERR_WORKSPACE_TOO_SMALL, "dtts_debug_tc_conv1d: scratch too small");
   cw.w = wp;
+  if (cw.lo8) {
+    cw.w8 = w8;
+    DTTS_CUDA(tc_pack_weights_lo8(w, w8, C_out, C_in, K, cw.N, cw.KC, cw.fmt, cw.pair, s));
+  }
   DTTS_CUDA(tc_pack_weights(w, wp, C_out, C_in, K, transposed, stride, cw.N, cw.KC, cw.planes, cw.fmt, cw.stack, s,
-                            cw.il_cb, cw.pair));
+                            cw.il_cb, cw.pair, cw.lo8 ? kLo8WScale : 1.f));
   DTTS_CUDA(tc_zero_halo(a_hi, a_lo, B * (C_in / 8), rows_in, TC_PADF, T_in, s));
   DTTS_CUDA(tc_to_planes(x, (long)C_in * T_in, T_in, 1, B, C_in, T_in, pre_slope, a_hi, a_lo, rows_in, TC_PADF, mode.fmt, s));
   if (res) DTTS_CUDA(tc_nct_to_stream(res, r32, B, C_out, T_out, s));

@@ -286,7 +286,7 @@ class HifiGanEngine:
     """HiFi-GAN V1 generator: mel [B,T,80] -> wav [B,T*hop] on the device."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: Optional[VocoderConfig] = None, device="cuda:0",
-                 arena: Optional[torch.Tensor] = None, table=None, precision: int = 3):
+                 arena: Optional[torch.Tensor] = None, table=None, precision: int = 6):
         if not torch.cuda.is_available():
             raise RuntimeError("HifiGanEngine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = binding.load()

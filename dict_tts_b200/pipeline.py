@@ -18,7 +18,7 @@ _INPUT_KEYS = ("word_tokens", "pron_modified", "keys", "values", "key_map", "pin
 
 class TextToWav:
     def __init__(self, acoustic_sd, vocoder_sd, acfg: Optional[AcousticConfig] = None,
-                 vcfg: Optional[VocoderConfig] = None, device="cuda:0", arenas=None, vocoder_precision: int = 3,
+                 vcfg: Optional[VocoderConfig] = None, device="cuda:0", arenas=None, vocoder_precision: int = 6,
                  acoustic_precision: int = 1, s2pa_route: int = 0, trim_padding: bool = True):
         """trim_padding: vocode only up to each utterance's valid length (the waveform past it is 0 instead of the
         vocoded padding frames; valid samples are bit-identical either way)."""

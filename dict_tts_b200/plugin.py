@@ -45,7 +45,7 @@ class B200HifiGAN:
         self.config = config
         cfg = VocoderConfig.from_dict(config) if config is not None else VocoderConfig()
         if precision is None:
-            precision = int(hp.get("b200_vocoder_precision", 3))
+            precision = int(hp.get("b200_vocoder_precision", 6))
         self.device = torch.device(device)
         self.engine = HifiGanEngine(state_dict, cfg, device, precision=precision)
 

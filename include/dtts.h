@@ -78,7 +78,9 @@ typedef struct dtts_vocoder_desc {
   int32_t rb_dilations[DTTS_MAX_RB][3];
   int32_t precision; /* 0 = fp32 FMA pipe; tcgen05 modes: 1 = bf16 hi/lo x hi/lo (3 MMAs, fp32-class accuracy),
                         2 = bf16 (1 MMA), 3 = fp16 activations x fp16 hi/lo weights (2 MMAs), 4 = fp16 (1 MMA),
-                        5 = as 3, but layers with C_out >= 128 use one weight plane (1 MMA there; hi|lo stacked elsewhere) */
+                        5 = as 3, but layers with C_out >= 128 use one weight plane (1 MMA there; hi|lo stacked elsewhere),
+                        6 = as 3, with the lo-plane correction of the C_out >= 128 ResBlock convolutions as an FP8 MMA
+                            (e5m2 x e5m2, K = 32 per instruction: 1.5 instead of 2 units of tensor work, same accuracy) */
 } dtts_vocoder_desc;
 
 typedef struct dtts_acoustic dtts_acoustic; /* opaque */

@@ -166,10 +166,11 @@ def test_tc_vocoder_batch_equals_single(vocoder_tc):
         assert torch.equal(one[0], full[b])
 
 
-@pytest.mark.parametrize("precision", [3, 4, 5])
+@pytest.mark.parametrize("precision", [3, 4, 5, 6])
 def test_fp16_vocoder_modes_within_tolerance(precision, golden_dir):
     """fp16 operand modes: measured against the reference-generated golden waveforms with the north-star tolerance.
-    Mode 3 (2 MMAs) is the default of bench.py; mode 4 (1 MMA) holds the tolerance with less margin."""
+    Mode 6 (mode 3 with the lo plane of the wide k >= 7 layers in FP8) is the default of bench.py; mode 3 is its all-fp16
+    form; mode 4 (1 MMA) holds the tolerance with less margin; mode 5 is the hybrid."""
     from dict_tts_b200.engine import HifiGanEngine
     eng = HifiGanEngine(synth.make_vocoder_state_dict(VOCODER_SEED), precision=precision)
     for name, kw in sorted(VOCODER_CASES.items()):
@@ -186,7 +187,7 @@ def test_fp16_vocoder_long_batch_vs_fp32_path():
     mel = synth.make_mel(31, 3, 150)
     ref_eng = HifiGanEngine(synth.make_vocoder_state_dict(VOCODER_SEED), precision=0)
     ref = ref_eng(mel)
-    for precision in (3, 4, 5):
+    for precision in (3, 4, 5, 6):
         eng = HifiGanEngine(synth.make_vocoder_state_dict(VOCODER_SEED), precision=precision)
         wav = eng(mel)
         rms = (wav - ref).pow(2).mean().sqrt().item()
@@ -227,7 +228,7 @@ def test_bf16_vocoder_error_is_bounded():
     eng.close()
 
 
-@pytest.mark.parametrize("precision", [0, 1, 3, 5])
+@pytest.mark.parametrize("precision", [0, 1, 3, 5, 6])
 def test_vocode_with_lengths_is_bit_identical_on_valid_samples(precision):
     """dtts_vocode_lens: samples before lengths[b]*hop are bit for bit those of the full-length call (the padded frames
     still feed the receptive field of the last valid samples), samples after it are 0.  Edge lengths: 0, 1, T, and
@@ -270,3 +271,40 @@ def test_vocode_with_lengths_cfg2_shape():
         assert torch.equal(part[b, :n], full[b, :n]), b
         assert (part[b, n:] == 0).all(), b
     eng.close()
+
+
+@pytest.mark.parametrize("shape", [TC_CONV_SHAPES[3], TC_CONV_SHAPES[4], TC_CONV_SHAPES[5]])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_tc_conv_fp8_lo_plane_matches_two_fp16_planes(shape, with_res, monkeypatch):
+    """precision 6: the lo-plane correction a * w_lo of a C_out >= 128 convolution as ONE e5m2 x e5m2 MMA (K = 32) per tap
+    instead of two fp16 MMAs.  It corrects a 2^-11 term, so the result must sit on top of precision 3 (difference far
+    below the activation rounding both share) and clearly inside precision 4 (no lo plane at all).  tools/gpu_round.sh
+    runs this test a second time with DTTS_TC_PAIR=0 (the switch is read once per process) for the single-CTA build."""
+    o3, _, ref = _run_tc_conv(shape, precision=3, with_res=with_res)
+    o6, a6, _ = _run_tc_conv(shape, precision=6, with_res=with_res)
+    o4, _, _ = _run_tc_conv(shape, precision=4, with_res=with_res)
+    scale = max(1.0, ref.abs().max().item())
+    e3, e6, e4 = [(o - ref).abs().max().item() / scale for o in (o3, o6, o4)]
+    d63 = (o6 - o3).abs().max().item() / scale
+    print(f"shape {shape[:5]}: err p3 {e3:.2e} p6 {e6:.2e} p4 {e4:.2e}, |p6 - p3| {d63:.2e}")
+    assert e6 < 1.5e-3 and d63 < 2e-4
+    assert (o6 - ref).pow(2).mean().sqrt() < 1.15 * (o3 - ref).pow(2).mean().sqrt() + 1e-7
+    want_act = F.leaky_relu(o6, 0.1)
+    assert (a6 - want_act).abs().max().item() < 6e-4 * scale
+
+
+def test_fp8_lo_plane_vocoder_matches_mode_3():
+    """Whole generator: precision 6 against the exact fp32 path and against precision 3 on a long batch."""
+    from dict_tts_b200.engine import HifiGanEngine
+    sd = synth.make_vocoder_state_dict(VOCODER_SEED)
+    mel = synth.make_mel(33, 3, 150)
+    ref_eng, e3, e6 = HifiGanEngine(sd, precision=0), HifiGanEngine(sd, precision=3), HifiGanEngine(sd, precision=6)
+    ref, w3, w6 = ref_eng(mel), e3(mel), e6(mel)
+    r3 = (w3 - ref).pow(2).mean().sqrt().item()
+    r6 = (w6 - ref).pow(2).mean().sqrt().item()
+    print(f"wav rms err: precision 3 {r3:.3e}, precision 6 {r6:.3e}, |6 - 3| rms {(w6 - w3).pow(2).mean().sqrt().item():.3e}")
+    assert r6 < TOL_WAV_RMS and r6 < 1.1 * r3
+    for b in range(3):
+        assert torch.equal(e6(mel[b:b + 1])[0], w6[b])
+    for e in (ref_eng, e3, e6):
+        e.close()

@@ -19,7 +19,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--bank", action="store_true", help="characters named by dictionary-bank id (SURVEY.md 8f-1)")
     ap.add_argument("--warm", type=int, default=1)
-    ap.add_argument("--vocoder-precision", type=int, default=3)
+    ap.add_argument("--vocoder-precision", type=int, default=6)
     a = ap.parse_args()
     pipe = TextToWav(synth.make_acoustic_state_dict(1234), synth.make_vocoder_state_dict(4321),
                      vocoder_precision=a.vocoder_precision)

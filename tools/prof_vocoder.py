@@ -12,7 +12,7 @@ from dict_tts_b200.engine import HifiGanEngine  # noqa: E402
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--precision", type=int, default=1)
+    ap.add_argument("--precision", type=int, default=6)
     ap.add_argument("--B", type=int, default=60)
     ap.add_argument("--T", type=int, default=400)
     ap.add_argument("--iters", type=int, default=2)
