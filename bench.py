@@ -112,6 +112,35 @@ def cpu_port_run(batch, n_utts, threads, iters):
     return frames / best, best, frames
 
 
+def eager_gpu_run(batch, dev, iters=2):
+    """The same restatement of the reference's PyTorch forward (oracle/dtts_oracle.py), run as PyTorch eager ON THE GPU:
+    the 'library kernels' bar of SURVEY.md §8d (cuDNN convolutions, cuBLAS GEMMs, element-wise kernels, fp32, TF32 off),
+    whole cfg-2 batch, vocoder batched (kinder than the reference's one utterance at a time).  Returns (frames/s, ms)."""
+    from oracle import dtts_oracle as O
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg, vcfg = AcousticConfig(), VocoderConfig()
+    W = {k: v.to(dev) for k, v in fold_weight_norm(synth.make_acoustic_state_dict(1234)).items()}
+    Wv = {k: v.to(dev) for k, v in fold_weight_norm(synth.make_vocoder_state_dict(4321)).items()}
+    b = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    frames = int(batch["mel_lengths"].sum())
+
+    def once():
+        with torch.no_grad():
+            ret = O.acoustic_forward(W, cfg, b, b["mel2word"], b["z_p"])
+            return O.hifigan_forward(Wv, vcfg, ret["mel_out"])
+    once()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        once()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return frames / (ms / 1e3), ms
+
+
 def claim_stdout():
     """stdout carries exactly ONE line (the JSON record): whatever libraries print there while the bench runs (NCCL's
     version banner, for one) is sent to stderr; returns the function that writes the record to the real stdout."""
@@ -132,6 +161,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true",
+                    help="skip timing the PyTorch-eager (cuDNN/cuBLAS) forward of the same batch on the GPU")
     ap.add_argument("--vocoder-precision", type=int, default=int(os.environ.get("DTTS_VOCODER_PRECISION", "6")),
                     help="0: fp32 FMA pipe; 1: tcgen05 bf16 hi/lo x hi/lo (3 MMAs, ~1e-6 wav RMS); 2: tcgen05 bf16 (cfg 3, "
                          "outside the tolerance); 3: tcgen05 fp16 x fp16 hi/lo weights (2 MMAs, ~6e-5 wav RMS, "
@@ -372,6 +403,17 @@ def main():
                                            f"oracle port on {cores} host threads, best of 2", seconds=secs)
     else:
         line["cpu_baseline"] = None
+    if not args.no_eager_baseline and world == 1:
+        try:
+            pipe.close()
+            del pipe, devb
+            torch.cuda.empty_cache()
+            fps, ms = eager_gpu_run(batch, dev)
+            line["eager_gpu_baseline"] = dict(value=fps, unit="frames/s", ms_per_step=ms, kind="port",
+                                              note="oracle restatement as PyTorch eager on the same B200 (cuDNN / cuBLAS, "
+                                                   "fp32, TF32 off), whole batch, device-resident inputs")
+        except Exception as e:                       # a baseline must never cost the bench line
+            line["eager_gpu_baseline"] = dict(unavailable=repr(e)[:200])
     emit(json.dumps(line))                   # written before NCCL teardown: a buffered line can be lost at process exit
     if world > 1:
         dist.destroy_process_group()

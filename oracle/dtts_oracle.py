@@ -105,7 +105,7 @@ def text_encode(W, cfg, word_tokens, pron_modified, keys, values, key_map, pinyi
     x = F.embedding(word_tokens, W[p + ".word_emb.weight"]) * math.sqrt(H)
     x = x.transpose(1, 2)
     Tw = x.shape[2]
-    x_mask = (torch.arange(Tw).unsqueeze(0) < x_lengths.unsqueeze(1)).unsqueeze(1).to(x.dtype)
+    x_mask = (torch.arange(Tw, device=x.device).unsqueeze(0) < x_lengths.unsqueeze(1)).unsqueeze(1).to(x.dtype)
     x = encoder(W, p + ".semantic_encoder", x, x_mask, cfg.enc_layers, cfg.n_heads, cfg.ffn_kernel)
     context, dict_attn, pron, pron_attn = s2pa_attention(
         W, p + ".s2pa_attention", x, keys, values, key_map, pinyin, pinyin_map, pron_modified, cfg.language_zh)
@@ -168,7 +168,8 @@ def length_regulate(dur_int, ilens, frames_multiple=4):
 def expand_by_mel2word(word_encoder_out, mel2word):
     """F.pad one zero row + torch.gather (dict_tts/model.py:105-107), then x * tgt_nonpadding (:53)."""
     B, Tw, H = word_encoder_out.shape
-    padded = torch.cat([torch.zeros(B, 1, H, dtype=word_encoder_out.dtype), word_encoder_out], dim=1)
+    padded = torch.cat([torch.zeros(B, 1, H, dtype=word_encoder_out.dtype, device=word_encoder_out.device),
+                        word_encoder_out], dim=1)
     x = torch.gather(padded, 1, mel2word.unsqueeze(-1).expand(-1, -1, H))
     nonpad = (mel2word > 0).float().unsqueeze(-1)
     return x * nonpad, nonpad
