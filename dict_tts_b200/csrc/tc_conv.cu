@@ -17,6 +17,7 @@
 #include "tc16.cuh"
 
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 namespace dtts {
@@ -1384,6 +1385,36 @@ cudaError_t tc_to_planes(const float* x, long bs, long cs, long ts, int B, int C
   dim3 grid(cdiv(T, 128), C / 8, B);
   tc_to_planes_kernel<<<grid, 128, 0, s>>>(x, bs, cs, ts, C, T, slope, hi, lo, rows, pad, fmt, 0, C / 8, 0);
   return cudaGetLastError();
+}
+
+// max |w| over a weight tensor (one-off, at create time)
+__global__ void tc_absmax_kernel(const float* __restrict__ w, size_t n, unsigned int* __restrict__ out) {
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(w[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));      // non-negative floats order like their bit patterns
+}
+
+cudaError_t tc_lo8_weights_fit(const float* w_ref, size_t n, cudaStream_t s, int* fits) {
+  // The hi plane of an lo8 layer is fp16(w * 2^10): it must stay finite, with headroom (|w| < 32 -> < 32768)
+  unsigned int* d = nullptr;
+  cudaError_t e = cudaMalloc((void**)&d, sizeof(unsigned int));
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(d, 0, sizeof(unsigned int), s);
+  if (e == cudaSuccess) {
+    tc_absmax_kernel<<<64, 256, 0, s>>>(w_ref, n, d);
+    e = cudaGetLastError();
+  }
+  unsigned int bits = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&bits, d, sizeof(bits), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(d);
+  if (e != cudaSuccess) return e;
+  float m;
+  memcpy(&m, &bits, sizeof(m));
+  *fits = (m < 32.f) ? 1 : 0;                                            // NaN compares false: no lo8 either
+  return cudaSuccess;
 }
 
 cudaError_t tc_pack_weights_lo8(const float* w_ref, uint8_t* out, int C_out, int C_in, int K, int N, int KC, int fmt,

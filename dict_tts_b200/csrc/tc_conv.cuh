@@ -100,9 +100,9 @@ struct TcConvW {
     return (size_t)(il_u ? il_u : 1) * C_out * C_in * ktaps * phases * planes * (stack ? 2 : 1);
   }
   // operand mode -> plane arrangement of this layer
-  void set_mode(const TcMode& m) {
+  void set_mode(const TcMode& m, int lo8_ok = 1) {
     fmt = m.fmt;
-    lo8 = (m.lo8 && !il_u && C_out >= 128 && N >= 128 && KC == 32 && m.a_planes == 1 && m.w_planes == 2 &&
+    lo8 = (m.lo8 && lo8_ok && !il_u && C_out >= 128 && N >= 128 && KC == 32 && m.a_planes == 1 && m.w_planes == 2 &&
            ktaps >= tc_lo8_min_taps()) ? 1 : 0;
     const int wp = ((m.hybrid && C_out >= 128) || lo8) ? 1 : m.w_planes;
     stack = (wp == 2 && N <= 64) ? 1 : 0;
@@ -184,6 +184,9 @@ cudaError_t tc_pack_weights(const float* w_ref, tc16* out, int C_out, int C_in, 
 // fp32 strided tensor x[b*bs + c*cs + t*ts] -> operand planes of leaky(x, slope) (valid rows only)
 cudaError_t tc_to_planes(const float* x, long bs, long cs, long ts, int B, int C, int T, float slope,
                          tc16* hi, tc16* lo, int rows, int pad, int fmt, cudaStream_t s);
+// *fits = 1 when fp16(w * 2^10) stays finite with headroom (max |w| < 32); synchronises the stream (create time only).
+// A layer whose weights do not fit keeps two fp16 planes.
+cudaError_t tc_lo8_weights_fit(const float* w_ref, size_t n, cudaStream_t s, int* fits);
 // e5m2 lo plane of the weights for TcConvW::lo8 (layout in TcConvW)
 cudaError_t tc_pack_weights_lo8(const float* w_ref, uint8_t* out, int C_out, int C_in, int K, int N, int KC, int fmt,
                                 int pair, cudaStream_t s);

@@ -74,6 +74,11 @@ int tc_pack(dtts_vocoder* h, tc16** cursor, const std::string& name, int C_out, 
     if (C_out % cw->N) return fail(DTTS_ERR_BAD_SHAPE, "tensor-core vocoder: unsupported channel count in " + name);
   }
   cw->set_mode(mode);
+  if (cw->lo8) {                                      // 2^10-scaled hi plane must stay inside fp16: else two fp16 planes
+    int fits = 0;
+    DTTS_CUDA(tc_lo8_weights_fit(w, (size_t)C_out * C_in * K, s, &fits));
+    if (!fits) cw->set_mode(mode, 0);
+  }
   cw->bias = b;
   if (cw->N % 32 || cw->N > 256 || C_in % cw->KC)
     return fail(DTTS_ERR_BAD_SHAPE, "tensor-core vocoder: unsupported channel count in " + name);
@@ -542,6 +547,11 @@ extern "C" int dtts_debug_tc_conv1d(const float* x, const float* w, const float*
     if (C_out % cw.N) return fail(DTTS_ERR_BAD_SHAPE, "tensor-core conv: unsupported channels");
   }
   cw.set_mode(mode); cw.bias = bias;
+  if (cw.lo8) {
+    int fits = 0;
+    DTTS_CUDA(tc_lo8_weights_fit(w, (size_t)C_out * C_in * K, s, &fits));
+    if (!fits) cw.set_mode(mode, 0);
+  }
   if (cw.N % 32 || cw.N > 256 || C_in % cw.KC) return fail(DTTS_ERR_BAD_SHAPE, "tensor-core conv: unsupported channels");
   const int T_out = transposed ? (T_in - 1) * stride - 2 * padding + K : T_in + 2 * padding - dilation * (K - 1);
   if (T_out <= 0) return fail(DTTS_ERR_BAD_SHAPE, "tensor-core conv: empty output");

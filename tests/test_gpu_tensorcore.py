@@ -36,12 +36,12 @@ TC_CONV_SHAPES = [
 ]
 
 
-def _run_tc_conv(shape, precision, with_res):
+def _run_tc_conv(shape, precision, with_res, w_scale=1.0):
     B, Ci, Ti, Co, K, s, p, d, tr, slope = shape
     lib = binding.load()
     g = torch.Generator().manual_seed(sum(shape[:9]) + 7)
     x = torch.randn(B, Ci, Ti, generator=g)
-    w = torch.randn((Ci, Co, K) if tr else (Co, Ci, K), generator=g) / (Ci * K) ** 0.5
+    w = torch.randn((Ci, Co, K) if tr else (Co, Ci, K), generator=g) / (Ci * K) ** 0.5 * w_scale
     b = torch.randn(Co, generator=g)
     xin = F.leaky_relu(x, slope) if slope != 1.0 else x
     ref = F.conv_transpose1d(xin, w, b, stride=s, padding=p) if tr else F.conv1d(xin, w, b, padding=p, dilation=d)
@@ -308,3 +308,17 @@ def test_fp8_lo_plane_vocoder_matches_mode_3():
         assert torch.equal(e6(mel[b:b + 1])[0], w6[b])
     for e in (ref_eng, e3, e6):
         e.close()
+
+
+def test_fp8_lo_plane_is_refused_for_weights_that_would_overflow():
+    """The hi plane of an lo8 layer is fp16(w * 2^10): a layer with max |w| >= 32 must keep two fp16 planes, i.e. precision 6
+    then IS precision 3 (bit for bit), instead of saturating silently."""
+    shape = TC_CONV_SHAPES[3]                                   # stage 2, k = 11: lo8-eligible
+    big = 2000.0                                                # weights up to ~ +-150
+    o3, _, ref = _run_tc_conv(shape, precision=3, with_res=False, w_scale=big)
+    o6, _, _ = _run_tc_conv(shape, precision=6, with_res=False, w_scale=big)
+    assert torch.equal(o3, o6)
+    assert (o6 - ref).abs().max().item() < 1.5e-3 * max(1.0, ref.abs().max().item())
+    o3s, _, _ = _run_tc_conv(shape, precision=3, with_res=False)
+    o6s, _, _ = _run_tc_conv(shape, precision=6, with_res=False)
+    assert not torch.equal(o3s, o6s)                            # ordinary weights: the FP8 path really runs
