@@ -199,7 +199,7 @@ def test_fp16_vocoder_long_batch_vs_fp32_path():
     ref_eng.close()
 
 
-@pytest.mark.parametrize("B,T", [(1, 300), (16, 32), (5, 77), (2, 1)])
+@pytest.mark.parametrize("B,T", [(1, 300), (16, 32), (5, 77), (2, 1), (1, 2000)])
 def test_default_vocoder_mode_on_baseline_shapes(B, T):
     """BASELINE.json shapes in miniature: cfg 1 (one long utterance), cfg 4 (many 32-frame segments), odd sizes and a
     single frame -- the default tensor-core mode (CTA pairs on the wide layers, stacked planes on the narrow ones,
@@ -322,3 +322,17 @@ def test_fp8_lo_plane_is_refused_for_weights_that_would_overflow():
     o3s, _, _ = _run_tc_conv(shape, precision=3, with_res=False)
     o6s, _, _ = _run_tc_conv(shape, precision=6, with_res=False)
     assert not torch.equal(o3s, o6s)                            # ordinary weights: the FP8 path really runs
+
+
+def test_vocode_with_lengths_rejects_more_than_512_items():
+    """The ragged tile schedule keeps one prefix entry per item in shared memory (TC_MAX_RAGGED_ITEMS): a larger batch is an
+    error, not a silent full-length call; without lengths the same batch is fine."""
+    from dict_tts_b200.engine import HifiGanEngine
+    eng = HifiGanEngine(synth.make_vocoder_state_dict(VOCODER_SEED))
+    mel = synth.make_mel(3, 513, 4)
+    with pytest.raises(RuntimeError, match="512"):
+        eng(mel, torch.full((513,), 4))
+    assert eng(mel).shape == (513, 4 * 256)
+    part = eng(mel[:512], torch.arange(512) % 5)
+    assert (part[0] == 0).all() and (part[4] != 0).any()
+    eng.close()
