@@ -336,6 +336,8 @@ __global__ void __launch_bounds__(256) s2pa_stream_kernel(const float* __restric
                                                            const int32_t* __restrict__ row_len) {
   // row_off != null: keys / values are a dictionary BANK [rows][D]; character (b,t) owns rows
   // [row_off[bt], row_off[bt] + row_len[bt]) of it and every further gloss position is an all-zero row (never read).
+  // (A persistent variant -- one wave of CTAs pulling characters from an atomic counter -- was measured slower: wrapping
+  // the body in a loop took the kernel from 56 to 114 registers, i.e. from 4 to 2 resident CTAs per SM: 140 us instead of 80 us at cfg 2.)
   extern __shared__ float sm[];
   float* s_q = sm;            // [D]
   float* s_w = sm + D;        // [Lk]
@@ -357,11 +359,24 @@ __global__ void __launch_bounds__(256) s2pa_stream_kernel(const float* __restric
     float logit = -1e9f;
     if (km[l] != 0.f) {
       float acc = 0.f;
-      for (int i = lane; l < nrow && i < D4; i += 32) {
-        const float4 kv = ld_stream_f4(kp + (size_t)l * D4 + i);
-        const float4 qv = *reinterpret_cast<const float4*>(s_q + 4 * i);
-        acc = fmaf(kv.x, qv.x, acc); acc = fmaf(kv.y, qv.y, acc);
-        acc = fmaf(kv.z, qv.z, acc); acc = fmaf(kv.w, qv.w, acc);
+      // all loads of the row are issued before the first FMA (8 x 128 bit in flight per lane); same summation order as
+      // the plain loop, which remains for D > 1024
+      for (int i0 = lane; l < nrow && i0 < D4; i0 += 256) {
+        float4 kv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + 32 * u;
+          if (i < D4) kv[u] = ld_stream_f4(kp + (size_t)l * D4 + i);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + 32 * u;
+          if (i < D4) {
+            const float4 qv = *reinterpret_cast<const float4*>(s_q + 4 * i);
+            acc = fmaf(kv[u].x, qv.x, acc); acc = fmaf(kv[u].y, qv.y, acc);
+            acc = fmaf(kv[u].z, qv.z, acc); acc = fmaf(kv[u].w, qv.w, acc);
+          }
+        }
       }
       acc = warp_sum(acc);
       logit = acc;
@@ -406,12 +421,26 @@ __global__ void __launch_bounds__(256) s2pa_stream_kernel(const float* __restric
   const bool all_masked = (s_any == 0);
   for (int i = tid; i < D4; i += 256) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int l = 0; l < nrow; ++l) {
-      const float w = s_w[l];
-      if (w == 0.f && !all_masked) continue;
-      const float4 vv = ld_stream_f4(vp + (size_t)l * D4 + i);
-      acc.x = fmaf(w, vv.x, acc.x); acc.y = fmaf(w, vv.y, acc.y);
-      acc.z = fmaf(w, vv.z, acc.z); acc.w = fmaf(w, vv.w, acc.w);
+    // four rows in flight per thread (the loads do not depend on the accumulator); rows are still added in order
+    for (int l0 = 0; l0 < nrow; l0 += 4) {
+      float w[4];
+      float4 vv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int l = l0 + u;
+        w[u] = l < nrow ? s_w[l] : 0.f;
+        const bool use = l < nrow && (w[u] != 0.f || all_masked);
+        if (use) vv[u] = ld_stream_f4(vp + (size_t)l * D4 + i);
+        else w[u] = 0.f, vv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int l = l0 + u;
+        if (l < nrow && (w[u] != 0.f || all_masked)) {
+          acc.x = fmaf(w[u], vv[u].x, acc.x); acc.y = fmaf(w[u], vv[u].y, acc.y);
+          acc.z = fmaf(w[u], vv[u].z, acc.z); acc.w = fmaf(w[u], vv[u].w, acc.w);
+        }
+      }
     }
     float* c = ctx + ((size_t)b * D + 4 * i) * Tw + t;
     c[0] = acc.x; c[Tw] = acc.y; c[2 * (size_t)Tw] = acc.z; c[3 * (size_t)Tw] = acc.w;
