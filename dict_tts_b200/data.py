@@ -169,15 +169,19 @@ class DictTTSTestSet:
             s["word_ids"] = [self.word_to_id.get(w, 2) for w in item["words"][1:-1]]
             return s
         keys, values, key_map, pinyin, pinyin_map = [], [], [], [], []
+        # The binarizer stores ONE feature tensor as both key and value (binarizer_zh.py:231-233; pickle keeps the identity):
+        # then `values` stays the same tensor as `keys` all the way to the device and only half the bytes cross PCIe.
+        alias = True
         for word in item["words"][1:-1]:                             # BOS / EOS carry no dictionary entry
             e = self._dict_entry(word)
+            alias = alias and (e["value"] is e["key"])
             keys.append(torch.as_tensor(e["key"], dtype=torch.float32))
-            values.append(torch.as_tensor(e["value"], dtype=torch.float32))
+            values.append(keys[-1] if e["value"] is e["key"] else torch.as_tensor(e["value"], dtype=torch.float32))
             key_map.append(torch.as_tensor(e["key_map"], dtype=torch.float32))
             pinyin.append(torch.LongTensor([self._pinyin_index[p] for p in e["pinyin"]]))
             pinyin_map.append(torch.LongTensor(e["pinyin_map"]))
-        s.update(keys=pad_2d(keys), values=pad_2d(values), key_map=pad_1d(key_map), pinyin=pad_1d(pinyin),
-                 pinyin_map=pad_1d(pinyin_map))
+        s.update(keys=pad_2d(keys), key_map=pad_1d(key_map), pinyin=pad_1d(pinyin), pinyin_map=pad_1d(pinyin_map))
+        s["values"] = s["keys"] if alias and keys else pad_2d(values)
         return s
 
     @staticmethod
@@ -196,7 +200,10 @@ class DictTTSTestSet:
             b["dict_ids"] = collate_dict_ids([s["dict_ids"] for s in samples])
             return b
         b["keys"] = F.pad(pad_3d([s["keys"] for s in samples]), (0, 0, 0, 0, 1, 1))
-        b["values"] = F.pad(pad_3d([s["values"] for s in samples]), (0, 0, 0, 0, 1, 1))
+        if all(s["values"] is s["keys"] for s in samples):           # same tensor in every item: keep it one tensor
+            b["values"] = b["keys"]
+        else:
+            b["values"] = F.pad(pad_3d([s["values"] for s in samples]), (0, 0, 0, 0, 1, 1))
         b["key_map"] = F.pad(pad_3d([s["key_map"].unsqueeze(-1) for s in samples]).squeeze(-1), (0, 0, 1, 1), value=1)
         b["pinyin"] = F.pad(pad_3d([s["pinyin"].unsqueeze(-1) for s in samples]).squeeze(-1), (0, 0, 1, 1), value=0)
         b["pinyin_map"] = F.pad(pad_3d([s["pinyin_map"].unsqueeze(-1) for s in samples]).squeeze(-1), (0, 0, 1, 1),

@@ -98,8 +98,9 @@ class DictTTSEngine:
         dev = self.device
         wt = _dev_i64(word_tokens, dev)
         B, Tw = wt.shape
+        same = values is None or values is keys
         keys = _dev_f32(keys, dev)
-        values = keys if values is None else _dev_f32(values, dev)
+        values = keys if same else _dev_f32(values, dev)
         key_map = _dev_f32(key_map, dev)
         pinyin = _dev_i64(pinyin, dev)
         pinyin_map = _dev_i64(pinyin_map, dev)

@@ -31,7 +31,7 @@ VOC_CONFIG = dict(resblock="1", upsample_rates=[8, 8, 2, 2], upsample_kernel_siz
 
 
 def write(root: str, exp: str = "fake_dict_tts", n_items: int = 5, n_vocab: int = 40, seed: int = 7,
-          steps=(1000, 3000, 2000), original_hifigan_layout: bool = False) -> dict:
+          steps=(1000, 3000, 2000), original_hifigan_layout: bool = False, same_key_value: bool = False) -> dict:
     g = torch.Generator().manual_seed(seed)
     ck = os.path.join(root, "checkpoints", exp)
     vk = os.path.join(root, "checkpoints", "fake_hifigan")
@@ -79,7 +79,8 @@ def write(root: str, exp: str = "fake_dict_tts", n_items: int = 5, n_vocab: int 
             pin += [pinyin_tokens[a], pinyin_tokens[b]]
             pmap += [i + 1, i + 1]
         feats = (torch.randn(len(key_map), 768, generator=g) * 0.5).numpy()
-        db.add_item({"key": feats, "value": feats.copy(), "key_map": key_map, "tokens_gloss": [], "pinyin": pin,
+        # same_key_value: ONE array as key and value, as the reference binarizer writes it (binarizer_zh.py:231-233)
+        db.add_item({"key": feats, "value": feats if same_key_value else feats.copy(), "key_map": key_map, "tokens_gloss": [], "pinyin": pin,
                      "pinyin_map": pmap})
     db.finalize()
     # ---- test items ----

@@ -116,3 +116,16 @@ def test_reference_dealing_of_the_test_set(exp):
     assert flat0 == ["fake_%03d" % i for i in range(0, 6, 2)] and flat1 == ["fake_%03d" % i for i in range(1, 6, 2)]
     with pytest.raises(ValueError):
         next(ds.batches(2, deal="nope"))
+
+
+def test_value_that_is_the_key_stays_one_tensor(tmp_path):
+    """The reference binarizer stores one feature tensor as both 'key' and 'value'; pickle keeps that identity, the reader
+    and the collate keep it, so the pipeline uploads it once (values_dev may alias keys_dev in the C ABI)."""
+    one = fake_exp.write(str(tmp_path / "one"), n_items=4, same_key_value=True)
+    two = fake_exp.write(str(tmp_path / "two"), n_items=4, same_key_value=False)
+    b1 = next(DictTTSTestSet(one["hparams"]).batches(max_sentences=4))
+    b2 = next(DictTTSTestSet(two["hparams"]).batches(max_sentences=4))
+    assert b1["values"] is b1["keys"]
+    assert b2["values"] is not b2["keys"] and torch.equal(b2["values"], b2["keys"])
+    for k in ("keys", "key_map", "pinyin", "pinyin_map", "word_tokens"):
+        assert torch.equal(b1[k], b2[k]), k
