@@ -387,7 +387,6 @@ extern "C" int dtts_vocoder_create(const dtts_vocoder_desc* d, const float* aren
     rc = tc_create(h, s);
     if (rc != DTTS_OK) {
       if (h->tc_pool) cudaFree(h->tc_pool);
-  if (h->tc_pool8) cudaFree(h->tc_pool8);
       if (h->tc_pool8) cudaFree(h->tc_pool8);
       return bail(rc);
     }
@@ -402,6 +401,7 @@ extern "C" int dtts_vocoder_destroy(dtts_vocoder* h) {
   if (!h) return DTTS_OK;
   h->pool.release();
   if (h->tc_pool) cudaFree(h->tc_pool);
+  if (h->tc_pool8) cudaFree(h->tc_pool8);
   delete h;
   return DTTS_OK;
 }
