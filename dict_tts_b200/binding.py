@@ -6,9 +6,12 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdtts.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 DTTS_MAX_UPS = 8
 DTTS_MAX_RB = 4
+# dtts_status (include/dtts.h)
+DTTS_OK, DTTS_ERR_BAD_ARG, DTTS_ERR_BAD_SHAPE, DTTS_ERR_MISSING_WEIGHT = 0, -1, -2, -3
+DTTS_ERR_WORKSPACE_TOO_SMALL, DTTS_ERR_UNSUPPORTED_ARCH, DTTS_ERR_CUDA, DTTS_ERR_ALIGNMENT = -4, -5, -6, -7
 
 
 class WeightEntry(C.Structure):
@@ -64,6 +67,7 @@ SYMBOLS = {
     "dtts_text_bank_workspace_bytes": (_U64, [_P, _I, _I, _I, _I]),
     "dtts_text_encode_bank": (C.c_int, [_P, C.POINTER(DictBankStruct), C.POINTER(TextInBank), C.POINTER(TextOut), _P,
                                         _U64, _P]),
+    "dtts_acoustic_status": (C.c_int, [_P, _P, _I]),
     "dtts_length_regulate_scan": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, C.POINTER(C.c_int32), _P]),
     "dtts_length_regulate_fill": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "dtts_expand": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),

@@ -61,6 +61,12 @@ struct dtts_acoustic {
   std::vector<FlowW> flows;   // in reference order (flows.0, .2, .4, .6)
   WNW dec_wn;
   uint64_t launches = 0;
+  // dictionary-bank gather status (dtts_text_encode_bank): device word written by dict_bank_gather_kernel, copied to the
+  // pinned host word after every gather; sticky until dtts_acoustic_status reports it
+  int* bank_err_dev = nullptr;
+  int* bank_err_host = nullptr;
+  cudaEvent_t bank_err_evt = nullptr;
+  int bank_err_sticky = 0;
 };
 
 namespace {
@@ -410,8 +416,10 @@ extern "C" int dtts_acoustic_create(const dtts_acoustic_desc* d, const float* ar
                                     dtts_acoustic** out) {
   if (!d || !out) return fail(DTTS_ERR_BAD_ARG, "null descriptor/out");
   *out = nullptr;
-  if (d->hidden <= 0 || d->hidden > 256 || d->hidden % d->n_heads || d->dict_dim % 4 || d->latent % 2 ||
-      d->frames_multiple != 4)
+  if (d->hidden <= 0 || d->hidden > 256 || d->n_heads <= 0 || d->hidden % d->n_heads || d->dict_dim <= 0 ||
+      d->dict_dim % 4 || d->latent <= 0 || d->latent % 2 || d->frames_multiple != 4 || d->enc_layers < 0 ||
+      d->ffn_kernel <= 0 || d->ffn_filter <= 0 || d->dur_layers < 0 || d->dur_chans <= 0 || d->flow_blocks < 0 ||
+      d->flow_hidden <= 0 || d->n_mel <= 0 || d->word_size <= 0 || d->pinyin_size <= 0)
     return fail(DTTS_ERR_BAD_SHAPE, "unsupported acoustic configuration");
   if (d->precision != 0 && d->precision != 1)
     return fail(DTTS_ERR_BAD_ARG, "acoustic precision must be 0 (fp32 FMA) or 1 (tcgen05, bf16 hi/lo split)");
@@ -548,13 +556,18 @@ extern "C" int dtts_acoustic_create(const dtts_acoustic_desc* d, const float* ar
   };
   rc = build();
   if (rc == DTTS_OK) {
+    cudaError_t e = cudaMalloc((void**)&h->bank_err_dev, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->bank_err_dev, 0, sizeof(int), s);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&h->bank_err_host, sizeof(int));
+    if (e == cudaSuccess) { *h->bank_err_host = 0; e = cudaEventCreateWithFlags(&h->bank_err_evt, cudaEventDisableTiming); }
+    if (e != cudaSuccess) rc = fail(DTTS_ERR_CUDA, std::string("acoustic create (status words): ") + cudaGetErrorString(e));
+  }
+  if (rc == DTTS_OK) {
     cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) rc = fail(DTTS_ERR_CUDA, std::string("acoustic create: ") + cudaGetErrorString(e));
   }
   if (rc != DTTS_OK) {
-    h->pool.release();
-    if (h->tc_pool) cudaFree(h->tc_pool);
-    delete h;
+    dtts_acoustic_destroy(h);
     return rc;
   }
   *out = h;
@@ -565,8 +578,31 @@ extern "C" int dtts_acoustic_destroy(dtts_acoustic* h) {
   if (!h) return DTTS_OK;
   h->pool.release();
   if (h->tc_pool) cudaFree(h->tc_pool);
+  if (h->bank_err_dev) cudaFree(h->bank_err_dev);
+  if (h->bank_err_host) cudaFreeHost(h->bank_err_host);
+  if (h->bank_err_evt) cudaEventDestroy(h->bank_err_evt);
   delete h;
   return DTTS_OK;
+}
+
+// Folds a landed gather status into the sticky word and reports it (0 = clean).
+static int bank_status(dtts_acoustic* h) {
+  if (h->bank_err_host && *h->bank_err_host) {
+    h->bank_err_sticky |= *h->bank_err_host;
+    *h->bank_err_host = 0;
+  }
+  const int st = h->bank_err_sticky;
+  if (!st) return DTTS_OK;
+  h->bank_err_sticky = 0;
+  if (st & 1) return fail(DTTS_ERR_BAD_ARG, "dtts_text_encode_bank: a dict_id was >= bank.n_entries (that character was encoded as an all-zero row)");
+  return fail(DTTS_ERR_BAD_SHAPE, "dtts_text_encode_bank: a bank entry is longer than the Lk / Lp of the call (it was truncated)");
+}
+
+extern "C" int dtts_acoustic_status(dtts_acoustic* h, void* stream, int32_t sync) {
+  if (!h) return fail(DTTS_ERR_BAD_ARG, "dtts_acoustic_status: null handle");
+  if (sync) DTTS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  else if (h->bank_err_evt && cudaEventQuery(h->bank_err_evt) == cudaErrorNotReady) return DTTS_OK;   // nothing landed yet
+  return bank_status(h);
 }
 
 extern "C" uint64_t dtts_acoustic_launch_count(const dtts_acoustic* h) { return h ? h->launches : 0; }
@@ -746,7 +782,7 @@ extern "C" int dtts_text_encode(dtts_acoustic* h, const dtts_text_in* in, const 
 static size_t bank_gather_bytes(int B, int Tw, int Lk, int Lp) {
   const size_t bt = (size_t)B * Tw;
   return ws_round(bt * Lk * sizeof(float)) + 2 * ws_round(bt * Lp * sizeof(int64_t)) + ws_round(bt * sizeof(int64_t)) +
-         ws_round(bt * sizeof(int32_t)) + ws_round(sizeof(int)) + 2048;
+         ws_round(bt * sizeof(int32_t)) + 2048;
 }
 
 extern "C" uint64_t dtts_text_bank_workspace_bytes(const dtts_acoustic* h, int32_t B, int32_t Tw, int32_t Lk,
@@ -774,11 +810,21 @@ extern "C" int dtts_text_encode_bank(dtts_acoustic* h, const dtts_dict_bank* ban
   int64_t* pinyin_map = bump.take<int64_t>(bt * Lp);
   int64_t* row_off = bump.take<int64_t>(bt);
   int32_t* row_len = bump.take<int32_t>(bt);
-  int* err = bump.take<int>(1);
   if (!bump.ok) return fail(DTTS_ERR_WORKSPACE_TOO_SMALL, "dtts_text_encode_bank: workspace too small");
+  // Status word: cleared, OR-ed by the kernel (1: id >= n_entries, 2: entry wider than Lk / Lp) and copied to the
+  // handle's pinned word on the same stream.  An earlier call's status that has landed but was never collected stays
+  // sticky; it is reported by dtts_acoustic_status and by dtts_length_regulate_scan (the path's one synchronising call).
+  cudaStream_t gs = (cudaStream_t)stream;
+  if (h->bank_err_host && *h->bank_err_host && cudaEventQuery(h->bank_err_evt) == cudaSuccess) {
+    h->bank_err_sticky |= *h->bank_err_host;
+    *h->bank_err_host = 0;
+  }
+  DTTS_CUDA(cudaMemsetAsync(h->bank_err_dev, 0, sizeof(int), gs));
   DTTS_CUDA(dict_bank_gather(in->dict_ids_dev, bank->tok_offsets_dev, bank->pin_offsets_dev, bank->key_map_dev,
                              bank->pinyin_dev, bank->pinyin_map_dev, bank->n_entries, B, Tw, Lk, Lp, key_map, pinyin,
-                             pinyin_map, row_off, row_len, err, (cudaStream_t)stream));
+                             pinyin_map, row_off, row_len, h->bank_err_dev, gs));
+  DTTS_CUDA(cudaMemcpyAsync(h->bank_err_host, h->bank_err_dev, sizeof(int), cudaMemcpyDeviceToHost, gs));
+  DTTS_CUDA(cudaEventRecord(h->bank_err_evt, gs));
   h->launches++;
   dtts_text_in tin{};
   tin.word_tokens_dev = in->word_tokens_dev;
@@ -806,7 +852,7 @@ extern "C" int dtts_length_regulate_scan(dtts_acoustic* h, const int64_t* dur_in
   h->launches++;
   DTTS_CUDA(cudaMemcpyAsync(t_raw_host, totals + B, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   DTTS_CUDA(cudaStreamSynchronize(s));
-  return DTTS_OK;
+  return bank_status(h);                     // a bad dictionary id / width of the text stage surfaces at this sync
 }
 
 extern "C" int dtts_length_regulate_fill(dtts_acoustic* h, const int32_t* cum, const int64_t* ilens, int32_t B,

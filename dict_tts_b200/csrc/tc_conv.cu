@@ -18,6 +18,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <type_traits>
 
 namespace dtts {
@@ -1190,6 +1191,14 @@ static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
 }
+// The DTTS_TC_* tuning knobs, read ONCE per process (thread-safe function-local static): tc_conv_plan runs for every
+// convolution launch (~100 per vocode) and getenv is neither free nor safe against a concurrent setenv.
+struct TcEnv { int nacc, astages, tg, wstages, cluster; };
+static const TcEnv& tc_env() {
+  static const TcEnv e = {env_int("DTTS_TC_NACC", 0), env_int("DTTS_TC_ASTAGES", 0), env_int("DTTS_TC_TG", 0),
+                          env_int("DTTS_TC_WSTAGES", 0), env_int("DTTS_TC_CLUSTER", 0)};
+  return e;
+}
 
 void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq, int a_planes) {
   p->w = w.w; p->bias = w.bias;
@@ -1203,7 +1212,7 @@ void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq, int a_planes) {
   p->nq = nq;
   int nacc = 256 / p->NM;                                    // one accumulator set = 256 TMEM columns (two sets)
   if (nacc > 4) nacc = 4;
-  const int force = env_int("DTTS_TC_NACC", 0);
+  const int force = tc_env().nacc;
   if (force > 0 && force <= nacc) nacc = force;
   while (nacc > 1 && (nacc - 1) * 128 >= nq) --nacc;         // short sequences: do not compute empty sub-tiles
   p->NACC = nacc;
@@ -1216,7 +1225,7 @@ void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq, int a_planes) {
   const size_t a_stage = (size_t)(p->KC / 8) * p->RA * 16 * p->a_planes + (p->lo8 ? (size_t)(p->KC / 16) * p->RA * 16 : 0);
   // activation stages: the (tile + halo) loads come from HBM with ~1.5 us latency; short tiles (few taps, small C) need
   // more of them in flight than the 2 a long K loop gets away with.  Keep at least ~64 KB for the weight stages.
-  int as = env_int("DTTS_TC_ASTAGES", 0);
+  int as = tc_env().astages;
   if (as <= 0) as = p->lo8 ? 3 : 2;                      // measured: 3 or 4 stages do not help (profiles/r01_summary.md);
                                                          // lo8 tiles are converted in shared memory after they land: one more
   if (as > kMaxAStages) as = kMaxAStages;
@@ -1224,7 +1233,7 @@ void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq, int a_planes) {
   p->a_stages = as;
   const size_t w_tap = (size_t)(p->pair ? p->NM / 2 : p->NM) * p->KC * (2 * p->w_planes + (p->lo8 ? 1 : 0));   // per CTA
   // taps per weight stage: ~32 KB stages, so that the per-stage barrier round trip is amortised over >= 8 MMAs
-  int tg = env_int("DTTS_TC_TG", 0);
+  int tg = tc_env().tg;
   if (tg <= 0) tg = (int)((32 * 1024) / w_tap);
   if (tg < 1) tg = 1;
   if (tg > p->ktaps) tg = p->ktaps;
@@ -1234,7 +1243,7 @@ void tc_conv_plan(TcConvParams* p, const TcConvW& w, int nq, int a_planes) {
   const size_t budget = kSmemLimit - kSmemHeader - p->a_stages * a_stage;
   int ws = (int)(budget / w_blob);
   if (ws > kMaxWStages) ws = kMaxWStages;
-  const int force_ws = env_int("DTTS_TC_WSTAGES", 0);
+  const int force_ws = tc_env().wstages;
   if (force_ws > 0 && force_ws < ws) ws = force_ws;
   p->w_stages = ws;
   p->csize = 1;
@@ -1255,20 +1264,25 @@ static size_t tc_smem_bytes(const TcConvParams& p) {
 }
 
 int tc_pair_enabled() {
-  static int v = -1;
-  if (v < 0) v = env_int("DTTS_TC_PAIR", 1) != 0;
+  static const int v = env_int("DTTS_TC_PAIR", 1) != 0;
   return v;
 }
 
 int tc_lo8_min_taps() {
-  static int v = -1;
-  if (v < 0) v = env_int("DTTS_TC_LO8_MINTAPS", 7);
+  static const int v = env_int("DTTS_TC_LO8_MINTAPS", 7);
   return v;
 }
 
-static int g_num_sms = 0;
-static int g_max_clusters[9] = {0};     // [csize] -> co-resident clusters of tc_conv_kernel<false> (0 = not queried yet)
-static int g_max_pairs = 0;             // co-resident CTA pairs of tc_conv_kernel<true>
+// Occupancy facts of the device a launch goes to, cached PER DEVICE ORDINAL (one process may drive several GPUs, e.g.
+// the reference-plugin path) and filled under a mutex (several host threads, one handle each).
+struct DevInfo {
+  int num_sms = 0;
+  int max_clusters[9] = {0};     // [csize] -> co-resident clusters of tc_conv_kernel<false> (0 = not queried yet)
+  int max_pairs = 0;             // co-resident CTA pairs of tc_conv_kernel<true>
+};
+constexpr int kMaxDevices = 64;
+static DevInfo g_dev[kMaxDevices];
+static std::mutex g_dev_mu;
 
 // Cluster size (CTAs sharing every weight stage through multicast).  Measured on B200 at the cfg-2 vocoder shapes
 // (profiles/r01_summary.md): 1 -> 35.2 ms, 2 -> 36.0 ms, 4 -> 36.0 ms per pass; the weight stream (<= 3.8 TB/s out of
@@ -1276,7 +1290,7 @@ static int g_max_pairs = 0;             // co-resident CTA pairs of tc_conv_kern
 static int pick_cluster(const TcConvParams& p, long row_tiles) {
   if (p.pair) return 2;
   if (p.lo8) return 1;
-  int c = env_int("DTTS_TC_CLUSTER", 0);
+  int c = tc_env().cluster;
   if (c <= 0) c = 1;
   while (c > 1 && (row_tiles < c || (p.NM * p.KC * 2 * p.w_planes) % (16 * c))) c >>= 1;
   return c;
@@ -1297,10 +1311,19 @@ cudaError_t launch_tc_conv(TcConvParams p, int B, cudaStream_t stream) {
   if (p.a_pad + p.min_off < 0 || p.a_pad + p.ntiles * p.MT + max_off > p.a_rows) return cudaErrorInvalidValue;
   const size_t smem = tc_smem_bytes(p);
   if (smem > (size_t)kSmemLimit) return cudaErrorInvalidConfiguration;
-  if (g_num_sms == 0) {
-    int dev = 0;
+  int dev = 0;
+  {
     cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  }
+  std::lock_guard<std::mutex> lock(g_dev_mu);      // the queries below run once per (device, cluster size)
+  DevInfo& di = g_dev[dev];
+  int& g_num_sms = di.num_sms;
+  int& g_max_pairs = di.max_pairs;
+  int (&g_max_clusters)[9] = di.max_clusters;
+  if (g_num_sms == 0) {
+    cudaError_t e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
   }
   p.B = B;

@@ -553,12 +553,12 @@ __global__ void dict_bank_gather_kernel(const int64_t* __restrict__ ids, const i
   int nl = 0, np = 0;
   if (id >= 0) {
     if (id >= n_entries) {
-      if (threadIdx.x == 0) atomicExch(err, 1);
+      if (threadIdx.x == 0) atomicOr(err, 1);
     } else {
       t0 = tok_off[id]; nl = (int)(tok_off[id + 1] - t0);
       p0 = pin_off[id]; np = (int)(pin_off[id + 1] - p0);
       if (nl > Lk || np > Lp) {
-        if (threadIdx.x == 0) atomicExch(err, 2);
+        if (threadIdx.x == 0) atomicOr(err, 2);
         nl = min(nl, Lk); np = min(np, Lp);
       }
     }

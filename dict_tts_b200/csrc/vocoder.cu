@@ -436,7 +436,6 @@ extern "C" int dtts_vocode(dtts_vocoder* h, const float* mel, int32_t B, int32_t
 extern "C" int dtts_vocode_lens(dtts_vocoder* h, const float* mel, const int32_t* lens_dev, int32_t B, int32_t T,
                                 float* wav, void* ws, uint64_t ws_bytes, void* stream) {
   if (!lens_dev) return fail(DTTS_ERR_BAD_ARG, "dtts_vocode_lens: null lengths");
-  if (B > TC_MAX_RAGGED_ITEMS) return fail(DTTS_ERR_BAD_SHAPE, "dtts_vocode_lens: at most 512 items per call");
   return vocode_impl(h, mel, lens_dev, B, T, wav, ws, ws_bytes, stream);
 }
 
@@ -447,7 +446,17 @@ static int vocode_impl(dtts_vocoder* h, const float* mel, const int32_t* lens, i
   if (ws_bytes < dtts_vocode_workspace_bytes(h, B, T))
     return fail(DTTS_ERR_WORKSPACE_TOO_SMALL, "dtts_vocode: workspace too small");
   const dtts_vocoder_desc& d = h->desc;
-  if (d.precision != 0) return tc_vocode(h, mel, B, T, wav, ws, ws_bytes, (cudaStream_t)stream, lens);
+  if (d.precision != 0) {
+    if (!lens || B <= TC_MAX_RAGGED_ITEMS) return tc_vocode(h, mel, B, T, wav, ws, ws_bytes, (cudaStream_t)stream, lens);
+    // the ragged tile schedule keeps its per-item tables in shared memory (TC_MAX_RAGGED_ITEMS): larger batches run as
+    // consecutive sub-batches on the same workspace (same stream, so they serialise on it)
+    for (int b0 = 0; b0 < B; b0 += TC_MAX_RAGGED_ITEMS) {
+      const int nb = B - b0 < TC_MAX_RAGGED_ITEMS ? B - b0 : TC_MAX_RAGGED_ITEMS;
+      DTTS_TRY(tc_vocode(h, mel + (size_t)b0 * T * d.n_mel, nb, T, wav + (size_t)b0 * T * h->hop, ws, ws_bytes,
+                         (cudaStream_t)stream, lens + b0));
+    }
+    return DTTS_OK;
+  }
   Bump bump(ws, ws_bytes);
   float* buf[5];
   for (int i = 0; i < 5; ++i) buf[i] = bump.take<float>((size_t)B * T * h->unit);

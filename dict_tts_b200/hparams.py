@@ -129,7 +129,8 @@ def set_hparams(config: str = "", exp_name: str = "", hparams_str: str = "", pri
         cfg.update(_load_chain(config, set(), chain, root))
     if not reset:
         cfg.update(saved)
-    cfg["work_dir"] = work_dir
+    # the reference always runs from its repo root; with an explicit root the checkpoint directory follows it
+    cfg["work_dir"] = os.path.join(root, work_dir) if (root and work_dir) else work_dir
     apply_overrides(cfg, hparams_str)
     cfg.update(infer=infer, debug=debug, validate=validate, exp_name=exp_name)
     if global_hparams:

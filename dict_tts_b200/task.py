@@ -187,7 +187,10 @@ class B200DictTTSTask:
         results = []
         for b in range(B):
             name, text = sample["item_name"][b], sample["text"][b]
-            base_fn = f'[{self.rank}_{self.results_id:06d}][{str(name).replace("%", "_")}][%s]'
+            # the reference numbers its files with results_id = position in the (un-shuffled, B = 1) test set; batches
+            # here arrive longest-first and per rank, so the dataset index is that number
+            uid = int(sample["id"][b]) if "id" in sample else self.results_id
+            base_fn = f'[{uid:06d}][{str(name).replace("%", "_")}][%s]'
             if text is not None:
                 base_fn += str(text).replace(":", "$3A")[:80]
             base_fn = base_fn.replace(" ", "_")
@@ -208,16 +211,42 @@ class B200DictTTSTask:
                     for t in pairs[b, i].tolist():
                         if t >= 0:
                             tokens.append(self.pinyin_encoder[int(t)])
-            results.append(dict(item_name=name, text=None if text is None else str(text).replace(",", "，").replace(".", "。"),
+            results.append(dict(id=uid, item_name=name,
+                                text=None if text is None else str(text).replace(",", "，").replace(".", "。"),
                                 pinyin_tokens=" ".join(tokens), wav_fn_pred=base_fn % "P", wav_fn_gt=base_fn % "G"))
             self.results_id += 1
         return results
 
-    def test_end(self, outputs: List[Dict]):
-        path = os.path.join(self.gen_dir, "meta.csv" if self.world == 1 else f"meta.rank{self.rank}.csv")
+    META_FIELDS = ["item_name", "text", "pinyin_tokens", "wav_fn_pred", "wav_fn_gt"]
+
+    @classmethod
+    def write_meta(cls, path: str, rows: List[Dict]) -> None:
+        """meta.csv exactly as the reference writes it, ``pd.DataFrame(outputs).to_csv`` (tts_base.py:371-372): a
+        leading unnamed index column, then the result fields, one row per utterance in DATASET order -- the order
+        scripts/get_pron_error.py aligns against label_set0.csv, reading the pinyin tokens as ``line.split(',')[3]``."""
+        rows = sorted(rows, key=lambda r: r.get("id", 0))
         with open(path, "w", newline="") as f:
-            w = csv.DictWriter(f, fieldnames=["item_name", "text", "pinyin_tokens", "wav_fn_pred", "wav_fn_gt"])
-            w.writeheader()
-            for r in outputs:
-                w.writerow(r)
+            w = csv.writer(f, lineterminator="\n")
+            w.writerow([""] + cls.META_FIELDS)
+            for i, r in enumerate(rows):
+                w.writerow([i] + ["" if r.get(k) is None else r[k] for k in cls.META_FIELDS])
+
+    def test_end(self, outputs: List[Dict]):
+        """One ordered meta.csv.  With several ranks every rank leaves its rows (with dataset ids) in a side file and
+        rank 0 merges them after the barrier."""
+        if self.world == 1:
+            self.write_meta(os.path.join(self.gen_dir, "meta.csv"), outputs)
+            return {}
+        import torch.distributed as dist
+        with open(os.path.join(self.gen_dir, f"meta.rank{self.rank}.pkl"), "wb") as f:
+            pickle.dump(outputs, f)
+        dist.barrier()
+        if self.rank == 0:
+            rows = []
+            for r in range(self.world):
+                part = os.path.join(self.gen_dir, f"meta.rank{r}.pkl")
+                with open(part, "rb") as f:
+                    rows.extend(pickle.load(f))
+                os.remove(part)
+            self.write_meta(os.path.join(self.gen_dir, "meta.csv"), rows)
         return {}

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DTTS_ABI_VERSION 3
+#define DTTS_ABI_VERSION 4
 
 typedef enum dtts_status {
   DTTS_OK = 0,
@@ -154,6 +154,13 @@ typedef struct dtts_text_in_bank {
 uint64_t dtts_text_bank_workspace_bytes(const dtts_acoustic* h, int32_t B, int32_t Tw, int32_t Lk, int32_t Lp);
 int dtts_text_encode_bank(dtts_acoustic* h, const dtts_dict_bank* bank, const dtts_text_in_bank* in,
                           const dtts_text_out* out, void* ws_dev, uint64_t ws_bytes, void* stream);
+/* Deferred status of the dictionary-bank gather.  dtts_text_encode_bank does not synchronise, so a dict_id >=
+ * bank.n_entries (DTTS_ERR_BAD_ARG; the character was encoded as an all-zero row) or a bank entry wider than the call's
+ * Lk / Lp (DTTS_ERR_BAD_SHAPE; it was truncated) is recorded in a pinned status word when the gather kernel has run.  It
+ * is reported -- once -- by the next dtts_length_regulate_scan on the handle (the path's synchronising call) or by this
+ * query: sync != 0 synchronises `stream` first, sync == 0 only looks at what has already landed.  The reference's own
+ * behaviour for a bad index is a Python IndexError in the collater (tasks/tts/dataset_utils.py:312-330). */
+int dtts_acoustic_status(dtts_acoustic* h, void* stream, int32_t sync);
 
 /* Length regulator (modules/fastspeech/tts_modules.py:215-251).  Step 1 scans durations on the device and
  * returns the longest utterance in *t_raw_host -- this call SYNCHRONISES the stream (the one data-dependent shape
@@ -187,7 +194,8 @@ uint64_t dtts_vocode_workspace_bytes(const dtts_vocoder* h, int32_t B, int32_t T
 int dtts_vocode(dtts_vocoder* h, const float* mel_dev, int32_t B, int32_t T, float* wav_dev, void* ws_dev,
                 uint64_t ws_bytes, void* stream);
 /* The same with the valid length of every item (extension; SURVEY.md §8b: spec2wav_batch(mel, lengths)).
- * lens_dev: int32 [B], valid mel frames per item (0 <= lens[b] <= T), B <= 512.  wav[b, t] for t < lens[b]*hop is bit
+ * lens_dev: int32 [B], valid mel frames per item (0 <= lens[b] <= T); more than 512 items run as consecutive
+ * sub-batches of 512 on the same workspace.  wav[b, t] for t < lens[b]*hop is bit
  * for bit what dtts_vocode writes (the frames after lens[b] still feed the receptive field of the last valid samples,
  * exactly as in the full-length call); samples past lens[b]*hop are written as 0 and the rows only they depend on are
  * not computed -- DictTTSTask.after_infer never looks at them (B = 1 upstream; here the task trims to the valid length). */

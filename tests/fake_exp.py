@@ -13,8 +13,8 @@ import numpy as np
 import torch
 import yaml
 
-from . import synth
-from .data import IndexedDatasetBuilder
+from dict_tts_b200 import synth
+from dict_tts_b200.data import IndexedDatasetBuilder
 
 HPARAMS = dict(
     task_cls="tasks.tts.dict_tts.DictTTSTask", vocoder="HifiGAN", hidden_size=192, num_heads=2,

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from dict_tts_b200 import fake_exp
+from tests import fake_exp
 from dict_tts_b200.batching import batch_by_size, build_batch_sampler, ordered_indices
 from dict_tts_b200.data import DictTTSTestSet
 

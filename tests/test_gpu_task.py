@@ -7,7 +7,8 @@ import numpy as np
 import pytest
 import torch
 
-from dict_tts_b200 import fake_exp, hparams as hp_mod, synth
+from dict_tts_b200 import hparams as hp_mod, synth
+from tests import fake_exp
 from dict_tts_b200.config import AcousticConfig, VocoderConfig
 from dict_tts_b200.data import DictTTSTestSet
 from dict_tts_b200.weights import fold_weight_norm
@@ -162,6 +163,41 @@ def test_dictionary_bank_path_equals_explicit_dict_msg():
             want = O.acoustic_forward(W, AcousticConfig(), exp, batch["mel2word"], batch["z_p"])
         assert (out["mel_out"].cpu() - want["mel_out"]).abs().max() < TOL_MEL_MAXABS
         assert (out["dict_attn"].cpu() - want["dict_attn"]).abs().max() < 1e-5
+    eng.close()
+
+
+def test_bank_gather_reports_bad_ids_and_widths():
+    """dtts_text_encode_bank does not synchronise: an id outside the bank / an entry wider than the call's Lk, Lp is
+    recorded on the device and reported once -- by dtts_acoustic_status or at the sync of dtts_length_regulate_scan --
+    instead of silently becoming a zero / truncated row."""
+    import ctypes as C
+    from dict_tts_b200 import binding
+    from dict_tts_b200.bank import DictBank
+    from dict_tts_b200.engine import DictTTSEngine
+    eng = DictTTSEngine(synth.make_acoustic_state_dict(1234))
+    lib = binding.load()
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    batch = synth.make_batch(seed=61, B=2, min_chars=4, max_chars=6, max_frames=40, Lk_cap=48)
+    bank, ids = DictBank.from_batch(batch)
+    eng.set_dict_bank(bank)
+    Lk, Lp = bank.batch_dims(ids)
+    good = eng.text_encode_bank(batch["word_tokens"], batch["pron_modified"], ids, Lk, Lp)
+    assert lib.dtts_acoustic_status(eng.handle, stream, 1) == 0
+    bad = ids.clone()
+    bad[0, 1] = bank.n_entries + 5                       # explicit widths: the host-side validation is skipped
+    eng.text_encode_bank(batch["word_tokens"], batch["pron_modified"], bad, Lk, Lp)
+    assert lib.dtts_acoustic_status(eng.handle, stream, 1) == binding.DTTS_ERR_BAD_ARG
+    assert b"n_entries" in lib.dtts_last_error()
+    assert lib.dtts_acoustic_status(eng.handle, stream, 1) == 0          # reported once
+    if Lk > 1:
+        out = eng.text_encode_bank(batch["word_tokens"], batch["pron_modified"], ids, Lk - 1, Lp)
+        with pytest.raises(RuntimeError, match="longer than"):          # surfaces at the length regulator's sync
+            eng.length_regulate(out["dur_int"], out["ilens"])
+    again = eng.text_encode_bank(batch["word_tokens"], batch["pron_modified"], ids, Lk, Lp)
+    assert lib.dtts_acoustic_status(eng.handle, stream, 1) == 0
+    assert torch.equal(again["word_encoder_out"], good["word_encoder_out"])
+    with pytest.raises(ValueError):                                      # without widths the ids are validated on the host
+        eng.text_encode_bank(batch["word_tokens"], batch["pron_modified"], bad)
     eng.close()
 
 

@@ -324,15 +324,20 @@ def test_fp8_lo_plane_is_refused_for_weights_that_would_overflow():
     assert not torch.equal(o3s, o6s)                            # ordinary weights: the FP8 path really runs
 
 
-def test_vocode_with_lengths_rejects_more_than_512_items():
-    """The ragged tile schedule keeps one prefix entry per item in shared memory (TC_MAX_RAGGED_ITEMS): a larger batch is an
-    error, not a silent full-length call; without lengths the same batch is fine."""
+@pytest.mark.parametrize("precision", [0, 6])
+def test_vocode_with_lengths_more_than_512_items(precision):
+    """The ragged tile schedule keeps one prefix entry per item in shared memory (TC_MAX_RAGGED_ITEMS = 512): a larger
+    batch runs as consecutive sub-batches of 512, and the fp32 path (precision 0, no tile schedule) has no limit at all.
+    Valid samples equal the full-length call bit for bit either way."""
     from dict_tts_b200.engine import HifiGanEngine
-    eng = HifiGanEngine(synth.make_vocoder_state_dict(VOCODER_SEED))
-    mel = synth.make_mel(3, 513, 4)
-    with pytest.raises(RuntimeError, match="512"):
-        eng(mel, torch.full((513,), 4))
-    assert eng(mel).shape == (513, 4 * 256)
-    part = eng(mel[:512], torch.arange(512) % 5)
-    assert (part[0] == 0).all() and (part[4] != 0).any()
+    eng = HifiGanEngine(synth.make_vocoder_state_dict(VOCODER_SEED), precision=precision)
+    mel = synth.make_mel(3, 515, 4)
+    lens = torch.arange(515) % 5
+    full = eng(mel)
+    assert full.shape == (515, 4 * 256)
+    part = eng(mel, lens)
+    for b in (0, 1, 4, 511, 512, 513, 514):
+        n = int(lens[b]) * 256
+        assert torch.equal(part[b, :n], full[b, :n]), (precision, b)
+        assert (part[b, n:] == 0).all(), (precision, b)
     eng.close()

@@ -11,7 +11,8 @@ import pytest
 import torch
 import yaml
 
-from dict_tts_b200 import fake_exp, hparams as hp_mod, synth
+from dict_tts_b200 import hparams as hp_mod, synth
+from tests import fake_exp
 from dict_tts_b200.config import AcousticConfig, VocoderConfig
 from dict_tts_b200.data import DictTTSTestSet, IndexedDataset, IndexedDatasetBuilder
 from dict_tts_b200.weights import (fold_weight_norm, get_last_checkpoint, load_acoustic_checkpoint,
@@ -55,7 +56,7 @@ def test_saved_config_overrides_chain_unless_reset(tmp_path):
     a = hp_mod.set_hparams("c.yaml", "e1", "", root=str(tmp_path), global_hparams=False)
     b = hp_mod.set_hparams("c.yaml", "e1", "", root=str(tmp_path), global_hparams=False, reset=True)
     assert a["hidden_size"] == 128 and b["hidden_size"] == 192 and a["hop_size"] == 256
-    assert a["work_dir"] == "checkpoints/e1"
+    assert a["work_dir"] == os.path.join(str(tmp_path), "checkpoints/e1")       # follows root (cwd-relative without one)
     with pytest.raises(ValueError):
         hp_mod.set_hparams("", "", "", argv=[])
 
@@ -240,3 +241,33 @@ def test_dict_ids_from_words():
     w2i = {"<pad>": 0, "<EOS>": 1, "<UNK>": 2, "<BOS>": 3, "a": 4, "b": 5}
     ids = ids_from_words([["<BOS>", "a", "b", "<EOS>"], ["<BOS>", "zz", "<EOS>"]], w2i, 5)
     assert ids.tolist() == [[-1, 4, 5, -2, -1], [-1, 2, -2, -2, -1]]     # column 0 and Tw-1: the collater's added rows
+
+
+def test_meta_csv_is_what_get_pron_error_reads(tmp_path):
+    """meta.csv must parse the way scripts/get_pron_error.py reads it (reference: pd.DataFrame(outputs).to_csv,
+    tts_base.py:371-372): a leading index column, the pinyin tokens in line.split(',')[3], one row per utterance in
+    dataset order -- whatever order (longest-first batches, several ranks) the rows were produced in."""
+    from dict_tts_b200.task import B200DictTTSTask
+    rows = [dict(id=i, item_name=f"utt{i}", text=f"文本{i}", pinyin_tokens=f"a{i} 1 b{i} 4",
+                 wav_fn_pred=f"[{i:06d}][utt{i}][P]", wav_fn_gt=f"[{i:06d}][utt{i}][G]") for i in (3, 0, 2, 1)]
+    path = str(tmp_path / "meta.csv")
+    B200DictTTSTask.write_meta(path, rows)
+    with open(path) as f:
+        lines = f.readlines()
+    assert lines[0].strip() == ",item_name,text,pinyin_tokens,wav_fn_pred,wav_fn_gt"
+    pred = []
+    for line in lines[1:]:                                  # scripts/get_pron_error.py:31-44
+        label = line.split(',')[3].replace('<UNK> ', '').replace('\n', '').split(' ')
+        pron, out = '', []
+        for i, item in enumerate(label):
+            pron += item
+            if i % 2 == 1:
+                out.append(pron)
+                pron = ''
+        pred.append(" ".join(out))
+    assert pred == [f"a{i}1 b{i}4" for i in range(4)]
+    assert [line.split(',')[0] for line in lines[1:]] == ["0", "1", "2", "3"]
+    import pandas as pd                                     # and it is byte for byte what pandas writes
+    ref = str(tmp_path / "ref.csv")
+    pd.DataFrame([{k: r[k] for k in B200DictTTSTask.META_FIELDS} for r in sorted(rows, key=lambda r: r["id"])]).to_csv(ref)
+    assert open(ref).read() == open(path).read()
