@@ -1,16 +1,26 @@
 """Benchmark of the Dict-TTS text -> mel -> waveform forward pass (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--quick]
 
-One "step" = one pass of the hot path over one Biaobei-shaped synthetic batch (cfg 2 of BASELINE.json: batch 60,
-<= 22 word tokens, L_k <= 96 gloss tokens, 400 mel frames, fp32, full text -> mel -> HiFi-GAN).  With N > 1 the
-driver launches this file under torchrun: every rank owns one GPU and one independent batch (weak scaling,
-SURVEY.md §8e), rank 0 broadcasts the weight arenas over NCCL once at load and there is no hot-path collective.
-Rank 0 prints ONE JSON line.
+One "step" = one pass of the hot path over one Biaobei-shaped synthetic batch -- cfg 2 of BASELINE.json (batch 60,
+<= 22 word tokens, L_k <= 96 gloss tokens, 400 mel frames, full text -> mel -> HiFi-GAN); it is the headline line.
+With N > 1 the driver launches this file under torchrun: every rank owns one GPU and one independent batch (weak
+scaling), rank 0 broadcasts the weight arenas over NCCL once at load and there is no hot-path collective.
+Rank 0 prints ONE JSON line.  At N = 1 the same line also carries (key "configs") the other BASELINE.json
+configurations -- cfg 1 (single 64-character utterance, with the reference's CPU path timed on all threads and on one,
+min and median), cfg 3 (bf16 tensor-core mode, with its measured error) and cfg 4 (vocoder only,
+256 x 32 frames, its own roofline) -- the fp32-class precision mode of cfg 2 ("fp32_class"), the stage rooflines
+("roofline_stages") and the PyTorch-eager-on-GPU library baselines.
+
+`--impl reference` times the reference's own CPU implementation of the path on the host cores: the UNMODIFIED reference
+modules through oracle/ref_loader.py when a reference tree is present (/root/reference in the build container,
+baseline/_ref on a pod that has one; cpu_baseline.kind = "reference"), otherwise the oracle port (kind = "port").  It
+runs the way the reference's inference runs: one utterance at a time (tasks/tts/dict_tts.py:229), un-padded.
 """
 import argparse
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -26,11 +36,36 @@ from dict_tts_b200 import synth  # noqa: E402
 from dict_tts_b200.config import HOP_SIZE, SAMPLE_RATE, AcousticConfig, VocoderConfig  # noqa: E402
 from dict_tts_b200.weights import drop_dead, fold_weight_norm, pack_arena  # noqa: E402
 
-# algorithmic work model (checked against torch FlopCounterMode on the reference)
+# ---- algorithmic work model (checked against torch FlopCounterMode on the reference) ----
 VOCODER_FLOP_PER_FRAME = 614.1e6
-TC_CONV_DRAM_BYTES_PER_LAUNCH = 1.076e9   # measured (ncu): 82.9 GB over the 77 launches of a valid-length pass (95.5 GB full length)
-WORKLOAD = dict(B=60, min_chars=12, max_chars=20, max_frames=400, Lk_cap=96)
+VOCODER_BYTES_PER_FRAME = 1344            # fully fused: 80 * 4 in + 256 * 4 out
+DECODER_FLOP_PER_FRAME = 4.69e6           # WN decoder 4.09 + prior flow 0.45 + g_pre_net 0.15 MFLOP
+DECODER_BYTES_PER_FRAME = 1104            # fully fused: g 768 + z 16 + mel 320
+ENCODER_FLOP_PER_TOKEN = 16.6e6           # 8 encoder layers
+S2PA_BYTES_PER_GLOSS_TOKEN = 6144         # keys + values rows, fp32 (3072 when values alias keys)
+LR_BYTES_PER_FRAME = 1536
+# ncu dram__bytes_read + dram__bytes_write of one valid-length vocode pass at cfg 2 (profiles/, see traffic_source)
+TC_CONV_DRAM_BYTES_PER_STEP = 82.9e9
+TC_CONV_TRAFFIC_SOURCE = ("profiles/r01_vocoder_lens_dram_agg.txt: ncu dram__bytes_read+write summed over the 77 "
+                          "tc_conv_kernel launches of one valid-length vocode pass = 82.9 GB (1.076 GB per launch). "
+                          "Byte models: SURVEY 8d fully-fused algorithmic 1344 B/frame = 27.8 MB per step (0.36 MB per "
+                          "launch); this design's unfused per-layer model 83 GB per step -- the measured traffic equals "
+                          "the latter, i.e. it is ~3000x the fully-fused figure and is what the layer-by-layer design costs")
+WORKLOADS = {
+    "cfg1": dict(B=1, min_chars=64, max_chars=64, max_frames=1280, Lk_cap=96),
+    "cfg2": dict(B=60, min_chars=12, max_chars=20, max_frames=400, Lk_cap=96),
+}
+CFG4 = dict(B=256, T=32)
+N_TC_CONV_LAUNCHES = 1 + 4 + 72          # conv_pre, 4 transposed convolutions, 72 ResBlock convolutions per vocode pass
 CPU_SAMPLE_UTTS = 30      # ~10 k of the batch's 20.7 k frames: 10-20 s of host work for the two timed passes
+VOC_DTYPE = {0: "f32", 1: "f32-class (bf16 hi/lo x hi/lo on tcgen05: 3 MMAs per product, fp32 accumulate)",
+             2: "bf16 (tcgen05, 1 MMA)", 3: "fp16 activations x fp16 hi/lo weights (tcgen05, 2 MMAs, fp32 accumulate)",
+             4: "fp16 (tcgen05, 1 MMA)", 5: "fp16 x fp16, hi/lo weights only where C_out < 128 (tcgen05)",
+             6: "fp16 activations x fp16 hi/lo weights, lo plane of the C_out >= 128 layers as e5m2 (tcgen05, fp32 accumulate)"}
+VOC_KERNEL = {0: "conv1d_f32_kernel (fp32 FMA pipe)", 1: "tc_conv_kernel (tcgen05, bf16 hi/lo x hi/lo: 3 MMAs per product)",
+              2: "tc_conv_kernel (tcgen05, bf16: 1 MMA)", 3: "tc_conv_kernel (tcgen05, fp16 x fp16 hi/lo weights: 2 MMAs)",
+              4: "tc_conv_kernel (tcgen05, fp16: 1 MMA)", 5: "tc_conv_kernel (tcgen05, fp16; hi/lo weights only where C_out < 128)",
+              6: "tc_conv_kernel (tcgen05, fp16 x fp16 hi/lo weights: 2 MMAs; lo plane in FP8 where C_out >= 128: 1.5)"}
 
 
 def load_peaks():
@@ -38,8 +73,9 @@ def load_peaks():
     if os.path.exists(path):
         with open(path) as f:
             p = json.load(f)
-        return dict(hbm_gbs=p["hbm_gbs"], tflops=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
-    return dict(hbm_gbs=6650.0, tflops=1400.0, source="fallback")
+        return dict(hbm_gbs=p["hbm_gbs"], tflops=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    tflops_burst=p["bf16_tflops"], source="measured")
+    return dict(hbm_gbs=6650.0, tflops=1400.0, tflops_burst=1650.0, source="fallback")
 
 
 class ClockSampler:
@@ -87,38 +123,103 @@ class ClockSampler:
         return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
 
 
-def cpu_port_run(batch, n_utts, threads, iters):
-    """The oracle port (own-words restatement of the reference's PyTorch CPU forward, oracle/dtts_oracle.py) on the
-    host cores, on the first n_utts utterances of the same batch.  Returns (frames/s, seconds per pass, frames)."""
+# ---------------------------------------------------------------------------------------------------------------
+# the reference's CPU path
+# ---------------------------------------------------------------------------------------------------------------
+def slice_utt(batch, b):
+    """Utterance b of a collated batch as the reference's own inference sees it: a batch of ONE (max_sentences = 1,
+    tasks/tts/dict_tts.py:229), i.e. without the batch's padding in any dimension."""
+    n = int(batch["word_lengths"][b])
+    T = int(batch["mel_lengths"][b])
+    km = batch["key_map"][b:b + 1, :n]
+    pm = batch["pinyin_map"][b:b + 1, :n]
+    Lk = max(int((km != 0).any(0).any(0).nonzero().max()) + 1, 1)
+    Lp = max(int((pm != 0).any(0).any(0).nonzero().max()) + 1, 1)
+    keys = batch["keys"][b:b + 1, :n, :Lk].contiguous()
+    values = keys if batch["values"] is batch["keys"] else batch["values"][b:b + 1, :n, :Lk].contiguous()
+    T4 = (T + 3) // 4
+    return dict(word_tokens=batch["word_tokens"][b:b + 1, :n], pron_modified=batch["pron_modified"][b:b + 1, :n],
+                keys=keys, values=values, key_map=km[:, :, :Lk].contiguous(),
+                pinyin=batch["pinyin"][b:b + 1, :n, :Lp].contiguous(), pinyin_map=pm[:, :, :Lp].contiguous(),
+                word_lengths=batch["word_lengths"][b:b + 1], mel2word=batch["mel2word"][b:b + 1, :T],
+                z_p=batch["z_p"][b:b + 1, :, :T4].contiguous(), mel_lengths=batch["mel_lengths"][b:b + 1])
+
+
+class CpuReference:
+    """text -> mel -> wav of one utterance on the host: the unmodified reference modules when a reference tree is
+    present (kind 'reference'), else the oracle port (kind 'port').  Test / baseline infrastructure only."""
+
+    def __init__(self, force_port=False):
+        from oracle import ref_loader
+        self.cfg, self.vcfg = AcousticConfig(), VocoderConfig()
+        a_sd, v_sd = synth.make_acoustic_state_dict(1234), synth.make_vocoder_state_dict(4321)
+        self.kind = "port"
+        force_port = force_port or os.environ.get("DTTS_BENCH_FORCE_PORT", "0") == "1"     # A/B: port vs real reference
+        if not force_port and ref_loader.available():
+            try:
+                self.model, self.voc = ref_loader.build_models(a_sd, v_sd)
+                self.kind = "reference"
+                self.root = ref_loader.REF_ROOT
+            except Exception as e:                       # noqa: BLE001 -- a broken tree must not cost the arm
+                print(f"reference tree at {ref_loader.REF_ROOT} not usable ({e!r}); timing the oracle port", file=sys.stderr)
+        if self.kind == "port":
+            self.W, self.Wv = fold_weight_norm(a_sd), fold_weight_norm(v_sd)
+
+    @torch.no_grad()
+    def run_utt(self, u):
+        """PortaSpeech_dict.forward(infer=True) with supplied durations (profile_infer, dict_tts.py:194) at B = 1, then
+        spec2wav on the un-padded mel (vocoders/hifigan.py:54-62)."""
+        T = int(u["mel_lengths"][0])
+        if self.kind == "reference":
+            import torch.distributions as D
+            orig, z = D.Normal.sample, u["z_p"]
+            D.Normal.sample = lambda self_, shape=torch.Size(): z.clone()     # the engine arm is given the same prior sample
+            try:
+                ret = self.model((u["word_tokens"], u["word_tokens"]), u["pron_modified"], (None, None, None),
+                                 ph2word=None, word_len=u["word_lengths"].max(),
+                                 dict_msg=(u["keys"], u["values"], u["key_map"], u["pinyin"], u["pinyin_map"]),
+                                 infer=True, forward_post_glow=False, spk_embed=None, two_stage=True,
+                                 mel2word=u["mel2word"])
+            finally:
+                D.Normal.sample = orig
+            mel = ret["mel_out"][0, :T]                                          # after_infer hands spec2wav one [T,80] mel
+            return self.voc(mel.T.unsqueeze(0)).view(-1)
+        from oracle import dtts_oracle as O
+        ret = O.acoustic_forward(self.W, self.cfg, u, u["mel2word"], u["z_p"])
+        return O.hifigan_forward(self.Wv, self.vcfg, ret["mel_out"][:, :T]).view(-1)
+
+    def time_passes(self, utts, threads, iters, warm_utts=1):
+        """Seconds of `iters` passes over the list of utterances (after `warm_utts` untimed ones)."""
+        torch.set_num_threads(threads)
+        for u in utts[:warm_utts]:
+            self.run_utt(u)
+        secs = []
+        for _ in range(iters):
+            t0 = time.perf_counter()
+            for u in utts:
+                self.run_utt(u)
+            secs.append(time.perf_counter() - t0)
+        return secs
+
+
+def cpu_stats(secs, frames):
+    return dict(min_s=min(secs), median_s=statistics.median(secs), iters=len(secs),
+                frames_per_s=frames / min(secs), frames_per_s_median=frames / statistics.median(secs),
+                x_realtime=frames * HOP_SIZE / SAMPLE_RATE / min(secs))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PyTorch eager on the GPU: the "library kernels" bar (cuDNN / cuBLAS), SURVEY.md §8d
+# ---------------------------------------------------------------------------------------------------------------
+def eager_gpu_run(batch, dev, mode, iters=2):
+    """The restatement of the reference's PyTorch forward (oracle/dtts_oracle.py), run as PyTorch eager ON THE GPU, whole
+    cfg-2 batch, vocoder batched (kinder than the reference's one utterance at a time).  mode: 'fp32' (TF32 off, what
+    the reference's amp: false means), 'tf32' (cuDNN / cuBLAS allowed to use TF32 tensor cores), 'fp16' (autocast).
+    Returns (frames/s, ms)."""
     from oracle import dtts_oracle as O
-    torch.set_num_threads(threads)
-    cfg, vcfg = AcousticConfig(), VocoderConfig()
-    W = fold_weight_norm(synth.make_acoustic_state_dict(1234))
-    Wv = fold_weight_norm(synth.make_vocoder_state_dict(4321))
-    sub = {k: (v[:n_utts].contiguous() if torch.is_tensor(v) else v) for k, v in batch.items()}
-    frames = int(sub["mel_lengths"].sum())
-
-    def once():
-        with torch.no_grad():
-            ret = O.acoustic_forward(W, cfg, sub, sub["mel2word"], sub["z_p"])
-            wavs = [O.hifigan_forward(Wv, vcfg, ret["mel_out"][b:b + 1]) for b in range(n_utts)]  # spec2wav is B=1
-        return wavs
-    best = None
-    for _ in range(iters):
-        t0 = time.perf_counter()
-        once()
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return frames / best, best, frames
-
-
-def eager_gpu_run(batch, dev, iters=2):
-    """The same restatement of the reference's PyTorch forward (oracle/dtts_oracle.py), run as PyTorch eager ON THE GPU:
-    the 'library kernels' bar of SURVEY.md §8d (cuDNN convolutions, cuBLAS GEMMs, element-wise kernels, fp32, TF32 off),
-    whole cfg-2 batch, vocoder batched (kinder than the reference's one utterance at a time).  Returns (frames/s, ms)."""
-    from oracle import dtts_oracle as O
-    torch.backends.cuda.matmul.allow_tf32 = False
-    torch.backends.cudnn.allow_tf32 = False
+    tf32 = mode != "fp32"
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    torch.backends.cudnn.allow_tf32 = tf32
     cfg, vcfg = AcousticConfig(), VocoderConfig()
     W = {k: v.to(dev) for k, v in fold_weight_norm(synth.make_acoustic_state_dict(1234)).items()}
     Wv = {k: v.to(dev) for k, v in fold_weight_norm(synth.make_vocoder_state_dict(4321)).items()}
@@ -128,7 +229,8 @@ def eager_gpu_run(batch, dev, iters=2):
     def once():
         with torch.no_grad():
             ret = O.acoustic_forward(W, cfg, b, b["mel2word"], b["z_p"])
-            return O.hifigan_forward(Wv, vcfg, ret["mel_out"])
+            with torch.autocast("cuda", dtype=torch.float16, enabled=(mode == "fp16")):
+                return O.hifigan_forward(Wv, vcfg, ret["mel_out"]).float()
     once()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -138,6 +240,8 @@ def eager_gpu_run(batch, dev, iters=2):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
     return frames / (ms / 1e3), ms
 
 
@@ -154,15 +258,65 @@ def claim_stdout():
     return emit
 
 
+def base_config(world):
+    return dict(workload="cfg2: Biaobei-shaped batch=60/GPU, Tw<=22, Lk<=96, T=400 frames, full text->mel->HiFi-GAN "
+                         "(reference arithmetic: fp32; see `dtype` / `precision` for this arm's operand formats)",
+                batch_per_gpu=WORKLOADS["cfg2"]["B"], frames_per_utt=WORKLOADS["cfg2"]["max_frames"],
+                parallelism=f"replicas x{world}", supplied_durations=True,
+                l2="every step's inputs and activations (>= 0.4 GB of keys, 80 GB of vocoder traffic) exceed the 126 MB L2")
+
+
+def reference_arm(args, emit, cores, world):
+    """bench.py --impl reference: the reference's CPU path, all host threads, K steps of a bounded sample each."""
+    batch = synth.make_batch(seed=1234, alias_values=True, **WORKLOADS["cfg2"])
+    ref = CpuReference()
+    torch.set_num_threads(cores)
+    utts_all = [slice_utt(batch, b) for b in range(batch["word_tokens"].shape[0])]
+    t0 = time.perf_counter()
+    ref.run_utt(utts_all[0])                                     # first call: thread-pool / primitive-cache warm-up
+    t0 = time.perf_counter()
+    ref.run_utt(utts_all[0])
+    t_utt = time.perf_counter() - t0
+    K, Wm = max(args.steps, 1), max(args.warmup, 0)
+    # bounded sample per step: the whole K + W run stays around two minutes on this host
+    n = int(max(1, min(len(utts_all), 120.0 / max(t_utt, 1e-3) / (K + Wm))))
+    utts = utts_all[:n]
+    frames = sum(int(u["mel_lengths"][0]) for u in utts)
+    for _ in range(Wm):
+        for u in utts:
+            ref.run_utt(u)
+    secs = []
+    for _ in range(K):
+        t0 = time.perf_counter()
+        for u in utts:
+            ref.run_utt(u)
+        secs.append(time.perf_counter() - t0)
+    total = sum(secs)
+    fps = frames * K / total
+    audio = frames * HOP_SIZE / SAMPLE_RATE
+    sample = (f"each step = the first {n} utterances ({frames} valid frames) of the cfg-2 batch, one utterance at a time, "
+              f"un-padded, as the reference's inference loop runs them; {K} timed steps on {cores} host threads")
+    emit(json.dumps(dict(
+        impl="reference", metric="mel_frames_per_s", value=fps, unit="frames/s", n_gpus=args.gpus, steps=K,
+        warmup=Wm, ms_per_step=total / K * 1e3, higher_is_better=True, scaling="weak",
+        vs_baseline=None, dtype="f32", data="synthetic", config=base_config(world), rtf=(total / K) / audio,
+        step_s_min=min(secs), step_s_median=statistics.median(secs),
+        cpu_baseline=dict(value=fps, unit="frames/s", cores=cores, kind=ref.kind, sample=sample,
+                          reference_root=getattr(ref, "root", None)),
+        e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--quick", action="store_true", help="headline line only: no other configs, no CPU / eager baselines")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true",
                     help="skip timing the PyTorch-eager (cuDNN/cuBLAS) forward of the same batch on the GPU")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip cfg 1 / 3 / 4 and the fp32-class arm")
     ap.add_argument("--vocoder-precision", type=int, default=int(os.environ.get("DTTS_VOCODER_PRECISION", "6")),
                     help="0: fp32 FMA pipe; 1: tcgen05 bf16 hi/lo x hi/lo (3 MMAs, ~1e-6 wav RMS); 2: tcgen05 bf16 (cfg 3, "
                          "outside the tolerance); 3: tcgen05 fp16 x fp16 hi/lo weights (2 MMAs, ~6e-5 wav RMS, "
@@ -172,31 +326,18 @@ def main():
     ap.add_argument("--acoustic-precision", type=int, default=int(os.environ.get("DTTS_ACOUSTIC_PRECISION", "1")),
                     help="0: fp32 FMA pipe; 1 (default): dense convolutions on tcgen05, bf16 hi/lo split (fp32-class)")
     args = ap.parse_args()
+    if args.quick:
+        args.no_cpu_baseline = args.no_eager_baseline = args.no_extra_configs = True
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
     emit = claim_stdout()
-    config = dict(workload="cfg2: Biaobei-shaped batch=60/GPU, Tw<=22, Lk<=96, T=400 frames, fp32, text->mel->HiFi-GAN",
-                  batch_per_gpu=WORKLOAD["B"], frames_per_utt=WORKLOAD["max_frames"], parallelism=f"replicas x{world}",
-                  supplied_durations=True, l2="inputs (779 MB keys+values per step) exceed the 126 MB L2")
+    config = base_config(world)
 
     if args.impl == "reference":
-        if rank != 0:
-            return
-        batch = synth.make_batch(seed=1234, **WORKLOAD)
-        steps = max(1, min(args.steps, 3))
-        if args.warmup > 0:
-            cpu_port_run(batch, 1, cores, 1)
-        fps, secs, frames = cpu_port_run(batch, CPU_SAMPLE_UTTS, cores, steps)
-        audio = frames * HOP_SIZE / SAMPLE_RATE
-        sample = f"first {CPU_SAMPLE_UTTS} utterances ({frames} frames) of the cfg-2 batch, best of {steps}"
-        emit(json.dumps(dict(
-            impl="reference", metric="mel_frames_per_s", value=fps, unit="frames/s", n_gpus=args.gpus, steps=steps,
-            warmup=min(args.warmup, 1), ms_per_step=secs * 1e3, higher_is_better=True, scaling="weak",
-            vs_baseline=None, dtype="f32", data="synthetic", config=config, rtf=secs / audio,
-            cpu_baseline=dict(value=fps, unit="frames/s", cores=cores, kind="port", sample=sample),
-            e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+        if rank == 0:
+            reference_arm(args, emit, cores, world)
         return
 
     if not torch.cuda.is_available():
@@ -206,6 +347,8 @@ def main():
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    from dict_tts_b200.bank import DictBank
+    from dict_tts_b200.engine import HifiGanEngine
     from dict_tts_b200.pipeline import TextToWav
 
     # ---- weights: rank 0 builds the arenas, one NCCL broadcast each ----
@@ -214,20 +357,37 @@ def main():
     v_sd = fold_weight_norm(synth.make_vocoder_state_dict(4321))
     a_host, a_table = pack_arena(a_sd)
     v_host, v_table = pack_arena(v_sd)
+    bcast_ms = None
     if world > 1:
         a_arena = a_host.to(dev) if rank == 0 else torch.empty_like(a_host, device=dev)
         v_arena = v_host.to(dev) if rank == 0 else torch.empty_like(v_host, device=dev)
+        warm = torch.zeros(1, device=dev)
+        dist.broadcast(warm, 0)                                   # communicator set-up is not the broadcast
+        torch.cuda.synchronize()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
         dist.broadcast(a_arena, 0)
         dist.broadcast(v_arena, 0)
+        b1.record()
+        torch.cuda.synchronize()
+        bcast_ms = b0.elapsed_time(b1)
     else:
         a_arena, v_arena = a_host.to(dev), v_host.to(dev)
-    pipe = TextToWav(None, None, acfg, vcfg, dev, arenas=((a_arena, a_table), (v_arena, v_table)),
-                     vocoder_precision=args.vocoder_precision, acoustic_precision=args.acoustic_precision)
+    arenas = ((a_arena, a_table), (v_arena, v_table))
 
-    batch = synth.make_batch(seed=1234 + rank, **WORKLOAD)
+    def make_pipe(vp, ap_=args.acoustic_precision, route=0):
+        return TextToWav(None, None, acfg, vcfg, dev, arenas=arenas, vocoder_precision=vp, acoustic_precision=ap_,
+                         s2pa_route=route)
+    pipe = make_pipe(args.vocoder_precision)
+
+    # values IS keys, as in the binarized data (binarizer_zh.py:231-233): one tensor, uploaded once
+    batch = synth.make_batch(seed=1234 + rank, alias_values=True, **WORKLOADS["cfg2"])
     frames = int(batch["mel_lengths"].sum())
-    audio_s = frames * HOP_SIZE / SAMPLE_RATE
-    host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    padded_frames = batch["mel2word"].shape[0] * batch["mel2word"].shape[1]
+    n_tokens = batch["word_tokens"].numel()
+    gloss_valid = int((batch["key_map"] != 0).sum())
+    host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in batch.items() if k != "values"}
+    host["values"] = host["keys"]
     devb = pipe.to_device(host)
     torch.cuda.synchronize()
 
@@ -246,99 +406,89 @@ def main():
     stream = torch.cuda.current_stream()
     stage_names = ("text_encode", "length_regulate", "decode_mel", "vocode")
 
-    # ---- device-resident arm ----
-    for _ in range(max(args.warmup, 3)):
-        pipe.run_device(devb)
-    barrier()
+    def time_device(p, d, steps, warm):
+        """Device-resident arm: (ms per step max over ranks, per-stage ms, launches in the timed region)."""
+        for _ in range(max(warm, 3)):
+            p.run_device(d)
+        barrier()
+        marks = []
+        l0 = p.launches
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(stream)
+        for _ in range(steps):
+            sm = [torch.cuda.Event(enable_timing=True)]
+            sm[0].record(stream)
+
+            def record(name, sm=sm):
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(stream)
+                sm.append(e)
+            p.run_device(d, record)
+            marks.append(sm)
+        ev1.record(stream)
+        barrier()
+        ms = max_over_ranks(ev0.elapsed_time(ev1)) / steps
+        st = {n: sum(m[i].elapsed_time(m[i + 1]) for m in marks) / steps for i, n in enumerate(stage_names)}
+        return ms, st, p.launches - l0
+
+    def time_stream(p, hb, steps, bufs):
+        """End-to-end arm: pinned host inputs -> H2D -> engine -> wav D2H every step through the public API
+        (synthesize_stream: the upload of step i+1 overlaps the compute of step i)."""
+        def gen(n):
+            for _ in range(n):
+                yield hb
+        for _ in p.synthesize_stream(gen(2), bufs):
+            pass
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        n_out = sum(1 for _ in p.synthesize_stream(gen(steps), bufs))
+        e1.record(stream)
+        barrier()
+        assert n_out == steps
+        return max_over_ranks(e0.elapsed_time(e1)) / steps
+
+    def time_serial(p, hb, out, steps):
+        for _ in range(2):
+            p.synthesize(hb, out)
+        barrier()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record(stream)
+        for _ in range(steps):
+            p.synthesize(hb, out)
+        l1.record(stream)
+        barrier()
+        return max_over_ranks(l0.elapsed_time(l1)) / steps
+
+    # ---- headline: device-resident arm ----
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    marks = []
-    launches0 = pipe.launches
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev1 = torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        step_marks = [torch.cuda.Event(enable_timing=True)]
-        step_marks[0].record(stream)
+    dev_ms, stage_ms, launches = time_device(pipe, devb, args.steps, args.warmup)
 
-        def record(name, sm=step_marks):
-            e = torch.cuda.Event(enable_timing=True)
-            e.record(stream)
-            sm.append(e)
-        pipe.run_device(devb, record)
-        marks.append(step_marks)
-    ev1.record(stream)
-    barrier()
-    launches = pipe.launches - launches0
-    dev_ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
-    stage_ms = {n: sum(m[i].elapsed_time(m[i + 1]) for m in marks) / args.steps for i, n in enumerate(stage_names)}
-
-    # ---- end-to-end arm: pinned host inputs -> H2D -> engine -> wav D2H, every step, through the public API.
-    # synthesize_stream() is the throughput call: the upload of step i+1 overlaps the compute of step i (second stream),
-    # every step still copies its 780 MB of inputs from pinned host memory and reads its waveform back.
-    wav_bufs = [torch.empty(WORKLOAD["B"], WORKLOAD["max_frames"] * HOP_SIZE, dtype=torch.float32, pin_memory=True)
-                for _ in range(2)]
+    # ---- end-to-end arms ----
+    B, Tmax = WORKLOADS["cfg2"]["B"], WORKLOADS["cfg2"]["max_frames"]
+    wav_bufs = [torch.empty(B, Tmax * HOP_SIZE, dtype=torch.float32, pin_memory=True) for _ in range(2)]
     wav_host = wav_bufs[0]
-
-    def host_batches(n):
-        for _ in range(n):
-            yield host
-    for _ in pipe.synthesize_stream(host_batches(2), wav_bufs):
-        pass
-    barrier()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    n_out = 0
-    for w in pipe.synthesize_stream(host_batches(args.steps), wav_bufs):
-        n_out += 1
-    e1.record(stream)
-    barrier()
-    assert n_out == args.steps
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-    # latency call (one batch, nothing overlapped): H2D + compute + D2H back to back
-    for _ in range(2):
-        pipe.synthesize(host, wav_host)
-    barrier()
-    l0 = torch.cuda.Event(enable_timing=True)
-    l1 = torch.cuda.Event(enable_timing=True)
-    l0.record(stream)
-    for _ in range(min(args.steps, 5)):
-        pipe.synthesize(host, wav_host)
-    l1.record(stream)
-    barrier()
-    e2e_serial_ms = max_over_ranks(l0.elapsed_time(l1)) / min(args.steps, 5)
-    # ---- same end-to-end call with the GPU-resident dictionary bank: the characters are named by
-    # id, keys/values never cross the bus again (the bank -- here one entry per character position of this batch -- is
-    # uploaded once, outside the timed region, like the weights)
-    from dict_tts_b200.bank import DictBank
+    d2h = wav_host.numel() * wav_host.element_size()
+    # (a) GPU-resident dictionary bank (SURVEY.md §8f-1) -- the task's default mode: characters are named by id, the bank
+    # is uploaded once like the weights, per step only ids / durations / noise cross the bus.  This is the headline e2e.
     bank, dict_ids = DictBank.from_batch(batch)
     pipe.acoustic.set_dict_bank(bank)
     slim = {k: v for k, v in host.items() if k not in ("keys", "values", "key_map", "pinyin", "pinyin_map")}
     slim["dict_ids"] = dict_ids.pin_memory()
-
-    def slim_batches(n):
-        for _ in range(n):
-            yield slim
-    for _ in pipe.synthesize_stream(slim_batches(2), wav_bufs):
-        pass
-    barrier()
-    b0 = torch.cuda.Event(enable_timing=True)
-    b1 = torch.cuda.Event(enable_timing=True)
-    b0.record(stream)
-    for w in pipe.synthesize_stream(slim_batches(args.steps), wav_bufs):
-        pass
-    b1.record(stream)
-    barrier()
-    bank_ms = max_over_ranks(b0.elapsed_time(b1)) / args.steps
+    bank_ms = time_stream(pipe, slim, args.steps, wav_bufs)
+    bank_serial_ms = time_serial(pipe, slim, wav_host, min(args.steps, 5))
     bank_h2d = sum(slim[k].numel() * slim[k].element_size() for k in
                    ("word_tokens", "pron_modified", "dict_ids", "mel2word", "z_p"))
+    # (b) the reference collater's padded [B,Tw,Lk,768] tensors from pinned host memory every step (keys uploaded once
+    # for keys and values, as the data holds one tensor for both)
+    pad_ms = time_stream(pipe, host, args.steps, wav_bufs)
+    pad_serial_ms = time_serial(pipe, host, wav_host, min(args.steps, 5))
+    pad_h2d = sum(host[k].numel() * host[k].element_size() for k in
+                  ("word_tokens", "pron_modified", "keys", "key_map", "pinyin", "pinyin_map", "mel2word", "z_p"))
     clocks = sampler.stop() if rank == 0 else None
-    h2d = sum(host[k].numel() * host[k].element_size() for k in
-              ("word_tokens", "pron_modified", "keys", "values", "key_map", "pinyin", "pinyin_map", "mel2word", "z_p"))
-    d2h = wav_host.numel() * wav_host.element_size()
 
     total_frames = frames
     if world > 1:
@@ -351,56 +501,188 @@ def main():
         return
 
     peaks = load_peaks()
-    dtype = {0: "f32", 1: "f32 (vocoder convs: bf16x3 split on tcgen05, fp32 accumulate)",
-             2: "bf16 vocoder convs (tcgen05), f32 elsewhere",
-             3: "f32 (vocoder convs: fp16 activations x fp16 hi/lo weights on tcgen05, fp32 accumulate)",
-             4: "fp16 vocoder convs (tcgen05), f32 elsewhere",
-             5: "f32 (vocoder convs: fp16 x fp16 on tcgen05, hi/lo weight planes where C_out < 128, fp32 accumulate)",
-             6: "f32 (vocoder convs: fp16 activations x fp16 hi/lo weights on tcgen05, lo-plane correction of the "
-                "C_out >= 128 layers as an e5m2 MMA, fp32 accumulate)"}[args.vocoder_precision]
-    config["vocoder_precision"] = args.vocoder_precision
-    config["acoustic_precision"] = args.acoustic_precision
-    voc_s = stage_ms["vocode"] / 1e3
+    audio_total = total_frames * HOP_SIZE / SAMPLE_RATE
+
+    def voc_roofline(vp, voc_ms, n_frames, n_launch):
+        ach = n_frames * VOCODER_FLOP_PER_FRAME / (voc_ms / 1e3) / 1e12
+        return dict(bound="tensor", kernel="%s, HiFi-GAN stack, %d launches/step" % (VOC_KERNEL[vp], n_launch),
+                    achieved=ach, peak=peaks["tflops"], unit="TFLOP/s", frac=ach / peaks["tflops"],
+                    peak_source=peaks["source"] + " bf16 dense (sustained)", avg_launch_ms=voc_ms / n_launch,
+                    flop_per_launch=n_frames * VOCODER_FLOP_PER_FRAME / n_launch)
+
+    n_voc_launch = N_TC_CONV_LAUNCHES
     # the vocoder is run up to each utterance's valid length (dtts_vocode_lens): algorithmic work = valid frames only
-    # (the ~1 frame of receptive-field margin it also computes per utterance is not counted)
-    padded_frames = frames
-    config["vocoder_frames"] = "valid frames + receptive-field margin (padded tail of the batch skipped)"
-    achieved = padded_frames * VOCODER_FLOP_PER_FRAME / voc_s / 1e12
-    n_voc_launch = 1 + 4 + 72 + (1 if args.vocoder_precision == 0 else 0)   # conv_post is a separate CUDA-core kernel on the TC path
-    kname = {0: "conv1d_f32_kernel (fp32 FMA pipe)", 1: "tc_conv_kernel (tcgen05, bf16 hi/lo x hi/lo: 3 MMAs per product)",
-             2: "tc_conv_kernel (tcgen05, bf16: 1 MMA)", 3: "tc_conv_kernel (tcgen05, fp16 x fp16 hi/lo weights: 2 MMAs)",
-             4: "tc_conv_kernel (tcgen05, fp16: 1 MMA)",
-             5: "tc_conv_kernel (tcgen05, fp16; hi/lo weights only where C_out < 128)",
-             6: "tc_conv_kernel (tcgen05, fp16 x fp16 hi/lo weights: 2 MMAs; lo plane in FP8 where C_out >= 128: 1.5)"
-             }[args.vocoder_precision]
-    roofline = dict(bound="tensor", kernel="%s, HiFi-GAN stack, %d launches/step" % (kname, n_voc_launch),
-                    achieved=achieved, peak=peaks["tflops"], unit="TFLOP/s", frac=achieved / peaks["tflops"],
-                    traffic=(TC_CONV_DRAM_BYTES_PER_LAUNCH if args.vocoder_precision in (3, 6) else None),   # same bytes in 3 and 6
-                    traffic_source="profiles/r01_vocoder_lens_dram_agg.txt (ncu dram__bytes_read+write, average over the "
-                                   "77 tc_conv_kernel launches of one valid-length vocode pass; algorithmic: 1.08 GB)",
-                    peak_source=peaks["source"] + " bf16 dense (sustained)",
-                    avg_launch_ms=stage_ms["vocode"] / n_voc_launch,
-                    flop_per_launch=padded_frames * VOCODER_FLOP_PER_FRAME / n_voc_launch)
+    roofline = voc_roofline(args.vocoder_precision, stage_ms["vocode"], frames, n_voc_launch)
+    roofline["traffic"] = TC_CONV_DRAM_BYTES_PER_STEP / n_voc_launch if args.vocoder_precision in (3, 6) else None
+    roofline["traffic_source"] = TC_CONV_TRAFFIC_SOURCE
+
+    def hbm(nbytes, ms):
+        a = nbytes / (ms / 1e3) / 1e9
+        return dict(achieved=a, peak=peaks["hbm_gbs"], unit="GB/s", frac=a / peaks["hbm_gbs"], bytes=nbytes)
+
+    def tensor(flop, ms):
+        a = flop / (ms / 1e3) / 1e12
+        return dict(achieved=a, peak=peaks["tflops"], unit="TFLOP/s", frac=a / peaks["tflops"], flop=flop)
+    s2pa_bytes = gloss_valid * S2PA_BYTES_PER_GLOSS_TOKEN // 2          # values alias keys: each valid row is read twice from
+    roofline_stages = dict(                                              # HBM/L2, but it is ONE tensor: 3072 B algorithmic
+        model="SURVEY.md 8d algorithmic work per unit x the units of one step, over the stage's CUDA-event time",
+        text_encode=dict(ms=stage_ms["text_encode"], tokens=n_tokens, valid_gloss_tokens=gloss_valid,
+                         tensor=tensor(n_tokens * ENCODER_FLOP_PER_TOKEN, stage_ms["text_encode"]),
+                         hbm=hbm(s2pa_bytes, stage_ms["text_encode"]),
+                         note="latency-bound stage: 8 encoder layers over 1 320 tokens; the S2PA pass alone is timed in profiles/"),
+        length_regulate=dict(ms=stage_ms["length_regulate"], hbm=hbm(padded_frames * LR_BYTES_PER_FRAME, stage_ms["length_regulate"])),
+        decode_mel=dict(ms=stage_ms["decode_mel"], frames=padded_frames,
+                        tensor=tensor(padded_frames * DECODER_FLOP_PER_FRAME, stage_ms["decode_mel"]),
+                        hbm=hbm(padded_frames * DECODER_BYTES_PER_FRAME, stage_ms["decode_mel"]),
+                        note="fully-fused byte model (g 768 + z 16 + mel 320 B per frame); padded frames are computed, as "
+                             "the batched reference computes them"),
+        vocode=dict(ms=stage_ms["vocode"], frames=frames, tensor=tensor(frames * VOCODER_FLOP_PER_FRAME, stage_ms["vocode"]),
+                    hbm=hbm(frames * VOCODER_BYTES_PER_FRAME, stage_ms["vocode"])))
+
     line = dict(metric="mel_frames_per_s", value=total_frames / (dev_ms / 1e3), unit="frames/s", n_gpus=world,
                 steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=dev_ms, higher_is_better=True,
-                scaling="weak", vs_baseline=None, dtype=dtype, data="synthetic", config=config,
-                rtf=(dev_ms / 1e3) / (total_frames * HOP_SIZE / SAMPLE_RATE),
-                x_realtime=(total_frames * HOP_SIZE / SAMPLE_RATE) / (dev_ms / 1e3),
+                scaling="weak", vs_baseline=None, dtype=VOC_DTYPE[args.vocoder_precision] + "; acoustic model: "
+                + ("bf16 hi/lo x hi/lo on tcgen05 (fp32-class)" if args.acoustic_precision else "f32"),
+                data="synthetic", config=config,
+                precision=dict(vocoder=args.vocoder_precision, acoustic=args.acoustic_precision,
+                               vocoder_frames="valid frames + receptive-field margin (padded tail of the batch skipped)"),
+                rtf=(dev_ms / 1e3) / audio_total, x_realtime=audio_total / (dev_ms / 1e3),
                 stages_ms=stage_ms, gpu_launches=int(launches), clocks=clocks, roofline=roofline,
-                e2e=dict(value=total_frames / (e2e_ms / 1e3), unit="frames/s", h2d_bytes_per_step=int(h2d),
-                         d2h_bytes_per_step=int(d2h), ms_per_step=e2e_ms,
-                         x_realtime=(total_frames * HOP_SIZE / SAMPLE_RATE) / (e2e_ms / 1e3),
-                         api="TextToWav.synthesize_stream (copy of step i+1 overlaps compute of step i)",
-                         serial_ms_per_step=e2e_serial_ms),
-                e2e_dict_bank=dict(value=total_frames / (bank_ms / 1e3), unit="frames/s", ms_per_step=bank_ms,
-                                   h2d_bytes_per_step=int(bank_h2d), d2h_bytes_per_step=int(d2h),
-                                   bank_bytes_resident=int(bank.nbytes),
-                                   note="same call with characters named by dictionary-bank id (SURVEY.md 8f-1)"))
+                roofline_stages=roofline_stages,
+                e2e=dict(value=total_frames / (bank_ms / 1e3), unit="frames/s", h2d_bytes_per_step=int(bank_h2d),
+                         d2h_bytes_per_step=int(d2h), ms_per_step=bank_ms, x_realtime=audio_total / (bank_ms / 1e3),
+                         api="TextToWav.synthesize_stream on host batches that name their characters by dictionary-bank "
+                             "id (SURVEY.md 8f-1, the task's default mode; the bank is resident like the weights); copy of "
+                             "step i+1 overlaps compute of step i",
+                         serial_ms_per_step=bank_serial_ms, bank_bytes_resident=int(bank.nbytes)),
+                e2e_padded=dict(value=total_frames / (pad_ms / 1e3), unit="frames/s", ms_per_step=pad_ms,
+                                h2d_bytes_per_step=int(pad_h2d), d2h_bytes_per_step=int(d2h),
+                                serial_ms_per_step=pad_serial_ms,
+                                note="same call with the reference collater's padded [B,Tw,Lk,768] dictionary features "
+                                     "from pinned host memory every step (one tensor for keys and values, as the data has it)"))
+    if bcast_ms is not None:
+        line["arena_broadcast_ms"] = bcast_ms
+        line["arena_broadcast_bytes"] = int((a_host.numel() + v_host.numel()) * 4)
+
+    extras = world == 1
+    # ---- cfg 2 in the fp32-class precision mode (vocoder precision 1: bf16 hi/lo x hi/lo, ~1e-6 waveform RMS) ----
+    if extras and not args.no_extra_configs:
+        try:
+            steps2 = max(3, min(args.steps, 10))
+            p1 = make_pipe(1)
+            ms1, st1, _ = time_device(p1, devb, steps2, 3)
+            r1, w1 = p1.run_device(devb)
+            ref_mel, ref_wav = r1["mel_out"].clone(), w1.clone()
+            n_valid = frames * HOP_SIZE                               # both arms write 0 past each utterance's valid length
+
+            def wav_rms(a, b):
+                return float(((a - b).double().pow(2).sum() / n_valid).sqrt())
+            line["fp32_class"] = dict(vocoder_precision=1, ms_per_step=ms1, value=frames / (ms1 / 1e3), stages_ms=st1,
+                                      roofline=voc_roofline(1, st1["vocode"], frames, n_voc_launch),
+                                      note="same workload with every tensor-core product as a 3-MMA bf16 hi/lo split: "
+                                           "waveform within ~1e-6 RMS of the reference's fp32 forward (tests)")
+            p1.close()
+            # default mode against it, on the bench batch itself
+            r6, w6 = pipe.run_device(devb)
+            line["precision"]["wav_rms_vs_fp32_class"] = wav_rms(w6, ref_wav)
+            line["precision"]["wav_signal_rms"] = wav_rms(ref_wav, torch.zeros_like(ref_wav))
+            line["precision"]["mel_maxabs_vs_fp32_class"] = float((r6["mel_out"] - ref_mel).abs().max())
+            # ---- cfg 3: bf16 tensor-core mode (single bf16 MMA in the vocoder, dict-attention as the K/V projection GEMM) ----
+            p3 = make_pipe(2, 1, 1)
+            ms3, st3, _l = time_device(p3, devb, steps2, 3)
+            r3, w3 = p3.run_device(devb)
+            line.setdefault("configs", {})["cfg3"] = dict(
+                workload="cfg3: the cfg-2 batch with single-pass bf16 tensor-core convolutions in the vocoder (1 MMA per "
+                         "product) and S2PA as the [B*Tw*Lk,768]x[768,384] K/V projection GEMM on tcgen05 (s2pa_route=1)",
+                ms_per_step=ms3, value=frames / (ms3 / 1e3), unit="frames/s", stages_ms=st3,
+                roofline=voc_roofline(2, st3["vocode"], frames, n_voc_launch),
+                error=dict(wav_rms_vs_fp32_class=wav_rms(w3, ref_wav),
+                           mel_maxabs_vs_fp32_class=float((r3["mel_out"] - ref_mel).abs().max()),
+                           tolerance="1e-4 RMS on the waveform: a throughput mode, OUTSIDE the tolerance (DESIGN.md §5)"))
+            p3.close()
+            del p3, p1
+        except Exception as e:                                   # an extra must never cost the headline
+            line.setdefault("configs", {})["cfg3"] = dict(unavailable=repr(e)[:300])
+        # ---- cfg 4: vocoder only, 256 x 32 frames (8192-sample segments) ----
+        try:
+            mel4 = synth.make_mel(4, CFG4["B"], CFG4["T"])
+            mel4_h = mel4.pin_memory()
+            mel4_d = mel4.to(dev)
+            voc = pipe.vocoder
+            for _ in range(3):
+                voc(mel4_d)
+            torch.cuda.synchronize()
+            n4 = max(10, args.steps)
+            l0 = voc.launches
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(n4):
+                voc(mel4_d)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms4 = e0.elapsed_time(e1) / n4
+            l4 = (voc.launches - l0) // n4
+            out4 = torch.empty(CFG4["B"], CFG4["T"] * HOP_SIZE, pin_memory=True)
+            e0.record(stream)
+            for _ in range(n4):
+                out4.copy_(voc(mel4_h.to(dev, non_blocking=True)), non_blocking=True)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms4e = e0.elapsed_time(e1) / n4
+            fr4 = CFG4["B"] * CFG4["T"]
+            r4 = voc_roofline(args.vocoder_precision, ms4, fr4, n_voc_launch)
+            r4["hbm_fully_fused"] = hbm(fr4 * VOCODER_BYTES_PER_FRAME, ms4)
+            line.setdefault("configs", {})["cfg4"] = dict(
+                workload="cfg4: HiFi-GAN only, spec2wav_batch on 256 x 32-frame mels (8192-sample segments), mel ~ U(-6,1.5)",
+                ms_per_step=ms4, value=fr4 / (ms4 / 1e3), unit="frames/s", launches_per_step=int(l4),
+                x_realtime=fr4 * HOP_SIZE / SAMPLE_RATE / (ms4 / 1e3), roofline=r4,
+                e2e=dict(value=fr4 / (ms4e / 1e3), unit="frames/s", ms_per_step=ms4e,
+                         h2d_bytes_per_step=int(mel4.numel() * 4), d2h_bytes_per_step=int(out4.numel() * 4)),
+                note="short segments: every layer is a fraction of a wave of row tiles; L2-resident between layers")
+        except Exception as e:
+            line.setdefault("configs", {})["cfg4"] = dict(unavailable=repr(e)[:300])
+        # ---- cfg 1: one 64-character utterance, T = 1280 frames: GPU latency + the reference's CPU path ----
+        try:
+            b1 = synth.make_batch(seed=1234, alias_values=True, **WORKLOADS["cfg1"])
+            fr1 = int(b1["mel_lengths"].sum())
+            h1 = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b1.items() if k != "values"}
+            h1["values"] = h1["keys"]
+            d1 = pipe.to_device(h1)
+            ms1d, st1d, l1d = time_device(pipe, d1, max(10, args.steps), 3)
+            out1 = torch.empty(1, WORKLOADS["cfg1"]["max_frames"] * HOP_SIZE, pin_memory=True)
+            ms1e = time_serial(pipe, h1, out1, max(10, args.steps))
+            audio1 = fr1 * HOP_SIZE / SAMPLE_RATE
+            c1 = dict(workload="cfg1: Biaobei dict_tts.yaml, single 64-character utterance (Tw=66), 1280 mel frames = "
+                               "14.9 s of audio, text->mel->wav",
+                      frames=fr1, audio_s=audio1,
+                      gpu=dict(device_ms=ms1d, stages_ms=st1d, launches=int(l1d) // max(10, args.steps),
+                               e2e_latency_ms=ms1e, x_realtime=audio1 / (ms1e / 1e3), frames_per_s=fr1 / (ms1e / 1e3),
+                               api="TextToWav.synthesize: pinned host batch -> H2D -> engine -> wav D2H, synchronised"))
+            if not args.no_cpu_baseline:
+                refc = CpuReference()
+                u1 = [slice_utt(b1, 0)]
+                allt = refc.time_passes(u1, cores, 5, warm_utts=1)
+                onet = refc.time_passes(u1, 1, 3, warm_utts=0)      # one thread: the primitives are warm from the passes above
+                torch.set_num_threads(cores)
+                c1["cpu"] = dict(kind=refc.kind, protocol="one utterance, B=1, exactly as after_infer calls spec2wav "
+                                 "(vocoders/hifigan.py:54-62); 1 warm-up + 5 timed passes on all threads; 3 timed passes on 1 thread",
+                                 all_threads=dict(cores=cores, **cpu_stats(allt, fr1)),
+                                 one_thread=dict(cores=1, **cpu_stats(onet, fr1)))
+                c1["gpu_vs_cpu_all_threads"] = min(allt) / (ms1e / 1e3)
+            line.setdefault("configs", {})["cfg1"] = c1
+        except Exception as e:
+            line.setdefault("configs", {})["cfg1"] = dict(unavailable=repr(e)[:300])
+
     if not args.no_cpu_baseline and world == 1:
-        fps, secs, fr = cpu_port_run(batch, CPU_SAMPLE_UTTS, cores, 2)
-        line["cpu_baseline"] = dict(value=fps, unit="frames/s", cores=cores, kind="port",
-                                    sample=f"first {CPU_SAMPLE_UTTS} utterances ({fr} frames) of the same batch, "
-                                           f"oracle port on {cores} host threads, best of 2", seconds=secs)
+        refc = CpuReference()
+        utts = [slice_utt(batch, b) for b in range(CPU_SAMPLE_UTTS)]
+        fr = sum(int(u["mel_lengths"][0]) for u in utts)
+        secs = refc.time_passes(utts, cores, 2, warm_utts=1)
+        line["cpu_baseline"] = dict(value=fr / min(secs), unit="frames/s", cores=cores, kind=refc.kind,
+                                    sample=f"first {CPU_SAMPLE_UTTS} utterances ({fr} valid frames) of the same batch, one "
+                                           f"utterance at a time and un-padded as the reference's inference loop runs them, "
+                                           f"{cores} host threads, best of 2 passes", seconds=min(secs),
+                                    seconds_median=statistics.median(secs))
     else:
         line["cpu_baseline"] = None
     if not args.no_eager_baseline and world == 1:
@@ -408,10 +690,20 @@ def main():
             pipe.close()
             del pipe, devb
             torch.cuda.empty_cache()
-            fps, ms = eager_gpu_run(batch, dev)
-            line["eager_gpu_baseline"] = dict(value=fps, unit="frames/s", ms_per_step=ms, kind="port",
-                                              note="oracle restatement as PyTorch eager on the same B200 (cuDNN / cuBLAS, "
-                                                   "fp32, TF32 off), whole batch, device-resident inputs")
+            eager = {}
+            for mode, what in (("fp32", "fp32, TF32 off (the reference's amp: false)"),
+                               ("tf32", "TF32 tensor cores allowed in cuDNN / cuBLAS"),
+                               ("fp16", "vocoder (98.6 % of the FLOPs) under torch.autocast(float16): fp16 tensor cores; acoustic "
+                                        "model with TF32 (its -1e9 mask fills overflow in fp16)")):
+                try:
+                    fps, ms = eager_gpu_run(batch, dev, mode)
+                    eager[mode] = dict(value=fps, unit="frames/s", ms_per_step=ms, what=what)
+                except Exception as e:               # noqa: BLE001
+                    eager[mode] = dict(unavailable=repr(e)[:200], what=what)
+            line["eager_gpu_baseline"] = dict(kind="port", **{k: v for k, v in eager["fp32"].items() if k != "what"}, modes=eager,
+                                              note="oracle restatement as PyTorch eager on the same B200 (cuDNN / cuBLAS), whole "
+                                                   "batch, device-resident inputs; the tf32 / fp16 modes are the like-for-like "
+                                                   "bars for an arm that uses 16-bit tensor-core operands")
         except Exception as e:                       # a baseline must never cost the bench line
             line["eager_gpu_baseline"] = dict(unavailable=repr(e)[:200])
     emit(json.dumps(line))                   # written before NCCL teardown: a buffered line can be lost at process exit

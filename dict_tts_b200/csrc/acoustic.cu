@@ -1,79 +1,16 @@
 // Acoustic model behind the C ABI: S2PA text encoder, duration predictor, length regulator, FVAE decoder with its
 // residual-coupling prior flow.  Mirrors PortaSpeech_dict.forward(infer=True) (modules/dict_tts/model.py:36-122).
-#include <algorithm>
-
-#include "engine.cuh"
-#include "tc_conv.cuh"
-#include "tc16.cuh"
+#include "acoustic.cuh"
 
 using namespace dtts;
+using namespace dtts::ac;
 
-namespace {
-
-// Every dense convolution exists twice: packed for the fp32 FMA kernel (precision 0, the exact path) and as tcgen05
-// blobs (precision 1: bf16 hi/lo on both operands, 3 MMAs per product, fp32-class accuracy -- durations must round the
-// same way as the reference's fp32 forward).
-struct EncLayerW {
-  ConvW qkv, o, ffn1, ffn2;
-  TcConvW t_qkv, t_o, t_ffn1, t_ffn2;
-  const float *g1, *b1, *g2, *b2;
-};
-struct EncoderW {
-  std::vector<EncLayerW> layers;
-  const float *last_g, *last_b;
-};
-struct WNW {
-  ConvW cond;
-  std::vector<ConvW> in_layers, res_skip;
-  TcConvW t_cond;
-  std::vector<TcConvW> t_in, t_rs;      // t_rs blocks of `hidden` channels: [0] -> x update, [1] -> skip
-};
-struct FlowW {
-  ConvW pre, post;
-  WNW wn;
-  int odd;     // 1: the latent is logically channel-flipped while this coupling layer runs
-};
-
-}  // namespace
-
-struct dtts_acoustic {
-  dtts_acoustic_desc d;
-  WeightTable tab;
-  Pool pool;
-  const float* word_emb;
-  const float* pinyin_emb;
-  EncoderW sem, lin;
-  ConvW s2pa_q, s2pa_kT, s2pa_v, s2pa_o;
-  TcConvW t_s2pa_q, t_s2pa_kT, t_s2pa_v, t_s2pa_o;
-  TcConvW t_s2pa_kv;              // s2pa_route = 1: [W_k ; W_v] side by side, dict_dim -> 2 * hidden (block 0 = k, block 1 = v)
-  TcConvW t_gpre;                 // g_pre_net as a stride-1 k=3 convolution over the 4x space-to-depth input (C' = 4H)
-  TcConvW t_out;                  // out_proj with C_out zero-padded to a multiple of 32
-  int out_pad = 0;
-  std::vector<ConvW> dur_conv;
-  std::vector<TcConvW> t_dur;
-  int precision = 0;              // 0: fp32 FMA pipe; 1: tcgen05 (bf16 hi/lo x hi/lo)
-  TcMode mode;
-  tc16* tc_pool = nullptr;
-  size_t tc_cap = 0, tc_used = 0;
-  std::vector<const float*> dur_ln_g, dur_ln_b;
-  const float *dur_w, *dur_b;
-  ConvW g_pre, dec_pre, dec_out;
-  std::vector<FlowW> flows;   // in reference order (flows.0, .2, .4, .6)
-  WNW dec_wn;
-  uint64_t launches = 0;
-  // dictionary-bank gather status (dtts_text_encode_bank): device word written by dict_bank_gather_kernel, copied to the
-  // pinned host word after every gather; sticky until dtts_acoustic_status reports it
-  int* bank_err_dev = nullptr;
-  int* bank_err_host = nullptr;
-  cudaEvent_t bank_err_evt = nullptr;
-  int bank_err_sticky = 0;
-};
-
-namespace {
+namespace dtts {
+namespace ac {
 
 // conv weight [C_out][C_in][K] (+ optional bias) -> packed
 int pack(dtts_acoustic* h, const std::string& name, int C_out, int C_in, int K, bool has_bias, ConvW* cw,
-         cudaStream_t s, int rci = 0, int rco = 0, const char* wsuffix = ".weight") {
+         cudaStream_t s, int rci, int rco, const char* wsuffix) {
   const float* w = h->tab.get(name + wsuffix, (uint64_t)C_out * C_in * K);
   if (!w) return DTTS_ERR_MISSING_WEIGHT;
   const float* b = nullptr;
@@ -125,7 +62,7 @@ int tc_pack(dtts_acoustic* h, const float* const* w, int parts, const float* bia
   return DTTS_OK;
 }
 int tc_pack1(dtts_acoustic* h, const std::string& name, bool has_bias, int C_out, int C_in, int K, int N, TcConvW* cw,
-             cudaStream_t s, int transposed = 0) {
+             cudaStream_t s, int transposed) {
   if (!h->precision) return DTTS_OK;
   const float* w = h->tab.get(name + ".weight", (uint64_t)C_out * C_in * K);
   if (!w) return DTTS_ERR_MISSING_WEIGHT;
@@ -134,125 +71,45 @@ int tc_pack1(dtts_acoustic* h, const std::string& name, bool has_bias, int C_out
   return tc_pack(h, &w, 1, b, C_out, C_in, K, transposed, N, cw, s);
 }
 
-// One set of operand planes in the caller's workspace; (C, T, rows) describe what it currently holds.
-struct Planes {
-  tc16 *hi = nullptr, *lo = nullptr;
-  size_t cap = 0;                 // elements per plane
-  int C = 0, T = 0, rows = 0;
-};
-
-// Per-call context of the tensor-core convolutions: operand-plane sets (inputs are written there by the producing
-// kernel -- LayerNorm, attention, gate, a convolution epilogue -- or converted from fp32 by stage()) and launch glue.
-struct TcRun {
-  dtts_acoustic* h;
-  Launcher* L;
-  int B;
-  Planes P[3];
-  struct Epi {
-    const float* res = nullptr; long r_bs = 0, r_cs = 0, r_ts = 1;
-    const float* mask = nullptr; int m_bs = 0;
-    int act = 0; float alpha = 1.f, post = 1.f; int accumulate = 0;
-    int c_valid = 0;              // > 0: number of real output channels (the rest is zero padding)
-  };
-  bool shape(Planes& p, int C, int T) {
-    p.C = C; p.T = T; p.rows = tc_rows(T);
-    if ((size_t)B * C * p.rows > p.cap) { (*L)(cudaErrorInvalidValue); return false; }
-    return true;
-  }
-  // destination descriptor for a producer kernel
-  PlaneOut out_of(Planes& p, int C, int T, bool zero_halo) {
-    PlaneOut o;
-    if (!shape(p, C, T)) return o;
-    o.hi = p.hi; o.lo = h->mode.a_planes == 2 ? p.lo : nullptr;
-    o.rows = p.rows; o.pad = TC_PADF; o.fmt = h->mode.fmt; o.zero_halo = zero_halo ? 1 : 0;
-    return o;
-  }
-  // fp32 x (element (c,t) of batch b at x[b*bs + c*cs + t*ts]) -> planes, halo rows zeroed
-  void stage(Planes& p, const float* x, long bs, long cs, long ts, int C, int T) {
-    if (!shape(p, C, T)) return;
-    (*L)(tc_to_planes_full(x, bs, cs, ts, B, C, T, 1.f, p.hi, h->mode.a_planes == 2 ? p.lo : nullptr, p.rows, TC_PADF,
-                           h->mode.fmt, L->stream));
-  }
-  void stage_nct(Planes& p, const float* x, int C, int T) { stage(p, x, (long)C * T, T, 1, C, T); }
-  // channels [c_off, c_off + C) of planes already shaped to (C_total, T)
-  void stage_sub(Planes& p, const float* x, long bs, long cs, long ts, int C, int c_off) {
-    (*L)(tc_to_planes_full(x, bs, cs, ts, B, C, p.T, 1.f, p.hi, h->mode.a_planes == 2 ? p.lo : nullptr, p.rows, TC_PADF,
-                           h->mode.fmt, L->stream, p.C, c_off));
-  }
-  // blocks [blk0, blk0+nblk) of w applied to `in`; fp32 result (optional) element (c,t) at out[b*o_bs + c*o_cs + t*o_ts]
-  // with c counted from the first block; `po` (optional) receives the result as operand planes of the next convolution.
-  void conv(const Planes& in, const TcConvW& w, int blk0, int nblk, float* out, long o_bs, long o_cs, long o_ts,
-            int T_out, int dil, int pad, const Epi& e, Planes* po = nullptr) {
-    if (w.C_in != in.C) { (*L)(cudaErrorInvalidValue); return; }
-    TcConvW sub = w;
-    const int nblocks = w.C_out / w.N;
-    if (nblk <= 0) nblk = nblocks - blk0;
-    sub.C_out = nblk * w.N;
-    sub.w = w.w + (size_t)blk0 * (w.elems() / nblocks);
-    sub.bias = w.bias ? w.bias + (size_t)blk0 * w.N : nullptr;
-    TcConvParams p{};
-    p.a_hi = in.hi; p.a_lo = h->mode.a_planes == 2 ? in.lo : nullptr;
-    p.a_bs = (long)in.C * in.rows; p.a_rows = in.rows; p.a_pad = TC_PADF;
-    p.tap_off0 = -pad; p.tap_step = dil;
-    tc_conv_plan(&p, sub, T_out, h->mode.a_planes);
-    p.ot_mul = 1; p.ot_add = 0; p.T_out = T_out;
-    p.o32 = out; p.o32_bs = o_bs; p.o_nct = 1; p.o_cs = o_cs; p.o_ts = o_ts;
-    p.res = e.res; p.r_bs = e.r_bs; p.r_cs = e.r_cs; p.r_ts = e.r_ts;
-    p.mask = e.mask; p.m_bs = e.m_bs; p.act = e.act; p.alpha = e.alpha; p.post = e.post; p.accumulate = e.accumulate;
-    p.slope = 1.f;
-    if (e.c_valid > 0) p.c_valid = e.c_valid;
-    if (po) {
-      if (!shape(*po, sub.C_out, T_out)) return;
-      p.o_hi = po->hi; p.o_lo = h->mode.a_planes == 2 ? po->lo : nullptr;
-      p.op_bs = (long)po->C * po->rows; p.op_rows = po->rows; p.op_pad = TC_PADF;
-    }
-    (*L)(launch_tc_conv(p, B, L->stream));
-  }
-  void conv_nct(const Planes& in, const TcConvW& w, float* out, int T_out, int dil, int pad, const Epi& e, int blk0 = 0,
-                int nblk = 0, Planes* po = nullptr) {
-    const int nblocks = w.C_out / w.N;
-    const int co = (nblk > 0 ? nblk : nblocks - blk0) * w.N;
-    conv(in, w, blk0, nblk, out, (long)co * T_out, T_out, 1, T_out, dil, pad, e, po);
-  }
-  // carve `n` plane sets of `cap` elements per plane out of the workspace
-  void take(Bump& bump, int n, size_t cap) {
-    for (int i = 0; i < n; ++i) {
-      P[i].cap = cap;
-      P[i].hi = bump.take<tc16>(cap);
-      P[i].lo = bump.take<tc16>(cap);
+int pack_qkv(dtts_acoustic* h, const std::string names[3], const std::string* bias_names, ConvW* qkv, TcConvW* t_qkv,
+             cudaStream_t s) {
+  const int H = h->d.hidden;
+  // q, k, v projections packed side by side: one [H][1][3H] weight, one launch
+  float* wqkv = h->pool.take((size_t)3 * H * H);
+  float* bqkv = bias_names ? h->pool.take((size_t)3 * H) : nullptr;
+  float* tmp = h->pool.take((size_t)H * H);
+  if (!wqkv || (bias_names && !bqkv) || !tmp) return fail(DTTS_ERR_CUDA, "weight pool exhausted");
+  const float* ws[3];
+  for (int j = 0; j < 3; ++j) {
+    ws[j] = h->tab.get(names[j], (uint64_t)H * H);
+    if (!ws[j]) return DTTS_ERR_MISSING_WEIGHT;
+    DTTS_CUDA(repack_conv(ws[j], tmp, H, H, 1, 0, 0, s));                    // [ci][co]
+    DTTS_CUDA(cudaMemcpy2DAsync(wqkv + j * H, 3 * H * sizeof(float), tmp, H * sizeof(float), H * sizeof(float), H,
+                                cudaMemcpyDeviceToDevice, s));
+    if (bias_names) {
+      const float* b = h->tab.get(bias_names[j], H);
+      if (!b) return DTTS_ERR_MISSING_WEIGHT;
+      DTTS_CUDA(cudaMemcpyAsync(bqkv + j * H, b, H * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
   }
-};
+  qkv->w = wqkv; qkv->bias = bqkv; qkv->C_out = 3 * H; qkv->C_in = H; qkv->ktaps = 1; qkv->phases = 1;
+  if (h->precision) DTTS_TRY(tc_pack(h, ws, 3, bqkv, H, H, 1, 0, 0, t_qkv, s));
+  return DTTS_OK;
+}
 
 int pack_encoder(dtts_acoustic* h, const std::string& p, EncoderW* e, cudaStream_t s) {
   const int H = h->d.hidden, F = h->d.ffn_filter, K = h->d.ffn_kernel;
   for (int i = 0; i < h->d.enc_layers; ++i) {
     EncLayerW L;
     const std::string a = p + ".attn_layers." + std::to_string(i);
-    // q, k, v projections packed side by side: one [H][1][3H] weight, one launch
-    float* wqkv = h->pool.take((size_t)3 * H * H);
-    float* bqkv = h->pool.take((size_t)3 * H);
-    float* tmp = h->pool.take((size_t)H * H);
-    if (!wqkv || !bqkv || !tmp) return fail(DTTS_ERR_CUDA, "weight pool exhausted");
-    const char* names[3] = {".conv_q", ".conv_k", ".conv_v"};
-    for (int j = 0; j < 3; ++j) {
-      const float* w = h->tab.get(a + names[j] + ".weight", (uint64_t)H * H);
-      const float* b = h->tab.get(a + names[j] + ".bias", H);
-      if (!w || !b) return DTTS_ERR_MISSING_WEIGHT;
-      DTTS_CUDA(repack_conv(w, tmp, H, H, 1, 0, 0, s));                    // [ci][co]
-      DTTS_CUDA(cudaMemcpy2DAsync(wqkv + j * H, 3 * H * sizeof(float), tmp, H * sizeof(float), H * sizeof(float), H,
-                                  cudaMemcpyDeviceToDevice, s));
-      DTTS_CUDA(cudaMemcpyAsync(bqkv + j * H, b, H * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    }
-    L.qkv.w = wqkv; L.qkv.bias = bqkv; L.qkv.C_out = 3 * H; L.qkv.C_in = H; L.qkv.ktaps = 1; L.qkv.phases = 1;
+    const std::string wn[3] = {a + ".conv_q.weight", a + ".conv_k.weight", a + ".conv_v.weight"};
+    const std::string bn[3] = {a + ".conv_q.bias", a + ".conv_k.bias", a + ".conv_v.bias"};
+    DTTS_TRY(pack_qkv(h, wn, bn, &L.qkv, &L.t_qkv, s));
     DTTS_TRY(pack(h, a + ".conv_o", H, H, 1, true, &L.o, s));
     const std::string f = p + ".ffn_layers." + std::to_string(i);
     DTTS_TRY(pack(h, f + ".conv_1", F, H, K, true, &L.ffn1, s));
     DTTS_TRY(pack(h, f + ".conv_2", H, F, 1, true, &L.ffn2, s));
     if (h->precision) {
-      const float* ws[3];
-      for (int j = 0; j < 3; ++j) ws[j] = h->tab.get(a + names[j] + ".weight", (uint64_t)H * H);
-      DTTS_TRY(tc_pack(h, ws, 3, bqkv, H, H, 1, 0, 0, &L.t_qkv, s));
       DTTS_TRY(tc_pack1(h, a + ".conv_o", true, H, H, 1, 0, &L.t_o, s));
       DTTS_TRY(tc_pack1(h, f + ".conv_1", true, F, H, K, 0, &L.t_ffn1, s));
       DTTS_TRY(tc_pack1(h, f + ".conv_2", true, H, F, 1, 0, &L.t_ffn2, s));
@@ -264,9 +121,13 @@ int pack_encoder(dtts_acoustic* h, const std::string& p, EncoderW* e, cudaStream
     if (!L.g1 || !L.b1 || !L.g2 || !L.b2) return DTTS_ERR_MISSING_WEIGHT;
     e->layers.push_back(L);
   }
-  e->last_g = h->tab.get(p + ".last_ln.gamma", H);
-  e->last_b = h->tab.get(p + ".last_ln.beta", H);
-  if (!e->last_g || !e->last_b) return DTTS_ERR_MISSING_WEIGHT;
+  if (h->tab.entries.count(p + ".last_ln.gamma")) {          // pre-LN encoders only (rel_transformer_encoder.py:52-53)
+    e->last_g = h->tab.get(p + ".last_ln.gamma", H);
+    e->last_b = h->tab.get(p + ".last_ln.beta", H);
+    if (!e->last_g || !e->last_b) return DTTS_ERR_MISSING_WEIGHT;
+  } else {
+    e->last_g = e->last_b = nullptr;
+  }
   return DTTS_OK;
 }
 
@@ -409,7 +270,124 @@ void run_wn(const WNW& W, int hidden, int K, float* hx, const float* g, int gin,
   }
 }
 
-}  // namespace
+void run_dur_predictor(dtts_acoustic* h, const float* dur_in, const float* keep, float* d1, float* d2, int B, int Tw,
+                       float* dur, int64_t* dur_int, Launcher& L, TcRun* tc) {
+  const dtts_acoustic_desc& d = h->d;
+  const int C = d.dur_chans;
+  cudaStream_t s = L.stream;
+  const int C_in = h->dur_conv.empty() ? 0 : h->dur_conv[0].C_in;
+  const float* cur = dur_in;
+  float* bufs[2] = {d1, d2};
+  if (tc) tc->stage_nct(tc->P[0], dur_in, C_in, Tw);
+  for (int i = 0; i < d.dur_layers; ++i) {
+    float* c = bufs[0];
+    float* y = bufs[1];
+    if (tc) {
+      TcRun::Epi er;
+      er.act = 1;
+      tc->conv_nct(tc->P[0], h->t_dur[i], c, Tw, 1, (d.dur_kernel - 1) / 2, er);
+      const bool last = i == d.dur_layers - 1;              // LayerNorm -> next convolution's planes (k = 5: zero halo)
+      L(channel_layernorm_planes(c, nullptr, y, h->dur_ln_g[i], h->dur_ln_b[i], 1e-5f, nullptr, keep, B, C, Tw,
+                                 last ? PlaneOut() : tc->out_of(tc->P[0], C, Tw, true), s));
+    } else {
+      ConvParams p = conv_params(cur, Tw, h->dur_conv[i], 0, C, c, Tw, 1, 1, (d.dur_kernel - 1) / 2);
+      p.act = ACT_RELU;
+      L(launch_conv1d_f32(p, B, s));
+      L(channel_layernorm(c, y, h->dur_ln_g[i], h->dur_ln_b[i], 1e-5f, nullptr, keep, B, C, Tw, s));
+    }
+    cur = y;
+    bufs[0] = c;      // conv output buffer can be reused: next conv reads y, writes c
+  }
+  L(dur_head(cur, h->dur_w, h->dur_b, keep, B, C, Tw, dur, dur_int, s));
+}
+
+int pack_dur_predictor(dtts_acoustic* h, int c_in, cudaStream_t s) {
+  const dtts_acoustic_desc* d = &h->d;
+  const int H = c_in;
+  for (int i = 0; i < d->dur_layers; ++i) {
+    ConvW c;
+    const std::string q = "dur_predictor.conv." + std::to_string(i);
+    DTTS_TRY(pack(h, q + ".1", d->dur_chans, i == 0 ? H : d->dur_chans, d->dur_kernel, true, &c, s));
+    h->dur_conv.push_back(c);
+    if (h->precision) {
+      TcConvW tcw;
+      DTTS_TRY(tc_pack1(h, q + ".1", true, d->dur_chans, i == 0 ? H : d->dur_chans, d->dur_kernel, 0, &tcw, s));
+      h->t_dur.push_back(tcw);
+    }
+    const float* g = h->tab.get(q + ".3.weight", d->dur_chans);
+    const float* b = h->tab.get(q + ".3.bias", d->dur_chans);
+    if (!g || !b) return DTTS_ERR_MISSING_WEIGHT;
+    h->dur_ln_g.push_back(g);
+    h->dur_ln_b.push_back(b);
+  }
+  h->dur_w = h->tab.get("dur_predictor.linear.0.weight", d->dur_chans);
+  h->dur_b = h->tab.get("dur_predictor.linear.0.bias", 1);
+  if (!h->dur_w || !h->dur_b) return DTTS_ERR_MISSING_WEIGHT;
+  return DTTS_OK;
+}
+
+int pack_decoder(dtts_acoustic* h, cudaStream_t s) {
+  const dtts_acoustic_desc* d = &h->d;
+  const int H = d->hidden;
+  DTTS_TRY(pack(h, "fvae.g_pre_net.0", H, H, 8, true, &h->g_pre, s));
+  if (h->precision) {
+    // Conv1d(H,H,k=8,s=4,p=2) == Conv1d(4H,H,k=3,p=1) over x'[(s,ci), q] = g[ci, 4q+s] with
+    // w'[co,(s,ci),a] = w[co,ci,4(a-1)+s+2] (zero where that tap does not exist)
+    const float* w8 = h->tab.get("fvae.g_pre_net.0.weight", (uint64_t)H * H * 8);
+    const float* b8 = h->tab.get("fvae.g_pre_net.0.bias", H);
+    if (!w8 || !b8) return DTTS_ERR_MISSING_WEIGHT;
+    float* w3 = h->pool.take((size_t)H * 4 * H * 3);
+    if (!w3) return fail(DTTS_ERR_CUDA, "weight pool exhausted");
+    DTTS_CUDA(repack_s2d4(w8, w3, H, H, s));
+    const float* w3c = w3;
+    DTTS_TRY(tc_pack(h, &w3c, 1, b8, H, 4 * H, 3, 0, 0, &h->t_gpre, s));
+  }
+  const int half = d->latent / 2;
+  for (int f = 0; f < d->flow_blocks; ++f) {
+    FlowW F;
+    // reversed(flows) = Flip, RCL_{n-1}, Flip, RCL_{n-2}, ...: RCL_f runs after (n - f) flips.
+    F.odd = ((d->flow_blocks - f) & 1);
+    const std::string q = "fvae.prior_flow.flows." + std::to_string(2 * f);
+    DTTS_TRY(pack(h, q + ".pre", d->flow_hidden, half, 1, true, &F.pre, s, F.odd, 0));
+    DTTS_TRY(pack(h, q + ".post", half, d->flow_hidden, 1, true, &F.post, s, 0, F.odd));
+    DTTS_TRY(pack_wn(h, q + ".enc", d->flow_hidden, d->flow_layers, d->flow_kernel, H, &F.wn, s));
+    h->flows.push_back(F);
+  }
+  {
+    // ConvTranspose1d(latent -> H, k=4, s=4): weight [latent][H][4]
+    const float* w = h->tab.get("fvae.decoder.pre_net.0.weight", (uint64_t)d->latent * H * 4);
+    const float* b = h->tab.get("fvae.decoder.pre_net.0.bias", H);
+    if (!w || !b) return DTTS_ERR_MISSING_WEIGHT;
+    float* dst = h->pool.take((size_t)d->latent * H * 4);
+    if (!dst) return fail(DTTS_ERR_CUDA, "weight pool exhausted");
+    DTTS_CUDA(repack_convT(w, dst, d->latent, H, 4, 4, s));
+    h->dec_pre.w = dst; h->dec_pre.bias = b; h->dec_pre.C_out = H; h->dec_pre.C_in = d->latent;
+    h->dec_pre.ktaps = 1; h->dec_pre.phases = 4;
+  }
+  DTTS_TRY(pack_wn(h, "fvae.decoder.wn", H, d->dec_layers, d->dec_kernel, H, &h->dec_wn, s));
+  DTTS_TRY(pack(h, "fvae.decoder.out_proj", d->n_mel, H, 1, true, &h->dec_out, s));
+  if (h->precision) {
+    // out_proj: C_out = n_mel (80) padded with zero rows to a multiple of 32 for the MMA's N
+    const int np = (d->n_mel + 31) / 32 * 32;
+    const float* wo = h->tab.get("fvae.decoder.out_proj.weight", (uint64_t)d->n_mel * H);
+    const float* bo = h->tab.get("fvae.decoder.out_proj.bias", d->n_mel);
+    if (!wo || !bo) return DTTS_ERR_MISSING_WEIGHT;
+    float* wp = h->pool.take((size_t)np * H);
+    float* bp = h->pool.take(np);
+    if (!wp || !bp) return fail(DTTS_ERR_CUDA, "weight pool exhausted");
+    DTTS_CUDA(cudaMemsetAsync(wp, 0, (size_t)np * H * sizeof(float), s));
+    DTTS_CUDA(cudaMemsetAsync(bp, 0, np * sizeof(float), s));
+    DTTS_CUDA(cudaMemcpyAsync(wp, wo, (size_t)d->n_mel * H * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    DTTS_CUDA(cudaMemcpyAsync(bp, bo, d->n_mel * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    const float* wpc = wp;
+    DTTS_TRY(tc_pack(h, &wpc, 1, bp, np, H, 1, 0, 0, &h->t_out, s));
+    h->out_pad = np;
+  }
+  return DTTS_OK;
+}
+
+}  // namespace ac
+}  // namespace dtts
 
 extern "C" int dtts_acoustic_create(const dtts_acoustic_desc* d, const float* arena_dev, uint64_t arena_floats,
                                     const dtts_weight_entry* table, int32_t n_entries, void* stream,
@@ -421,6 +399,11 @@ extern "C" int dtts_acoustic_create(const dtts_acoustic_desc* d, const float* ar
       d->ffn_kernel <= 0 || d->ffn_filter <= 0 || d->dur_layers < 0 || d->dur_chans <= 0 || d->flow_blocks < 0 ||
       d->flow_hidden <= 0 || d->n_mel <= 0 || d->word_size <= 0 || d->pinyin_size <= 0)
     return fail(DTTS_ERR_BAD_SHAPE, "unsupported acoustic configuration");
+  if (d->model != DTTS_MODEL_DICT && d->model != DTTS_MODEL_PORTASPEECH)
+    return fail(DTTS_ERR_BAD_ARG, "dtts_acoustic_desc.model must be DTTS_MODEL_DICT or DTTS_MODEL_PORTASPEECH");
+  if (d->model == DTTS_MODEL_PORTASPEECH && (d->ph_size <= 0 || d->word_enc_layers < 0 || d->rel_window < 0 ||
+                                             d->hidden % 2 || d->hidden < 4))
+    return fail(DTTS_ERR_BAD_SHAPE, "unsupported PortaSpeech configuration");
   if (d->precision != 0 && d->precision != 1)
     return fail(DTTS_ERR_BAD_ARG, "acoustic precision must be 0 (fp32 FMA) or 1 (tcgen05, bf16 hi/lo split)");
   if (d->s2pa_route != 0 && d->s2pa_route != 1)
@@ -452,12 +435,18 @@ extern "C" int dtts_acoustic_create(const dtts_acoustic_desc* d, const float* ar
   }
   auto build = [&]() -> int {
     const int H = d->hidden, D = d->dict_dim;
+    if (d->model == DTTS_MODEL_PORTASPEECH) {          // own text side, shared predictor / decoder
+      DTTS_TRY(create_ps(h, s));
+      DTTS_TRY(pack_dur_predictor(h, H, s));
+      return pack_decoder(h, s);
+    }
     const std::string p = "dict_encoder.S2PA_module";
     h->word_emb = h->tab.get(p + ".word_emb.weight", (uint64_t)d->word_size * H);
     h->pinyin_emb = h->tab.get(p + ".s2pa_attention.pinyin_embedding.weight", (uint64_t)d->pinyin_size * H);
     if (!h->word_emb || !h->pinyin_emb) return DTTS_ERR_MISSING_WEIGHT;
     DTTS_TRY(pack_encoder(h, p + ".semantic_encoder", &h->sem, s));
     DTTS_TRY(pack_encoder(h, p + ".linguistic_encoder", &h->lin, s));
+    if (!h->sem.last_g || !h->lin.last_g) return fail(DTTS_ERR_MISSING_WEIGHT, "missing weight: <encoder>.last_ln.gamma");
     const std::string a = p + ".s2pa_attention";
     DTTS_TRY(pack(h, a + ".q_transform", H, H, 1, false, &h->s2pa_q, s));
     DTTS_TRY(pack(h, a + ".v_transform", H, D, 1, false, &h->s2pa_v, s));
@@ -479,79 +468,8 @@ extern "C" int dtts_acoustic_create(const dtts_acoustic_desc* d, const float* ar
       if (!wkv[0] || !wkv[1]) return DTTS_ERR_MISSING_WEIGHT;
       DTTS_TRY(tc_pack(h, wkv, 2, nullptr, H, D, 1, 0, H, &h->t_s2pa_kv, s));      // N = H: one block per projection
     }
-    for (int i = 0; i < d->dur_layers; ++i) {
-      ConvW c;
-      const std::string q = "dur_predictor.conv." + std::to_string(i);
-      DTTS_TRY(pack(h, q + ".1", d->dur_chans, i == 0 ? H : d->dur_chans, d->dur_kernel, true, &c, s));
-      h->dur_conv.push_back(c);
-      if (h->precision) {
-        TcConvW tcw;
-        DTTS_TRY(tc_pack1(h, q + ".1", true, d->dur_chans, i == 0 ? H : d->dur_chans, d->dur_kernel, 0, &tcw, s));
-        h->t_dur.push_back(tcw);
-      }
-      const float* g = h->tab.get(q + ".3.weight", d->dur_chans);
-      const float* b = h->tab.get(q + ".3.bias", d->dur_chans);
-      if (!g || !b) return DTTS_ERR_MISSING_WEIGHT;
-      h->dur_ln_g.push_back(g);
-      h->dur_ln_b.push_back(b);
-    }
-    h->dur_w = h->tab.get("dur_predictor.linear.0.weight", d->dur_chans);
-    h->dur_b = h->tab.get("dur_predictor.linear.0.bias", 1);
-    if (!h->dur_w || !h->dur_b) return DTTS_ERR_MISSING_WEIGHT;
-    DTTS_TRY(pack(h, "fvae.g_pre_net.0", H, H, 8, true, &h->g_pre, s));
-    if (h->precision) {
-      // Conv1d(H,H,k=8,s=4,p=2) == Conv1d(4H,H,k=3,p=1) over x'[(s,ci), q] = g[ci, 4q+s] with
-      // w'[co,(s,ci),a] = w[co,ci,4(a-1)+s+2] (zero where that tap does not exist)
-      const float* w8 = h->tab.get("fvae.g_pre_net.0.weight", (uint64_t)H * H * 8);
-      const float* b8 = h->tab.get("fvae.g_pre_net.0.bias", H);
-      if (!w8 || !b8) return DTTS_ERR_MISSING_WEIGHT;
-      float* w3 = h->pool.take((size_t)H * 4 * H * 3);
-      if (!w3) return fail(DTTS_ERR_CUDA, "weight pool exhausted");
-      DTTS_CUDA(repack_s2d4(w8, w3, H, H, s));
-      const float* w3c = w3;
-      DTTS_TRY(tc_pack(h, &w3c, 1, b8, H, 4 * H, 3, 0, 0, &h->t_gpre, s));
-    }
-    const int half = d->latent / 2;
-    for (int f = 0; f < d->flow_blocks; ++f) {
-      FlowW F;
-      // reversed(flows) = Flip, RCL_{n-1}, Flip, RCL_{n-2}, ...: RCL_f runs after (n - f) flips.
-      F.odd = ((d->flow_blocks - f) & 1);
-      const std::string q = "fvae.prior_flow.flows." + std::to_string(2 * f);
-      DTTS_TRY(pack(h, q + ".pre", d->flow_hidden, half, 1, true, &F.pre, s, F.odd, 0));
-      DTTS_TRY(pack(h, q + ".post", half, d->flow_hidden, 1, true, &F.post, s, 0, F.odd));
-      DTTS_TRY(pack_wn(h, q + ".enc", d->flow_hidden, d->flow_layers, d->flow_kernel, H, &F.wn, s));
-      h->flows.push_back(F);
-    }
-    {
-      // ConvTranspose1d(latent -> H, k=4, s=4): weight [latent][H][4]
-      const float* w = h->tab.get("fvae.decoder.pre_net.0.weight", (uint64_t)d->latent * H * 4);
-      const float* b = h->tab.get("fvae.decoder.pre_net.0.bias", H);
-      if (!w || !b) return DTTS_ERR_MISSING_WEIGHT;
-      float* dst = h->pool.take((size_t)d->latent * H * 4);
-      if (!dst) return fail(DTTS_ERR_CUDA, "weight pool exhausted");
-      DTTS_CUDA(repack_convT(w, dst, d->latent, H, 4, 4, s));
-      h->dec_pre.w = dst; h->dec_pre.bias = b; h->dec_pre.C_out = H; h->dec_pre.C_in = d->latent;
-      h->dec_pre.ktaps = 1; h->dec_pre.phases = 4;
-    }
-    DTTS_TRY(pack_wn(h, "fvae.decoder.wn", H, d->dec_layers, d->dec_kernel, H, &h->dec_wn, s));
-    DTTS_TRY(pack(h, "fvae.decoder.out_proj", d->n_mel, H, 1, true, &h->dec_out, s));
-    if (h->precision) {
-      // out_proj: C_out = n_mel (80) padded with zero rows to a multiple of 32 for the MMA's N
-      const int np = (d->n_mel + 31) / 32 * 32;
-      const float* wo = h->tab.get("fvae.decoder.out_proj.weight", (uint64_t)d->n_mel * H);
-      const float* bo = h->tab.get("fvae.decoder.out_proj.bias", d->n_mel);
-      if (!wo || !bo) return DTTS_ERR_MISSING_WEIGHT;
-      float* wp = h->pool.take((size_t)np * H);
-      float* bp = h->pool.take(np);
-      if (!wp || !bp) return fail(DTTS_ERR_CUDA, "weight pool exhausted");
-      DTTS_CUDA(cudaMemsetAsync(wp, 0, (size_t)np * H * sizeof(float), s));
-      DTTS_CUDA(cudaMemsetAsync(bp, 0, np * sizeof(float), s));
-      DTTS_CUDA(cudaMemcpyAsync(wp, wo, (size_t)d->n_mel * H * sizeof(float), cudaMemcpyDeviceToDevice, s));
-      DTTS_CUDA(cudaMemcpyAsync(bp, bo, d->n_mel * sizeof(float), cudaMemcpyDeviceToDevice, s));
-      const float* wpc = wp;
-      DTTS_TRY(tc_pack(h, &wpc, 1, bp, np, H, 1, 0, 0, &h->t_out, s));
-      h->out_pad = np;
-    }
+    DTTS_TRY(pack_dur_predictor(h, H, s));
+    DTTS_TRY(pack_decoder(h, s));
     return DTTS_OK;
   };
   rc = build();
@@ -577,6 +495,7 @@ extern "C" int dtts_acoustic_create(const dtts_acoustic_desc* d, const float* ar
 extern "C" int dtts_acoustic_destroy(dtts_acoustic* h) {
   if (!h) return DTTS_OK;
   h->pool.release();
+  destroy_ps(h);
   if (h->tc_pool) cudaFree(h->tc_pool);
   if (h->bank_err_dev) cudaFree(h->bank_err_dev);
   if (h->bank_err_host) cudaFreeHost(h->bank_err_host);
@@ -631,6 +550,8 @@ extern "C" uint64_t dtts_text_workspace_bytes(const dtts_acoustic* h, int32_t B,
 static int text_encode_impl(dtts_acoustic* h, const dtts_text_in* in, const dtts_text_out* out, void* ws,
                             uint64_t ws_bytes, void* stream, const int64_t* row_off, const int32_t* row_len) {
   if (!h || !in || !out || !ws) return fail(DTTS_ERR_BAD_ARG, "dtts_text_encode: null argument");
+  if (h->d.model != DTTS_MODEL_DICT)
+    return fail(DTTS_ERR_BAD_ARG, "dtts_text_encode: this handle holds a PortaSpeech model (use dtts_ps_text_encode)");
   const int B = in->B, Tw = in->Tw, Lk = in->Lk, Lp = in->Lp;
   if (B <= 0 || Tw <= 0 || Lk <= 0 || Lp <= 0) return fail(DTTS_ERR_BAD_SHAPE, "dtts_text_encode: empty shape");
   if (!in->word_tokens_dev || !in->keys_dev || !in->values_dev || !in->key_map_dev || !in->pinyin_dev ||
@@ -746,29 +667,7 @@ static int text_encode_impl(dtts_acoustic* h, const dtts_text_in* in, const dtts
   L(finish_text(hb, tok_mask, B, Tw, H, out->word_encoder_out_dev, dur_in, keep, s));
   L(count_keep(keep, B, Tw, out->ilens_dev, s));
   // duration predictor (portaspeech/model.py:58-66)
-  const float* cur = dur_in;
-  float* bufs[2] = {d1, d2};
-  if (tc) tc->stage_nct(tc->P[0], dur_in, H, Tw);
-  for (int i = 0; i < d.dur_layers; ++i) {
-    float* c = bufs[0];
-    float* y = bufs[1];
-    if (tc) {
-      TcRun::Epi er;
-      er.act = 1;
-      tc->conv_nct(tc->P[0], h->t_dur[i], c, Tw, 1, (d.dur_kernel - 1) / 2, er);
-      const bool last = i == d.dur_layers - 1;              // LayerNorm -> next convolution's planes (k = 5: zero halo)
-      L(channel_layernorm_planes(c, nullptr, y, h->dur_ln_g[i], h->dur_ln_b[i], 1e-5f, nullptr, keep, B, C, Tw,
-                                 last ? PlaneOut() : tc->out_of(tc->P[0], C, Tw, true), s));
-    } else {
-      ConvParams p = conv_params(cur, Tw, h->dur_conv[i], 0, C, c, Tw, 1, 1, (d.dur_kernel - 1) / 2);
-      p.act = ACT_RELU;
-      L(launch_conv1d_f32(p, B, s));
-      L(channel_layernorm(c, y, h->dur_ln_g[i], h->dur_ln_b[i], 1e-5f, nullptr, keep, B, C, Tw, s));
-    }
-    cur = y;
-    bufs[0] = c;      // conv output buffer can be reused: next conv reads y, writes c
-  }
-  L(dur_head(cur, h->dur_w, h->dur_b, keep, B, C, Tw, out->dur_dev, out->dur_int_dev, s));
+  run_dur_predictor(h, dur_in, keep, d1, d2, B, Tw, out->dur_dev, out->dur_int_dev, L, tc);
   if (L.err != cudaSuccess) return fail(DTTS_ERR_CUDA, std::string("dtts_text_encode: ") + cudaGetErrorString(L.err));
   return DTTS_OK;
 }

@@ -13,6 +13,7 @@ import torch
 
 from . import binding
 from .config import AcousticConfig, VocoderConfig
+from .profiling import Timer
 from .weights import drop_dead, fold_weight_norm, pack_arena
 
 
@@ -77,6 +78,7 @@ class DictTTSEngine:
                                                         len(table), _stream(), C.byref(self.handle)), "acoustic_create")
         self.ws = _Workspace(self.device)
         self._t_raw = C.c_int32(0)
+        self.profile_infer = False     # hparams['profile_infer']: the stage Timers synchronise and print like upstream
 
     def close(self):
         if getattr(self, "handle", None):
@@ -251,31 +253,35 @@ class DictTTSEngine:
         if spk_embed is not None:
             raise NotImplementedError("multi-speaker conditioning is off in dict_tts.yaml (use_spk_embed: false)")
         word_tokens = txt_tokens[0] if isinstance(txt_tokens, (tuple, list)) else txt_tokens
+        prof = self.profile_infer
         with torch.cuda.device(self.device):
             ret = {}
-            if dict_ids is not None and dict_msg is None:     # extension: characters named by dictionary-bank id
-                t = self.text_encode_bank(word_tokens, pron_modified, dict_ids)
-            else:
-                keys, values, key_map, pinyin, pinyin_map = dict_msg
-                t = self.text_encode(word_tokens, pron_modified, keys, values, key_map, pinyin, pinyin_map)
-            ret["dict_attn"], ret["rel"], ret["dp_attn"] = t["dict_attn"], None, None
-            ret["pron_attn"], ret["dur"], ret["word_encoder_out"] = t["pron_attn"], t["dur"], t["word_encoder_out"]
-            fm = self.cfg.frames_multiple
-            if mel2word is None:
-                mel2word = self.length_regulate(t["dur_int"], t["ilens"])
-            else:
-                mel2word = _dev_i64(mel2word, self.device)
-                if mel2word.shape[1] % fm:                    # model.py:98-100
-                    pad = fm - mel2word.shape[1] % fm
-                    mel2word = torch.cat([mel2word] + [mel2word[:, -1:]] * pad, -1).contiguous()
-            ret["mel2word"] = mel2word
-            decoder_inp, g_bct, x_mask = self.expand(t["word_encoder_out"], mel2word)
+            with Timer("encoder", enable=prof):                   # model.py:50 (run_text_encoder)
+                with Timer("dict_encoder", enable=prof):          # model.py:86
+                    if dict_ids is not None and dict_msg is None:     # extension: characters named by dictionary-bank id
+                        t = self.text_encode_bank(word_tokens, pron_modified, dict_ids)
+                    else:
+                        keys, values, key_map, pinyin, pinyin_map = dict_msg
+                        t = self.text_encode(word_tokens, pron_modified, keys, values, key_map, pinyin, pinyin_map)
+                ret["dict_attn"], ret["rel"], ret["dp_attn"] = t["dict_attn"], None, None
+                ret["pron_attn"], ret["dur"], ret["word_encoder_out"] = t["pron_attn"], t["dur"], t["word_encoder_out"]
+                fm = self.cfg.frames_multiple
+                if mel2word is None:
+                    mel2word = self.length_regulate(t["dur_int"], t["ilens"])
+                else:
+                    mel2word = _dev_i64(mel2word, self.device)
+                    if mel2word.shape[1] % fm:                    # model.py:98-100
+                        pad = fm - mel2word.shape[1] % fm
+                        mel2word = torch.cat([mel2word] + [mel2word[:, -1:]] * pad, -1).contiguous()
+                ret["mel2word"] = mel2word
+                decoder_inp, g_bct, x_mask = self.expand(t["word_encoder_out"], mel2word)
             ret["x_mask"], ret["decoder_inp"] = x_mask.unsqueeze(-1), decoder_inp
             ret["synta"] = torch.zeros_like(g_bct)
             B, _, T = g_bct.shape
             if z_p is None:
                 z_p = torch.distributions.Normal(0, 1).sample([B, self.cfg.latent, T // fm])
-            mel, z_out = self.decode_mel(g_bct, z_p)
+            with Timer("fvae", enable=prof):                      # model.py:57
+                mel, z_out = self.decode_mel(g_bct, z_p)
             ret["mel_out_fvae"] = ret["mel_out"] = mel
             ret["z_p"] = z_out
         return ret
@@ -315,6 +321,7 @@ class HifiGanEngine:
             binding.check(self.lib.dtts_vocoder_create(C.byref(desc), _ptr(self.arena), self.arena.numel(), tab,
                                                        len(table), _stream(), C.byref(self.handle)), "vocoder_create")
         self.ws = _Workspace(self.device)
+        self.profile_infer = False
 
     def close(self):
         if getattr(self, "handle", None):
@@ -341,7 +348,7 @@ class HifiGanEngine:
             raise ValueError("mel must be [B,T,n_mel]")
         B, T, _ = mel.shape
         wav = torch.empty(B, T * self.cfg.hop, device=self.device)
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), Timer("hifigan", enable=self.profile_infer):   # vocoders/hifigan.py:59
             ws = self.ws.get(self.lib.dtts_vocode_workspace_bytes(self.handle, B, T))
             if lengths is None:
                 binding.check(self.lib.dtts_vocode(self.handle, _ptr(mel), B, T, _ptr(wav), _ptr(ws), ws.numel(),

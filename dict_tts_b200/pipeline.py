@@ -11,6 +11,7 @@ import torch
 
 from .config import AcousticConfig, VocoderConfig
 from .engine import DictTTSEngine, HifiGanEngine
+from .profiling import Timer
 
 _INPUT_KEYS = ("word_tokens", "pron_modified", "keys", "values", "key_map", "pinyin", "pinyin_map", "mel2word", "z_p",
                "dict_ids")
@@ -58,33 +59,39 @@ class TextToWav:
     def run_device(self, dev: Dict[str, torch.Tensor], record=None):
         """Device-resident inputs -> (ret dict, wav [B, T*hop]) on the device.  ``record(name)`` marks stage ends."""
         eng = self.acoustic
+        prof = eng.profile_infer
         with torch.cuda.device(self.device):
-            if "keys" in dev:
-                t = eng.text_encode(dev["word_tokens"], dev.get("pron_modified"), dev["keys"], dev["values"],
-                                    dev["key_map"], dev["pinyin"], dev["pinyin_map"])
-            else:                                 # GPU-resident dictionary bank: only ids cross the bus
-                if "_bank" in dev:
-                    eng.set_dict_bank(dev["_bank"])
-                t = eng.text_encode_bank(dev["word_tokens"], dev.get("pron_modified"), dev["dict_ids"], *dev["_dims"])
-            if record:
-                record("text_encode")
-            m2w = dev.get("mel2word")
-            if m2w is None:
-                m2w = eng.length_regulate(t["dur_int"], t["ilens"])
-            elif m2w.shape[1] % eng.cfg.frames_multiple:
-                pad = eng.cfg.frames_multiple - m2w.shape[1] % eng.cfg.frames_multiple
-                m2w = torch.cat([m2w] + [m2w[:, -1:]] * pad, -1).contiguous()
-            dec_in, g_bct, x_mask = eng.expand(t["word_encoder_out"], m2w)
-            if record:
-                record("length_regulate")
+            with Timer("encoder", enable=prof):       # the reference's stage names (profiling.py)
+                with Timer("dict_encoder", enable=prof):
+                    if "keys" in dev:
+                        t = eng.text_encode(dev["word_tokens"], dev.get("pron_modified"), dev["keys"], dev["values"],
+                                            dev["key_map"], dev["pinyin"], dev["pinyin_map"])
+                    else:                             # GPU-resident dictionary bank: only ids cross the bus
+                        if "_bank" in dev:
+                            eng.set_dict_bank(dev["_bank"])
+                        t = eng.text_encode_bank(dev["word_tokens"], dev.get("pron_modified"), dev["dict_ids"],
+                                                 *dev["_dims"])
+                if record:
+                    record("text_encode")
+                m2w = dev.get("mel2word")
+                if m2w is None:
+                    m2w = eng.length_regulate(t["dur_int"], t["ilens"])
+                elif m2w.shape[1] % eng.cfg.frames_multiple:
+                    pad = eng.cfg.frames_multiple - m2w.shape[1] % eng.cfg.frames_multiple
+                    m2w = torch.cat([m2w] + [m2w[:, -1:]] * pad, -1).contiguous()
+                dec_in, g_bct, x_mask = eng.expand(t["word_encoder_out"], m2w)
+                if record:
+                    record("length_regulate")
             z = dev.get("z_p")
             if z is None:
                 z = torch.distributions.Normal(0, 1).sample([g_bct.shape[0], eng.cfg.latent,
                                                              g_bct.shape[2] // eng.cfg.frames_multiple])
-            mel, z_p = eng.decode_mel(g_bct, z)
+            with Timer("fvae", enable=prof):
+                mel, z_p = eng.decode_mel(g_bct, z)
             if record:
                 record("decode_mel")
-            # valid frames per utterance: the vocoder skips what only the padded tail depends on (dtts_vocode_lens)
+            # valid frames per utterance: the vocoder skips what only the padded tail depends on (dtts_vocode_lens);
+            # HifiGanEngine.forward opens the 'hifigan' range itself
             wav = self.vocoder(mel, (m2w > 0).sum(-1) if self.trim_padding else None)
             if record:
                 record("vocode")

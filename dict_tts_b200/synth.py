@@ -152,8 +152,12 @@ _NPRON_P = [0.86, 0.09, 0.03, 0.012, 0.005, 0.003]     # zh-dict.json statistics
 def make_batch(seed: int = 1234, B: int = 60, min_chars: int = 12, max_chars: int = 20,
                max_frames: int = 400, Lk_cap: int = 96, dict_dim: int = 768, word_size: int = 8000,
                pinyin_size: int = 185, pron_modified_p: float = 0.02, frames_multiple: int = 4,
-               with_mel2word: bool = True) -> Dict[str, torch.Tensor]:
+               with_mel2word: bool = True, alias_values: bool = False) -> Dict[str, torch.Tensor]:
     """One collated batch in the layout DictTTSDataset.collater produces (dataset_utils.py:264-302).
+
+    alias_values: ``values`` IS the ``keys`` tensor, as the binarized data has it (one feature tensor stored as both
+    'key' and 'value', data_gen/tts/binarizer_zh.py:231-233) and as data.DictTTSTestSet keeps it; default: a separate
+    equal tensor, as the reference collater builds it.
 
     Returns word_tokens[B,Tw] i64, pron_modified[B,Tw] i64, keys/values[B,Tw,Lk,768] f32, key_map[B,Tw,Lk] f32,
     pinyin/pinyin_map[B,Tw,Lp] i64, word_lengths[B], mel2word[B,T] i64 (supplied durations: the reference's own
@@ -214,7 +218,7 @@ def make_batch(seed: int = 1234, B: int = 60, min_chars: int = 12, max_chars: in
                 pinyin_map[b, t, 2 * i:2 * i + 2] = i + 1
             if len(segs) > 1 and float(torch.rand(1, generator=g)) < pron_modified_p * 8:
                 pron_modified[b, t] = int(torch.randint(1, len(segs) + 1, (1,), generator=g))
-    values = keys.clone()                                    # binarizer stores the same LM features as key and value
+    values = keys if alias_values else keys.clone()          # binarizer stores the same LM features as key and value
     out = dict(word_tokens=word_tokens, pron_modified=pron_modified, keys=keys, values=values, key_map=key_map,
                pinyin=pinyin, pinyin_map=pinyin_map, word_lengths=n_chars + 2)
     if with_mel2word:

@@ -128,6 +128,7 @@ class B200DictTTSTask:
         self.model = DictTTSEngine(None, acfg, self.device, arena=dev_arena, table=table,
                                    precision=int(hp.get("b200_acoustic_precision", 1)),
                                    s2pa_route=int(hp.get("b200_s2pa_route", 0)))
+        self.model.profile_infer = bool(hp.get("profile_infer", False))     # stage Timers print like upstream
         return self.model
 
     def test_start(self):
@@ -136,6 +137,8 @@ class B200DictTTSTask:
         os.makedirs(os.path.join(self.gen_dir, "wavs"), exist_ok=True)
         cls = get_vocoder_cls(hp)
         self.vocoder = cls(device=self.device) if cls.__name__ == "B200HifiGAN" else cls()
+        if hasattr(self.vocoder, "engine"):
+            self.vocoder.engine.profile_infer = bool(hp.get("profile_infer", False))
         path = os.path.join(hp["binary_data_dir"], "pinyin_encoder.pkl")
         self.pinyin_encoder = None
         if os.path.exists(path):

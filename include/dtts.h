@@ -66,7 +66,17 @@ typedef struct dtts_acoustic_desc {
                               [B*Tw*Lk, dict_dim] x [dict_dim, 2*hidden] GEMM on tcgen05 (needs precision = 1), then
                               per-character scores / softmax / weighted sum over the projected rows.  Not available
                               with the dictionary bank (dtts_text_encode_bank). */
+  int32_t model;       /* DTTS_MODEL_DICT (0): PortaSpeech_dict, the fields above.  DTTS_MODEL_PORTASPEECH (1): the non-dict
+                          sibling (modules/portaspeech/model.py:132-366): phoneme encoder with
+                          relative-position attention + FFT-block word encoder + word-to-phoneme attention in front of
+                          the SAME duration predictor / length regulator / FVAE decoder; dict_dim, word_size, pinyin_size,
+                          language_zh and s2pa_route are ignored, the three fields below are used */
+  int32_t ph_size;          /* phoneme vocabulary (rows of ph_encoder.emb.weight)                                       */
+  int32_t word_enc_layers;  /* FFT blocks of the word encoder (hparams word_enc_layers)                                 */
+  int32_t rel_window;       /* relative-position window of the phoneme encoder's attention (4 upstream)                 */
 } dtts_acoustic_desc;
+#define DTTS_MODEL_DICT 0
+#define DTTS_MODEL_PORTASPEECH 1
 
 /* HiFi-GAN V1 generator description (egs/egs_bases/tts/vocoder/hifigan.yaml:3-10). */
 #define DTTS_MAX_UPS 8
@@ -182,6 +192,44 @@ int dtts_expand(dtts_acoustic* h, const float* word_encoder_out_dev, const int64
 uint64_t dtts_decode_workspace_bytes(const dtts_acoustic* h, int32_t B, int32_t T);
 int dtts_decode_mel(dtts_acoustic* h, const float* g_bct_dev, const float* z_in_dev, int32_t B, int32_t T,
                     float* mel_dev, float* z_p_dev, void* ws_dev, uint64_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * PortaSpeech (non-dict) sibling, SURVEY.md §8f-3: replaces PortaSpeech.run_text_encoder
+ * (modules/portaspeech/model.py:239-262) on a handle created with desc.model = DTTS_MODEL_PORTASPEECH.  The duration
+ * scan / fill (dtts_length_regulate_*) and dtts_decode_mel are the calls of the dict model.
+ *   dtts_ps_text_encode: TextEncoder (model.py:69-129: embedding, ConvReluNorm pre-net, post-LN encoder with
+ *     relative-position attention, rel_transformer_encoder.py:26-247) * src_nonpadding; group_hidden_by_segs
+ *     (portaspeech/utils.py:3-16) + FFT-block word encoder (fastspeech/tts_modules.py:458-566,
+ *     commons/common_layers.py:624-673); phoneme-level durations summed per word (model.py:317-340).
+ *   dtts_ps_attend: in-word sinusoidal positions (model.py:359-363), gather by mel2word, enc_pos_proj / dec_query_proj /
+ *     dec_res_proj and the one-head word-to-phoneme attention whose mask lets a frame see only the phonemes of its own
+ *     word (model.py:304-315), * tgt_nonpadding: the decoder input.
+ * Shapes: B utterances, Tp phonemes, Tw words (= word_len.max()), T mel frames (a multiple of frames_multiple).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct dtts_ps_text_in {
+  const int64_t* txt_tokens_dev; /* [B,Tp] phoneme ids, 0 = padding                      */
+  const int64_t* ph2word_dev;    /* [B,Tp] 1-based word index of every phoneme, 0 = pad  */
+  int32_t B, Tp, Tw;
+} dtts_ps_text_in;
+
+typedef struct dtts_ps_text_out {
+  float* ph_encoder_out_dev;   /* [B,Tp,hidden]  ret['ph_encoder_out']                                     */
+  float* word_encoder_out_dev; /* [B,Tw,hidden]  ret['word_encoder_out']                                   */
+  float* dur_dev;              /* [B,Tw]         ret['dur']: per-word sum of the phoneme-level predictions */
+  int64_t* dur_int_dev;        /* [B,Tw]         clamp(round(exp(dur)-1),0)                                */
+  int64_t* ilens_dev;          /* [B]            (1-src_padding).sum(-1) over PHONEMES, as add_dur passes it */
+} dtts_ps_text_out;
+
+uint64_t dtts_ps_text_workspace_bytes(const dtts_acoustic* h, int32_t B, int32_t Tp, int32_t Tw);
+int dtts_ps_text_encode(dtts_acoustic* h, const dtts_ps_text_in* in, const dtts_ps_text_out* out, void* ws_dev,
+                        uint64_t ws_bytes, void* stream);
+uint64_t dtts_ps_attend_workspace_bytes(const dtts_acoustic* h, int32_t B, int32_t Tp, int32_t Tw, int32_t T);
+/* attn_dev (optional): [B,T,Tp] attention weights, ret['attn'].  decoder_inp [B,T,hidden], g_bct [B,hidden,T] (the
+ * layout dtts_decode_mel reads), x_mask [B,T] = mel2word > 0. */
+int dtts_ps_attend(dtts_acoustic* h, const float* ph_encoder_out_dev, const float* word_encoder_out_dev,
+                   const int64_t* ph2word_dev, const int64_t* mel2word_dev, int32_t B, int32_t Tp, int32_t Tw, int32_t T,
+                   float* attn_dev, float* decoder_inp_dev, float* g_bct_dev, float* x_mask_dev, void* ws_dev,
+                   uint64_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Vocoder: replaces HifiGanGenerator.forward behind BaseVocoder.spec2wav (vocoders/hifigan.py:54-62).

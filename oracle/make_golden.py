@@ -37,23 +37,8 @@ VOCODER_CASES = [("voc_small", dict(seed=21, B=2, T=24)), ("voc_single", dict(se
 
 
 def build_reference_models():
-    R = ref_loader.load()
-    enc = R["TokenTextEncoder"](None, vocab_list=["a", "b", "c"], replace_oov="<UNK>")
-    model = R["model_cls"](enc).eval()
     sd = synth.make_acoustic_state_dict(1234)
-    missing, unexpected = model.load_state_dict(sd, strict=False)
-    assert not unexpected, unexpected
-    assert all(m.startswith("fvae.encoder.") for m in missing), missing
-
-    def _rm(m):
-        try:
-            torch.nn.utils.remove_weight_norm(m)
-        except ValueError:
-            pass
-    model.apply(_rm)                                                     # tasks/tts/ps_flow.py:262-268
-    voc = R["hifigan_cls"](R["voc_cfg"]).eval()
-    voc.load_state_dict(synth.make_vocoder_state_dict(4321), strict=True)
-    voc.remove_weight_norm()
+    model, voc = ref_loader.build_models(sd, synth.make_vocoder_state_dict(4321))
     return model, voc, sd
 
 

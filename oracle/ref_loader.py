@@ -11,7 +11,20 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("DTTS_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root() -> str:
+    """$DTTS_REFERENCE_ROOT, then /root/reference (the build container), then baseline/_ref (a driver-installed copy on
+    the GPU pod) -- the first that holds the model code."""
+    cands = [os.environ.get("DTTS_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "modules", "dict_tts")):
+            return c
+    return cands[1]
+
+
+REF_ROOT = _find_root()
 
 
 def available() -> bool:
@@ -48,3 +61,27 @@ def load():
     _loaded.update(model_cls=PortaSpeech_dict, hifigan_cls=HifiGanGenerator, hparams=hparams,
                    TokenTextEncoder=TokenTextEncoder, voc_cfg=voc_cfg)
     return _loaded
+
+
+def build_models(acoustic_sd, vocoder_sd):
+    """The UNMODIFIED reference modules holding the given checkpoints, in the state the reference's own inference
+    leaves them in: eval mode, weight-norm removed (tasks/tts/ps_flow.py:257-268, vocoders/hifigan.py:16-32).
+    Returns (PortaSpeech_dict, HifiGanGenerator)."""
+    import torch
+    R = load()
+    enc = R["TokenTextEncoder"](None, vocab_list=["a", "b", "c"], replace_oov="<UNK>")
+    model = R["model_cls"](enc).eval()
+    missing, unexpected = model.load_state_dict(acoustic_sd, strict=False)
+    assert not unexpected, unexpected
+    assert all(m.startswith("fvae.encoder.") for m in missing), missing
+
+    def _rm(m):
+        try:
+            torch.nn.utils.remove_weight_norm(m)
+        except ValueError:
+            pass
+    model.apply(_rm)
+    voc = R["hifigan_cls"](R["voc_cfg"]).eval()
+    voc.load_state_dict(vocoder_sd, strict=True)
+    voc.remove_weight_norm()
+    return model, voc
