@@ -22,7 +22,21 @@ class AcousticDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "hidden", "n_heads", "enc_layers", "ffn_kernel", "ffn_filter", "dict_dim", "word_size", "pinyin_size",
         "dur_layers", "dur_kernel", "dur_chans", "frames_multiple", "latent", "dec_layers", "dec_kernel",
-        "flow_hidden", "flow_kernel", "flow_blocks", "flow_layers", "n_mel", "language_zh", "precision", "s2pa_route")]
+        "flow_hidden", "flow_kernel", "flow_blocks", "flow_layers", "n_mel", "language_zh", "precision", "s2pa_route",
+        "model", "ph_size", "word_enc_layers", "rel_window")]
+
+
+MODEL_DICT, MODEL_PORTASPEECH = 0, 1
+
+
+class PsTextIn(C.Structure):
+    _fields_ = [("txt_tokens", C.c_void_p), ("ph2word", C.c_void_p), ("B", C.c_int32), ("Tp", C.c_int32),
+                ("Tw", C.c_int32)]
+
+
+class PsTextOut(C.Structure):
+    _fields_ = [("ph_encoder_out", C.c_void_p), ("word_encoder_out", C.c_void_p), ("dur", C.c_void_p),
+                ("dur_int", C.c_void_p), ("ilens", C.c_void_p)]
 
 
 class VocoderDesc(C.Structure):
@@ -68,6 +82,10 @@ SYMBOLS = {
     "dtts_text_encode_bank": (C.c_int, [_P, C.POINTER(DictBankStruct), C.POINTER(TextInBank), C.POINTER(TextOut), _P,
                                         _U64, _P]),
     "dtts_acoustic_status": (C.c_int, [_P, _P, _I]),
+    "dtts_ps_text_workspace_bytes": (_U64, [_P, _I, _I, _I]),
+    "dtts_ps_text_encode": (C.c_int, [_P, C.POINTER(PsTextIn), C.POINTER(PsTextOut), _P, _U64, _P]),
+    "dtts_ps_attend_workspace_bytes": (_U64, [_P, _I, _I, _I, _I]),
+    "dtts_ps_attend": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _U64, _P]),
     "dtts_length_regulate_scan": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, C.POINTER(C.c_int32), _P]),
     "dtts_length_regulate_fill": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "dtts_expand": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),

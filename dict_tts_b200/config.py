@@ -47,6 +47,26 @@ class AcousticConfig:
 
 
 @dataclass
+class PortaSpeechConfig(AcousticConfig):
+    """The non-dict sibling (egs/egs_bases/tts/ps_flow.yaml; modules/portaspeech/model.py:132-200): same predictor /
+    FVAE sizes, plus the phoneme vocabulary, the word encoder depth and the relative-position window."""
+    ph_size: int = 80            # len(phone dictionary): rows of ph_encoder.emb.weight
+    word_enc_layers: int = 4     # word_enc_layers        (ps_flow.yaml)
+    rel_window: int = 4          # TextEncoder(window_size=4) (portaspeech/model.py:79)
+
+    @staticmethod
+    def from_hparams(hp, ph_size: int = 80) -> "PortaSpeechConfig":
+        return PortaSpeechConfig(
+            hidden=hp["hidden_size"], n_heads=hp["num_heads"], enc_layers=hp["enc_layers"],
+            ffn_kernel=hp["enc_ffn_kernel_size"], ffn_filter=4 * hp["hidden_size"],
+            dur_layers=hp["dur_predictor_layers"], dur_kernel=hp["dur_predictor_kernel"],
+            frames_multiple=hp["frames_multiple"], latent=hp["latent_size"], dec_layers=hp["fvae_dec_n_layers"],
+            dec_kernel=hp["fvae_kernel_size"], flow_hidden=hp["prior_glow_hidden"], flow_kernel=hp["glow_kernel_size"],
+            flow_blocks=hp["prior_glow_n_blocks"], n_mel=hp["audio_num_mel_bins"], ph_size=ph_size,
+            word_enc_layers=hp["word_enc_layers"])
+
+
+@dataclass
 class VocoderConfig:
     """HiFi-GAN V1 generator (egs/egs_bases/tts/vocoder/hifigan.yaml:3-10)."""
     n_mel: int = 80

@@ -42,26 +42,26 @@ struct PsW;     // PortaSpeech text-side weights (portaspeech.cu)
 
 struct dtts_acoustic {
   dtts_acoustic_desc d;
-  WeightTable tab;
-  Pool pool;
+  dtts::WeightTable tab;
+  dtts::Pool pool;
   const float* word_emb;
   const float* pinyin_emb;
   dtts::ac::EncoderW sem, lin;
-  ConvW s2pa_q, s2pa_kT, s2pa_v, s2pa_o;
-  TcConvW t_s2pa_q, t_s2pa_kT, t_s2pa_v, t_s2pa_o;
-  TcConvW t_s2pa_kv;              // s2pa_route = 1: [W_k ; W_v] side by side, dict_dim -> 2 * hidden (block 0 = k, block 1 = v)
-  TcConvW t_gpre;                 // g_pre_net as a stride-1 k=3 convolution over the 4x space-to-depth input (C' = 4H)
-  TcConvW t_out;                  // out_proj with C_out zero-padded to a multiple of 32
+  dtts::ConvW s2pa_q, s2pa_kT, s2pa_v, s2pa_o;
+  dtts::TcConvW t_s2pa_q, t_s2pa_kT, t_s2pa_v, t_s2pa_o;
+  dtts::TcConvW t_s2pa_kv;              // s2pa_route = 1: [W_k ; W_v] side by side, dict_dim -> 2 * hidden (block 0 = k, block 1 = v)
+  dtts::TcConvW t_gpre;                 // g_pre_net as a stride-1 k=3 convolution over the 4x space-to-depth input (C' = 4H)
+  dtts::TcConvW t_out;                  // out_proj with C_out zero-padded to a multiple of 32
   int out_pad = 0;
-  std::vector<ConvW> dur_conv;
-  std::vector<TcConvW> t_dur;
+  std::vector<dtts::ConvW> dur_conv;
+  std::vector<dtts::TcConvW> t_dur;
   int precision = 0;              // 0: fp32 FMA pipe; 1: tcgen05 (bf16 hi/lo x hi/lo)
-  TcMode mode;
-  tc16* tc_pool = nullptr;
+  dtts::TcMode mode;
+  dtts::tc16* tc_pool = nullptr;
   size_t tc_cap = 0, tc_used = 0;
   std::vector<const float*> dur_ln_g, dur_ln_b;
   const float *dur_w, *dur_b;
-  ConvW g_pre, dec_pre, dec_out;
+  dtts::ConvW g_pre, dec_pre, dec_out;
   std::vector<dtts::ac::FlowW> flows;   // in reference order (flows.0, .2, .4, .6)
   dtts::ac::WNW dec_wn;
   dtts::ac::PsW* ps = nullptr;     // model = 1 (PortaSpeech sibling): its text-side weights; the dict-encoder members stay empty

@@ -16,7 +16,7 @@
 
 namespace dtts {
 
-enum { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2, ACT_GELU = 3 };   // GELU: exact (erf) form, F.gelu default
 
 struct ConvParams {
   // input, element (c, t) of batch b at x[b*x_bs + c*x_cs + t*x_ts]
@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(256, 2) conv1d_f32_kernel(const ConvParams p) 
       if (p.bias) v += __ldg(p.bias + co);
       if (p.act == ACT_RELU) v = fmaxf(v, 0.f);
       else if (p.act == ACT_TANH) v = tanhf(v);
+      else if (p.act == ACT_GELU) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
       v *= p.alpha * mk;
       if (p.res) v += p.res[(size_t)b * p.r_bs + (size_t)co * p.r_cs + (size_t)t * p.r_ts];
       v *= p.post;

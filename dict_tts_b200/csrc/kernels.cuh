@@ -24,8 +24,10 @@ cudaError_t fill_f32(float* p, float v, size_t n, cudaStream_t s);
 cudaError_t embed_tokens(const int64_t* tok, const float* emb, float scale, int B, int Tw, int H, int vocab,
                          float* x, float* seq_mask, float* tok_mask, int* lens, cudaStream_t s);
 // y = LN_c(x * in_mask) * gamma + beta, then * out_mask   (masks may be null) ; layout [B,C,T]
+// relu: y = relu(LN(.)) * out_mask (ConvReluNorm, portaspeech/glow_modules.py:65-72)
 cudaError_t channel_layernorm(const float* x, float* y, const float* gamma, const float* beta, float eps,
-                              const float* in_mask, const float* out_mask, int B, int C, int T, cudaStream_t s);
+                              const float* in_mask, const float* out_mask, int B, int C, int T, cudaStream_t s,
+                              int relu = 0);
 // Tiled LayerNorm with optional extra outputs: xw = x * in_mask (may alias x), y [B,C,T] (may be null) and operand planes.
 struct PlaneOut;
 cudaError_t channel_layernorm_planes(const float* x, float* xw, float* y, const float* gamma, const float* beta, float eps,
@@ -83,6 +85,29 @@ cudaError_t lr_fill(const int* cum, const int64_t* ilens, int B, int Tw, int T_r
 // gather: out_btc[b,t,:] = enc[b, m-1, :] (0 if m==0) ; out_bct = transpose ; nonpad[b,t] = m>0
 cudaError_t lr_gather(const float* enc_btc, const int64_t* mel2word, int B, int Tw, int T, int H, float* out_btc,
                       float* out_bct, float* nonpad, cudaStream_t s);
+
+// ---- PortaSpeech sibling (ps_kernels.cu) ----
+// self attention of any length on q,k,v slices of one [B,3C,T] tensor, with the relative-position terms of
+// rel_transformer_encoder.py:117-233 when rel_k / rel_v ([2*window+1, C/heads], shared by the heads) are given
+cudaError_t rel_self_attention(const float* q, const float* k, const float* v, const float* mask, const float* rel_k,
+                               const float* rel_v, int window, float* out, int B, int C, int T, int heads,
+                               const PlaneOut& po, cudaStream_t s);
+cudaError_t ps_finish_ph(const float* x, const int64_t* tok, int B, int Tp, int H, float* ph_btc, float* ph_bct,
+                         float* keep, cudaStream_t s);
+cudaError_t ps_group_by_segs(const float* ph, const int64_t* ph2word, int B, int Tp, int Tw, int H, float* out,
+                             cudaStream_t s);
+cudaError_t ps_fft_prepare(float* x, const float* table, int table_rows, const float* alpha, int B, int C, int T,
+                           float* keep, cudaStream_t s);
+cudaError_t ps_word_durations(const float* dur_ph, const float* keep_ph, const int64_t* ph2word, int B, int Tp, int Tw,
+                              float* dur, int64_t* dur_int, int64_t* ilens, cudaStream_t s);
+// out [B,2H,N] = [features ; sinusoidal in-word positions]; features = feat_btc[b,n,:] (gather == 0) or
+// feat_btc[b, x2word[b,n]-1, :] (gather != 0, feat_btc is [B,Tw,H], zero row for x2word == 0)
+cudaError_t ps_build_cat(const float* feat_btc, int gather, const int64_t* x2word, const float* freqs, int B, int N,
+                         int Tw, int H, float* out, cudaStream_t s);
+cudaError_t ps_word_attention(const float* q, const float* kv, const int64_t* mel2word, const int64_t* ph2word, int B,
+                              int H, int T, int Tp, float* attn, float* ctx, cudaStream_t s);
+cudaError_t bct_to_btc(const float* in, float* out, int B, int C, int T, cudaStream_t s);
+cudaError_t nonpad_mask(const int64_t* idx, float* mask, size_t n, cudaStream_t s);
 
 // ---- WaveNet gate ----
 // acts[b,c,t] = tanh(a[b,c,t]) * sigmoid(a[b,c+H,t]),  a [B,2H,T]

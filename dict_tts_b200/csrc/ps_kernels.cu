@@ -241,13 +241,13 @@ cudaError_t ps_word_durations(const float* dur_ph, const float* keep_ph, const i
 
 // ------------------------------------------------------------------------------------------------------------
 // Concatenated attention inputs, channel-first [B, 2H, N] (model.py:279-283,359-363):
-//   channels [0, H)  : feat[b, :, n]            (src_bct != null: the phoneme encoder output)
-//                      or word[b, x2word - 1, :] (gather by mel2word, zero row for 0)
+//   channels [0, H)  : feat[b, n, :]            (gather == 0: the phoneme encoder output [B,N,H])
+//                      or feat[b, x2word - 1, :] (gather != 0: word encoder output [B,Tw,H] by mel2word, zero row for 0)
 //   channels [H, 2H) : SinusoidalPosEmb(pos)[c], pos = (rank of n among the positions of its word) / (size of the word),
 //                      0 for x2word == 0 or a word id above Tw; emb = [sin(pos * e_i) | cos(pos * e_i)], i < H/2
 // x2word need not be sorted: rank and size are counted over the whole row, as the reference's cumsum over the
 // [B, T_word, N] mask does.
-__global__ void ps_build_cat_kernel(const float* __restrict__ src_bct, const float* __restrict__ word_btc,
+__global__ void ps_build_cat_kernel(const float* __restrict__ feat_btc, int gather,
                                     const int64_t* __restrict__ x2word, const float* __restrict__ freqs, int N, int Tw,
                                     int H, float* __restrict__ out) {
   extern __shared__ float s_posv[];             // [N]
@@ -273,26 +273,26 @@ __global__ void ps_build_cat_kernel(const float* __restrict__ src_bct, const flo
   for (int i = threadIdx.x; i < H * N; i += blockDim.x) {
     const int c = i / N, n = i - c * N;
     float f;
-    if (src_bct) {
-      f = src_bct[((size_t)b * H + c) * N + n];
+    if (!gather) {
+      f = feat_btc[((size_t)b * N + n) * H + c];
     } else {
       const int64_t w = seg[n];
-      f = (w >= 1 && w <= Tw) ? word_btc[((size_t)b * Tw + (w - 1)) * H + c] : 0.f;
+      f = (w >= 1 && w <= Tw) ? feat_btc[((size_t)b * Tw + (w - 1)) * H + c] : 0.f;
     }
     ob[i] = f;
     const float a = s_posv[n] * freqs[c < half ? c : c - half];
     ob[(size_t)H * N + i] = c < half ? sinf(a) : cosf(a);
   }
 }
-cudaError_t ps_build_cat(const float* src_bct, const float* word_btc, const int64_t* x2word, const float* freqs, int B,
-                         int N, int Tw, int H, float* out, cudaStream_t s) {
-  if (H % 2 || (!src_bct == !word_btc)) return cudaErrorInvalidValue;
+cudaError_t ps_build_cat(const float* feat_btc, int gather, const int64_t* x2word, const float* freqs, int B, int N,
+                         int Tw, int H, float* out, cudaStream_t s) {
+  if (H % 2 || !feat_btc) return cudaErrorInvalidValue;
   const size_t smem = (size_t)N * sizeof(float);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(ps_build_cat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  ps_build_cat_kernel<<<B, 256, smem, s>>>(src_bct, word_btc, x2word, freqs, N, Tw, H, out);
+  ps_build_cat_kernel<<<B, 256, smem, s>>>(feat_btc, gather, x2word, freqs, N, Tw, H, out);
   return cudaGetLastError();
 }
 

@@ -879,6 +879,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
           if (p.act == 1) {
 #pragma unroll
             for (int k = 0; k < 32; ++k) v[k] = fmaxf(v[k], 0.f);
+          } else if (p.act == 3) {                      // exact GELU (FFT-block FFN, common_layers.py:640-647)
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = 0.5f * v[k] * (1.f + erff(v[k] * 0.70710678118654752f));
           }
           if (p.alpha != 1.f || p.mask) {               // out = post * (act(conv + bias) * alpha * mask + res)
             const float am = p.alpha * (p.mask ? __ldg(p.mask + (size_t)tc.b * p.m_bs + t) : 1.f);

@@ -141,7 +141,7 @@ struct TcConvParams {
   long o_cs, o_ts, r_bs, r_cs, r_ts;
   const float* mask;             // optional [B][m_bs] multiplier per (b, t)
   int m_bs;
-  int act;                       // 0: none, 1: ReLU (applied to conv + bias)
+  int act;                       // 0: none, 1: ReLU, 3: exact GELU (applied to conv + bias; codes of conv1d_f32.cuh)
   float alpha;                   // out = post * (act(conv + bias) * alpha * mask + res)  (+ out if accumulate)
   int c_valid;                   // o_nct: only output channels < c_valid are stored (weights zero-padded to N % 32 == 0)
   int a_stages, w_stages;

@@ -46,7 +46,7 @@ cudaError_t embed_tokens(const int64_t* tok, const float* emb, float scale, int 
 // One thread per (b, t) column; lanes run along t so every pass over C is coalesced.
 __global__ void channel_ln_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, float eps, const float* __restrict__ in_mask,
-                                  const float* __restrict__ out_mask, int C, int T) {
+                                  const float* __restrict__ out_mask, int C, int T, int relu) {
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
@@ -64,15 +64,17 @@ __global__ void channel_ln_kernel(const float* __restrict__ x, float* __restrict
   }
   const float rstd = rsqrtf(var / (float)C + eps);
   for (int c = 0; c < C; ++c) {
-    const float v = (xp[(size_t)c * T] * im - mean) * rstd * gamma[c] + beta[c];
+    float v = (xp[(size_t)c * T] * im - mean) * rstd * gamma[c] + beta[c];
+    if (relu) v = fmaxf(v, 0.f);
     yp[(size_t)c * T] = v * om;
   }
 }
 
 cudaError_t channel_layernorm(const float* x, float* y, const float* gamma, const float* beta, float eps,
-                              const float* in_mask, const float* out_mask, int B, int C, int T, cudaStream_t s) {
+                              const float* in_mask, const float* out_mask, int B, int C, int T, cudaStream_t s,
+                              int relu) {
   dim3 grid(cdiv(T, 32), B);
-  channel_ln_kernel<<<grid, 32, 0, s>>>(x, y, gamma, beta, eps, in_mask, out_mask, C, T);
+  channel_ln_kernel<<<grid, 32, 0, s>>>(x, y, gamma, beta, eps, in_mask, out_mask, C, T, relu);
   return cudaGetLastError();
 }
 

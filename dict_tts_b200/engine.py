@@ -12,7 +12,7 @@ from typing import Dict, Optional
 import torch
 
 from . import binding
-from .config import AcousticConfig, VocoderConfig
+from .config import AcousticConfig, PortaSpeechConfig, VocoderConfig
 from .profiling import Timer
 from .weights import drop_dead, fold_weight_norm, pack_arena
 
@@ -70,7 +70,7 @@ class DictTTSEngine:
                                     c.word_size, c.pinyin_size, c.dur_layers, c.dur_kernel, c.dur_chans,
                                     c.frames_multiple, c.latent, c.dec_layers, c.dec_kernel, c.flow_hidden,
                                     c.flow_kernel, c.flow_blocks, c.flow_layers, c.n_mel, int(c.language_zh), int(precision),
-                                    int(s2pa_route))
+                                    int(s2pa_route), binding.MODEL_DICT, 0, 0, 0)
         tab, self._keep = binding.make_table(table)
         self.handle = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -281,6 +281,114 @@ class DictTTSEngine:
             if z_p is None:
                 z_p = torch.distributions.Normal(0, 1).sample([B, self.cfg.latent, T // fm])
             with Timer("fvae", enable=prof):                      # model.py:57
+                mel, z_out = self.decode_mel(g_bct, z_p)
+            ret["mel_out_fvae"] = ret["mel_out"] = mel
+            ret["z_p"] = z_out
+        return ret
+
+    __call__ = forward
+
+
+class PortaSpeechEngine(DictTTSEngine):
+    """The PortaSpeech (non-dict) sibling, SURVEY.md §8f-3: ``forward`` keeps the call signature and the returned dict of
+    ``PortaSpeech.forward`` (modules/portaspeech/model.py:202-237) at ``dur_level: word`` / ``use_post_glow: False`` (the
+    only inference path the reference checkout can construct: ``modules/glow`` is absent from it).  It shares the length
+    regulator and ``decode_mel`` with the dict model; the text side runs through ``dtts_ps_text_encode`` /
+    ``dtts_ps_attend``."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: Optional[PortaSpeechConfig] = None, device="cuda:0",
+                 arena: Optional[torch.Tensor] = None, table=None, precision: int = 1):
+        if not torch.cuda.is_available():
+            raise RuntimeError("PortaSpeechEngine needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = binding.load()
+        self.cfg = cfg or PortaSpeechConfig()
+        self.device = torch.device(device)
+        if arena is None:
+            sd = {k: v for k, v in fold_weight_norm(state_dict).items()
+                  if not k.startswith(("fvae.encoder.", "mel_disc.", "post_flow.", "g_proj.")) and v.is_floating_point()}
+            host, table = pack_arena(sd)
+            arena = host.to(self.device)
+        self.arena, self.table = arena, table
+        c = self.cfg
+        desc = binding.AcousticDesc(c.hidden, c.n_heads, c.enc_layers, c.ffn_kernel, c.ffn_filter, c.dict_dim,
+                                    c.word_size, c.pinyin_size, c.dur_layers, c.dur_kernel, c.dur_chans,
+                                    c.frames_multiple, c.latent, c.dec_layers, c.dec_kernel, c.flow_hidden,
+                                    c.flow_kernel, c.flow_blocks, c.flow_layers, c.n_mel, 0, int(precision), 0,
+                                    binding.MODEL_PORTASPEECH, c.ph_size, c.word_enc_layers, c.rel_window)
+        tab, self._keep = binding.make_table(table)
+        self.handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            binding.check(self.lib.dtts_acoustic_create(C.byref(desc), _ptr(self.arena), self.arena.numel(), tab,
+                                                        len(table), _stream(), C.byref(self.handle)), "acoustic_create")
+        self.ws = _Workspace(self.device)
+        self._t_raw = C.c_int32(0)
+        self.profile_infer = False
+
+    def ps_text_encode(self, txt_tokens, ph2word, word_len: int):
+        dev = self.device
+        txt = _dev_i64(txt_tokens, dev)
+        p2w = _dev_i64(ph2word, dev)
+        B, Tp = txt.shape
+        Tw = int(word_len)
+        if tuple(p2w.shape) != (B, Tp) or Tw <= 0:
+            raise ValueError("ph2word must be [B,Tp] like txt_tokens and word_len positive")
+        H = self.cfg.hidden
+        out = dict(ph_encoder_out=torch.empty(B, Tp, H, device=dev), word_encoder_out=torch.empty(B, Tw, H, device=dev),
+                   dur=torch.empty(B, Tw, device=dev), dur_int=torch.empty(B, Tw, dtype=torch.int64, device=dev),
+                   ilens=torch.empty(B, dtype=torch.int64, device=dev))
+        tin = binding.PsTextIn(_ptr(txt), _ptr(p2w), B, Tp, Tw)
+        tout = binding.PsTextOut(*[_ptr(out[k]) for k in ("ph_encoder_out", "word_encoder_out", "dur", "dur_int", "ilens")])
+        ws = self.ws.get(self.lib.dtts_ps_text_workspace_bytes(self.handle, B, Tp, Tw))
+        binding.check(self.lib.dtts_ps_text_encode(self.handle, C.byref(tin), C.byref(tout), _ptr(ws), ws.numel(),
+                                                   _stream()), "ps_text_encode")
+        out["ph2word"] = p2w
+        return out
+
+    def ps_attend(self, t, mel2word):
+        dev = self.device
+        B, Tp, H = t["ph_encoder_out"].shape
+        Tw = t["word_encoder_out"].shape[1]
+        T = mel2word.shape[1]
+        attn = torch.empty(B, T, Tp, device=dev)
+        decoder_inp = torch.empty(B, T, H, device=dev)
+        g_bct = torch.empty(B, H, T, device=dev)
+        x_mask = torch.empty(B, T, device=dev)
+        ws = self.ws.get(self.lib.dtts_ps_attend_workspace_bytes(self.handle, B, Tp, Tw, T))
+        binding.check(self.lib.dtts_ps_attend(self.handle, _ptr(t["ph_encoder_out"]), _ptr(t["word_encoder_out"]),
+                                              _ptr(t["ph2word"]), _ptr(mel2word), B, Tp, Tw, T, _ptr(attn),
+                                              _ptr(decoder_inp), _ptr(g_bct), _ptr(x_mask), _ptr(ws), ws.numel(),
+                                              _stream()), "ps_attend")
+        return attn, decoder_inp, g_bct, x_mask
+
+    @torch.no_grad()
+    def forward(self, txt_tokens, ph2word, word_len, mel2word=None, mel2ph=None, spk_embed=None, infer=True,
+                tgt_mels=None, forward_post_glow=False, two_stage=True, z_p=None):
+        """Same arguments as PortaSpeech.forward (portaspeech/model.py:202-203); ``z_p`` (extension) as in the dict engine."""
+        if not infer:
+            raise NotImplementedError("the B200 engine implements the inference path only (infer=True)")
+        if spk_embed is not None:
+            raise NotImplementedError("multi-speaker conditioning is off in ps_flow.yaml (use_spk_embed: false)")
+        prof = self.profile_infer
+        fm = self.cfg.frames_multiple
+        with torch.cuda.device(self.device):
+            ret = {}
+            with Timer("encoder", enable=prof):
+                t = self.ps_text_encode(txt_tokens, ph2word, int(word_len))
+                ret.update(ph_encoder_out=t["ph_encoder_out"], word_encoder_out=t["word_encoder_out"], dur=t["dur"])
+                if mel2word is None:
+                    mel2word = self.length_regulate(t["dur_int"], t["ilens"])
+                else:
+                    mel2word = _dev_i64(mel2word, self.device)
+                    if mel2word.shape[1] % fm:                    # model.py:250-252
+                        pad = fm - mel2word.shape[1] % fm
+                        mel2word = torch.cat([mel2word] + [mel2word[:, -1:]] * pad, -1).contiguous()
+                ret["mel2word"] = mel2word
+                attn, decoder_inp, g_bct, x_mask = self.ps_attend(t, mel2word)
+            ret["attn"], ret["x_mask"], ret["decoder_inp"] = attn, x_mask.unsqueeze(-1), decoder_inp
+            B, _, T = g_bct.shape
+            if z_p is None:
+                z_p = torch.distributions.Normal(0, 1).sample([B, self.cfg.latent, T // fm])
+            with Timer("fvae", enable=prof):
                 mel, z_out = self.decode_mel(g_bct, z_p)
             ret["mel_out_fvae"] = ret["mel_out"] = mel
             ret["z_p"] = z_out

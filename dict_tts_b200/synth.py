@@ -256,3 +256,106 @@ def make_mel(seed: int, B: int, T: int, n_mel: int = 80) -> torch.Tensor:
     """cfg-4 vocoder input: mel ~ U(mel_vmin, mel_vmax) = U(-6, 1.5) (tts/base.yaml:59-60), layout [B,T,80]."""
     g = torch.Generator().manual_seed(seed)
     return torch.rand(B, T, n_mel, generator=g) * 7.5 - 6.0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PortaSpeech (non-dict) sibling, SURVEY.md §8f-3
+# ---------------------------------------------------------------------------------------------------------------
+def make_ps_state_dict(seed: int = 2468, cfg=None) -> Dict[str, torch.Tensor]:
+    """Checkpoint-format ``state_dict['model']`` of PortaSpeech (modules/portaspeech/model.py:132-200) with
+    ``use_post_glow: False``; key names and shapes as tests/golden/ps_small.npz holds them (written from the real model)."""
+    from .config import PortaSpeechConfig
+    cfg = cfg or PortaSpeechConfig()
+    H, F, dk = cfg.hidden, cfg.ffn_filter, cfg.hidden // cfg.n_heads
+    it = _Init(seed)
+    e = it.normal("ph_encoder.emb.weight", (cfg.ph_size, H), H ** -0.5)
+    e[0].zero_()                                                   # padding_idx=0
+    for i in range(3):                                             # ConvReluNorm(kernel 5, 3 layers)
+        it.conv(f"ph_encoder.pre.conv_layers.{i}", H, H, 5)
+        it.ln(f"ph_encoder.pre.norm_layers.{i}", H)
+    it.conv("ph_encoder.pre.proj", H, H, 1, gain=0.5)              # zero-init upstream; non-trivial here
+    q = "ph_encoder.encoder"
+    for i in range(cfg.enc_layers):
+        it.normal(f"{q}.attn_layers.{i}.emb_rel_k", (1, 2 * cfg.rel_window + 1, dk), dk ** -0.5)
+        it.normal(f"{q}.attn_layers.{i}.emb_rel_v", (1, 2 * cfg.rel_window + 1, dk), dk ** -0.5)
+        for c in "qkvo":
+            it.conv(f"{q}.attn_layers.{i}.conv_{c}", H, H, 1)
+        it.ln(f"{q}.norm_layers_1.{i}", H)
+        it.conv(f"{q}.ffn_layers.{i}.conv_1", F, H, cfg.ffn_kernel)
+        it.conv(f"{q}.ffn_layers.{i}.conv_2", H, F, 1)
+        it.ln(f"{q}.norm_layers_2.{i}", H)
+    it.sd["word_encoder.pos_embed_alpha"] = torch.tensor([1.0])
+    it.sd["word_encoder.embed_positions._float_tensor"] = torch.zeros(1)
+    for i in range(cfg.word_enc_layers):
+        w = f"word_encoder.layers.{i}.op"
+        it.ln(w + ".layer_norm1", H, names=("weight", "bias"))
+        it.uniform(w + ".self_attn.in_proj_weight", (3 * H, H), 1 / math.sqrt(H))
+        it.uniform(w + ".self_attn.out_proj.weight", (H, H), 1 / math.sqrt(H))
+        it.ln(w + ".layer_norm2", H, names=("weight", "bias"))
+        it.conv(w + ".ffn.ffn_1", F, H, 1)
+        it.linear(w + ".ffn.ffn_2", H, F)
+    it.ln("word_encoder.layer_norm", H, names=("weight", "bias"))
+    it.linear("enc_pos_proj", H, 2 * H)
+    it.linear("dec_query_proj", H, 2 * H)
+    it.linear("dec_res_proj", H, 2 * H)
+    it.uniform("attn.in_proj_weight", (3 * H, H), 2 / math.sqrt(H))
+    it.uniform("attn.out_proj.weight", (H, H), 1 / math.sqrt(H))
+    for i in range(cfg.dur_layers):
+        it.conv(f"dur_predictor.conv.{i}.1", cfg.dur_chans, H if i == 0 else cfg.dur_chans, cfg.dur_kernel)
+        it.ln(f"dur_predictor.conv.{i}.3", cfg.dur_chans, names=("weight", "bias"))
+    it.linear("dur_predictor.linear.0", 1, cfg.dur_chans, gain=0.5)
+    it.sd["dur_predictor.linear.0.bias"] = torch.tensor([0.1])     # phoneme-level log-durations are SUMMED per word
+    it.conv("fvae.g_pre_net.0", H, H, 8)
+    for f in range(cfg.flow_blocks):
+        p = f"fvae.prior_flow.flows.{2 * f}"
+        it.conv(p + ".pre", cfg.flow_hidden, cfg.latent // 2, 1)
+        for j in range(cfg.flow_layers):
+            it.conv(p + f".enc.in_layers.{j}", 2 * cfg.flow_hidden, cfg.flow_hidden, cfg.flow_kernel, wn=True)
+        for j in range(cfg.flow_layers):
+            rs = 2 * cfg.flow_hidden if j < cfg.flow_layers - 1 else cfg.flow_hidden
+            it.conv(p + f".enc.res_skip_layers.{j}", rs, cfg.flow_hidden, 1, wn=True)
+        it.conv(p + ".enc.cond_layer", 2 * cfg.flow_hidden * cfg.flow_layers, H, 1, wn=True)
+        it.conv(p + ".post", cfg.latent // 2, cfg.flow_hidden, 1, gain=0.5)
+    it.conv("fvae.decoder.pre_net.0", H, cfg.latent, 4, transposed=True)
+    for j in range(cfg.dec_layers):
+        it.conv(f"fvae.decoder.wn.in_layers.{j}", 2 * H, H, cfg.dec_kernel, wn=True)
+    for j in range(cfg.dec_layers):
+        rs = 2 * H if j < cfg.dec_layers - 1 else H
+        it.conv(f"fvae.decoder.wn.res_skip_layers.{j}", rs, H, 1, wn=True)
+    it.conv("fvae.decoder.wn.cond_layer", 2 * H * cfg.dec_layers, H, 1, wn=True)
+    it.conv("fvae.decoder.out_proj", cfg.n_mel, H, 1)
+    return it.sd
+
+
+def make_ps_batch(seed: int = 31, B: int = 4, min_words: int = 3, max_words: int = 9, max_ph_per_word: int = 4,
+                  max_frames: int = 64, ph_size: int = 80, frames_multiple: int = 4) -> Dict[str, torch.Tensor]:
+    """One collated word-level PortaSpeech batch (FastSpeechWordDataset.collater, tasks/tts/dataset_utils.py): phoneme ids
+    ``txt_tokens [B,Tp]``, ``ph2word [B,Tp]`` (1-based, 0 = padding), ``word_lengths [B]``, supplied ``mel2word [B,T]``,
+    ``mel_lengths [B]`` and the prior sample ``z_p [B,16,T/4]``."""
+    g = torch.Generator().manual_seed(seed)
+    n_words = torch.randint(min_words, max_words + 1, (B,), generator=g)
+    n_words[0] = max_words
+    n_words, _ = torch.sort(n_words, descending=True)
+    per_word = [torch.randint(1, max_ph_per_word + 1, (int(n),), generator=g) for n in n_words]
+    Tp = max(int(p.sum()) for p in per_word)
+    txt = torch.zeros(B, Tp, dtype=torch.long)
+    ph2word = torch.zeros(B, Tp, dtype=torch.long)
+    mel2word = torch.zeros(B, max_frames, dtype=torch.long)
+    mel_lengths = torch.zeros(B, dtype=torch.long)
+    for b in range(B):
+        n = int(n_words[b])
+        seg = torch.repeat_interleave(torch.arange(1, n + 1), per_word[b])
+        ph2word[b, :seg.numel()] = seg
+        txt[b, :seg.numel()] = torch.randint(3, ph_size, (seg.numel(),), generator=g)
+        d = torch.randint(4, 15, (n,), generator=g).float()
+        target = max_frames if b == 0 else int(max_frames * (0.7 + 0.3 * float(torch.rand(1, generator=g))))
+        d = torch.clamp((d * target / d.sum()).floor(), min=1).long()
+        d[-1] += target - int(d.sum())
+        if d[-1] < 1:
+            d[-1] = 1
+        m = torch.repeat_interleave(torch.arange(1, n + 1), d)[:max_frames]
+        mel2word[b, :m.numel()] = m
+        mel_lengths[b] = m.numel()
+    assert max_frames % frames_multiple == 0
+    return dict(txt_tokens=txt, ph2word=ph2word, word_lengths=n_words, mel2word=mel2word, mel_lengths=mel_lengths,
+                z_p=draw_z(B, 16, max_frames // frames_multiple, seed + 7))

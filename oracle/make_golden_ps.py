@@ -100,6 +100,66 @@ def main():
     path = os.path.join(ROOT, "tests", "golden", "ps_small.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, round(os.path.getsize(path) / 1e6, 2), "MB")
+    full_size(PortaSpeech, TokenTextEncoder, set_hparams, ref_root)
+
+
+FULL_BATCH = dict(seed=31, B=4, min_words=3, max_words=9, max_ph_per_word=4, max_frames=64)
+FULL_WEIGHT_SEED = 2468
+FULL_PH_SIZE = 80
+
+
+def full_size(PortaSpeech, TokenTextEncoder, set_hparams, ref_root):
+    """tests/golden/ps_full.npz: the reference model at the shipped Biaobei size (hidden 192, 4 + 4 layers) holding the
+    seeded synthetic checkpoint of dict_tts_b200.synth.make_ps_state_dict -- outputs only, weights and inputs are
+    regenerated from their seeds at test time."""
+    from dict_tts_b200 import synth
+    from dict_tts_b200.config import PortaSpeechConfig
+    from dict_tts_b200.weights import fold_weight_norm
+    cwd = os.getcwd()
+    os.chdir(ref_root)
+    try:
+        set_hparams(config="egs/datasets/audio/biaobei/ps_flow.yaml", exp_name="", hparams_str="use_post_glow=False",
+                    print_hparams=False)
+        enc = TokenTextEncoder(None, vocab_list=[f"p{i}" for i in range(FULL_PH_SIZE - 3)], replace_oov="<UNK>")
+        assert len(enc) == FULL_PH_SIZE
+        model = PortaSpeech(enc).eval()
+    finally:
+        os.chdir(cwd)
+    cfg = PortaSpeechConfig(ph_size=FULL_PH_SIZE)
+    sd = synth.make_ps_state_dict(FULL_WEIGHT_SEED, cfg)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all(m.startswith("fvae.encoder.") for m in missing), (missing, unexpected)
+
+    def strip(m):
+        try:
+            torch.nn.utils.remove_weight_norm(m)
+        except ValueError:
+            pass
+    model.apply(strip)
+    W = fold_weight_norm(sd)
+    b = synth.make_ps_batch(ph_size=FULL_PH_SIZE, **FULL_BATCH)
+    out = {}
+    for tag, m2w in (("given", b["mel2word"]), ("pred", None)):
+        torch.manual_seed(9)
+        with torch.no_grad():
+            ref = model(b["txt_tokens"], b["ph2word"], b["word_lengths"].max(), mel2word=m2w, infer=True,
+                        forward_post_glow=False, two_stage=True)
+        T4 = ref["mel_out"].shape[1]
+        torch.manual_seed(9)
+        z = torch.distributions.Normal(0, 1).sample([b["txt_tokens"].shape[0], cfg.latent, T4 // 4])
+        with torch.no_grad():
+            mine = P.ps_forward(W, cfg, b["txt_tokens"], b["ph2word"], b["word_lengths"].max(), m2w, z)
+        for k in ("ph_encoder_out", "word_encoder_out", "dur", "attn", "decoder_inp", "z_p", "mel_out"):
+            err = (mine[k] - ref[k]).abs().max().item()
+            print(f"full {tag:6s} {k:18s} max-abs diff oracle vs reference {err:.2e}")
+            assert err < 2e-5, (tag, k, err)
+        out.update({f"{tag}_{k}": ref[k].numpy() for k in ("ph_encoder_out", "word_encoder_out", "dur", "attn",
+                                                            "decoder_inp", "z_p", "mel_out")})
+        out[f"{tag}_z_in"] = z.numpy()
+        out[f"{tag}_mel2word"] = mine["mel2word"].numpy()
+    path = os.path.join(ROOT, "tests", "golden", "ps_full.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, round(os.path.getsize(path) / 1e6, 2), "MB")
 
 
 if __name__ == "__main__":

@@ -13,3 +13,10 @@ VOCODER_SEED = 4321
 # north-star tolerances (BASELINE.json): mel <= 1e-3 max-abs, wav <= 1e-4 RMS, integers bit-exact
 TOL_MEL_MAXABS = 1e-3
 TOL_WAV_RMS = 1e-4
+
+# PortaSpeech sibling: tests/golden/ps_full.npz holds the reference outputs for these seeds
+# (oracle/make_golden_ps.py: FULL_BATCH / FULL_WEIGHT_SEED / FULL_PH_SIZE)
+PS_FULL_BATCH = dict(seed=31, B=4, min_words=3, max_words=9, max_ph_per_word=4, max_frames=64)
+PS_FULL_WEIGHT_SEED = 2468
+PS_FULL_PH_SIZE = 80
+PS_STAGES = ("ph_encoder_out", "word_encoder_out", "dur", "attn", "decoder_inp", "z_p", "mel_out")

@@ -59,3 +59,23 @@ def test_group_hidden_by_segs_is_a_segment_mean():
     assert g.shape == (1, 4, 4)
     assert torch.equal(g[0, 0], h[0, :2].mean(0)) and torch.equal(g[0, 1], h[0, 2]) and torch.equal(g[0, 2], h[0, 3:5].mean(0))
     assert (g[0, 3] == 0).all()                                                  # a word without phonemes
+
+
+@pytest.mark.parametrize("tag", ["given", "pred"])
+def test_ps_oracle_matches_full_size_reference_outputs(tag):
+    """tests/golden/ps_full.npz: outputs of the unmodified reference model at the shipped Biaobei size for the seeded
+    synthetic checkpoint (weights and inputs are regenerated from their seeds)."""
+    from dict_tts_b200 import synth
+    from dict_tts_b200.config import PortaSpeechConfig
+    from dict_tts_b200.weights import fold_weight_norm
+    from tests.cases import PS_FULL_BATCH, PS_FULL_PH_SIZE, PS_FULL_WEIGHT_SEED, PS_STAGES
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "ps_full.npz"))
+    cfg = PortaSpeechConfig(ph_size=PS_FULL_PH_SIZE)
+    W = fold_weight_norm(synth.make_ps_state_dict(PS_FULL_WEIGHT_SEED, cfg))
+    b = synth.make_ps_batch(ph_size=PS_FULL_PH_SIZE, **PS_FULL_BATCH)
+    with torch.no_grad():
+        out = P.ps_forward(W, cfg, b["txt_tokens"], b["ph2word"], b["word_lengths"].max(),
+                           b["mel2word"] if tag == "given" else None, torch.from_numpy(gold[f"{tag}_z_in"]))
+    assert np.array_equal(out["mel2word"].numpy(), gold[f"{tag}_mel2word"])
+    for k in PS_STAGES:
+        assert np.abs(out[k].numpy() - gold[f"{tag}_{k}"]).max() < 2e-5, k
