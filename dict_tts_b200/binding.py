@@ -101,6 +101,7 @@ SYMBOLS = {
     "dtts_pron_tokens": (C.c_int, [_P, _P, C.POINTER(DictBankStruct), _P, _I, _I, _I, _P, _P]),
     "dtts_vocoder_launch_count": (_U64, [_P]),
     "dtts_acoustic_launch_count": (_U64, [_P]),
+    "dtts_debug_set_tc_fuse": (C.c_int, [_I]),
     "dtts_debug_conv1d": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P]),
     "dtts_debug_tc_conv1d": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _F, _I, _P,
                                        _U64, _P]),

@@ -35,6 +35,21 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
   return r;
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream is still running -- after the predecessor's CTAs have all executed
+// griddep_launch() (or exited) -- and must execute griddep_wait() before it touches anything the predecessor wrote (or
+// writes anything the predecessor reads): the wait returns when the predecessor grid has completed and its memory
+// operations are visible.  Used to hide the prologue (barrier init, TMEM allocation, first weight stages) of the ~250
+// short launches of a step behind the tail of the kernel in front.  Kernels launched without the attribute are ordered
+// as usual; griddep_launch() in a kernel nobody depends on is a no-op.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Early trigger for short element-wise kernels whose whole grid is resident at once (a multi-wave grid would lose SM
+// capacity to the dependent's CTAs waiting in griddep_wait()).
+__device__ __forceinline__ void griddep_launch_if_resident() {
+  if ((unsigned long long)gridDim.x * gridDim.y * gridDim.z <= 1184ull) griddep_launch();
+}
+
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace dtts

@@ -1,0 +1,435 @@
+// Fused ResBlock convolution pair for the narrow HiFi-GAN stages (C = 32, the last stage): conv1 (dilated) -> leaky-ReLU ->
+// conv2 (dilation 1) -> + residual in ONE launch; the intermediate activation never leaves the SM.
+//
+//   t1[t]  = fp16(leaky(conv1(x)[t] + b1))           (zero outside [0, T): conv2's zero padding)
+//   out[t] = post * (conv2(t1)[t] + b2 + res[t])     (+ out[t] if accumulate), planes_out = fp16(leaky(out))
+//
+// Unfused (tc_conv.cu) the pair moves 16 B per element through HBM (2 in + 2 out | 2 in + 4 residual + 4 + 2 out) and its
+// second launch runs at the HBM roof; fused it moves 12 B and the 2 + 2 B of the intermediate become shared-memory
+// traffic.  Reference: ResBlock1.forward, modules/hifigan/hifigan.py:51-58.
+//
+// Both convolutions are the same implicit GEMM as tc_conv_kernel (M = 128 time rows per MMA, hi | lo weight planes
+// stacked along N = 64, K = 32 channels = 2 MMA K-steps per tap, fp32 accumulators in TMEM) and issue their MMAs in the
+// same order, and the intermediate is rounded exactly like the operand planes the unfused pair writes -- so the fused
+// result is BIT-IDENTICAL to the two launches it replaces (tests/test_gpu_tensorcore.py).  The output planes must be a
+// different buffer than the input planes (a tile stages its neighbours' rows as halo); the fp32 stream may be updated in
+// place (rows map one to one).
+//
+// Tile = 256 rows [t0, t0 + 256), t0 = q0 - h2 (h2 = (k-1)/2): conv1 produces all 256 rows into a shared-memory tile in
+// the UMMA K-major layout, conv2 reads its taps from that tile by moving the descriptor start address; its rows
+// [h2, 256 - h2) are complete, so tiles advance by S = 256 - 2*h2 rows (<= 4 % recompute).  All weights of both
+// convolutions (2 * k * 4 KB) stay resident in shared memory for the life of the persistent CTA.
+// Pipeline (one CTA per SM, 352 threads):
+//   warp 0    input tiles (tile + conv1 halo) by cp.async.bulk, 3 stages; the weights once
+//   warp 2    TMEM: 2 x conv1 accumulator sets + 2 x conv2 sets (4 x 128 columns); one thread issues
+//             M1(i) then M2(i-1): conv1 of the next tile fills the tensor pipe while the epilogue warps turn tile i's
+//             conv1 accumulators into the conv2 operand
+//   warps 3-10  E1(i): TMEM -> bias, leaky, fp16 -> shared tile (fence.proxy.async) ; E2(i-1): TMEM -> bias, residual,
+//             1/3 mean, fp32 stream + next layer's operand planes
+#include "tc_conv.cuh"
+#include "tc16.cuh"
+#include "tc_ptx.cuh"
+
+#include <mutex>
+
+namespace dtts {
+
+namespace {
+
+constexpr int kPairThreads = 96 + 8 * 32;
+constexpr int kPairRows = 256;                 // rows per tile (two 128-row MMA sub-tiles)
+constexpr int kPairC = 32, kPairNM = 64;       // channels; MMA N (hi | lo stacked)
+constexpr int kPairAStages = 3;
+constexpr int kTapBytes = kPairNM * kPairC * 2;   // one tap of one convolution: 4 KB
+// mbarriers
+constexpr int kPAFull = 0, kPAEmpty = kPAFull + kPairAStages, kPWFull = kPAEmpty + kPairAStages, kPAcc1Full = kPWFull + 1,
+              kPAcc1Empty = kPAcc1Full + 2, kPAcc2Full = kPAcc1Empty + 2, kPAcc2Empty = kPAcc2Full + 2,
+              kPTFull = kPAcc2Empty + 2, kPTEmpty = kPTFull + 2, kPNumBars = kPTEmpty + 2;
+constexpr int kPTmemOff = kPNumBars * 8;
+constexpr int kPBiasOff = (kPTmemOff + 4 + 63) / 64 * 64;                 // b1[32], b2[32]
+constexpr int kPPrefOff = kPBiasOff + 2 * kPairC * 4;                      // ragged tables
+constexpr int kPHeader = (kPPrefOff + (2 * TC_MAX_RAGGED_ITEMS + 8) * 4 + 127) / 128 * 128;
+
+struct PairTile { int b, q0, lim; };
+struct PairCursor { int b = 0; uint32_t base = 0; };
+// row tile rt (tiles of all items back to back) -> (item, first output row, row limit of the item)
+__device__ __forceinline__ PairTile pair_decode(const RbPairParams& p, const int* pref, const int* limv, uint32_t rt,
+                                                PairCursor& cur) {
+  PairTile c;
+  if (pref) {
+    int b = cur.b;
+    while (b + 1 < p.B && (uint32_t)pref[b + 1] <= rt) ++b;
+    cur.b = b;
+    c.b = b;
+    c.q0 = (int)(rt - (uint32_t)pref[b]) * p.S;
+    c.lim = limv[b];
+  } else {
+    const uint32_t nt = (uint32_t)p.ntiles;
+    while (rt >= cur.base + nt) { cur.base += nt; ++cur.b; }
+    c.b = cur.b;
+    c.q0 = (int)(rt - cur.base) * p.S;
+    c.lim = p.T;
+  }
+  return c;
+}
+
+__global__ void __launch_bounds__(kPairThreads, 1) rb_pair32_kernel(const RbPairParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = p.k, h2 = (p.k - 1) / 2, hd = h2 * p.dil;
+  const int RA = kPairRows + 2 * hd;           // staged input rows per tile
+  const int RT = kPairRows + 2 * h2;           // rows of the intermediate tile (h2 margin rows on both sides)
+  const uint32_t bar0 = smem_u32(smem);
+  auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + kPTmemOff);
+  float* bias_s = reinterpret_cast<float*>(smem + kPBiasOff);
+  int* pref_s = reinterpret_cast<int*>(smem + kPPrefOff);
+  int* lim_s = pref_s + TC_MAX_RAGGED_ITEMS + 1;
+  const uint32_t w_bytes = (uint32_t)k * kTapBytes;                  // one convolution's weights
+  const uint32_t a_stage_bytes = (uint32_t)(kPairC / 8) * RA * 16u;
+  const uint32_t t_buf_bytes = (uint32_t)(kPairC / 8) * RT * 16u;
+  const uint32_t w1_base = smem_u32(smem + kPHeader);
+  const uint32_t w2_base = w1_base + w_bytes;
+  const uint32_t a_base = w2_base + w_bytes;
+  const uint32_t t_base = a_base + kPairAStages * a_stage_bytes;
+
+  griddep_launch();                            // programmatic dependent launch, as tc_conv_kernel (common.cuh)
+  if (p.lens && warp == 3) {                   // per-item row limits and the exclusive prefix of their tile counts
+    griddep_wait();
+    int carry = 0;
+    for (int b0 = 0; b0 < p.B; b0 += 32) {
+      const int b = b0 + lane;
+      int lim = 0;
+      if (b < p.B) {
+        const long v = (long)__ldg(p.lens + b) * p.len_mul + p.len_add;
+        lim = v < 0 ? 0 : (v > p.T ? p.T : (int)v);
+        lim_s[b] = lim;
+      }
+      int nt = (lim + p.S - 1) / p.S, inc = nt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+      }
+      if (b < p.B) pref_s[b] = carry + inc - nt;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) pref_s[p.B] = carry;
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kPairAStages; ++s) { mbar_init(bar(kPAFull + s), 1); mbar_init(bar(kPAEmpty + s), 1); }
+    mbar_init(bar(kPWFull), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar(kPAcc1Full + s), 1); mbar_init(bar(kPAcc1Empty + s), 8);
+      mbar_init(bar(kPAcc2Full + s), 1); mbar_init(bar(kPAcc2Empty + s), 8);
+      mbar_init(bar(kPTFull + s), 8);    mbar_init(bar(kPTEmpty + s), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem + kPTmemOff)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x >= 96 && threadIdx.x < 96 + 2 * kPairC) {
+    const int i = threadIdx.x - 96;
+    bias_s[i] = i < kPairC ? __ldg(p.b1 + i) : __ldg(p.b2 + i - kPairC);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  // everything above overlaps the tail of the previous launch; the weights (constants) are fetched by warp 0's first
+  // bulk copies right below, activations / residuals / outputs only after the predecessor grid has completed
+  if (warp == 0 && elect_one()) {
+    mbar_arrive_expect_tx(bar(kPWFull), 2u * w_bytes);
+    bulk_g2s(w1_base, p.w1, w_bytes, bar(kPWFull));
+    bulk_g2s(w2_base, p.w2, w_bytes, bar(kPWFull));
+  }
+  griddep_wait();
+  const uint32_t tmem_base = *tmem_ptr_s;
+  const int* pref = p.lens ? pref_s : nullptr;
+  const int nrt = p.lens ? pref_s[p.B] : p.ntiles * p.B;
+  const int G = gridDim.x, cta = blockIdx.x;
+  const int n_it = nrt > cta ? (nrt - cta + G - 1) / G : 0;           // tiles of this CTA: cta, cta + G, ...
+
+  if (warp == 0) {
+    // ------------------------------------------------ producer: the input tiles (the weights were requested above)
+    __syncwarp();
+    int s = 0;
+    uint32_t ph = 1;
+    PairCursor cur;
+    for (int it = 0; it < n_it; ++it) {
+      const PairTile tc = pair_decode(p, pref, lim_s, (uint32_t)(cta + it * G), cur);
+      mbar_wait(bar(kPAEmpty + s), ph);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar(kPAFull + s), a_stage_bytes);
+        const size_t row0 = (size_t)(p.a_pad + tc.q0 - h2 - hd);
+        const tc16* src = p.a_hi + (size_t)tc.b * p.a_bs;
+        for (int sl = 0; sl < kPairC / 8; ++sl)
+          bulk_g2s(a_base + s * a_stage_bytes + sl * (uint32_t)RA * 16u, src + ((size_t)sl * p.a_rows + row0) * 8,
+                   (uint32_t)RA * 16u, bar(kPAFull + s));
+      }
+      __syncwarp();
+      if (++s == kPairAStages) { s = 0; ph ^= 1u; }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------ MMA issuer: M1(i), then M2(i - 1)
+    if (elect_one()) {
+      const uint32_t hiw = (128u >> 4) | (1u << 14);                  // SBO = 128 B, descriptor version 1
+      const uint32_t f16b = p.fmt ? 1u : 0u;
+      const uint32_t idesc = (1u << 4) | (f16b << 7) | (f16b << 10) | ((uint32_t)(kPairNM >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t a_low0 = ((a_base >> 4) & 0x3FFFu) | ((uint32_t)RA << 16);
+      const uint32_t t_low0 = ((t_base >> 4) & 0x3FFFu) | ((uint32_t)RT << 16);
+      const uint32_t w1_low0 = ((w1_base >> 4) & 0x3FFFu) | ((uint32_t)kPairNM << 16);
+      const uint32_t w2_low0 = ((w2_base >> 4) & 0x3FFFu) | ((uint32_t)kPairNM << 16);
+      const uint32_t a_kstep = 2u * (uint32_t)RA, t_kstep = 2u * (uint32_t)RT, b_kstep = 2u * kPairNM;
+      const uint32_t w_tap16 = kTapBytes >> 4, a_stage16 = a_stage_bytes >> 4, t_buf16 = t_buf_bytes >> 4;
+      mbar_wait(bar(kPWFull), 0);
+      int sa = 0;
+      uint32_t pa = 0;
+      for (int i = 0; i <= n_it; ++i) {
+        if (i < n_it) {                                               // conv1 of tile i
+          const int as = i & 1;
+          mbar_wait(bar(kPAFull + sa), pa);
+          mbar_wait(bar(kPAcc1Empty + as), ((i >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_base = tmem_base + (uint32_t)(as * 128);
+          uint32_t a_tap = a_low0 + (uint32_t)sa * a_stage16, b_lo = w1_low0;
+          for (int j = 0; j < k; ++j, a_tap += (uint32_t)p.dil, b_lo += w_tap16) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks)
+                umma_bf16(d_base + (uint32_t)(m * kPairNM), desc64(a_tap + (uint32_t)(m * 128) + ks * a_kstep, hiw),
+                          desc64(b_lo + ks * b_kstep, hiw), idesc, (j | ks) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(bar(kPAEmpty + sa));
+          umma_commit(bar(kPAcc1Full + as));
+          if (++sa == kPairAStages) { sa = 0; pa ^= 1u; }
+        }
+        if (i >= 1) {                                                 // conv2 of tile i - 1
+          const int t = i - 1, ts = t & 1;
+          mbar_wait(bar(kPTFull + ts), (t >> 1) & 1);
+          mbar_wait(bar(kPAcc2Empty + ts), ((t >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_base = tmem_base + 256u + (uint32_t)(ts * 128);
+          uint32_t a_tap = t_low0 + (uint32_t)ts * t_buf16, b_lo = w2_low0;
+          for (int j = 0; j < k; ++j, a_tap += 1u, b_lo += w_tap16) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks)
+                umma_bf16(d_base + (uint32_t)(m * kPairNM), desc64(a_tap + (uint32_t)(m * 128) + ks * t_kstep, hiw),
+                          desc64(b_lo + ks * b_kstep, hiw), idesc, (j | ks) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(bar(kPTEmpty + ts));
+          umma_commit(bar(kPAcc2Full + ts));
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 3) {
+    // ------------------------------------------------ epilogue: E1(i), then E2(i - 1); one 128-row sub-tile quadrant per warp
+    const int quad = warp & 3;                       // TMEM lanes [32*quad, 32*quad + 32)
+    const int m = (warp - 3) >> 2;                   // sub-tile
+    const int r = m * 128 + quad * 32 + lane;        // row inside the tile
+    const int fmt = p.fmt;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(m * kPairNM);
+    const float4* b1v = reinterpret_cast<const float4*>(bias_s);
+    const float4* b2v = reinterpret_cast<const float4*>(bias_s + kPairC);
+    PairCursor cur;
+    PairTile prev{0, 0, 0};
+    for (int i = 0; i <= n_it; ++i) {
+      // residual of tile i - 1 (consumed by E2 below): in flight while E1 runs
+      float4 rc[8];
+      bool ok2 = false;
+      int t2 = 0;
+      if (i >= 1) {
+        t2 = prev.q0 - h2 + r;
+        ok2 = r >= h2 && r < kPairRows - h2 && t2 < prev.lim;
+        if (p.res && ok2) {
+          const float4* rp = reinterpret_cast<const float4*>(p.res + (size_t)prev.b * p.o32_bs) + t2;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) rc[q] = rp[(size_t)q * p.T];
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) rc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      PairTile tc = prev;
+      if (i < n_it) {
+        tc = pair_decode(p, pref, lim_s, (uint32_t)(cta + i * G), cur);
+        const int as = i & 1;
+        mbar_wait(bar(kPAcc1Full + as), (i >> 1) & 1);
+        mbar_wait(bar(kPTEmpty + as), ((i >> 1) & 1) ^ 1);             // conv2 of tile i - 2 has read this buffer
+        tc_fence_after();
+        uint32_t a[32], l[32];
+        __syncwarp();
+        tmem_ld32_nowait(lane_addr + (uint32_t)(as * 128), a);
+        tmem_ld32_nowait(lane_addr + (uint32_t)(as * 128 + kPairC), l);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(kPAcc1Empty + as));             // accumulators are in registers
+        float* af = reinterpret_cast<float*>(a);
+        const float* lf = reinterpret_cast<const float*>(l);
+#pragma unroll
+        for (int q = 0; q < 32; q += 2) add2(af[q], af[q + 1], lf[q], lf[q + 1]);     // hi + lo weight plane
+        const int t = tc.q0 - h2 + r;
+        const bool inside = t >= 0 && t < p.T;                         // conv2 sees zeros outside the sequence
+        const uint32_t dst = t_base + (uint32_t)as * t_buf_bytes + (uint32_t)(h2 + r) * 16u;
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+          uint32_t hw[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float4 bq = b1v[2 * sl + (e >> 1)];
+            float v0 = af[8 * sl + 2 * e], v1 = af[8 * sl + 2 * e + 1];
+            fma2(v0, v1, 1.f, (e & 1) ? bq.z : bq.x, (e & 1) ? bq.w : bq.y);
+            float l0, l1;
+            leaky2(v0, v1, p.slope, l0, l1);
+            hw[e] = inside ? pack2(l0, l1, fmt) : 0u;
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)sl * (uint32_t)RT * 16u), "r"(hw[0]),
+                       "r"(hw[1]), "r"(hw[2]), "r"(hw[3])
+                       : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(kPTFull + as));
+      }
+      if (i >= 1) {
+        const int t = i - 1, ts = t & 1;
+        mbar_wait(bar(kPAcc2Full + ts), (t >> 1) & 1);
+        tc_fence_after();
+        uint32_t a[32], l[32];
+        __syncwarp();
+        tmem_ld32_nowait(lane_addr + 256u + (uint32_t)(ts * 128), a);
+        tmem_ld32_nowait(lane_addr + 256u + (uint32_t)(ts * 128 + kPairC), l);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(kPAcc2Empty + ts));
+        if (ok2) {
+          float* v = reinterpret_cast<float*>(a);
+          const float* lf = reinterpret_cast<const float*>(l);
+#pragma unroll
+          for (int q = 0; q < 32; q += 2) add2(v[q], v[q + 1], lf[q], lf[q + 1]);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 bq = b2v[q];
+            fma2(v[4 * q], v[4 * q + 1], 1.f, bq.x, bq.y);
+            fma2(v[4 * q + 2], v[4 * q + 3], 1.f, bq.z, bq.w);
+          }
+          if (p.res) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              add2(v[4 * q], v[4 * q + 1], rc[q].x, rc[q].y);
+              add2(v[4 * q + 2], v[4 * q + 3], rc[q].z, rc[q].w);
+            }
+          }
+          if (p.post != 1.f) {
+#pragma unroll
+            for (int q = 0; q < 32; q += 2) mul2(v[q], v[q + 1], p.post, p.post);
+          }
+          if (p.o32) {
+            float4* op = reinterpret_cast<float4*>(p.o32 + (size_t)prev.b * p.o32_bs) + t2;
+            if (p.accumulate) {
+              float4 old[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) old[q] = op[(size_t)q * p.T];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                v[4 * q] += old[q].x; v[4 * q + 1] += old[q].y; v[4 * q + 2] += old[q].z; v[4 * q + 3] += old[q].w;
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) op[(size_t)q * p.T] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+          if (p.o_hi) {
+            const size_t prow = (size_t)prev.b * p.op_bs + ((size_t)p.op_pad + t2) * 8;
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl) {
+              uint32_t hw[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float l0, l1;
+                leaky2(v[8 * sl + 2 * e], v[8 * sl + 2 * e + 1], p.slope, l0, l1);
+                hw[e] = pack2(l0, l1, fmt);
+              }
+              *reinterpret_cast<uint4*>(p.o_hi + prow + (size_t)sl * p.op_rows * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            }
+          }
+        }
+      }
+      prev = tc;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+size_t pair_smem_bytes(int k, int dil) {
+  const int h2 = (k - 1) / 2, hd = h2 * dil;
+  return (size_t)kPHeader + 2 * (size_t)k * kTapBytes + (size_t)kPairAStages * 4 * (kPairRows + 2 * hd) * 16 +
+         2 * (size_t)4 * (kPairRows + 2 * h2) * 16;
+}
+
+}  // namespace
+
+int rb_pair_supported(const TcConvW& c1, const TcConvW& c2, int dil, int a_planes) {
+  if (c1.C_in != kPairC || c1.C_out != kPairC || c2.C_in != kPairC || c2.C_out != kPairC) return 0;
+  if (c1.ktaps != c2.ktaps || !(c1.ktaps & 1) || c1.ktaps > 11 || dil < 1) return 0;
+  if (!c1.stack || !c2.stack || c1.planes != 1 || c2.planes != 1 || c1.N != kPairC || c2.N != kPairC || c1.KC != 32 ||
+      c2.KC != 32 || c1.il_u || c2.il_u || c1.pair || c2.pair || c1.lo8 || c2.lo8 || a_planes != 1 || c1.fmt != c2.fmt)
+    return 0;
+  const int h2 = (c1.ktaps - 1) / 2;
+  if (h2 + h2 * dil > TC_PADF) return 0;                              // the conv1 halo of the first tile starts inside the front padding
+  return pair_smem_bytes(c1.ktaps, dil) <= 227 * 1024;
+}
+
+cudaError_t launch_rb_pair(RbPairParams p, cudaStream_t stream) {
+  if (p.B <= 0 || p.T <= 0) return cudaSuccess;
+  if (p.lens && p.B > TC_MAX_RAGGED_ITEMS) return cudaErrorInvalidValue;
+  const int h2 = (p.k - 1) / 2, hd = h2 * p.dil;
+  p.S = kPairRows - 2 * h2;
+  p.ntiles = cdiv(p.T, p.S);
+  // the last tile stages rows up to q0 - h2 + 256 + hd of the input planes: they must exist (tc_rows keeps TC_PADB + slack)
+  if (p.a_pad - h2 - hd < 0 || p.a_pad + (p.ntiles - 1) * p.S - h2 + kPairRows + hd > p.a_rows) return cudaErrorInvalidValue;
+  const size_t smem = pair_smem_bytes(p.k, p.dil);
+  if (smem > (size_t)227 * 1024) return cudaErrorInvalidConfiguration;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(rb_pair32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (attr_err != cudaSuccess) return attr_err;
+  int dev = 0, sms = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return e;
+  const long tiles = (long)p.ntiles * p.B;
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  // the CTA owns all 512 TMEM columns: it must be alone on its SM (shared memory above half of the SM's guarantees it)
+  const size_t smem_launch = smem < 116 * 1024 ? 116 * 1024 : smem;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kPairThreads);
+  cfg.dynamicSmemBytes = smem_launch;
+  cfg.stream = stream;
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = tc_pdl_enabled();
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, rb_pair32_kernel, p);
+}
+
+}  // namespace dtts

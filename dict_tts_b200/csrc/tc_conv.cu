@@ -15,6 +15,7 @@
 // Without this the weight stream (C_out*C_in*K*2 B per 128-row tile) makes the big layers L2-bandwidth bound.
 #include "tc_conv.cuh"
 #include "tc16.cuh"
+#include "tc_ptx.cuh"
 
 #include <cstdlib>
 #include <cstring>
@@ -41,213 +42,6 @@ constexpr int kMaxItems = TC_MAX_RAGGED_ITEMS;
 constexpr int kSmemHeader = kPrefOff + (2 * kMaxItems + 8) * 4;   // barriers + tmem ptr, bias, ragged tables
 constexpr int kSmemLimit = 227 * 1024;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred P1;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, P1;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug traps (launch failure on the host) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) __trap();
-  }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// arrives on the barrier at the same shared-memory offset in every CTA of the cluster named by mask
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"(mask)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
-      : "memory");
-}
-// cta_group::2 forms: the MMA spans the CTA pair (M = 256: 128 rows from each CTA's A tile, each CTA holds half of B),
-// the commit multicasts to the barriers of both CTAs.
-__device__ __forceinline__ void umma_bf16_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                               uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// FP8 forms (kind::f8f6f4, K = 32 per instruction): the lo-plane correction of TcMode::lo8
-__device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                        uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_f8_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"((uint16_t)3)
-               : "memory");
-}
-// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
-  uint32_t raddr;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(bar), "r"(rank));
-  // relaxed: what the arrive publishes was produced by the async proxy (bulk copy completed on the local barrier) or is
-  // a completed tcgen05.ld (wait::ld) -- there is no generic-proxy write to release, and a release at cluster scope costs
-  // a full memory barrier per stage on the relay thread (measured: the pair was slower than two single CTAs with it).
-  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t bar, uint32_t rank) {
-  uint32_t raddr;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(bar), "r"(rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// Shared-memory matrix descriptors are no-swizzle, K-major: core matrix = 8 rows x 16 B stored contiguously (128 B);
-// LBO = byte distance between the two 16-byte K halves of one MMA, SBO = byte distance between 8-row groups
-// (bits 0-13 start >> 4, 16-29 LBO >> 4, 32-45 SBO >> 4, bit 46 = descriptor version 1 on sm_100).
-
-__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
-}
-// 32 contiguous bytes (one full L2 sector) from one thread; the address must be 32-byte aligned
-__device__ __forceinline__ void st_global_256(void* p, uint4 a, uint4 b) {
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z),
-               "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
-               : "memory");
-}
-// two 16-byte pieces that are adjacent in memory (lo at p, hi at p + 16 B); either may be disabled
-__device__ __forceinline__ void st_pair(void* p, uint4 a, uint4 b, bool oka, bool okb) {
-  if (oka && okb && (((uintptr_t)p) & 31) == 0) {
-    st_global_256(p, a, b);
-  } else {
-    if (oka) *reinterpret_cast<uint4*>(p) = a;
-    if (okb) *(reinterpret_cast<uint4*>(p) + 1) = b;
-  }
-}
-// Packed fp32 pairs (FADD2 / FMUL2 on sm_100): the epilogue is latency bound on the narrow layers (two warps per
-// scheduler), every instruction it does not issue counts.  Per lane these are the IEEE operations of the scalar forms.
-#ifdef DTTS_NO_PACKED_F32      // A/B switch for measurements: the scalar forms
-__device__ __forceinline__ void add2(float& x0, float& x1, float y0, float y1) { x0 += y0; x1 += y1; }
-__device__ __forceinline__ void mul2(float& x0, float& x1, float y0, float y1) { x0 *= y0; x1 *= y1; }
-#else
-__device__ __forceinline__ void add2(float& x0, float& x1, float y0, float y1) {
-  asm("{\n\t.reg .b64 a, b;\n\tmov.b64 a, {%0, %1};\n\tmov.b64 b, {%2, %3};\n\tadd.rn.f32x2 a, a, b;\n\tmov.b64 {%0, %1}, a;\n\t}"
-      : "+f"(x0), "+f"(x1)
-      : "f"(y0), "f"(y1));
-}
-__device__ __forceinline__ void mul2(float& x0, float& x1, float y0, float y1) {
-  asm("{\n\t.reg .b64 a, b;\n\tmov.b64 a, {%0, %1};\n\tmov.b64 b, {%2, %3};\n\tmul.rn.f32x2 a, a, b;\n\tmov.b64 {%0, %1}, a;\n\t}"
-      : "+f"(x0), "+f"(x1)
-      : "f"(y0), "f"(y1));
-}
-#endif
-// x = x * s + y on a pair (FFMA2); s = 1 gives exactly x + y
-__device__ __forceinline__ void fma2(float& x0, float& x1, float s, float y0, float y1) {
-#ifdef DTTS_NO_PACKED_F32
-  x0 = fmaf(x0, s, y0); x1 = fmaf(x1, s, y1);
-#else
-  asm("{\n\t.reg .b64 a, b, c;\n\tmov.b64 a, {%0, %1};\n\tmov.b64 b, {%2, %2};\n\tmov.b64 c, {%3, %4};\n\t"
-      "fma.rn.f32x2 a, a, b, c;\n\tmov.b64 {%0, %1}, a;\n\t}"
-      : "+f"(x0), "+f"(x1)
-      : "f"(s), "f"(y0), "f"(y1));
-#endif
-}
-// leaky(v) = max(v, slope * v) for 0 <= slope <= 1, two channels at a time
-__device__ __forceinline__ void leaky2(float a0, float a1, float slope, float& o0, float& o1) {
-  float m0 = a0, m1 = a1;
-  mul2(m0, m1, slope, slope);
-  o0 = fmaxf(a0, m0);
-  o1 = fmaxf(a1, m1);
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-
-// One lane of a converged warp (the compiler keeps warp-uniform operands in uniform registers inside the branch).
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred P1;\n\t"
-      "elect.sync _|P1, 0xffffffff;\n\t"
-      "selp.b32 %0, 1, 0, P1;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
-__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
-  uint64_t d;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
-  return d;
-}
 
 // Work decode.  A unit = csize consecutive row tiles (row tile rt = b * ntiles + time tile) of one output-channel
 // block; the CTA of cluster rank r takes row tile (unit % nu) * csize + r.  A cluster walks its units
@@ -444,7 +238,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
   const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
   int* pref_s = reinterpret_cast<int*>(smem + kPrefOff);              // ragged launches only
   int* lim_s = pref_s + kMaxItems + 1;
+  griddep_launch();                            // the next launch may set itself up while this one runs (common.cuh)
   if (p.lens && warp == 3) {
+    griddep_wait();                            // lens is an input of the pass: written by whatever ran before
     // per-item row limits and the exclusive prefix of their tile counts (B <= kMaxItems, checked by the launcher)
     int carry = 0;
     for (int b0 = 0; b0 < p.B; b0 += 32) {
@@ -492,6 +288,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
   __syncthreads();
   if (csize > 1) cluster_sync_all();           // every peer's barriers are initialised before any remote arrive / copy
   tc_fence_after();
+  // Programmatic dependent launch: everything up to here (barriers, TMEM, and -- for warp 1 -- the first weight stages,
+  // which are constants) overlaps the tail of the kernel in front; activations, residuals and outputs are only touched
+  // after the predecessor grid has completed.
+  if (warp != 1) griddep_wait();
   const uint32_t tmem_base = *tmem_ptr_s;
   Sched sc;
   sc.pref = p.lens ? pref_s : nullptr;
@@ -1059,6 +859,7 @@ __global__ void tc_to_planes_kernel(const float* __restrict__ x, long bs, long c
                                     int slabs_total, int slab0) {
   // full: the grid walks ALL rows of the slab and zero-fills the halo rows (one launch instead of convert + zero_halo)
   // slabs_total / slab0: the C source channels fill slabs [slab0, slab0 + C/8) of planes holding slabs_total slabs
+  griddep_launch_if_resident();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const int t = full ? r - pad : r;
   const int sl = blockIdx.y, b = blockIdx.z;
@@ -1140,40 +941,51 @@ __global__ void tc_planes_to_nct_kernel(const tc16* __restrict__ hi, const tc16*
   }
 }
 
-// conv_post + tanh on the CUDA cores (C_out = 1: 2*C*K flop per sample against C*4 bytes read -> HBM bound).
+// conv_post + tanh on the CUDA cores (C_out = 1: 2*C*K flop per sample against C*4 bytes read).  Block = 256 samples of
+// one item: the (256 + K - 1) x C input tile is staged once in shared memory with the leaky-ReLU applied (the first
+// version loaded and activated every element K times from L1 and was instruction bound: 0.40 ms at cfg 2), then every
+// thread runs its C*K FMAs from shared memory in the same order as before (bit-identical results).
 template <int KMAX>
 __global__ void __launch_bounds__(256) tc_conv_post_kernel(const float* __restrict__ st, const float* __restrict__ w,
                                                            const float* __restrict__ bias, float* __restrict__ wav,
                                                            int C, int T, int K, float slope,
                                                            const int* __restrict__ lens, int len_mul) {
   __shared__ float ws[64 * KMAX];
+  extern __shared__ float4 tile[];                   // [C/4][256 + K - 1]
   const int b = blockIdx.y;
+  const int t0 = blockIdx.x * 256;
   // ragged: samples past the item's valid length are zero (their inputs were never computed)
   const long valid = lens ? (long)__ldg(lens + b) * len_mul : (long)T;
-  if (lens && (long)blockIdx.x * blockDim.x >= valid) {          // whole block past the end
-    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t0 < T) wav[(size_t)b * T + t0] = 0.f;
+  const int t = t0 + threadIdx.x;
+  if (lens && (long)t0 >= valid) {                   // whole block past the end
+    if (t < T) wav[(size_t)b * T + t] = 0.f;
     return;
   }
   for (int i = threadIdx.x; i < C * K; i += blockDim.x) ws[i] = w[i];
+  const int pad = (K - 1) / 2, W = 256 + K - 1;
+  const float4* sp = reinterpret_cast<const float4*>(st) + (size_t)b * (C / 4) * T;
+  for (int i = threadIdx.x; i < (C / 4) * W; i += blockDim.x) {
+    const int s4 = i / W, x = i - s4 * W;
+    const int tt = t0 + x - pad;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tt >= 0 && tt < T) v = __ldg(sp + (size_t)s4 * T + tt);
+    tile[i] = make_float4(leaky(v.x, slope), leaky(v.y, slope), leaky(v.z, slope), leaky(v.w, slope));
+  }
   __syncthreads();
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
   if ((long)t >= valid) { wav[(size_t)b * T + t] = 0.f; return; }
-  const int pad = (K - 1) / 2;
   float acc = bias ? bias[0] : 0.f;
-  const float4* sp = reinterpret_cast<const float4*>(st) + (size_t)b * (C / 4) * T;
   for (int s4 = 0; s4 < C / 4; ++s4) {
-    const float4* row = sp + (size_t)s4 * T;
+    const float4* row = tile + s4 * W + threadIdx.x;
     const float* wc = ws + s4 * 4 * K;
     for (int j = 0; j < K; ++j) {
       const int tt = t + j - pad;
-      if (tt < 0 || tt >= T) continue;
-      const float4 x = __ldg(row + tt);
-      acc = fmaf(wc[j], leaky(x.x, slope), acc);
-      acc = fmaf(wc[K + j], leaky(x.y, slope), acc);
-      acc = fmaf(wc[2 * K + j], leaky(x.z, slope), acc);
-      acc = fmaf(wc[3 * K + j], leaky(x.w, slope), acc);
+      if (tt < 0 || tt >= T) continue;               // (zero rows: skipped like the original loop, same summation)
+      const float4 x = row[j];
+      acc = fmaf(wc[j], x.x, acc);
+      acc = fmaf(wc[K + j], x.y, acc);
+      acc = fmaf(wc[2 * K + j], x.z, acc);
+      acc = fmaf(wc[3 * K + j], x.w, acc);
     }
   }
   wav[(size_t)b * T + t] = tanhf(acc);
@@ -1271,6 +1083,18 @@ int tc_pair_enabled() {
   return v;
 }
 
+int tc_pdl_enabled() {
+  static const int v = env_int("DTTS_TC_PDL", 1) != 0;
+  return v;
+}
+
+static int g_fuse_override = -1;            // dtts_debug_set_tc_fuse (unit tests): -1 = follow DTTS_TC_FUSE
+void tc_fuse_override(int v) { g_fuse_override = v; }
+int tc_fuse_enabled() {
+  static const int v = env_int("DTTS_TC_FUSE", 1) != 0;
+  return g_fuse_override >= 0 ? g_fuse_override : v;
+}
+
 int tc_lo8_min_taps() {
   static const int v = env_int("DTTS_TC_LO8_MINTAPS", 7);
   return v;
@@ -1336,13 +1160,15 @@ cudaError_t launch_tc_conv(TcConvParams p, int B, cudaStream_t stream) {
   const long row_tiles = (long)p.ntiles * B;
   int csize = pick_cluster(p, row_tiles);
   cudaLaunchConfig_t cfg{};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // see griddep_wait() in the kernel
+  attr[1].val.programmaticStreamSerializationAllowed = tc_pdl_enabled();
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   int max_clusters = 0;
   if (p.pair) {
     if (g_max_pairs == 0) {
@@ -1488,7 +1314,8 @@ cudaError_t tc_conv_post(const float* st, const float* w, const float* bias, flo
                          float slope, cudaStream_t s, const int* lens, int len_mul) {
   if (C % 4 || C > 64 || K > 16) return cudaErrorInvalidValue;
   dim3 grid(cdiv(T, 256), B);
-  tc_conv_post_kernel<16><<<grid, 256, 0, s>>>(st, w, bias, wav, C, T, K, slope, lens, len_mul);
+  const size_t smem = (size_t)(C / 4) * (256 + K - 1) * sizeof(float4);
+  tc_conv_post_kernel<16><<<grid, 256, smem, s>>>(st, w, bias, wav, C, T, K, slope, lens, len_mul);
   return cudaGetLastError();
 }
 

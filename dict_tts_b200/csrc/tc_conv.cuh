@@ -161,6 +161,43 @@ struct TcConvParams {
   float acc_scale;
 };
 
+// Fused ResBlock pair (rb_pair.cu): conv1 (kernel k, dilation dil) -> leaky -> conv2 (kernel k, dilation 1) -> + residual
+// for C = 32 with hi | lo stacked weights and single-plane activations; bit-identical to the two tc_conv launches.
+struct RbPairParams {
+  const tc16* a_hi;              // input operand planes [B][4][a_rows][8] (already leaky-ReLU'd by their producer)
+  long a_bs;
+  int a_rows, a_pad;
+  const tc16* w1;                // stacked weight blobs [tap][4 slabs][64][8] of conv1 / conv2 (TcConvW::w)
+  const tc16* w2;
+  const float* b1;               // [32] fp32
+  const float* b2;
+  int k, dil;
+  int T;                         // sequence length (rows)
+  int fmt;
+  float slope;                   // leaky slope of the intermediate AND of the output planes
+  const float* res;              // fp32 stream residual (may be null) / output [B][8][T][4]
+  float* o32;
+  long o32_bs;
+  tc16* o_hi;                    // output operand planes (may be null)
+  long op_bs;
+  int op_rows, op_pad;
+  float post;
+  int accumulate;
+  const int* lens;               // ragged launch (optional), as TcConvParams
+  int len_mul, len_add;
+  int B;
+  int S, ntiles;                 // set by the launcher: tile stride 256 - (k - 1), tiles per item
+};
+// rows the fused kernel may stage past tc_rows(T): its last tile reads up to 256 + halo rows beyond the tile start
+constexpr int TC_FUSE_EXTRA_ROWS = 320;
+int rb_pair_supported(const TcConvW& c1, const TcConvW& c2, int dil, int a_planes);
+cudaError_t launch_rb_pair(RbPairParams p, cudaStream_t stream);
+// DTTS_TC_PDL=0 launches the tcgen05 kernels without programmatic dependent launch (default on)
+int tc_pdl_enabled();
+// DTTS_TC_FUSE=0 turns the fused ResBlock pairs off (default on)
+int tc_fuse_enabled();
+void tc_fuse_override(int v);      // -1: environment default; 0 / 1: force (unit tests compare the two builds of a pass)
+
 // output channels per N block of an interleaved transposed convolution: the largest multiple of 8 dividing C_out with
 // stride * cb <= 256 and stride * cb a multiple of 32 (0: unsupported)
 static inline int tc_il_block(int C_out, int stride) {

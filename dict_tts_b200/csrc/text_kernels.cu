@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(256) channel_ln_tiled_kernel(const float* __re
                                                                const float* __restrict__ out_mask, int C, int T,
                                                                PlaneOut po) {
   extern __shared__ float sm[];                      // xs[C][33], red[8][32], mean[32], rstd[32]
+  griddep_launch_if_resident();                      // the consumer (a tcgen05 launch) may set itself up meanwhile
   float* xs = sm;
   float* red = sm + (size_t)C * 33;
   float* mean_s = red + 256;
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(256) self_attn_small_kernel(const float* __res
                                                               const float* __restrict__ mask, float* __restrict__ out,
                                                               int C, int T, int heads, long bs, PlaneOut po) {
   extern __shared__ float sm[];                      // qs[dk][T], ks[dk][T], vs[dk][T], p[T][T+1]
+  griddep_launch_if_resident();
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int dk = C / heads;
   float* qs = sm;
@@ -745,6 +747,7 @@ cudaError_t wn_gate(const float* a, float* acts, int B, int H, int T, cudaStream
 
 // Same gate, written straight into tensor-core operand planes: thread = (8-channel slab, t).
 __global__ void wn_gate_planes_kernel(const float* __restrict__ a, int H, int T, PlaneOut po) {
+  griddep_launch_if_resident();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int sl = blockIdx.y, b = blockIdx.z;
   if (t >= T) return;

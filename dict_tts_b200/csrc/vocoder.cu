@@ -152,6 +152,9 @@ int tc_create(dtts_vocoder* h, cudaStream_t s) {
 }
 
 // per-call buffer geometry of the tensor-core path
+// rows per slab of the stage buffers: tc_rows + what the fused ResBlock kernel may stage past its last tile (zero rows)
+static inline int voc_rows(int T) { return tc_rows(T) + TC_FUSE_EXTRA_ROWS; }
+
 struct TcGeom {
   size_t plane_elems = 0;   // elements of ONE bf16 plane buffer (max over stages)
   size_t stream_elems = 0;  // floats of one fp32 stream buffer (max over stages)
@@ -162,11 +165,11 @@ TcGeom tc_geom(const dtts_vocoder* h, int B, int T) {
   TcGeom g;
   g.mel_plane_elems = (size_t)B * d.n_mel * tc_rows(T);
   int ch = d.init_ch, len = T;
-  g.plane_elems = (size_t)B * ch * tc_rows(len);
+  g.plane_elems = (size_t)B * ch * voc_rows(len);
   for (int i = 0; i < d.n_ups; ++i) {
     ch /= 2;
     len *= d.up_rates[i];
-    const size_t pe = (size_t)B * ch * tc_rows(len) + 64, se = (size_t)B * ch * len + 64;   // + slack for the odd-pad offset
+    const size_t pe = (size_t)B * ch * voc_rows(len) + 64, se = (size_t)B * ch * len + 64;   // + slack for the odd-pad offset
     if (pe > g.plane_elems) g.plane_elems = pe;
     if (se > g.stream_elems) g.stream_elems = se;
   }
@@ -240,7 +243,7 @@ int tc_vocode(dtts_vocoder* h, const float* mel, int B, int T, float* wav, void*
   L.counter = &h->launches;
 
   auto shape = [&](PlaneBuf& pb, int C, int Tn) {      // re-purpose a plane buffer: new geometry + zero halos
-    pb.C = C; pb.T = Tn; pb.rows = tc_rows(Tn);
+    pb.C = C; pb.T = Tn; pb.rows = (&pb == &PM) ? tc_rows(Tn) : voc_rows(Tn);
     L(tc_zero_halo(pb.hi, pb.lo, B * (C / 8), pb.rows, TC_PADF, Tn, s));
   };
   auto base = [&](const TcConvW& w, const PlaneBuf& in, int nq, int off0, int step) {
@@ -299,6 +302,32 @@ int tc_vocode(dtts_vocoder* h, const float* mel, int B, int T, float* wav, void*
         const int dil = d.rb_dilations[j][m];
         const TcConvW& c1 = h->tc_rb1[(i * d.n_rb + j) * 3 + m];
         const TcConvW& c2 = h->tc_rb2[(i * d.n_rb + j) * 3 + m];
+        if (tc_fuse_enabled() && rb_pair_supported(c1, c2, dil, h->mode.a_planes)) {
+          // one launch for the pair: the intermediate activation stays in shared memory (rb_pair.cu).  The tiles of a
+          // launch read their neighbours' rows as halo, so the output planes must not be the input planes: the three
+          // pairs of a ResBlock go PXU -> PY -> PT -> (PX)
+          const PlaneBuf& in = m == 0 ? PXUo : (m == 1 ? PY : PT);
+          const PlaneBuf& outp = m == 0 ? PY : PT;
+          RbPairParams fp{};
+          fp.a_hi = in.hi; fp.a_bs = in.bs(); fp.a_rows = in.rows; fp.a_pad = TC_PADF;
+          fp.w1 = c1.w; fp.w2 = c2.w; fp.b1 = c1.bias; fp.b2 = c2.bias;
+          fp.k = kr; fp.dil = dil; fp.T = len; fp.fmt = c1.fmt; fp.slope = 0.1f;
+          fp.res = m == 0 ? XU : Y32;
+          fp.o32_bs = (long)ch * len;
+          fp.post = 1.f; fp.accumulate = 0;
+          if (m < 2) {
+            fp.o32 = Y32;
+            fp.o_hi = outp.hi; fp.op_bs = outp.bs(); fp.op_rows = outp.rows; fp.op_pad = TC_PADF;
+          } else {
+            fp.o32 = ACC32;
+            fp.post = 1.f / (float)d.n_rb;
+            fp.accumulate = j > 0;
+            if (j == d.n_rb - 1 && !last_stage) { fp.o_hi = PX.hi; fp.op_bs = PX.bs(); fp.op_rows = PX.rows; fp.op_pad = TC_PADF; }
+          }
+          fp.lens = lens; fp.len_mul = ls.rpf[i + 1]; fp.len_add = ls.stage_add[i]; fp.B = B;
+          L(launch_rb_pair(fp, s));
+          continue;
+        }
         TcConvParams p1 = base(c1, m == 0 ? PXUo : PY, len, -(kr * dil - dil) / 2, dil);
         p1.T_out = len;
         p1.lens = lens; p1.len_mul = ls.rpf[i + 1]; p1.len_add = ls.stage_add[i];
@@ -524,6 +553,12 @@ static int vocode_impl(dtts_vocoder* h, const float* mel, const int32_t* lens, i
     L(cudaGetLastError());
   }
   if (L.err != cudaSuccess) return fail(DTTS_ERR_CUDA, std::string("dtts_vocode: ") + cudaGetErrorString(L.err));
+  return DTTS_OK;
+}
+
+extern "C" int dtts_debug_set_tc_fuse(int32_t mode) {
+  if (mode < -1 || mode > 1) return fail(DTTS_ERR_BAD_ARG, "dtts_debug_set_tc_fuse: mode must be -1, 0 or 1");
+  tc_fuse_override(mode);
   return DTTS_OK;
 }
 

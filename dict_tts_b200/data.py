@@ -262,3 +262,74 @@ class DictTTSTestSet:
             raise ValueError("deal must be 'batches' or 'reference'")
         for g in groups:
             yield collate([self[i] for i in g])
+
+
+class PortaSpeechTestSet:
+    """Word-level PortaSpeech items as FastSpeechWordDataset reads and collates them (tasks/tts/dataset_utils.py:112-223):
+    ``txt_tokens`` = phoneme ids (``item['phone']``), ``ph2word``, ``word_lengths`` (BOS / EOS included), ``mel2word`` for
+    the profiling mode.  Same sampler entry points as DictTTSTestSet."""
+
+    def __init__(self, hp: Dict, prefix: str = "test", data_dir: Optional[str] = None):
+        self.hp = hp
+        self.dir = data_dir or hp["binary_data_dir"]
+        self.prefix = prefix
+        sizes = np.load(os.path.join(self.dir, f"{prefix}_lengths.npy"))
+        n_test = hp.get("num_test_samples", 0)
+        if n_test and n_test > 0:
+            idxs = list(hp.get("test_ids", [])) + [i for i in range(n_test) if i < len(sizes)]
+        else:
+            idxs = list(range(len(sizes)))
+        if hp.get("min_frames", 0) > 0:
+            idxs = [i for i in idxs if sizes[i] >= hp["min_frames"]]
+        self.idxs = idxs
+        self.sizes = [int(sizes[i]) for i in idxs]
+        self.items = None
+        path = os.path.join(self.dir, "phone_set.json")
+        self.phone_list = None
+        if os.path.exists(path):
+            with open(path) as f:
+                self.phone_list = json.load(f)
+
+    def __len__(self):
+        return len(self.idxs)
+
+    def __getitem__(self, i: int) -> Dict:
+        if self.items is None:
+            self.items = IndexedDataset(os.path.join(self.dir, self.prefix))
+        item = self.items[self.idxs[i]]
+        hp = self.hp
+        fm = hp.get("frames_multiple", 1)
+        T = min(len(item["mel"]), hp.get("max_frames", 1 << 30)) // fm * fm
+        n_in = hp.get("max_input_tokens", 1 << 30)
+        s = dict(id=i, item_name=item["item_name"], text=item.get("txt"), words=item.get("words"),
+                 txt_tokens=torch.LongTensor(item["phone"][:n_in]), ph2word=torch.LongTensor(item["ph2word"][:n_in]),
+                 n_words=len(item["word_tokens"]), mel_length=T)
+        if item.get("mel2word") is not None:
+            s["mel2word"] = torch.LongTensor(item["mel2word"])[:T]
+        return s
+
+    @staticmethod
+    def collate(samples: List[Dict]) -> Dict:
+        b = dict(id=torch.LongTensor([s["id"] for s in samples]), item_name=[s["item_name"] for s in samples],
+                 text=[s["text"] for s in samples], words=[s["words"] for s in samples], nsamples=len(samples),
+                 txt_tokens=pad_1d([s["txt_tokens"] for s in samples]), ph2word=pad_1d([s["ph2word"] for s in samples]),
+                 txt_lengths=torch.LongTensor([s["txt_tokens"].numel() for s in samples]),
+                 word_lengths=torch.LongTensor([s["n_words"] for s in samples]),
+                 mel_lengths=torch.LongTensor([s["mel_length"] for s in samples]))
+        b["mel2word"] = pad_1d([s["mel2word"] for s in samples]) if "mel2word" in samples[0] else None
+        return b
+
+    def batches(self, max_sentences: int = 1, rank: int = 0, world: int = 1, sort_by_len: bool = True,
+                max_tokens: Optional[int] = None, deal: str = "batches") -> Iterator[Dict]:
+        if deal == "reference":
+            from .batching import build_batch_sampler
+            groups = build_batch_sampler(self.sizes, max_tokens=max_tokens, max_sentences=max_sentences,
+                                         by_size=max_tokens is not None, world=world, rank=rank,
+                                         max_frames=self.hp.get("max_frames"), drop_ragged=False)
+        else:
+            order = list(range(len(self)))
+            if sort_by_len:
+                order.sort(key=lambda i: -self.sizes[i])
+            groups = [order[i:i + max_sentences] for i in range(0, len(order), max_sentences)][rank::world]
+        for g in groups:
+            yield self.collate([self[i] for i in g])

@@ -8,7 +8,9 @@ import importlib
 
 from . import hparams as hp_mod
 
-_ALIASES = {"tasks.tts.dict_tts.DictTTSTask": "dict_tts_b200.task.B200DictTTSTask"}
+_ALIASES = {"tasks.tts.dict_tts.DictTTSTask": "dict_tts_b200.task.B200DictTTSTask",
+            "tasks.tts.ps_flow.PortaSpeechFlowTask": "dict_tts_b200.task.B200PortaSpeechTask",
+            "tasks.tts.ps_adv.PortaSpeechAdvTask": "dict_tts_b200.task.B200PortaSpeechTask"}
 
 
 def run_task():

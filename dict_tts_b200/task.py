@@ -21,10 +21,10 @@ import numpy as np
 import torch
 
 from . import hparams as hp_mod
-from .config import AcousticConfig, VocoderConfig
-from .data import DictTTSTestSet
-from .engine import DictTTSEngine, HifiGanEngine
-from .weights import load_acoustic_checkpoint, load_vocoder_checkpoint, pack_arena
+from .config import AcousticConfig, PortaSpeechConfig, VocoderConfig
+from .data import DictTTSTestSet, PortaSpeechTestSet
+from .engine import DictTTSEngine, HifiGanEngine, PortaSpeechEngine
+from .weights import fold_weight_norm, get_last_checkpoint, load_acoustic_checkpoint, load_vocoder_checkpoint, pack_arena
 
 
 def get_vocoder_cls(hp):
@@ -253,3 +253,116 @@ class B200DictTTSTask:
                 os.remove(part)
             self.write_meta(os.path.join(self.gen_dir, "meta.csv"), rows)
         return {}
+
+
+class B200PortaSpeechTask(B200DictTTSTask):
+    """The PortaSpeech (non-dict) sibling behind the same ``task_cls`` seam: what ``tasks/run.py --infer``
+    does for ``PortaSpeechFlowTask`` (tasks/tts/ps_flow.py:257-312, tasks/tts/tts_base.py:247-376) at ``dur_level: word`` /
+    ``use_post_glow: False``.  Selected with ``--hparams task_cls=dict_tts_b200.task.B200PortaSpeechTask``."""
+    META_FIELDS = ["item_name", "text", "ph_tokens", "wav_fn_pred", "wav_fn_gt"]
+
+    @classmethod
+    def start(cls):
+        hp = hp_mod.hparams
+        if not hp.get("infer", True):
+            raise SystemExit("dict_tts_b200 implements the --infer path only")
+        if hp.get("use_post_glow", False):
+            raise SystemExit("use_post_glow: true needs modules/glow, which the reference checkout does not ship; "
+                             "run with --hparams use_post_glow=False (mel_out = mel_out_fvae)")
+        if not torch.cuda.is_available():
+            raise RuntimeError("B200PortaSpeechTask needs a CUDA device (sm_100a); there is no CPU fallback")
+        rank = int(os.environ.get("RANK", "0"))
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        if world > 1:
+            import torch.distributed as dist
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        task = cls(hp, f"cuda:{local}", rank, world)
+        task.build_model()
+        task.test_start()
+        ds = PortaSpeechTestSet(hp, hp.get("test_set_name", "test"))
+        task.phone_list = ds.phone_list
+        outputs = []
+        bs = int(hp.get("b200_max_sentences", hp.get("max_valid_sentences", 1)) or 1)
+        for i, batch in enumerate(ds.batches(bs, rank, world, max_tokens=hp.get("b200_max_tokens"),
+                                             deal=str(hp.get("b200_deal", "batches")))):
+            outputs.extend(task.test_step(batch, i))
+        task.test_end(outputs)
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
+        return outputs
+
+    def build_model(self):
+        import torch.distributed as dist
+        hp, rank, world = self.hp, self.rank, self.world
+        meta, arena = [None], None
+        if rank == 0:
+            ckpt, _ = get_last_checkpoint(hp["work_dir"])
+            if ckpt is None:
+                raise FileNotFoundError(f'no model_ckpt_steps_*.ckpt under {hp["work_dir"]}')
+            self.global_step = int(ckpt.get("global_step", 0))
+            sd = {k: v for k, v in fold_weight_norm(ckpt["state_dict"]["model"]).items()
+                  if not k.startswith(("fvae.encoder.", "post_flow.", "g_proj.")) and v.is_floating_point()}
+            arena, table = pack_arena(sd)
+            meta = [(table, arena.numel(), self.global_step, int(sd["ph_encoder.emb.weight"].shape[0]))]
+        if world > 1:
+            dist.broadcast_object_list(meta, 0)
+        table, numel, self.global_step, ph_size = meta[0]
+        cfg = PortaSpeechConfig.from_hparams(hp, ph_size)
+        dev_arena = broadcast_arena(arena, numel, self.device, rank, world)
+        self.model = PortaSpeechEngine(None, cfg, self.device, arena=dev_arena, table=table,
+                                       precision=int(hp.get("b200_acoustic_precision", 1)))
+        self.model.profile_infer = bool(hp.get("profile_infer", False))
+        return self.model
+
+    def run_model(self, sample: Dict) -> Dict:
+        """The exact call of PortaSpeechFlowTask.test_step (ps_flow.py:274-284)."""
+        hp = self.hp
+        return self.model(sample["txt_tokens"], ph2word=sample["ph2word"], word_len=sample["word_lengths"].max(),
+                          infer=True, forward_post_glow=False, spk_embed=None, two_stage=hp.get("two_stage", True),
+                          mel2word=sample["mel2word"] if hp.get("profile_infer", False) else None)
+
+    @torch.no_grad()
+    def test_step(self, sample: Dict, batch_idx: int) -> List[Dict]:
+        out = self.run_model(sample)
+        sample["outputs"] = out["mel_out"]
+        sample["mel2word_pred"] = out["mel2word"]
+        return self.after_infer(sample)
+
+    def after_infer(self, sample: Dict) -> List[Dict]:
+        """TTSBaseTask.after_infer (tts_base.py:256-334) for a batch: vocode on the device, int16 wavs, one row per utterance."""
+        hp = self.hp
+        mel = sample["outputs"]
+        B = mel.shape[0]
+        hop = hp.get("hop_size", 256)
+        frames_dev = (sample["mel2word_pred"] > 0).sum(-1)
+        wav = self.vocoder.spec2wav_batch(mel, frames_dev if B > 1 else None)
+        pcm = self.model.pcm16(wav).cpu().numpy()
+        frames = frames_dev.cpu().numpy()
+        results = []
+        for b in range(B):
+            name, text = sample["item_name"][b], sample["text"][b]
+            uid = int(sample["id"][b])
+            base_fn = f'[{uid:06d}][{str(name).replace("%", "_")}][%s]'
+            if text is not None:
+                base_fn += str(text).replace(":", "$3A")[:80]
+            base_fn = base_fn.replace(" ", "_")
+            n = int(frames[b]) * hop if B > 1 else pcm.shape[1]
+            if not hp.get("profile_infer", False):
+                from scipy.io import wavfile
+                wavfile.write(os.path.join(self.gen_dir, "wavs", (base_fn % "P") + ".wav"),
+                              hp.get("audio_sample_rate", 22050), pcm[b, :n])
+            toks = [int(t) for t in sample["txt_tokens"][b].tolist() if t > 0]
+            if getattr(self, "phone_list", None):                 # TokenTextEncoder.decode: ids -> phone strings
+                reserved = ["<pad>", "<EOS>", "<UNK>"]
+                vocab = reserved + [p for p in self.phone_list if p not in reserved]
+                ph = " ".join(vocab[t] if t < len(vocab) else "<UNK>" for t in toks)
+            else:
+                ph = " ".join(str(t) for t in toks)
+            results.append(dict(id=uid, item_name=name, text=text, ph_tokens=ph, wav_fn_pred=base_fn % "P",
+                                wav_fn_gt=base_fn % "G"))
+            self.results_id += 1
+        return results

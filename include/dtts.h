@@ -283,6 +283,11 @@ int dtts_debug_tc_conv1d(const float* x_dev, const float* w_dev, const float* bi
                          float pre_slope, float post, float act_slope, int32_t precision, void* scratch_dev,
                          uint64_t scratch_bytes, void* stream);
 
+/* Unit-test hook: the fused ResBlock pair kernel (conv1 -> leaky -> conv2 -> + residual of the C = 32 stage in one
+ * launch, intermediate in shared memory) is bit-identical to the two launches it replaces; this switch lets a test run
+ * both.  mode 1 / 0: force on / off for the process, -1: the default (on; DTTS_TC_FUSE=0 turns it off). */
+int dtts_debug_set_tc_fuse(int32_t mode);
+
 #ifdef __cplusplus
 }
 #endif

@@ -104,3 +104,58 @@ def write(root: str, exp: str = "fake_dict_tts", n_items: int = 5, n_vocab: int 
     ib.finalize()
     np.save(os.path.join(bd, "test_lengths.npy"), np.array(lengths))
     return dict(root=root, exp=exp, work_dir=ck, vocoder_dir=vk, binary_dir=bd, n_items=n_items, hparams=hp)
+
+
+PS_HPARAMS = dict(
+    task_cls="tasks.tts.ps_flow.PortaSpeechFlowTask", vocoder="HifiGAN", hidden_size=192, num_heads=2, enc_layers=4,
+    word_enc_layers=4, enc_ffn_kernel_size=5, dur_predictor_layers=3, dur_predictor_kernel=5, frames_multiple=4,
+    latent_size=16, fvae_dec_n_layers=4, fvae_kernel_size=5, prior_glow_hidden=64, glow_kernel_size=3,
+    prior_glow_n_blocks=4, audio_num_mel_bins=80, hop_size=256, audio_sample_rate=22050, max_frames=1548, min_frames=0,
+    num_test_samples=0, test_ids=[], two_stage=True, profile_infer=False, out_wav_norm=False, gen_dir_name="",
+    max_valid_sentences=1, test_set_name="test", seed=1234, use_post_glow=False, dur_level="word", max_input_tokens=1550)
+
+
+def write_ps(root: str, exp: str = "fake_ps", n_items: int = 5, ph_size: int = 80, seed: int = 9) -> dict:
+    """A PortaSpeech (non-dict) experiment: checkpoints/<exp>/{model_ckpt_steps_*.ckpt, config.yaml}, the vocoder
+    checkpoint of write(), data/binary/fake_ps/{test.data, test.idx, test_lengths.npy, phone_set.json}."""
+    from dict_tts_b200.config import PortaSpeechConfig
+    g = torch.Generator().manual_seed(seed)
+    ck = os.path.join(root, "checkpoints", exp)
+    vk = os.path.join(root, "checkpoints", "fake_hifigan")
+    bd = os.path.join(root, "data", "binary", "fake_ps")
+    for d in (ck, vk, bd):
+        os.makedirs(d, exist_ok=True)
+    sd = synth.make_ps_state_dict(2468, PortaSpeechConfig(ph_size=ph_size))
+    for st in (500, 2500):
+        model = sd if st == 2500 else {k: torch.zeros_like(v) for k, v in sd.items()}
+        torch.save({"epoch": 1, "global_step": st, "optimizer_states": [], "state_dict": {"model": model}},
+                   os.path.join(ck, f"model_ckpt_steps_{st}.ckpt"), _use_new_zipfile_serialization=False)
+    hp = dict(PS_HPARAMS, binary_data_dir=bd, vocoder_ckpt=vk)
+    with open(os.path.join(ck, "config.yaml"), "w") as f:
+        yaml.safe_dump(hp, f)
+    if not os.path.exists(os.path.join(vk, "config.yaml")):
+        with open(os.path.join(vk, "config.yaml"), "w") as f:
+            yaml.safe_dump(VOC_CONFIG, f)
+        torch.save({"state_dict": {"model_gen": synth.make_vocoder_state_dict(4321), "model_disc": {}}},
+                   os.path.join(vk, "model_ckpt_steps_1200.ckpt"))
+    phones = [f"ph{i}" for i in range(ph_size - 3)]
+    with open(os.path.join(bd, "phone_set.json"), "w") as f:
+        json.dump(phones, f)
+    ib = IndexedDatasetBuilder(os.path.join(bd, "test"))
+    lengths = []
+    for it in range(n_items):
+        n_words = 3 + int(torch.randint(0, 5, (1,), generator=g))
+        per = torch.randint(1, 4, (n_words,), generator=g)
+        ph2word = torch.repeat_interleave(torch.arange(1, n_words + 1), per)
+        phone = torch.randint(3, ph_size, (int(per.sum()),), generator=g)
+        dur = torch.randint(3, 9, (n_words,), generator=g)
+        T = int(dur.sum()) // 4 * 4
+        mel2word = torch.repeat_interleave(torch.arange(1, n_words + 1), dur)[:T]
+        lengths.append(T)
+        words = [f"w{j}" for j in range(n_words)]
+        ib.add_item({"item_name": f"ps_{it:03d}", "txt": " ".join(words), "words": words, "ph_words": words,
+                     "word_tokens": list(range(3, 3 + n_words)), "phone": phone.tolist(), "ph2word": ph2word.tolist(),
+                     "mel": np.zeros((T, 80), np.float32), "mel2word": mel2word.numpy()})
+    ib.finalize()
+    np.save(os.path.join(bd, "test_lengths.npy"), np.array(lengths))
+    return dict(root=root, exp=exp, work_dir=ck, vocoder_dir=vk, binary_dir=bd, n_items=n_items, hparams=hp)

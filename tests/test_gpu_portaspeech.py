@@ -130,3 +130,47 @@ def test_ps_handle_refuses_dict_entry_points_and_vice_versa(full):
     assert lib.dtts_ps_text_encode(dict_eng.handle, C.byref(tin), C.byref(tout), C.c_void_p(1), 0, None) == binding.DTTS_ERR_BAD_ARG
     ps.close()
     dict_eng.close()
+
+
+def test_portaspeech_infer_entry_point(tmp_path):
+    """``python -m dict_tts_b200.run --exp_name <ps exp> --infer``: the reference's own task name in config.yaml maps onto
+    B200PortaSpeechTask; checkpoint discovery, word-level collate, predicted durations, vocoder, wavs and meta.csv."""
+    import csv
+    from scipy.io import wavfile
+    from dict_tts_b200 import run
+    from dict_tts_b200.data import PortaSpeechTestSet
+    from dict_tts_b200 import hparams as hp_mod
+    from tests import fake_exp
+    exp = fake_exp.write_ps(str(tmp_path), n_items=5)
+    cwd = os.getcwd()
+    os.chdir(exp["root"])
+    try:
+        torch.manual_seed(1234)
+        results = run.main(["--exp_name", exp["exp"], "--infer", "--hparams", "b200_max_sentences=3,gen_dir_name=ps"])
+    finally:
+        os.chdir(cwd)
+    gen = os.path.join(exp["work_dir"], "generated_2500_ps")
+    with open(os.path.join(gen, "meta.csv")) as f:
+        rows = list(csv.DictReader(f))
+    assert len(rows) == len(results) == 5
+    assert [r["item_name"] for r in rows] == [f"ps_{i:03d}" for i in range(5)]           # dataset order
+    for r in rows:
+        sr, pcm = wavfile.read(os.path.join(gen, "wavs", r["wav_fn_pred"] + ".wav"))
+        assert sr == 22050 and pcm.dtype == np.int16 and len(pcm) > 0 and len(pcm) % 256 == 0
+        assert all(tok.startswith("ph") for tok in r["ph_tokens"].split())
+    # one test_step of the task == the oracle forward on the same collated batch (predicted durations)
+    from dict_tts_b200.task import B200PortaSpeechTask
+    hp = hp_mod.set_hparams("", exp["exp"], "", root=exp["root"], global_hparams=False)
+    task = B200PortaSpeechTask(hp)
+    task.build_model()
+    ds = PortaSpeechTestSet(hp)
+    batch = next(ds.batches(3))
+    torch.manual_seed(5)
+    out = task.run_model(batch)
+    W = fold_weight_norm(synth.make_ps_state_dict(2468, PortaSpeechConfig(ph_size=80)))
+    with torch.no_grad():
+        want = P.ps_forward(W, task.model.cfg, batch["txt_tokens"], batch["ph2word"], batch["word_lengths"].max(), None,
+                            out["z_p"].cpu() * 0 + synth.draw_z(3, 16, out["mel_out"].shape[1] // 4, 1))
+    assert torch.equal(out["mel2word"].cpu(), want["mel2word"])
+    assert float((out["word_encoder_out"].cpu() - want["word_encoder_out"]).abs().max()) < TOL_STAGE
+    task.model.close()

@@ -341,3 +341,37 @@ def test_vocode_with_lengths_more_than_512_items(precision):
         assert torch.equal(part[b, :n], full[b, :n]), (precision, b)
         assert (part[b, n:] == 0).all(), (precision, b)
     eng.close()
+
+
+@pytest.mark.parametrize("precision", [3, 6, 4])
+def test_fused_resblock_pair_is_bit_identical_to_two_launches(precision):
+    """rb_pair32_kernel (conv1 -> leaky -> conv2 -> + residual of the C = 32 stage in ONE launch, the intermediate tile in
+    shared memory) issues the same MMAs in the same order and rounds the intermediate exactly like the operand planes of
+    the unfused pair: every sample must match bit for bit -- full length, ragged, several tiles per item, lengths 0 / 1."""
+    from dict_tts_b200.engine import HifiGanEngine
+    lib = binding.load()
+    eng = HifiGanEngine(synth.make_vocoder_state_dict(VOCODER_SEED), precision=precision)
+    try:
+        g = torch.Generator().manual_seed(3)
+        big = torch.randint(300, 401, (60,), generator=g).tolist()      # the bench shape: hundreds of tiles per item, all SMs busy
+        for seed, B, T, lens in ((5, 2, 24, None), (6, 3, 72, [72, 1, 40]), (7, 1, 130, None), (8, 4, 9, [9, 0, 5, 2]),
+                                 (9, 60, 400, big), (10, 7, 400, None)):
+            mel = synth.make_mel(seed, B, T)
+            ln = None if lens is None else torch.tensor(lens)
+            assert lib.dtts_debug_set_tc_fuse(0) == 0
+            eng(synth.make_mel(99, B, T))                     # different data in the buffers first
+            two = eng(mel, ln).clone()
+            launches0 = eng.launches
+            eng(mel, ln)
+            n_two = eng.launches - launches0
+            assert lib.dtts_debug_set_tc_fuse(1) == 0
+            launches0 = eng.launches
+            one = eng(mel, ln)
+            n_one = eng.launches - launches0
+            # nine pairs of the last stage became nine launches (single-plane fp16 weights, precision 4, are not stacked
+            # along N and keep the two-launch form)
+            assert n_two - n_one == (9 if precision in (3, 6) else 0), (n_two, n_one)
+            assert torch.equal(one, two), (precision, seed, float((one - two).abs().max()))
+    finally:
+        lib.dtts_debug_set_tc_fuse(-1)
+        eng.close()
