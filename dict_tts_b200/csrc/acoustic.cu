@@ -830,7 +830,9 @@ extern "C" int dtts_decode_mel(dtts_acoustic* h, const float* g, const float* z_
   if (tc) {
     Planes& P0 = tc->P[0];
     if (tc->shape(P0, 4 * H, T4)) {
-      for (int sp = 0; sp < 4; ++sp) tc->stage_sub(P0, g + sp, (long)H * T, T, 4, H, sp * H);
+      // x'[(sp, ci), q] = g[ci, 4q + sp]: one staging launch for the four phases
+      L(tc_to_planes_full(g, (long)H * T, T, 4, B, 4 * H, T4, 1.f, P0.hi, h->mode.a_planes == 2 ? P0.lo : nullptr, P0.rows,
+                          TC_PADF, h->mode.fmt, s, 0, 0, H));
       tc->conv_nct(P0, h->t_gpre, g_sqz, T4, 1, 1, TcRun::Epi());
     }
   } else {
@@ -842,7 +844,10 @@ extern "C" int dtts_decode_mel(dtts_acoustic* h, const float* g, const float* z_
   for (int f = d.flow_blocks - 1; f >= 0; --f) {
     const FlowW& F = h->flows[f];
     const int c_x0 = F.odd ? half : 0, c_x1 = F.odd ? 0 : half;
-    {
+    if (FH % 8 == 0 && half % 8 == 0) {      // 8 <-> 64 channels: one thread per position (pointwise_small_kernel)
+      L(pointwise_small(z_p + (size_t)c_x0 * T4, (long)d.latent * T4, F.pre.w, F.pre.bias, half, FH, B, T4, 1.f, nullptr,
+                        0, fh, (long)FH * T4, s));
+    } else {
       ConvParams p = conv_params(z_p + (size_t)c_x0 * T4, T4, F.pre, 0, FH, fh, T4, 1, 1, 0);
       p.x_bs = (long)d.latent * T4;
       L(launch_conv1d_f32(p, B, s));
@@ -851,11 +856,16 @@ extern "C" int dtts_decode_mel(dtts_acoustic* h, const float* g, const float* z_
     {
       // x1 = x1 - m   (mean_only, logs = 0)
       float* x1 = z_p + (size_t)c_x1 * T4;
-      ConvParams p = conv_params(fskip, T4, F.post, 0, half, x1, T4, 1, 1, 0);
-      p.o_bs = (long)d.latent * T4;
-      p.alpha = -1.f;
-      p.res = x1; p.r_bs = (long)d.latent * T4; p.r_cs = T4; p.r_ts = 1;
-      L(launch_conv1d_f32(p, B, s));
+      if (FH % 8 == 0 && half % 8 == 0) {
+        L(pointwise_small(fskip, (long)FH * T4, F.post.w, F.post.bias, FH, half, B, T4, -1.f, x1, (long)d.latent * T4, x1,
+                          (long)d.latent * T4, s));
+      } else {
+        ConvParams p = conv_params(fskip, T4, F.post, 0, half, x1, T4, 1, 1, 0);
+        p.o_bs = (long)d.latent * T4;
+        p.alpha = -1.f;
+        p.res = x1; p.r_bs = (long)d.latent * T4; p.r_cs = T4; p.r_ts = 1;
+        L(launch_conv1d_f32(p, B, s));
+      }
     }
   }
   // decoder (fvae_semantics.py:53-58)

@@ -113,5 +113,9 @@ cudaError_t nonpad_mask(const int64_t* idx, float* mask, size_t n, cudaStream_t 
 // acts[b,c,t] = tanh(a[b,c,t]) * sigmoid(a[b,c+H,t]),  a [B,2H,T]
 cudaError_t wn_gate(const float* a, float* acts, int B, int H, int T, cudaStream_t s);
 cudaError_t copy_f32(const float* in, float* out, size_t n, cudaStream_t s);
+// out[b,co,t] = alpha * (sum_ci w[ci][co] * x[b,ci,t] + bias[co]) + res[b,co,t]; x / out / res [.,C,T] with batch strides;
+// w packed [C_in][C_out] (ConvW of a 1x1 convolution), C_out % 8 == 0
+cudaError_t pointwise_small(const float* x, long x_bs, const float* w, const float* bias, int C_in, int C_out, int B, int T,
+                            float alpha, const float* res, long r_bs, float* out, long o_bs, cudaStream_t s);
 
 }  // namespace dtts

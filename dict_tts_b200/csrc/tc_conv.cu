@@ -856,7 +856,9 @@ __global__ void tc_pack_weights_lo8_kernel(const float* __restrict__ w, uint8_t*
 
 __global__ void tc_to_planes_kernel(const float* __restrict__ x, long bs, long cs, long ts, int C, int T, float slope,
                                     tc16* __restrict__ hi, tc16* __restrict__ lo, int rows, int pad, int fmt, int full,
-                                    int slabs_total, int slab0) {
+                                    int slabs_total, int slab0, int s2d_H) {
+  // s2d_H > 0: space-to-depth source -- destination channel ch reads x[(ch % s2d_H) * cs + t * ts + ch / s2d_H]
+  // (the stride-4 g_pre_net as a stride-1 convolution over 4 * H channels, acoustic.cu)
   // full: the grid walks ALL rows of the slab and zero-fills the halo rows (one launch instead of convert + zero_halo)
   // slabs_total / slab0: the C source channels fill slabs [slab0, slab0 + C/8) of planes holding slabs_total slabs
   griddep_launch_if_resident();
@@ -887,8 +889,11 @@ __global__ void tc_to_planes_kernel(const float* __restrict__ x, long bs, long c
   } else {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float a0 = leaky(x[(size_t)b * bs + (size_t)(sl * 8 + 2 * e) * cs + (size_t)t * ts], slope);
-      const float a1 = leaky(x[(size_t)b * bs + (size_t)(sl * 8 + 2 * e + 1) * cs + (size_t)t * ts], slope);
+      const int c0 = sl * 8 + 2 * e, c1 = c0 + 1;
+      const size_t o0 = s2d_H ? (size_t)(c0 % s2d_H) * cs + c0 / s2d_H : (size_t)c0 * cs;
+      const size_t o1 = s2d_H ? (size_t)(c1 % s2d_H) * cs + c1 / s2d_H : (size_t)c1 * cs;
+      const float a0 = leaky(x[(size_t)b * bs + o0 + (size_t)t * ts], slope);
+      const float a1 = leaky(x[(size_t)b * bs + o1 + (size_t)t * ts], slope);
       split2(a0, a1, fmt, hw[e], lw[e]);
     }
   }
@@ -1235,7 +1240,7 @@ cudaError_t tc_to_planes(const float* x, long bs, long cs, long ts, int B, int C
                          tc16* hi, tc16* lo, int rows, int pad, int fmt, cudaStream_t s) {
   if (C % 8) return cudaErrorInvalidValue;
   dim3 grid(cdiv(T, 128), C / 8, B);
-  tc_to_planes_kernel<<<grid, 128, 0, s>>>(x, bs, cs, ts, C, T, slope, hi, lo, rows, pad, fmt, 0, C / 8, 0);
+  tc_to_planes_kernel<<<grid, 128, 0, s>>>(x, bs, cs, ts, C, T, slope, hi, lo, rows, pad, fmt, 0, C / 8, 0, 0);
   return cudaGetLastError();
 }
 
@@ -1278,11 +1283,12 @@ cudaError_t tc_pack_weights_lo8(const float* w_ref, uint8_t* out, int C_out, int
 }
 
 cudaError_t tc_to_planes_full(const float* x, long bs, long cs, long ts, int B, int C, int T, float slope, tc16* hi,
-                              tc16* lo, int rows, int pad, int fmt, cudaStream_t s, int C_total, int c_off) {
+                              tc16* lo, int rows, int pad, int fmt, cudaStream_t s, int C_total, int c_off, int s2d_H) {
   if (C_total <= 0) C_total = C;
-  if (C % 8 || C_total % 8 || c_off % 8 || c_off + C > C_total) return cudaErrorInvalidValue;
+  if (C % 8 || C_total % 8 || c_off % 8 || c_off + C > C_total || (s2d_H && (cs == 1 || C % s2d_H))) return cudaErrorInvalidValue;
   dim3 grid(cdiv(rows, 128), C / 8, B);
-  tc_to_planes_kernel<<<grid, 128, 0, s>>>(x, bs, cs, ts, C, T, slope, hi, lo, rows, pad, fmt, 1, C_total / 8, c_off / 8);
+  tc_to_planes_kernel<<<grid, 128, 0, s>>>(x, bs, cs, ts, C, T, slope, hi, lo, rows, pad, fmt, 1, C_total / 8, c_off / 8,
+                                           s2d_H);
   return cudaGetLastError();
 }
 

@@ -229,8 +229,10 @@ cudaError_t tc_pack_weights_lo8(const float* w_ref, uint8_t* out, int C_out, int
                                 int pair, cudaStream_t s);
 // same, and zero-fills every row outside [pad, pad+T) (one launch for a freshly re-shaped scratch buffer)
 // C_total / c_off: the C source channels become channels [c_off, c_off + C) of planes that hold C_total channels
+// s2d_H > 0: space-to-depth source, plane channel ch = x channel ch % s2d_H at time t * ts + ch / s2d_H
 cudaError_t tc_to_planes_full(const float* x, long bs, long cs, long ts, int B, int C, int T, float slope, tc16* hi,
-                              tc16* lo, int rows, int pad, int fmt, cudaStream_t s, int C_total = 0, int c_off = 0);
+                              tc16* lo, int rows, int pad, int fmt, cudaStream_t s, int C_total = 0, int c_off = 0,
+                              int s2d_H = 0);
 // zero the halo rows [0,pad) and [pad+T, rows) of every slab of a plane pair
 cudaError_t tc_zero_halo(tc16* hi, tc16* lo, int n_slabs_total, int rows, int pad, int T,
                          cudaStream_t s);

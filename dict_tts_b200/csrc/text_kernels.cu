@@ -327,10 +327,16 @@ cudaError_t self_attention(const float* q, const float* k, const float* v, const
 
 // ------------------------------------------------------------------------------------------------------------
 // S2PA, folded form: logits[l] = keys[b,t,l,:] . qk[b,t,:]  (qk = W_k^T (W_q x) * D^-1/2), masked softmax over the
-// gloss tokens of this character, ctx = sum_l w[l] * values[b,t,l,:].  HBM-bound: every key/value row is read
-// exactly once with 128-bit streaming loads; rows with key_map == 0 (logit forced to -1e9 -> weight exactly 0
-// unless the whole row is masked) are not read at all.
-__global__ void __launch_bounds__(256) s2pa_stream_kernel(const float* __restrict__ keys,
+// gloss tokens of this character, ctx = sum_l w[l] * values[b,t,l,:].  HBM-bound, and ONE pass over the gloss rows:
+// every warp keeps a running (max, sum, weighted row sum) over the rows it owns (online softmax) and the eight partial
+// results are merged at the end, so a key row is used for its logit and -- when `values` is the same tensor, as in the
+// binarized data -- for the weighted sum from the same registers: 3 072 B per valid gloss token instead of 6 144 B.
+// Rows with key_map == 0 (logit forced to -1e9 -> weight exactly 0 unless the whole row is masked) are not read at all;
+// 128-bit streaming loads, two rows in flight per warp.  The attention weights themselves are the exact softmax of the
+// stored logits.  (The two-pass predecessor of this kernel read every row twice and idled at the softmax barrier in
+// between: 79 us alone, 122 us inside the step at cfg 2.)
+template <bool ALIASED>
+__global__ void __launch_bounds__(256, 2) s2pa_stream_kernel(const float* __restrict__ keys,
                                                            const float* __restrict__ values,
                                                            const float* __restrict__ key_map,
                                                            const float* __restrict__ qk, int Tw, int Lk, int D,
@@ -340,128 +346,140 @@ __global__ void __launch_bounds__(256) s2pa_stream_kernel(const float* __restric
                                                            const int32_t* __restrict__ row_len) {
   // row_off != null: keys / values are a dictionary BANK [rows][D]; character (b,t) owns rows
   // [row_off[bt], row_off[bt] + row_len[bt]) of it and every further gloss position is an all-zero row (never read).
-  // (A persistent variant -- one wave of CTAs pulling characters from an atomic counter -- was measured slower: wrapping
-  // the body in a loop took the kernel from 56 to 114 registers, i.e. from 4 to 2 resident CTAs per SM: 140 us instead of 80 us at cfg 2.)
   extern __shared__ float sm[];
-  float* s_q = sm;            // [D]
-  float* s_w = sm + D;        // [Lk]
-  __shared__ float s_red[8];
-  __shared__ int s_any;
+  float* s_q = sm;                  // [D]
+  float* s_w = s_q + D;             // [Lk] logits, then weights
+  float* s_acc = s_w + ((Lk + 3) & ~3);   // [8][D] per-warp weighted row sums (16-byte aligned: float4 stores)
+  __shared__ float s_m[8], s_s[8];
+  constexpr int R = 6;              // float4 per lane and row: D <= 768 (checked by the launcher)
   const int bt = blockIdx.x;
   const int b = bt / Tw, t = bt - b * Tw;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_any = 0;
+  griddep_launch_if_resident();
   for (int d = tid; d < D; d += 256) s_q[d] = qk[((size_t)b * D + d) * Tw + t];
   __syncthreads();
   const float* km = key_map + (size_t)bt * Lk;
   const int nrow = row_off ? row_len[bt] : Lk;                 // rows that exist in memory
   const size_t row0 = row_off ? (size_t)(nrow > 0 ? row_off[bt] : 0) : (size_t)bt * Lk;
-  const float4* kp = reinterpret_cast<const float4*>(keys + row0 * D);
   const int D4 = D >> 2;
-  // pass 1: logits (one warp per gloss token)
-  for (int l = warp; l < Lk; l += 8) {
-    float logit = -1e9f;
-    if (km[l] != 0.f) {
-      float acc = 0.f;
-      // all loads of the row are issued before the first FMA (8 x 128 bit in flight per lane); same summation order as
-      // the plain loop, which remains for D > 1024
-      for (int i0 = lane; l < nrow && i0 < D4; i0 += 256) {
-        float4 kv[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int i = i0 + 32 * u;
-          if (i < D4) kv[u] = ld_stream_f4(kp + (size_t)l * D4 + i);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int i = i0 + 32 * u;
-          if (i < D4) {
-            const float4 qv = *reinterpret_cast<const float4*>(s_q + 4 * i);
-            acc = fmaf(kv[u].x, qv.x, acc); acc = fmaf(kv[u].y, qv.y, acc);
-            acc = fmaf(kv[u].z, qv.z, acc); acc = fmaf(kv[u].w, qv.w, acc);
-          }
-        }
-      }
-      acc = warp_sum(acc);
-      logit = acc;
-      if (lane == 0) s_any = 1;
-    }
-    if (lane == 0) s_w[l] = logit;
-  }
-  __syncthreads();
-  // softmax over Lk
-  float mx = -INFINITY;
-  for (int l = tid; l < Lk; l += 256) mx = fmaxf(mx, s_w[l]);
-  mx = warp_max(mx);
-  if (lane == 0) s_red[warp] = mx;
-  __syncthreads();
-  mx = s_red[0];
-#pragma unroll
-  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, s_red[i]);
-  __syncthreads();
-  float sum = 0.f;
-  for (int l = tid; l < Lk; l += 256) {
-    const float e = expf(s_w[l] - mx);
-    s_w[l] = e;
-    sum += e;
-  }
-  sum = warp_sum(sum);
-  if (lane == 0) s_red[warp] = sum;
-  __syncthreads();
-  sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) sum += s_red[i];
-  const float rs = 1.f / sum;
-  for (int l = tid; l < Lk; l += 256) {
-    const float w = s_w[l] * rs;
-    s_w[l] = w;
-    weights[(size_t)bt * Lk + l] = w;
-    align[((size_t)b * Lk + l) * Tw + t] = w;                 // [B,1,Lk,Tw]
-  }
-  __syncthreads();
-  // pass 2: ctx[d] = sum_l w[l] * values[l][d]; each thread owns float4 columns, rows with w == 0 are skipped.
-  // A fully masked row has uniform weights 1/Lk and all-zero-padded values: it still has to be read.
+  const float4* kp = reinterpret_cast<const float4*>(keys + row0 * D);
   const float4* vp = reinterpret_cast<const float4*>(values + row0 * D);
-  const bool all_masked = (s_any == 0);
+  float m = -INFINITY, ssum = 0.f;
+  float4 acc[R];
+#pragma unroll
+  for (int u = 0; u < R; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto load_row = [&](const float4* base, int l, float4 (&dst)[R]) {
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const int i = lane + 32 * u;
+      dst[u] = (l < nrow && i < D4) ? ld_stream_f4(base + (size_t)l * D4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto consume = [&](int l, const float4 (&kr)[R], const float4 (&vr)[R]) {
+    float dot = 0.f;
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const int i = lane + 32 * u;
+      if (i < D4) {                                               // q stays in shared memory: registers hold rows in flight
+        const float4 q4 = *reinterpret_cast<const float4*>(s_q + 4 * i);
+        dot = fmaf(kr[u].x, q4.x, dot); dot = fmaf(kr[u].y, q4.y, dot);
+        dot = fmaf(kr[u].z, q4.z, dot); dot = fmaf(kr[u].w, q4.w, dot);
+      }
+    }
+    dot = warp_sum(dot);
+    if (lane == 0) s_w[l] = dot;
+    const float mn = fmaxf(m, dot);
+    const float sc = expf(m - mn), pw = expf(dot - mn);          // first row: exp(-inf) = 0
+    ssum = fmaf(ssum, sc, pw);
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      acc[u].x = fmaf(pw, vr[u].x, acc[u].x * sc); acc[u].y = fmaf(pw, vr[u].y, acc[u].y * sc);
+      acc[u].z = fmaf(pw, vr[u].z, acc[u].z * sc); acc[u].w = fmaf(pw, vr[u].w, acc[u].w * sc);
+    }
+    m = mn;
+  };
+  // rows l = warp, warp + 8, ...; two unmasked rows of this warp are in flight at a time
+  int any = 0;
+  for (int l0 = warp; l0 < Lk; l0 += 16) {
+    const int l1 = l0 + 8;
+    const bool u0 = km[l0] != 0.f, u1 = l1 < Lk && km[l1] != 0.f;
+    float4 k0[R], k1[R];
+    if (u0) load_row(kp, l0, k0);
+    if (u1) load_row(kp, l1, k1);
+    if (ALIASED) {
+      if (u0) consume(l0, k0, k0); else if (lane == 0) s_w[l0] = -1e9f;
+      if (u1) consume(l1, k1, k1); else if (lane == 0 && l1 < Lk) s_w[l1] = -1e9f;
+    } else {
+      float4 v0[R];
+      if (u0) { load_row(vp, l0, v0); consume(l0, k0, v0); } else if (lane == 0) s_w[l0] = -1e9f;
+      if (u1) { load_row(vp, l1, v0); consume(l1, k1, v0); } else if (lane == 0 && l1 < Lk) s_w[l1] = -1e9f;
+    }
+    any |= (u0 || u1);
+  }
+  if (lane == 0) { s_m[warp] = m; s_s[warp] = ssum; }
+  __syncthreads();
+  // merge the eight partial softmaxes
+  float M = s_m[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) M = fmaxf(M, s_m[i]);
+  const bool all_masked = M == -INFINITY;                        // no unmasked gloss token at all
+  if (!all_masked) {
+    float S = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) S += s_s[i] * expf(s_m[i] - M);   // exp(-inf) = 0 for a warp without rows
+    const float rs = 1.f / S;
+    const float mine = any ? expf(m - M) : 0.f;
+    float* dst = s_acc + (size_t)warp * D;
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const int i = lane + 32 * u;
+      if (i < D4)
+        *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(acc[u].x * mine, acc[u].y * mine, acc[u].z * mine, acc[u].w * mine);
+    }
+    for (int l = tid; l < Lk; l += 256) {
+      const float w = expf(s_w[l] - M) * rs;                     // masked: exp(-1e9 - M) = 0
+      weights[(size_t)bt * Lk + l] = w;
+      align[((size_t)b * Lk + l) * Tw + t] = w;                  // [B,1,Lk,Tw]
+    }
+    __syncthreads();
+    for (int d = tid; d < D; d += 256) {
+      float v = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v += s_acc[(size_t)i * D + d];
+      ctx[((size_t)b * D + d) * Tw + t] = v * rs;
+    }
+    return;
+  }
+  // Fully masked character (padding): softmax of Lk equal logits = 1/Lk each, ctx = mean over ALL Lk positions of the
+  // value rows (zero rows where nothing exists) -- still read, like the reference does.
+  const float w = 1.f / (float)Lk;
+  for (int l = tid; l < Lk; l += 256) {
+    weights[(size_t)bt * Lk + l] = w;
+    align[((size_t)b * Lk + l) * Tw + t] = w;
+  }
   for (int i = tid; i < D4; i += 256) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    // four rows in flight per thread (the loads do not depend on the accumulator); rows are still added in order
-    for (int l0 = 0; l0 < nrow; l0 += 4) {
-      float w[4];
-      float4 vv[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int l = l0 + u;
-        w[u] = l < nrow ? s_w[l] : 0.f;
-        const bool use = l < nrow && (w[u] != 0.f || all_masked);
-        if (use) vv[u] = ld_stream_f4(vp + (size_t)l * D4 + i);
-        else w[u] = 0.f, vv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int l = l0 + u;
-        if (l < nrow && (w[u] != 0.f || all_masked)) {
-          acc.x = fmaf(w[u], vv[u].x, acc.x); acc.y = fmaf(w[u], vv[u].y, acc.y);
-          acc.z = fmaf(w[u], vv[u].z, acc.z); acc.w = fmaf(w[u], vv[u].w, acc.w);
-        }
-      }
+    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int l = 0; l < nrow; ++l) {
+      const float4 vv = ld_stream_f4(vp + (size_t)l * D4 + i);
+      a4.x = fmaf(w, vv.x, a4.x); a4.y = fmaf(w, vv.y, a4.y); a4.z = fmaf(w, vv.z, a4.z); a4.w = fmaf(w, vv.w, a4.w);
     }
     float* c = ctx + ((size_t)b * D + 4 * i) * Tw + t;
-    c[0] = acc.x; c[Tw] = acc.y; c[2 * (size_t)Tw] = acc.z; c[3 * (size_t)Tw] = acc.w;
+    c[0] = a4.x; c[Tw] = a4.y; c[2 * (size_t)Tw] = a4.z; c[3 * (size_t)Tw] = a4.w;
   }
 }
 
 cudaError_t s2pa_stream(const float* keys, const float* values, const float* key_map, const float* qk, int B, int Tw,
                         int Lk, int D, float* weights, float* align, float* ctx, cudaStream_t s,
                         const int64_t* row_off, const int32_t* row_len) {
-  if (D % 4) return cudaErrorInvalidValue;
-  const size_t smem = (size_t)(D + Lk) * sizeof(float);
+  if (D % 4 || D > 768) return cudaErrorInvalidValue;           // 6 x 128 bit per lane and row
+  const size_t smem = (size_t)(9 * D + ((Lk + 3) & ~3)) * sizeof(float);
+  const bool aliased = keys == values;
+  auto kern = aliased ? s2pa_stream_kernel<true> : s2pa_stream_kernel<false>;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(s2pa_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  s2pa_stream_kernel<<<B * Tw, 256, smem, s>>>(keys, values, key_map, qk, Tw, Lk, D, weights, align, ctx, row_off,
-                                               row_len);
+  kern<<<B * Tw, 256, smem, s>>>(keys, values, key_map, qk, Tw, Lk, D, weights, align, ctx, row_off, row_len);
   return cudaGetLastError();
 }
 
@@ -765,6 +783,58 @@ cudaError_t wn_gate_planes(const float* a, int B, int H, int T, const PlaneOut& 
   if (H % 8 || !po.hi) return cudaErrorInvalidValue;
   dim3 grid(cdiv(T, 128), H / 8, B);
   wn_gate_planes_kernel<<<grid, 128, 0, s>>>(a, H, T, po);
+  return cudaGetLastError();
+}
+
+// 1x1 convolution with a handful of channels on one side (the 8 <-> 64 channel pre / post projections of a coupling
+// layer, glow_modules.py:113-127): out[b,co,t] = alpha * (sum_ci w[ci][co] * x[b,ci,t] + bias[co]) + res[b,co,t].
+// One thread per (b, t) walks the output channels eight at a time; w is the packed [C_in][C_out] layout of ConvW.
+// (The generic register-tiled kernel spent 13 / 49 us on these 3-MFLOP layers.)
+__global__ void __launch_bounds__(128) pointwise_small_kernel(const float* __restrict__ x, long x_bs,
+                                                              const float* __restrict__ w,
+                                                              const float* __restrict__ bias, int C_in, int C_out,
+                                                              int T, float alpha, const float* __restrict__ res,
+                                                              long r_bs, float* __restrict__ out, long o_bs) {
+  griddep_launch_if_resident();
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const float* xb = x + (size_t)b * x_bs + t;
+  for (int c0 = 0; c0 < C_out; c0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int ci0 = 0; ci0 < C_in; ci0 += 8) {                    // eight independent loads in flight per thread: the
+      float xv[8];                                               // layer is pure load latency (6 000 positions in all)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) xv[u] = ci0 + u < C_in ? xb[(size_t)(ci0 + u) * T] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (ci0 + u < C_in) {
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + (size_t)(ci0 + u) * C_out + c0));
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + (size_t)(ci0 + u) * C_out + c0 + 4));
+          acc[0] = fmaf(w0.x, xv[u], acc[0]); acc[1] = fmaf(w0.y, xv[u], acc[1]); acc[2] = fmaf(w0.z, xv[u], acc[2]);
+          acc[3] = fmaf(w0.w, xv[u], acc[3]); acc[4] = fmaf(w1.x, xv[u], acc[4]); acc[5] = fmaf(w1.y, xv[u], acc[5]);
+          acc[6] = fmaf(w1.z, xv[u], acc[6]); acc[7] = fmaf(w1.w, xv[u], acc[7]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float v = acc[k];
+      if (bias) v += __ldg(bias + c0 + k);
+      v *= alpha;
+      const size_t o = (size_t)(c0 + k) * T + t;
+      if (res) v += res[(size_t)b * r_bs + o];
+      out[(size_t)b * o_bs + o] = v;
+    }
+  }
+}
+cudaError_t pointwise_small(const float* x, long x_bs, const float* w, const float* bias, int C_in, int C_out, int B, int T,
+                            float alpha, const float* res, long r_bs, float* out, long o_bs, cudaStream_t s) {
+  if (C_out % 8 || (((uintptr_t)w) & 15)) return cudaErrorInvalidValue;
+  dim3 grid(cdiv(T, 128), B);
+  pointwise_small_kernel<<<grid, 128, 0, s>>>(x, x_bs, w, bias, C_in, C_out, T, alpha, res, r_bs, out, o_bs);
   return cudaGetLastError();
 }
 

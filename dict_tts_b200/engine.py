@@ -411,23 +411,11 @@ class HifiGanEngine:
             host, table = pack_arena(fold_weight_norm(state_dict))
             arena = host.to(self.device)
         self.arena, self.table = arena, table
-        c = self.cfg
-        desc = binding.VocoderDesc()
-        desc.n_mel, desc.init_ch, desc.n_ups, desc.n_rb = c.n_mel, c.init_ch, len(c.up_rates), len(c.rb_kernels)
-        for i, (u, k) in enumerate(zip(c.up_rates, c.up_kernels)):
-            desc.up_rates[i], desc.up_kernels[i] = u, k
-        for j, (k, dl) in enumerate(zip(c.rb_kernels, c.rb_dilations)):
-            desc.rb_kernels[j] = k
+        for dl in self.cfg.rb_dilations:
             if len(dl) != 3:
                 raise ValueError("ResBlock1 needs 3 dilations per block")
-            for m in range(3):
-                desc.rb_dilations[j][m] = dl[m]
-        desc.precision = precision
-        tab, self._keep = binding.make_table(table)
-        self.handle = C.c_void_p()
-        with torch.cuda.device(self.device):
-            binding.check(self.lib.dtts_vocoder_create(C.byref(desc), _ptr(self.arena), self.arena.numel(), tab,
-                                                       len(table), _stream(), C.byref(self.handle)), "vocoder_create")
+        self.precision = int(precision)
+        self.handle, self._keep = self._create(self.precision)
         self.ws = _Workspace(self.device)
         self.profile_infer = False
 
@@ -435,6 +423,51 @@ class HifiGanEngine:
         if getattr(self, "handle", None):
             self.lib.dtts_vocoder_destroy(self.handle)
             self.handle = None
+
+    def _create(self, precision: int):
+        c = self.cfg
+        desc = binding.VocoderDesc()
+        desc.n_mel, desc.init_ch, desc.n_ups, desc.n_rb = c.n_mel, c.init_ch, len(c.up_rates), len(c.rb_kernels)
+        for i, (u, k) in enumerate(zip(c.up_rates, c.up_kernels)):
+            desc.up_rates[i], desc.up_kernels[i] = u, k
+        for j, (k, dl) in enumerate(zip(c.rb_kernels, c.rb_dilations)):
+            desc.rb_kernels[j] = k
+            for m in range(3):
+                desc.rb_dilations[j][m] = dl[m]
+        desc.precision = precision
+        tab, keep = binding.make_table(self.table)
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            binding.check(self.lib.dtts_vocoder_create(C.byref(desc), _ptr(self.arena), self.arena.numel(), tab,
+                                                       len(self.table), _stream(), C.byref(handle)), "vocoder_create")
+        return handle, keep
+
+    @torch.no_grad()
+    def self_check(self, tol: float = 1e-4, margin: float = 0.85, frames: int = 48, seed: int = 0,
+                   mel: Optional[torch.Tensor] = None) -> Dict:
+        """Guard for the reduced-precision tensor-core modes on THIS checkpoint: the waveform
+        tolerance is absolute (1e-4 RMS) and the fixtures behind the default mode are random-weight, so a trained
+        generator with a wider dynamic range could leave it -- fp16 operands saturate at 65504.  Runs a probe mel
+        (U(mel_vmin, mel_vmax) unless given) through the current mode and through the fp32-class mode (precision 1: bf16
+        hi/lo x hi/lo, 3 MMAs, bf16 range), both on the GPU, and if their RMS difference exceeds ``margin * tol`` switches
+        this engine to precision 1 for good.  Returns {'precision', 'rms', 'switched'}."""
+        from . import synth
+        if self.precision in (0, 1):
+            return dict(precision=self.precision, rms=0.0, switched=False)
+        probe = synth.make_mel(seed, 2, frames) if mel is None else mel
+        got = self.forward(probe)
+        ref_handle, ref_keep = self._create(1)
+        cur = (self.handle, self._keep, self.precision)
+        self.handle, self._keep, self.precision = ref_handle, ref_keep, 1
+        want = self.forward(probe)
+        rms = float((got - want).double().pow(2).mean().sqrt())
+        ok = bool(torch.isfinite(got).all()) and rms <= margin * tol
+        if ok:                                            # keep the fast mode, drop the probe handle
+            self.lib.dtts_vocoder_destroy(ref_handle)
+            self.handle, self._keep, self.precision = cur
+        else:                                             # stay on the fp32-class handle
+            self.lib.dtts_vocoder_destroy(cur[0])
+        return dict(precision=self.precision, rms=rms, switched=not ok)
 
     def __del__(self):
         try:

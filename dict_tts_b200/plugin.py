@@ -48,6 +48,14 @@ class B200HifiGAN:
             precision = int(hp.get("b200_vocoder_precision", 6))
         self.device = torch.device(device)
         self.engine = HifiGanEngine(state_dict, cfg, device, precision=precision)
+        # reduced-precision modes are checked against the fp32-class mode on this very checkpoint and fall back if the
+        # waveform tolerance is at risk (HifiGanEngine.self_check); b200_vocoder_selfcheck=False skips the probe
+        self.selfcheck = None
+        if hp.get("b200_vocoder_selfcheck", True):
+            self.selfcheck = self.engine.self_check()
+            if self.selfcheck["switched"]:
+                print("| B200 HifiGAN: precision %d left the 1e-4 RMS budget on this checkpoint (probe RMS %.2e); "
+                      "running the fp32-class mode (precision 1)" % (precision, self.selfcheck["rms"]))
 
     def spec2wav(self, mel, **kwargs):
         """mel: ndarray or tensor [T, n_mel] -> float32 ndarray [T*hop] (vocoders/hifigan.py:54-62)."""

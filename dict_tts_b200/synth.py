@@ -119,8 +119,13 @@ def make_acoustic_state_dict(seed: int = 1234, cfg: Optional[AcousticConfig] = N
     return it.sd
 
 
-def make_vocoder_state_dict(seed: int = 4321, cfg: Optional[VocoderConfig] = None) -> Dict[str, torch.Tensor]:
-    """Checkpoint-format ``model_gen`` of HifiGanGenerator (modules/hifigan/hifigan.py:101-124)."""
+def make_vocoder_state_dict(seed: int = 4321, cfg: Optional[VocoderConfig] = None,
+                            hot: float = 1.0) -> Dict[str, torch.Tensor]:
+    """Checkpoint-format ``model_gen`` of HifiGanGenerator (modules/hifigan/hifigan.py:101-124).
+
+    hot: "trained-like" dynamic range -- conv_pre is scaled by ``hot`` and conv_post by ``1 / hot``, so every activation
+    between them is ``hot`` times larger (the default init keeps them at O(1..10)) while the waveform stays in range.
+    hot ~ 1e2 puts stage-1 activations at 1e2..1e3; hot ~ 2e4 pushes them past the fp16 range (65504)."""
     cfg = cfg or VocoderConfig()
     it = _Init(seed)
     it.conv("conv_pre", cfg.init_ch, cfg.n_mel, 7, wn=True)
@@ -139,6 +144,10 @@ def make_vocoder_state_dict(seed: int = 4321, cfg: Optional[VocoderConfig] = Non
                 it.conv(f"{r}.convs1.{m}", ch, ch, k_r, wn=True, gain=1.2)
                 it.conv(f"{r}.convs2.{m}", ch, ch, k_r, wn=True, gain=1.2)
     it.conv("conv_post", 1, ch, 7, wn=True, gain=0.6)
+    if hot != 1.0:
+        it.sd["conv_pre.weight_g"] = it.sd["conv_pre.weight_g"] * hot
+        it.sd["conv_pre.bias"] = it.sd["conv_pre.bias"] * hot
+        it.sd["conv_post.weight_g"] = it.sd["conv_post.weight_g"] / hot
     return it.sd
 
 

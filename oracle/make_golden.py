@@ -34,6 +34,9 @@ ACOUSTIC_CASES = [
     ("ac_single", dict(seed=14, B=1, min_chars=12, max_chars=12, max_frames=120, Lk_cap=96), False),
 ]
 VOCODER_CASES = [("voc_small", dict(seed=21, B=2, T=24)), ("voc_single", dict(seed=22, B=1, T=57))]
+# "trained-like" dynamic range: the same generator with its internal activations scaled by `hot`
+# (synth.make_vocoder_state_dict): 1e2 -> stage-1 activations of 1e2..1e3; 2e4 -> past the fp16 range
+HOT_VOCODER_CASES = [("voc_hot", dict(seed=23, B=1, T=40), 100.0), ("voc_overflow", dict(seed=24, B=1, T=24), 20000.0)]
 
 
 def build_reference_models():
@@ -118,6 +121,20 @@ def main():
         e = maxabs(ref, mine)
         print(name, "wav err %.2e" % e, "rms %.3f max %.3f" % (float(ref.pow(2).mean().sqrt()), float(ref.abs().max())))
         assert e < 2e-5
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), wav=ref.numpy())
+    R = ref_loader.load()
+    for name, kw, hot in HOT_VOCODER_CASES:
+        sd_hot = synth.make_vocoder_state_dict(4321, hot=hot)
+        vh = R["hifigan_cls"](R["voc_cfg"]).eval()
+        vh.load_state_dict(sd_hot, strict=True)
+        vh.remove_weight_norm()
+        mel = synth.make_mel(kw["seed"], kw["B"], kw["T"])
+        with torch.no_grad():
+            ref = vh(mel.transpose(1, 2)).squeeze(1)
+            mine = O.hifigan_forward(fold_weight_norm(sd_hot), vcfg, mel)
+        e = maxabs(ref, mine)
+        print(name, "hot=%g wav err %.2e" % (hot, e), "rms %.3f max %.3f" % (float(ref.pow(2).mean().sqrt()), float(ref.abs().max())))
+        assert e < 5e-5                        # fp32 summation-order noise grows with the internal scale
         np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), wav=ref.numpy())
     # spec2wav semantics (vocoders/hifigan.py:54-62): one utterance [T,80] -> flat wav
     print("golden fixtures written to", GOLDEN)

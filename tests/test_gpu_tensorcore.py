@@ -375,3 +375,60 @@ def test_fused_resblock_pair_is_bit_identical_to_two_launches(precision):
     finally:
         lib.dtts_debug_set_tc_fuse(-1)
         eng.close()
+
+
+def test_default_vocoder_mode_over_ten_weight_seeds():
+    """The default mode (fp16 activations x fp16 hi/lo weights, FP8 lo plane in the wide layers) against the oracle for
+    TEN different generators: every one must hold the 1e-4 RMS waveform tolerance."""
+    from dict_tts_b200.config import VocoderConfig
+    from dict_tts_b200.engine import HifiGanEngine
+    worst = 0.0
+    for seed in range(100, 110):
+        sd = synth.make_vocoder_state_dict(seed)
+        mel = synth.make_mel(seed + 1, 1, 20)
+        with torch.no_grad():
+            want = O.hifigan_forward(fold_weight_norm(sd), VocoderConfig(), mel)
+        eng = HifiGanEngine(sd)
+        rms = float((eng(mel).cpu() - want).pow(2).mean().sqrt())
+        chk = eng.self_check()
+        eng.close()
+        print("generator seed %d: wav RMS error %.2e vs the oracle, self-check probe %.2e" % (seed, rms, chk["rms"]))
+        worst = max(worst, rms)
+        assert rms < TOL_WAV_RMS, (seed, rms)
+        assert chk["switched"] is False, (seed, chk)         # the probe agrees: inside the budget, the fast mode stays
+    print("worst wav RMS error over 10 generators: %.2e" % worst)
+
+
+def test_trained_like_dynamic_range_fixture(golden_dir):
+    """tests/golden/voc_hot.npz: the real HifiGanGenerator with its internal activations scaled x100 (stage-1 activations
+    of 1e2..1e3, as a trained generator has them; oracle/make_golden.py HOT_VOCODER_CASES).  fp16 rounding is relative, so
+    the default mode must still hold the tolerance and the self-check must keep it."""
+    from dict_tts_b200.engine import HifiGanEngine
+    gold = np.load(os.path.join(golden_dir, "voc_hot.npz"))["wav"]
+    for precision in (6, 3, 1):
+        eng = HifiGanEngine(synth.make_vocoder_state_dict(VOCODER_SEED, hot=100.0), precision=precision)
+        wav = eng(synth.make_mel(23, 1, 40)).cpu().numpy()
+        rms = float(np.sqrt(np.mean((wav - gold) ** 2)))
+        assert rms < TOL_WAV_RMS, (precision, rms)
+        chk = eng.self_check()
+        assert chk["switched"] is False and chk["precision"] == precision, chk
+        eng.close()
+
+
+def test_fp16_overflow_falls_back_to_the_fp32_class_mode(golden_dir):
+    """tests/golden/voc_overflow.npz: activations scaled x20000 leave the fp16 range (65504).  The default mode saturates
+    and misses the tolerance by orders of magnitude; HifiGanEngine.self_check (run by the B200HifiGAN plugin at load)
+    detects it on a probe mel and moves the engine to precision 1 (bf16 hi/lo x hi/lo), which holds the tolerance."""
+    from dict_tts_b200.engine import HifiGanEngine
+    gold = np.load(os.path.join(golden_dir, "voc_overflow.npz"))["wav"]
+    sd = synth.make_vocoder_state_dict(VOCODER_SEED, hot=20000.0)
+    mel = synth.make_mel(24, 1, 24)
+    eng = HifiGanEngine(sd)
+    bad = float(np.sqrt(np.mean((eng(mel).cpu().numpy() - gold) ** 2)))
+    assert not bad < TOL_WAV_RMS, bad                  # saturated (or non-finite): far outside
+    chk = eng.self_check()
+    assert chk["switched"] is True and chk["precision"] == 1 and eng.precision == 1, chk
+    rms = float(np.sqrt(np.mean((eng(mel).cpu().numpy() - gold) ** 2)))
+    assert rms < TOL_WAV_RMS, rms
+    assert eng.self_check()["switched"] is False
+    eng.close()

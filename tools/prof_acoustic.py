@@ -14,10 +14,14 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=2)
     ap.add_argument("--s2pa-route", type=int, default=0, help="1: K/V projection GEMM on tcgen05 (dtts.h s2pa_route)")
+    ap.add_argument("--alias", action="store_true", help="values IS keys (one tensor), as the binarized data has it")
     a = ap.parse_args()
     eng = DictTTSEngine(synth.make_acoustic_state_dict(1234), s2pa_route=a.s2pa_route)
-    b = synth.make_batch(seed=1234, B=60, min_chars=12, max_chars=20, max_frames=400, Lk_cap=96)
+    b = synth.make_batch(seed=1234, B=60, min_chars=12, max_chars=20, max_frames=400, Lk_cap=96, alias_values=a.alias)
     dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in b.items()}
+    if a.alias:
+        dev["values"] = dev["keys"]
+    print("valid gloss tokens:", int((b["key_map"] != 0).sum()), "of", b["key_map"].numel())
 
     def once():
         return eng.forward((dev["word_tokens"],), dev["pron_modified"],
