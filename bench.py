@@ -673,6 +673,77 @@ def main():
         except Exception as e:
             line.setdefault("configs", {})["cfg1"] = dict(unavailable=repr(e)[:300])
 
+    # ---- the PortaSpeech (non-dict) sibling on the same workload shape (B=60, ~50 phonemes, 400 frames) ----
+    if extras and not args.no_extra_configs:
+        try:
+            from dict_tts_b200.config import PortaSpeechConfig
+            from dict_tts_b200.engine import PortaSpeechEngine
+            pcfg = PortaSpeechConfig()
+            p_sd = synth.make_ps_state_dict(2468, pcfg)
+            peng = PortaSpeechEngine(p_sd, pcfg, dev, precision=args.acoustic_precision)
+            pb = synth.make_ps_batch(seed=77, B=60, min_words=12, max_words=20, max_ph_per_word=4, max_frames=400,
+                                     ph_size=pcfg.ph_size)
+            pd = {k: v.to(dev) for k, v in pb.items()}
+            pframes = int(pb["mel_lengths"].sum())
+            wl = int(pb["word_lengths"].max())
+
+            def ps_step():
+                out = peng.forward(pd["txt_tokens"], pd["ph2word"], wl, mel2word=pd["mel2word"], z_p=pd["z_p"])
+                return pipe.vocoder(out["mel_out"], (out["mel2word"] > 0).sum(-1))
+            for _ in range(3):
+                ps_step()
+            torch.cuda.synchronize()
+            nps = max(10, args.steps)
+            l0 = peng.launches
+            e0, e1, em = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            ac_ms = 0.0
+            e0.record(stream)
+            for _ in range(nps):
+                ps_step()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ps_ms = e0.elapsed_time(e1) / nps
+            e0.record(stream)
+            for _ in range(nps):
+                peng.forward(pd["txt_tokens"], pd["ph2word"], wl, mel2word=pd["mel2word"], z_p=pd["z_p"])
+            em.record(stream)
+            torch.cuda.synchronize()
+            ac_ms = e0.elapsed_time(em) / nps
+            ps_line = dict(workload="PortaSpeech (non-dict) sibling, SURVEY 8f-3: batch=60, 12-20 words (<= 4 phonemes each), "
+                                    "T=400 frames, supplied durations, text->mel (dtts_ps_text_encode / dtts_ps_attend / "
+                                    "dtts_decode_mel) -> HiFi-GAN",
+                           ms_per_step=ps_ms, value=pframes / (ps_ms / 1e3), unit="frames/s", acoustic_ms=ac_ms,
+                           phonemes=int((pb["txt_tokens"] > 0).sum()), frames=pframes,
+                           acoustic_launches=int(peng.launches - l0) // (2 * nps))
+            if not args.no_cpu_baseline:
+                from oracle import ps_oracle as PO
+                Wp = fold_weight_norm(p_sd)
+                Wv_cpu = fold_weight_norm(synth.make_vocoder_state_dict(4321))
+                from oracle import dtts_oracle as O
+                torch.set_num_threads(cores)
+                nu = 6
+
+                def ps_cpu():
+                    with torch.no_grad():
+                        for b in range(nu):
+                            n = int((pb["txt_tokens"][b] > 0).sum())
+                            T = int(pb["mel_lengths"][b])
+                            T4 = (T + 3) // 4
+                            r = PO.ps_forward(Wp, pcfg, pb["txt_tokens"][b:b + 1, :n], pb["ph2word"][b:b + 1, :n],
+                                              pb["word_lengths"][b], pb["mel2word"][b:b + 1, :T], pb["z_p"][b:b + 1, :, :T4])
+                            O.hifigan_forward(Wv_cpu, vcfg, r["mel_out"][:, :T])
+                ps_cpu()
+                t0 = time.perf_counter()
+                ps_cpu()
+                dt = time.perf_counter() - t0
+                fr = int(pb["mel_lengths"][:nu].sum())
+                ps_line["cpu_baseline"] = dict(value=fr / dt, unit="frames/s", cores=cores, kind="port", seconds=dt,
+                                               sample=f"first {nu} utterances ({fr} frames), one at a time, oracle port")
+            line.setdefault("configs", {})["portaspeech"] = ps_line
+            peng.close()
+        except Exception as e:
+            line.setdefault("configs", {})["portaspeech"] = dict(unavailable=repr(e)[:300])
+
     if not args.no_cpu_baseline and world == 1:
         refc = CpuReference()
         utts = [slice_utt(batch, b) for b in range(CPU_SAMPLE_UTTS)]

@@ -376,6 +376,392 @@ __global__ void __launch_bounds__(kPairThreads, 1) rb_pair32_kernel(const RbPair
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same fusion for C = 64 (the third HiFi-GAN stage), where the unfused pair is HBM bound too (16 B per element
+// against a tensor floor of half its time) but the weights of one convolution (k * 16 KB) no longer fit in shared memory
+// next to the tiles: they are STREAMED per tile through a ring of ~32 KB stages by warp 1, in exactly the order the MMA
+// thread consumes them -- conv1(0) | conv2(0) conv1(1) | conv2(1) conv1(2) | ... -- as tc_conv_kernel streams them per
+// tile today (all CTAs read the same blobs, they stay in L2).  K = 64 = two 32-channel chunks: conv1 waits for one
+// staged input chunk at a time, conv2 reads both chunks of the intermediate tile.  One accumulator set per
+// convolution (2 x 128 columns x 2 sub-tiles = all 512 TMEM columns) but TWO intermediate tiles, and the issue order
+//     M1(0) | M1(1) M2(0) | M1(2) M2(1) | ...        epilogue:  E1(0) | E1(1) E2(0) | E1(2) E2(1) | ...
+// so that E1(i+1) (conv1 accumulators -> operand tile) runs under M2(i) and E2(i) (stores) under M1(i+2): with the
+// first, simpler order M2(i) M1(i+1) every tile paid E1 on the critical path (k = 11: 11 us per tile for 7 us of MMAs).
+// Same MMA order (chunk, tap, sub-tile, K step) and same rounding as the two tc_conv launches: bit-identical.
+constexpr int kP64C = 64, kP64NM = 128, kP64KC = 32;
+constexpr int kP64TapBytes = kP64NM * kP64KC * 2;               // one (chunk, tap) blob: 8 KB
+constexpr int kP64AStages = 3, kP64WStages = 3, kP64MaxTG = 4;   // (p.a_stages <= kP64AStages input stages are used)
+constexpr int kQAFull = 0, kQAEmpty = kQAFull + kP64AStages, kQWFull = kQAEmpty + kP64AStages,
+              kQWEmpty = kQWFull + kP64WStages, kQAcc1Full = kQWEmpty + kP64WStages, kQAcc1Empty = kQAcc1Full + 1,
+              kQAcc2Full = kQAcc1Empty + 1, kQAcc2Empty = kQAcc2Full + 1, kQTFull = kQAcc2Empty + 1,
+              kQTEmpty = kQTFull + 2, kQNumBars = kQTEmpty + 2;
+constexpr int kQTmemOff = kQNumBars * 8;
+constexpr int kQBiasOff = (kQTmemOff + 4 + 63) / 64 * 64;                 // b1[64], b2[64]
+constexpr int kQPrefOff = kQBiasOff + 2 * kP64C * 4;
+constexpr int kQHeader = (kQPrefOff + (2 * TC_MAX_RAGGED_ITEMS + 8) * 4 + 127) / 128 * 128;
+
+__global__ void __launch_bounds__(kPairThreads, 1) rb_pair64_kernel(const RbPairParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = p.k, h2 = (p.k - 1) / 2, hd = h2 * p.dil;
+  const int RA = kPairRows + 2 * hd, RT = kPairRows + 2 * h2;
+  const int TG = p.TG;                                                 // taps per weight stage
+  const uint32_t bar0 = smem_u32(smem);
+  auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + kQTmemOff);
+  float* bias_s = reinterpret_cast<float*>(smem + kQBiasOff);
+  int* pref_s = reinterpret_cast<int*>(smem + kQPrefOff);
+  int* lim_s = pref_s + TC_MAX_RAGGED_ITEMS + 1;
+  const uint32_t w_stage_bytes = (uint32_t)TG * kP64TapBytes;
+  const uint32_t a_stage_bytes = 4u * (uint32_t)RA * 16u;             // one 32-channel chunk of a tile
+  const uint32_t t_chunk_bytes = 4u * (uint32_t)RT * 16u;
+  const int a_stages = p.a_stages;
+  const uint32_t t_buf_bytes = 2u * t_chunk_bytes;                    // one intermediate tile: both chunks
+  const uint32_t w_base = smem_u32(smem + kQHeader);
+  const uint32_t a_base = w_base + kP64WStages * w_stage_bytes;
+  const uint32_t t_base = a_base + (uint32_t)a_stages * a_stage_bytes;
+
+  griddep_launch();
+  if (p.lens && warp == 3) {
+    griddep_wait();
+    int carry = 0;
+    for (int b0 = 0; b0 < p.B; b0 += 32) {
+      const int b = b0 + lane;
+      int lim = 0;
+      if (b < p.B) {
+        const long v = (long)__ldg(p.lens + b) * p.len_mul + p.len_add;
+        lim = v < 0 ? 0 : (v > p.T ? p.T : (int)v);
+        lim_s[b] = lim;
+      }
+      int nt = (lim + p.S - 1) / p.S, inc = nt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+      }
+      if (b < p.B) pref_s[b] = carry + inc - nt;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) pref_s[p.B] = carry;
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kP64AStages; ++s) { mbar_init(bar(kQAFull + s), 1); mbar_init(bar(kQAEmpty + s), 1); }
+    for (int s = 0; s < kP64WStages; ++s) { mbar_init(bar(kQWFull + s), 1); mbar_init(bar(kQWEmpty + s), 1); }
+    mbar_init(bar(kQAcc1Full), 1); mbar_init(bar(kQAcc1Empty), 8);
+    mbar_init(bar(kQAcc2Full), 1); mbar_init(bar(kQAcc2Empty), 8);
+    for (int s = 0; s < 2; ++s) { mbar_init(bar(kQTFull + s), 8); mbar_init(bar(kQTEmpty + s), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem + kQTmemOff)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x >= 96 && threadIdx.x < 96 + 2 * kP64C) {
+    const int i = threadIdx.x - 96;
+    bias_s[i] = i < kP64C ? __ldg(p.b1 + i) : __ldg(p.b2 + i - kP64C);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp != 1) griddep_wait();                 // warp 1 only reads the (constant) weights: it may run ahead
+  const uint32_t tmem_base = *tmem_ptr_s;
+  const int* pref = p.lens ? pref_s : nullptr;
+  const int nrt = p.lens ? pref_s[p.B] : p.ntiles * p.B;
+  const int G = gridDim.x, cta = blockIdx.x;
+  const int n_it = nrt > cta ? (nrt - cta + G - 1) / G : 0;
+
+  if (warp == 0) {
+    // ------------------------------------------------ input producer: two 32-channel chunks per tile
+    int s = 0;
+    uint32_t ph = 1;
+    PairCursor cur;
+    for (int it = 0; it < n_it; ++it) {
+      const PairTile tc = pair_decode(p, pref, lim_s, (uint32_t)(cta + it * G), cur);
+      const size_t row0 = (size_t)(p.a_pad + tc.q0 - h2 - hd);
+      const tc16* src = p.a_hi + (size_t)tc.b * p.a_bs;
+      for (int c = 0; c < 2; ++c) {
+        mbar_wait(bar(kQAEmpty + s), ph);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar(kQAFull + s), a_stage_bytes);
+          for (int sl = 0; sl < 4; ++sl)
+            bulk_g2s(a_base + s * a_stage_bytes + sl * (uint32_t)RA * 16u,
+                     src + ((size_t)(c * 4 + sl) * p.a_rows + row0) * 8, (uint32_t)RA * 16u, bar(kQAFull + s));
+        }
+        __syncwarp();
+        if (++s == a_stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ weight producer: conv1(0) | conv1(1) conv2(0) | conv1(2) conv2(1) ...
+    int s = 0;
+    uint32_t ph = 1;
+    auto stream_conv = [&](const tc16* w) {
+      for (int c = 0; c < 2; ++c)
+        for (int j0 = 0; j0 < k; j0 += TG) {
+          const uint32_t ntap = (uint32_t)min(TG, k - j0);
+          mbar_wait(bar(kQWEmpty + s), ph);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar(kQWFull + s), ntap * kP64TapBytes);
+            bulk_g2s(w_base + s * w_stage_bytes, w + (size_t)(c * k + j0) * (kP64TapBytes / 2), ntap * kP64TapBytes,
+                     bar(kQWFull + s));
+          }
+          __syncwarp();
+          if (++s == kP64WStages) { s = 0; ph ^= 1u; }
+        }
+    };
+    if (n_it > 0) stream_conv(p.w1);
+    for (int it = 0; it < n_it; ++it) {
+      if (it + 1 < n_it) stream_conv(p.w1);
+      stream_conv(p.w2);
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------ MMA issuer: M1(0), then M1(i + 1), M2(i)
+    if (elect_one()) {
+      const uint32_t hiw = (128u >> 4) | (1u << 14);
+      const uint32_t f16b = p.fmt ? 1u : 0u;
+      const uint32_t idesc = (1u << 4) | (f16b << 7) | (f16b << 10) | ((uint32_t)(kP64NM >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t a_low0 = ((a_base >> 4) & 0x3FFFu) | ((uint32_t)RA << 16);
+      const uint32_t t_low0 = ((t_base >> 4) & 0x3FFFu) | ((uint32_t)RT << 16);
+      const uint32_t w_low0 = ((w_base >> 4) & 0x3FFFu) | ((uint32_t)kP64NM << 16);
+      const uint32_t a_kstep = 2u * (uint32_t)RA, t_kstep = 2u * (uint32_t)RT, b_kstep = 2u * kP64NM;
+      const uint32_t w_tap16 = kP64TapBytes >> 4, w_stage16 = w_stage_bytes >> 4, a_stage16 = a_stage_bytes >> 4;
+      const uint32_t t_chunk16 = t_chunk_bytes >> 4, t_buf16 = t_buf_bytes >> 4;
+      int sa = 0, sw = 0;
+      uint32_t pa = 0, pw = 0;
+      // one convolution of one tile: chunks x tap groups.  from_stage: the staged input chunks; else intermediate tile tb
+      auto conv = [&](uint32_t d_base, bool from_stage, uint32_t tap_step, int tb) {
+        for (int c = 0; c < 2; ++c) {
+          uint32_t a_tap;
+          if (from_stage) {
+            mbar_wait(bar(kQAFull + sa), pa);
+            tc_fence_after();
+            a_tap = a_low0 + (uint32_t)sa * a_stage16;
+          } else {
+            a_tap = t_low0 + (uint32_t)tb * t_buf16 + (uint32_t)c * t_chunk16;
+          }
+          const uint32_t kst = from_stage ? a_kstep : t_kstep;
+          for (int j0 = 0; j0 < k; j0 += TG) {
+            mbar_wait(bar(kQWFull + sw), pw);
+            tc_fence_after();
+            uint32_t b_lo = w_low0 + (uint32_t)sw * w_stage16;
+            const int j1 = min(j0 + TG, k);
+            for (int j = j0; j < j1; ++j, a_tap += tap_step, b_lo += w_tap16) {
+              const uint32_t first = (c | j) != 0 ? 1u : 0u;
+#pragma unroll
+              for (int m = 0; m < 2; ++m) {
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+                  umma_bf16(d_base + (uint32_t)(m * kP64NM), desc64(a_tap + (uint32_t)(m * 128) + ks * kst, hiw),
+                            desc64(b_lo + ks * b_kstep, hiw), idesc, ks == 0 ? first : 1u);
+              }
+            }
+            umma_commit(bar(kQWEmpty + sw));
+            if (++sw == kP64WStages) { sw = 0; pw ^= 1u; }
+          }
+          if (from_stage) {
+            umma_commit(bar(kQAEmpty + sa));
+            if (++sa == a_stages) { sa = 0; pa ^= 1u; }
+          }
+        }
+      };
+      auto conv1 = [&](int i) {
+        mbar_wait(bar(kQAcc1Empty), (i & 1) ^ 1);                     // E1(i - 1) has the accumulators in registers
+        tc_fence_after();
+        conv(tmem_base, true, (uint32_t)p.dil, 0);
+        umma_commit(bar(kQAcc1Full));
+      };
+      if (n_it > 0) conv1(0);
+      for (int i = 0; i < n_it; ++i) {
+        if (i + 1 < n_it) conv1(i + 1);                               // runs while E1(i) / E2(i - 1) finish
+        const int tb = i & 1;
+        mbar_wait(bar(kQTFull + tb), (i >> 1) & 1);                   // E1(i) wrote intermediate tile tb
+        mbar_wait(bar(kQAcc2Empty), (i & 1) ^ 1);                     // E2(i - 1) has its accumulators in registers
+        tc_fence_after();
+        conv(tmem_base + 256u, false, 1u, tb);
+        umma_commit(bar(kQTEmpty + tb));
+        umma_commit(bar(kQAcc2Full));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------ epilogue: E1(i), E2(i); warp = (lane quadrant, sub-tile), two
+    // 32-channel column chunks each
+    const int quad = warp & 3, m = (warp - 3) >> 2;
+    const int r = m * 128 + quad * 32 + lane;
+    const int fmt = p.fmt;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(m * kP64NM);
+    PairCursor cur;
+    auto load_res = [&](const PairTile& tc, int cc, bool ok, int t, float4 (&dst)[8]) {
+      if (p.res && ok) {
+        const float4* rp = reinterpret_cast<const float4*>(p.res + (size_t)tc.b * p.o32_bs) + (size_t)(cc * 8) * p.T + t;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dst[q] = rp[(size_t)q * p.T];
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    // E1(j): conv1 accumulators of tile j -> + b1, leaky, fp16 -> intermediate tile j & 1
+    auto E1 = [&](int j, const PairTile& tj) {
+      const int t = tj.q0 - h2 + r;
+      const bool inside = t >= 0 && t < p.T;
+      const int tb = j & 1;
+      mbar_wait(bar(kQAcc1Full), j & 1);
+      mbar_wait(bar(kQTEmpty + tb), ((j >> 1) & 1) ^ 1);               // conv2 of tile j - 2 has read this buffer
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t a[32], l[32];
+        __syncwarp();
+        tmem_ld32_nowait(lane_addr + (uint32_t)(cc * 32), a);
+        tmem_ld32_nowait(lane_addr + (uint32_t)(kP64C + cc * 32), l);
+        tmem_ld_wait();
+        if (cc == 1) {                                                // both chunks are in registers: conv1 of the next tile may go
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(kQAcc1Empty));
+        }
+        float* af = reinterpret_cast<float*>(a);
+        const float* lf = reinterpret_cast<const float*>(l);
+#pragma unroll
+        for (int q = 0; q < 32; q += 2) add2(af[q], af[q + 1], lf[q], lf[q + 1]);
+        const float4* bv = reinterpret_cast<const float4*>(bias_s + cc * 32);
+        const uint32_t dst = t_base + (uint32_t)tb * t_buf_bytes + (uint32_t)cc * t_chunk_bytes + (uint32_t)(h2 + r) * 16u;
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+          uint32_t hw[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float4 bq = bv[2 * sl + (e >> 1)];
+            float v0 = af[8 * sl + 2 * e], v1 = af[8 * sl + 2 * e + 1];
+            fma2(v0, v1, 1.f, (e & 1) ? bq.z : bq.x, (e & 1) ? bq.w : bq.y);
+            float l0, l1;
+            leaky2(v0, v1, p.slope, l0, l1);
+            hw[e] = inside ? pack2(l0, l1, fmt) : 0u;
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)sl * (uint32_t)RT * 16u), "r"(hw[0]),
+                       "r"(hw[1]), "r"(hw[2]), "r"(hw[3])
+                       : "memory");
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(kQTFull + tb));
+    };
+    PairTile tc{0, 0, 0}, tn{0, 0, 0};
+    if (n_it > 0) {
+      tc = pair_decode(p, pref, lim_s, (uint32_t)cta, cur);
+      E1(0, tc);
+    }
+    for (int i = 0; i < n_it; ++i) {
+      const int t = tc.q0 - h2 + r;
+      const bool ok2 = r >= h2 && r < kPairRows - h2 && t < tc.lim;
+      float4 rc[8];
+      load_res(tc, 0, ok2, t, rc);                                    // in flight while E1(i + 1) runs
+      if (i + 1 < n_it) {
+        tn = pair_decode(p, pref, lim_s, (uint32_t)(cta + (i + 1) * G), cur);
+        E1(i + 1, tn);
+      }
+      // ---- E2(i): conv2 accumulators -> + b2 + residual, 1/3 mean, fp32 stream + operand planes
+      mbar_wait(bar(kQAcc2Full), i & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t a[32], l[32];
+        __syncwarp();
+        tmem_ld32_nowait(lane_addr + 256u + (uint32_t)(cc * 32), a);
+        tmem_ld32_nowait(lane_addr + 256u + (uint32_t)(kP64C + cc * 32), l);
+        float4 rn[8];
+        if (cc == 0) load_res(tc, 1, ok2, t, rn);                     // the second chunk's residual behind the first one's math
+        tmem_ld_wait();
+        if (cc == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(kQAcc2Empty));               // both chunks are in registers
+        }
+        if (ok2) {
+          float* v = reinterpret_cast<float*>(a);
+          const float* lf = reinterpret_cast<const float*>(l);
+#pragma unroll
+          for (int q = 0; q < 32; q += 2) add2(v[q], v[q + 1], lf[q], lf[q + 1]);
+          const float4* bv = reinterpret_cast<const float4*>(bias_s + kP64C + cc * 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 bq = bv[q];
+            fma2(v[4 * q], v[4 * q + 1], 1.f, bq.x, bq.y);
+            fma2(v[4 * q + 2], v[4 * q + 3], 1.f, bq.z, bq.w);
+          }
+          if (p.res) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              add2(v[4 * q], v[4 * q + 1], rc[q].x, rc[q].y);
+              add2(v[4 * q + 2], v[4 * q + 3], rc[q].z, rc[q].w);
+            }
+          }
+          if (p.post != 1.f) {
+#pragma unroll
+            for (int q = 0; q < 32; q += 2) mul2(v[q], v[q + 1], p.post, p.post);
+          }
+          if (p.o32) {
+            float4* op = reinterpret_cast<float4*>(p.o32 + (size_t)tc.b * p.o32_bs) + (size_t)(cc * 8) * p.T + t;
+            if (p.accumulate) {
+              float4 old[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) old[q] = op[(size_t)q * p.T];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                v[4 * q] += old[q].x; v[4 * q + 1] += old[q].y; v[4 * q + 2] += old[q].z; v[4 * q + 3] += old[q].w;
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) op[(size_t)q * p.T] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+          if (p.o_hi) {
+            const size_t prow = (size_t)tc.b * p.op_bs + ((size_t)(cc * 4) * p.op_rows + p.op_pad + t) * 8;
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl) {
+              uint32_t hw[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float l0, l1;
+                leaky2(v[8 * sl + 2 * e], v[8 * sl + 2 * e + 1], p.slope, l0, l1);
+                hw[e] = pack2(l0, l1, fmt);
+              }
+              *reinterpret_cast<uint4*>(p.o_hi + prow + (size_t)sl * p.op_rows * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            }
+          }
+        }
+        if (cc == 0) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) rc[q] = rn[q];
+        }
+      }
+      tc = tn;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+int pair64_tg(int k) {                           // taps per weight stage: <= 4 (32 KB), balanced (11 -> 4 + 4 + 3)
+  const int groups = (k + kP64MaxTG - 1) / kP64MaxTG;
+  return (k + groups - 1) / groups;
+}
+size_t pair64_smem_bytes(int k, int dil, int a_stages) {
+  const int h2 = (k - 1) / 2, hd = h2 * dil;
+  return (size_t)kQHeader + (size_t)kP64WStages * pair64_tg(k) * kP64TapBytes +
+         (size_t)a_stages * 4 * (kPairRows + 2 * hd) * 16 + (size_t)2 * 8 * (kPairRows + 2 * h2) * 16;
+}
+int pair64_a_stages(int k, int dil) {            // three input stages when they fit next to the two intermediate tiles
+  return pair64_smem_bytes(k, dil, kP64AStages) <= (size_t)227 * 1024 ? kP64AStages : 2;
+}
+
 size_t pair_smem_bytes(int k, int dil) {
   const int h2 = (k - 1) / 2, hd = h2 * dil;
   return (size_t)kPHeader + 2 * (size_t)k * kTapBytes + (size_t)kPairAStages * 4 * (kPairRows + 2 * hd) * 16 +
@@ -385,14 +771,17 @@ size_t pair_smem_bytes(int k, int dil) {
 }  // namespace
 
 int rb_pair_supported(const TcConvW& c1, const TcConvW& c2, int dil, int a_planes) {
-  if (c1.C_in != kPairC || c1.C_out != kPairC || c2.C_in != kPairC || c2.C_out != kPairC) return 0;
+  const int C = c1.C_in;
+  if ((C != kPairC && C != kP64C) || c1.C_out != C || c2.C_in != C || c2.C_out != C) return 0;
   if (c1.ktaps != c2.ktaps || !(c1.ktaps & 1) || c1.ktaps > 11 || dil < 1) return 0;
-  if (!c1.stack || !c2.stack || c1.planes != 1 || c2.planes != 1 || c1.N != kPairC || c2.N != kPairC || c1.KC != 32 ||
+  if (!c1.stack || !c2.stack || c1.planes != 1 || c2.planes != 1 || c1.N != C || c2.N != C || c1.KC != 32 ||
       c2.KC != 32 || c1.il_u || c2.il_u || c1.pair || c2.pair || c1.lo8 || c2.lo8 || a_planes != 1 || c1.fmt != c2.fmt)
     return 0;
   const int h2 = (c1.ktaps - 1) / 2;
   if (h2 + h2 * dil > TC_PADF) return 0;                              // the conv1 halo of the first tile starts inside the front padding
-  return pair_smem_bytes(c1.ktaps, dil) <= 227 * 1024;
+  if (C == kP64C && !tc_fuse64_enabled()) return 0;
+  return (C == kPairC ? pair_smem_bytes(c1.ktaps, dil)
+                      : pair64_smem_bytes(c1.ktaps, dil, pair64_a_stages(c1.ktaps, dil))) <= 227 * 1024;
 }
 
 cudaError_t launch_rb_pair(RbPairParams p, cudaStream_t stream) {
@@ -403,12 +792,18 @@ cudaError_t launch_rb_pair(RbPairParams p, cudaStream_t stream) {
   p.ntiles = cdiv(p.T, p.S);
   // the last tile stages rows up to q0 - h2 + 256 + hd of the input planes: they must exist (tc_rows keeps TC_PADB + slack)
   if (p.a_pad - h2 - hd < 0 || p.a_pad + (p.ntiles - 1) * p.S - h2 + kPairRows + hd > p.a_rows) return cudaErrorInvalidValue;
-  const size_t smem = pair_smem_bytes(p.k, p.dil);
+  if (p.C != kPairC && p.C != kP64C) return cudaErrorInvalidValue;
+  const bool wide = p.C == kP64C;
+  p.TG = wide ? pair64_tg(p.k) : 0;
+  p.a_stages = wide ? pair64_a_stages(p.k, p.dil) : kPairAStages;
+  const size_t smem = wide ? pair64_smem_bytes(p.k, p.dil, p.a_stages) : pair_smem_bytes(p.k, p.dil);
   if (smem > (size_t)227 * 1024) return cudaErrorInvalidConfiguration;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
     attr_err = cudaFuncSetAttribute(rb_pair32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(rb_pair64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) return attr_err;
   int dev = 0, sms = 0;
@@ -429,7 +824,7 @@ cudaError_t launch_rb_pair(RbPairParams p, cudaStream_t stream) {
   attr[0].val.programmaticStreamSerializationAllowed = tc_pdl_enabled();
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, rb_pair32_kernel, p);
+  return wide ? cudaLaunchKernelEx(&cfg, rb_pair64_kernel, p) : cudaLaunchKernelEx(&cfg, rb_pair32_kernel, p);
 }
 
 }  // namespace dtts

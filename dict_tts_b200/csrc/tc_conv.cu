@@ -1093,6 +1093,11 @@ int tc_pdl_enabled() {
   return v;
 }
 
+int tc_fuse64_enabled() {
+  static const int v = env_int("DTTS_TC_FUSE64", 1) != 0;
+  return v;
+}
+
 static int g_fuse_override = -1;            // dtts_debug_set_tc_fuse (unit tests): -1 = follow DTTS_TC_FUSE
 void tc_fuse_override(int v) { g_fuse_override = v; }
 int tc_fuse_enabled() {

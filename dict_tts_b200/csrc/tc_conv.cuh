@@ -162,7 +162,7 @@ struct TcConvParams {
 };
 
 // Fused ResBlock pair (rb_pair.cu): conv1 (kernel k, dilation dil) -> leaky -> conv2 (kernel k, dilation 1) -> + residual
-// for C = 32 with hi | lo stacked weights and single-plane activations; bit-identical to the two tc_conv launches.
+// for C = 32 / 64 with hi | lo stacked weights and single-plane activations; bit-identical to the two tc_conv launches.
 struct RbPairParams {
   const tc16* a_hi;              // input operand planes [B][4][a_rows][8] (already leaky-ReLU'd by their producer)
   long a_bs;
@@ -186,7 +186,9 @@ struct RbPairParams {
   const int* lens;               // ragged launch (optional), as TcConvParams
   int len_mul, len_add;
   int B;
+  int C;                         // channels: 32 (weights resident in shared memory) or 64 (weights streamed per tile)
   int S, ntiles;                 // set by the launcher: tile stride 256 - (k - 1), tiles per item
+  int TG, a_stages;              // C = 64: taps per weight stage, input stages (launcher)
 };
 // rows the fused kernel may stage past tc_rows(T): its last tile reads up to 256 + halo rows beyond the tile start
 constexpr int TC_FUSE_EXTRA_ROWS = 320;
@@ -194,6 +196,8 @@ int rb_pair_supported(const TcConvW& c1, const TcConvW& c2, int dil, int a_plane
 cudaError_t launch_rb_pair(RbPairParams p, cudaStream_t stream);
 // DTTS_TC_PDL=0 launches the tcgen05 kernels without programmatic dependent launch (default on)
 int tc_pdl_enabled();
+// DTTS_TC_FUSE64=0 keeps the C = 64 stage on the two-launch form (default: fused)
+int tc_fuse64_enabled();
 // DTTS_TC_FUSE=0 turns the fused ResBlock pairs off (default on)
 int tc_fuse_enabled();
 void tc_fuse_override(int v);      // -1: environment default; 0 / 1: force (unit tests compare the two builds of a pass)

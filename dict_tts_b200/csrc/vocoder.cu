@@ -311,7 +311,7 @@ int tc_vocode(dtts_vocoder* h, const float* mel, int B, int T, float* wav, void*
           RbPairParams fp{};
           fp.a_hi = in.hi; fp.a_bs = in.bs(); fp.a_rows = in.rows; fp.a_pad = TC_PADF;
           fp.w1 = c1.w; fp.w2 = c2.w; fp.b1 = c1.bias; fp.b2 = c2.bias;
-          fp.k = kr; fp.dil = dil; fp.T = len; fp.fmt = c1.fmt; fp.slope = 0.1f;
+          fp.k = kr; fp.dil = dil; fp.T = len; fp.fmt = c1.fmt; fp.slope = 0.1f; fp.C = ch;
           fp.res = m == 0 ? XU : Y32;
           fp.o32_bs = (long)ch * len;
           fp.post = 1.f; fp.accumulate = 0;

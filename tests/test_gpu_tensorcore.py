@@ -345,9 +345,10 @@ def test_vocode_with_lengths_more_than_512_items(precision):
 
 @pytest.mark.parametrize("precision", [3, 6, 4])
 def test_fused_resblock_pair_is_bit_identical_to_two_launches(precision):
-    """rb_pair32_kernel (conv1 -> leaky -> conv2 -> + residual of the C = 32 stage in ONE launch, the intermediate tile in
-    shared memory) issues the same MMAs in the same order and rounds the intermediate exactly like the operand planes of
-    the unfused pair: every sample must match bit for bit -- full length, ragged, several tiles per item, lengths 0 / 1."""
+    """rb_pair32_kernel / rb_pair64_kernel (conv1 -> leaky -> conv2 -> + residual of the C = 32 and C = 64 stages in ONE
+    launch, the intermediate tile in shared memory) issue the same MMAs in the same order and round the intermediate
+    exactly like the operand planes of the unfused pair: every sample must match bit for bit -- full length, ragged,
+    several tiles per item, lengths 0 / 1."""
     from dict_tts_b200.engine import HifiGanEngine
     lib = binding.load()
     eng = HifiGanEngine(synth.make_vocoder_state_dict(VOCODER_SEED), precision=precision)
@@ -368,9 +369,9 @@ def test_fused_resblock_pair_is_bit_identical_to_two_launches(precision):
             launches0 = eng.launches
             one = eng(mel, ln)
             n_one = eng.launches - launches0
-            # nine pairs of the last stage became nine launches (single-plane fp16 weights, precision 4, are not stacked
-            # along N and keep the two-launch form)
-            assert n_two - n_one == (9 if precision in (3, 6) else 0), (n_two, n_one)
+            # the nine pairs of each of the two narrow stages (C = 64, 32) became nine launches each (single-plane fp16
+            # weights, precision 4, are not stacked along N and keep the two-launch form)
+            assert n_two - n_one == (18 if precision in (3, 6) else 0), (n_two, n_one)
             assert torch.equal(one, two), (precision, seed, float((one - two).abs().max()))
     finally:
         lib.dtts_debug_set_tc_fuse(-1)
