@@ -46,8 +46,8 @@ constexpr int kPAFull = 0, kPAEmpty = kPAFull + kPairAStages, kPWFull = kPAEmpty
               kPAcc1Empty = kPAcc1Full + 2, kPAcc2Full = kPAcc1Empty + 2, kPAcc2Empty = kPAcc2Full + 2,
               kPTFull = kPAcc2Empty + 2, kPTEmpty = kPTFull + 2, kPNumBars = kPTEmpty + 2;
 constexpr int kPTmemOff = kPNumBars * 8;
-constexpr int kPBiasOff = (kPTmemOff + 4 + 63) / 64 * 64;                 // b1[32], b2[32]
-constexpr int kPPrefOff = kPBiasOff + 2 * kPairC * 4;                      // ragged tables
+constexpr int kPBiasOff = (kPTmemOff + 4 + 63) / 64 * 64;                 // b1[32], b2[32], conv_post weights [32][7]
+constexpr int kPPrefOff = kPBiasOff + (2 * kPairC + kPairC * 7) * 4;       // ragged tables
 constexpr int kPHeader = (kPPrefOff + (2 * TC_MAX_RAGGED_ITEMS + 8) * 4 + 127) / 128 * 128;
 
 struct PairTile { int b, q0, lim; };
@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) rb_pair32_kernel(const RbPair
     const int i = threadIdx.x - 96;
     bias_s[i] = i < kPairC ? __ldg(p.b1 + i) : __ldg(p.b2 + i - kPairC);
   }
+  if (p.post_part && threadIdx.x >= 96 && threadIdx.x < 96 + kPairC * 7) bias_s[2 * kPairC + threadIdx.x - 96] = __ldg(p.post_w + threadIdx.x - 96);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -346,8 +347,27 @@ __global__ void __launch_bounds__(kPairThreads, 1) rb_pair32_kernel(const RbPair
                 v[4 * q] += old[q].x; v[4 * q + 1] += old[q].y; v[4 * q + 2] += old[q].z; v[4 * q + 3] += old[q].w;
               }
             }
+            if (!p.post_part) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) op[(size_t)q * p.T] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              for (int q = 0; q < 8; ++q) op[(size_t)q * p.T] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+          }
+          if (p.post_part) {
+            // conv_post folded in: the seven per-tap partial dot products of this row (tc_conv_post_finish adds the
+            // shifted partials and applies tanh); the final fp32 stream is never written
+            const float* pw = bias_s + 2 * kPairC;
+            float pj[7];
+#pragma unroll
+            for (int j = 0; j < 7; ++j) pj[j] = 0.f;
+#pragma unroll
+            for (int c = 0; c < kPairC; ++c) {
+              const float lv = fmaxf(v[c], v[c] * p.post_slope);
+#pragma unroll
+              for (int j = 0; j < 7; ++j) pj[j] = fmaf(pw[c * 7 + j], lv, pj[j]);
+            }
+            float* pp = p.post_part + (size_t)prev.b * 7 * p.T + t2;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) pp[(size_t)j * p.T] = pj[j];
           }
           if (p.o_hi) {
             const size_t prow = (size_t)prev.b * p.op_bs + ((size_t)p.op_pad + t2) * 8;
@@ -793,6 +813,7 @@ cudaError_t launch_rb_pair(RbPairParams p, cudaStream_t stream) {
   // the last tile stages rows up to q0 - h2 + 256 + hd of the input planes: they must exist (tc_rows keeps TC_PADB + slack)
   if (p.a_pad - h2 - hd < 0 || p.a_pad + (p.ntiles - 1) * p.S - h2 + kPairRows + hd > p.a_rows) return cudaErrorInvalidValue;
   if (p.C != kPairC && p.C != kP64C) return cudaErrorInvalidValue;
+  if (p.post_part && (p.C != kPairC || !p.post_w)) return cudaErrorInvalidValue;
   const bool wide = p.C == kP64C;
   p.TG = wide ? pair64_tg(p.k) : 0;
   p.a_stages = wide ? pair64_a_stages(p.k, p.dil) : kPairAStages;

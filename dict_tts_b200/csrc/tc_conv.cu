@@ -996,6 +996,26 @@ __global__ void __launch_bounds__(256) tc_conv_post_kernel(const float* __restri
   wav[(size_t)b * T + t] = tanhf(acc);
 }
 
+// wav[b,t] = tanh(bias + sum_j part[b][j][t + j - 3]): the shifted sum of the per-tap partials the last fused pair wrote
+__global__ void __launch_bounds__(256) tc_conv_post_finish_kernel(const float* __restrict__ part,
+                                                                  const float* __restrict__ bias,
+                                                                  float* __restrict__ wav, int T,
+                                                                  const int* __restrict__ lens, int len_mul) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const long valid = lens ? (long)__ldg(lens + b) * len_mul : (long)T;
+  if ((long)t >= valid) { wav[(size_t)b * T + t] = 0.f; return; }
+  const float* pb = part + (size_t)b * 7 * T;
+  float acc = bias ? __ldg(bias) : 0.f;
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const int tt = t + j - 3;
+    if (tt >= 0 && tt < T) acc += __ldg(pb + (size_t)j * T + tt);
+  }
+  wav[(size_t)b * T + t] = tanhf(acc);
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1102,7 +1122,12 @@ static int g_fuse_override = -1;            // dtts_debug_set_tc_fuse (unit test
 void tc_fuse_override(int v) { g_fuse_override = v; }
 int tc_fuse_enabled() {
   static const int v = env_int("DTTS_TC_FUSE", 1) != 0;
-  return g_fuse_override >= 0 ? g_fuse_override : v;
+  return g_fuse_override >= 0 ? (g_fuse_override != 0) : v;
+}
+int tc_fold_post_enabled() {
+  static const int v = env_int("DTTS_TC_FOLD_POST", 1) != 0;
+  if (g_fuse_override >= 0) return g_fuse_override == 1;
+  return v && tc_fuse_enabled();
 }
 
 int tc_lo8_min_taps() {
@@ -1318,6 +1343,13 @@ cudaError_t tc_planes_to_nct(const tc16* hi, const tc16* lo, float* out, int B, 
                              int rows, int pad, int fmt, cudaStream_t s) {
   dim3 grid(cdiv(T, 128), C / 8, B);
   tc_planes_to_nct_kernel<<<grid, 128, 0, s>>>(hi, lo, out, C, T, rows, pad, fmt);
+  return cudaGetLastError();
+}
+
+cudaError_t tc_conv_post_finish(const float* part, const float* bias, float* wav, int B, int T, cudaStream_t s,
+                                const int* lens, int len_mul) {
+  dim3 grid(cdiv(T, 256), B);
+  tc_conv_post_finish_kernel<<<grid, 256, 0, s>>>(part, bias, wav, T, lens, len_mul);
   return cudaGetLastError();
 }
 

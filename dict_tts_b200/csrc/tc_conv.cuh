@@ -189,6 +189,13 @@ struct RbPairParams {
   int C;                         // channels: 32 (weights resident in shared memory) or 64 (weights streamed per tile)
   int S, ntiles;                 // set by the launcher: tile stride 256 - (k - 1), tiles per item
   int TG, a_stages;              // C = 64: taps per weight stage, input stages (launcher)
+  // conv_post folded into the epilogue of the LAST pair (C = 32 only): instead of storing the final fp32 stream (o32 is
+  // then only read, for `accumulate`) every row writes the seven per-tap partial dot products
+  //   part[b][j][t] = sum_c post_w[c][j] * leaky(out[b, c, t], post_slope)
+  // and tc_conv_post_finish adds the shifted partials: wav[t] = tanh(bias + sum_j part[j][t + j - 3]).
+  const float* post_w;           // [32][7] (conv_post.weight), null: off
+  float* post_part;              // [B][7][T]
+  float post_slope;
 };
 // rows the fused kernel may stage past tc_rows(T): its last tile reads up to 256 + halo rows beyond the tile start
 constexpr int TC_FUSE_EXTRA_ROWS = 320;
@@ -200,7 +207,10 @@ int tc_pdl_enabled();
 int tc_fuse64_enabled();
 // DTTS_TC_FUSE=0 turns the fused ResBlock pairs off (default on)
 int tc_fuse_enabled();
-void tc_fuse_override(int v);      // -1: environment default; 0 / 1: force (unit tests compare the two builds of a pass)
+void tc_fuse_override(int v);      // -1: environment default; 0 / 1: force (unit tests compare the two builds of a pass);
+                                   // 2: fused pairs but conv_post as its own kernel (bit-identical to mode 0)
+// conv_post folded into the last fused pair (default on with the fused pairs; DTTS_TC_FOLD_POST=0 or override 2: off)
+int tc_fold_post_enabled();
 
 // output channels per N block of an interleaved transposed convolution: the largest multiple of 8 dividing C_out with
 // stride * cb <= 256 and stride * cb a multiple of 32 (0: unsupported)
@@ -246,6 +256,10 @@ cudaError_t tc_nct_to_stream(const float* in, float* st, int B, int C, int T, cu
 // operand planes (hi + lo) -> fp32 [B][C][T]  (tests)
 cudaError_t tc_planes_to_nct(const tc16* hi, const tc16* lo, float* out, int B, int C, int T,
                              int rows, int pad, int fmt, cudaStream_t s);
+// second half of the folded conv_post (RbPairParams::post_part): wav[b,t] = tanh(bias + sum_j part[b][j][t + j - 3]);
+// samples t >= lens[b] * len_mul are written as 0
+cudaError_t tc_conv_post_finish(const float* part, const float* bias, float* wav, int B, int T, cudaStream_t s,
+                                const int* lens = nullptr, int len_mul = 0);
 // conv_post: y[b,t] = tanh(bias + sum_{c,j} w[c][j] * leaky(x[b,c,t+j-pad], slope)) from an fp32 stream
 // lens (optional, device int32 [B]): samples t >= lens[b] * len_mul of item b are written as 0 without being computed
 cudaError_t tc_conv_post(const float* st, const float* w, const float* bias, float* wav, int B, int C, int T, int K,

@@ -271,6 +271,8 @@ int tc_vocode(dtts_vocoder* h, const float* mel, int B, int T, float* wav, void*
     L(launch_tc_conv(p, B, s));
   }
   int ch = d.init_ch, len = T;
+  bool post_folded = false;                             // conv_post folded into the last fused pair (rb_pair.cu)
+  float* post_part = XU32;                              // [B][7][len]: the ups output is dead by then
   for (int i = 0; i < d.n_ups; ++i) {
     const int u = d.up_rates[i], k = d.up_kernels[i];
     const int len_o = len * u, co = ch / 2;
@@ -323,6 +325,11 @@ int tc_vocode(dtts_vocoder* h, const float* mel, int B, int T, float* wav, void*
             fp.post = 1.f / (float)d.n_rb;
             fp.accumulate = j > 0;
             if (j == d.n_rb - 1 && !last_stage) { fp.o_hi = PX.hi; fp.op_bs = PX.bs(); fp.op_rows = PX.rows; fp.op_pad = TC_PADF; }
+            if (j == d.n_rb - 1 && last_stage && ch == 32 && tc_fold_post_enabled() &&
+                (size_t)7 * B * len <= g.stream_elems) {
+              fp.post_w = h->post_w; fp.post_part = post_part; fp.post_slope = 0.01f;     // F.leaky_relu default (hifigan.py:138)
+              post_folded = true;
+            }
           }
           fp.lens = lens; fp.len_mul = ls.rpf[i + 1]; fp.len_add = ls.stage_add[i]; fp.B = B;
           L(launch_rb_pair(fp, s));
@@ -352,7 +359,8 @@ int tc_vocode(dtts_vocoder* h, const float* mel, int B, int T, float* wav, void*
     }
   }
   // F.leaky_relu default slope 0.01 (hifigan.py:138), conv_post, tanh
-  L(tc_conv_post(ACC32, h->post_w, h->post_b, wav, B, ch, len, 7, 0.01f, s, lens, ls.rpf[d.n_ups]));
+  if (post_folded) L(tc_conv_post_finish(post_part, h->post_b, wav, B, len, s, lens, ls.rpf[d.n_ups]));
+  else L(tc_conv_post(ACC32, h->post_w, h->post_b, wav, B, ch, len, 7, 0.01f, s, lens, ls.rpf[d.n_ups]));
   if (L.err != cudaSuccess) return fail(DTTS_ERR_CUDA, std::string("dtts_vocode(tc): ") + cudaGetErrorString(L.err));
   return DTTS_OK;
 }
@@ -557,7 +565,7 @@ static int vocode_impl(dtts_vocoder* h, const float* mel, const int32_t* lens, i
 }
 
 extern "C" int dtts_debug_set_tc_fuse(int32_t mode) {
-  if (mode < -1 || mode > 1) return fail(DTTS_ERR_BAD_ARG, "dtts_debug_set_tc_fuse: mode must be -1, 0 or 1");
+  if (mode < -1 || mode > 2) return fail(DTTS_ERR_BAD_ARG, "dtts_debug_set_tc_fuse: mode must be -1, 0, 1 or 2");
   tc_fuse_override(mode);
   return DTTS_OK;
 }

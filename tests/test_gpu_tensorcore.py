@@ -365,7 +365,7 @@ def test_fused_resblock_pair_is_bit_identical_to_two_launches(precision):
             launches0 = eng.launches
             eng(mel, ln)
             n_two = eng.launches - launches0
-            assert lib.dtts_debug_set_tc_fuse(1) == 0
+            assert lib.dtts_debug_set_tc_fuse(2) == 0         # fused pairs, conv_post as its own kernel
             launches0 = eng.launches
             one = eng(mel, ln)
             n_one = eng.launches - launches0
@@ -373,6 +373,15 @@ def test_fused_resblock_pair_is_bit_identical_to_two_launches(precision):
             # weights, precision 4, are not stacked along N and keep the two-launch form)
             assert n_two - n_one == (18 if precision in (3, 6) else 0), (n_two, n_one)
             assert torch.equal(one, two), (precision, seed, float((one - two).abs().max()))
+            # the default adds conv_post folded into the last pair: per-tap partial sums instead of one running sum
+            assert lib.dtts_debug_set_tc_fuse(1) == 0
+            launches0 = eng.launches
+            folded = eng(mel, ln)
+            assert eng.launches - launches0 == n_one
+            assert float((folded - two).abs().max()) < 2e-6, (precision, seed)
+            if ln is not None:
+                for b, n in enumerate(ln.tolist()):
+                    assert (folded[b, n * 256:] == 0).all()
     finally:
         lib.dtts_debug_set_tc_fuse(-1)
         eng.close()
