@@ -426,6 +426,14 @@ __global__ void __launch_bounds__(kPairThreads, 1) rb_pair64_kernel(const RbPair
   const int k = p.k, h2 = (p.k - 1) / 2, hd = h2 * p.dil;
   const int RA = kPairRows + 2 * hd, RT = kPairRows + 2 * h2;
   const int TG = p.TG;                                                 // taps per weight stage
+  // csize = 2: the two CTAs of a cluster walk their tiles in lockstep and share the weight stream -- each fetches HALF of
+  // every weight stage and multicasts it into both shared memories (cp.async.bulk ... multicast::cluster), a stage slot is
+  // re-filled once the MMA threads of BOTH CTAs have released it (tcgen05.commit ... multicast onto both w_empty
+  // barriers): the L2 -> SM weight traffic (5.4 TB/s at k = 11) halves.  Measured: no gain -- the kernel is bound by
+  // shared-memory bandwidth (operand fetch of back-to-back N' = 128 MMAs takes all 128 B/clk), so the launcher only uses
+  // it with DTTS_TC_PAIR64_CLUSTER=1 (tools/gpu_round.sh runs the parity tests that way too).
+  const int csize = p.csize;
+  const uint32_t rank = csize > 1 ? cluster_ctarank() : 0u;
   const uint32_t bar0 = smem_u32(smem);
   auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + kQTmemOff);
@@ -466,7 +474,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) rb_pair64_kernel(const RbPair
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < kP64AStages; ++s) { mbar_init(bar(kQAFull + s), 1); mbar_init(bar(kQAEmpty + s), 1); }
-    for (int s = 0; s < kP64WStages; ++s) { mbar_init(bar(kQWFull + s), 1); mbar_init(bar(kQWEmpty + s), 1); }
+    for (int s = 0; s < kP64WStages; ++s) { mbar_init(bar(kQWFull + s), 1); mbar_init(bar(kQWEmpty + s), (uint32_t)csize); }
     mbar_init(bar(kQAcc1Full), 1); mbar_init(bar(kQAcc1Empty), 8);
     mbar_init(bar(kQAcc2Full), 1); mbar_init(bar(kQAcc2Empty), 8);
     for (int s = 0; s < 2; ++s) { mbar_init(bar(kQTFull + s), 8); mbar_init(bar(kQTEmpty + s), 1); }
@@ -484,6 +492,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) rb_pair64_kernel(const RbPair
   }
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();             // the peer's barriers exist before any multicast copy / remote arrive
   tc_fence_after();
   if (warp != 1) griddep_wait();                 // warp 1 only reads the (constant) weights: it may run ahead
   const uint32_t tmem_base = *tmem_ptr_s;
@@ -491,6 +500,10 @@ __global__ void __launch_bounds__(kPairThreads, 1) rb_pair64_kernel(const RbPair
   const int nrt = p.lens ? pref_s[p.B] : p.ntiles * p.B;
   const int G = gridDim.x, cta = blockIdx.x;
   const int n_it = nrt > cta ? (nrt - cta + G - 1) / G : 0;
+  // tiles of the cluster's first CTA: the weight stream runs for that many tiles in both CTAs (the second one may have
+  // one tile less: it then consumes the last tile's weight stages without issuing MMAs)
+  const int cta0 = cta - (int)rank;
+  const int n_w = nrt > cta0 ? (nrt - cta0 + G - 1) / G : 0;
 
   if (warp == 0) {
     // ------------------------------------------------ input producer: two 32-channel chunks per tile
@@ -521,19 +534,25 @@ __global__ void __launch_bounds__(kPairThreads, 1) rb_pair64_kernel(const RbPair
       for (int c = 0; c < 2; ++c)
         for (int j0 = 0; j0 < k; j0 += TG) {
           const uint32_t ntap = (uint32_t)min(TG, k - j0);
-          mbar_wait(bar(kQWEmpty + s), ph);
+          mbar_wait(bar(kQWEmpty + s), ph);                         // released by the MMA threads of all CTAs of the cluster
           if (elect_one()) {
-            mbar_arrive_expect_tx(bar(kQWFull + s), ntap * kP64TapBytes);
-            bulk_g2s(w_base + s * w_stage_bytes, w + (size_t)(c * k + j0) * (kP64TapBytes / 2), ntap * kP64TapBytes,
-                     bar(kQWFull + s));
+            mbar_arrive_expect_tx(bar(kQWFull + s), ntap * kP64TapBytes);   // the whole stage lands here, one slice per CTA
+            const tc16* src = w + (size_t)(c * k + j0) * (kP64TapBytes / 2);
+            if (csize > 1) {
+              const uint32_t half = ntap * kP64TapBytes / 2u;
+              bulk_g2s_mc(w_base + s * w_stage_bytes + rank * half, src + (size_t)rank * (half / 2), half, bar(kQWFull + s),
+                          (uint16_t)3);
+            } else {
+              bulk_g2s(w_base + s * w_stage_bytes, src, ntap * kP64TapBytes, bar(kQWFull + s));
+            }
           }
           __syncwarp();
           if (++s == kP64WStages) { s = 0; ph ^= 1u; }
         }
     };
-    if (n_it > 0) stream_conv(p.w1);
-    for (int it = 0; it < n_it; ++it) {
-      if (it + 1 < n_it) stream_conv(p.w1);
+    if (n_w > 0) stream_conv(p.w1);
+    for (int it = 0; it < n_w; ++it) {
+      if (it + 1 < n_w) stream_conv(p.w1);
       stream_conv(p.w2);
     }
   } else if (warp == 2) {
@@ -577,7 +596,8 @@ __global__ void __launch_bounds__(kPairThreads, 1) rb_pair64_kernel(const RbPair
                             desc64(b_lo + ks * b_kstep, hiw), idesc, ks == 0 ? first : 1u);
               }
             }
-            umma_commit(bar(kQWEmpty + sw));
+            if (csize > 1) umma_commit_mc(bar(kQWEmpty + sw), (uint16_t)3);   // w_empty here and at the peer's producer
+            else umma_commit(bar(kQWEmpty + sw));
             if (++sw == kP64WStages) { sw = 0; pw ^= 1u; }
           }
           if (from_stage) {
@@ -592,9 +612,16 @@ __global__ void __launch_bounds__(kPairThreads, 1) rb_pair64_kernel(const RbPair
         conv(tmem_base, true, (uint32_t)p.dil, 0);
         umma_commit(bar(kQAcc1Full));
       };
-      if (n_it > 0) conv1(0);
-      for (int i = 0; i < n_it; ++i) {
-        if (i + 1 < n_it) conv1(i + 1);                               // runs while E1(i) / E2(i - 1) finish
+      // a tile this CTA does not have (the cluster's odd tile): keep the shared weight pipeline moving, nothing else
+      auto skip_conv = [&]() {
+        for (int c = 0; c < 2; ++c)
+          for (int j0 = 0; j0 < k; j0 += TG) {
+            mbar_wait(bar(kQWFull + sw), pw);
+            umma_commit_mc(bar(kQWEmpty + sw), (uint16_t)3);
+            if (++sw == kP64WStages) { sw = 0; pw ^= 1u; }
+          }
+      };
+      auto conv2 = [&](int i) {
         const int tb = i & 1;
         mbar_wait(bar(kQTFull + tb), (i >> 1) & 1);                   // E1(i) wrote intermediate tile tb
         mbar_wait(bar(kQAcc2Empty), (i & 1) ^ 1);                     // E2(i - 1) has its accumulators in registers
@@ -602,6 +629,13 @@ __global__ void __launch_bounds__(kPairThreads, 1) rb_pair64_kernel(const RbPair
         conv(tmem_base + 256u, false, 1u, tb);
         umma_commit(bar(kQTEmpty + tb));
         umma_commit(bar(kQAcc2Full));
+      };
+      auto c1 = [&](int i) { if (i < n_it) conv1(i); else skip_conv(); };
+      auto c2 = [&](int i) { if (i < n_it) conv2(i); else skip_conv(); };
+      if (n_w > 0) c1(0);
+      for (int i = 0; i < n_w; ++i) {
+        if (i + 1 < n_w) c1(i + 1);                                   // runs while E1(i) / E2(i - 1) finish
+        c2(i);
       }
     }
     __syncwarp();
@@ -763,6 +797,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) rb_pair64_kernel(const RbPair
   }
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();             // no peer may still multicast into / arrive on this CTA's shared memory
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -832,12 +867,11 @@ cudaError_t launch_rb_pair(RbPairParams p, cudaStream_t stream) {
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return e;
   const long tiles = (long)p.ntiles * p.B;
-  const int grid = (int)(tiles < sms ? tiles : sms);
+  int grid = (int)(tiles < sms ? tiles : sms);
   // the CTA owns all 512 TMEM columns: it must be alone on its SM (shared memory above half of the SM's guarantees it)
   const size_t smem_launch = smem < 116 * 1024 ? 116 * 1024 : smem;
   cudaLaunchConfig_t cfg{};
-  cudaLaunchAttribute attr[1];
-  cfg.gridDim = dim3((unsigned)grid);
+  cudaLaunchAttribute attr[2];
   cfg.blockDim = dim3(kPairThreads);
   cfg.dynamicSmemBytes = smem_launch;
   cfg.stream = stream;
@@ -845,6 +879,36 @@ cudaError_t launch_rb_pair(RbPairParams p, cudaStream_t stream) {
   attr[0].val.programmaticStreamSerializationAllowed = tc_pdl_enabled();
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  p.csize = 1;
+  if (wide && tc_pair64_cluster_enabled() && tiles >= 2) {
+    // clusters of two CTAs sharing the weight stream; as many as can be co-resident (queried once per device)
+    static std::mutex mu;
+    static int max_clusters[64] = {0};
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64) {
+      attr[1].id = cudaLaunchAttributeClusterDimension;
+      attr[1].val.clusterDim = {2, 1, 1};
+      cfg.numAttrs = 2;
+      if (max_clusters[dev] == 0) {
+        int n = 0;
+        cfg.gridDim = dim3((unsigned)(sms / 2 * 2));
+        cfg.dynamicSmemBytes = 227 * 1024;
+        cudaError_t q = cudaOccupancyMaxActiveClusters(&n, rb_pair64_kernel, &cfg);
+        cfg.dynamicSmemBytes = smem_launch;
+        max_clusters[dev] = (q == cudaSuccess && n > 0) ? n : -1;
+        if (q != cudaSuccess) (void)cudaGetLastError();
+      }
+      if (max_clusters[dev] > 0) {
+        const long want = tiles / 2;
+        const int nc = (int)(want < max_clusters[dev] ? want : max_clusters[dev]);
+        grid = 2 * nc;
+        p.csize = 2;
+      } else {
+        cfg.numAttrs = 1;
+      }
+    }
+  }
+  cfg.gridDim = dim3((unsigned)grid);
   return wide ? cudaLaunchKernelEx(&cfg, rb_pair64_kernel, p) : cudaLaunchKernelEx(&cfg, rb_pair32_kernel, p);
 }
 

@@ -1113,6 +1113,11 @@ int tc_pdl_enabled() {
   return v;
 }
 
+int tc_pair64_cluster_enabled() {
+  static const int v = env_int("DTTS_TC_PAIR64_CLUSTER", 0) != 0;
+  return v;
+}
+
 int tc_fuse64_enabled() {
   static const int v = env_int("DTTS_TC_FUSE64", 1) != 0;
   return v;

@@ -188,7 +188,7 @@ struct RbPairParams {
   int B;
   int C;                         // channels: 32 (weights resident in shared memory) or 64 (weights streamed per tile)
   int S, ntiles;                 // set by the launcher: tile stride 256 - (k - 1), tiles per item
-  int TG, a_stages;              // C = 64: taps per weight stage, input stages (launcher)
+  int TG, a_stages, csize;       // C = 64: taps per weight stage, input stages, CTAs sharing the weight stream (launcher)
   // conv_post folded into the epilogue of the LAST pair (C = 32 only): instead of storing the final fp32 stream (o32 is
   // then only read, for `accumulate`) every row writes the seven per-tap partial dot products
   //   part[b][j][t] = sum_c post_w[c][j] * leaky(out[b, c, t], post_slope)
@@ -203,6 +203,11 @@ int rb_pair_supported(const TcConvW& c1, const TcConvW& c2, int dil, int a_plane
 cudaError_t launch_rb_pair(RbPairParams p, cudaStream_t stream);
 // DTTS_TC_PDL=0 launches the tcgen05 kernels without programmatic dependent launch (default on)
 int tc_pdl_enabled();
+// DTTS_TC_PAIR64_CLUSTER=1: the fused C = 64 kernel with the 2-CTA weight multicast.  Built, bit-identical, and measured
+// on a B200 without any gain (per-launch times equal to the microsecond: the kernel is bound by shared-memory bandwidth --
+// MMA operand fetch at N' = 128 needs the full 128 B/clk next to the bulk copies -- not by the L2 -> SM weight stream),
+// so it is off by default.
+int tc_pair64_cluster_enabled();
 // DTTS_TC_FUSE64=0 keeps the C = 64 stage on the two-launch form (default: fused)
 int tc_fuse64_enabled();
 // DTTS_TC_FUSE=0 turns the fused ResBlock pairs off (default on)

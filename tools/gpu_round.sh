@@ -8,6 +8,9 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv > gpurun_out/${TAG}_gpu.txt 2>&1
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest_gpu.log
 tail -4 gpurun_out/${TAG}_pytest_gpu.log
+# the opt-in builds of the tcgen05 kernels (switches are read once per process)
+DTTS_TC_PAIR64_CLUSTER=1 timeout 300 python -m pytest tests/test_gpu_tensorcore.py -m gpu -q -k "fused or lengths" > gpurun_out/${TAG}_pytest_gpu_cluster64.log 2>&1; echo "pytest (DTTS_TC_PAIR64_CLUSTER=1) rc=$?" | tee -a gpurun_out/${TAG}_pytest_gpu_cluster64.log
+DTTS_TC_PAIR=0 DTTS_TC_PDL=0 timeout 300 python -m pytest tests/test_gpu_tensorcore.py -m gpu -q -k "fp8_lo or lengths or baseline_shapes or fused" > gpurun_out/${TAG}_pytest_gpu_nopair.log 2>&1; echo "pytest (DTTS_TC_PAIR=0 DTTS_TC_PDL=0) rc=$?" | tee -a gpurun_out/${TAG}_pytest_gpu_nopair.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | tee gpurun_out/${TAG}_smoke.log
 timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_bench_n1.err; echo "bench rc=$?"
 head -c 600 gpurun_out/${TAG}_bench_n1.json; echo
