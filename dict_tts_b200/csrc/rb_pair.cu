@@ -29,6 +29,7 @@
 #include "tc_conv.cuh"
 #include "tc16.cuh"
 #include "tc_ptx.cuh"
+#include "rb_pair_common.cuh"
 
 #include <mutex>
 
@@ -36,8 +37,6 @@ namespace dtts {
 
 namespace {
 
-constexpr int kPairThreads = 96 + 8 * 32;
-constexpr int kPairRows = 256;                 // rows per tile (two 128-row MMA sub-tiles)
 constexpr int kPairC = 32, kPairNM = 64;       // channels; MMA N (hi | lo stacked)
 constexpr int kPairAStages = 3;
 constexpr int kTapBytes = kPairNM * kPairC * 2;   // one tap of one convolution: 4 KB
@@ -49,29 +48,6 @@ constexpr int kPTmemOff = kPNumBars * 8;
 constexpr int kPBiasOff = (kPTmemOff + 4 + 63) / 64 * 64;                 // b1[32], b2[32], conv_post weights [32][7]
 constexpr int kPPrefOff = kPBiasOff + (2 * kPairC + kPairC * 7) * 4;       // ragged tables
 constexpr int kPHeader = (kPPrefOff + (2 * TC_MAX_RAGGED_ITEMS + 8) * 4 + 127) / 128 * 128;
-
-struct PairTile { int b, q0, lim; };
-struct PairCursor { int b = 0; uint32_t base = 0; };
-// row tile rt (tiles of all items back to back) -> (item, first output row, row limit of the item)
-__device__ __forceinline__ PairTile pair_decode(const RbPairParams& p, const int* pref, const int* limv, uint32_t rt,
-                                                PairCursor& cur) {
-  PairTile c;
-  if (pref) {
-    int b = cur.b;
-    while (b + 1 < p.B && (uint32_t)pref[b + 1] <= rt) ++b;
-    cur.b = b;
-    c.b = b;
-    c.q0 = (int)(rt - (uint32_t)pref[b]) * p.S;
-    c.lim = limv[b];
-  } else {
-    const uint32_t nt = (uint32_t)p.ntiles;
-    while (rt >= cur.base + nt) { cur.base += nt; ++cur.b; }
-    c.b = cur.b;
-    c.q0 = (int)(rt - cur.base) * p.S;
-    c.lim = p.T;
-  }
-  return c;
-}
 
 __global__ void __launch_bounds__(kPairThreads, 1) rb_pair32_kernel(const RbPairParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -827,6 +803,7 @@ size_t pair_smem_bytes(int k, int dil) {
 
 int rb_pair_supported(const TcConvW& c1, const TcConvW& c2, int dil, int a_planes) {
   const int C = c1.C_in;
+  if (C == 128) return rb_pair128_supported(c1, c2, dil, a_planes);
   if ((C != kPairC && C != kP64C) || c1.C_out != C || c2.C_in != C || c2.C_out != C) return 0;
   if (c1.ktaps != c2.ktaps || !(c1.ktaps & 1) || c1.ktaps > 11 || dil < 1) return 0;
   if (!c1.stack || !c2.stack || c1.planes != 1 || c2.planes != 1 || c1.N != C || c2.N != C || c1.KC != 32 ||
@@ -841,6 +818,7 @@ int rb_pair_supported(const TcConvW& c1, const TcConvW& c2, int dil, int a_plane
 
 cudaError_t launch_rb_pair(RbPairParams p, cudaStream_t stream) {
   if (p.B <= 0 || p.T <= 0) return cudaSuccess;
+  if (p.C == 128) return launch_rb_pair128(p, stream);
   if (p.lens && p.B > TC_MAX_RAGGED_ITEMS) return cudaErrorInvalidValue;
   const int h2 = (p.k - 1) / 2, hd = h2 * p.dil;
   p.S = kPairRows - 2 * h2;

@@ -95,6 +95,10 @@ struct TcConvW {
   // plane e5m2((w - fp16(w)) * 2^10), [group][K-chunk][tap]([half])[KC/16][N][16] bytes
   const uint8_t* w8 = nullptr;
   int lo8 = 0;
+  // rb_pair128.cu: the same blobs as ONE contiguous stream per CTA of the pair, [half][chunk][tap]{fp16 plane(s), e5m2
+  // plane}, so that a weight stage of the fused kernel is a single bulk copy (null: not built for this layer)
+  const uint8_t* wstream = nullptr;
+  size_t stream_bytes() const { return (size_t)C_out * C_in * ktaps * (2 * planes + (lo8 ? 1 : 0)); }
   size_t elems8() const { return (size_t)C_out * C_in * ktaps; }      // bytes of w8
   size_t elems() const {
     return (size_t)(il_u ? il_u : 1) * C_out * C_in * ktaps * phases * planes * (stack ? 2 : 1);
@@ -161,8 +165,9 @@ struct TcConvParams {
   float acc_scale;
 };
 
-// Fused ResBlock pair (rb_pair.cu): conv1 (kernel k, dilation dil) -> leaky -> conv2 (kernel k, dilation 1) -> + residual
-// for C = 32 / 64 with hi | lo stacked weights and single-plane activations; bit-identical to the two tc_conv launches.
+// Fused ResBlock pair (rb_pair.cu, rb_pair128.cu): conv1 (kernel k, dilation dil) -> leaky -> conv2 (kernel k, dilation 1)
+// -> + residual for C = 32 / 64 (hi | lo stacked weights) and C = 128 (CTA pairs, two fp16 weight planes or fp16 + FP8),
+// single-plane activations; bit-identical to the two tc_conv launches.
 struct RbPairParams {
   const tc16* a_hi;              // input operand planes [B][4][a_rows][8] (already leaky-ReLU'd by their producer)
   long a_bs;
@@ -189,6 +194,7 @@ struct RbPairParams {
   int C;                         // channels: 32 (weights resident in shared memory) or 64 (weights streamed per tile)
   int S, ntiles;                 // set by the launcher: tile stride 256 - (k - 1), tiles per item
   int TG, a_stages, csize;       // C = 64: taps per weight stage, input stages, CTAs sharing the weight stream (launcher)
+  int w_stages, pf;              // C = 128: depth of the weight ring, L2 prefetch of the next tile's input (launcher)
   // conv_post folded into the epilogue of the LAST pair (C = 32 only): instead of storing the final fp32 stream (o32 is
   // then only read, for `accumulate`) every row writes the seven per-tap partial dot products
   //   part[b][j][t] = sum_c post_w[c][j] * leaky(out[b, c, t], post_slope)
@@ -196,6 +202,12 @@ struct RbPairParams {
   const float* post_w;           // [32][7] (conv_post.weight), null: off
   float* post_part;              // [B][7][T]
   float post_slope;
+  // C = 128 (rb_pair128.cu, CTA pairs): the weights as per-CTA streams (TcConvW::wstream); w_planes fp16 planes (2: hi +
+  // lo, one MMA each) or, with lo8, one fp16 plane x 2^10 plus the e5m2 lo plane
+  const uint8_t* w1s;
+  const uint8_t* w2s;
+  int w_planes, lo8;
+  float acc_scale;               // the accumulators hold conv / acc_scale (TcConvParams::acc_scale)
 };
 // rows the fused kernel may stage past tc_rows(T): its last tile reads up to 256 + halo rows beyond the tile start
 constexpr int TC_FUSE_EXTRA_ROWS = 320;
@@ -210,10 +222,16 @@ int tc_pdl_enabled();
 int tc_pair64_cluster_enabled();
 // DTTS_TC_FUSE64=0 keeps the C = 64 stage on the two-launch form (default: fused)
 int tc_fuse64_enabled();
+// largest kernel size whose C = 128 ResBlock pairs run fused (rb_pair128.cu).  DTTS_TC_FUSE128_MAXK, default 3: measured on
+// a B200 the fused k = 3 pairs take 535 us against 594 for two launches, k = 7 the same 860, k = 11 1250 against 1047 (the
+// 102 KB intermediate tile leaves too little shared memory for the input stages); 0 turns the kernel off,
+// 11 fuses all of them (what tc_fuse_override(3) does for the bit-identity tests)
+int tc_fuse128_maxk();
 // DTTS_TC_FUSE=0 turns the fused ResBlock pairs off (default on)
 int tc_fuse_enabled();
 void tc_fuse_override(int v);      // -1: environment default; 0 / 1: force (unit tests compare the two builds of a pass);
-                                   // 2: fused pairs but conv_post as its own kernel (bit-identical to mode 0)
+                                   // 2: fused pairs but conv_post as its own kernel (bit-identical to mode 0);
+                                   // 3: as 2 with every C = 128 pair fused too (tc_fuse128_maxk)
 // conv_post folded into the last fused pair (default on with the fused pairs; DTTS_TC_FOLD_POST=0 or override 2: off)
 int tc_fold_post_enabled();
 
@@ -246,6 +264,8 @@ cudaError_t tc_lo8_weights_fit(const float* w_ref, size_t n, cudaStream_t s, int
 // e5m2 lo plane of the weights for TcConvW::lo8 (layout in TcConvW)
 cudaError_t tc_pack_weights_lo8(const float* w_ref, uint8_t* out, int C_out, int C_in, int K, int N, int KC, int fmt,
                                 int pair, cudaStream_t s);
+// TcConvW::wstream of a packed pair-mode convolution with C_in = C_out = 128 (rb_pair128.cu)
+cudaError_t rb_pair128_pack_stream(const TcConvW& w, uint8_t* out, cudaStream_t s);
 // same, and zero-fills every row outside [pad, pad+T) (one launch for a freshly re-shaped scratch buffer)
 // C_total / c_off: the C source channels become channels [c_off, c_off + C) of planes that hold C_total channels
 // s2d_H > 0: space-to-depth source, plane channel ch = x channel ch % s2d_H at time t * ts + ch / s2d_H

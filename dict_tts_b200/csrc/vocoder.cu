@@ -22,6 +22,7 @@ struct dtts_vocoder {
   TcMode mode;
   tc16* tc_pool = nullptr;
   uint8_t* tc_pool8 = nullptr;   // e5m2 lo planes (precision 6)
+  uint8_t* tc_pool_s = nullptr;  // per-CTA weight streams of the fused C = 128 ResBlock pairs (rb_pair128.cu)
   TcConvW tc_pre;
   std::vector<TcConvW> tc_ups, tc_rb1, tc_rb2;
   const float *post_w = nullptr, *post_b = nullptr;
@@ -144,6 +145,27 @@ int tc_create(dtts_vocoder* h, cudaStream_t s) {
     }
   }
   if ((size_t)(cur - h->tc_pool) > total) return fail(DTTS_ERR_CUDA, "tc weight pool overrun");
+  {
+    // the C = 128 CTA-pair convolutions once more as contiguous per-CTA streams (a weight stage of rb_pair128_kernel is then
+    // ONE bulk copy); ~2 MB for HiFi-GAN V1
+    auto wants = [](const TcConvW& c) { return c.pair && c.C_in == 128 && c.C_out == 128 && c.N == 128 && c.KC == 32 && !c.il_u; };
+    size_t total_s = 0;
+    for (auto* v : {&h->tc_rb1, &h->tc_rb2})
+      for (const TcConvW& c : *v)
+        if (wants(c)) total_s += (c.stream_bytes() + 127) / 128 * 128;
+    if (total_s) {
+      e = cudaMalloc((void**)&h->tc_pool_s, total_s);
+      if (e != cudaSuccess) return fail(DTTS_ERR_CUDA, std::string("cudaMalloc(weight streams): ") + cudaGetErrorString(e));
+      uint8_t* cs = h->tc_pool_s;
+      for (auto* v : {&h->tc_rb1, &h->tc_rb2})
+        for (TcConvW& c : *v)
+          if (wants(c)) {
+            DTTS_CUDA(rb_pair128_pack_stream(c, cs, s));
+            c.wstream = cs;
+            cs += (c.stream_bytes() + 127) / 128 * 128;
+          }
+    }
+  }
   if (ch % 4 || ch > 64) return fail(DTTS_ERR_BAD_SHAPE, "tensor-core vocoder: conv_post needs <= 64 input channels");
   h->post_w = h->tab.get("conv_post.weight", (uint64_t)ch * 7);
   h->post_b = h->tab.get("conv_post.bias", 1);
@@ -313,6 +335,8 @@ int tc_vocode(dtts_vocoder* h, const float* mel, int B, int T, float* wav, void*
           RbPairParams fp{};
           fp.a_hi = in.hi; fp.a_bs = in.bs(); fp.a_rows = in.rows; fp.a_pad = TC_PADF;
           fp.w1 = c1.w; fp.w2 = c2.w; fp.b1 = c1.bias; fp.b2 = c2.bias;
+          fp.w1s = c1.wstream; fp.w2s = c2.wstream; fp.w_planes = c1.planes; fp.lo8 = c1.lo8;
+          fp.acc_scale = c1.lo8 ? 1.f / kLo8WScale : 1.f;
           fp.k = kr; fp.dil = dil; fp.T = len; fp.fmt = c1.fmt; fp.slope = 0.1f; fp.C = ch;
           fp.res = m == 0 ? XU : Y32;
           fp.o32_bs = (long)ch * len;
@@ -425,6 +449,7 @@ extern "C" int dtts_vocoder_create(const dtts_vocoder_desc* d, const float* aren
     if (rc != DTTS_OK) {
       if (h->tc_pool) cudaFree(h->tc_pool);
       if (h->tc_pool8) cudaFree(h->tc_pool8);
+      if (h->tc_pool_s) cudaFree(h->tc_pool_s);
       return bail(rc);
     }
   }
@@ -439,6 +464,7 @@ extern "C" int dtts_vocoder_destroy(dtts_vocoder* h) {
   h->pool.release();
   if (h->tc_pool) cudaFree(h->tc_pool);
   if (h->tc_pool8) cudaFree(h->tc_pool8);
+  if (h->tc_pool_s) cudaFree(h->tc_pool_s);
   delete h;
   return DTTS_OK;
 }
@@ -565,7 +591,7 @@ static int vocode_impl(dtts_vocoder* h, const float* mel, const int32_t* lens, i
 }
 
 extern "C" int dtts_debug_set_tc_fuse(int32_t mode) {
-  if (mode < -1 || mode > 2) return fail(DTTS_ERR_BAD_ARG, "dtts_debug_set_tc_fuse: mode must be -1, 0, 1 or 2");
+  if (mode < -1 || mode > 3) return fail(DTTS_ERR_BAD_ARG, "dtts_debug_set_tc_fuse: mode must be -1 .. 3");
   tc_fuse_override(mode);
   return DTTS_OK;
 }

@@ -345,8 +345,9 @@ def test_vocode_with_lengths_more_than_512_items(precision):
 
 @pytest.mark.parametrize("precision", [3, 6, 4])
 def test_fused_resblock_pair_is_bit_identical_to_two_launches(precision):
-    """rb_pair32_kernel / rb_pair64_kernel (conv1 -> leaky -> conv2 -> + residual of the C = 32 and C = 64 stages in ONE
-    launch, the intermediate tile in shared memory) issue the same MMAs in the same order and round the intermediate
+    """rb_pair32_kernel / rb_pair64_kernel / rb_pair128_kernel (conv1 -> leaky -> conv2 -> + residual of the C = 32, 64 and
+    128 stages in ONE launch, the intermediate tile in shared memory; C = 128 on CTA pairs with two fp16 weight planes,
+    fp16 + FP8 lo plane or a single plane) issue the same MMAs in the same order and round the intermediate
     exactly like the operand planes of the unfused pair: every sample must match bit for bit -- full length, ragged,
     several tiles per item, lengths 0 / 1."""
     from dict_tts_b200.engine import HifiGanEngine
@@ -369,10 +370,17 @@ def test_fused_resblock_pair_is_bit_identical_to_two_launches(precision):
             launches0 = eng.launches
             one = eng(mel, ln)
             n_one = eng.launches - launches0
-            # the nine pairs of each of the two narrow stages (C = 64, 32) became nine launches each (single-plane fp16
-            # weights, precision 4, are not stacked along N and keep the two-launch form)
-            assert n_two - n_one == (18 if precision in (3, 6) else 0), (n_two, n_one)
+            # the nine pairs of each of the stages C = 64, 32 and the three k = 3 pairs of the CTA-pair stage C = 128 became
+            # one launch each (single-plane fp16 weights, precision 4, are not stacked along N: there only C = 128 has a
+            # fused form)
+            assert n_two - n_one == (21 if precision in (3, 6) else 3), (n_two, n_one)
             assert torch.equal(one, two), (precision, seed, float((one - two).abs().max()))
+            # ... and with every C = 128 pair fused (k = 7, 11: FP8 lo plane in mode 6; off by default, no faster)
+            assert lib.dtts_debug_set_tc_fuse(3) == 0
+            launches0 = eng.launches
+            full = eng(mel, ln)
+            assert n_two - (eng.launches - launches0) == (27 if precision in (3, 6) else 9)
+            assert torch.equal(full, two), (precision, seed, float((full - two).abs().max()))
             # the default adds conv_post folded into the last pair: per-tap partial sums instead of one running sum
             assert lib.dtts_debug_set_tc_fuse(1) == 0
             launches0 = eng.launches

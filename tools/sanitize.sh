@@ -18,8 +18,11 @@ run() {   # tag, tool, env..., -- args
 }
 run pair   memcheck DTTS_TC_PAIR=1 --
 [ -n "$SAN_FIRST_ONLY" ] && { run pair racecheck DTTS_TC_PAIR=1 -- --frames 8; exit 0; }
+[ -n "$SAN_FUSE128_ONLY" ] && { run fuse128 memcheck DTTS_TC_PAIR=1 -- --skip-acoustic --fuse-all; run fuse128 racecheck DTTS_TC_PAIR=1 -- --skip-acoustic --fuse-all --frames 8; exit 0; }
 run single memcheck DTTS_TC_PAIR=0 --
 run cluster2 memcheck DTTS_TC_PAIR=0 DTTS_TC_CLUSTER=2 -- --skip-acoustic --vocoder-precision 3
 run p1     memcheck DTTS_TC_PAIR=1 -- --skip-acoustic --vocoder-precision 1
+run fuse128 memcheck DTTS_TC_PAIR=1 -- --skip-acoustic --fuse-all
 run pair   racecheck DTTS_TC_PAIR=1 -- --frames 8
+run fuse128 racecheck DTTS_TC_PAIR=1 -- --skip-acoustic --fuse-all --frames 8
 run single racecheck DTTS_TC_PAIR=0 -- --frames 8

@@ -20,7 +20,12 @@ def main():
     ap.add_argument("--vocoder-precision", type=int, default=6)
     ap.add_argument("--frames", type=int, default=24)
     ap.add_argument("--skip-acoustic", action="store_true")
+    ap.add_argument("--fuse-all", action="store_true",
+                    help="dtts_debug_set_tc_fuse(3): every C = 128 ResBlock pair on rb_pair128_kernel (default: k = 3 only)")
     args = ap.parse_args()
+    if args.fuse_all:
+        from dict_tts_b200 import binding
+        assert binding.load().dtts_debug_set_tc_fuse(3) == 0
     if not args.skip_acoustic:
         batch = synth.make_batch(seed=3, B=2, min_chars=3, max_chars=5, max_frames=32, Lk_cap=32)
         for route in (0, 1):
