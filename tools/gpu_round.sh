@@ -28,7 +28,10 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:rb_p
   python tools/prof_vocoder.py --precision 6 --iters 0 --lens > /dev/null 2>&1; echo "ncu pair32 rc=$?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:rb_pair64 -s 7 -c 1 -o gpurun_out/${TAG}_rb_pair64_k11 -f \
   python tools/prof_vocoder.py --precision 6 --iters 0 --lens > /dev/null 2>&1; echo "ncu pair64 rc=$?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:tc_conv_kernel -s 33 -c 1 -o gpurun_out/${TAG}_tc_conv_s2_k11 -f \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:tc_conv_kernel -s 27 -c 1 -o gpurun_out/${TAG}_tc_conv_s2_k11 -f \
   python tools/prof_vocoder.py --precision 6 --iters 0 --lens > /dev/null 2>&1; echo "ncu s2 rc=$?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:rb_pair128 -s 0 -c 1 -o gpurun_out/${TAG}_rb_pair128_k3 -f \
+  python tools/prof_vocoder.py --precision 6 --iters 0 --lens > /dev/null 2>&1; echo "ncu pair128 rc=$?"
+./tools/_build/mma_rate > gpurun_out/${TAG}_mma_rate.log 2>&1; echo "mma_rate rc=$?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:s2pa_stream -c 1 -o gpurun_out/${TAG}_s2pa_stream -f \
   python tools/prof_acoustic.py --iters 0 --alias > /dev/null 2>&1; echo "ncu s2pa rc=$?"

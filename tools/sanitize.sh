@@ -16,9 +16,9 @@ run() {   # tag, tool, env..., -- args
   local rc=$?
   echo "[$tool/$tag] rc=$rc $(tail -1 gpurun_out/sanitizer_${tool}_${tag}.out) | $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $log | tail -1)"
 }
+[ -n "$SAN_FUSE128_ONLY" ] && { run fuse128 memcheck DTTS_TC_PAIR=1 -- --skip-acoustic --fuse-all; run fuse128 racecheck DTTS_TC_PAIR=1 -- --skip-acoustic --fuse-all --frames 8; exit 0; }
 run pair   memcheck DTTS_TC_PAIR=1 --
 [ -n "$SAN_FIRST_ONLY" ] && { run pair racecheck DTTS_TC_PAIR=1 -- --frames 8; exit 0; }
-[ -n "$SAN_FUSE128_ONLY" ] && { run fuse128 memcheck DTTS_TC_PAIR=1 -- --skip-acoustic --fuse-all; run fuse128 racecheck DTTS_TC_PAIR=1 -- --skip-acoustic --fuse-all --frames 8; exit 0; }
 run single memcheck DTTS_TC_PAIR=0 --
 run cluster2 memcheck DTTS_TC_PAIR=0 DTTS_TC_CLUSTER=2 -- --skip-acoustic --vocoder-precision 3
 run p1     memcheck DTTS_TC_PAIR=1 -- --skip-acoustic --vocoder-precision 1
