@@ -32,6 +32,8 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:tc_c
   python tools/prof_vocoder.py --precision 6 --iters 0 --lens > /dev/null 2>&1; echo "ncu s2 rc=$?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:rb_pair128 -s 0 -c 1 -o gpurun_out/${TAG}_rb_pair128_k3 -f \
   python tools/prof_vocoder.py --precision 6 --iters 0 --lens > /dev/null 2>&1; echo "ncu pair128 rc=$?"
+mkdir -p tools/_build
+[ -x tools/_build/mma_rate ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I dict_tts_b200/csrc -o tools/_build/mma_rate tools/mma_rate.cu
 ./tools/_build/mma_rate > gpurun_out/${TAG}_mma_rate.log 2>&1; echo "mma_rate rc=$?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:s2pa_stream -c 1 -o gpurun_out/${TAG}_s2pa_stream -f \
   python tools/prof_acoustic.py --iters 0 --alias > /dev/null 2>&1; echo "ncu s2pa rc=$?"
