@@ -97,11 +97,124 @@ __global__ void __launch_bounds__(256) rel_self_attn_kernel(const float* __restr
   }
 }
 
+// The same attention for T <= 64 with q, k, v of one (batch item, head) -- and the relative-position tables -- resident in
+// shared memory, one block per (b, head): the per-row kernel above re-reads K and V from L2 for every query row and pays a
+// warp reduction per output channel (255 us at [60, 2 heads, T = 64]; this one: one staging pass + T*T*dk FMAs from shared
+// memory).  Same formulas, scores summed over d in the same order.
+__global__ void __launch_bounds__(256) rel_self_attn_small_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                                   const float* __restrict__ v,
+                                                                   const float* __restrict__ mask,
+                                                                   const float* __restrict__ rel_k,
+                                                                   const float* __restrict__ rel_v, int window,
+                                                                   float* __restrict__ out, int C, int T, int heads,
+                                                                   long bs, PlaneOut po) {
+  extern __shared__ float sm[];   // qs[dk][T], ks[dk][T], vs[dk][T], ps[T][T+1], rk[dk][2w+1] (transposed), rv[2w+1][dk]
+  griddep_launch_if_resident();
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int dk = C / heads, nrel = 2 * window + 1;
+  float* qs = sm;
+  float* ks = qs + (size_t)dk * T;
+  float* vs = ks + (size_t)dk * T;
+  float* ps = vs + (size_t)dk * T;
+  float* rk = ps + (size_t)T * (T + 1);
+  float* rv = rk + (size_t)dk * nrel;
+  const size_t base = (size_t)b * bs + (size_t)h * dk * T;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < dk * T; i += blockDim.x) {
+    const float a = __ldg(q + base + i), c = __ldg(k + base + i), d = __ldg(v + base + i);
+    qs[i] = a;
+    ks[i] = c;
+    vs[i] = d;
+  }
+  if (rel_k) {
+    for (int i = threadIdx.x; i < nrel * dk; i += blockDim.x) {
+      const int r = i / dk, d = i - r * dk;
+      rk[d * nrel + r] = __ldg(rel_k + i);
+      rv[i] = __ldg(rel_v + i);
+    }
+  }
+  __syncthreads();
+  const float* mb = mask + (size_t)b * T;
+  const float inv = rsqrtf((float)dk);
+  for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
+    const int t = i / T, s2 = i - t * T;
+    float acc = 0.f;
+    for (int d = 0; d < dk; ++d) acc = fmaf(qs[d * T + t], ks[d * T + s2], acc);
+    acc *= inv;
+    const int r = s2 - t + window;
+    if (rel_k && r >= 0 && r < nrel) {
+      float a2 = 0.f;
+      for (int d = 0; d < dk; ++d) a2 = fmaf(qs[d * T + t], rk[d * nrel + r], a2);
+      acc += a2 * inv;
+    }
+    if (mb[t] * mb[s2] == 0.f) acc = -1e4f;
+    ps[t * (T + 1) + s2] = acc;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int t = warp; t < T; t += nw) {               // softmax of row t by one warp
+    float* pr = ps + t * (T + 1);
+    float mx = -INFINITY;
+    for (int s2 = lane; s2 < T; s2 += 32) mx = fmaxf(mx, pr[s2]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int s2 = lane; s2 < T; s2 += 32) {
+      const float e = expf(pr[s2] - mx);
+      pr[s2] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float rs = 1.f / sum;
+    for (int s2 = lane; s2 < T; s2 += 32) pr[s2] *= rs;
+  }
+  __syncthreads();
+  // out[d, t] = sum_s p[t, s] v[d, s] + sum_{|s - t| <= w} p[t, s] rel_v[s - t + w][d]; results overwrite qs (q is dead)
+  for (int i = threadIdx.x; i < dk * T; i += blockDim.x) {
+    const int d = i / T, t = i - d * T;
+    const float* pr = ps + t * (T + 1);
+    float acc = 0.f;
+    for (int s2 = 0; s2 < T; ++s2) acc = fmaf(pr[s2], vs[d * T + s2], acc);
+    if (rel_v) {
+      for (int j = 0; j < nrel; ++j) {
+        const int s2 = t - window + j;
+        if (s2 >= 0 && s2 < T) acc = fmaf(pr[s2], rv[j * dk + d], acc);
+      }
+    }
+    qs[i] = acc;
+    if (out) out[(size_t)b * C * T + (size_t)h * dk * T + i] = acc;
+  }
+  if (po.hi) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < (dk / 8) * T; i += blockDim.x) {
+      const int sl = i / T, t = i - sl * T;
+      float v8[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v8[e] = qs[(sl * 8 + e) * T + t];
+      store_slab(po, b, C, h * (dk / 8) + sl, t, v8);
+    }
+  }
+}
+
 cudaError_t rel_self_attention(const float* q, const float* k, const float* v, const float* mask, const float* rel_k,
                                const float* rel_v, int window, float* out, int B, int C, int T, int heads,
                                const PlaneOut& po, cudaStream_t s) {
   const int dk = C / heads;
   if (C % heads || (po.hi && dk % 8) || (rel_k && 2 * window + 1 > 32) || (!rel_k != !rel_v)) return cudaErrorInvalidValue;
+  if (T <= 64) {
+    const int nrel = rel_k ? 2 * window + 1 : 0;
+    const size_t small = ((size_t)3 * dk * T + (size_t)T * (T + 1) + (size_t)2 * nrel * dk) * sizeof(float);
+    if (small <= 160 * 1024) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(rel_self_attn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+      }
+      rel_self_attn_small_kernel<<<B * heads, 256, small, s>>>(q, k, v, mask, rel_k, rel_v, rel_k ? window : 0, out, C, T, heads,
+                                                               (long)3 * C * T, po);
+      return cudaGetLastError();
+    }
+  }
   const int nw = 8;
   const size_t smem = (size_t)nw * (2 * dk + T) * sizeof(float);
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
@@ -347,9 +460,96 @@ __global__ void __launch_bounds__(256) ps_word_attn_kernel(const float* __restri
     if (lane == 0) ctx[((size_t)b * H + c) * T + t] = acc;
   }
 }
+// The same attention with K and V of the utterance and a tile of 64 query frames resident in shared memory (block = one
+// utterance x 64 frames, 8 warps x 8 frames): the per-frame kernel above re-reads K | V (2 * H * Tp floats) from L2 for every
+// frame -- 2.3 GB for a [60, 192, 400] x [.., 64] call, 795 us.  Scores are summed over c in the same order (attn is
+// bit-identical); ctx sums over s sequentially with lanes along the channels instead of a warp reduction per channel.
+__global__ void __launch_bounds__(256) ps_word_attn_tile_kernel(const float* __restrict__ q, const float* __restrict__ kv,
+                                                                 const int64_t* __restrict__ mel2word,
+                                                                 const int64_t* __restrict__ ph2word, int H, int T, int Tp,
+                                                                 float* __restrict__ attn, float* __restrict__ ctx) {
+  extern __shared__ float sm[];   // ks[H][Tp], vs[H][Tp+1], qt[H][64] (becomes the ctx tile), pr[8][Tp], seg[Tp]
+  constexpr int FPB = 64;
+  const int b = blockIdx.y, t0 = blockIdx.x * FPB;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float* ks = sm;
+  float* vs = ks + (size_t)H * Tp;
+  float* qt = vs + (size_t)H * (Tp + 1);
+  float* prs = qt + (size_t)H * FPB;
+  int* seg = reinterpret_cast<int*>(prs + (size_t)nw * Tp);
+  const float* kb = kv + (size_t)b * 2 * H * Tp;
+  const float* vb = kb + (size_t)H * Tp;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < H * Tp; i += blockDim.x) {
+    const float a = __ldg(kb + i), c = __ldg(vb + i);
+    ks[i] = a;
+    vs[(i / Tp) * (Tp + 1) + (i % Tp)] = c;
+  }
+  const int nf = min(FPB, T - t0);
+#pragma unroll 4
+  for (int i = threadIdx.x; i < H * FPB; i += blockDim.x) {
+    const int c = i / FPB, f = i - c * FPB;
+    qt[i] = f < nf ? __ldg(q + ((size_t)b * H + c) * T + t0 + f) : 0.f;
+  }
+  for (int i = threadIdx.x; i < Tp; i += blockDim.x) seg[i] = (int)ph2word[(size_t)b * Tp + i];
+  __syncthreads();
+  float* pr = prs + (size_t)warp * Tp;
+  for (int f = warp; f < nf; f += nw) {
+    const int t = t0 + f;
+    const int wt = (int)mel2word[(size_t)b * T + t];
+    float mx = -INFINITY;
+    for (int s = lane; s < Tp; s += 32) {
+      float acc = 0.f;
+      for (int c = 0; c < H; ++c) acc = fmaf(qt[c * FPB + f], ks[c * Tp + s], acc);
+      acc += (seg[s] == wt) ? 0.f : -1e9f;
+      pr[s] = acc;
+      mx = fmaxf(mx, acc);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int s = lane; s < Tp; s += 32) {
+      const float e = expf(pr[s] - mx);
+      pr[s] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float rs = 1.f / sum;
+    for (int s = lane; s < Tp; s += 32) {
+      const float w = pr[s] * rs;
+      pr[s] = w;
+      if (attn) attn[((size_t)b * T + t) * Tp + s] = w;
+    }
+    __syncwarp();
+    for (int c = lane; c < H; c += 32) {               // lanes along the channels; column f of the q tile is dead by now
+      const float* vr = vs + (size_t)c * (Tp + 1);
+      float acc = 0.f;
+      for (int s = 0; s < Tp; ++s) acc = fmaf(pr[s], vr[s], acc);
+      qt[c * FPB + f] = acc;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H * FPB; i += blockDim.x) {
+    const int c = i / FPB, f = i - c * FPB;
+    if (f < nf) ctx[((size_t)b * H + c) * T + t0 + f] = qt[i];
+  }
+}
+
 cudaError_t ps_word_attention(const float* q, const float* kv, const int64_t* mel2word, const int64_t* ph2word, int B,
                               int H, int T, int Tp, float* attn, float* ctx, cudaStream_t s) {
   const int nw = 8;
+  const size_t tile = ((size_t)H * Tp + (size_t)H * (Tp + 1) + (size_t)H * 64 + (size_t)nw * Tp + Tp) * sizeof(float);
+  if (tile <= 200 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(ps_word_attn_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    dim3 grid(cdiv(T, 64), B);
+    ps_word_attn_tile_kernel<<<grid, nw * 32, tile, s>>>(q, kv, mel2word, ph2word, H, T, Tp, attn, ctx);
+    return cudaGetLastError();
+  }
   const size_t smem = (size_t)nw * (H + Tp) * sizeof(float);
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
   if (smem > 48 * 1024) {

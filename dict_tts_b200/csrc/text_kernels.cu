@@ -71,10 +71,20 @@ __global__ void channel_ln_kernel(const float* __restrict__ x, float* __restrict
   }
 }
 
+__global__ void channel_ln_tiled_kernel(const float* __restrict__ x, float* __restrict__ xw, float* __restrict__ y,
+                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                        const float* __restrict__ in_mask, const float* __restrict__ out_mask, int C, int T,
+                                        PlaneOut po, int relu);
+
 cudaError_t channel_layernorm(const float* x, float* y, const float* gamma, const float* beta, float eps,
                               const float* in_mask, const float* out_mask, int B, int C, int T, cudaStream_t s,
                               int relu) {
   dim3 grid(cdiv(T, 32), B);
+  const size_t smem = ((size_t)C * 33 + 256 + 64) * sizeof(float);
+  if (smem <= 48 * 1024) {          // the tiled kernel (8 x 32 threads per 32 time steps): 30 -> 10 us at [60, 192, 64]
+    channel_ln_tiled_kernel<<<grid, 256, smem, s>>>(x, nullptr, y, gamma, beta, eps, in_mask, out_mask, C, T, PlaneOut{}, relu);
+    return cudaGetLastError();
+  }
   channel_ln_kernel<<<grid, 32, 0, s>>>(x, y, gamma, beta, eps, in_mask, out_mask, C, T, relu);
   return cudaGetLastError();
 }
@@ -90,7 +100,7 @@ __global__ void __launch_bounds__(256) channel_ln_tiled_kernel(const float* __re
                                                                const float* __restrict__ beta, float eps,
                                                                const float* __restrict__ in_mask,
                                                                const float* __restrict__ out_mask, int C, int T,
-                                                               PlaneOut po) {
+                                                               PlaneOut po, int relu) {
   extern __shared__ float sm[];                      // xs[C][33], red[8][32], mean[32], rstd[32]
   griddep_launch_if_resident();                      // the consumer (a tcgen05 launch) may set itself up meanwhile
   float* xs = sm;
@@ -151,7 +161,9 @@ __global__ void __launch_bounds__(256) channel_ln_tiled_kernel(const float* __re
   const float rstd = rstd_s[lane];
 #pragma unroll 4
   for (int c = grp; c < C; c += 8) {
-    const float v = ((xs[c * 33 + lane] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c)) * om;
+    float v = (xs[c * 33 + lane] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+    if (relu) v = fmaxf(v, 0.f);
+    v *= om;
     xs[c * 33 + lane] = v;
     if (y && tv) y[(size_t)b * C * T + (size_t)c * T + t] = v;
   }
@@ -175,7 +187,7 @@ cudaError_t channel_layernorm_planes(const float* x, float* xw, float* y, const 
   const size_t smem = ((size_t)C * 33 + 256 + 64) * sizeof(float);
   if (smem > 48 * 1024) return cudaErrorInvalidConfiguration;
   dim3 grid(cdiv(T, 32), B);
-  channel_ln_tiled_kernel<<<grid, 256, smem, s>>>(x, xw, y, gamma, beta, eps, in_mask, out_mask, C, T, po);
+  channel_ln_tiled_kernel<<<grid, 256, smem, s>>>(x, xw, y, gamma, beta, eps, in_mask, out_mask, C, T, po, 0);
   return cudaGetLastError();
 }
 
