@@ -6,7 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdtts.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 DTTS_MAX_UPS = 8
 DTTS_MAX_RB = 4
 # dtts_status (include/dtts.h)
@@ -102,6 +102,7 @@ SYMBOLS = {
     "dtts_vocoder_launch_count": (_U64, [_P]),
     "dtts_acoustic_launch_count": (_U64, [_P]),
     "dtts_debug_set_tc_fuse": (C.c_int, [_I]),
+    "dtts_debug_set_acoustic_fuse": (C.c_int, [_I]),
     "dtts_debug_conv1d": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P]),
     "dtts_debug_tc_conv1d": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _F, _I, _P,
                                        _U64, _P]),

@@ -353,6 +353,44 @@ int pack_decoder(dtts_acoustic* h, cudaStream_t s) {
     DTTS_TRY(pack_wn(h, q + ".enc", d->flow_hidden, d->flow_layers, d->flow_kernel, H, &F.wn, s));
     h->flows.push_back(F);
   }
+  if (h->precision && d->flow_blocks > 0 &&
+      flow_fused_supported(H, d->flow_hidden, d->latent, d->flow_kernel, d->flow_layers, d->flow_blocks)) {
+    // the same weights once more as the stream of flow_fused_kernel, in execution order (reverse pass: last layer first)
+    FlowFusedW& W = h->flow_fused;
+    W.n_flows = d->flow_blocks; W.n_layers = d->flow_layers; W.n_chunks = H / 64; W.H = H;
+    W.par_stride = flow_fused_par_floats(d->flow_layers);
+    W.par = h->pool.take((size_t)W.par_stride * W.n_flows);
+    if (!W.par) return fail(DTTS_ERR_CUDA, "weight pool exhausted");
+    if (cudaMalloc((void**)&W.stream, W.stream_bytes()) != cudaSuccess) {
+      W.stream = nullptr;
+      return fail(DTTS_ERR_CUDA, "fused prior flow: weight stream allocation failed");
+    }
+    const int FH = d->flow_hidden, Ln = d->flow_layers;
+    for (int e = 0; e < W.n_flows; ++e) {
+      const int f = d->flow_blocks - 1 - e;
+      const FlowW& F = h->flows[f];
+      if (F.odd) W.odd_mask |= 1u << e;
+      const std::string q = "fvae.prior_flow.flows." + std::to_string(2 * f) + ".enc";
+      const float* cw = h->tab.get(q + ".cond_layer.weight", (uint64_t)2 * FH * Ln * H);
+      FlowParSrc src{};
+      src.n_layers = Ln;
+      src.cond_b = h->tab.get(q + ".cond_layer.bias", (uint64_t)2 * FH * Ln);
+      if (!cw || !src.cond_b) return DTTS_ERR_MISSING_WEIGHT;
+      for (int i = 0; i < Ln; ++i) {
+        const int rs = (i < Ln - 1) ? 2 * FH : FH;
+        const std::string li = std::to_string(i);
+        const float* iw = h->tab.get(q + ".in_layers." + li + ".weight", (uint64_t)2 * FH * FH * d->flow_kernel);
+        const float* rw = h->tab.get(q + ".res_skip_layers." + li + ".weight", (uint64_t)rs * FH);
+        src.in_b[i] = h->tab.get(q + ".in_layers." + li + ".bias", 2 * FH);
+        src.rs_b[i] = h->tab.get(q + ".res_skip_layers." + li + ".bias", rs);
+        if (!iw || !rw || !src.in_b[i] || !src.rs_b[i]) return DTTS_ERR_MISSING_WEIGHT;
+        DTTS_CUDA(flow_fused_pack_layer(iw, cw + (size_t)i * 2 * FH * H, rw, rs, H,
+                                        W.stream + ((size_t)e * Ln + i) * (W.n_chunks + 4) * 32768, s));
+      }
+      src.pre_w = F.pre.w; src.pre_b = F.pre.bias; src.post_w = F.post.w; src.post_b = F.post.bias;
+      DTTS_CUDA(flow_fused_pack_par(src, W.par + (size_t)e * W.par_stride, s));
+    }
+  }
   {
     // ConvTranspose1d(latent -> H, k=4, s=4): weight [latent][H][4]
     const float* w = h->tab.get("fvae.decoder.pre_net.0.weight", (uint64_t)d->latent * H * 4);
@@ -497,6 +535,7 @@ extern "C" int dtts_acoustic_destroy(dtts_acoustic* h) {
   h->pool.release();
   destroy_ps(h);
   if (h->tc_pool) cudaFree(h->tc_pool);
+  if (h->flow_fused.stream) cudaFree(h->flow_fused.stream);
   if (h->bank_err_dev) cudaFree(h->bank_err_dev);
   if (h->bank_err_host) cudaFreeHost(h->bank_err_host);
   if (h->bank_err_evt) cudaEventDestroy(h->bank_err_evt);
@@ -826,6 +865,7 @@ extern "C" int dtts_decode_mel(dtts_acoustic* h, const float* g, const float* z_
   cudaStream_t s = L.stream;
   tcr.h = h; tcr.L = &L; tcr.B = B;
 
+  const bool fuse_flow = tc && h->flow_fused.ready() && ac_fuse_enabled();
   // g_sqz = Conv1d(H,H,k=8,s=4,p=2)(g)  (fvae_semantics.py:93-94; semantics == 0)
   if (tc) {
     Planes& P0 = tc->P[0];
@@ -833,15 +873,27 @@ extern "C" int dtts_decode_mel(dtts_acoustic* h, const float* g, const float* z_
       // x'[(sp, ci), q] = g[ci, 4q + sp]: one staging launch for the four phases
       L(tc_to_planes_full(g, (long)H * T, T, 4, B, 4 * H, T4, 1.f, P0.hi, h->mode.a_planes == 2 ? P0.lo : nullptr, P0.rows,
                           TC_PADF, h->mode.fmt, s, 0, 0, H));
-      tc->conv_nct(P0, h->t_gpre, g_sqz, T4, 1, 1, TcRun::Epi());
+      // fused prior flow: g_sqz is only needed as the operand planes of the conditioning GEMMs
+      if (fuse_flow) tc->conv_nct(P0, h->t_gpre, nullptr, T4, 1, 1, TcRun::Epi(), 0, 0, &tc->P[1]);
+      else tc->conv_nct(P0, h->t_gpre, g_sqz, T4, 1, 1, TcRun::Epi());
     }
   } else {
     L(launch_conv1d_f32(conv_params(g, T, h->g_pre, 0, H, g_sqz, T4, 1, 4, 2), B, s));
   }
   // prior flow, reverse (glow_modules.py:108-128,157-163).  The channel Flip is folded into the pre/post weights:
   // on "odd" layers the conditioning half is physical channels [half, 2*half) and the updated half is [0, half).
-  L(copy_f32(z_in, z_p, (size_t)B * d.latent * T4, s));
-  for (int f = d.flow_blocks - 1; f >= 0; --f) {
+  if (fuse_flow) {
+    // every coupling layer in ONE launch (flow_fused.cu): activations stay in shared memory / TMEM
+    const Planes& Pg = tc->P[1];
+    FlowFusedParams fp{};
+    fp.g_hi = Pg.hi; fp.g_lo = Pg.lo; fp.g_bs = (long)Pg.C * Pg.rows; fp.g_rows = Pg.rows; fp.g_pad = TC_PADF;
+    fp.z_in = z_in; fp.z_out = z_p; fp.T = T4; fp.B = B;
+    if (z_in == z_p) L(cudaErrorInvalidValue);
+    else L(launch_flow_fused(h->flow_fused, fp, s));
+  } else {
+    L(copy_f32(z_in, z_p, (size_t)B * d.latent * T4, s));
+  }
+  for (int f = d.flow_blocks - 1; f >= 0 && !fuse_flow; --f) {
     const FlowW& F = h->flows[f];
     const int c_x0 = F.odd ? half : 0, c_x1 = F.odd ? 0 : half;
     if (FH % 8 == 0 && half % 8 == 0) {      // 8 <-> 64 channels: one thread per position (pointwise_small_kernel)
@@ -882,6 +934,12 @@ extern "C" int dtts_decode_mel(dtts_acoustic* h, const float* g, const float* z_
     L(launch_conv1d_f32(p, B, s));
   }
   if (L.err != cudaSuccess) return fail(DTTS_ERR_CUDA, std::string("dtts_decode_mel: ") + cudaGetErrorString(L.err));
+  return DTTS_OK;
+}
+
+extern "C" int dtts_debug_set_acoustic_fuse(int32_t mode) {
+  if (mode < -1 || mode > 1) return fail(DTTS_ERR_BAD_ARG, "dtts_debug_set_acoustic_fuse: mode must be -1, 0 or 1");
+  ac_fuse_override(mode);
   return DTTS_OK;
 }
 

@@ -5,6 +5,7 @@
 #include <algorithm>
 
 #include "engine.cuh"
+#include "flow_fused.cuh"
 #include "tc_conv.cuh"
 #include "tc16.cuh"
 
@@ -64,6 +65,7 @@ struct dtts_acoustic {
   dtts::ConvW g_pre, dec_pre, dec_out;
   std::vector<dtts::ac::FlowW> flows;   // in reference order (flows.0, .2, .4, .6)
   dtts::ac::WNW dec_wn;
+  dtts::FlowFusedW flow_fused;          // the whole prior flow as one launch (flow_fused.cu); empty: per-layer launches
   dtts::ac::PsW* ps = nullptr;     // model = 1 (PortaSpeech sibling): its text-side weights; the dict-encoder members stay empty
   uint64_t launches = 0;
   // dictionary-bank gather status (dtts_text_encode_bank): device word written by dict_bank_gather_kernel, copied to the

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DTTS_ABI_VERSION 4
+#define DTTS_ABI_VERSION 5
 
 typedef enum dtts_status {
   DTTS_OK = 0,
@@ -291,6 +291,12 @@ int dtts_debug_tc_conv1d(const float* x_dev, const float* w_dev, const float* bi
  * measured no faster than two launches, DTTS_TC_FUSE128_MAXK); -1: back to the default / the DTTS_TC_FUSE,
  * DTTS_TC_FOLD_POST environment switches. */
 int dtts_debug_set_tc_fuse(int32_t mode);
+
+/* Unit-test hook: the fused kernels of the acoustic model (flow_fused_kernel: the whole reverse prior flow of
+ * FVAE_semantics.forward(infer=True), modules/dict_tts/fvae_semantics.py:96-101, as one launch instead of one launch per
+ * layer) compute the same arithmetic as the per-layer path in another summation order; this switch lets a test run both.
+ * mode 0: one launch per layer; 1: fused; -1: back to the default (fused) / the DTTS_AC_FUSE environment switch. */
+int dtts_debug_set_acoustic_fuse(int32_t mode);
 
 #ifdef __cplusplus
 }

@@ -266,3 +266,42 @@ def test_acoustic_random_shapes_against_oracle(case, acoustic):
                         batch["pinyin"], batch["pinyin_map"])
     for k in ("word_encoder_out", "pron_attn", "dur_int"):
         assert torch.equal(a[k], b[k]), k
+
+
+# --------------------------------------------------------------------------------------------------
+# fused prior flow (flow_fused_kernel): one launch for every coupling layer, against the per-layer path and the oracle
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,T", [(2, 4), (3, 100), (2, 448), (2, 452), (1, 1280), (60, 400)])
+def test_fused_prior_flow_matches_per_layer_path_and_oracle(B, T):
+    """T/4 latent frames: 1 (single row), 25, 112 (largest one-tile length), 113 (first two-tile length), 320 (four
+    tiles, the cfg-1 utterance) and the cfg-2 batch; tiles overlap by 2 x 16 rows and store only their core rows."""
+    from dict_tts_b200.engine import DictTTSEngine
+    lib = binding.load()
+    sd = synth.make_acoustic_state_dict(ACOUSTIC_SEED)
+    eng = DictTTSEngine(sd, precision=1)
+    W = fold_weight_norm(sd)
+    cfg = AcousticConfig()
+    g = torch.Generator().manual_seed(1000 + T)
+    x = torch.randn(B, T, cfg.hidden, generator=g) * 0.5
+    z = torch.randn(B, cfg.latent, T // 4, generator=g)
+    g_bct = x.transpose(1, 2).contiguous().cuda()
+    try:
+        assert lib.dtts_debug_set_acoustic_fuse(1) == 0
+        n0 = eng.launches
+        mel_f, zp_f = eng.decode_mel(g_bct, z.cuda())
+        n_fused = eng.launches - n0
+        assert lib.dtts_debug_set_acoustic_fuse(0) == 0
+        n0 = eng.launches
+        mel_u, zp_u = eng.decode_mel(g_bct, z.cuda())
+        n_unfused = eng.launches - n0
+    finally:
+        lib.dtts_debug_set_acoustic_fuse(-1)
+    torch.cuda.synchronize()
+    assert n_fused <= n_unfused - 70, (n_fused, n_unfused)
+    with torch.no_grad():
+        mel_r, zp_r = O.decode_mel(W, cfg, x, z)
+    assert torch.isfinite(zp_f).all()
+    assert (zp_f.cpu() - zp_r).abs().max().item() < 1e-4
+    assert (zp_f - zp_u).abs().max().item() < 2e-5
+    assert (mel_f.cpu() - mel_r).abs().max().item() < TOL_MEL_MAXABS
+    eng.close()
