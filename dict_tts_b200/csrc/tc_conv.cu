@@ -1113,6 +1113,14 @@ int tc_pdl_enabled() {
   return v;
 }
 
+int tc_nmax() {
+  static const int v = [] {
+    const int n = env_int("DTTS_TC_NMAX", 256);
+    return (n == 64 || n == 128 || n == 256) ? n : 256;
+  }();
+  return v;
+}
+
 int tc_pair64_cluster_enabled() {
   static const int v = env_int("DTTS_TC_PAIR64_CLUSTER", 0) != 0;
   return v;

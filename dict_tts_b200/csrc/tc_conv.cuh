@@ -68,6 +68,10 @@ static inline int tc_rows(int T) {
 
 // DTTS_TC_PAIR=0 turns the CTA-pair path off (default on)
 int tc_pair_enabled();
+// widest MMA N of a vocoder convolution (DTTS_TC_NMAX: 64, 128 or 256): C_out = 256 as ONE N = 256 block (a 128-row tile per
+// CTA: TMEM holds two 256-column accumulator sets) or as two N = 128 blocks (256-row tiles: every weight byte that reaches
+// shared memory is used for twice as many rows, the activation tile is staged once per block)
+int tc_nmax();
 // fewest taps of a convolution that uses the FP8 lo plane under TcMode::lo8 (DTTS_TC_LO8_MINTAPS, default 7: the k = 3
 // layers are latency / HBM bound, the extra conversion step in front of their MMAs costs more than the MMAs it saves)
 int tc_lo8_min_taps();

@@ -71,7 +71,7 @@ int tc_pack(dtts_vocoder* h, tc16** cursor, const std::string& name, int C_out, 
     cw->N = cw->il_cb * stride;
     if (!cw->il_cb) return fail(DTTS_ERR_BAD_SHAPE, "tensor-core vocoder: unsupported transposed convolution " + name);
   } else {
-    cw->N = C_out > 256 ? 256 : C_out;
+    cw->N = C_out > tc_nmax() ? tc_nmax() : C_out;
     if (C_out % cw->N) return fail(DTTS_ERR_BAD_SHAPE, "tensor-core vocoder: unsupported channel count in " + name);
   }
   cw->set_mode(mode);
