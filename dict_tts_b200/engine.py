@@ -42,6 +42,10 @@ class _Workspace:
 
     def get(self, nbytes: int) -> torch.Tensor:
         if self.buf is None or self.buf.numel() < nbytes:
+            if self.buf is not None:
+                # the old block goes back to the allocator of the stream it was created on while kernels of ANOTHER stream
+                # (synthesize_stream runs the acoustic model on its own stream) may still use it: growth is rare, wait
+                torch.cuda.synchronize(self.device)
             self.buf = None
             self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
         return self.buf

@@ -114,6 +114,11 @@ def test_pipeline_stream_equals_serial_calls():
     assert len(streamed) == len(serial)
     for a, b in zip(serial, streamed):
         assert torch.equal(a, b)
+    # the opt-in variant that runs the acoustic model of batch i+1 on its own stream next to the vocoder of batch i
+    overlapped = [w.clone() for w in pipe.synthesize_stream(iter(batches), overlap_acoustic=True)]
+    assert len(overlapped) == len(serial)
+    for a, b in zip(serial, overlapped):
+        assert torch.equal(a, b)
     W = fold_weight_norm(synth.make_acoustic_state_dict(1234))
     Wv = fold_weight_norm(synth.make_vocoder_state_dict(4321))
     with torch.no_grad():

@@ -35,5 +35,10 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:rb_p
 mkdir -p tools/_build
 [ -x tools/_build/mma_rate ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I dict_tts_b200/csrc -o tools/_build/mma_rate tools/mma_rate.cu
 ./tools/_build/mma_rate > gpurun_out/${TAG}_mma_rate.log 2>&1; echo "mma_rate rc=$?"
+python tools/prof_decode.py --iters 20 2>&1 | tail -4 | tee gpurun_out/${TAG}_decode_times.log
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches_decode.csv \
+  python tools/prof_decode.py --ncu > /dev/null 2>&1; echo "ncu decode rc=$?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:flow_fused -c 1 -o gpurun_out/${TAG}_flow_fused -f \
+  python tools/prof_decode.py --ncu > /dev/null 2>&1; echo "ncu flow rc=$?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:s2pa_stream -c 1 -o gpurun_out/${TAG}_s2pa_stream -f \
   python tools/prof_acoustic.py --iters 0 --alias > /dev/null 2>&1; echo "ncu s2pa rc=$?"
