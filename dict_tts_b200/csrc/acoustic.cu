@@ -132,7 +132,7 @@ int pack_encoder(dtts_acoustic* h, const std::string& p, EncoderW* e, cudaStream
 }
 
 int pack_wn(dtts_acoustic* h, const std::string& p, int hidden, int n_layers, int K, int gin, WNW* wn,
-            cudaStream_t s) {
+            cudaStream_t s, bool gated) {
   DTTS_TRY(pack(h, p + ".cond_layer", 2 * hidden * n_layers, gin, 1, true, &wn->cond, s));
   for (int i = 0; i < n_layers; ++i) {
     ConvW a, r;
@@ -150,6 +150,36 @@ int pack_wn(dtts_acoustic* h, const std::string& p, int hidden, int n_layers, in
     }
   }
   DTTS_TRY(tc_pack1(h, p + ".cond_layer", true, 2 * hidden * n_layers, gin, 1, 0, &wn->t_cond, s));
+  const int Ng = pick_n(2 * hidden);
+  if (gated && h->precision && Ng % 64 == 0 && hidden % (Ng / 2) == 0) {
+    // gate in the epilogue (TcConvParams::gate): in_layers and cond_layer once more with [tanh | sigmoid] halves per N block
+    const size_t in_n = (size_t)2 * hidden * hidden * K, cond_n = (size_t)2 * hidden * n_layers * gin;
+    for (int i = 0; i < n_layers; ++i) {
+      const std::string q = p + ".in_layers." + std::to_string(i);
+      const float* w = h->tab.get(q + ".weight", in_n);
+      const float* b = h->tab.get(q + ".bias", 2 * hidden);
+      float* wp = h->pool.take(in_n);
+      float* bp = h->pool.take(2 * hidden);
+      if (!w || !b) return DTTS_ERR_MISSING_WEIGHT;
+      if (!wp || !bp) return fail(DTTS_ERR_CUDA, "weight pool exhausted");
+      DTTS_CUDA(permute_gate_rows(w, wp, 1, hidden, Ng, (long)hidden * K, s));
+      DTTS_CUDA(permute_gate_rows(b, bp, 1, hidden, Ng, 1, s));
+      TcConvW t;
+      const float* wpc = wp;
+      DTTS_TRY(tc_pack(h, &wpc, 1, bp, 2 * hidden, hidden, K, 0, Ng, &t, s));
+      wn->t_in_g.push_back(t);
+    }
+    const float* cw = h->tab.get(p + ".cond_layer.weight", cond_n);
+    const float* cb = h->tab.get(p + ".cond_layer.bias", (uint64_t)2 * hidden * n_layers);
+    float* cwp = h->pool.take(cond_n);
+    float* cbp = h->pool.take((size_t)2 * hidden * n_layers);
+    if (!cw || !cb) return DTTS_ERR_MISSING_WEIGHT;
+    if (!cwp || !cbp) return fail(DTTS_ERR_CUDA, "weight pool exhausted");
+    DTTS_CUDA(permute_gate_rows(cw, cwp, n_layers, hidden, Ng, gin, s));
+    DTTS_CUDA(permute_gate_rows(cb, cbp, n_layers, hidden, Ng, 1, s));
+    const float* cwpc = cwp;
+    DTTS_TRY(tc_pack(h, &cwpc, 1, cbp, 2 * hidden * n_layers, gin, 1, 0, wn->t_cond.N, &wn->t_cond_g, s));
+  }
   return DTTS_OK;
 }
 
@@ -220,20 +250,28 @@ void run_encoder(dtts_acoustic* h, const EncoderW& E, float* x, float* hbuf, flo
 
 // WN.forward with x_mask = 1 (modules/commons/wavenet.py:54-78).  hx [B,hidden,T] is updated in place,
 // skip [B,hidden,T] receives the output.
+// x_planes_ready: tc->P[1] already holds hx as operand planes with a zeroed halo (its producer wrote them);
+// skip_po (optional): receives the final skip sum as operand planes (the consumer's staging launch is then not needed).
 void run_wn(const WNW& W, int hidden, int K, float* hx, const float* g, int gin, float* cond, float* a, float* acts,
-            float* skip, int B, int T, Launcher& L, TcRun* tc) {
+            float* skip, int B, int T, Launcher& L, TcRun* tc, bool x_planes_ready = false, Planes* skip_po = nullptr) {
   cudaStream_t s = L.stream;
   const int n = (int)W.in_layers.size();
   if (tc) {
     Planes &Pg = tc->P[0], &Px = tc->P[1], &Pa = tc->P[2];
+    const bool gate_epi = ac_fuse_enabled() && (int)W.t_in_g.size() == n && W.t_cond_g.w;
     tc->stage_nct(Pg, g, gin, T);
-    tc->conv_nct(Pg, W.t_cond, cond, T, 1, 0, TcRun::Epi());
-    tc->stage_nct(Px, hx, hidden, T);                                   // halo zeroed once; epilogues refresh rows [0,T)
+    tc->conv_nct(Pg, gate_epi ? W.t_cond_g : W.t_cond, cond, T, 1, 0, TcRun::Epi());
+    if (!x_planes_ready) tc->stage_nct(Px, hx, hidden, T);              // halo zeroed once; epilogues refresh rows [0,T)
     for (int i = 0; i < n; ++i) {
       TcRun::Epi ea;
       ea.res = cond + (size_t)2 * hidden * i * T; ea.r_bs = (long)W.cond.C_out * T; ea.r_cs = T; ea.r_ts = 1;
-      tc->conv_nct(Px, W.t_in[i], a, T, 1, K / 2, ea);
-      L(wn_gate_planes(a, B, hidden, T, tc->out_of(Pa, hidden, T, false), s));
+      if (gate_epi) {                                                     // tanh * sigmoid in the epilogue -> planes Pa
+        ea.gate = 1;
+        tc->conv_nct(Px, W.t_in_g[i], nullptr, T, 1, K / 2, ea, 0, 0, &Pa);
+      } else {
+        tc->conv_nct(Px, W.t_in[i], a, T, 1, K / 2, ea);
+        L(wn_gate_planes(a, B, hidden, T, tc->out_of(Pa, hidden, T, false), s));
+      }
       TcRun::Epi ex, es;
       ex.res = hx; ex.r_bs = (long)hidden * T; ex.r_cs = T; ex.r_ts = 1;
       es.accumulate = (i > 0);
@@ -241,7 +279,7 @@ void run_wn(const WNW& W, int hidden, int K, float* hx, const float* g, int gin,
         tc->conv_nct(Pa, W.t_rs[i], hx, T, 1, 0, ex, 0, 1, &Px);        // x = x + rs[:hidden]  (fp32 + planes)
         tc->conv_nct(Pa, W.t_rs[i], skip, T, 1, 0, es, 1, 1);           // out += rs[hidden:]
       } else {
-        tc->conv_nct(Pa, W.t_rs[i], skip, T, 1, 0, es, 0, 1);
+        tc->conv_nct(Pa, W.t_rs[i], skip, T, 1, 0, es, 0, 1, skip_po);
       }
     }
     return;
@@ -402,7 +440,7 @@ int pack_decoder(dtts_acoustic* h, cudaStream_t s) {
     h->dec_pre.w = dst; h->dec_pre.bias = b; h->dec_pre.C_out = H; h->dec_pre.C_in = d->latent;
     h->dec_pre.ktaps = 1; h->dec_pre.phases = 4;
   }
-  DTTS_TRY(pack_wn(h, "fvae.decoder.wn", H, d->dec_layers, d->dec_kernel, H, &h->dec_wn, s));
+  DTTS_TRY(pack_wn(h, "fvae.decoder.wn", H, d->dec_layers, d->dec_kernel, H, &h->dec_wn, s, true));
   DTTS_TRY(pack(h, "fvae.decoder.out_proj", d->n_mel, H, 1, true, &h->dec_out, s));
   if (h->precision) {
     // out_proj: C_out = n_mel (80) padded with zero rows to a multiple of 32 for the MMA's N
@@ -458,10 +496,12 @@ extern "C" int dtts_acoustic_create(const dtts_acoustic_desc* d, const float* ar
   if (rc != DTTS_OK) { delete h; return rc; }
   size_t total = 0;
   for (auto& e : h->tab.entries) total += e.second.second + 64;
-  rc = h->pool.reserve(total + 2 * 1024 * 1024);
+  // slack: q|k|v side-by-side copies, the space-to-depth g_pre_net weight, the gate-permuted decoder WaveNet, alignment
+  const size_t gate_extra = (size_t)d->dec_layers * 2 * d->hidden * d->hidden * (d->dec_kernel + 1) + 4096;
+  rc = h->pool.reserve(total + 2 * 1024 * 1024 + gate_extra);
   if (rc != DTTS_OK) { delete h; return rc; }
   if (h->precision) {
-    h->tc_cap = 2 * total + (1 << 20);               // two 16-bit planes per weight
+    h->tc_cap = 2 * total + (1 << 20) + 2 * gate_extra;   // two 16-bit planes per weight (+ the gate-permuted copies)
     if (d->s2pa_route == 1) h->tc_cap += (size_t)4 * d->hidden * d->dict_dim + 256;   // second copy of W_k, W_v
     cudaError_t e = cudaMalloc((void**)&h->tc_pool, h->tc_cap * sizeof(tc16));
     if (e == cudaSuccess) e = tc_conv_init();
@@ -921,12 +961,20 @@ extern "C" int dtts_decode_mel(dtts_acoustic* h, const float* g, const float* z_
     }
   }
   // decoder (fvae_semantics.py:53-58)
-  L(launch_conv1d_f32(convT_params(z_p, T4, h->dec_pre, x, T, 4, 0), B, s));
-  run_wn(h->dec_wn, H, d.dec_kernel, x, g, H, cond, a, acts, skip, B, T, L, tc);
+  const bool fuse_dec = tc && ac_fuse_enabled() && H % 8 == 0 && (d.latent == 16 || d.latent == 8);
+  if (fuse_dec) {
+    // ConvTranspose1d(latent -> H, k = 4, s = 4) straight into the fp32 stream AND the operand planes of the first
+    // WaveNet convolution (one launch instead of the generic fp32 kernel + a staging pass)
+    L(fvae_pre_net_planes(z_p, h->dec_pre.w, h->dec_pre.bias, B, d.latent, H, T4, x, tc->out_of(tc->P[1], H, T, true), s));
+    run_wn(h->dec_wn, H, d.dec_kernel, x, g, H, cond, a, acts, skip, B, T, L, tc, true, &tc->P[0]);
+  } else {
+    L(launch_conv1d_f32(convT_params(z_p, T4, h->dec_pre, x, T, 4, 0), B, s));
+    run_wn(h->dec_wn, H, d.dec_kernel, x, g, H, cond, a, acts, skip, B, T, L, tc);
+  }
   if (tc) {
     TcRun::Epi eo;
     eo.c_valid = d.n_mel;
-    tc->stage_nct(tc->P[0], skip, H, T);
+    if (!fuse_dec) tc->stage_nct(tc->P[0], skip, H, T);     // (fused: the last res_skip epilogue wrote the planes)
     tc->conv(tc->P[0], h->t_out, 0, 0, mel, (long)T * d.n_mel, 1, d.n_mel, T, 1, 0, eo);    // mel_out is [B,T,80]
   } else {
     ConvParams p = conv_params(skip, T, h->dec_out, 0, d.n_mel, mel, T, 1, 1, 0);

@@ -29,6 +29,10 @@ struct WNW {
   std::vector<ConvW> in_layers, res_skip;
   TcConvW t_cond;
   std::vector<TcConvW> t_in, t_rs;      // t_rs blocks of `hidden` channels: [0] -> x update, [1] -> skip
+  // the same in_layers / cond_layer with their output channels permuted so that every N block holds [N/2 tanh channels |
+  // the N/2 sigmoid channels that gate them]: the gate then runs in the convolution epilogue (empty: not built)
+  std::vector<TcConvW> t_in_g;
+  TcConvW t_cond_g;
 };
 struct FlowW {
   ConvW pre, post;
@@ -109,6 +113,7 @@ struct TcRun {
     const float* mask = nullptr; int m_bs = 0;
     int act = 0; float alpha = 1.f, post = 1.f; int accumulate = 0;
     int c_valid = 0;              // > 0: number of real output channels (the rest is zero padding)
+    int gate = 0;                 // 1: WaveNet gate in the epilogue (TcConvParams::gate): `po` receives C_out / 2 channels
   };
   bool shape(Planes& p, int C, int T) {
     p.C = C; p.T = T; p.rows = tc_rows(T);
@@ -157,8 +162,9 @@ struct TcRun {
     p.mask = e.mask; p.m_bs = e.m_bs; p.act = e.act; p.alpha = e.alpha; p.post = e.post; p.accumulate = e.accumulate;
     p.slope = 1.f;
     if (e.c_valid > 0) p.c_valid = e.c_valid;
+    p.gate = e.gate;
     if (po) {
-      if (!shape(*po, sub.C_out, T_out)) return;
+      if (!shape(*po, e.gate ? sub.C_out / 2 : sub.C_out, T_out)) return;
       p.o_hi = po->hi; p.o_lo = h->mode.a_planes == 2 ? po->lo : nullptr;
       p.op_bs = (long)po->C * po->rows; p.op_rows = po->rows; p.op_pad = TC_PADF;
     }
@@ -186,7 +192,8 @@ struct TcRun {
 int pack_qkv(dtts_acoustic* h, const std::string names[3], const std::string* bias_names, ConvW* qkv, TcConvW* t_qkv,
              cudaStream_t s);
 int pack_encoder(dtts_acoustic* h, const std::string& p, EncoderW* e, cudaStream_t s);
-int pack_wn(dtts_acoustic* h, const std::string& p, int hidden, int n_layers, int K, int gin, WNW* wn, cudaStream_t s);
+int pack_wn(dtts_acoustic* h, const std::string& p, int hidden, int n_layers, int K, int gin, WNW* wn, cudaStream_t s,
+            bool gated = false);
 int pack_dur_predictor(dtts_acoustic* h, int c_in, cudaStream_t s);
 int pack_decoder(dtts_acoustic* h, cudaStream_t s);
 // DurationPredictor.forward (portaspeech/model.py:58-66) + softplus head: dur_in [B,H,Tw] channel-first, keep [B,Tw];

@@ -72,15 +72,6 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// tanh(t) * sigmoid(s) without the slow paths of tanhf / expf (a quarter of the kernel's issue slots went to their
-// range-check branches): tanh(t) = 1 - 2 / (1 + e^{2t}), both exponentials on ex2.approx (2 ulp) and the divisions as
-// approximate reciprocals; absolute error ~2e-7 per gate, the saturated ends are exact (e^{2t} = inf -> 1, 0 -> -1).
-__device__ __forceinline__ float gate_fast(float t, float s) {
-  const float th = 1.f - __fdividef(2.f, 1.f + __expf(2.f * t));
-  const float sg = __fdividef(1.f, 1.f + __expf(-s));
-  return th * sg;
-}
-
 __global__ void __launch_bounds__(kFThreads, 1) flow_fused_kernel(const FlowKernelArgs k) {
   extern __shared__ __align__(128) uint8_t smem[];
   const FlowFusedParams& p = k.p;

@@ -18,6 +18,9 @@ cudaError_t reverse_vec(const float* in, float* out, int n, cudaStream_t s);
 // stride-4 / pad-2 / k=8 Conv1d weight -> the stride-1 / pad-1 / k=3 weight over the 4x space-to-depth input
 cudaError_t repack_s2d4(const float* w, float* out, int C_out, int C_in, cudaStream_t s);
 cudaError_t fill_f32(float* p, float v, size_t n, cudaStream_t s);
+// WaveNet in_layers / cond_layer rows ([groups][tanh half | sigmoid half][row_len]) re-ordered per N-row block as
+// [N/2 tanh | the N/2 sigmoid rows that gate them] (TcConvParams::gate)
+cudaError_t permute_gate_rows(const float* in, float* out, int groups, int hidden, int N, long row_len, cudaStream_t s);
 
 // ---- text encoder ----
 // x[b,c,t] = emb[tok[b,t]][c]*scale ; lens[b] = #(tok>0) ; seq_mask[b,t] = t < lens[b] ; tok_mask[b,t] = tok>0
@@ -108,6 +111,12 @@ cudaError_t ps_word_attention(const float* q, const float* kv, const int64_t* me
                               int H, int T, int Tp, float* attn, float* ctx, cudaStream_t s);
 cudaError_t bct_to_btc(const float* in, float* out, int B, int C, int T, cudaStream_t s);
 cudaError_t nonpad_mask(const int64_t* idx, float* mask, size_t n, cudaStream_t s);
+
+// ---- FVAE decoder pre_net ----
+// ConvTranspose1d(C_in -> C_out, kernel = stride = 4) (fvae_semantics.py:40-41,53): out[b,co,4q+ph] = bias[co] +
+// sum_ci w[ph][ci][co] * z[b,ci,q]  (w in repack_convT layout) -> fp32 [B,C_out,4*Tq] and operand planes (halo zeroed)
+cudaError_t fvae_pre_net_planes(const float* z, const float* w, const float* bias, int B, int C_in, int C_out, int Tq,
+                                float* out, const PlaneOut& po, cudaStream_t s);
 
 // ---- WaveNet gate ----
 // acts[b,c,t] = tanh(a[b,c,t]) * sigmoid(a[b,c+H,t]),  a [B,2H,T]

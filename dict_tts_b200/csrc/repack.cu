@@ -80,3 +80,25 @@ cudaError_t repack_s2d4(const float* w, float* out, int C_out, int C_in, cudaStr
 }
 
 }  // namespace dtts
+
+namespace dtts {
+// Rows of a [groups * 2 * hidden][row_len] matrix (groups = WaveNet layers; rows [0, hidden) of a group are the tanh
+// channels, [hidden, 2 * hidden) the sigmoid channels) re-ordered so that every block of N rows holds N/2 tanh channels
+// followed by the N/2 sigmoid channels that gate them.
+__global__ void permute_gate_rows_kernel(const float* __restrict__ in, float* __restrict__ out, int groups, int hidden,
+                                         int N, long row_len) {
+  const long n = (long)groups * 2 * hidden * row_len;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / row_len, c = i - r * row_len;
+    const int g = (int)(r / (2 * hidden)), rr = (int)(r - (long)g * 2 * hidden);
+    const int blk = rr / N, j = rr - blk * N;
+    const int src = j < N / 2 ? blk * (N / 2) + j : hidden + blk * (N / 2) + (j - N / 2);
+    out[i] = in[((long)g * 2 * hidden + src) * row_len + c];
+  }
+}
+cudaError_t permute_gate_rows(const float* in, float* out, int groups, int hidden, int N, long row_len, cudaStream_t s) {
+  if (N % 2 || (2 * hidden) % N || hidden % (N / 2)) return cudaErrorInvalidValue;
+  permute_gate_rows_kernel<<<256, 256, 0, s>>>(in, out, groups, hidden, N, row_len);
+  return cudaGetLastError();
+}
+}  // namespace dtts

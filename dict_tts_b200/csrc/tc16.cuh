@@ -33,6 +33,15 @@ __device__ __forceinline__ void split2(float a0, float a1, int fmt, uint32_t& hw
   lw = pack2(a0 - back16(hw & 0xFFFFu, fmt), a1 - back16(hw >> 16, fmt), fmt);
 }
 
+// tanh(t) * sigmoid(s) (the WaveNet gate, wavenet.py:64-70) without the slow paths of tanhf / expf: tanh(t) =
+// 1 - 2 / (1 + e^{2t}), both exponentials on ex2.approx (2 ulp), the divisions as approximate reciprocals; absolute error
+// ~2e-7 per gate, the saturated ends are exact (e^{2t} = inf -> 1, 0 -> -1).
+__device__ __forceinline__ float gate_fast(float t, float s) {
+  const float th = 1.f - __fdividef(2.f, 1.f + __expf(2.f * t));
+  const float sg = __fdividef(1.f, 1.f + __expf(-s));
+  return th * sg;
+}
+
 // FP8 lo-plane correction (tc_conv.cuh, TcMode::lo8): the weights of such a layer are packed x 2^10 -- fp16(w * 2^10) for the
 // hi plane, e5m2((w - fp16(w)) * 2^10) for the lo plane, which puts w_lo (2^-12 of w) into the e5m2 range -- and the epilogue
 // multiplies the accumulator by 2^-10.  The activations need no scale: their e5m2 copy is the high byte of the fp16 value.

@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
       };
       int m = 0, cc = half;
       while (cc >= ncc) { cc -= ncc; ++m; }
-      if (half < nitems) load_res(m, cc, rc);
+      if (half < nitems && !p.gate) load_res(m, cc, rc);
 
       mbar_wait(acc_full(as), (t_it >> 1) & 1);
       tc_fence_after();
@@ -635,6 +635,64 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
           else mbar_arrive(acc_empty(as));
         }
         continue;
+      }
+      if constexpr (!PAIR) {                        // (not in the CTA-pair build: the vocoder's epilogue keeps its registers)
+      if (p.gate) {
+        // ---- WaveNet gate (wavenet.py:64-70) on the accumulators: acts never exist as a [B, 2H, T] fp32 tensor
+        const int nh = N / 64;                         // 32-channel gate items per sub-tile
+        const int cbase = (tc.g / p.phases) * (N / 2);
+        for (int idx = half; idx < p.NACC * nh; idx += 2) {
+          const int gm = idx / nh, gc = idx - gm * nh;
+          int t; bool ok;
+          item_row(gm, t, ok);
+          const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256 + gm * NM + gc * 32);
+          const int ct = co_off + gc * 32, cs = ct + N / 2;
+          const size_t prow = (size_t)tc.b * p.op_bs + ((size_t)((cbase + gc * 32) / 8) * p.op_rows + p.op_pad + (ok ? t : 0)) * 8;
+#pragma unroll 1
+          for (int hh = 0; hh < 2; ++hh) {                // 16 channels at a time (register pressure)
+            uint32_t ra[16], rb[16];
+            __syncwarp();                                 // tcgen05.ld is .sync.aligned
+            tmem_ld16_nowait(tcol + (uint32_t)(16 * hh), ra);
+            tmem_ld16_nowait(tcol + (uint32_t)(N / 2 + 16 * hh), rb);
+            float rt[16], rs[16];
+            if (resb && ok) {
+              const float* pt = resb + (size_t)(ct + 16 * hh) * p.r_cs + (size_t)t * p.r_ts;
+              const float* ps = resb + (size_t)(cs + 16 * hh) * p.r_cs + (size_t)t * p.r_ts;
+#pragma unroll
+              for (int k = 0; k < 16; ++k) { rt[k] = pt[(size_t)k * p.r_cs]; rs[k] = ps[(size_t)k * p.r_cs]; }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 16; ++k) rt[k] = rs[k] = 0.f;
+            }
+            tmem_ld_wait();
+            if (!ok) continue;
+            float v[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+              v[k] = gate_fast(__uint_as_float(ra[k]) + bias_s[ct + 16 * hh + k] + rt[k],
+                               __uint_as_float(rb[k]) + bias_s[cs + 16 * hh + k] + rs[k]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (split) split2(v[8 * h + 2 * e], v[8 * h + 2 * e + 1], fmt, hw[e], lw[e]);
+                else hw[e] = pack2(v[8 * h + 2 * e], v[8 * h + 2 * e + 1], fmt);
+              }
+              const size_t off = prow + (size_t)(2 * hh + h) * p.op_rows * 8;
+              *reinterpret_cast<uint4*>(p.o_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              if (split) *reinterpret_cast<uint4*>(p.o_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (pair && rank != 0) mbar_arrive_remote(acc_empty(as), 0);
+          else mbar_arrive(acc_empty(as));
+        }
+        continue;
+      }
       }
       // The item loop exists twice: with a residual (conv2 of a ResBlock: the next item's residual is prefetched while
       // this one is processed -- that ordering is what keeps those HBM-bound layers at 6 TB/s) and without one (conv1:
@@ -1185,6 +1243,8 @@ cudaError_t launch_tc_conv(TcConvParams p, int B, cudaStream_t stream) {
   if (p.TG < 1 || p.w_stages < 1 || p.N % 32 != 0 || p.N > 256 || p.KC % 16 != 0 || p.C_in % p.KC != 0 ||
       p.N * p.nblocks > kMaxBias || p.NACC * p.NM > 256 || (p.stack && (p.w_planes != 1 || p.NM != 2 * p.N)) ||
       (!p.stack && p.NM != p.N))
+    return cudaErrorInvalidConfiguration;
+  if (p.gate && (p.N % 64 || !p.o_hi || !p.o_nct || p.il_u || p.stack || p.pair || p.phases != 1 || p.ot_mul != 1))
     return cudaErrorInvalidConfiguration;
   const int max_off = p.min_off + (p.RA - p.MT);
   if (p.a_pad + p.min_off < 0 || p.a_pad + p.ntiles * p.MT + max_off > p.a_rows) return cudaErrorInvalidValue;

@@ -152,6 +152,10 @@ struct TcConvParams {
   int act;                       // 0: none, 1: ReLU, 3: exact GELU (applied to conv + bias; codes of conv1d_f32.cuh)
   float alpha;                   // out = post * (act(conv + bias) * alpha * mask + res)  (+ out if accumulate)
   int c_valid;                   // o_nct: only output channels < c_valid are stored (weights zero-padded to N % 32 == 0)
+  // WaveNet gate fused into the epilogue (o_nct residual = the conditioning slice, o_hi / o_lo required, o32 unused): the
+  // weights are packed so that column j < N/2 of a block is a tanh channel and column j + N/2 its sigmoid channel;
+  // planes channel (block * N/2 + j) = tanh(conv_j + bias + res) * sigmoid(conv_{j+N/2} + bias + res).  N % 64 == 0.
+  int gate;
   int a_stages, w_stages;
   int TG;                        // taps per weight stage
   int ntiles, B;                 // time tiles per (group, batch item); batch size (set by the launcher)

@@ -816,6 +816,95 @@ cudaError_t wn_gate_planes(const float* a, int B, int H, int T, const PlaneOut& 
   return cudaGetLastError();
 }
 
+// FVAE decoder pre_net: block = (32 latent positions = 128 output frames, batch item), 256 threads = 8 warps, lane = latent
+// position, warp w takes the 8-channel slabs w, w + 8, ...  A thread computes ALL FOUR phases of its position, so that
+// what it stores are whole 32-byte sectors -- four consecutive fp32 samples of a channel, two consecutive 16-byte plane
+// rows -- (a phase per warp wrote quarter sectors: L2 read every sector back from HBM to merge, 41 us; a phase per lane
+// with a rolled loop was a chain of dependent cache misses, 64 us); weight reads are warp-uniform broadcasts.
+__device__ __forceinline__ void st_rows2(tc16* p, const uint32_t (&a)[4], const uint32_t (&b)[4]) {   // 32 B, 32-B aligned
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]),
+               "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3])
+               : "memory");
+}
+template <int CI>
+__global__ void __launch_bounds__(256) fvae_pre_net_planes_kernel(const float* __restrict__ z, const float* __restrict__ w,
+                                                                  const float* __restrict__ bias, int C_out, int Tq,
+                                                                  float* __restrict__ out, PlaneOut po) {
+  extern __shared__ float4 wsm4[];                   // the whole weight [4][CI][C_out]: fetched once, all loads in flight
+  griddep_launch_if_resident();
+  const int b = blockIdx.y, q = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int warp = threadIdx.x >> 5;
+  const int T = 4 * Tq;
+  {
+    const float4* wg = reinterpret_cast<const float4*>(w);
+    for (int i = threadIdx.x; i < CI * C_out; i += 256) wsm4[i] = __ldg(wg + i);      // 4 * CI * C_out floats
+  }
+  float zv[CI];
+#pragma unroll
+  for (int ci = 0; ci < CI; ++ci) zv[ci] = q < Tq ? z[((size_t)b * CI + ci) * Tq + q] : 0.f;
+  __syncthreads();
+  const float* ws = reinterpret_cast<const float*>(wsm4);
+  const int slabs = C_out / 8;
+  for (int sl = warp; sl < slabs; sl += 8) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + sl * 8));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + sl * 8 + 4));
+    float v[4][8];
+#pragma unroll
+    for (int ph = 0; ph < 4; ++ph) {
+      const float* wp = ws + (size_t)ph * CI * C_out + sl * 8;
+      float4 w0[CI], w1[CI];
+#pragma unroll
+      for (int ci = 0; ci < CI; ++ci) {
+        w0[ci] = *reinterpret_cast<const float4*>(wp + (size_t)ci * C_out);
+        w1[ci] = *reinterpret_cast<const float4*>(wp + (size_t)ci * C_out + 4);
+      }
+      v[ph][0] = b0.x; v[ph][1] = b0.y; v[ph][2] = b0.z; v[ph][3] = b0.w;
+      v[ph][4] = b1.x; v[ph][5] = b1.y; v[ph][6] = b1.z; v[ph][7] = b1.w;
+#pragma unroll
+      for (int ci = 0; ci < CI; ++ci) {
+        v[ph][0] = fmaf(w0[ci].x, zv[ci], v[ph][0]); v[ph][1] = fmaf(w0[ci].y, zv[ci], v[ph][1]);
+        v[ph][2] = fmaf(w0[ci].z, zv[ci], v[ph][2]); v[ph][3] = fmaf(w0[ci].w, zv[ci], v[ph][3]);
+        v[ph][4] = fmaf(w1[ci].x, zv[ci], v[ph][4]); v[ph][5] = fmaf(w1[ci].y, zv[ci], v[ph][5]);
+        v[ph][6] = fmaf(w1[ci].z, zv[ci], v[ph][6]); v[ph][7] = fmaf(w1[ci].w, zv[ci], v[ph][7]);
+      }
+    }
+    if (q < Tq) {
+      float4* op = reinterpret_cast<float4*>(out + ((size_t)b * C_out + sl * 8) * T + 4 * q);   // T % 4 == 0: 16-B aligned
+#pragma unroll
+      for (int e = 0; e < 8; ++e) op[(size_t)e * (T / 4)] = make_float4(v[0][e], v[1][e], v[2][e], v[3][e]);
+      if (po.hi) {
+        uint32_t hw[4][4], lw[4][4];
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (po.lo) split2(v[ph][2 * e], v[ph][2 * e + 1], po.fmt, hw[ph][e], lw[ph][e]);
+            else hw[ph][e] = pack2(v[ph][2 * e], v[ph][2 * e + 1], po.fmt);
+          }
+        const size_t off = (((size_t)b * slabs + sl) * po.rows + po.pad + 4 * q) * 8;     // pad % 2 == 0: 32-B aligned rows
+        st_rows2(po.hi + off, hw[0], hw[1]);
+        st_rows2(po.hi + off + 16, hw[2], hw[3]);
+        if (po.lo) {
+          st_rows2(po.lo + off, lw[0], lw[1]);
+          st_rows2(po.lo + off + 16, lw[2], lw[3]);
+        }
+      }
+    }
+  }
+  if (po.hi && po.zero_halo && blockIdx.x == 0) zero_halo_rows(po, b, C_out, T);
+}
+cudaError_t fvae_pre_net_planes(const float* z, const float* w, const float* bias, int B, int C_in, int C_out, int Tq,
+                                float* out, const PlaneOut& po, cudaStream_t s) {
+  if ((C_in != 16 && C_in != 8) || C_out % 8 || B <= 0 || Tq <= 0 || (po.hi && ((po.pad & 1) || (po.rows & 1))))
+    return cudaErrorInvalidValue;
+  dim3 grid(cdiv(Tq, 32), B);
+  const size_t smem = (size_t)4 * C_in * C_out * sizeof(float);
+  if (smem > 48 * 1024) return cudaErrorInvalidConfiguration;
+  if (C_in == 16) fvae_pre_net_planes_kernel<16><<<grid, 256, smem, s>>>(z, w, bias, C_out, Tq, out, po);
+  else fvae_pre_net_planes_kernel<8><<<grid, 256, smem, s>>>(z, w, bias, C_out, Tq, out, po);
+  return cudaGetLastError();
+}
+
 // 1x1 convolution with a handful of channels on one side (the 8 <-> 64 channel pre / post projections of a coupling
 // layer, glow_modules.py:113-127): out[b,co,t] = alpha * (sum_ci w[ci][co] * x[b,ci,t] + bias[co]) + res[b,co,t].
 // One thread per (b, t) walks the output channels eight at a time; w is the packed [C_in][C_out] layout of ConvW.
