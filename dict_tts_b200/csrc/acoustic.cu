@@ -192,11 +192,17 @@ void run_encoder(dtts_acoustic* h, const EncoderW& E, float* x, float* hbuf, flo
     Planes &P0 = tc->P[0], &P1 = tc->P[1];
     TcRun::Epi res_x;
     res_x.res = x; res_x.r_bs = (long)H * Tw; res_x.r_cs = Tw; res_x.r_ts = 1;
-    for (size_t i = 0; i < E.layers.size(); ++i) {
+    // Fused form: the LayerNorm that follows a residual update runs in the epilogue of the convolution that makes it
+    // (O -> LN2, FFN2 -> LN1 of the next layer / the last LN): one standalone LayerNorm per encoder instead of nine
+    const size_t nl = E.layers.size();
+    const bool fuse_ln = ac_fuse_enabled() && nl > 0 && TcRun::ln_fusable(E.layers[0].t_o, Tw) &&
+                         TcRun::ln_fusable(E.layers[0].t_ffn2, Tw);
+    for (size_t i = 0; i < nl; ++i) {
       const EncLayerW& W = E.layers[i];
       // x = x * x_mask ; LN1 -> operand planes of the fused q|k|v projection
-      L(channel_layernorm_planes(x, x, nullptr, W.g1, W.b1, 1e-4f, seq_mask, nullptr, B, H, Tw,
-                                 tc->out_of(P0, H, Tw, false), s));
+      if (!fuse_ln || i == 0)
+        L(channel_layernorm_planes(x, x, nullptr, W.g1, W.b1, 1e-4f, seq_mask, nullptr, B, H, Tw,
+                                   tc->out_of(P0, H, Tw, fuse_ln), s));       // (fused: halo zeroed once, for every FFN)
       tc->conv_nct(P0, W.t_qkv, qkv, Tw, 1, 0, TcRun::Epi());
       if (Tw <= 64) {
         L(self_attention_planes(qkv, qkv + (size_t)H * Tw, qkv + (size_t)2 * H * Tw, seq_mask, nullptr, B, H, Tw,
@@ -205,20 +211,37 @@ void run_encoder(dtts_acoustic* h, const EncoderW& E, float* x, float* hbuf, flo
         L(self_attention(qkv, qkv + (size_t)H * Tw, qkv + (size_t)2 * H * Tw, seq_mask, att, B, H, Tw, h->d.n_heads, s));
         tc->stage_nct(P0, att, H, Tw);
       }
-      tc->conv_nct(P0, W.t_o, x, Tw, 1, 0, res_x);
-      // LN2 (* x_mask) -> planes with zeroed halo (the FFN's first convolution has k = 5)
-      L(channel_layernorm_planes(x, nullptr, nullptr, W.g2, W.b2, 1e-4f, nullptr, seq_mask, B, H, Tw,
-                                 tc->out_of(P0, H, Tw, true), s));
+      if (fuse_ln) {
+        TcRun::Epi eo = res_x;                                                // x += O(att) ; LN2(x) * mask -> P0 (rows [0,T))
+        eo.ln_gamma = W.g2; eo.ln_beta = W.b2; eo.ln_eps = 1e-4f; eo.ln_out_mask = seq_mask;
+        tc->conv_nct(P0, W.t_o, x, Tw, 1, 0, eo, 0, 0, &P0);
+      } else {
+        tc->conv_nct(P0, W.t_o, x, Tw, 1, 0, res_x);
+        // LN2 (* x_mask) -> planes with zeroed halo (the FFN's first convolution has k = 5)
+        L(channel_layernorm_planes(x, nullptr, nullptr, W.g2, W.b2, 1e-4f, nullptr, seq_mask, B, H, Tw,
+                                   tc->out_of(P0, H, Tw, true), s));
+      }
       TcRun::Epi e1;
       e1.act = 1; e1.mask = seq_mask; e1.m_bs = Tw;
       tc->conv_nct(P0, W.t_ffn1, nullptr, Tw, 1, K / 2, e1, 0, 0, &P1);      // relu(.) * mask straight into planes
       TcRun::Epi e2 = res_x;
       e2.mask = seq_mask; e2.m_bs = Tw;
-      tc->conv_nct(P1, W.t_ffn2, x, Tw, 1, 0, e2);
+      if (fuse_ln) {
+        if (i + 1 < nl) {                    // next layer: x = x * x_mask ; LN1(x) -> P0
+          e2.ln_gamma = E.layers[i + 1].g1; e2.ln_beta = E.layers[i + 1].b1; e2.ln_in_mask = seq_mask;
+        } else {                             // last LN: fp32 [B,H,T] for the consumers and planes for the S2PA query projection
+          e2.ln_gamma = E.last_g; e2.ln_beta = E.last_b; e2.ln_out_mask = seq_mask; e2.ln_y = hbuf;
+        }
+        e2.ln_eps = 1e-4f;
+        tc->conv_nct(P1, W.t_ffn2, x, Tw, 1, 0, e2, 0, 0, &P0);
+      } else {
+        tc->conv_nct(P1, W.t_ffn2, x, Tw, 1, 0, e2);
+      }
     }
     // last LN: fp32 [B,H,T] for the consumers and planes (P0) for the S2PA query projection
-    L(channel_layernorm_planes(x, nullptr, hbuf, E.last_g, E.last_b, 1e-4f, nullptr, seq_mask, B, H, Tw,
-                               tc->out_of(P0, H, Tw, false), s));
+    if (!fuse_ln)
+      L(channel_layernorm_planes(x, nullptr, hbuf, E.last_g, E.last_b, 1e-4f, nullptr, seq_mask, B, H, Tw,
+                                 tc->out_of(P0, H, Tw, false), s));
     return;
   }
   for (size_t i = 0; i < E.layers.size(); ++i) {

@@ -114,7 +114,12 @@ struct TcRun {
     int act = 0; float alpha = 1.f, post = 1.f; int accumulate = 0;
     int c_valid = 0;              // > 0: number of real output channels (the rest is zero padding)
     int gate = 0;                 // 1: WaveNet gate in the epilogue (TcConvParams::gate): `po` receives C_out / 2 channels
+    // channel LayerNorm of the output in the epilogue (TcConvParams::ln_*): `po` receives LN(out) instead of out
+    const float* ln_gamma = nullptr; const float* ln_beta = nullptr; float ln_eps = 0.f;
+    const float* ln_in_mask = nullptr; const float* ln_out_mask = nullptr; float* ln_y = nullptr;
   };
+  // can conv(w) carry a fused LayerNorm over its C_out channels for sequences of T steps?
+  static bool ln_fusable(const TcConvW& w, int T) { return w.C_out == w.N && w.N <= 256 && !w.pair && !w.stack && T <= 128; }
   bool shape(Planes& p, int C, int T) {
     p.C = C; p.T = T; p.rows = tc_rows(T);
     if ((size_t)B * C * p.rows > p.cap) { (*L)(cudaErrorInvalidValue); return false; }
@@ -163,6 +168,9 @@ struct TcRun {
     p.slope = 1.f;
     if (e.c_valid > 0) p.c_valid = e.c_valid;
     p.gate = e.gate;
+    p.ln_gamma = e.ln_gamma; p.ln_beta = e.ln_beta; p.ln_eps = e.ln_eps;
+    p.ln_in_mask = e.ln_in_mask; p.ln_out_mask = e.ln_out_mask; p.ln_y = e.ln_y;
+    if (e.ln_gamma && !e.mask) p.m_bs = T_out;       // the LN masks are [B][T] like the convolution's
     if (po) {
       if (!shape(*po, e.gate ? sub.C_out / 2 : sub.C_out, T_out)) return;
       p.o_hi = po->hi; p.o_lo = h->mode.a_planes == 2 ? po->lo : nullptr;

@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
       };
       int m = 0, cc = half;
       while (cc >= ncc) { cc -= ncc; ++m; }
-      if (half < nitems && !p.gate) load_res(m, cc, rc);
+      if (half < nitems && !p.gate && !p.ln_gamma) load_res(m, cc, rc);
 
       mbar_wait(acc_full(as), (t_it >> 1) & 1);
       tc_fence_after();
@@ -637,6 +637,86 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcConvParams
         continue;
       }
       if constexpr (!PAIR) {                        // (not in the CTA-pair build: the vocoder's epilogue keeps its registers)
+      if (p.ln_gamma) {
+        // ---- residual add + channel LayerNorm in the epilogue (rel_transformer_encoder.py:58-79): the row of a tile is
+        // split between the two warps of a TMEM lane quadrant (32-column chunks half, half + 2, ...); they exchange their
+        // partial sums through shared memory and a 64-thread named barrier
+        float* ln_s = bias_s + 1024;                    // [128 rows][2 halves][2]
+        int t; bool ok;
+        item_row(0, t, ok);
+        const float cm = (p.mask && ok) ? __ldg(p.mask + (size_t)tc.b * p.m_bs + t) : 1.f;
+        const float im = (p.ln_in_mask && ok) ? __ldg(p.ln_in_mask + (size_t)tc.b * p.m_bs + t) : 1.f;
+        float s1 = 0.f, s2 = 0.f;
+        for (int c2 = half; c2 < ncc; c2 += 2) {
+          uint32_t r[32];
+          __syncwarp();
+          tmem_ld32_nowait(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256 + c2 * 32), r);
+          float rr[32];
+          const int n0 = co_off + c2 * 32;
+          if (resb && ok) {
+            const float* rp = resb + (size_t)n0 * p.r_cs + (size_t)t * p.r_ts;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) rr[k] = rp[(size_t)k * p.r_cs];
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) rr[k] = 0.f;
+          }
+          tmem_ld_wait();
+          if (ok) {
+            float* op = o32b + (size_t)n0 * p.o_cs + (size_t)t * p.o_ts;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const float v = ((__uint_as_float(r[k]) + bias_s[n0 + k]) * cm + rr[k]) * im;
+              op[(size_t)k * p.o_cs] = v;
+              s1 += v;
+              s2 = fmaf(v, v, s2);
+            }
+          }
+        }
+        tc_fence_before();                              // the accumulators are not read again
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty(as));
+        const int row = quad * 32 + lane;
+        ln_s[row * 4 + half * 2] = s1;
+        ln_s[row * 4 + half * 2 + 1] = s2;
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
+        const float S1 = ln_s[row * 4] + ln_s[row * 4 + 2], S2 = ln_s[row * 4 + 1] + ln_s[row * 4 + 3];
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");     // both warps have read before the next tile writes
+        const float mean = S1 / (float)N;
+        const float rstd = rsqrtf(fmaxf(S2 / (float)N - mean * mean, 0.f) + p.ln_eps);
+        if (ok) {
+          const float om = p.ln_out_mask ? __ldg(p.ln_out_mask + (size_t)tc.b * p.m_bs + t) : 1.f;
+          for (int c2 = half; c2 < ncc; c2 += 2) {
+            const int n0 = co_off + c2 * 32;
+            const float* op = o32b + (size_t)n0 * p.o_cs + (size_t)t * p.o_ts;      // this thread's own stores
+            float v[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = op[(size_t)k * p.o_cs];
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              v[k] = ((v[k] - mean) * rstd * __ldg(p.ln_gamma + n0 + k) + __ldg(p.ln_beta + n0 + k)) * om;
+            if (p.ln_y) {
+              float* yp = p.ln_y + (size_t)tc.b * p.o32_bs + (size_t)n0 * p.o_cs + (size_t)t * p.o_ts;
+#pragma unroll
+              for (int k = 0; k < 32; ++k) yp[(size_t)k * p.o_cs] = v[k];
+            }
+            const size_t prow = (size_t)tc.b * p.op_bs + ((size_t)(n0 / 8) * p.op_rows + p.op_pad + t) * 8;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (split) split2(v[8 * h + 2 * e], v[8 * h + 2 * e + 1], fmt, hw[e], lw[e]);
+                else hw[e] = pack2(v[8 * h + 2 * e], v[8 * h + 2 * e + 1], fmt);
+              }
+              const size_t off = prow + (size_t)h * p.op_rows * 8;
+              *reinterpret_cast<uint4*>(p.o_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              if (split) *reinterpret_cast<uint4*>(p.o_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+          }
+        }
+        continue;
+      }
       if (p.gate) {
         // ---- WaveNet gate (wavenet.py:64-70) on the accumulators: acts never exist as a [B, 2H, T] fp32 tensor
         const int nh = N / 64;                         // 32-channel gate items per sub-tile
@@ -1243,6 +1323,10 @@ cudaError_t launch_tc_conv(TcConvParams p, int B, cudaStream_t stream) {
   if (p.TG < 1 || p.w_stages < 1 || p.N % 32 != 0 || p.N > 256 || p.KC % 16 != 0 || p.C_in % p.KC != 0 ||
       p.N * p.nblocks > kMaxBias || p.NACC * p.NM > 256 || (p.stack && (p.w_planes != 1 || p.NM != 2 * p.N)) ||
       (!p.stack && p.NM != p.N))
+    return cudaErrorInvalidConfiguration;
+  if (p.ln_gamma && (!p.ln_beta || !p.o32 || !p.o_hi || !p.o_nct || p.nblocks != 1 || p.NACC != 1 || p.N > 256 ||
+                     p.c_valid != p.N || p.il_u || p.stack || p.pair || p.phases != 1 || p.ot_mul != 1 || p.ot_add != 0 ||
+                     p.act || p.accumulate || p.alpha != 1.f || p.post != 1.f || p.gate || p.lo8))
     return cudaErrorInvalidConfiguration;
   if (p.gate && (p.N % 64 || !p.o_hi || !p.o_nct || p.il_u || p.stack || p.pair || p.phases != 1 || p.ot_mul != 1))
     return cudaErrorInvalidConfiguration;

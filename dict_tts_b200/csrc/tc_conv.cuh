@@ -156,6 +156,17 @@ struct TcConvParams {
   // weights are packed so that column j < N/2 of a block is a tanh channel and column j + N/2 its sigmoid channel;
   // planes channel (block * N/2 + j) = tanh(conv_j + bias + res) * sigmoid(conv_{j+N/2} + bias + res).  N % 64 == 0.
   int gate;
+  // Channel LayerNorm of the OUTPUT fused into the epilogue (acoustic encoders: x = x + conv(..) followed by LN(x)):
+  //   x_new = (conv + bias) * mask + res          -> o32 (generic strides), multiplied by ln_in_mask when given
+  //   y     = LN_c(x_new) * gamma + beta, * ln_out_mask -> operand planes o_hi / o_lo and (optional) ln_y [same strides as o32]
+  // One N block must hold all channels (nblocks == 1, N == C_out), one 128-row sub-tile per tile; not in the CTA-pair
+  // build.  Statistics are single-pass (sum, sum of squares) over the values as stored.
+  const float* ln_gamma;         // null: off
+  const float* ln_beta;
+  float ln_eps;
+  const float* ln_in_mask;       // [B][m_bs] or null
+  const float* ln_out_mask;      // [B][m_bs] or null
+  float* ln_y;
   int a_stages, w_stages;
   int TG;                        // taps per weight stage
   int ntiles, B;                 // time tiles per (group, batch item); batch size (set by the launcher)

@@ -305,3 +305,33 @@ def test_fused_prior_flow_matches_per_layer_path_and_oracle(B, T):
     assert (zp_f - zp_u).abs().max().item() < 2e-5
     assert (mel_f.cpu() - mel_r).abs().max().item() < TOL_MEL_MAXABS
     eng.close()
+
+
+@pytest.mark.parametrize("name", sorted(ACOUSTIC_CASES))
+def test_fused_text_encoder_epilogues_match_per_layer_path(name):
+    """LayerNorm fused into the O / FFN2 convolution epilogues (one standalone LayerNorm per encoder instead of nine)
+    against the per-layer launches: same durations bit for bit, activations within fp32 reordering noise."""
+    from dict_tts_b200.engine import DictTTSEngine
+    lib = binding.load()
+    eng = DictTTSEngine(synth.make_acoustic_state_dict(ACOUSTIC_SEED), precision=1)
+    kw, _ = ACOUSTIC_CASES[name]
+    b = synth.make_batch(**kw)
+    args = (b["word_tokens"], b["pron_modified"], b["keys"], b["values"], b["key_map"], b["pinyin"], b["pinyin_map"])
+    try:
+        assert lib.dtts_debug_set_acoustic_fuse(1) == 0
+        n0 = eng.launches
+        f = {k: v.clone() for k, v in eng.text_encode(*args).items() if torch.is_tensor(v)}
+        n_fused = eng.launches - n0
+        assert lib.dtts_debug_set_acoustic_fuse(0) == 0
+        n0 = eng.launches
+        u = {k: v.clone() for k, v in eng.text_encode(*args).items() if torch.is_tensor(v)}
+        n_unfused = eng.launches - n0
+    finally:
+        lib.dtts_debug_set_acoustic_fuse(-1)
+    torch.cuda.synchronize()
+    assert n_fused <= n_unfused - 16, (n_fused, n_unfused)
+    assert torch.equal(f["dur_int"], u["dur_int"])
+    for k in ("word_encoder_out", "dict_attn", "pron_attn", "dur"):
+        assert torch.isfinite(f[k]).all()
+        assert (f[k] - u[k]).abs().max().item() < 2e-5, k
+    eng.close()
