@@ -520,7 +520,8 @@ extern "C" int dtts_acoustic_create(const dtts_acoustic_desc* d, const float* ar
   size_t total = 0;
   for (auto& e : h->tab.entries) total += e.second.second + 64;
   // slack: q|k|v side-by-side copies, the space-to-depth g_pre_net weight, the gate-permuted decoder WaveNet, alignment
-  const size_t gate_extra = (size_t)d->dec_layers * 2 * d->hidden * d->hidden * (d->dec_kernel + 1) + 4096;
+  const size_t gate_extra = (size_t)d->dec_layers * 2 * d->hidden * d->hidden * (d->dec_kernel + 1) + 4096 +
+                            (size_t)2 * d->hidden * d->dict_dim;     // + the pre-multiplied S2PA projections
   rc = h->pool.reserve(total + 2 * 1024 * 1024 + gate_extra);
   if (rc != DTTS_OK) { delete h; return rc; }
   if (h->precision) {
@@ -563,6 +564,22 @@ extern "C" int dtts_acoustic_create(const dtts_acoustic_desc* d, const float* ar
     DTTS_TRY(tc_pack1(h, a + ".q_transform", false, H, H, 1, 0, &h->t_s2pa_q, s));
     DTTS_TRY(tc_pack1(h, a + ".v_transform", false, H, D, 1, 0, &h->t_s2pa_v, s));
     DTTS_TRY(tc_pack1(h, a + ".output_transform", false, H, H, 1, 0, &h->t_s2pa_o, s));
+    if (h->precision) {
+      const float* wq = h->tab.get(a + ".q_transform.weight", (uint64_t)H * H);
+      const float* wk = h->tab.get(a + ".k_transform.weight", (uint64_t)H * D);
+      const float* wv = h->tab.get(a + ".v_transform.weight", (uint64_t)H * D);
+      const float* wo = h->tab.get(a + ".output_transform.weight", (uint64_t)H * H);
+      float* wqk = h->pool.take((size_t)D * H);
+      float* wvo = h->pool.take((size_t)H * D);
+      if (!wq || !wk || !wv || !wo) return DTTS_ERR_MISSING_WEIGHT;
+      if (!wqk || !wvo) return fail(DTTS_ERR_CUDA, "weight pool exhausted");
+      DTTS_CUDA(matmul_f32(wk, wq, wqk, D, H, H, 1, s));        // [D][H] = W_k^T [D][H'] W_q [H'][H]
+      DTTS_CUDA(matmul_f32(wo, wv, wvo, H, D, H, 0, s));        // [H][D] = W_o [H][H'] W_v [H'][D]
+      const float* c1 = wqk;
+      const float* c2 = wvo;
+      DTTS_TRY(tc_pack(h, &c1, 1, nullptr, D, H, 1, 0, 0, &h->t_s2pa_qk, s));
+      DTTS_TRY(tc_pack(h, &c2, 1, nullptr, H, D, 1, 0, 0, &h->t_s2pa_vo, s));
+    }
     if (d->s2pa_route == 1) {
       const float* wkv[2] = {h->tab.get(a + ".k_transform.weight", (uint64_t)H * D),
                              h->tab.get(a + ".v_transform.weight", (uint64_t)H * D)};
@@ -740,8 +757,12 @@ static int text_encode_impl(dtts_acoustic* h, const dtts_text_in* in, const dtts
   if (tc) {
     TcRun::Epi ek;
     ek.alpha = 1.f / sqrtf((float)D);
-    tc->conv_nct(tc->P[0], h->t_s2pa_q, nullptr, Tw, 1, 0, TcRun::Epi(), 0, 0, &tc->P[1]);   // P[0] = last LN of the encoder
-    tc->conv_nct(tc->P[1], h->t_s2pa_kT, qk, Tw, 1, 0, ek);
+    if (h->t_s2pa_qk.w && ac_fuse_enabled()) {
+      tc->conv_nct(tc->P[0], h->t_s2pa_qk, qk, Tw, 1, 0, ek);                                 // P[0] = last LN of the encoder
+    } else {
+      tc->conv_nct(tc->P[0], h->t_s2pa_q, nullptr, Tw, 1, 0, TcRun::Epi(), 0, 0, &tc->P[1]);
+      tc->conv_nct(tc->P[1], h->t_s2pa_kT, qk, Tw, 1, 0, ek);
+    }
   } else {
     L(launch_conv1d_f32(conv_params(hb, Tw, h->s2pa_q, 0, H, q, Tw, 1, 1, 0), B, s));
     ConvParams p = conv_params(q, Tw, h->s2pa_kT, 0, D, qk, Tw, 1, 1, 0);
@@ -752,8 +773,12 @@ static int text_encode_impl(dtts_acoustic* h, const dtts_text_in* in, const dtts
                 row_off, row_len));
   if (tc) {
     tc->stage_nct(tc->P[0], ctx, D, Tw);
-    tc->conv_nct(tc->P[0], h->t_s2pa_v, nullptr, Tw, 1, 0, TcRun::Epi(), 0, 0, &tc->P[1]);
-    tc->conv_nct(tc->P[1], h->t_s2pa_o, context, Tw, 1, 0, TcRun::Epi());
+    if (h->t_s2pa_vo.w && ac_fuse_enabled()) {
+      tc->conv_nct(tc->P[0], h->t_s2pa_vo, context, Tw, 1, 0, TcRun::Epi());
+    } else {
+      tc->conv_nct(tc->P[0], h->t_s2pa_v, nullptr, Tw, 1, 0, TcRun::Epi(), 0, 0, &tc->P[1]);
+      tc->conv_nct(tc->P[1], h->t_s2pa_o, context, Tw, 1, 0, TcRun::Epi());
+    }
   } else {
     L(launch_conv1d_f32(conv_params(ctx, Tw, h->s2pa_v, 0, H, ctxv, Tw, 1, 1, 0), B, s));
     L(launch_conv1d_f32(conv_params(ctxv, Tw, h->s2pa_o, 0, H, context, Tw, 1, 1, 0), B, s));

@@ -54,6 +54,9 @@ struct dtts_acoustic {
   dtts::ac::EncoderW sem, lin;
   dtts::ConvW s2pa_q, s2pa_kT, s2pa_v, s2pa_o;
   dtts::TcConvW t_s2pa_q, t_s2pa_kT, t_s2pa_v, t_s2pa_o;
+  // folded route with the projections that are applied back to back multiplied once at create time:
+  // qk = (W_k^T W_q) x and context = (W_o W_v) ctx -- one tcgen05 launch each instead of two (empty: not built)
+  dtts::TcConvW t_s2pa_qk, t_s2pa_vo;
   dtts::TcConvW t_s2pa_kv;              // s2pa_route = 1: [W_k ; W_v] side by side, dict_dim -> 2 * hidden (block 0 = k, block 1 = v)
   dtts::TcConvW t_gpre;                 // g_pre_net as a stride-1 k=3 convolution over the 4x space-to-depth input (C' = 4H)
   dtts::TcConvW t_out;                  // out_proj with C_out zero-padded to a multiple of 32

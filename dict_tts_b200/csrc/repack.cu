@@ -101,4 +101,19 @@ cudaError_t permute_gate_rows(const float* in, float* out, int groups, int hidde
   permute_gate_rows_kernel<<<256, 256, 0, s>>>(in, out, groups, hidden, N, row_len);
   return cudaGetLastError();
 }
+// C[m][n] = sum_k A(m,k) * B[k][n], fp32, k ascending; transA: A is stored [K][M] (create-time products of two 1x1
+// projections that the forward applies back to back)
+__global__ void matmul_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M,
+                                  int N, int K, int transA) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)M * N) return;
+  const int m = (int)(i / N), n = (int)(i - (long)m * N);
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc = fmaf(transA ? A[(size_t)k * M + m] : A[(size_t)m * K + k], B[(size_t)k * N + n], acc);
+  C[i] = acc;
+}
+cudaError_t matmul_f32(const float* A, const float* B, float* C, int M, int N, int K, int transA, cudaStream_t s) {
+  matmul_f32_kernel<<<cdiv((long)M * N, 256), 256, 0, s>>>(A, B, C, M, N, K, transA);
+  return cudaGetLastError();
+}
 }  // namespace dtts

@@ -331,7 +331,10 @@ def test_fused_text_encoder_epilogues_match_per_layer_path(name):
     torch.cuda.synchronize()
     assert n_fused <= n_unfused - 16, (n_fused, n_unfused)
     assert torch.equal(f["dur_int"], u["dur_int"])
-    for k in ("word_encoder_out", "dict_attn", "pron_attn", "dur"):
-        assert torch.isfinite(f[k]).all()
-        assert (f[k] - u[k]).abs().max().item() < 2e-5, k
+    # half the fixture tolerances (the fused build also multiplies the S2PA projection pairs W_k^T W_q and W_o W_v once at
+    # create time, so the two builds differ by more than a summation order)
+    errs = {k: (f[k] - u[k]).abs().max().item() for k in ("word_encoder_out", "dict_attn", "pron_attn", "dur")}
+    tol = dict(word_encoder_out=1e-4, dict_attn=5e-6, pron_attn=5e-6, dur=5e-5)
+    assert all(torch.isfinite(f[k]).all() for k in errs)
+    assert all(errs[k] < tol[k] for k in errs), errs
     eng.close()
