@@ -540,6 +540,7 @@ extern "C" int dtts_acoustic_create(const dtts_acoustic_desc* d, const float* ar
     if (d->model == DTTS_MODEL_PORTASPEECH) {          // own text side, shared predictor / decoder
       DTTS_TRY(create_ps(h, s));
       DTTS_TRY(pack_dur_predictor(h, H, s));
+      h->tc_text_end = h->tc_used;
       return pack_decoder(h, s);
     }
     const std::string p = "dict_encoder.S2PA_module";
@@ -587,6 +588,7 @@ extern "C" int dtts_acoustic_create(const dtts_acoustic_desc* d, const float* ar
       DTTS_TRY(tc_pack(h, wkv, 2, nullptr, H, D, 1, 0, H, &h->t_s2pa_kv, s));      // N = H: one block per projection
     }
     DTTS_TRY(pack_dur_predictor(h, H, s));
+    h->tc_text_end = h->tc_used;
     DTTS_TRY(pack_decoder(h, s));
     return DTTS_OK;
   };
@@ -729,6 +731,7 @@ static int text_encode_impl(dtts_acoustic* h, const dtts_text_in* in, const dtts
   cudaStream_t s = L.stream;
   tcr.h = h; tcr.L = &L; tcr.B = B;
 
+  if (tc && ac_fuse_enabled()) L(l2_prefetch(h->tc_pool, h->tc_text_end * sizeof(tc16), s));   // weights -> L2 (kernels.cuh)
   // word embedding * sqrt(H), masks (dict_encoder.py:131-136)
   L(embed_tokens(in->word_tokens_dev, h->word_emb, sqrtf((float)H), B, Tw, H, d.word_size, x, seq_mask, tok_mask, lens,
                  s));
@@ -954,6 +957,10 @@ extern "C" int dtts_decode_mel(dtts_acoustic* h, const float* g, const float* z_
   tcr.h = h; tcr.L = &L; tcr.B = B;
 
   const bool fuse_flow = tc && h->flow_fused.ready() && ac_fuse_enabled();
+  if (tc && ac_fuse_enabled()) {               // decoder weights -> L2 while the first launches run (kernels.cuh)
+    L(l2_prefetch(h->tc_pool + h->tc_text_end, (h->tc_used - h->tc_text_end) * sizeof(tc16), s));
+    if (fuse_flow) L(l2_prefetch(h->flow_fused.stream, h->flow_fused.stream_bytes(), s));
+  }
   // g_sqz = Conv1d(H,H,k=8,s=4,p=2)(g)  (fvae_semantics.py:93-94; semantics == 0)
   if (tc) {
     Planes& P0 = tc->P[0];

@@ -67,6 +67,7 @@ struct dtts_acoustic {
   dtts::TcMode mode;
   dtts::tc16* tc_pool = nullptr;
   size_t tc_cap = 0, tc_used = 0;
+  size_t tc_text_end = 0;         // tc_pool[0, tc_text_end): text side + duration predictor; the rest: decoder (L2 prefetch ranges)
   std::vector<const float*> dur_ln_g, dur_ln_b;
   const float *dur_w, *dur_b;
   dtts::ConvW g_pre, dec_pre, dec_out;

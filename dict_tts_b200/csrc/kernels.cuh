@@ -20,6 +20,8 @@ cudaError_t repack_s2d4(const float* w, float* out, int C_out, int C_in, cudaStr
 cudaError_t fill_f32(float* p, float v, size_t n, cudaStream_t s);
 // WaveNet in_layers / cond_layer rows ([groups][tanh half | sigmoid half][row_len]) re-ordered per N-row block as
 // [N/2 tanh | the N/2 sigmoid rows that gate them] (TcConvParams::gate)
+// prefetch.global.L2 over [p, p + bytes) (returns at once; the fills proceed in the background)
+cudaError_t l2_prefetch(const void* p, size_t bytes, cudaStream_t s);
 // C [M][N] = A B with A [M][K] (or [K][M] when transA) and B [K][N], row-major fp32
 cudaError_t matmul_f32(const float* A, const float* B, float* C, int M, int N, int K, int transA, cudaStream_t s);
 cudaError_t permute_gate_rows(const float* in, float* out, int groups, int hidden, int N, long row_len, cudaStream_t s);

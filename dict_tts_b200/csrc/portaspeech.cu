@@ -243,6 +243,7 @@ extern "C" int dtts_ps_text_encode(dtts_acoustic* h, const dtts_ps_text_in* in, 
   PsRun R{h, &L, tc, B};
   TcRun::Epi none;
 
+  if (tc && ac_fuse_enabled()) L(l2_prefetch(h->tc_pool, h->tc_text_end * sizeof(tc16), s));   // weights -> L2 (kernels.cuh)
   // ---- TextEncoder.forward (model.py:119-129): embedding * sqrt(H), prefix mask by count, pre-net, post-LN encoder ----
   L(embed_tokens(in->txt_tokens_dev, P.ph_emb, sqrtf((float)H), B, Tp, H, d.ph_size, x, seq_mask, tok_mask, lens, s));
   L(apply_mask(x, seq_mask, B, H, Tp, s));               // x_org * x_mask: every use of it below is masked
