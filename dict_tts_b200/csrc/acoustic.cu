@@ -204,7 +204,7 @@ void run_encoder(dtts_acoustic* h, const EncoderW& E, float* x, float* hbuf, flo
         L(channel_layernorm_planes(x, x, nullptr, W.g1, W.b1, 1e-4f, seq_mask, nullptr, B, H, Tw,
                                    tc->out_of(P0, H, Tw, fuse_ln), s));       // (fused: halo zeroed once, for every FFN)
       tc->conv_nct(P0, W.t_qkv, qkv, Tw, 1, 0, TcRun::Epi());
-      if (Tw <= 64) {
+      if (self_attention_planes_fits(H, Tw, h->d.n_heads)) {
         L(self_attention_planes(qkv, qkv + (size_t)H * Tw, qkv + (size_t)2 * H * Tw, seq_mask, nullptr, B, H, Tw,
                                 h->d.n_heads, tc->out_of(P0, H, Tw, false), s));
       } else {

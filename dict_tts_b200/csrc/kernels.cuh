@@ -40,7 +40,9 @@ struct PlaneOut;
 cudaError_t channel_layernorm_planes(const float* x, float* xw, float* y, const float* gamma, const float* beta, float eps,
                                      const float* in_mask, const float* out_mask, int B, int C, int T, const PlaneOut& po,
                                      cudaStream_t s);
-// Shared-memory self attention for T <= 64; q,k,v are the three C-channel thirds of one [B,3C,T] tensor.
+// Shared-memory self attention for short sequences (self_attention_planes_fits: T <= 128 at d_k = 96); q,k,v are the three
+// C-channel thirds of one [B,3C,T] tensor.
+bool self_attention_planes_fits(int C, int T, int heads);
 cudaError_t self_attention_planes(const float* q, const float* k, const float* v, const float* mask, float* out, int B,
                                   int C, int T, int heads, const PlaneOut& po, cudaStream_t s);
 cudaError_t wn_gate_planes(const float* a, int B, int H, int T, const PlaneOut& po, cudaStream_t s);

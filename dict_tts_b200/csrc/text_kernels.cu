@@ -265,18 +265,22 @@ __global__ void __launch_bounds__(256) self_attn_small_kernel(const float* __res
   }
 }
 
+// q, k, v of one (item, head) and the T x T scores must fit in shared memory: T <= 128 at d_k = 96 (213 KB)
+bool self_attention_planes_fits(int C, int T, int heads) {
+  const size_t dk = (size_t)(C / (heads > 0 ? heads : 1));
+  return T > 0 && T <= 128 && (3 * dk * T + (size_t)T * (T + 1)) * sizeof(float) <= (size_t)227 * 1024;
+}
 cudaError_t self_attention_planes(const float* q, const float* k, const float* v, const float* mask, float* out, int B,
                                   int C, int T, int heads, const PlaneOut& po, cudaStream_t s) {
   const int dk = C / heads;
-  if (T > 64 || (po.hi && dk % 8)) return cudaErrorInvalidValue;
+  if (!self_attention_planes_fits(C, T, heads) || (po.hi && dk % 8)) return cudaErrorInvalidValue;
   const size_t smem = ((size_t)3 * dk * T + (size_t)T * (T + 1)) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(self_attn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(self_attn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  if (smem > 160 * 1024) return cudaErrorInvalidConfiguration;
   self_attn_small_kernel<<<B * heads, 256, smem, s>>>(q, k, v, mask, out, C, T, heads, (long)3 * C * T, po);
   return cudaGetLastError();
 }

@@ -221,7 +221,8 @@ SWEEP = [
     (302, 2, 1, 3, 18, 12, "tiny gloss lists, T % 4 == 2"),
     (303, 5, 2, 11, 61, 33, "odd everything"),
     (304, 3, 20, 40, 200, 48, "Tw = 42: still the shared-memory attention"),
-    (305, 2, 70, 90, 400, 24, "Tw = 92 > 64: the general attention kernel"),
+    (305, 2, 70, 90, 400, 24, "Tw = 92: shared-memory attention with 128 KB of q | k | v"),
+    (307, 1, 131, 140, 560, 8, "Tw = 142 > 128: the general attention kernel, LayerNorm as its own launches"),
     (306, 7, 1, 6, 28, 96, "many short utterances, long gloss lists"),
 ]
 
