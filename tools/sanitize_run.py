@@ -20,6 +20,8 @@ def main():
     ap.add_argument("--vocoder-precision", type=int, default=6)
     ap.add_argument("--frames", type=int, default=24)
     ap.add_argument("--skip-acoustic", action="store_true")
+    ap.add_argument("--skip-vocoder", action="store_true")
+    ap.add_argument("--long", action="store_true", help="also a 2-tile prior flow (T/4 = 120) and the per-layer acoustic build")
     ap.add_argument("--fuse-all", action="store_true",
                     help="dtts_debug_set_tc_fuse(3): every C = 128 ResBlock pair on rb_pair128_kernel (default: k = 3 only)")
     args = ap.parse_args()
@@ -39,8 +41,21 @@ def main():
                 eng.forward((batch["word_tokens"],), batch["pron_modified"], dict_ids=ids, mel2word=batch["mel2word"],
                             z_p=batch["z_p"])
                 eng.pron_tokens(out["pron_attn"], pinyin=batch["pinyin"])
+            if args.long and route == 0:
+                from dict_tts_b200 import binding
+                g = torch.Generator().manual_seed(1)
+                gb = (torch.randn(2, 192, 480, generator=g) * 0.5).cuda()
+                zz = torch.randn(2, 16, 120, generator=g).cuda()
+                eng.decode_mel(gb, zz)                                   # flow_fused_kernel with two tiles per utterance
+                binding.load().dtts_debug_set_acoustic_fuse(0)
+                eng.decode_mel(gb, zz)                                   # the per-layer build of the same pass
+                eng.forward((batch["word_tokens"],), batch["pron_modified"], dict_msg=dm)
+                binding.load().dtts_debug_set_acoustic_fuse(-1)
             torch.cuda.synchronize()
             eng.close()
+    if args.skip_vocoder:
+        print("sanitize_run ok (acoustic only)")
+        return
     voc = HifiGanEngine(synth.make_vocoder_state_dict(4321), precision=args.vocoder_precision)
     mel = synth.make_mel(5, 3, args.frames)
     w = voc(mel)
