@@ -1279,6 +1279,11 @@ int tc_fuse128_maxk() {
   static const int v = env_int("DTTS_TC_FUSE128_MAXK", 3);
   return g_fuse_override == 3 ? 11 : v;
 }
+int tc_fuse_block_enabled() {
+  static const int v = env_int("DTTS_TC_FUSE_BLOCK", 1) != 0;
+  if (g_fuse_override >= 0) return g_fuse_override == 4;
+  return v && tc_fuse_enabled();
+}
 int tc_fold_post_enabled() {
   static const int v = env_int("DTTS_TC_FOLD_POST", 1) != 0;
   if (g_fuse_override >= 0) return g_fuse_override == 1;

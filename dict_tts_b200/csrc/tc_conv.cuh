@@ -228,6 +228,35 @@ struct RbPairParams {
   int w_planes, lo8;
   float acc_scale;               // the accumulators hold conv / acc_scale (TcConvParams::acc_scale)
 };
+// Whole ResBlock (three pairs, kernel 3, C = 32) in one launch (rb_block.cu): the fp32 residual stream of a row stays in
+// registers, the operand planes between the pairs in shared memory; bit-identical to the three pair launches.
+struct RbBlockParams {
+  const tc16* a_hi;              // input operand planes [B][4][a_rows][8] (leaky-ReLU'd by their producer)
+  long a_bs;
+  int a_rows, a_pad;
+  const tc16* w[6];              // stacked weight blobs of conv1(0), conv2(0), conv1(1), conv2(1), conv1(2), conv2(2)
+  const float* bias[6];
+  int dil[3];                    // dilation of conv1 of each pair (conv2: 1)
+  int T, fmt;
+  float slope;
+  const float* res;              // fp32 stream: x of the ResBlock (may be null)
+  float* o32;                    // fp32 stream out: post * y (+ out if accumulate)
+  long o32_bs;
+  tc16* o_hi;                    // output operand planes of leaky(out) (may be null)
+  long op_bs;
+  int op_rows, op_pad;
+  float post;
+  int accumulate;
+  const int* lens;               // ragged launch (optional), as TcConvParams
+  int len_mul, len_add;
+  int B;
+  int halo, S, ntiles;           // set by the launcher: sum(dil + 1), tile stride 256 - 2 halo, tiles per item
+};
+int rb_block32_supported(const TcConvW* const c1[3], const TcConvW* const c2[3], const int dil[3], int a_planes);
+cudaError_t launch_rb_block32(RbBlockParams p, cudaStream_t stream);
+// the k = 3 ResBlock of the C = 32 stage as one launch (default on with the fused pairs; DTTS_TC_FUSE_BLOCK=0 or a
+// tc_fuse_override other than 4: off)
+int tc_fuse_block_enabled();
 // rows the fused kernel may stage past tc_rows(T): its last tile reads up to 256 + halo rows beyond the tile start
 constexpr int TC_FUSE_EXTRA_ROWS = 320;
 int rb_pair_supported(const TcConvW& c1, const TcConvW& c2, int dil, int a_planes);
@@ -251,6 +280,7 @@ int tc_fuse_enabled();
 void tc_fuse_override(int v);      // -1: environment default; 0 / 1: force (unit tests compare the two builds of a pass);
                                    // 2: fused pairs but conv_post as its own kernel (bit-identical to mode 0);
                                    // 3: as 2 with every C = 128 pair fused too (tc_fuse128_maxk)
+                                   // 4: as 2 with the k = 3 ResBlock of the C = 32 stage as ONE launch (rb_block.cu)
 // conv_post folded into the last fused pair (default on with the fused pairs; DTTS_TC_FOLD_POST=0 or override 2: off)
 int tc_fold_post_enabled();
 

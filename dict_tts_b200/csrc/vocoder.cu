@@ -322,6 +322,35 @@ int tc_vocode(dtts_vocoder* h, const float* mel, int B, int T, float* wav, void*
     if (!last_stage) shape(PX, ch, len);                // PX is free again: it becomes the next stage's input
     for (int j = 0; j < d.n_rb; ++j) {
       const int kr = d.rb_kernels[j];
+      {
+        // the whole ResBlock as ONE launch where it is HBM bound as three (k = 3, C = 32; rb_block.cu): the fp32 stream of
+        // a row stays in registers, the planes between the pairs in shared memory
+        const TcConvW* b1[3]; const TcConvW* b2[3];
+        int dils[3];
+        for (int m = 0; m < 3; ++m) {
+          b1[m] = &h->tc_rb1[(i * d.n_rb + j) * 3 + m];
+          b2[m] = &h->tc_rb2[(i * d.n_rb + j) * 3 + m];
+          dils[m] = d.rb_dilations[j][m];
+        }
+        const bool folds_post = j == d.n_rb - 1 && last_stage;       // (the last pair of the last ResBlock carries conv_post)
+        if (tc_fuse_block_enabled() && ch == 32 && kr == 3 && !folds_post &&
+            rb_block32_supported(b1, b2, dils, h->mode.a_planes)) {
+          RbBlockParams bp{};
+          bp.a_hi = PXUo.hi; bp.a_bs = PXUo.bs(); bp.a_rows = PXUo.rows; bp.a_pad = TC_PADF;
+          for (int m = 0; m < 3; ++m) {
+            bp.w[2 * m] = b1[m]->w; bp.w[2 * m + 1] = b2[m]->w;
+            bp.bias[2 * m] = b1[m]->bias; bp.bias[2 * m + 1] = b2[m]->bias;
+            bp.dil[m] = dils[m];
+          }
+          bp.T = len; bp.fmt = b1[0]->fmt; bp.slope = 0.1f;
+          bp.res = XU; bp.o32 = ACC32; bp.o32_bs = (long)ch * len;
+          bp.post = 1.f / (float)d.n_rb; bp.accumulate = j > 0;
+          if (j == d.n_rb - 1 && !last_stage) { bp.o_hi = PX.hi; bp.op_bs = PX.bs(); bp.op_rows = PX.rows; bp.op_pad = TC_PADF; }
+          bp.lens = lens; bp.len_mul = ls.rpf[i + 1]; bp.len_add = ls.stage_add[i]; bp.B = B;
+          L(launch_rb_block32(bp, s));
+          continue;
+        }
+      }
       for (int m = 0; m < 3; ++m) {
         const int dil = d.rb_dilations[j][m];
         const TcConvW& c1 = h->tc_rb1[(i * d.n_rb + j) * 3 + m];
@@ -591,7 +620,7 @@ static int vocode_impl(dtts_vocoder* h, const float* mel, const int32_t* lens, i
 }
 
 extern "C" int dtts_debug_set_tc_fuse(int32_t mode) {
-  if (mode < -1 || mode > 3) return fail(DTTS_ERR_BAD_ARG, "dtts_debug_set_tc_fuse: mode must be -1 .. 3");
+  if (mode < -1 || mode > 4) return fail(DTTS_ERR_BAD_ARG, "dtts_debug_set_tc_fuse: mode must be -1 .. 4");
   tc_fuse_override(mode);
   return DTTS_OK;
 }

@@ -288,8 +288,9 @@ int dtts_debug_tc_conv1d(const float* x_dev, const float* w_dev, const float* bi
  * both.  mode 0: two launches per pair; 2: fused pairs, conv_post as its own kernel (bit-identical to mode 0); 1: fused
  * pairs with conv_post folded into the last one (the default; other summation order inside conv_post, ~1e-7);
  * 3: as 2, and every ResBlock pair of the C = 128 stage fused as well (by default only its k = 3 pairs are: the others
- * measured no faster than two launches, DTTS_TC_FUSE128_MAXK); -1: back to the default / the DTTS_TC_FUSE,
- * DTTS_TC_FOLD_POST environment switches. */
+ * measured no faster than two launches, DTTS_TC_FUSE128_MAXK); 4: as 2, and the whole k = 3 ResBlock of the C = 32 stage
+ * (three pairs) as ONE launch, bit-identical again (part of the default); -1: back to the default / the DTTS_TC_FUSE,
+ * DTTS_TC_FOLD_POST, DTTS_TC_FUSE_BLOCK environment switches. */
 int dtts_debug_set_tc_fuse(int32_t mode);
 
 /* Unit-test hook: the fused kernels of the acoustic model (flow_fused_kernel: the whole reverse prior flow of
