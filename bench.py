@@ -45,15 +45,15 @@ ENCODER_FLOP_PER_TOKEN = 16.6e6           # 8 encoder layers
 S2PA_BYTES_PER_GLOSS_TOKEN = 6144         # keys + values rows, fp32 (3072 when values alias keys)
 LR_BYTES_PER_FRAME = 1536
 # ncu dram__bytes_read + dram__bytes_write of one valid-length vocode pass at cfg 2 (profiles/, see traffic_source)
-TC_CONV_DRAM_BYTES_PER_STEP = 65.1e9
-TC_CONV_TRAFFIC_SOURCE = ("profiles/r02i_vocoder_lens_dram_agg.txt: ncu dram__bytes_read+write summed over the 54 tensor-core "
-                          "launches of one valid-length vocode pass (35 tc_conv_kernel + 3 rb_pair128_kernel + 9 rb_pair64_kernel "
-                          "+ 6 rb_pair32_kernel + 1 rb_block32_kernel) = 65.1 GB = 1.21 GB per launch (65.2 GB with the conv_post "
-                          "finishing kernel; before the k = 3 ResBlock of the last stage became one launch: 69.1 GB over 56; "
-                          "round 1, before the fused ResBlock pairs: 82.9 GB over 77 launches). Byte models: SURVEY 8d "
+TC_CONV_DRAM_BYTES_PER_STEP = 61.1e9
+TC_CONV_TRAFFIC_SOURCE = ("profiles/r02j_vocoder_lens_dram_agg.txt: ncu dram__bytes_read+write summed over the 52 tensor-core "
+                          "launches of one valid-length vocode pass (35 tc_conv_kernel + 3 rb_pair128_kernel + 6 rb_pair64_kernel "
+                          "+ 6 rb_pair32_kernel + 2 rb_block_kernel) = 61.1 GB = 1.17 GB per launch (61.3 GB with the conv_post "
+                          "finishing kernel; before the k = 3 ResBlocks of the two narrow stages became one launch each: 69.1 GB "
+                          "over 56; round 1, before the fused ResBlock pairs: 82.9 GB over 77 launches). Byte models: SURVEY 8d "
                           "fully-fused algorithmic 1344 B/frame = 27.8 MB per step; this design's per-layer model (16 B per "
-                          "element and ResBlock pair, 12 B where the pair is fused, 10 B for the block-fused ResBlock) = 65 GB "
-                          "per step -- the measured traffic equals the per-layer model, i.e. ~2300x the fully-fused figure: "
+                          "element and ResBlock pair, 12 B where the pair is fused, 10 B for a block-fused ResBlock) = 61 GB "
+                          "per step -- the measured traffic equals the per-layer model, i.e. ~2200x the fully-fused figure: "
                           "that factor is what a layer-by-layer design costs, not re-reads")
 WORKLOADS = {
     "cfg1": dict(B=1, min_chars=64, max_chars=64, max_frames=1280, Lk_cap=96),
@@ -61,9 +61,9 @@ WORKLOADS = {
 }
 CFG4 = dict(B=256, T=32)
 # tensor-core launches of one vocode pass: conv_pre, 4 transposed convolutions, 30 ResBlock convolutions of stages 1-2, the 3
-# fused k = 3 pairs of stage 2 (rb_pair128.cu), the 15 fused ResBlock pairs of stages 3-4 (rb_pair.cu) and the k = 3 ResBlock of
-# stage 4 as one launch (rb_block.cu); 72 ResBlock convolutions = 77 launches before the fusion
-N_TC_CONV_LAUNCHES = 1 + 4 + 30 + 3 + 15 + 1
+# fused k = 3 pairs of stage 2 (rb_pair128.cu), the 12 fused ResBlock pairs of stages 3-4 (rb_pair.cu) and the k = 3 ResBlocks of
+# stages 3-4 as one launch each (rb_block.cu); 72 ResBlock convolutions = 77 launches before the fusion
+N_TC_CONV_LAUNCHES = 1 + 4 + 30 + 3 + 12 + 2
 CPU_SAMPLE_UTTS = 30      # ~10 k of the batch's 20.7 k frames: 10-20 s of host work for the two timed passes
 VOC_DTYPE = {0: "f32", 1: "f32-class (bf16 hi/lo x hi/lo on tcgen05: 3 MMAs per product, fp32 accumulate)",
              2: "bf16 (tcgen05, 1 MMA)", 3: "fp16 activations x fp16 hi/lo weights (tcgen05, 2 MMAs, fp32 accumulate)",
@@ -74,7 +74,7 @@ VOC_KERNEL = {0: "conv1d_f32_kernel (fp32 FMA pipe)", 1: "tc_conv_kernel (tcgen0
               4: "tc_conv_kernel (tcgen05, fp16: 1 MMA)", 5: "tc_conv_kernel (tcgen05, fp16; hi/lo weights only where C_out < 128)",
               6: "tc_conv_kernel + rb_pair{32,64,128}_kernel (tcgen05, fp16 x fp16 hi/lo weights: 2 MMAs; lo plane in FP8 where "
                  "C_out >= 128: 1.5; ResBlock pairs of the C <= 64 stages and the k = 3 pairs of the C = 128 stage fused, the k = 3 "
-                 "ResBlock of the C = 32 stage as one launch)"}
+                 "ResBlocks of the C = 32 / 64 stages as one launch each)"}
 
 
 def load_peaks():

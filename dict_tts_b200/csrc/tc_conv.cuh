@@ -228,10 +228,11 @@ struct RbPairParams {
   int w_planes, lo8;
   float acc_scale;               // the accumulators hold conv / acc_scale (TcConvParams::acc_scale)
 };
-// Whole ResBlock (three pairs, kernel 3, C = 32) in one launch (rb_block.cu): the fp32 residual stream of a row stays in
+// Whole ResBlock (three pairs, kernel 3, C = 32 or 64) in one launch (rb_block.cu): the fp32 residual stream of a row stays in
 // registers, the operand planes between the pairs in shared memory; bit-identical to the three pair launches.
 struct RbBlockParams {
-  const tc16* a_hi;              // input operand planes [B][4][a_rows][8] (leaky-ReLU'd by their producer)
+  int C;                         // channels: 32 (weights resident in shared memory) or 64 (one convolution per phase streamed)
+  const tc16* a_hi;              // input operand planes [B][C/8][a_rows][8] (leaky-ReLU'd by their producer)
   long a_bs;
   int a_rows, a_pad;
   const tc16* w[6];              // stacked weight blobs of conv1(0), conv2(0), conv1(1), conv2(1), conv1(2), conv2(2)
@@ -252,9 +253,9 @@ struct RbBlockParams {
   int B;
   int halo, S, ntiles;           // set by the launcher: sum(dil + 1), tile stride 256 - 2 halo, tiles per item
 };
-int rb_block32_supported(const TcConvW* const c1[3], const TcConvW* const c2[3], const int dil[3], int a_planes);
-cudaError_t launch_rb_block32(RbBlockParams p, cudaStream_t stream);
-// the k = 3 ResBlock of the C = 32 stage as one launch (default on with the fused pairs; DTTS_TC_FUSE_BLOCK=0 or a
+int rb_block_supported(const TcConvW* const c1[3], const TcConvW* const c2[3], const int dil[3], int a_planes);
+cudaError_t launch_rb_block(RbBlockParams p, cudaStream_t stream);
+// the k = 3 ResBlocks of the C = 32 and C = 64 stages as one launch each (default on with the fused pairs; DTTS_TC_FUSE_BLOCK=0 or a
 // tc_fuse_override other than 4: off)
 int tc_fuse_block_enabled();
 // rows the fused kernel may stage past tc_rows(T): its last tile reads up to 256 + halo rows beyond the tile start

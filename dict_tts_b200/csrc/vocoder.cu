@@ -323,7 +323,7 @@ int tc_vocode(dtts_vocoder* h, const float* mel, int B, int T, float* wav, void*
     for (int j = 0; j < d.n_rb; ++j) {
       const int kr = d.rb_kernels[j];
       {
-        // the whole ResBlock as ONE launch where it is HBM bound as three (k = 3, C = 32; rb_block.cu): the fp32 stream of
+        // the whole ResBlock as ONE launch where it is HBM bound as three (k = 3, C = 32 / 64; rb_block.cu): the fp32 stream of
         // a row stays in registers, the planes between the pairs in shared memory
         const TcConvW* b1[3]; const TcConvW* b2[3];
         int dils[3];
@@ -333,9 +333,9 @@ int tc_vocode(dtts_vocoder* h, const float* mel, int B, int T, float* wav, void*
           dils[m] = d.rb_dilations[j][m];
         }
         const bool folds_post = j == d.n_rb - 1 && last_stage;       // (the last pair of the last ResBlock carries conv_post)
-        if (tc_fuse_block_enabled() && ch == 32 && kr == 3 && !folds_post &&
-            rb_block32_supported(b1, b2, dils, h->mode.a_planes)) {
+        if (tc_fuse_block_enabled() && kr == 3 && !folds_post && rb_block_supported(b1, b2, dils, h->mode.a_planes)) {
           RbBlockParams bp{};
+          bp.C = ch;
           bp.a_hi = PXUo.hi; bp.a_bs = PXUo.bs(); bp.a_rows = PXUo.rows; bp.a_pad = TC_PADF;
           for (int m = 0; m < 3; ++m) {
             bp.w[2 * m] = b1[m]->w; bp.w[2 * m + 1] = b2[m]->w;
@@ -347,7 +347,7 @@ int tc_vocode(dtts_vocoder* h, const float* mel, int B, int T, float* wav, void*
           bp.post = 1.f / (float)d.n_rb; bp.accumulate = j > 0;
           if (j == d.n_rb - 1 && !last_stage) { bp.o_hi = PX.hi; bp.op_bs = PX.bs(); bp.op_rows = PX.rows; bp.op_pad = TC_PADF; }
           bp.lens = lens; bp.len_mul = ls.rpf[i + 1]; bp.len_add = ls.stage_add[i]; bp.B = B;
-          L(launch_rb_block32(bp, s));
+          L(launch_rb_block(bp, s));
           continue;
         }
       }
