@@ -956,7 +956,7 @@ extern "C" int dtts_decode_mel(dtts_acoustic* h, const float* g, const float* z_
   cudaStream_t s = L.stream;
   tcr.h = h; tcr.L = &L; tcr.B = B;
 
-  const bool fuse_flow = tc && h->flow_fused.ready() && ac_fuse_enabled();
+  const bool fuse_flow = tc && h->flow_fused.ready() && ac_fuse_enabled() && z_in != z_p;   // (its tiles read z_in as halo)
   if (tc && ac_fuse_enabled()) {               // decoder weights -> L2 while the first launches run (kernels.cuh)
     L(l2_prefetch(h->tc_pool + h->tc_text_end, (h->tc_used - h->tc_text_end) * sizeof(tc16), s));
     if (fuse_flow) L(l2_prefetch(h->flow_fused.stream, h->flow_fused.stream_bytes(), s));
@@ -983,8 +983,7 @@ extern "C" int dtts_decode_mel(dtts_acoustic* h, const float* g, const float* z_
     FlowFusedParams fp{};
     fp.g_hi = Pg.hi; fp.g_lo = Pg.lo; fp.g_bs = (long)Pg.C * Pg.rows; fp.g_rows = Pg.rows; fp.g_pad = TC_PADF;
     fp.z_in = z_in; fp.z_out = z_p; fp.T = T4; fp.B = B;
-    if (z_in == z_p) L(cudaErrorInvalidValue);
-    else L(launch_flow_fused(h->flow_fused, fp, s));
+    L(launch_flow_fused(h->flow_fused, fp, s));
   } else {
     L(copy_f32(z_in, z_p, (size_t)B * d.latent * T4, s));
   }
@@ -1016,7 +1015,8 @@ extern "C" int dtts_decode_mel(dtts_acoustic* h, const float* g, const float* z_
     }
   }
   // decoder (fvae_semantics.py:53-58)
-  const bool fuse_dec = tc && ac_fuse_enabled() && H % 8 == 0 && (d.latent == 16 || d.latent == 8);
+  const bool fuse_dec = tc && ac_fuse_enabled() && H % 8 == 0 && (d.latent == 16 || d.latent == 8) &&
+                        (size_t)4 * d.latent * H * sizeof(float) <= 48 * 1024;     // pre_net weights in shared memory
   if (fuse_dec) {
     // ConvTranspose1d(latent -> H, k = 4, s = 4) straight into the fp32 stream AND the operand planes of the first
     // WaveNet convolution (one launch instead of the generic fp32 kernel + a staging pass)
