@@ -20,14 +20,16 @@ timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --cloc
 python tools/agg_launches.py gpurun_out/${TAG}_launches_step.csv > gpurun_out/${TAG}_launches_step_agg.txt 2>&1; head -14 gpurun_out/${TAG}_launches_step_agg.txt
 python tools/prof_vocoder.py --precision 6 --iters 3 --lens 2>&1 | tail -1 | tee gpurun_out/${TAG}_vocoder_times.log
 timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
-  -k regex:"tc_conv|rb_pair" --log-file gpurun_out/${TAG}_vocoder_lens_dram_per_launch.csv python tools/prof_vocoder.py --precision 6 --iters 0 --lens > /dev/null 2>&1
+  -k regex:"tc_conv|rb_pair|rb_block" --log-file gpurun_out/${TAG}_vocoder_lens_dram_per_launch.csv python tools/prof_vocoder.py --precision 6 --iters 0 --lens > /dev/null 2>&1
 python tools/agg_launches.py gpurun_out/${TAG}_vocoder_lens_dram_per_launch.csv ALL > gpurun_out/${TAG}_vocoder_lens_dram_agg.txt 2>&1; head -8 gpurun_out/${TAG}_vocoder_lens_dram_agg.txt
-# full captures: the fused pair kernels (C = 32: launch 5 of its 9 = k 7; C = 64: launch 8 = k 11), a stage-2 k=11 pair-mode
-# convolution and the S2PA stream kernel
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:rb_pair32 -s 4 -c 1 -o gpurun_out/${TAG}_rb_pair32_k7 -f \
+# full captures: the fused pair kernels (C = 32: launch 2 of its 6 = k 7; C = 64: launch 5 = k 11), the two block-fused k = 3
+# ResBlocks, a stage-2 k=11 pair-mode convolution, the fused prior flow and the S2PA stream kernel
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:rb_pair32 -s 1 -c 1 -o gpurun_out/${TAG}_rb_pair32_k7 -f \
   python tools/prof_vocoder.py --precision 6 --iters 0 --lens > /dev/null 2>&1; echo "ncu pair32 rc=$?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:rb_pair64 -s 7 -c 1 -o gpurun_out/${TAG}_rb_pair64_k11 -f \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:rb_pair64 -s 4 -c 1 -o gpurun_out/${TAG}_rb_pair64_k11 -f \
   python tools/prof_vocoder.py --precision 6 --iters 0 --lens > /dev/null 2>&1; echo "ncu pair64 rc=$?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:rb_block -c 2 -o gpurun_out/${TAG}_rb_block -f \
+  python tools/prof_vocoder.py --precision 6 --iters 0 --lens > /dev/null 2>&1; echo "ncu block rc=$?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:tc_conv_kernel -s 27 -c 1 -o gpurun_out/${TAG}_tc_conv_s2_k11 -f \
   python tools/prof_vocoder.py --precision 6 --iters 0 --lens > /dev/null 2>&1; echo "ncu s2 rc=$?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:rb_pair128 -s 0 -c 1 -o gpurun_out/${TAG}_rb_pair128_k3 -f \
