@@ -161,7 +161,6 @@ __global__ void __launch_bounds__(kBThreads, 1) rb_block_kernel(const RbBlockPar
   } else if (warp == 1) {
     // ------------------------------------------------ C = 64: weight producer, one convolution per (tile pair, phase)
     if (!G_::Resident) {
-      griddep_launch();
       int st = 0;
       uint32_t ph_w = 1;
       for (int i0 = 0; i0 < n_it; i0 += 2) {
