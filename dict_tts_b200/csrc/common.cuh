@@ -52,4 +52,19 @@ __device__ __forceinline__ void griddep_launch_if_resident() {
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: set it once per (kernel, device
+// ordinal) -- one process may drive several GPUs (the reference-plugin path).  `done` is the caller's static bit mask;
+// a lost race only repeats the idempotent call.
+template <typename K>
+static inline cudaError_t ensure_max_dyn_smem(K kernel, int bytes, unsigned long long* done) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (__atomic_load_n(done, __ATOMIC_ACQUIRE) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) __atomic_fetch_or(done, bit, __ATOMIC_RELEASE);
+  return e;
+}
+
 }  // namespace dtts

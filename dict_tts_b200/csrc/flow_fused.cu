@@ -448,11 +448,8 @@ cudaError_t launch_flow_fused(const FlowFusedW& w, const FlowFusedParams& p, cud
   // the first and the last tile keep their sequence-edge rows: T <= 128 - halo fits one tile
   k.ntiles = p.T <= kFRows - k.halo ? 1 : 1 + cdiv(p.T - (kFRows - k.halo), k.core);
   const size_t smem = flow_smem_bytes(w.H);
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(flow_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
+  static unsigned long long attr_done = 0;
+  const cudaError_t attr_err = ensure_max_dyn_smem(flow_fused_kernel, 227 * 1024, &attr_done);
   if (attr_err != cudaSuccess) return attr_err;
   if (smem > (size_t)227 * 1024) return cudaErrorInvalidConfiguration;
   cudaLaunchConfig_t cfg{};

@@ -204,11 +204,10 @@ cudaError_t rel_self_attention(const float* q, const float* k, const float* v, c
     const int nrel = rel_k ? 2 * window + 1 : 0;
     const size_t small = ((size_t)3 * dk * T + (size_t)T * (T + 1) + (size_t)2 * nrel * dk) * sizeof(float);
     if (small <= 160 * 1024) {
-      static bool attr_set = false;
-      if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(rel_self_attn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      static unsigned long long attr_done = 0;
+      {
+        const cudaError_t e = ensure_max_dyn_smem(rel_self_attn_small_kernel, 160 * 1024, &attr_done);
         if (e != cudaSuccess) return e;
-        attr_set = true;
       }
       rel_self_attn_small_kernel<<<B * heads, 256, small, s>>>(q, k, v, mask, rel_k, rel_v, rel_k ? window : 0, out, C, T, heads,
                                                                (long)3 * C * T, po);
@@ -540,11 +539,10 @@ cudaError_t ps_word_attention(const float* q, const float* kv, const int64_t* me
   const int nw = 8;
   const size_t tile = ((size_t)H * Tp + (size_t)H * (Tp + 1) + (size_t)H * 64 + (size_t)nw * Tp + Tp) * sizeof(float);
   if (tile <= 200 * 1024) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(ps_word_attn_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    static unsigned long long attr_done = 0;
+    {
+      const cudaError_t e = ensure_max_dyn_smem(ps_word_attn_tile_kernel, 200 * 1024, &attr_done);
       if (e != cudaSuccess) return e;
-      attr_set = true;
     }
     dim3 grid(cdiv(T, 64), B);
     ps_word_attn_tile_kernel<<<grid, nw * 32, tile, s>>>(q, kv, mel2word, ph2word, H, T, Tp, attn, ctx);

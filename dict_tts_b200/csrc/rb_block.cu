@@ -401,13 +401,9 @@ cudaError_t launch_rb_block(RbBlockParams p, cudaStream_t stream) {
   // the last tile stages rows up to q0 - halo - 5 + 266 of the input planes: they must exist
   if (p.a_pad - p.halo - kBMaxDil < 0 || p.a_pad + (p.ntiles - 1) * p.S - p.halo - kBMaxDil + kBRP > p.a_rows)
     return cudaErrorInvalidValue;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(rb_block_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(rb_block_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
+  static unsigned long long done32 = 0, done64 = 0;
+  const cudaError_t attr_err = p.C == 32 ? ensure_max_dyn_smem(rb_block_kernel<32>, 227 * 1024, &done32)
+                                         : ensure_max_dyn_smem(rb_block_kernel<64>, 227 * 1024, &done64);
   if (attr_err != cudaSuccess) return attr_err;
   int dev = 0, sms = 0;
   cudaError_t e = cudaGetDevice(&dev);

@@ -832,13 +832,9 @@ cudaError_t launch_rb_pair(RbPairParams p, cudaStream_t stream) {
   p.a_stages = wide ? pair64_a_stages(p.k, p.dil) : kPairAStages;
   const size_t smem = wide ? pair64_smem_bytes(p.k, p.dil, p.a_stages) : pair_smem_bytes(p.k, p.dil);
   if (smem > (size_t)227 * 1024) return cudaErrorInvalidConfiguration;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(rb_pair32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(rb_pair64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
+  static unsigned long long done32 = 0, done64 = 0;
+  const cudaError_t attr_err = p.C == kPairC ? ensure_max_dyn_smem(rb_pair32_kernel, 227 * 1024, &done32)
+                                             : ensure_max_dyn_smem(rb_pair64_kernel, 227 * 1024, &done64);
   if (attr_err != cudaSuccess) return attr_err;
   int dev = 0, sms = 0;
   cudaError_t e = cudaGetDevice(&dev);

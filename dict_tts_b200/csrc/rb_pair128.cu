@@ -719,11 +719,8 @@ cudaError_t launch_rb_pair128(RbPairParams p, cudaStream_t stream) {
   if (getenv("DTTS_P128_COPYLAT")) p.csize |= 16;       // event 13 becomes the issue -> landed time of one weight copy per tile
   if (getenv("DTTS_P128_NOEPI")) { p.res = nullptr; p.o32 = nullptr; p.o_hi = nullptr; p.accumulate = 0; }   // experiment: no epilogue HBM traffic
 #endif
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(rb_pair128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
+  static unsigned long long attr_done = 0;
+  const cudaError_t attr_err = ensure_max_dyn_smem(rb_pair128_kernel, 227 * 1024, &attr_done);
   if (attr_err != cudaSuccess) return attr_err;
   int dev = 0, sms = 0;
   cudaError_t e = cudaGetDevice(&dev);

@@ -275,11 +275,10 @@ cudaError_t self_attention_planes(const float* q, const float* k, const float* v
   const int dk = C / heads;
   if (!self_attention_planes_fits(C, T, heads) || (po.hi && dk % 8)) return cudaErrorInvalidValue;
   const size_t smem = ((size_t)3 * dk * T + (size_t)T * (T + 1)) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(self_attn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  static unsigned long long attr_done = 0;
+  {
+    const cudaError_t e = ensure_max_dyn_smem(self_attn_small_kernel, 227 * 1024, &attr_done);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   self_attn_small_kernel<<<B * heads, 256, smem, s>>>(q, k, v, mask, out, C, T, heads, (long)3 * C * T, po);
   return cudaGetLastError();
